@@ -1,0 +1,237 @@
+// TEST INFRASTRUCTURE ONLY (oracle/): C-ABI harness around the reference's *own, unmodified*
+// hot-path classes, compiled in place from $CONVOPEQ_REF/src (never copied into this repo).
+// It exists so tests/ and bench.py's cpu_baseline / --impl reference leg can run the real
+// reference algorithm: convo::MKLNonUniformConvolver (src/MKLNonUniformConvolver.{h,cpp}) and
+// EQProcessor::process(block, params, cache) (src/eqprocessor/EQProcessor.Processing.cpp:1019).
+// The product path (convopeq_b200/, include/) never links or loads this file.
+//
+// EQProcessor.Core.cpp needs the real JUCE and is not linked; the four members it would provide
+// (ctor, dtor, getTotalGain, retireBandNodeDeferred) are defined here as the minimum needed to
+// construct the object, and prepareToPlay()'s effect on the fields that process() reads
+// (EQProcessor.Core.cpp:679-826: maxInternalBlockSize, smoothTotalGain, bypassFadeGain,
+// filterState, totalGainTarget) is applied directly.
+#include <algorithm>
+#include <array>
+#include <atomic>
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <optional>
+#include <thread>
+#include <vector>
+#include <functional>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <limits>
+#include <new>
+#include <bit>
+#include <immintrin.h>
+
+#define private public
+#define protected public
+#include "MKLNonUniformConvolver.h"
+#include "eqprocessor/EQProcessor.h"
+#undef private
+#undef protected
+
+// ---- members normally provided by EQProcessor.Core.cpp -----------------------------------
+EQProcessor::EQProcessor()
+{
+    for (auto& b : bandNodeBits) b.store(0, std::memory_order_relaxed);
+}
+EQProcessor::~EQProcessor() {}
+float EQProcessor::getTotalGain() const { return totalGainDbTarget.load(); }
+bool EQProcessor::retireBandNodeDeferred(BandNode* node) noexcept
+{
+    delete node;
+    return true;
+}
+
+extern "C" {
+
+struct cpqref_filter_spec
+{
+    double sample_rate;
+    int hc_mode;   // 0 Sharp, 1 Natural, 2 Soft
+    int lc_mode;   // 0 Natural, 1 Soft
+    int tail_mode; // 0 air absorption, 1 layer tail contouring, 2 bypass
+    int tail_enabled;
+    double tail_start_seconds;
+    double tail_strength;
+    int tail_l1l2_multiplier;
+};
+
+struct cpqref_eq_band
+{
+    float frequency, gain_db, q;
+    int enabled, type, channel_mode;
+};
+
+// ------------------------------------------------------------------ convolver
+void* cpqref_nuc_create(void) { return new (std::nothrow) convo::MKLNonUniformConvolver(); }
+void cpqref_nuc_destroy(void* h) { delete static_cast<convo::MKLNonUniformConvolver*>(h); }
+
+int cpqref_nuc_set_impulse(void* h, const double* ir, int len, int block, double scale, int direct_head,
+                           const cpqref_filter_spec* fs)
+{
+    auto* c = static_cast<convo::MKLNonUniformConvolver*>(h);
+    if (!fs) return c->SetImpulse(ir, len, block, scale, direct_head != 0, nullptr) ? 1 : 0;
+    convo::FilterSpec s;
+    s.sampleRate = fs->sample_rate;
+    s.hcMode = static_cast<convo::HCMode>(fs->hc_mode);
+    s.lcMode = static_cast<convo::LCMode>(fs->lc_mode);
+    s.tailMode = fs->tail_mode;
+    s.tailEnabled = fs->tail_enabled != 0;
+    s.tailStartSeconds = fs->tail_start_seconds;
+    s.tailStrength = fs->tail_strength;
+    s.tailL1L2Multiplier = fs->tail_l1l2_multiplier;
+    return c->SetImpulse(ir, len, block, scale, direct_head != 0, &s) ? 1 : 0;
+}
+
+// The reference call pattern (StereoConvolver::process, ConvolverProcessor.Runtime.cpp:1159-1184):
+// Add(in, n); got = Get(out, n); zero-fill the shortfall.
+void cpqref_nuc_process(void* h, const double* in, double* out, long total, int call)
+{
+    auto* c = static_cast<convo::MKLNonUniformConvolver*>(h);
+    juce::ScopedNoDenormals nd;
+    for (long pos = 0; pos < total; pos += call)
+    {
+        const int n = (int) std::min<long>(call, total - pos);
+        c->Add(in ? in + pos : nullptr, n);
+        const int got = c->Get(out + pos, n);
+        if (got < n) std::memset(out + pos + std::max(got, 0), 0, sizeof(double) * (size_t) (n - std::max(got, 0)));
+    }
+}
+
+void cpqref_nuc_reset(void* h) { static_cast<convo::MKLNonUniformConvolver*>(h)->Reset(); }
+int cpqref_nuc_latency(void* h) { return static_cast<convo::MKLNonUniformConvolver*>(h)->getLatency(); }
+
+// layout[l] = {partSize, numPartsIR, numParts, partsPerCallback, outputDelaySamples, delayLineCapacity, isImmediate, fftSize}
+int cpqref_nuc_layout(void* h, int* layout /*[3][8]*/, double* gains /*[3]*/)
+{
+    auto* c = static_cast<convo::MKLNonUniformConvolver*>(h);
+    for (int l = 0; l < c->m_numActiveLayers; ++l)
+    {
+        const auto& L = c->m_layers[l];
+        int* o = layout + l * 8;
+        o[0] = L.partSize; o[1] = L.numPartsIR; o[2] = L.numParts; o[3] = L.partsPerCallback;
+        o[4] = L.outputDelaySamples; o[5] = L.delayLineCapacity; o[6] = L.isImmediate ? 1 : 0; o[7] = L.fftSize;
+    }
+    for (int l = 0; l < 3; ++l) gains[l] = c->m_tailLayerGain[l];
+    return c->m_numActiveLayers;
+}
+
+// Copy out one layer's stored partition spectrum (reference order = reversed partitions), SoA.
+int cpqref_nuc_ir_spectrum(void* h, int layer, int part, double* re, double* im)
+{
+    auto* c = static_cast<convo::MKLNonUniformConvolver*>(h);
+    if (layer < 0 || layer >= c->m_numActiveLayers) return 0;
+    const auto& L = c->m_layers[layer];
+    if (part < 0 || part >= L.numParts) return 0;
+    std::memcpy(re, L.irFreqReal + (size_t) part * L.complexSize, sizeof(double) * (size_t) L.complexSize);
+    std::memcpy(im, L.irFreqImag + (size_t) part * L.complexSize, sizeof(double) * (size_t) L.complexSize);
+    return L.complexSize;
+}
+
+// ------------------------------------------------------------------ EQ
+struct RefEq
+{
+    EQProcessor proc;
+    convo::EQParameters params;
+    std::unique_ptr<EQCoeffCache> cache;
+    double sr = 48000.0;
+    int maxBlock = 512;
+};
+
+void* cpqref_eq_create(double sr, int max_block, float total_gain_db)
+{
+    auto* e = new (std::nothrow) RefEq();
+    if (!e) return nullptr;
+    e->sr = sr;
+    e->maxBlock = max_block;
+    auto& p = e->proc;
+    // prepareToPlay (EQProcessor.Core.cpp:679-826), the part process() depends on:
+    p.currentSampleRate.store(sr);
+    p.maxInternalBlockSize = max_block;
+    p.smoothTotalGain.totalSteps = convo::LinearRamp::computeTotalSteps(sr, EQProcessor::SMOOTHING_TIME_SEC);
+    p.bypassFadeGain.totalSteps = convo::LinearRamp::computeTotalSteps(sr, EQProcessor::BYPASS_FADE_TIME_SEC);
+    p.totalGainDbTarget.store(total_gain_db);
+    const double lin = juce::Decibels::decibelsToGain<double>(static_cast<double>(total_gain_db));
+    p.totalGainTarget.store(lin);
+    p.smoothTotalGain.current = p.smoothTotalGain.target = lin;
+    p.smoothTotalGain.step = 0.0;
+    p.smoothTotalGain.remaining = 0;
+    p.bypassFadeGain.current = p.bypassFadeGain.target = 1.0;
+    p.bypassFadeGain.step = 0.0;
+    p.bypassFadeGain.remaining = 0;
+    std::memset(p.filterState.data(), 0, sizeof(p.filterState));
+    const int channelRequired = juce::nextPowerOfTwo(max_block) * EQProcessor::MAX_CHANNELS;
+    p.parallelInputBuffer = convo::makeAlignedArray<double>((size_t) channelRequired);
+    p.parallelWorkBuffer = convo::makeAlignedArray<double>((size_t) channelRequired);
+    p.parallelAccumBuffer = convo::makeAlignedArray<double>((size_t) channelRequired);
+    p.parallelBufferCapacity = channelRequired;
+    return e;
+}
+
+void cpqref_eq_destroy(void* h) { delete static_cast<RefEq*>(h); }
+
+int cpqref_eq_set_params(void* h, const cpqref_eq_band* bands /*[20]*/, float saturation, int structure, int agc)
+{
+    auto* e = static_cast<RefEq*>(h);
+    for (int i = 0; i < 20; ++i)
+    {
+        auto& b = e->params.bands[(size_t) i];
+        b.frequency = bands[i].frequency;
+        b.gain = bands[i].gain_db;
+        b.q = bands[i].q;
+        b.enabled = bands[i].enabled != 0;
+        b.type = bands[i].type;
+        b.channelMode = bands[i].channel_mode;
+    }
+    e->params.nonlinearSaturation = saturation;
+    e->params.filterStructure = structure;
+    e->params.agcEnabled = agc != 0;
+    e->cache.reset(EQProcessor::createCoeffCache(e->params, e->sr, e->maxBlock, 1));
+    return e->cache ? 1 : 0;
+}
+
+// setTotalGain (EQProcessor.Parameters.cpp:109 -> storeTotalGainDb): starts the 50 ms ramp at the next process().
+void cpqref_eq_set_total_gain(void* h, float db)
+{
+    auto* e = static_cast<RefEq*>(h);
+    e->proc.totalGainDbTarget.store(db);
+    e->proc.totalGainTarget.store(juce::Decibels::decibelsToGain<double>(static_cast<double>(db)));
+}
+
+void cpqref_eq_process(void* h, double* L, double* R, long total, int block)
+{
+    auto* e = static_cast<RefEq*>(h);
+    for (long pos = 0; pos < total; pos += block)
+    {
+        const int n = (int) std::min<long>(block, total - pos);
+        double* chans[2] = { L + pos, R ? R + pos : nullptr };
+        juce::dsp::AudioBlock<double> blk(chans, R ? 2u : 1u, (size_t) n);
+        e->proc.process(blk, e->params, e->cache.get());
+    }
+}
+
+void cpqref_eq_get_state(void* h, double* out /*[2][20][2]*/)
+{
+    auto* e = static_cast<RefEq*>(h);
+    for (int ch = 0; ch < 2; ++ch)
+        for (int b = 0; b < 20; ++b)
+            for (int k = 0; k < 2; ++k) out[(ch * 20 + b) * 2 + k] = e->proc.filterState[(size_t) ch][(size_t) b][(size_t) k];
+}
+
+void cpqref_eq_design(int type, float f, float g, float q, double sr, double* out /*a1,a2,a3,m0,m1,m2*/)
+{
+    const EQCoeffsSVF c = EQProcessor::calcSVFCoeffs(static_cast<EQBandType>(type), f, g, q, sr);
+    out[0] = c.a1; out[1] = c.a2; out[2] = c.a3; out[3] = c.m0; out[4] = c.m1; out[5] = c.m2;
+}
+
+int cpqref_abi_version(void) { return 1; }
+}
