@@ -1,0 +1,1160 @@
+// cpq_engine.cu -- engine + C ABI (include/cpq.h) over the sm_100a kernels in cpq_kernels.cuh.
+//
+// Offline form of the reference's per-callback chain
+//   convolverRt().process -> eqRt().process(block, params, cache) -> makeup gain -> processOutputDouble
+// (AudioEngine.Processing.DSPCoreDouble.cpp:386-414,465-469,577-663) for a batch of independent streams.
+// There is no CPU path: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/cpq.h"
+#include "cpq_plan.hpp"
+#include "cpq_kernels.cuh"
+
+namespace cpq
+{
+
+#define CPQ_CUDA(expr)                                                                              \
+    do                                                                                              \
+    {                                                                                               \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+        {                                                                                           \
+            setError(std::string(#expr) + ": " + cudaGetErrorString(e_));                           \
+            return e_ == cudaErrorMemoryAllocation ? CPQ_ERR_OOM : CPQ_ERR_CUDA;                    \
+        }                                                                                           \
+    } while (0)
+
+template <typename T>
+struct DevBuf
+{
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+};
+
+struct EqSet
+{
+    cpq_svf_coeffs coeffs[CPQ_NUM_BANDS];
+    uint8_t active[CPQ_NUM_BANDS];
+    int32_t mode[CPQ_NUM_BANDS];
+    double saturation = (double) 0.2f;
+    double totalGain = 1.0;
+    bool set = false;
+    std::vector<GainEvent> events;
+};
+
+struct LayerDev
+{
+    DevBuf<double2> H;      // [nH][Q][M]
+    DevBuf<double2> tw;     // [P+1]
+    DevBuf<double> gain;    // [M] spectrum filter gain (when a FilterSpec is given)
+    DevBuf<double> tilt;    // [M]
+    bool hasGain = false, hasTilt = false;
+    DevBuf<double2> X, Y;   // workspace spectra for a chunk of sequences
+    DevBuf<double> tail;    // [chunk][K*P] (layers >= 1)
+    DevBuf<int64_t> tailSrc;
+    DevBuf<int32_t> blockMap;
+    bool hasBlockMap = false;
+};
+
+struct Engine
+{
+    cpq_config cfg {};
+    int nSeq = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // convolver
+    bool planSet = false;
+    ConvPlan plan;
+    std::vector<uint8_t> haveImpulse;   // per H row
+    int nH = 0;
+    LayerDev layer[CPQ_MAX_LAYERS];
+    GatherPlan gplan;
+    int64_t gplanCallbacks = -1;
+    int partBegin = 0, partEnd = -1;    // partition-range sharding
+    bool outerPending = false;
+
+    // io
+    DevBuf<double> io;
+    DevBuf<double> irScratch;
+
+    // EQ
+    std::vector<EqSet> eqSets;
+    bool eqDirty = true;
+    DevBuf<double> eqc, satDev, gainConst, gainTab, stateOut;
+    DevBuf<unsigned> bandMask;
+    DevBuf<int> setOfSeq;
+    int64_t gainTabCallbacks = -1;
+    bool haveGainTab = false;
+    DevBuf<double> chainRec;
+    DevBuf<unsigned> ticketFault;       // [0] ticket, [1] fault
+    unsigned long long epoch = 0;
+
+    // epilogue
+    double makeup = 1.0;
+    int ditherBits = 0;
+    DevBuf<double> uniforms, ditherZ;
+    int64_t uniformsPerCh = 0;
+
+    // timing
+    cudaEvent_t ev[8] {};
+    cpq_timings timings {};
+    int64_t launches = 0;
+
+    void setError(const std::string& s) { err = s; }
+
+    ~Engine()
+    {
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    int hRowOf(int stream_, int ch) const { return cfg.shared_ir ? ch : stream_ * cfg.n_channels + ch; }
+
+    cpq_status init(const cpq_config* c);
+    cpq_status setImpulse(int stream_, int ch, const double* ir, int len, double scale, const cpq_filter_spec* spec);
+    cpq_status ensureTwiddles(int li);
+    cpq_status uploadEq(int64_t nCallbacks);
+    cpq_status ensureGather(int64_t nCallbacks);
+    cpq_status processDevice(double* dIo, int64_t stride, int64_t T, unsigned stages);
+    cpq_status launchFwd(int log2P, const FwdArgs& a);
+    cpq_status launchInv(int log2P, const InvArgs& a);
+    cpq_status launchEq(EqArgs& a);
+};
+
+// ------------------------------------------------------------------------------------------------
+static bool g_attrDone[16][2] = {};
+
+template <int LOG2P>
+static cudaError_t fwdLaunch(const FwdArgs& a, cudaStream_t s)
+{
+    using C = FftCfg<LOG2P>;
+    if (!g_attrDone[LOG2P][0])
+    {
+        cudaError_t e = cudaFuncSetAttribute(fft_fwd_kernel<LOG2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
+        if (e != cudaSuccess) return e;
+        g_attrDone[LOG2P][0] = true;
+    }
+    const unsigned grid = (unsigned) ((a.totalFrames + C::FPC - 1) / C::FPC);
+    fft_fwd_kernel<LOG2P><<<grid, C::THREADS, C::SMEM, s>>>(a);
+    return cudaGetLastError();
+}
+template <int LOG2P>
+static cudaError_t invLaunch(const InvArgs& a, cudaStream_t s)
+{
+    using C = FftCfg<LOG2P>;
+    if (!g_attrDone[LOG2P][1])
+    {
+        cudaError_t e = cudaFuncSetAttribute(fft_inv_kernel<LOG2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
+        if (e != cudaSuccess) return e;
+        g_attrDone[LOG2P][1] = true;
+    }
+    const unsigned grid = (unsigned) ((a.totalFrames + C::FPC - 1) / C::FPC);
+    fft_inv_kernel<LOG2P><<<grid, C::THREADS, C::SMEM, s>>>(a);
+    return cudaGetLastError();
+}
+
+cpq_status Engine::launchFwd(int log2P, const FwdArgs& a)
+{
+    if (a.totalFrames <= 0) return CPQ_OK;
+    cudaError_t e;
+    switch (log2P)
+    {
+        case 6: e = fwdLaunch<6>(a, stream); break;
+        case 7: e = fwdLaunch<7>(a, stream); break;
+        case 8: e = fwdLaunch<8>(a, stream); break;
+        case 9: e = fwdLaunch<9>(a, stream); break;
+        case 10: e = fwdLaunch<10>(a, stream); break;
+        case 11: e = fwdLaunch<11>(a, stream); break;
+        case 12: e = fwdLaunch<12>(a, stream); break;
+        case 13: e = fwdLaunch<13>(a, stream); break;
+        default: setError("partition size outside 64..8192 is not built yet"); return CPQ_ERR_UNSUPPORTED;
+    }
+    ++launches;
+    CPQ_CUDA(e);
+    return CPQ_OK;
+}
+cpq_status Engine::launchInv(int log2P, const InvArgs& a)
+{
+    if (a.totalFrames <= 0) return CPQ_OK;
+    cudaError_t e;
+    switch (log2P)
+    {
+        case 6: e = invLaunch<6>(a, stream); break;
+        case 7: e = invLaunch<7>(a, stream); break;
+        case 8: e = invLaunch<8>(a, stream); break;
+        case 9: e = invLaunch<9>(a, stream); break;
+        case 10: e = invLaunch<10>(a, stream); break;
+        case 11: e = invLaunch<11>(a, stream); break;
+        case 12: e = invLaunch<12>(a, stream); break;
+        case 13: e = invLaunch<13>(a, stream); break;
+        default: setError("partition size outside 64..8192 is not built yet"); return CPQ_ERR_UNSUPPORTED;
+    }
+    ++launches;
+    CPQ_CUDA(e);
+    return CPQ_OK;
+}
+
+cpq_status Engine::init(const cpq_config* c)
+{
+    cfg = *c;
+    if (cfg.n_streams <= 0 || cfg.n_channels < 1 || cfg.n_channels > 2 || cfg.sample_rate <= 0.0 || cfg.max_samples <= 0)
+    {
+        setError("invalid config");
+        return CPQ_ERR_INVALID;
+    }
+    if (cfg.block_size < 64 || cfg.block_size > 8192 || (cfg.block_size & (cfg.block_size - 1)) != 0)
+    {
+        setError("block_size must be a power of two in 64..8192");
+        return CPQ_ERR_UNSUPPORTED;
+    }
+    if (cfg.max_samples % cfg.block_size != 0)
+    {
+        setError("max_samples must be a multiple of block_size");
+        return CPQ_ERR_INVALID;
+    }
+    if (cfg.workspace_bytes == 0) cfg.workspace_bytes = (size_t) 4 << 30;
+    nSeq = cfg.n_streams * cfg.n_channels;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
+    {
+        cudaGetLastError();
+        setError("no CUDA device: convopeq_b200 has no CPU fallback");
+        return CPQ_ERR_CUDA;
+    }
+    if (cfg.device < 0 || cfg.device >= count)
+    {
+        setError("device ordinal out of range");
+        return CPQ_ERR_INVALID;
+    }
+    CPQ_CUDA(cudaSetDevice(cfg.device));
+    cudaDeviceProp prop {};
+    CPQ_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
+    if (prop.major < 10)
+    {
+        setError("device is not sm_100 class (B200 required)");
+        return CPQ_ERR_CUDA;
+    }
+    CPQ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto& e : ev) CPQ_CUDA(cudaEventCreate(&e));
+    nH = cfg.shared_ir ? cfg.n_channels : nSeq;
+    haveImpulse.assign((size_t) nH, 0);
+    eqSets.assign((size_t) (cfg.shared_eq ? 1 : cfg.n_streams), EqSet {});
+    CPQ_CUDA(ticketFault.ensure(2));
+    CPQ_CUDA(cudaMemsetAsync(ticketFault.p, 0, 2 * sizeof(unsigned), stream));
+    CPQ_CUDA(ditherZ.ensure((size_t) nSeq * 12));
+    CPQ_CUDA(cudaMemsetAsync(ditherZ.p, 0, (size_t) nSeq * 12 * sizeof(double), stream));
+    CPQ_CUDA(stateOut.ensure((size_t) nSeq * CPQ_NUM_BANDS * 2));
+    CPQ_CUDA(cudaMemsetAsync(stateOut.p, 0, (size_t) nSeq * CPQ_NUM_BANDS * 2 * sizeof(double), stream));
+    CPQ_CUDA(cudaStreamSynchronize(stream));
+    return CPQ_OK;
+}
+
+cpq_status Engine::ensureTwiddles(int li)
+{
+    LayerDev& L = layer[li];
+    const int P = plan.layers[li].partSize;
+    if (L.tw.p && L.tw.n == (size_t) P + 1) return CPQ_OK;
+    std::vector<double2> tw((size_t) P + 1);
+    const long double twoPiOverN = 2.0L * 3.141592653589793238462643383279502884L / (long double) (2 * P);
+    for (int t = 0; t <= P; ++t)
+    {
+        // octant symmetry keeps the table exact at the special angles
+        long double c, s;
+        if (t == 0) { c = 1.0L; s = 0.0L; }
+        else if (t == P) { c = -1.0L; s = 0.0L; }
+        else if (2 * t == P) { c = 0.0L; s = 1.0L; }
+        else { c = cosl(twoPiOverN * t); s = sinl(twoPiOverN * t); }
+        tw[(size_t) t] = make_double2((double) c, (double) -s);
+    }
+    CPQ_CUDA(L.tw.ensure((size_t) P + 1));
+    CPQ_CUDA(cudaMemcpyAsync(L.tw.p, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
+    CPQ_CUDA(cudaStreamSynchronize(stream));
+    return CPQ_OK;
+}
+
+cpq_status Engine::setImpulse(int stream_, int ch, const double* ir, int len, double scale, const cpq_filter_spec* spec)
+{
+    if (!ir || len <= 0 || ch < 0 || ch >= cfg.n_channels)
+    {
+        setError("set_impulse: bad argument");
+        return CPQ_ERR_INVALID;
+    }
+    if (cfg.shared_ir ? (stream_ != -1 && stream_ != 0) : (stream_ < 0 || stream_ >= cfg.n_streams))
+    {
+        setError("set_impulse: stream out of range");
+        return CPQ_ERR_INVALID;
+    }
+    ConvPlan p;
+    if (!makeConvPlan(len, cfg.block_size, spec, p))
+    {
+        setError("set_impulse: SetImpulse would reject these parameters");
+        return CPQ_ERR_INVALID;
+    }
+    for (int li = 0; li < p.numLayers; ++li)
+        if (p.layers[li].partSize > 8192)
+        {
+            setError("set_impulse: layer partition > 8192 (FFT > 16384) is not built yet");
+            return CPQ_ERR_UNSUPPORTED;
+        }
+    if (planSet && !plan.sameGeometry(p))
+    {
+        setError("set_impulse: every stream-channel of a handle must share the layer geometry");
+        return CPQ_ERR_GEOMETRY;
+    }
+    CPQ_CUDA(cudaSetDevice(cfg.device));
+    const bool first = !planSet;
+    if (first)
+    {
+        plan = p;
+        planSet = true;
+        gplanCallbacks = -1;
+        for (int li = 0; li < plan.numLayers; ++li)
+        {
+            const LayerPlan& l = plan.layers[li];
+            cpq_status st = ensureTwiddles(li);
+            if (st != CPQ_OK) return st;
+            CPQ_CUDA(layer[li].H.ensure((size_t) nH * l.numPartsIR * l.bins));
+            CPQ_CUDA(cudaMemsetAsync(layer[li].H.p, 0, (size_t) nH * l.numPartsIR * l.bins * sizeof(double2), stream));
+        }
+    }
+    // Per-bin gains depend on the FilterSpec, which may differ between channels only in ways that keep the
+    // geometry; rebuild them for this call.
+    const int row = hRowOf(stream_ < 0 ? 0 : stream_, ch);
+    CPQ_CUDA(irScratch.ensure((size_t) len + 2));
+    CPQ_CUDA(cudaMemcpyAsync(irScratch.p, ir, (size_t) len * sizeof(double), cudaMemcpyHostToDevice, stream));
+    for (int li = 0; li < p.numLayers; ++li)
+    {
+        const LayerPlan& l = p.layers[li];
+        LayerDev& L = layer[li];
+        std::vector<double> g, t;
+        const double* dGain = nullptr;
+        const double* dTilt = nullptr;
+        if (p.hasSpec)
+        {
+            spectrumGain(p, li, g);
+            CPQ_CUDA(L.gain.ensure(g.size()));
+            CPQ_CUDA(cudaMemcpyAsync(L.gain.p, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+            dGain = L.gain.p;
+        }
+        if (tiltGain(p, li, t))
+        {
+            CPQ_CUDA(L.tilt.ensure(t.size()));
+            CPQ_CUDA(cudaMemcpyAsync(L.tilt.p, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+            dTilt = L.tilt.p;
+        }
+        FwdArgs a {};
+        a.src = irScratch.p;
+        a.srcStride = 0;
+        a.frameStart0 = l.irOffset;
+        a.lo = l.irOffset;
+        a.hi = (int64_t) l.irOffset + l.irLen;
+        a.halfOnly = 1;
+        a.framesPerSeq = l.numPartsIR;
+        a.totalFrames = l.numPartsIR;
+        a.out = L.H.p + (size_t) row * l.numPartsIR * l.bins;
+        a.outFramesPerSeq = l.numPartsIR;
+        a.outFrameOffset = 0;
+        a.tw = L.tw.p;
+        a.scale = scale;
+        a.applyScale = std::fabs(scale - 1.0) > 1e-12 ? 1 : 0;
+        a.gain = dGain;
+        a.tilt = dTilt;
+        cpq_status st = launchFwd(ilog2(l.partSize), a);
+        if (st != CPQ_OK) return st;
+        // the host vectors g/t must outlive the async copies
+        CPQ_CUDA(cudaStreamSynchronize(stream));
+    }
+    haveImpulse[(size_t) row] = 1;
+    return CPQ_OK;
+}
+
+static void matmul2(const long double* a, const long double* b, long double* c)
+{
+    long double r[4] = { a[0] * b[0] + a[1] * b[2], a[0] * b[1] + a[1] * b[3], a[2] * b[0] + a[3] * b[2], a[2] * b[1] + a[3] * b[3] };
+    for (int i = 0; i < 4; ++i) c[i] = r[i];
+}
+
+static void buildBandConstants(const cpq_svf_coeffs& c, double* out /* kEqcStride */)
+{
+    std::memset(out, 0, sizeof(double) * kEqcStride);
+    out[0] = c.a1; out[1] = c.a2; out[2] = c.a3; out[3] = c.m0; out[4] = c.m1; out[5] = c.m2;
+    // s' = A s + b v0   (EQProcessor.Processing.cpp:148-153 in affine form)
+    const long double A[4] = { 2.0L * c.a1 - 1.0L, -2.0L * c.a2, 2.0L * c.a2, 1.0L - 2.0L * c.a3 };
+    const long double b[2] = { 2.0L * c.a2, 2.0L * c.a3 };
+    // w[j] = A^(15-j) b
+    long double v[2] = { b[0], b[1] };
+    for (int j = kEqL - 1; j >= 0; --j)
+    {
+        out[kEqcW + 2 * j] = (double) v[0];
+        out[kEqcW + 2 * j + 1] = (double) v[1];
+        const long double n0 = A[0] * v[0] + A[1] * v[1], n1 = A[2] * v[0] + A[3] * v[1];
+        v[0] = n0; v[1] = n1;
+    }
+    long double A16[4] = { 1, 0, 0, 1 };
+    for (int i = 0; i < kEqL; ++i) matmul2(A16, A, A16);
+    long double Tl[4] = { 1, 0, 0, 1 };
+    for (int lane = 0; lane < 32; ++lane)
+    {
+        for (int i = 0; i < 4; ++i) out[kEqcTl + 4 * lane + i] = (double) Tl[i];
+        matmul2(Tl, A16, Tl);
+    }
+    long double M[4] = { A16[0], A16[1], A16[2], A16[3] };
+    for (int d = 0; d < 5; ++d)
+    {
+        for (int i = 0; i < 4; ++i) out[kEqcMs + 4 * d + i] = (double) M[i];
+        matmul2(M, M, M);
+    }
+    // M is now A^(16*32) = A^512
+    for (int i = 0; i < 4; ++i) out[kEqcMw + i] = (double) M[i];
+    for (int d = 0; d < 3; ++d) matmul2(M, M, M);   // ^8 -> A^4096
+    for (int i = 0; i < 4; ++i) out[kEqcMt + i] = (double) M[i];
+}
+
+cpq_status Engine::uploadEq(int64_t nCallbacks)
+{
+    const size_t nSets = eqSets.size();
+    if (eqDirty)
+    {
+        std::vector<double> host(nSets * CPQ_NUM_BANDS * kEqcStride);
+        std::vector<double> sat(nSets), gc(nSets);
+        for (size_t s = 0; s < nSets; ++s)
+        {
+            if (!eqSets[s].set)
+            {
+                setError("process: EQ stage requested but cpq_set_eq was not called for every stream");
+                return CPQ_ERR_NOT_READY;
+            }
+            for (int b = 0; b < CPQ_NUM_BANDS; ++b)
+                buildBandConstants(eqSets[s].coeffs[b], host.data() + (s * CPQ_NUM_BANDS + b) * kEqcStride);
+            sat[s] = eqSets[s].saturation;
+            gc[s] = eqSets[s].totalGain;
+        }
+        std::vector<unsigned> mask((size_t) nSeq);
+        std::vector<int> sos((size_t) nSeq);
+        for (int q = 0; q < nSeq; ++q)
+        {
+            const int st = q / cfg.n_channels, ch = q % cfg.n_channels;
+            const EqSet& e = eqSets[cfg.shared_eq ? 0 : (size_t) st];
+            unsigned m = 0;
+            for (int b = 0; b < CPQ_NUM_BANDS; ++b)
+            {
+                if (!e.active[b]) continue;
+                const int mode = e.mode[b];
+                // Processing.cpp:1239-1252: Stereo -> both; Left -> ch 0; Right -> ch 1
+                const bool on = (mode == 0) || (mode == 1 && ch == 0) || (mode == 2 && ch == 1);
+                if (on) m |= 1u << b;
+            }
+            mask[(size_t) q] = m;
+            sos[(size_t) q] = cfg.shared_eq ? 0 : st;
+        }
+        CPQ_CUDA(eqc.ensure(host.size()));
+        CPQ_CUDA(satDev.ensure(nSets));
+        CPQ_CUDA(gainConst.ensure(nSets));
+        CPQ_CUDA(bandMask.ensure((size_t) nSeq));
+        CPQ_CUDA(setOfSeq.ensure((size_t) nSeq));
+        CPQ_CUDA(cudaMemcpyAsync(eqc.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CPQ_CUDA(cudaMemcpyAsync(satDev.p, sat.data(), nSets * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CPQ_CUDA(cudaMemcpyAsync(gainConst.p, gc.data(), nSets * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CPQ_CUDA(cudaMemcpyAsync(bandMask.p, mask.data(), mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice, stream));
+        CPQ_CUDA(cudaMemcpyAsync(setOfSeq.p, sos.data(), sos.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        CPQ_CUDA(cudaStreamSynchronize(stream));
+        eqDirty = false;
+        gainTabCallbacks = -1;
+    }
+    bool anyEvents = false;
+    for (auto& e : eqSets) anyEvents |= !e.events.empty();
+    haveGainTab = anyEvents;
+    if (anyEvents && gainTabCallbacks != nCallbacks)
+    {
+        std::vector<double> tab(nSets * (size_t) nCallbacks * 2), one;
+        const int steps = std::max(1, (int) (cfg.sample_rate * 0.05 + 0.5));   // SMOOTHING_TIME_SEC, computeTotalSteps
+        for (size_t s = 0; s < nSets; ++s)
+        {
+            gainRampTable(eqSets[s].totalGain, steps, cfg.block_size, nCallbacks, eqSets[s].events, one);
+            std::memcpy(tab.data() + s * (size_t) nCallbacks * 2, one.data(), one.size() * sizeof(double));
+        }
+        CPQ_CUDA(gainTab.ensure(tab.size()));
+        CPQ_CUDA(cudaMemcpyAsync(gainTab.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CPQ_CUDA(cudaStreamSynchronize(stream));
+        gainTabCallbacks = nCallbacks;
+    }
+    return CPQ_OK;
+}
+
+cpq_status Engine::ensureGather(int64_t nCallbacks)
+{
+    if (gplanCallbacks == nCallbacks) return CPQ_OK;
+    simulateCallbacks(plan, nCallbacks, gplan);
+    for (int li = 1; li < plan.numLayers; ++li)
+    {
+        LayerDev& L = layer[li];
+        CPQ_CUDA(L.tailSrc.ensure((size_t) nCallbacks));
+        CPQ_CUDA(cudaMemcpyAsync(L.tailSrc.p, gplan.tailSrc[li].data(), (size_t) nCallbacks * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+        L.hasBlockMap = !gplan.blockIdentity[li];
+        if (L.hasBlockMap)
+        {
+            CPQ_CUDA(L.blockMap.ensure(gplan.blockOfStream[li].size()));
+            CPQ_CUDA(cudaMemcpyAsync(L.blockMap.p, gplan.blockOfStream[li].data(), gplan.blockOfStream[li].size() * sizeof(int32_t),
+                                     cudaMemcpyHostToDevice, stream));
+        }
+    }
+    CPQ_CUDA(cudaStreamSynchronize(stream));
+    gplanCallbacks = nCallbacks;
+    return CPQ_OK;
+}
+
+cpq_status Engine::launchEq(EqArgs& a)
+{
+    a.nTiles = (int) ((a.T + kEqTile - 1) / kEqTile);
+    // one CTA per sequence when the batch alone fills the GPU, else one CTA per tile chained through
+    // (sequence, run, band) records
+    const bool wide = a.nSeq >= 888;   // 148 SMs x 3 resident CTAs x 2
+    a.tilesPerRun = (wide || !a.doEq) ? (a.doEq ? a.nTiles : 1) : 1;
+    a.nRuns = (a.nTiles + a.tilesPerRun - 1) / a.tilesPerRun;
+    ++epoch;
+    a.chain.epoch = epoch;
+    a.chain.ticket = ticketFault.p;
+    a.fault = ticketFault.p + 1;
+    if (a.doEq && a.tilesPerRun == 1 && a.nRuns > 1)
+    {
+        CPQ_CUDA(chainRec.ensure((size_t) a.nSeq * a.nRuns * CPQ_NUM_BANDS * 4));
+        if (epoch == 1 || chainRec.n == 0) {}
+    }
+    a.chain.rec = chainRec.p;
+    CPQ_CUDA(cudaMemsetAsync(ticketFault.p, 0, sizeof(unsigned), stream));
+    const unsigned grid = (unsigned) a.nSeq * (unsigned) a.nRuns;
+    eq_kernel<<<grid, kEqThreads, 0, stream>>>(a);
+    ++launches;
+    CPQ_CUDA(cudaGetLastError());
+    return CPQ_OK;
+}
+
+cpq_status Engine::processDevice(double* dIo, int64_t stride, int64_t T, unsigned stages)
+{
+    if (!dIo || T <= 0 || T > cfg.max_samples || T % cfg.block_size != 0 || stride < T || (stride & 1))
+    {
+        setError("process: T must be a positive multiple of block_size <= max_samples; stride even and >= T");
+        return CPQ_ERR_INVALID;
+    }
+    if ((stages & ~CPQ_STAGE_ALL) || stages == 0)
+    {
+        setError("process: bad stage mask");
+        return CPQ_ERR_INVALID;
+    }
+    CPQ_CUDA(cudaSetDevice(cfg.device));
+    const int B = cfg.block_size;
+    const int64_t nCallbacks = T / B;
+    const bool doConv = stages & CPQ_STAGE_CONV, doEq = stages & CPQ_STAGE_EQ, doEpi = stages & CPQ_STAGE_EPILOGUE;
+    const int launches0 = (int) launches;
+    timings = cpq_timings {};
+
+    if (doConv)
+    {
+        if (!planSet)
+        {
+            setError("process: no impulse set");
+            return CPQ_ERR_NOT_READY;
+        }
+        for (int r = 0; r < nH; ++r)
+            if (!haveImpulse[(size_t) r])
+            {
+                setError("process: cpq_set_impulse was not called for every stream-channel");
+                return CPQ_ERR_NOT_READY;
+            }
+        cpq_status st = ensureGather(nCallbacks);
+        if (st != CPQ_OK) return st;
+    }
+    if (doEq)
+    {
+        cpq_status st = uploadEq(nCallbacks);
+        if (st != CPQ_OK) return st;
+    }
+    if (doEpi && ditherBits > 0 && uniformsPerCh < T)
+    {
+        setError("process: dither enabled but cpq_set_dither_uniforms holds fewer than T samples per channel");
+        return CPQ_ERR_NOT_READY;
+    }
+
+    // partition range -> per-layer [qBegin, qEnd)
+    int qb[CPQ_MAX_LAYERS] = {}, qe[CPQ_MAX_LAYERS] = {};
+    bool fullRange = true;
+    if (doConv)
+    {
+        int total = 0;
+        for (int li = 0; li < plan.numLayers; ++li) total += plan.layers[li].numPartsIR;
+        const int pb = std::max(0, partBegin), pe = partEnd < 0 ? total : std::min(partEnd, total);
+        fullRange = (pb == 0 && pe == total);
+        int base = 0;
+        for (int li = 0; li < plan.numLayers; ++li)
+        {
+            const int Q = plan.layers[li].numPartsIR;
+            qb[li] = clampv(0, Q, pb - base);
+            qe[li] = clampv(0, Q, pe - base);
+            base += Q;
+        }
+    }
+
+    cudaEventRecord(ev[0], stream);
+    float fwdMs = 0.f, macMs = 0.f, invMs = 0.f, eqMs = 0.f;
+
+    auto fillEqCommon = [&](EqArgs& a) {
+        a.blockSize = B;
+        a.T = T;
+        a.ioStride = stride;
+        a.doEq = doEq ? 1 : 0;
+        a.eqc = eqc.p;
+        a.sat = satDev.p;
+        a.gainTab = (doEq && haveGainTab) ? gainTab.p : nullptr;
+        a.gainConst = gainConst.p;
+        a.nCallbacks = nCallbacks;
+        a.doEpilogue = doEpi ? 1 : 0;
+        a.makeup = makeup;
+        a.applyHeadroom = (doEpi && ditherBits <= 0) ? 1 : 0;
+        a.wetGain = equalPowerSin(1.0) * 1.0;   // CONVOLUTION_HEADROOM_GAIN = 1.0 (ConvolverProcessor.h:209)
+    };
+
+    if (doConv)
+    {
+        // bytes of workspace per sequence
+        size_t perSeq = 0;
+        int64_t K[CPQ_MAX_LAYERS] = {};
+        for (int li = 0; li < plan.numLayers; ++li)
+        {
+            const LayerPlan& l = plan.layers[li];
+            K[li] = gplan.framesNeeded[li];
+            perSeq += (size_t) K[li] * l.bins * sizeof(double2) * 2;
+            if (li > 0) perSeq += (size_t) K[li] * l.partSize * sizeof(double);
+        }
+        int chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) nSeq, cfg.workspace_bytes / std::max<size_t>(perSeq, 1)));
+        for (int li = 0; li < plan.numLayers; ++li)
+        {
+            const LayerPlan& l = plan.layers[li];
+            CPQ_CUDA(layer[li].X.ensure((size_t) chunk * K[li] * l.bins));
+            CPQ_CUDA(layer[li].Y.ensure((size_t) chunk * K[li] * l.bins));
+            if (li > 0) CPQ_CUDA(layer[li].tail.ensure((size_t) chunk * K[li] * l.partSize + 2));
+        }
+        for (int s0 = 0; s0 < nSeq; s0 += chunk)
+        {
+            const int ns = std::min(chunk, nSeq - s0);
+            double* ioC = dIo + (size_t) s0 * stride;
+            // ---- forward FFTs of every layer (all read the untouched input) ----
+            cudaEventRecord(ev[1], stream);
+            for (int li = 0; li < plan.numLayers; ++li)
+            {
+                const LayerPlan& l = plan.layers[li];
+                if (K[li] == 0 || qb[li] >= qe[li]) continue;
+                FwdArgs a {};
+                a.src = ioC;
+                a.srcStride = stride;
+                a.frameStart0 = -(int64_t) l.partSize;
+                a.lo = 0;
+                a.hi = T;
+                a.halfOnly = 0;
+                a.framesPerSeq = (int) K[li];
+                a.totalFrames = (int64_t) ns * K[li];
+                a.out = layer[li].X.p;
+                a.outFramesPerSeq = (int) K[li];
+                a.outFrameOffset = 0;
+                a.tw = layer[li].tw.p;
+                a.scale = 1.0;
+                cpq_status st = launchFwd(ilog2(l.partSize), a);
+                if (st != CPQ_OK) return st;
+            }
+            cudaEventRecord(ev[2], stream);
+            // ---- MAC ----
+            for (int li = 0; li < plan.numLayers; ++li)
+            {
+                const LayerPlan& l = plan.layers[li];
+                if (K[li] == 0) continue;
+                if (qb[li] >= qe[li])
+                {
+                    // this rank holds no partition of the layer: its contribution is zero
+                    if (li == 0) CPQ_CUDA(cudaMemset2DAsync(ioC, (size_t) stride * sizeof(double), 0, (size_t) T * sizeof(double), (size_t) ns, stream));
+                    else CPQ_CUDA(cudaMemsetAsync(layer[li].tail.p, 0, (size_t) ns * K[li] * l.partSize * sizeof(double), stream));
+                    continue;
+                }
+                MacArgs a {};
+                a.X = layer[li].X.p;
+                a.H = layer[li].H.p;
+                a.Y = layer[li].Y.p;
+                a.K = (int) K[li];
+                a.M = l.bins;
+                a.Q = l.numPartsIR;
+                a.qBegin = qb[li];
+                a.qEnd = qe[li];
+                a.hSeqStride = (int64_t) l.numPartsIR * l.bins;
+                a.hSeqMod = cfg.shared_ir ? cfg.n_channels : 0;
+                // H rows are absolute sequence indices when not shared
+                if (!cfg.shared_ir) a.H += (size_t) s0 * a.hSeqStride;
+                constexpr int KT = 8, QT = 4;
+                dim3 grid((unsigned) ((l.bins + 127) / 128), (unsigned) ((K[li] + KT - 1) / KT), (unsigned) ns);
+                mac_kernel<KT, QT><<<grid, 128, 0, stream>>>(a);
+                ++launches;
+                CPQ_CUDA(cudaGetLastError());
+            }
+            cudaEventRecord(ev[3], stream);
+            // ---- inverse FFTs: L0 in place into io, tails into their stream buffers ----
+            for (int li = 0; li < plan.numLayers; ++li)
+            {
+                const LayerPlan& l = plan.layers[li];
+                if (K[li] == 0 || qb[li] >= qe[li]) continue;
+                InvArgs a {};
+                a.in = layer[li].Y.p;
+                a.framesPerSeq = (int) K[li];
+                a.framesOut = (int) K[li];
+                a.totalFrames = (int64_t) ns * K[li];
+                a.out = li == 0 ? ioC : layer[li].tail.p;
+                a.outStride = li == 0 ? stride : (int64_t) K[li] * l.partSize;
+                a.tw = layer[li].tw.p;
+                cpq_status st = launchInv(ilog2(l.partSize), a);
+                if (st != CPQ_OK) return st;
+            }
+            cudaEventRecord(ev[4], stream);
+            // ---- assembly + EQ + epilogue for this chunk ----
+            EqArgs e {};
+            fillEqCommon(e);
+            e.io = ioC;
+            e.nSeq = ns;
+            e.assemble = 1;
+            e.nTail = plan.numLayers - 1;
+            for (int li = 1; li < plan.numLayers; ++li)
+            {
+                e.tail[li - 1] = layer[li].tail.p;
+                e.tailStride[li - 1] = (int64_t) K[li] * plan.layers[li].partSize;
+                e.tailSrc[li - 1] = layer[li].tailSrc.p;
+                e.blockMap[li - 1] = layer[li].hasBlockMap ? layer[li].blockMap.p : nullptr;
+                e.tailPart[li - 1] = plan.layers[li].partSize;
+                e.tailGain[li - 1] = plan.layers[li].gain;
+            }
+            e.outer = (cfg.conv_boundary == CPQ_CONV_OUTER && fullRange) ? 1 : 0;
+            e.bandMask = bandMask.p ? bandMask.p + s0 : nullptr;
+            e.setOfSeq = setOfSeq.p ? setOfSeq.p + s0 : nullptr;
+            e.stateOut = stateOut.p + (size_t) s0 * CPQ_NUM_BANDS * 2;
+            if (!cfg.shared_eq && e.setOfSeq)
+            {
+                // setOfSeq holds absolute set indices; eqc/sat/gain tables are indexed absolutely too
+            }
+            cpq_status st = launchEq(e);
+            if (st != CPQ_OK) return st;
+            cudaEventRecord(ev[5], stream);
+            CPQ_CUDA(cudaEventSynchronize(ev[5]));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[1], ev[2]); fwdMs += ms;
+            cudaEventElapsedTime(&ms, ev[2], ev[3]); macMs += ms;
+            cudaEventElapsedTime(&ms, ev[3], ev[4]); invMs += ms;
+            cudaEventElapsedTime(&ms, ev[4], ev[5]); eqMs += ms;
+        }
+        outerPending = (cfg.conv_boundary == CPQ_CONV_OUTER && !fullRange);
+    }
+    else
+    {
+        EqArgs e {};
+        fillEqCommon(e);
+        e.io = dIo;
+        e.nSeq = nSeq;
+        e.assemble = outerPending ? 1 : 0;   // no tails; only the deferred outer-boundary scrub + wet gain
+        e.nTail = 0;
+        e.outer = outerPending ? 1 : 0;
+        outerPending = false;
+        e.bandMask = bandMask.p;
+        e.setOfSeq = setOfSeq.p;
+        e.stateOut = stateOut.p;
+        cudaEventRecord(ev[4], stream);
+        cpq_status st = launchEq(e);
+        if (st != CPQ_OK) return st;
+        cudaEventRecord(ev[5], stream);
+        CPQ_CUDA(cudaEventSynchronize(ev[5]));
+        cudaEventElapsedTime(&eqMs, ev[4], ev[5]);
+    }
+
+    if (doEpi && ditherBits > 0)
+    {
+        DitherArgs d {};
+        d.io = dIo;
+        d.ioStride = stride;
+        d.T = T;
+        d.nSeq = nSeq;
+        d.uniforms = uniforms.p;
+        ditherCoeffs(cfg.sample_rate, ditherBits, d.coeff);
+        d.scale = 1.0 / std::pow(2.0, ditherBits - 1);
+        d.invScale = std::pow(2.0, ditherBits - 1);
+        d.z = ditherZ.p;
+        if (uniformsPerCh != T)
+        {
+            setError("process: dither uniforms must be laid out for exactly T samples per channel");
+            return CPQ_ERR_INVALID;
+        }
+        dither_kernel<<<(unsigned) ((nSeq + 31) / 32), 32, 0, stream>>>(d);
+        ++launches;
+        CPQ_CUDA(cudaGetLastError());
+    }
+    cudaEventRecord(ev[6], stream);
+    CPQ_CUDA(cudaEventSynchronize(ev[6]));
+    unsigned tf[2] = {};
+    CPQ_CUDA(cudaMemcpy(tf, ticketFault.p, sizeof(tf), cudaMemcpyDeviceToHost));
+    cudaEventElapsedTime(&timings.total_ms, ev[0], ev[6]);
+    timings.fft_fwd_ms = fwdMs;
+    timings.mac_ms = macMs;
+    timings.fft_inv_ms = invMs;
+    timings.eq_ms = eqMs;
+    timings.kernel_launches = (int) launches - launches0;
+    if (tf[1] != 0)
+    {
+        CPQ_CUDA(cudaMemset(ticketFault.p + 1, 0, sizeof(unsigned)));
+        setError("EQ filter state became non-finite or exceeded 1e15: the reference resets the state there "
+                 "(EQProcessor.Processing.cpp:174-175), which the blocked scan does not reproduce");
+        return CPQ_ERR_UNSUPPORTED;
+    }
+    return CPQ_OK;
+}
+
+} // namespace cpq
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using cpq::Engine;
+struct cpq_engine : Engine {};
+
+extern "C" {
+
+int cpq_abi_version(void) { return CPQ_ABI_VERSION; }
+
+const char* cpq_status_string(cpq_status s)
+{
+    switch (s)
+    {
+        case CPQ_OK: return "ok";
+        case CPQ_ERR_INVALID: return "invalid argument";
+        case CPQ_ERR_NOT_READY: return "not ready";
+        case CPQ_ERR_CUDA: return "CUDA error / no device";
+        case CPQ_ERR_OOM: return "out of memory";
+        case CPQ_ERR_UNSUPPORTED: return "unsupported";
+        case CPQ_ERR_GEOMETRY: return "layer geometry mismatch";
+    }
+    return "?";
+}
+
+static thread_local std::string g_createError;
+
+const char* cpq_last_error(cpq_handle h) { return h ? h->err.c_str() : g_createError.c_str(); }
+
+void cpq_filter_spec_default(cpq_filter_spec* out)
+{
+    if (out) cpq::filterSpecDefault(out);
+}
+
+void cpq_config_default(cpq_config* out)
+{
+    if (!out) return;
+    std::memset(out, 0, sizeof(*out));
+    out->device = 0;
+    out->n_streams = 1;
+    out->n_channels = 2;
+    out->block_size = 512;
+    out->sample_rate = 48000.0;
+    out->max_samples = 48000 * 10 / 512 * 512;
+    out->conv_boundary = CPQ_CONV_INNER;
+    out->workspace_bytes = 0;
+}
+
+cpq_status cpq_create(const cpq_config* cfg, cpq_handle* out)
+{
+    if (!cfg || !out) return CPQ_ERR_INVALID;
+    *out = nullptr;
+    auto* e = new (std::nothrow) cpq_engine();
+    if (!e) return CPQ_ERR_OOM;
+    cpq_status st = e->init(cfg);
+    if (st != CPQ_OK)
+    {
+        g_createError = e->err;
+        delete e;
+        return st;
+    }
+    *out = e;
+    return CPQ_OK;
+}
+
+void cpq_destroy(cpq_handle h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    delete h;
+}
+
+cpq_status cpq_reset(cpq_handle h)
+{
+    if (!h) return CPQ_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    cudaMemsetAsync(h->ditherZ.p, 0, (size_t) h->nSeq * 12 * sizeof(double), h->stream);
+    cudaMemsetAsync(h->stateOut.p, 0, (size_t) h->nSeq * CPQ_NUM_BANDS * 2 * sizeof(double), h->stream);
+    cudaStreamSynchronize(h->stream);
+    h->outerPending = false;
+    for (auto& e : h->eqSets) e.events.clear();
+    h->gainTabCallbacks = -1;
+    return CPQ_OK;
+}
+
+cpq_status cpq_set_impulse(cpq_handle h, int stream, int channel, const double* ir, int ir_len, double scale,
+                           const cpq_filter_spec* spec)
+{
+    if (!h) return CPQ_ERR_INVALID;
+    return h->setImpulse(stream, channel, ir, ir_len, scale, spec);
+}
+
+cpq_status cpq_set_eq(cpq_handle h, int stream, const cpq_svf_coeffs coeffs[CPQ_NUM_BANDS],
+                      const uint8_t active[CPQ_NUM_BANDS], const int32_t chan_mode[CPQ_NUM_BANDS],
+                      double saturation, double total_gain_lin)
+{
+    if (!h || !coeffs || !active || !chan_mode) return CPQ_ERR_INVALID;
+    if (h->cfg.shared_eq ? (stream != -1 && stream != 0) : (stream < 0 || stream >= h->cfg.n_streams))
+    {
+        h->setError("set_eq: stream out of range");
+        return CPQ_ERR_INVALID;
+    }
+    for (int b = 0; b < CPQ_NUM_BANDS; ++b)
+    {
+        if (active[b] && chan_mode[b] >= 3)
+        {
+            h->setError("set_eq: Mid/Side channel modes take the reference's other process() path (Processing.cpp:1037-1044)");
+            return CPQ_ERR_UNSUPPORTED;
+        }
+        if (active[b] && chan_mode[b] < 0) return CPQ_ERR_INVALID;
+    }
+    if (!(saturation >= 0.0) || !std::isfinite(total_gain_lin)) return CPQ_ERR_INVALID;
+    cpq::EqSet& e = h->eqSets[h->cfg.shared_eq ? 0 : (size_t) stream];
+    std::memcpy(e.coeffs, coeffs, sizeof(e.coeffs));
+    std::memcpy(e.active, active, sizeof(e.active));
+    std::memcpy(e.mode, chan_mode, sizeof(e.mode));
+    e.saturation = saturation;
+    e.totalGain = total_gain_lin;
+    e.set = true;
+    e.events.clear();
+    h->eqDirty = true;
+    return CPQ_OK;
+}
+
+cpq_status cpq_schedule_total_gain(cpq_handle h, int stream, int64_t at_callback, double new_gain_lin)
+{
+    if (!h || at_callback < 0 || !std::isfinite(new_gain_lin)) return CPQ_ERR_INVALID;
+    if (h->cfg.shared_eq ? (stream != -1 && stream != 0) : (stream < 0 || stream >= h->cfg.n_streams)) return CPQ_ERR_INVALID;
+    cpq::EqSet& e = h->eqSets[h->cfg.shared_eq ? 0 : (size_t) stream];
+    e.events.push_back({ at_callback, new_gain_lin });
+    h->gainTabCallbacks = -1;
+    return CPQ_OK;
+}
+
+cpq_status cpq_set_epilogue(cpq_handle h, double makeup_gain, int dither_bits)
+{
+    if (!h || !std::isfinite(makeup_gain) || dither_bits > 32) return CPQ_ERR_INVALID;
+    h->makeup = makeup_gain;
+    h->ditherBits = dither_bits < 0 ? 0 : dither_bits;
+    return CPQ_OK;
+}
+
+cpq_status cpq_set_dither_uniforms(cpq_handle h, const double* uniforms, int64_t samples_per_channel)
+{
+    if (!h || !uniforms || samples_per_channel <= 0) return CPQ_ERR_INVALID;
+    Engine* e = h;
+    auto setError = [&](const std::string& s) { e->setError(s); };
+    CPQ_CUDA(cudaSetDevice(e->cfg.device));
+    const size_t n = (size_t) e->nSeq * 2 * (size_t) samples_per_channel;
+    CPQ_CUDA(e->uniforms.ensure(n));
+    CPQ_CUDA(cudaMemcpy(e->uniforms.p, uniforms, n * sizeof(double), cudaMemcpyHostToDevice));
+    e->uniformsPerCh = samples_per_channel;
+    return CPQ_OK;
+}
+
+cpq_status cpq_design_band(int type, float freq_hz, float gain_db, float q, double sample_rate, cpq_svf_coeffs* out)
+{
+    if (!out) return CPQ_ERR_INVALID;
+    return cpq::designBand(type, freq_hz, gain_db, q, sample_rate, out) ? CPQ_OK : CPQ_ERR_INVALID;
+}
+double cpq_db_to_gain(float db) { return cpq::dbToGain(db); }
+double cpq_equal_power_sin(double x) { return cpq::equalPowerSin(x); }
+
+cpq_status cpq_process_device(cpq_handle h, double* d_io, int64_t stride, int64_t T, unsigned stages)
+{
+    if (!h) return CPQ_ERR_INVALID;
+    return h->processDevice(d_io, stride, T, stages);
+}
+
+cpq_status cpq_process(cpq_handle h, double* const* planar, int64_t T, unsigned stages)
+{
+    if (!h || !planar) return CPQ_ERR_INVALID;
+    Engine* e = h;
+    auto setError = [&](const std::string& s) { e->setError(s); };
+    if (T <= 0 || T > e->cfg.max_samples || T % e->cfg.block_size != 0)
+    {
+        e->setError("process: T must be a positive multiple of block_size and <= max_samples");
+        return CPQ_ERR_INVALID;
+    }
+    CPQ_CUDA(cudaSetDevice(e->cfg.device));
+    const int64_t stride = (T + 1) & ~(int64_t) 1;
+    CPQ_CUDA(e->io.ensure((size_t) e->nSeq * stride));
+    cudaEvent_t h0 = e->ev[7];
+    cudaEventRecord(h0, e->stream);
+    for (int s = 0; s < e->nSeq; ++s)
+    {
+        if (!planar[s]) { e->setError("process: null channel pointer"); return CPQ_ERR_INVALID; }
+        CPQ_CUDA(cudaMemcpyAsync(e->io.p + (size_t) s * stride, planar[s], (size_t) T * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    }
+    cudaEventRecord(e->ev[0], e->stream);
+    CPQ_CUDA(cudaEventSynchronize(e->ev[0]));
+    float h2d = 0.f;
+    cudaEventElapsedTime(&h2d, h0, e->ev[0]);
+    cpq_status st = e->processDevice(e->io.p, stride, T, stages);
+    if (st != CPQ_OK) return st;
+    cudaEventRecord(h0, e->stream);
+    for (int s = 0; s < e->nSeq; ++s)
+        CPQ_CUDA(cudaMemcpyAsync(planar[s], e->io.p + (size_t) s * stride, (size_t) T * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    cudaEventRecord(e->ev[0], e->stream);
+    CPQ_CUDA(cudaEventSynchronize(e->ev[0]));
+    float d2h = 0.f;
+    cudaEventElapsedTime(&d2h, h0, e->ev[0]);
+    e->timings.h2d_ms = h2d;
+    e->timings.d2h_ms = d2h;
+    e->timings.total_ms += h2d + d2h;
+    return CPQ_OK;
+}
+
+cpq_status cpq_set_partition_range(cpq_handle h, int part_begin, int part_end)
+{
+    if (!h || part_begin < 0) return CPQ_ERR_INVALID;
+    h->partBegin = part_begin;
+    h->partEnd = part_end;
+    return CPQ_OK;
+}
+
+int cpq_total_partitions(cpq_handle h)
+{
+    if (!h || !h->planSet) return 0;
+    int total = 0;
+    for (int li = 0; li < h->plan.numLayers; ++li) total += h->plan.layers[li].numPartsIR;
+    return total;
+}
+
+static void fillLayout(const cpq::ConvPlan& plan, const cpq::GatherPlan* g, cpq_layout* out)
+{
+    std::memset(out, 0, sizeof(*out));
+    out->num_layers = plan.numLayers;
+    out->latency = plan.numLayers > 0 ? plan.layers[0].partSize : 0;
+    for (int li = 0; li < plan.numLayers; ++li)
+    {
+        const cpq::LayerPlan& l = plan.layers[li];
+        cpq_layer_layout& o = out->layers[li];
+        o.part_size = l.partSize;
+        o.fft_size = l.fftSize;
+        o.num_parts_ir = l.numPartsIR;
+        o.num_parts = l.numParts;
+        o.parts_per_callback = l.partsPerCallback;
+        o.output_delay_samples = l.outputDelaySamples;
+        o.ir_offset = l.irOffset;
+        o.ir_len = l.irLen;
+        o.gain = l.gain;
+        o.first_output_sample = g ? g->firstOutput[li] : -1;
+        o.skipped_callbacks = g ? g->skipped[li] : 0;
+    }
+}
+
+cpq_status cpq_get_layout(cpq_handle h, cpq_layout* out)
+{
+    if (!h || !out) return CPQ_ERR_INVALID;
+    if (!h->planSet) return CPQ_ERR_NOT_READY;
+    cpq::GatherPlan g;
+    cpq::simulateCallbacks(h->plan, h->cfg.max_samples / h->cfg.block_size, g);
+    fillLayout(h->plan, &g, out);
+    return CPQ_OK;
+}
+
+int cpq_latency(cpq_handle h) { return (h && h->planSet) ? h->plan.layers[0].partSize : 0; }
+
+cpq_status cpq_get_timings(cpq_handle h, cpq_timings* out)
+{
+    if (!h || !out) return CPQ_ERR_INVALID;
+    *out = h->timings;
+    return CPQ_OK;
+}
+
+cpq_status cpq_get_eq_state(cpq_handle h, int stream, double* out)
+{
+    if (!h || !out || stream < 0 || stream >= h->cfg.n_streams) return CPQ_ERR_INVALID;
+    Engine* e = h;
+    auto setError = [&](const std::string& s) { e->setError(s); };
+    CPQ_CUDA(cudaSetDevice(e->cfg.device));
+    const size_t per = (size_t) e->cfg.n_channels * CPQ_NUM_BANDS * 2;
+    CPQ_CUDA(cudaMemcpy(out, e->stateOut.p + (size_t) stream * per, per * sizeof(double), cudaMemcpyDeviceToHost));
+    return CPQ_OK;
+}
+
+void* cpq_cuda_stream(cpq_handle h) { return h ? (void*) h->stream : nullptr; }
+int64_t cpq_kernel_launch_count(cpq_handle h) { return h ? h->launches : 0; }
+
+cpq_status cpq_plan_layout(int ir_len, int block_size, const cpq_filter_spec* spec, int64_t n_callbacks,
+                           cpq_layout* out, int64_t* src_offsets)
+{
+    if (!out || n_callbacks < 0) return CPQ_ERR_INVALID;
+    cpq::ConvPlan plan;
+    if (!cpq::makeConvPlan(ir_len, block_size, spec, plan)) return CPQ_ERR_INVALID;
+    cpq::GatherPlan g;
+    cpq::simulateCallbacks(plan, n_callbacks, g);
+    fillLayout(plan, &g, out);
+    if (src_offsets)
+        for (int li = 1; li < plan.numLayers; ++li)
+            std::memcpy(src_offsets + (size_t) (li - 1) * n_callbacks, g.tailSrc[li].data(), (size_t) n_callbacks * sizeof(int64_t));
+    return CPQ_OK;
+}
+
+/* DFMA throughput probe used by bench.py for the FP64-pipe roofline (not part of the reference path). */
+double cpq_probe_dfma_tflops(int device, int iters)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop {};
+    cudaGetDeviceProperties(&prop, device);
+    double* d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return -1.0;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    cpq::dfma_probe_kernel<<<blocks, threads>>>(d, 64);
+    cudaDeviceSynchronize();
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a);
+    cpq::dfma_probe_kernel<<<blocks, threads>>>(d, iters);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    if (cudaGetLastError() != cudaSuccess || ms <= 0.f) return -1.0;
+    const double flops = 2.0 * 8.0 * (double) iters * (double) blocks * threads;
+    return flops / (ms * 1e-3) / 1e12;
+}
+}

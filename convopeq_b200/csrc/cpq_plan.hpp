@@ -1,0 +1,501 @@
+// cpq_plan.hpp -- host-side integer/scalar logic of the hot path (no CUDA in this header).
+//
+// The reference's real-time machinery (ring buffers, frequency-domain delay line slots, time-sliced tail
+// MAC, delay-line cursors) has only *integer* observable consequences for an offline run: which layer
+// output sample lands on which output sample, and which callbacks skip a layer.  This header derives
+// those from the same rules the reference applies, so that the GPU can compute every layer as one plain
+// batched block convolution and then follow a small gather plan.
+//
+// Reference (paths relative to the reference's src/):
+//   layer plan / gains          MKLNonUniformConvolver.cpp:626-684, 738-758, 784-786, 988-994, 1004-1024
+//   callback state machine      MKLNonUniformConvolver.cpp:1407-1548 (Add), 1553-1688 (Get, delay line)
+//   spectrum filter / tilt      MKLNonUniformConvolver.cpp:336-443, 1060-1097
+//   SVF design                  eqprocessor/EQProcessor.Coefficients.cpp:84-130, 431-618
+//   total-gain ramp             DspNumericPolicy.h:319-421, eqprocessor/EQProcessor.Processing.cpp:1262-1274
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "../../include/cpq.h"
+
+namespace cpq
+{
+
+constexpr double kPi = 3.14159265358979323846;
+
+inline int nextPow2(int n)
+{
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+inline int ilog2(int n)
+{
+    int l = 0;
+    while ((1 << l) < n) ++l;
+    return l;
+}
+template <typename T>
+inline T clampv(T lo, T hi, T v) { return v < lo ? lo : (hi < v ? hi : v); }
+
+struct LayerPlan
+{
+    int partSize = 0, fftSize = 0, bins = 0;       // P, N = 2P, M = P + 1
+    int numPartsIR = 0, numParts = 0;              // Q, nextPow2(Q)
+    int partsPerCallback = 0, callbacksPerCycle = 0;
+    int outputDelaySamples = 0;                    // sum of previous layers' IR lengths
+    int irOffset = 0, irLen = 0;
+    bool immediate = false;
+    double gain = 1.0;
+};
+
+struct ConvPlan
+{
+    int numLayers = 0;
+    int blockSize = 0;
+    int irLen = 0;
+    int tailMode = 1;
+    bool tailEnabled = true;
+    double tailStartSec = 0.085, strength01 = 0.5;
+    bool hasSpec = false;
+    cpq_filter_spec spec {};
+    LayerPlan layers[CPQ_MAX_LAYERS];
+
+    bool sameGeometry(const ConvPlan& o) const
+    {
+        if (numLayers != o.numLayers || blockSize != o.blockSize) return false;
+        for (int l = 0; l < numLayers; ++l)
+        {
+            const LayerPlan &a = layers[l], &b = o.layers[l];
+            if (a.partSize != b.partSize || a.numPartsIR != b.numPartsIR || a.partsPerCallback != b.partsPerCallback ||
+                a.outputDelaySamples != b.outputDelaySamples || a.gain != b.gain)
+                return false;
+        }
+        return true;
+    }
+};
+
+inline void filterSpecDefault(cpq_filter_spec* s)
+{
+    s->sample_rate = 48000.0;
+    s->hc_mode = 1;
+    s->lc_mode = 0;
+    s->tail_mode = 1;
+    s->tail_enabled = 1;
+    s->tail_start_seconds = 0.085;
+    s->tail_strength = 1.0;
+    s->tail_l1l2_multiplier = 8;
+    s->reserved_ = 0;
+}
+
+// SetImpulse's parameter table and layer plan.  Returns false for the inputs SetImpulse rejects.
+inline bool makeConvPlan(int irLen, int blockSize, const cpq_filter_spec* fs, ConvPlan& out)
+{
+    if (irLen <= 0 || blockSize <= 0) return false;
+    out = ConvPlan {};
+    out.blockSize = blockSize;
+    out.irLen = irLen;
+    out.hasSpec = fs != nullptr;
+    if (fs) out.spec = *fs;
+
+    const int tailMode = fs ? clampv(0, 2, (int) fs->tail_mode) : 1;
+    const bool tailEnabled = (tailMode != 2) && (fs ? fs->tail_enabled != 0 : true);
+    const double srTail = fs ? fs->sample_rate : 48000.0;
+    double tailStart = fs ? clampv(0.01, 0.80, fs->tail_start_seconds) : 0.085;
+    const double userStrength = fs ? clampv(0.0, 2.0, fs->tail_strength) : 1.0;
+    double tailStrength = userStrength;
+    int mult = fs ? clampv(2, 16, (int) fs->tail_l1l2_multiplier) : 8;
+    double g1 = 1.0, g2 = 1.0;
+    const double s01 = clampv(0.0, 1.0, userStrength * 0.5);
+    if (!tailEnabled) { g1 = 0.0; g2 = 0.0; }
+    else if (tailMode == 0)
+    {
+        tailStart = clampv(0.01, 0.80, std::max(tailStart, 0.055));
+        mult = clampv(2, 16, std::max(mult, 6));
+        tailStrength = clampv(0.0, 2.0, userStrength);
+        g1 = clampv(0.0, 2.0, tailStrength * (0.95 - 0.25 * s01));
+        g2 = clampv(0.0, 2.0, tailStrength * (0.80 - 0.45 * s01));
+    }
+    else if (tailMode == 1)
+    {
+        tailStart = clampv(0.01, 0.80, std::max(tailStart, 0.12));
+        tailStrength = clampv(0.0, 2.0, std::max(tailStrength, 1.25));
+        mult = clampv(2, 16, std::max(mult, 8));
+        g1 = clampv(0.0, 2.0, tailStrength * (1.05 + 0.20 * s01));
+        g2 = clampv(0.0, 2.0, tailStrength * (0.82 + 0.12 * s01));
+    }
+    else { g1 = 0.0; g2 = 0.0; }
+    out.tailMode = tailMode;
+    out.tailEnabled = tailEnabled;
+    out.tailStartSec = tailStart;
+    out.strength01 = s01;
+
+    const int l0Part = nextPow2(std::max(blockSize, 64));
+    const long long l1PartLL = (long long) l0Part * mult;
+    const long long l2PartLL = l1PartLL * mult;
+    const int l0MaxLen = 32 * l0Part;
+    const int l0ByTail = (int) std::llround(tailStart * srTail);
+    const int l0Target = clampv(l0Part, l0MaxLen, l0ByTail);
+    const int l0Len = std::min(irLen, tailEnabled ? l0Target : l0MaxLen);
+    const long long l1Cap = 64LL * l1PartLL;
+    const int l1Len = tailEnabled ? (int) std::max(0LL, std::min((long long) irLen - l0Len, l1Cap)) : 0;
+    const int l2Len = tailEnabled ? std::max(0, irLen - l0Len - l1Len) : 0;
+
+    const int offs[3] = { 0, l0Len, l0Len + l1Len };
+    const int lens[3] = { l0Len, l1Len, l2Len };
+    const long long parts[3] = { l0Part, l1PartLL, l2PartLL };
+    const double gains[3] = { 1.0, g1, g2 };
+
+    int prevTotal = 0;
+    for (int li = 0; li < 3; ++li)
+    {
+        if (lens[li] <= 0) continue;
+        if (parts[li] > (1LL << 28)) return false;
+        LayerPlan& l = out.layers[out.numLayers];
+        l.partSize = (int) parts[li];
+        l.fftSize = l.partSize * 2;
+        l.bins = l.partSize + 1;
+        l.immediate = (li == 0);
+        l.numPartsIR = (lens[li] + l.partSize - 1) / l.partSize;
+        l.numParts = nextPow2(l.numPartsIR);
+        l.irOffset = offs[li];
+        l.irLen = lens[li];
+        // the reference indexes m_tailLayerGain by *active* layer index (Get(), :1626-1628)
+        l.gain = tailEnabled ? gains[out.numLayers] : 0.0;
+        if (!l.immediate)
+        {
+            const int bs = std::max(blockSize, 1);
+            const int blocksPerPart = (l.partSize + bs - 1) / bs;
+            int ppc = std::max(1, (l.numPartsIR + blocksPerPart - 1) / blocksPerPart);
+            ppc = std::min(ppc, l.numPartsIR);
+            l.partsPerCallback = ppc;
+            l.callbacksPerCycle = (l.numPartsIR + ppc - 1) / ppc;
+        }
+        l.outputDelaySamples = prevTotal;
+        prevTotal += lens[li];
+        ++out.numLayers;
+    }
+    if (out.numLayers > 0) out.layers[0].gain = 1.0;
+    return out.numLayers > 0;
+}
+
+// Real per-bin gain applied to every partition spectrum of layer `li` (applySpectrumFilter + tilt).
+inline void spectrumGain(const ConvPlan& plan, int li, std::vector<double>& gain)
+{
+    const LayerPlan& l = plan.layers[li];
+    gain.assign((size_t) l.bins, 1.0);
+    if (plan.hasSpec)
+    {
+        const cpq_filter_spec& spec = plan.spec;
+        const double fs = spec.sample_rate;
+        const double nyquist = fs * 0.5;
+        const double hcStart = (fs <= 48000.0) ? 18000.0 : 22000.0;
+        const double hcEnd = nyquist;
+        const double lcEnd = (spec.lc_mode == 1) ? 6.0 : 8.0;
+        const double lcStart = (spec.lc_mode == 1) ? 15.0 : 18.0;
+        const int N = l.fftSize, halfN = N / 2, cs = l.bins;
+        {
+            const int kStart = (int) std::round(hcStart * N / fs);
+            const int kEnd = std::min(halfN, (int) std::round(hcEnd * N / fs));
+            for (int k = 0; k < cs; ++k)
+            {
+                if (k <= kStart) continue;
+                if (k <= kEnd)
+                {
+                    const double denom = (double) (kEnd - kStart);
+                    const double x = (double) (k - kStart) / denom;
+                    switch (spec.hc_mode)
+                    {
+                        case 0: gain[(size_t) k] = 1.0 / std::sqrt(1.0 + std::pow(x, 8.0)); break;
+                        case 1: gain[(size_t) k] = 0.5 * (1.0 + std::cos(kPi * x)); break;
+                        case 2: gain[(size_t) k] = std::exp(-4.60517 * x * x); break;
+                        default: break;
+                    }
+                }
+            }
+        }
+        {
+            const int kEnd = (int) std::round(lcEnd * N / fs);
+            const int kStart = (int) std::round(lcStart * N / fs);
+            for (int k = 0; k < cs; ++k)
+            {
+                if (k <= kEnd) gain[(size_t) k] = 0.0;
+                else if (k < kStart)
+                {
+                    const double denom = (double) std::max(1, kStart - kEnd);
+                    const double x = (double) (k - kEnd) / denom;
+                    gain[(size_t) k] *= 0.5 * (1.0 - std::cos(kPi * x));
+                }
+            }
+        }
+    }
+}
+
+// Air-absorption tilt for layers >= 1 in tail mode 0; returns false when no tilt applies.
+inline bool tiltGain(const ConvPlan& plan, int li, std::vector<double>& tilt)
+{
+    if (!(plan.tailEnabled && plan.tailMode == 0) || li < 1) return false;
+    const LayerPlan& l = plan.layers[li];
+    const double startNorm = clampv(0.65, 1.55, plan.tailStartSec / 0.085);
+    const double dampingBase = (0.35 + 1.10 * plan.strength01) * startNorm;
+    const double w = (li == 1) ? 1.0 : 1.6;
+    const double dc = dampingBase * w;
+    const double denom = (double) std::max(1, l.bins - 1);
+    tilt.resize((size_t) l.bins);
+    for (int k = 0; k < l.bins; ++k)
+    {
+        const double fn = (double) k / denom;
+        tilt[(size_t) k] = std::exp(-dc * fn * fn);
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gather plan: run the reference's per-callback integer state machine for `nCallbacks` callbacks of
+// exactly blockSize samples (Add then Get).
+//
+//   L0   : ring of completed L0 blocks; per callback (ringSrc, count): out[0..count) = y0[ringSrc ...],
+//          rest zero.  With blockSize == partSize this is the identity (ringSrc = c*B, count = B).
+//   L>=1 : the delay line is the concatenation of *completed* blocks (a block whose distribution cycle
+//          is restarted before it finished is never written); per callback either -1 (skipped) or the
+//          stream position read.  blockOfStream maps stream block j to the frame index k it came from.
+// ------------------------------------------------------------------------------------------------
+struct GatherPlan
+{
+    int64_t nCallbacks = 0;
+    std::vector<int64_t> l0Src;                    // [nCallbacks] or empty when identity
+    std::vector<int32_t> l0Count;                  // [nCallbacks]
+    bool l0Identity = true;
+    std::vector<int64_t> tailSrc[CPQ_MAX_LAYERS];  // [nCallbacks], -1 = skip   (index = layer)
+    std::vector<int32_t> blockOfStream[CPQ_MAX_LAYERS];  // stream block -> frame k; empty when identity
+    bool blockIdentity[CPQ_MAX_LAYERS] = { true, true, true };
+    int64_t firstOutput[CPQ_MAX_LAYERS] = { -1, -1, -1 };
+    int64_t skipped[CPQ_MAX_LAYERS] = { 0, 0, 0 };
+    int64_t framesNeeded[CPQ_MAX_LAYERS] = { 0, 0, 0 };  // frames k < framesNeeded must be computed
+};
+
+inline void simulateCallbacks(const ConvPlan& plan, int64_t nCallbacks, GatherPlan& g)
+{
+    g = GatherPlan {};
+    g.nCallbacks = nCallbacks;
+    const int B = plan.blockSize;
+
+    // ---- L0 ring (ringWrite/ringRead; capacity never binds when Get follows every Add) ----
+    {
+        const LayerPlan& l = plan.layers[0];
+        const int P = l.partSize;
+        g.framesNeeded[0] = (nCallbacks * (int64_t) B) / P;
+        if (P == B) g.l0Identity = true;
+        else
+        {
+            g.l0Identity = false;
+            g.l0Src.resize((size_t) nCallbacks);
+            g.l0Count.resize((size_t) nCallbacks);
+            int64_t written = 0, read = 0;
+            int inputPos = 0;
+            for (int64_t c = 0; c < nCallbacks; ++c)
+            {
+                int consumed = 0;
+                while (consumed < B)
+                {
+                    const int fill = std::min(B - consumed, P - inputPos);
+                    inputPos += fill;
+                    consumed += fill;
+                    if (inputPos >= P) { inputPos = 0; written += P; }
+                }
+                const int64_t avail = written - read;
+                const int cnt = (int) std::min<int64_t>(B, avail);
+                g.l0Src[(size_t) c] = read;
+                g.l0Count[(size_t) c] = cnt;
+                read += cnt;
+            }
+        }
+        g.firstOutput[0] = 0;
+    }
+
+    // ---- tails ----
+    for (int li = 1; li < plan.numLayers; ++li)
+    {
+        const LayerPlan& l = plan.layers[li];
+        const int P = l.partSize;
+        g.tailSrc[li].assign((size_t) nCallbacks, -1);
+        std::vector<int32_t> completed;
+        int inputPos = 0, nextPart = 0;
+        bool distributing = false;
+        int32_t frameInFlight = -1, framesPushed = 0;
+        uint64_t w = 0, r = 0;
+        bool spoke = false;
+        for (int64_t c = 0; c < nCallbacks; ++c)
+        {
+            // Add
+            int consumed = 0;
+            while (consumed < B)
+            {
+                const int fill = std::min(B - consumed, P - inputPos);
+                inputPos += fill;
+                consumed += fill;
+                if (inputPos >= P)
+                {
+                    inputPos = 0;
+                    frameInFlight = framesPushed++;
+                    nextPart = 0;
+                    distributing = true;
+                }
+            }
+            if (distributing)
+            {
+                const int endPart = std::min(nextPart + l.partsPerCallback, l.numPartsIR);
+                nextPart = endPart;
+                if (nextPart >= l.numPartsIR)
+                {
+                    completed.push_back(frameInFlight);
+                    w += (uint64_t) P;
+                    distributing = false;
+                    nextPart = 0;
+                }
+            }
+            // Get -> delayLineReadAdd
+            const uint64_t maxRead = (w >= (uint64_t) l.outputDelaySamples) ? w - (uint64_t) l.outputDelaySamples : 0;
+            const uint64_t start = std::max(r, maxRead);
+            if (start + (uint64_t) B > w)
+            {
+                if (spoke) ++g.skipped[li];
+                continue;
+            }
+            g.tailSrc[li][(size_t) c] = (int64_t) start;
+            r = start + (uint64_t) B;
+            if (!spoke) { spoke = true; g.firstOutput[li] = c * (int64_t) B; }
+        }
+        bool ident = true;
+        for (size_t j = 0; j < completed.size(); ++j)
+            if (completed[j] != (int32_t) j) { ident = false; break; }
+        g.blockIdentity[li] = ident;
+        if (!ident) g.blockOfStream[li] = completed;
+        g.framesNeeded[li] = completed.empty() ? 0 : (int64_t) (*std::max_element(completed.begin(), completed.end())) + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// EQ design (float parameters clamped, then promoted) and the per-band scan constants.
+// ------------------------------------------------------------------------------------------------
+inline void bypassCoeffs(cpq_svf_coeffs* c) { c->a1 = 1.0; c->a2 = 0.0; c->a3 = 0.0; c->m0 = 1.0; c->m1 = 0.0; c->m2 = 0.0; }
+
+inline bool designBand(int type, float freq, float gainDb, float q, double sr, cpq_svf_coeffs* out)
+{
+    if (type < 0 || type > 4) return false;
+    if (sr <= 0.0) { bypassCoeffs(out); return true; }
+    const float nyq = static_cast<float>(sr * 0.5);
+    const float maxFreq = std::min(20000.0f, nyq * 0.95f);
+    freq = clampv(20.0f, maxFreq, freq);
+    q = clampv(0.01f, 20.0f, q);
+    gainDb = clampv(-48.0f, 48.0f, gainDb);
+    const double f = (double) freq, gdb = (double) gainDb, Q = (double) q;
+    double A = 1.0, g = 0.0, k = 0.0;
+    const double t = std::tan(kPi * f / sr);
+    switch (type)
+    {
+        case 0: A = std::pow(10.0, gdb / 40.0); g = t / std::sqrt(A); k = 1.0 / Q; break;
+        case 1: A = std::pow(10.0, gdb / 40.0); g = t; k = 1.0 / (Q * A); break;
+        case 2: A = std::pow(10.0, gdb / 40.0); g = t * std::sqrt(A); k = 1.0 / Q; break;
+        default: g = t; k = 1.0 / Q; break;
+    }
+    if (!std::isfinite(g) || !std::isfinite(k)) { bypassCoeffs(out); return true; }
+    const double den = 1.0 + g * (g + k);
+    if (std::fabs(den) < 1.0e-15) { bypassCoeffs(out); return true; }
+    out->a1 = 1.0 / den;
+    out->a2 = g * out->a1;
+    out->a3 = g * out->a2;
+    switch (type)
+    {
+        case 0: out->m0 = 1.0; out->m1 = k * (A - 1.0); out->m2 = A * A - 1.0; break;
+        case 1: out->m0 = 1.0; out->m1 = (A - 1.0 / A) / Q; out->m2 = 0.0; break;
+        case 2: out->m0 = A * A; out->m1 = k * (1.0 - A) * A; out->m2 = 1.0 - A * A; break;
+        case 3: out->m0 = 0.0; out->m1 = 0.0; out->m2 = 1.0; break;
+        default: out->m0 = 1.0; out->m1 = -k; out->m2 = -1.0; break;
+    }
+    return true;
+}
+
+inline double dbToGain(float db)
+{
+    const double d = (double) db;
+    return d > -100.0 ? std::pow(10.0, d * 0.05) : 0.0;
+}
+
+inline double equalPowerSin(double x)
+{
+    const double t = x * (kPi * 0.5);
+    const double t2 = t * t;
+    return t * (1.0 + t2 * (-1.0 / 6.0 + t2 * (1.0 / 120.0 + t2 * (-1.0 / 5040.0 + t2 * (1.0 / 362880.0)))));
+}
+
+// Total-gain LinearRamp evaluated per callback: (start, increment) pairs.
+struct GainEvent { int64_t atCallback; double target; };
+
+inline void gainRampTable(double initial, int totalSteps, int blockSize, int64_t nCallbacks,
+                          std::vector<GainEvent> events, std::vector<double>& startInc /* [nCallbacks][2] */)
+{
+    std::stable_sort(events.begin(), events.end(), [](const GainEvent& a, const GainEvent& b) { return a.atCallback < b.atCallback; });
+    double current = initial, target = initial, step = 0.0, wanted = initial;
+    int remaining = 0;
+    size_t ev = 0;
+    startInc.resize((size_t) nCallbacks * 2);
+    for (int64_t c = 0; c < nCallbacks; ++c)
+    {
+        while (ev < events.size() && events[ev].atCallback <= c) wanted = events[ev++].target;
+        if (std::fabs(target - wanted) > 1e-6 && wanted != target)
+        {
+            target = wanted;
+            const int steps = remaining > 0 ? remaining : totalSteps;
+            step = (target - current) / (double) steps;
+            remaining = steps;
+        }
+        const double start = current;
+        if (remaining > 0)
+        {
+            if (blockSize >= remaining) { current = target; remaining = 0; }
+            else { current += step * (double) blockSize; remaining -= blockSize; }
+        }
+        startInc[(size_t) c * 2] = start;
+        startInc[(size_t) c * 2 + 1] = (current - start) / (double) blockSize;
+    }
+}
+
+// PsychoacousticDither coefficient selection (PsychoacousticDither.h:192-275)
+inline void ditherCoeffs(double sampleRate, int bitDepth, double* out12)
+{
+    static const double table[6][3][12] = {
+        { { 2.93, -5.06, 6.97, -7.66, 7.11, -5.63, 3.96, -2.18, 0.80, -0.24, 0.10, -0.04 },
+          { 2.49, -4.30, 5.92, -6.51, 6.05, -4.79, 3.37, -1.86, 0.68, -0.20, 0.08, -0.03 },
+          { 2.04, -3.52, 4.85, -5.34, 4.95, -3.92, 2.76, -1.52, 0.56, -0.17, 0.07, -0.03 } },
+        { { 2.85, -4.92, 6.78, -7.45, 6.92, -5.48, 3.85, -2.12, 0.78, -0.23, 0.09, -0.04 },
+          { 2.42, -4.18, 5.75, -6.32, 5.87, -4.65, 3.27, -1.80, 0.66, -0.20, 0.08, -0.03 },
+          { 1.98, -3.42, 4.71, -5.18, 4.81, -3.81, 2.68, -1.47, 0.54, -0.16, 0.06, -0.03 } },
+        { { 3.28, -5.66, 7.80, -8.57, 7.96, -6.30, 4.43, -2.44, 0.90, -0.27, 0.11, -0.05 },
+          { 2.78, -4.80, 6.61, -7.26, 6.75, -5.34, 3.75, -2.07, 0.76, -0.23, 0.09, -0.04 },
+          { 2.28, -3.94, 5.42, -5.95, 5.53, -4.38, 3.08, -1.69, 0.62, -0.19, 0.07, -0.03 } },
+        { { 3.71, -6.40, 8.82, -9.69, 9.00, -7.12, 5.01, -2.76, 1.02, -0.31, 0.12, -0.05 },
+          { 3.15, -5.44, 7.50, -8.24, 7.65, -6.05, 4.25, -2.34, 0.86, -0.26, 0.10, -0.04 },
+          { 2.58, -4.46, 6.15, -6.75, 6.27, -4.96, 3.48, -1.92, 0.70, -0.21, 0.08, -0.03 } },
+        { { 4.12, -7.10, 9.78, -10.75, 9.98, -7.89, 5.55, -3.06, 1.13, -0.34, 0.14, -0.06 },
+          { 3.49, -6.03, 8.31, -9.13, 8.47, -6.70, 4.71, -2.59, 0.95, -0.29, 0.11, -0.05 },
+          { 2.86, -4.94, 6.81, -7.48, 6.94, -5.49, 3.86, -2.12, 0.78, -0.23, 0.09, -0.04 } },
+        { { 4.48, -7.73, 10.64, -11.70, 10.86, -8.59, 6.04, -3.33, 1.23, -0.37, 0.15, -0.06 },
+          { 3.80, -6.56, 9.04, -9.93, 9.22, -7.29, 5.13, -2.82, 1.04, -0.31, 0.12, -0.05 },
+          { 3.11, -5.37, 7.41, -8.13, 7.55, -5.97, 4.20, -2.31, 0.85, -0.26, 0.10, -0.04 } },
+    };
+    int srBand;
+    if (sampleRate < 46050.0) srBand = 0;
+    else if (sampleRate < 72000.0) srBand = 1;
+    else if (sampleRate < 144000.0) srBand = 2;
+    else if (sampleRate < 264600.0) srBand = 3;
+    else if (sampleRate < 529200.0) srBand = 4;
+    else srBand = 5;
+    const int bp = bitDepth <= 16 ? 0 : (bitDepth <= 24 ? 1 : 2);
+    for (int i = 0; i < 12; ++i) out12[i] = table[srBand][bp][i];
+}
+
+} // namespace cpq

@@ -1,0 +1,197 @@
+"""Host-side mirror of the reference's processing interface over the C ABI (include/cpq.h).
+
+Names follow the reference: prepare with IR, sample rate and block size (`prepare_to_play`,
+`set_impulse` ~ StereoConvolver::init / MKLNonUniformConvolver::SetImpulse), set per-band parameters
+(`set_band` ~ EQProcessor::setBand*/createCoeffCache), process a block in place (`process`).
+PyTorch is only used by callers for device memory; nothing here imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import capi
+
+_dp = C.POINTER(C.c_double)
+
+# EQProcessor::DEFAULT_FREQS (eqprocessor/EQProcessor.h:158-163)
+DEFAULT_FREQS = [25.0, 40.0, 63.0, 100.0, 160.0, 250.0, 400.0, 630.0, 1000.0, 1600.0,
+                 2500.0, 4000.0, 6300.0, 10000.0, 11000.0, 12500.0, 14000.0, 16000.0, 18000.0, 20000.0]
+
+LOW_SHELF, PEAKING, HIGH_SHELF, LOW_PASS, HIGH_PASS = range(5)
+STEREO, LEFT, RIGHT = range(3)
+
+
+@dataclass
+class Band:
+    """convo::EQBandParams (core/EQParameters.h:11-20); float parameters, like the reference."""
+    frequency: float = 1000.0
+    gain: float = 0.0
+    q: float = 0.707
+    enabled: bool = True
+    type: int = PEAKING
+    channel_mode: int = STEREO
+
+
+def design_band(band: Band, sample_rate: float) -> capi.SvfCoeffs:
+    """EQProcessor::calcSVFCoeffs (EQProcessor.Coefficients.cpp:101-130)."""
+    out = capi.SvfCoeffs()
+    st = capi.load().cpq_design_band(int(band.type), C.c_float(band.frequency), C.c_float(band.gain),
+                                     C.c_float(band.q), float(sample_rate), C.byref(out))
+    if st != capi.OK:
+        raise capi.CpqError(st, "design_band")
+    return out
+
+
+class ConvoPeqEngine:
+    """A batch of independent (stereo or mono) streams on one B200."""
+
+    def __init__(self, n_streams: int = 1, n_channels: int = 2, sample_rate: float = 48000.0, block_size: int = 512,
+                 max_samples: int = 480000 // 512 * 512, device: int = 0, conv_boundary: int = capi.CONV_INNER,
+                 shared_ir: bool = False, shared_eq: bool = False, workspace_bytes: int = 0):
+        self.lib = capi.load()
+        cfg = capi.Config()
+        self.lib.cpq_config_default(C.byref(cfg))
+        cfg.device = device
+        cfg.n_streams = n_streams
+        cfg.n_channels = n_channels
+        cfg.block_size = block_size
+        cfg.sample_rate = sample_rate
+        cfg.max_samples = max_samples
+        cfg.conv_boundary = conv_boundary
+        cfg.shared_ir = int(shared_ir)
+        cfg.shared_eq = int(shared_eq)
+        cfg.workspace_bytes = workspace_bytes
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        st = self.lib.cpq_create(C.byref(cfg), C.byref(self.h))
+        if st != capi.OK:
+            raise capi.CpqError(st, self.lib.cpq_last_error(None).decode())
+        self.n_seq = n_streams * n_channels
+        self.sample_rate = sample_rate
+
+    # ---- lifecycle ----
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.cpq_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int):
+        if st != capi.OK:
+            raise capi.CpqError(st, self.lib.cpq_last_error(self.h).decode())
+
+    def reset(self):
+        self._check(self.lib.cpq_reset(self.h))
+
+    # ---- prepare ----
+    def set_impulse(self, stream: int, channel: int, ir: np.ndarray, scale: float = 1.0,
+                    spec: Optional[capi.FilterSpec] = None):
+        ir = np.ascontiguousarray(ir, dtype=np.float64)
+        self._check(self.lib.cpq_set_impulse(self.h, stream, channel, ir.ctypes.data_as(_dp), ir.size, scale,
+                                             C.byref(spec) if spec is not None else None))
+
+    def set_eq(self, stream: int, bands: Sequence[Band], saturation: float = 0.2, total_gain_db: float = 0.0):
+        """createCoeffCache(params) + EQParameters (ProcessingCache.cpp:56-96). saturation/total gain are float in
+        the reference and promoted to double before use."""
+        assert len(bands) == capi.NUM_BANDS
+        co = (capi.SvfCoeffs * capi.NUM_BANDS)()
+        act = (C.c_uint8 * capi.NUM_BANDS)()
+        mode = (C.c_int32 * capi.NUM_BANDS)()
+        for i, b in enumerate(bands):
+            on = bool(b.enabled) and self.sample_rate > 0
+            act[i] = 1 if on else 0
+            mode[i] = int(b.channel_mode)
+            co[i] = design_band(b, self.sample_rate) if on else capi.SvfCoeffs()
+        sat = float(np.float32(saturation))
+        gain = self.lib.cpq_db_to_gain(C.c_float(total_gain_db))
+        self._check(self.lib.cpq_set_eq(self.h, stream, co, act, mode, sat, gain))
+
+    def set_eq_raw(self, stream: int, coeffs: np.ndarray, active: Sequence[int], modes: Sequence[int],
+                   saturation: float, total_gain_lin: float):
+        co = (capi.SvfCoeffs * capi.NUM_BANDS)()
+        for i in range(capi.NUM_BANDS):
+            co[i] = capi.SvfCoeffs(*[float(v) for v in coeffs[i]])
+        act = (C.c_uint8 * capi.NUM_BANDS)(*[int(a) for a in active])
+        mode = (C.c_int32 * capi.NUM_BANDS)(*[int(m) for m in modes])
+        self._check(self.lib.cpq_set_eq(self.h, stream, co, act, mode, saturation, total_gain_lin))
+
+    def schedule_total_gain(self, stream: int, at_callback: int, gain_db: float):
+        self._check(self.lib.cpq_schedule_total_gain(self.h, stream, at_callback,
+                                                     self.lib.cpq_db_to_gain(C.c_float(gain_db))))
+
+    def set_epilogue(self, makeup_gain: float = 1.0, dither_bits: int = 0, uniforms: Optional[np.ndarray] = None):
+        self._check(self.lib.cpq_set_epilogue(self.h, makeup_gain, dither_bits))
+        if uniforms is not None:
+            u = np.ascontiguousarray(uniforms, dtype=np.float64)
+            assert u.shape[0] == self.n_seq and u.shape[1] % 2 == 0
+            self._check(self.lib.cpq_set_dither_uniforms(self.h, u.ctypes.data_as(_dp), u.shape[1] // 2))
+
+    def set_partition_range(self, begin: int, end: int):
+        self._check(self.lib.cpq_set_partition_range(self.h, begin, end))
+
+    def total_partitions(self) -> int:
+        return self.lib.cpq_total_partitions(self.h)
+
+    # ---- process ----
+    def process(self, x: np.ndarray, stages: int = capi.STAGE_ALL) -> np.ndarray:
+        """In place on a host array [n_seq, T] (rows = stream*n_channels + ch). H2D/D2H inside."""
+        assert x.dtype == np.float64 and x.ndim == 2 and x.shape[0] == self.n_seq and x.flags["C_CONTIGUOUS"]
+        ptrs = (_dp * self.n_seq)(*[x[i].ctypes.data_as(_dp) for i in range(self.n_seq)])
+        self._check(self.lib.cpq_process(self.h, ptrs, x.shape[1], stages))
+        return x
+
+    def process_host_ptrs(self, base_ptr: int, row_stride_doubles: int, T: int, stages: int = capi.STAGE_ALL):
+        """Same as process() for a host buffer given by address (e.g. a pinned torch tensor)."""
+        ptrs = (_dp * self.n_seq)(*[C.cast(base_ptr + 8 * i * row_stride_doubles, _dp) for i in range(self.n_seq)])
+        self._check(self.lib.cpq_process(self.h, ptrs, T, stages))
+
+    def process_device(self, data_ptr: int, stride: int, T: int, stages: int = capi.STAGE_ALL):
+        """In place on device memory [n_seq][stride] doubles (e.g. torch tensor .data_ptr())."""
+        self._check(self.lib.cpq_process_device(self.h, C.c_void_p(data_ptr), stride, T, stages))
+
+    # ---- introspection ----
+    def layout(self) -> capi.Layout:
+        out = capi.Layout()
+        self._check(self.lib.cpq_get_layout(self.h, C.byref(out)))
+        return out
+
+    def latency(self) -> int:
+        return self.lib.cpq_latency(self.h)
+
+    def timings(self) -> capi.Timings:
+        t = capi.Timings()
+        self._check(self.lib.cpq_get_timings(self.h, C.byref(t)))
+        return t
+
+    def eq_state(self, stream: int) -> np.ndarray:
+        out = np.zeros((self.cfg.n_channels, capi.NUM_BANDS, 2))
+        self._check(self.lib.cpq_get_eq_state(self.h, stream, out.ctypes.data_as(_dp)))
+        return out
+
+    def cuda_stream(self) -> int:
+        return int(self.lib.cpq_cuda_stream(self.h) or 0)
+
+    def kernel_launch_count(self) -> int:
+        return int(self.lib.cpq_kernel_launch_count(self.h))
+
+
+def plan_layout(ir_len: int, block_size: int, spec: Optional[capi.FilterSpec], n_callbacks: int):
+    """Host-only layer plan + gather plan (no device needed)."""
+    lib = capi.load()
+    out = capi.Layout()
+    src = (C.c_int64 * (2 * max(n_callbacks, 1)))()
+    st = lib.cpq_plan_layout(ir_len, block_size, C.byref(spec) if spec is not None else None, n_callbacks,
+                             C.byref(out), src)
+    if st != capi.OK:
+        raise capi.CpqError(st, "plan_layout")
+    tails = [np.array(src[i * n_callbacks:(i + 1) * n_callbacks], dtype=np.int64) for i in range(max(out.num_layers - 1, 0))]
+    return out, tails

@@ -1,0 +1,206 @@
+/*
+ * cpq.h -- C ABI of convopeq_b200: the B200 (sm_100a) implementation of ConvoPeq's DSP hot path
+ * in offline / batched form:
+ *
+ *   FP64 non-uniform partitioned overlap-save convolver  ->  20-band TPT-SVF EQ  ->  gain / dither
+ *
+ * This header is the drop-in boundary.  Each entry point names the reference interface it
+ * replaces (paths relative to the reference's src/).  Plain C types only: no torch, no C++.
+ * One handle = one CUDA device + one batch of independent stereo (or mono) streams that share a
+ * sample rate, a host block size and a layer geometry.  A handle is single-threaded; different
+ * handles are independent.  Errors are status codes (the reference's path is noexcept and reports
+ * failure as silence + counters); cpq_last_error() gives the text.  There is no CPU fallback:
+ * every compute entry point fails with CPQ_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef CPQ_H
+#define CPQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPQ_ABI_VERSION 1
+#define CPQ_NUM_BANDS 20        /* EQProcessor::NUM_BANDS, eqprocessor/EQProcessor.h:153 */
+#define CPQ_MAX_LAYERS 3        /* MKLNonUniformConvolver::kNumLayers, MKLNonUniformConvolver.h:391 */
+#define CPQ_NS_ORDER 12         /* PsychoacousticDither::NS_ORDER, PsychoacousticDither.h:60 */
+
+typedef struct cpq_engine* cpq_handle;
+
+typedef enum cpq_status
+{
+    CPQ_OK = 0,
+    CPQ_ERR_INVALID = 1,      /* bad argument (the reference returns false / silently ignores) */
+    CPQ_ERR_NOT_READY = 2,    /* process before every stream-channel has an impulse / EQ */
+    CPQ_ERR_CUDA = 3,         /* CUDA runtime error or no usable device */
+    CPQ_ERR_OOM = 4,
+    CPQ_ERR_UNSUPPORTED = 5,  /* reference feature outside the hot path (M/S modes, AGC, parallel EQ ...) */
+    CPQ_ERR_GEOMETRY = 6      /* stream-channels of one handle must share the layer geometry */
+} cpq_status;
+
+/* convo::FilterSpec, MKLNonUniformConvolver.h:123-133 (same fields, same defaults when zero-initialised
+ * through cpq_filter_spec_default). */
+typedef struct cpq_filter_spec
+{
+    double sample_rate;          /* 48000 */
+    int32_t hc_mode;             /* convo::HCMode  0 Sharp, 1 Natural (default), 2 Soft   OutputFilter.h:75 */
+    int32_t lc_mode;             /* convo::LCMode  0 Natural (default), 1 Soft             OutputFilter.h:85 */
+    int32_t tail_mode;           /* 0 air absorption, 1 layer tail contouring (default), 2 bypass */
+    int32_t tail_enabled;        /* 1 */
+    double tail_start_seconds;   /* 0.085 */
+    double tail_strength;        /* 1.0 */
+    int32_t tail_l1l2_multiplier;/* 8 */
+    int32_t reserved_;
+} cpq_filter_spec;
+
+/* EQCoeffsSVF a1,a2,a3,m0,m1,m2 (eqprocessor/EQProcessor.h:91-96) */
+typedef struct cpq_svf_coeffs
+{
+    double a1, a2, a3, m0, m1, m2;
+} cpq_svf_coeffs;
+
+/* Which reference boundary cpq_process reproduces for the convolver stage. */
+typedef enum cpq_conv_boundary
+{
+    CPQ_CONV_INNER = 0, /* MKLNonUniformConvolver Add/Get (StereoConvolver::process, ConvolverProcessor.Runtime.cpp:1159) */
+    CPQ_CONV_OUTER = 1  /* ConvolverProcessor::process at mix = 1: scrub(|x|>=1e300 or non-finite -> 0) then
+                           x * equalPowerSin(1.0) (Runtime.cpp:26-31,50-60,675,722,748) */
+} cpq_conv_boundary;
+
+/* cpq_process stage selection (DSPCore::processDouble order ConvolverThenEQ, AudioEngine.Processing.DSPCoreDouble.cpp:386-414) */
+enum
+{
+    CPQ_STAGE_CONV = 1u,      /* convolverRt().process */
+    CPQ_STAGE_EQ = 2u,        /* eqRt().process(block, params, cache) */
+    CPQ_STAGE_EPILOGUE = 4u,  /* makeup gain (:465-469) + processOutputDouble headroom / dither (:581,:644-663) */
+    CPQ_STAGE_ALL = 7u
+};
+
+typedef struct cpq_config
+{
+    int32_t device;        /* CUDA ordinal */
+    int32_t n_streams;     /* independent streams in the batch */
+    int32_t n_channels;    /* channels per stream: 1 or 2 (the reference engine is <= 2 channels) */
+    int32_t block_size;    /* host callback size the reference would run with (power of two, 64..8192) */
+    double sample_rate;
+    int64_t max_samples;   /* capacity per channel for one cpq_process call (multiple of block_size) */
+    int32_t conv_boundary; /* cpq_conv_boundary */
+    int32_t shared_ir;     /* 1: one IR pair (per channel) shared by all streams */
+    int32_t shared_eq;     /* 1: one EQ setting shared by all streams */
+    int32_t reserved_;
+    size_t workspace_bytes;/* upper bound for the per-call spectra workspace; 0 = default (4 GiB) */
+} cpq_config;
+
+/* cpq_get_layout: what SetImpulse decided (MKLNonUniformConvolver.cpp:738-758,988-994,1004-1024) plus the
+ * effective tail delay D = first output sample at which the layer contributes. */
+typedef struct cpq_layer_layout
+{
+    int32_t part_size, fft_size, num_parts_ir, num_parts, parts_per_callback, output_delay_samples;
+    int32_t ir_offset, ir_len;
+    int64_t first_output_sample;  /* -1 if the layer never contributes within max_samples */
+    int64_t skipped_callbacks;    /* callbacks in which delayLineReadAdd skipped this layer after it first spoke */
+    double gain;                  /* m_tailLayerGain */
+} cpq_layer_layout;
+
+typedef struct cpq_layout
+{
+    int32_t num_layers;
+    int32_t latency;              /* getLatency(): L0 partition size (reported, not the real onset) */
+    cpq_layer_layout layers[CPQ_MAX_LAYERS];
+} cpq_layout;
+
+typedef struct cpq_timings
+{
+    float h2d_ms, fft_fwd_ms, mac_ms, fft_inv_ms, eq_ms, d2h_ms, total_ms;
+    int32_t kernel_launches;
+    int32_t reserved_;
+} cpq_timings;
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+int cpq_abi_version(void);
+const char* cpq_status_string(cpq_status s);
+const char* cpq_last_error(cpq_handle h);
+void cpq_filter_spec_default(cpq_filter_spec* out);   /* FilterSpec{} defaults */
+void cpq_config_default(cpq_config* out);
+
+/* ConvolverProcessor::prepareToPlay(sr, block) + EQProcessor::prepareToPlay(sr, maxBlock)
+ * (convolver/ConvolverProcessor.Lifecycle.cpp:211, eqprocessor/EQProcessor.Core.cpp:679). */
+cpq_status cpq_create(const cpq_config* cfg, cpq_handle* out);
+void cpq_destroy(cpq_handle h);
+
+/* MKLNonUniformConvolver::Reset (MKLNonUniformConvolver.cpp:1693) + EQ state clear + dither state clear. */
+cpq_status cpq_reset(cpq_handle h);
+
+/* ---- prepare ----------------------------------------------------------------------------- */
+/* MKLNonUniformConvolver::SetImpulse(impulse, irLen, blockSize, scale, enableDirectHead=false, filterSpec)
+ * (MKLNonUniformConvolver.h:197-200, .cpp:610-1149).  `ir` is borrowed (copied).  spec == NULL is the
+ * reference's nullptr.  stream = -1 with cfg.shared_ir sets the channel's IR for every stream. */
+cpq_status cpq_set_impulse(cpq_handle h, int stream, int channel, const double* ir, int ir_len, double scale,
+                           const cpq_filter_spec* spec);
+
+/* EQCoeffCache + EQParameters as consumed by EQProcessor::process(block, params, cache)
+ * (eqprocessor/EQProcessor.h:121-138, ProcessingCache.cpp:56-96, Processing.cpp:1019-1276), Serial structure,
+ * AGC off.  chan_mode: 0 Stereo, 1 Left, 2 Right (>= 3 = Mid/Side -> CPQ_ERR_UNSUPPORTED).
+ * saturation is the already-promoted double, e.g. (double)0.2f.  total_gain_lin is
+ * Decibels::decibelsToGain((double)totalGainDb) (settled LinearRamp). stream = -1 with cfg.shared_eq. */
+cpq_status cpq_set_eq(cpq_handle h, int stream, const cpq_svf_coeffs coeffs[CPQ_NUM_BANDS],
+                      const uint8_t active[CPQ_NUM_BANDS], const int32_t chan_mode[CPQ_NUM_BANDS],
+                      double saturation, double total_gain_lin);
+
+/* EQProcessor::setTotalGain at a callback boundary (EQProcessor.Parameters.cpp:109): from callback index
+ * `at_callback` of the next cpq_process the total gain ramps to new_gain_lin over 50 ms
+ * (LinearRamp, DspNumericPolicy.h:319-421; Processing.cpp:1262-1274). */
+cpq_status cpq_schedule_total_gain(cpq_handle h, int stream, int64_t at_callback, double new_gain_lin);
+
+/* outputMakeupGain (DSPCoreDouble.cpp:465-469), kOutputHeadroom / dither (:581,:644-663,
+ * PsychoacousticDither.h:192-355).  dither_bits <= 0: y *= makeup * 0.8912509381337456.
+ * dither_bits > 0: uniforms must hold 2*T doubles per stream-channel, planar
+ * [stream*n_channels + ch][2*T] (u1,u2 per sample) on the host; they are the injected replacement of the
+ * reference's MKL VSL ring. */
+cpq_status cpq_set_epilogue(cpq_handle h, double makeup_gain, int dither_bits);
+cpq_status cpq_set_dither_uniforms(cpq_handle h, const double* uniforms, int64_t samples_per_channel);
+
+/* EQProcessor::calcSVFCoeffs (eqprocessor/EQProcessor.Coefficients.cpp:101-130,431-618), host-side:
+ * float parameters clamped then promoted to double exactly like the reference.
+ * type: 0 LowShelf 1 Peaking 2 HighShelf 3 LowPass 4 HighPass. */
+cpq_status cpq_design_band(int type, float freq_hz, float gain_db, float q, double sample_rate, cpq_svf_coeffs* out);
+double cpq_db_to_gain(float db);            /* juce::Decibels::decibelsToGain<double>((double)db) */
+double cpq_equal_power_sin(double x);       /* ConvolverProcessor.Runtime.cpp:26-31 */
+
+/* ---- process ----------------------------------------------------------------------------- */
+/* In place, planar, host buffers: planar[stream*n_channels + ch] points at T doubles.  Equivalent to the
+ * reference running T/block_size callbacks of DSPCore::processDouble's conv -> EQ -> output chain on each
+ * stream from a reset state.  T must be a multiple of block_size and <= max_samples.  H2D and D2H copies
+ * are part of the call. */
+cpq_status cpq_process(cpq_handle h, double* const* planar, int64_t T, unsigned stages);
+
+/* Same, data already resident: d_io is a device pointer to [n_streams*n_channels][stride] doubles. */
+cpq_status cpq_process_device(cpq_handle h, double* d_io, int64_t stride, int64_t T, unsigned stages);
+
+/* Partition-range sharding for very long IRs (cfg 5): only layers/partitions in
+ * [part_begin, part_end) of the flattened (layer, partition) list contribute to the convolver sum.
+ * cpq_process_device(..., CPQ_STAGE_CONV) then yields this rank's partial y; the caller reduces the
+ * partials (NCCL) and runs the remaining stages with cpq_process_device(..., CPQ_STAGE_EQ|EPILOGUE). */
+cpq_status cpq_set_partition_range(cpq_handle h, int part_begin, int part_end);
+int cpq_total_partitions(cpq_handle h);
+
+/* ---- introspection ----------------------------------------------------------------------- */
+cpq_status cpq_get_layout(cpq_handle h, cpq_layout* out);
+int cpq_latency(cpq_handle h);                       /* getLatency(), MKLNonUniformConvolver.cpp:1055 */
+cpq_status cpq_get_timings(cpq_handle h, cpq_timings* out);   /* CUDA-event times of the last cpq_process */
+cpq_status cpq_get_eq_state(cpq_handle h, int stream, double* out /* [n_channels][20][2] ic1eq, ic2eq */);
+void* cpq_cuda_stream(cpq_handle h);                 /* cudaStream_t the kernels are launched on */
+int64_t cpq_kernel_launch_count(cpq_handle h);       /* launches since create */
+
+/* Host-only: the layer plan + per-callback gather plan without a device (used by tests and by
+ * INTEGRATION.md's binding to validate geometry). src_offsets (nullable) receives, for each layer >= 1 and
+ * each of n_callbacks callbacks, the delay-line stream position read (or -1 = skipped), layer-major. */
+cpq_status cpq_plan_layout(int ir_len, int block_size, const cpq_filter_spec* spec, int64_t n_callbacks,
+                           cpq_layout* out, int64_t* src_offsets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPQ_H */

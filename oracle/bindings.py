@@ -1,0 +1,302 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes bindings for the two CPU checkers under oracle/.
+
+* ``Oracle``  -> oracle/libcpq_oracle.so  (our C restatement, oracle/cpq_oracle.c; always buildable)
+* ``Ref``     -> oracle/_ref/libcpq_ref.so (the reference's own TUs compiled in place; exists only when
+  it was built where /root/reference is mounted -- the prebuilt .so travels to the GPU box)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+Both classes expose the same small surface so a test can run either as "the reference".
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libcpq_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libcpq_ref.so")
+REFERENCE_ROOT = os.environ.get("CONVOPEQ_REF", "/root/reference")
+
+_dp = C.POINTER(C.c_double)
+
+
+def _p(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_dp)
+
+
+class FilterSpec(C.Structure):
+    """Mirror of convo::FilterSpec (MKLNonUniformConvolver.h:123-133), defaults included."""
+
+    _fields_ = [
+        ("sample_rate", C.c_double),
+        ("hc_mode", C.c_int),
+        ("lc_mode", C.c_int),
+        ("tail_mode", C.c_int),
+        ("tail_enabled", C.c_int),
+        ("tail_start_seconds", C.c_double),
+        ("tail_strength", C.c_double),
+        ("tail_l1l2_multiplier", C.c_int),
+    ]
+
+    def __init__(self, sample_rate=48000.0, hc_mode=1, lc_mode=0, tail_mode=1, tail_enabled=1,
+                 tail_start_seconds=0.085, tail_strength=1.0, tail_l1l2_multiplier=8):
+        super().__init__(sample_rate, hc_mode, lc_mode, tail_mode, tail_enabled, tail_start_seconds,
+                         tail_strength, tail_l1l2_multiplier)
+
+
+class EqBand(C.Structure):
+    _fields_ = [("frequency", C.c_float), ("gain_db", C.c_float), ("q", C.c_float),
+                ("enabled", C.c_int), ("type", C.c_int), ("channel_mode", C.c_int)]
+
+
+def build(verbose: bool = False) -> None:
+    """Compile the checkers (oracle always; _ref only where the reference tree is mounted)."""
+    env = dict(os.environ, CONVOPEQ_REF=REFERENCE_ROOT)
+    out = subprocess.run(["make", "-C", HERE, "all", f"CONVOPEQ_REF={REFERENCE_ROOT}"], env=env,
+                         capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:], out.stderr[-4000:])
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed")
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def have_oracle() -> bool:
+    return os.path.exists(ORACLE_SO)
+
+
+class _Base:
+    prefix = ""
+    lib: C.CDLL
+
+    # ---- convolver -------------------------------------------------------------------------
+    def nuc_run(self, ir: np.ndarray, x: np.ndarray, block: int, scale: float = 1.0,
+                spec: Optional[FilterSpec] = None, call: Optional[int] = None):
+        """SetImpulse + (Add, Get) loop over x in calls of `call` (default = block) samples."""
+        ir = np.ascontiguousarray(ir, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros_like(x)
+        h = self._nuc_create()
+        try:
+            ok = self._nuc_set_impulse(h, ir, block, scale, spec)
+            if not ok:
+                raise RuntimeError("SetImpulse failed")
+            layout = self._nuc_layout(h)
+            self._f("nuc_process")(h, _p(x), _p(y), x.size, int(call or block))
+        finally:
+            self._f("nuc_destroy")(h)
+        return y, layout
+
+    def nuc_layout_only(self, ir_len: int, block: int, spec: Optional[FilterSpec] = None):
+        ir = np.zeros(ir_len)
+        ir[0] = 1.0
+        h = self._nuc_create()
+        try:
+            if not self._nuc_set_impulse(h, ir, block, 1.0, spec):
+                raise RuntimeError("SetImpulse failed")
+            return self._nuc_layout(h)
+        finally:
+            self._f("nuc_destroy")(h)
+
+    def nuc_spectra(self, ir: np.ndarray, block: int, scale: float = 1.0, spec: Optional[FilterSpec] = None):
+        """Stored partition spectra per layer, list of complex arrays [numParts][P+1] in reference order."""
+        ir = np.ascontiguousarray(ir, dtype=np.float64)
+        h = self._nuc_create()
+        try:
+            if not self._nuc_set_impulse(h, ir, block, scale, spec):
+                raise RuntimeError("SetImpulse failed")
+            layout = self._nuc_layout(h)
+            out = []
+            for li, lay in enumerate(layout["layers"]):
+                cs = lay["part_size"] + 1
+                arr = np.zeros((lay["num_parts"], cs), dtype=np.complex128)
+                re = np.zeros(cs)
+                im = np.zeros(cs)
+                for p in range(lay["num_parts"]):
+                    n = self._f("nuc_ir_spectrum")(h, li, p, _p(re), _p(im))
+                    assert n == cs
+                    arr[p] = re + 1j * im
+                out.append(arr)
+            return out, layout
+        finally:
+            self._f("nuc_destroy")(h)
+
+    def _f(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def _nuc_create(self):
+        return self._f("nuc_create")()
+
+    def _nuc_layout(self, h):
+        lay = (C.c_int * 24)()
+        g = (C.c_double * 3)()
+        n = self._f("nuc_layout")(h, lay, g)
+        keys = ["part_size", "num_parts_ir", "num_parts", "parts_per_callback", "output_delay_samples",
+                "delay_capacity", "is_immediate", "fft_size"]
+        return {"num_layers": n, "gains": [g[i] for i in range(3)],
+                "layers": [dict(zip(keys, [lay[l * 8 + i] for i in range(8)])) for l in range(n)]}
+
+    # ---- EQ ----------------------------------------------------------------------------------
+    def eq_design(self, type_: int, f: float, gain_db: float, q: float, sr: float) -> np.ndarray:
+        out = np.zeros(6)
+        self._f("eq_design")(int(type_), C.c_float(f), C.c_float(gain_db), C.c_float(q), C.c_double(sr), _p(out))
+        return out
+
+
+def _common_sigs(lib, pre, nuc_set_impulse_extra):
+    vp = C.c_void_p
+    f = lambda n: getattr(lib, pre + n)
+    f("nuc_create").restype = vp
+    f("nuc_destroy").argtypes = [vp]
+    f("nuc_destroy").restype = None
+    f("nuc_process").argtypes = [vp, _dp, _dp, C.c_long, C.c_int]
+    f("nuc_process").restype = None
+    f("nuc_layout").argtypes = [vp, C.POINTER(C.c_int), _dp]
+    f("nuc_ir_spectrum").argtypes = [vp, C.c_int, C.c_int, _dp, _dp]
+    f("eq_design").argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_double, _dp]
+    f("eq_design").restype = None
+
+
+class Oracle(_Base):
+    """Our C restatement (oracle/cpq_oracle.c)."""
+
+    prefix = "cpqo_"
+    kind = "port"
+
+    def __init__(self):
+        if not have_oracle():
+            build()
+        self.lib = C.CDLL(ORACLE_SO)
+        L = self.lib
+        _common_sigs(L, self.prefix, None)
+        L.cpqo_nuc_set_impulse.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, C.c_double, C.POINTER(FilterSpec)]
+        L.cpqo_eq_create.restype = C.c_void_p
+        L.cpqo_eq_create.argtypes = [C.c_double, C.c_float]
+        L.cpqo_eq_destroy.argtypes = [C.c_void_p]
+        L.cpqo_eq_set_band.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_int]
+        L.cpqo_eq_set_saturation.argtypes = [C.c_void_p, C.c_float]
+        L.cpqo_eq_set_total_gain.argtypes = [C.c_void_p, C.c_float]
+        L.cpqo_eq_process.argtypes = [C.c_void_p, _dp, _dp, C.c_long, C.c_int]
+        L.cpqo_eq_get_state.argtypes = [C.c_void_p, _dp]
+        L.cpqo_epilogue.argtypes = [_dp, C.c_long, C.c_double, C.c_double, C.c_int, _dp, _dp, _dp]
+        L.cpqo_epilogue.restype = None
+        L.cpqo_outer_wet.argtypes = [_dp, C.c_long, C.c_double]
+        L.cpqo_outer_wet.restype = None
+        L.cpqo_equal_power_sin.argtypes = [C.c_double]
+        L.cpqo_equal_power_sin.restype = C.c_double
+        L.cpqo_db_to_gain.argtypes = [C.c_float]
+        L.cpqo_db_to_gain.restype = C.c_double
+        L.cpqo_dither_coeffs.argtypes = [C.c_double, C.c_int, _dp]
+
+    def _nuc_set_impulse(self, h, ir, block, scale, spec):
+        return self.lib.cpqo_nuc_set_impulse(h, _p(ir), ir.size, block, scale, C.byref(spec) if spec is not None else None)
+
+    def eq_run(self, bands: Sequence[EqBand], xl: np.ndarray, xr: Optional[np.ndarray], sr: float, block: int,
+               saturation: float = 0.2, total_gain_db: float = 0.0, gain_change_db: Optional[float] = None,
+               gain_change_at: int = 0):
+        """createCoeffCache + process(block, params, cache) over the signal; returns (L, R, state[2][20][2])."""
+        L = self.lib
+        e = L.cpqo_eq_create(sr, C.c_float(total_gain_db))
+        try:
+            for i, b in enumerate(bands):
+                active = bool(b.enabled) and sr > 0
+                co = self.eq_design(b.type, b.frequency, b.gain_db, b.q, sr) if active else np.zeros(6)
+                L.cpqo_eq_set_band(e, i, _p(co), int(active), int(b.channel_mode))
+            L.cpqo_eq_set_saturation(e, C.c_float(saturation))
+            l = np.ascontiguousarray(xl, dtype=np.float64).copy()
+            r = None if xr is None else np.ascontiguousarray(xr, dtype=np.float64).copy()
+            if gain_change_db is None:
+                rc = L.cpqo_eq_process(e, _p(l), _p(r), l.size, block)
+            else:
+                rc = L.cpqo_eq_process(e, _p(l[:gain_change_at]), _p(r[:gain_change_at]) if r is not None else None,
+                                       gain_change_at, block)
+                L.cpqo_eq_set_total_gain(e, C.c_float(gain_change_db))
+                l2 = l[gain_change_at:]
+                r2 = None if r is None else r[gain_change_at:]
+                rc |= L.cpqo_eq_process(e, _p(l2), _p(r2), l2.size, block)
+            if rc != 0:
+                raise RuntimeError("EQ oracle: unsupported channel mode")
+            st = np.zeros((2, 20, 2))
+            L.cpqo_eq_get_state(e, _p(st))
+        finally:
+            L.cpqo_eq_destroy(e)
+        return l, r, st
+
+    def epilogue(self, x: np.ndarray, makeup_gain: float, sr: float, bit_depth: int,
+                 uniforms: Optional[np.ndarray] = None):
+        d = np.ascontiguousarray(x, dtype=np.float64).copy()
+        z = np.zeros(12)
+        tmp = np.zeros_like(d)
+        self.lib.cpqo_epilogue(_p(d), d.size, makeup_gain, sr, bit_depth, _p(uniforms), _p(z), _p(tmp))
+        return d, tmp, z
+
+    def outer_wet(self, x: np.ndarray, mix: float = 1.0) -> np.ndarray:
+        d = np.ascontiguousarray(x, dtype=np.float64).copy()
+        self.lib.cpqo_outer_wet(_p(d), d.size, mix)
+        return d
+
+
+class Ref(_Base):
+    """The reference's own code (oracle/_ref/libcpq_ref.so)."""
+
+    prefix = "cpqref_"
+    kind = "reference"
+
+    def __init__(self):
+        if not have_ref():
+            raise FileNotFoundError(REF_SO)
+        self.lib = C.CDLL(REF_SO)
+        L = self.lib
+        _common_sigs(L, self.prefix, None)
+        L.cpqref_nuc_set_impulse.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(FilterSpec)]
+        L.cpqref_eq_create.restype = C.c_void_p
+        L.cpqref_eq_create.argtypes = [C.c_double, C.c_int, C.c_float]
+        L.cpqref_eq_destroy.argtypes = [C.c_void_p]
+        L.cpqref_eq_set_params.argtypes = [C.c_void_p, C.POINTER(EqBand), C.c_float, C.c_int, C.c_int]
+        L.cpqref_eq_set_total_gain.argtypes = [C.c_void_p, C.c_float]
+        L.cpqref_eq_process.argtypes = [C.c_void_p, _dp, _dp, C.c_long, C.c_int]
+        L.cpqref_eq_get_state.argtypes = [C.c_void_p, _dp]
+
+    def _nuc_set_impulse(self, h, ir, block, scale, spec):
+        return self.lib.cpqref_nuc_set_impulse(h, _p(ir), ir.size, block, scale, 0,
+                                               C.byref(spec) if spec is not None else None)
+
+    def eq_run(self, bands: Sequence[EqBand], xl, xr, sr, block, saturation=0.2, total_gain_db=0.0,
+               gain_change_db=None, gain_change_at=0):
+        L = self.lib
+        e = L.cpqref_eq_create(sr, max(block, 1), C.c_float(total_gain_db))
+        try:
+            arr = (EqBand * 20)(*bands)
+            if not L.cpqref_eq_set_params(e, arr, C.c_float(saturation), 0, 0):
+                raise RuntimeError("createCoeffCache failed")
+            l = np.ascontiguousarray(xl, dtype=np.float64).copy()
+            r = None if xr is None else np.ascontiguousarray(xr, dtype=np.float64).copy()
+            if gain_change_db is None:
+                L.cpqref_eq_process(e, _p(l), _p(r), l.size, block)
+            else:
+                L.cpqref_eq_process(e, _p(l[:gain_change_at]), _p(r[:gain_change_at]) if r is not None else None,
+                                    gain_change_at, block)
+                L.cpqref_eq_set_total_gain(e, C.c_float(gain_change_db))
+                l2 = l[gain_change_at:]
+                r2 = None if r is None else r[gain_change_at:]
+                L.cpqref_eq_process(e, _p(l2), _p(r2), l2.size, block)
+            st = np.zeros((2, 20, 2))
+            L.cpqref_eq_get_state(e, _p(st))
+        finally:
+            L.cpqref_eq_destroy(e)
+        return l, r, st
+
+
+def best_checker():
+    """The strongest checker available: the real reference if it was compiled, else the restatement."""
+    return Ref() if have_ref() else Oracle()

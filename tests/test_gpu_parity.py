@@ -1,0 +1,222 @@
+"""GPU parity: the CUDA path through the C ABI against the checker (the compiled reference when
+oracle/_ref exists, else the C restatement) on the same seeded inputs.  Tolerance: max abs error
+<= 1e-10 of full scale (BASELINE.json north_star); onset positions sample-exact."""
+import numpy as np
+import pytest
+
+from convopeq_b200 import capi
+from convopeq_b200.engine import ConvoPeqEngine
+from oracle.bindings import FilterSpec as OFilterSpec
+from tests import signals
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _specs(kw):
+    if kw is None:
+        return None, None
+    return OFilterSpec(**kw), capi.default_filter_spec(**kw)
+
+
+def _run_conv(ir_l, ir_r, x, block, sr, kw, boundary=capi.CONV_INNER, scale=1.0):
+    ospec, cspec = _specs(kw)
+    T = x.shape[1]
+    eng = ConvoPeqEngine(n_streams=1, n_channels=2, sample_rate=sr, block_size=block, max_samples=T, conv_boundary=boundary)
+    eng.set_impulse(0, 0, ir_l, scale, cspec)
+    eng.set_impulse(0, 1, ir_r, scale, cspec)
+    y = x.copy()
+    eng.process(y, capi.STAGE_CONV)
+    lay = eng.layout()
+    eng.close()
+    return y, lay, ospec
+
+
+CONV_CASES = [
+    # (ir_len, block, T, sr, spec kwargs)            config
+    (4096, 512, 16384, 48000.0, None),               # single layer == linear convolution
+    (65536, 512, 65536, 48000.0, None),              # cfg1a: L0 12x512 + L1 15x4096, D1 7168, g1 1.4375
+    (65536, 512, 65536, 48000.0, {}),                # cfg1a with the production default FilterSpec
+    (131072, 512, 49152, 48000.0, {}),               # cfg4 geometry
+    (65536, 256, 32768, 48000.0, {}),                # three layers 256/2048/16384 -> needs P=16384: skipped below
+    (65536, 64, 16384, 48000.0, None),               # three layers 64/512/4096
+    (65536, 1024, 131072, 48000.0, None),            # irregular plan: drops + starves
+    (2047, 256, 4096, 48000.0, None), (2048, 256, 4096, 48000.0, None), (2049, 256, 4096, 48000.0, None),
+    (70000, 512, 65536, 48000.0, dict(tail_mode=0, tail_start_seconds=0.03)),   # air absorption tilt
+    (70000, 512, 32768, 48000.0, dict(tail_mode=2)),
+    (262144, 512, 98304, 96000.0, dict(sample_rate=96000.0)),                   # cfg3 geometry
+]
+
+
+@pytest.mark.parametrize("ir_len,block,T,sr,kw", CONV_CASES)
+def test_convolver_matches_reference(checker, ir_len, block, T, sr, kw):
+    from convopeq_b200.engine import plan_layout
+    lay, _ = plan_layout(ir_len, block, capi.default_filter_spec(**kw) if kw is not None else None, 8)
+    if any(lay.layers[i].part_size > 8192 for i in range(lay.num_layers)):
+        pytest.skip("partition > 8192 not built yet")
+    ir_l, ir_r = signals.synth_ir(ir_len, 2), signals.synth_ir(ir_len, 3)
+    x = np.stack([signals.noise(T, 1), signals.noise(T, 11)])
+    y, _, ospec = _run_conv(ir_l, ir_r, x, block, sr, kw)
+    for ch, ir in enumerate((ir_l, ir_r)):
+        want, _ = checker.nuc_run(ir, x[ch], block, spec=ospec)
+        err = np.abs(y[ch] - want).max()
+        assert err <= TOL, (ch, err)
+
+
+def test_impulse_onsets_are_sample_exact(checker):
+    """delta at n=0 and n=B-1: the layout (L0 at 0 latency, tails at D_l with gain g_l) is sample exact."""
+    ir_len, block, T = 65536, 512, 90112
+    ir = signals.synth_ir(ir_len, 5)
+    for at in (0, block - 1):
+        x = np.stack([signals.impulse(T, at), signals.silence_then_step(T, 1000)])
+        y, lay, _ = _run_conv(ir, ir, x, block, 48000.0, None)
+        want0, _ = checker.nuc_run(ir, x[0], block)
+        want1, _ = checker.nuc_run(ir, x[1], block)
+        assert np.abs(y[0] - want0).max() <= TOL and np.abs(y[1] - want1).max() <= TOL
+        nz_got = np.flatnonzero(np.abs(y[0]) > 1e-13)
+        nz_want = np.flatnonzero(np.abs(want0) > 1e-13)
+        assert nz_got[0] == nz_want[0] == at
+        assert lay.layers[1].first_output_sample == 7168
+
+
+def test_outer_boundary_wet_gain(checker, oracle):
+    ir = signals.synth_ir(8192, 4)
+    T = 16384
+    x = np.stack([signals.noise(T, 1), signals.noise(T, 2)])
+    y, _, _ = _run_conv(ir, ir, x, 512, 48000.0, None, boundary=capi.CONV_OUTER)
+    want, _ = checker.nuc_run(ir, x[0], 512)
+    want = oracle.outer_wet(want, 1.0)
+    assert np.abs(y[0] - want).max() <= TOL
+
+
+def test_ir_scale(checker):
+    ir = signals.synth_ir(20000, 4)
+    T = 16384
+    x = np.stack([signals.noise(T, 1), signals.noise(T, 2)])
+    y, _, _ = _run_conv(ir, ir, x, 512, 48000.0, {}, scale=0.37)
+    want, _ = checker.nuc_run(ir, x[1], 512, scale=0.37, spec=OFilterSpec())
+    assert np.abs(y[1] - want).max() <= TOL
+
+
+EQ_CASES = [
+    ("default", dict(seed=7), dict()),
+    ("sat0", dict(seed=7), dict(saturation=0.0)),
+    ("stress_q20", dict(seed=7, stress=True), dict()),
+    ("modes", dict(seed=8, modes=[i % 3 for i in range(20)]), dict()),
+    ("types", dict(seed=9, types=[i % 5 for i in range(20)]), dict()),
+    ("disabled", dict(seed=10, enabled=[i % 2 for i in range(20)]), dict()),
+    ("gain", dict(seed=7), dict(total_gain_db=-3.0)),
+]
+
+
+@pytest.mark.parametrize("name,bkw,kw", EQ_CASES)
+@pytest.mark.parametrize("T", [4096 * 3 + 512, 96000])
+def test_eq_matches_reference(checker, name, bkw, kw, T):
+    sr, block = 48000.0, 512
+    T = T // block * block
+    params = signals.band_params(**bkw)
+    xl, xr = signals.log_sweep(T, sr)
+    eng = ConvoPeqEngine(1, 2, sr, block, T)
+    eng.set_eq(0, signals.to_band(params), kw.get("saturation", 0.2), kw.get("total_gain_db", 0.0))
+    y = np.stack([xl, xr]).copy()
+    eng.process(y, capi.STAGE_EQ)
+    state = eng.eq_state(0)
+    eng.close()
+    wl, wr, wstate = checker.eq_run(signals.to_eqband(params), xl, xr, sr, block, **kw)
+    assert np.abs(y[0] - wl).max() <= TOL and np.abs(y[1] - wr).max() <= TOL
+    assert np.abs(state - wstate).max() <= 1e-9
+
+
+def test_eq_mono_stream(checker):
+    sr, block, T = 48000.0, 512, 40960
+    params = signals.band_params(seed=12, modes=[i % 3 for i in range(20)])
+    xl, _ = signals.log_sweep(T, sr)
+    eng = ConvoPeqEngine(1, 1, sr, block, T)
+    eng.set_eq(0, signals.to_band(params))
+    y = xl[None, :].copy()
+    eng.process(y, capi.STAGE_EQ)
+    eng.close()
+    wl, _, _ = checker.eq_run(signals.to_eqband(params), xl, None, sr, block)
+    assert np.abs(y[0] - wl).max() <= TOL
+
+
+def test_eq_total_gain_ramp(checker):
+    sr, block, T = 48000.0, 512, 512 * 60
+    params = signals.band_params(seed=7)
+    xl, xr = signals.log_sweep(T, sr)
+    eng = ConvoPeqEngine(1, 2, sr, block, T)
+    eng.set_eq(0, signals.to_band(params), 0.2, 0.0)
+    eng.schedule_total_gain(0, 20, -6.0)
+    y = np.stack([xl, xr]).copy()
+    eng.process(y, capi.STAGE_EQ)
+    eng.close()
+    wl, wr, _ = checker.eq_run(signals.to_eqband(params), xl, xr, sr, block, gain_change_db=-6.0, gain_change_at=20 * block)
+    assert np.abs(y[0] - wl).max() <= TOL and np.abs(y[1] - wr).max() <= TOL
+
+
+def test_full_chain_batch_of_streams(checker, oracle):
+    """cfg4 in miniature: several streams, distinct IRs and EQs, conv -> EQ -> makeup + headroom."""
+    sr, block, T, n_streams, ir_len = 48000.0, 512, 32768, 5, 131072
+    eng = ConvoPeqEngine(n_streams, 2, sr, block, T, conv_boundary=capi.CONV_OUTER)
+    x = np.stack([signals.noise(T, 100 + i) for i in range(2 * n_streams)])
+    irs = [signals.synth_ir(ir_len, 200 + i) for i in range(2 * n_streams)]
+    cspec, ospec = capi.default_filter_spec(), OFilterSpec()
+    for s in range(n_streams):
+        for ch in range(2):
+            eng.set_impulse(s, ch, irs[2 * s + ch], 1.0, cspec)
+        eng.set_eq(s, signals.to_band(signals.band_params(300 + s)))
+    eng.set_epilogue(makeup_gain=1.3, dither_bits=0)
+    y = x.copy()
+    eng.process(y, capi.STAGE_ALL)
+    t = eng.timings()
+    assert t.kernel_launches >= 7
+    eng.close()
+    for s in range(n_streams):
+        w = []
+        for ch in range(2):
+            c, _ = checker.nuc_run(irs[2 * s + ch], x[2 * s + ch], block, spec=ospec)
+            w.append(oracle.outer_wet(c, 1.0))
+        wl, wr, _ = checker.eq_run(signals.to_eqband(signals.band_params(300 + s)), w[0], w[1], sr, block)
+        for ch, wv in enumerate((wl, wr)):
+            want, _, _ = oracle.epilogue(wv, 1.3, sr, 0)
+            assert np.abs(y[2 * s + ch] - want).max() <= TOL, (s, ch)
+
+
+def test_dither_epilogue(oracle):
+    """Injected uniforms: pre-quantiser value within 1e-10, quantised output judged in LSB flips."""
+    sr, block, T, bits = 48000.0, 512, 8192, 24
+    x = np.stack([signals.noise(T, 1, 0.3), signals.noise(T, 2, 0.3)])
+    u = np.random.default_rng(5).random((2, 2 * T))
+    eng = ConvoPeqEngine(1, 2, sr, block, T)
+    eng.set_epilogue(0.9, bits, u)
+    y = x.copy()
+    eng.process(y, capi.STAGE_EPILOGUE)
+    eng.close()
+    lsb = 1.0 / 2 ** (bits - 1)
+    for ch in range(2):
+        want, tmp, _ = oracle.epilogue(x[ch], 0.9, sr, bits, u[ch])
+        flips = np.count_nonzero(np.abs(y[ch] - want) > 0.25 * lsb)
+        assert flips == 0, flips
+        assert np.abs(y[ch] - tmp).max() <= lsb      # quantised within one step of the pre-quantiser value
+
+
+def test_partition_range_partials_sum_to_full(checker):
+    """cfg5 in miniature: the convolver is linear in the IR, so rank partials over partition ranges add up."""
+    ir_len, block, T = 131072, 512, 32768
+    ir = signals.synth_ir(ir_len, 9)
+    x = np.stack([signals.noise(T, 1), signals.noise(T, 2)])
+    eng = ConvoPeqEngine(1, 2, 48000.0, block, T)
+    eng.set_impulse(0, 0, ir)
+    eng.set_impulse(0, 1, ir)
+    total = eng.total_partitions()
+    acc = np.zeros_like(x)
+    ranks = 4
+    for r in range(ranks):
+        b, e = total * r // ranks, total * (r + 1) // ranks
+        eng.set_partition_range(b, e)
+        y = x.copy()
+        eng.process(y, capi.STAGE_CONV)
+        acc += y
+    eng.close()
+    want, _ = checker.nuc_run(ir, x[0], block)
+    assert np.abs(acc[0] - want).max() <= TOL

@@ -1,0 +1,120 @@
+"""CPU tests of the host logic behind the C ABI: the library loads and exports what include/cpq.h declares,
+the layer plan equals the reference's, and the offline formulation (plain block convolution per layer + the
+gather plan) reproduces the callback-by-callback state machine. No compute entry point is called."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+
+from convopeq_b200 import capi
+from convopeq_b200.engine import plan_layout, design_band, Band
+from oracle.bindings import FilterSpec as OFilterSpec
+from tests import signals
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.load()
+    header = open(capi.lib_path().replace("convopeq_b200/libcpq.so", "include/cpq.h")).read()
+    declared = set(re.findall(r"\b(cpq_[a-z_0-9]+)\s*\(", header))
+    declared -= {"cpq_filter_spec_default"} - set(capi.EXPORTS)
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+    for name in capi.EXPORTS:
+        assert hasattr(L, name), name
+    assert L.cpq_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """Without a device every compute path must fail loudly (CPQ_ERR_CUDA), never compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = capi.load()
+    cfg = capi.Config()
+    L.cpq_config_default(C.byref(cfg))
+    h = C.c_void_p()
+    st = L.cpq_create(C.byref(cfg), C.byref(h))
+    assert st == capi.ERR_CUDA and not h.value
+    assert b"no CPU fallback" in L.cpq_last_error(None)
+
+
+def _spec_pair(**kw):
+    o = OFilterSpec(**kw)
+    c = capi.default_filter_spec(**kw)
+    return o, c
+
+
+PLAN_CASES = [
+    (4096, 512, None), (65536, 512, None), (131072, 512, None), (262144, 512, dict(sample_rate=96000.0)),
+    (2097152, 512, dict(sample_rate=192000.0)), (65536, 256, {}), (65536, 64, None), (65536, 1024, None),
+    (65536, 128, dict(sample_rate=44100.0)), (2047, 256, None), (2048, 256, None), (2049, 256, None),
+    (70000, 512, dict(tail_mode=0, tail_start_seconds=0.03)), (70000, 512, dict(tail_mode=2)),
+    (70000, 512, dict(tail_enabled=0)), (300000, 512, dict(tail_l1l2_multiplier=16)),
+    (300000, 512, dict(tail_l1l2_multiplier=2, tail_strength=1.7)), (100, 512, None), (1, 64, None),
+]
+
+
+@pytest.mark.parametrize("ir_len,block,kw", PLAN_CASES)
+def test_layer_plan_matches_checker(checker, ir_len, block, kw):
+    ospec = cspec = None
+    if kw is not None:
+        ospec, cspec = _spec_pair(**kw)
+    want = checker.nuc_layout_only(ir_len, block, ospec)
+    got, _ = plan_layout(ir_len, block, cspec, 8)
+    assert got.num_layers == want["num_layers"]
+    for li in range(got.num_layers):
+        g, w = got.layers[li], want["layers"][li]
+        assert (g.part_size, g.fft_size, g.num_parts_ir, g.num_parts, g.parts_per_callback, g.output_delay_samples) == \
+               (w["part_size"], w["fft_size"], w["num_parts_ir"], w["num_parts"], w["parts_per_callback"], w["output_delay_samples"])
+        if li > 0:
+            assert g.gain == want["gains"][li]
+
+
+def _offline_numpy(ir, x, block, cspec, scale=1.0):
+    """The product's formulation in numpy: per layer a plain linear convolution of x with the layer's IR slice
+    (no spectrum filter), then y = y0 + sum g_l * y_l[gather]."""
+    n_cb = len(x) // block
+    lay, tails = plan_layout(len(ir), block, cspec, n_cb)
+    y = np.zeros(len(x))
+    for li in range(lay.num_layers):
+        l = lay.layers[li]
+        h = ir[l.ir_offset:l.ir_offset + l.ir_len] * scale
+        full = np.convolve(x, h) if len(h) < 2000 else __import__("scipy.signal").signal.fftconvolve(x, h)
+        K = len(x) // l.part_size
+        yl = full[:K * l.part_size]
+        if li == 0:
+            y[:len(yl)] += yl
+        else:
+            src = tails[li - 1]
+            for c in range(n_cb):
+                if src[c] >= 0:
+                    y[c * block:(c + 1) * block] += l.gain * yl[src[c]:src[c] + block]
+    return y, lay
+
+
+@pytest.mark.parametrize("ir_len,block,T", [(65536, 512, 65536), (65536, 256, 32768), (65536, 64, 16384),
+                                            (65536, 1024, 131072), (40000, 128, 32768), (300000, 2048, 262144)])
+def test_offline_formulation_equals_state_machine(oracle, ir_len, block, T):
+    """Regular and irregular (drop/starve) plans: block convolution + gather plan == Add/Get loop."""
+    ir = signals.synth_ir(ir_len, 2)
+    x = signals.noise(T, 1)
+    want, _ = oracle.nuc_run(ir, x, block)
+    got, lay = _offline_numpy(ir, x, block, None)
+    assert np.abs(got - want).max() < 1e-12
+
+
+def test_irregular_plan_reports_skips():
+    lay, tails = plan_layout(65536, 1024, None, 400)
+    assert lay.layers[1].skipped_callbacks > 0          # B=1024 default plan drops tail samples
+    lay, tails = plan_layout(65536, 512, None, 400)
+    assert lay.layers[1].skipped_callbacks == 0 and lay.layers[1].first_output_sample == 7168
+
+
+def test_design_band_matches_checker(checker):
+    for ty in range(5):
+        for (f, g, q) in [(1000, 3, 0.7), (19, 50, 25), (30000, -60, 0.001), (100, 0, 1), (25, -6.5, 4)]:
+            for sr in (44100.0, 48000.0, 96000.0, 192000.0):
+                a = design_band(Band(f, g, q, True, ty, 0), sr)
+                b = checker.eq_design(ty, f, g, q, sr)
+                got = np.array([a.a1, a.a2, a.a3, a.m0, a.m1, a.m2])
+                assert np.allclose(got, b, rtol=4e-16, atol=1e-300), (ty, f, g, q, sr, got, b)
