@@ -50,7 +50,7 @@ class Layout(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("fft_fwd_ms", C.c_float), ("mac_ms", C.c_float), ("fft_inv_ms", C.c_float),
                 ("eq_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
-                ("kernel_launches", C.c_int32), ("reserved_", C.c_int32)]
+                ("kernel_launches", C.c_int32), ("chunks", C.c_int32)]
 
 
 # every symbol include/cpq.h declares (tests check the library exports exactly these)

@@ -115,7 +115,7 @@ typedef struct cpq_timings
 {
     float h2d_ms, fft_fwd_ms, mac_ms, fft_inv_ms, eq_ms, d2h_ms, total_ms;
     int32_t kernel_launches;
-    int32_t reserved_;
+    int32_t chunks;           /* sequence chunks of the last call = launches of each stage kernel per layer */
 } cpq_timings;
 
 /* ---- lifecycle --------------------------------------------------------------------------- */

@@ -165,6 +165,10 @@ def _common_sigs(lib, pre, nuc_set_impulse_extra):
     f("nuc_ir_spectrum").argtypes = [vp, C.c_int, C.c_int, _dp, _dp]
     f("eq_design").argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_double, _dp]
     f("eq_design").restype = None
+    f("chain_process").argtypes = [vp, vp, vp, _dp, _dp, C.c_long, C.c_int, C.c_int, C.c_double, C.c_int]
+    f("chain_process").restype = None
+    f("eq_destroy").argtypes = [vp]
+    f("eq_destroy").restype = None
 
 
 class Oracle(_Base):
@@ -297,6 +301,91 @@ class Ref(_Base):
         return l, r, st
 
 
+def _chain_run(self, irs, bands, x, sr, block, spec, saturation, total_gain_db, makeup, outer, do_eq, do_epilogue):
+    """One stream through the per-callback ConvolverThenEQ chain (conv -> wet gain -> EQ -> makeup*headroom).
+    irs: (irL, irR) or None; x: [2, T] (copied). Returns y [2, T]. Releases the GIL inside the C call."""
+    L = self.lib
+    pre = self.prefix
+    y = np.ascontiguousarray(x, dtype=np.float64).copy()
+    nucs = [None, None]
+    eq = None
+    try:
+        if irs is not None:
+            for c in range(2):
+                nucs[c] = self._nuc_create()
+                if not self._nuc_set_impulse(nucs[c], np.ascontiguousarray(irs[c], dtype=np.float64), block, 1.0, spec):
+                    raise RuntimeError("SetImpulse failed")
+        if do_eq:
+            if pre == "cpqref_":
+                eq = L.cpqref_eq_create(sr, block, C.c_float(total_gain_db))
+                arr = (EqBand * 20)(*bands)
+                L.cpqref_eq_set_params(eq, arr, C.c_float(saturation), 0, 0)
+            else:
+                eq = L.cpqo_eq_create(sr, C.c_float(total_gain_db))
+                for i, b in enumerate(bands):
+                    active = bool(b.enabled) and sr > 0
+                    co = self.eq_design(b.type, b.frequency, b.gain_db, b.q, sr) if active else np.zeros(6)
+                    L.cpqo_eq_set_band(eq, i, _p(co), int(active), int(b.channel_mode))
+                L.cpqo_eq_set_saturation(eq, C.c_float(saturation))
+        self._f("chain_process")(nucs[0], nucs[1], eq, _p(y[0]), _p(y[1]), y.shape[1], block, int(outer),
+                                 float(makeup), int(do_epilogue))
+    finally:
+        for n in nucs:
+            if n:
+                self._f("nuc_destroy")(n)
+        if eq:
+            self._f("eq_destroy")(eq)
+    return y
+
+
+def _chain_prepare(self, irs, bands, sr, block, spec, saturation=0.2, total_gain_db=0.0):
+    """Build (nucL, nucR, eq) once so a benchmark can time processing only."""
+    L = self.lib
+    nucs = []
+    for c in range(2):
+        n = self._nuc_create()
+        if not self._nuc_set_impulse(n, np.ascontiguousarray(irs[c], dtype=np.float64), block, 1.0, spec):
+            raise RuntimeError("SetImpulse failed")
+        nucs.append(n)
+    if self.prefix == "cpqref_":
+        eq = L.cpqref_eq_create(sr, block, C.c_float(total_gain_db))
+        arr = (EqBand * 20)(*bands)
+        L.cpqref_eq_set_params(eq, arr, C.c_float(saturation), 0, 0)
+    else:
+        eq = L.cpqo_eq_create(sr, C.c_float(total_gain_db))
+        for i, b in enumerate(bands):
+            active = bool(b.enabled) and sr > 0
+            co = self.eq_design(b.type, b.frequency, b.gain_db, b.q, sr) if active else np.zeros(6)
+            L.cpqo_eq_set_band(eq, i, _p(co), int(active), int(b.channel_mode))
+        L.cpqo_eq_set_saturation(eq, C.c_float(saturation))
+    return nucs[0], nucs[1], eq
+
+
+def _chain_process_prepared(self, handles, y, block, outer=1, makeup=1.0, epilogue=1):
+    self._f("chain_process")(handles[0], handles[1], handles[2], _p(y[0]), _p(y[1]), y.shape[1], block, int(outer),
+                             float(makeup), int(epilogue))
+
+
+def _chain_free(self, handles):
+    self._f("nuc_destroy")(handles[0])
+    self._f("nuc_destroy")(handles[1])
+    self._f("eq_destroy")(handles[2])
+
+
+def _install_chain():
+    for cls in (Oracle, Ref):
+        def chain_run(self, irs, bands, x, sr, block, spec=None, saturation=0.2, total_gain_db=0.0, makeup=1.0,
+                      outer=True, do_eq=True, do_epilogue=True):
+            return _chain_run(self, irs, bands, x, sr, block, spec, saturation, total_gain_db, makeup, outer, do_eq, do_epilogue)
+        cls.chain_run = chain_run
+        cls.chain_prepare = _chain_prepare
+        cls.chain_process_prepared = _chain_process_prepared
+        cls.chain_free = _chain_free
+
+
 def best_checker():
     """The strongest checker available: the real reference if it was compiled, else the restatement."""
     return Ref() if have_ref() else Oracle()
+
+
+_install_chain()

@@ -1017,4 +1017,25 @@ void cpqo_epilogue(double* data, long n, double makeup_gain, double sample_rate,
     }
 }
 
+/* The ConvolverThenEQ chain per callback (DSPCoreDouble.cpp:386-414,465-469,655-663), no dither. */
+void cpqo_chain_process(cpqo_nuc* nl, cpqo_nuc* nr, cpqo_eq* eq, double* L, double* R, long total, int block,
+                        int outer, double makeup, int epilogue)
+{
+    for (long pos = 0; pos < total; pos += block)
+    {
+        const int n = (int) ((total - pos) < block ? (total - pos) : block);
+        double* ch[2] = { L + pos, R ? R + pos : NULL };
+        cpqo_nuc* cv[2] = { nl, nr };
+        for (int c = 0; c < (R ? 2 : 1); ++c)
+        {
+            if (!cv[c]) continue;
+            cpqo_nuc_process(cv[c], ch[c], ch[c], n, n);
+            if (outer) cpqo_outer_wet(ch[c], n, 1.0);
+        }
+        if (eq) cpqo_eq_process(eq, ch[0], ch[1], n, n);
+        if (epilogue)
+            for (int c = 0; c < (R ? 2 : 1); ++c) cpqo_epilogue(ch[c], n, makeup, 48000.0, 0, NULL, NULL, NULL);
+    }
+}
+
 int cpqo_abi_version(void) { return 1; }

@@ -233,5 +233,48 @@ void cpqref_eq_design(int type, float f, float g, float q, double sr, double* ou
     out[0] = c.a1; out[1] = c.a2; out[2] = c.a3; out[3] = c.m0; out[4] = c.m1; out[5] = c.m2;
 }
 
+// DSPCore::processDouble's ConvolverThenEQ chain per callback (DSPCoreDouble.cpp:386-414,465-469,655-663):
+// StereoConvolver::process per channel -> ConvolverProcessor wet scrub + equalPowerSin(1) gain ->
+// EQProcessor::process(block, params, cache) -> makeup gain -> kOutputHeadroom.  Used as the CPU baseline.
+void cpqref_chain_process(void* nucL, void* nucR, void* eq, double* L, double* R, long total, int block,
+                          int outer, double makeup, int epilogue)
+{
+    auto* cl = static_cast<convo::MKLNonUniformConvolver*>(nucL);
+    auto* cr = static_cast<convo::MKLNonUniformConvolver*>(nucR);
+    auto* e = static_cast<RefEq*>(eq);
+    juce::ScopedNoDenormals nd;
+    const double t = 1.0 * (juce::MathConstants<double>::pi * 0.5);
+    const double t2 = t * t;
+    const double wetG = t * (1.0 + t2 * (-1.0 / 6.0 + t2 * (1.0 / 120.0 + t2 * (-1.0 / 5040.0 + t2 * (1.0 / 362880.0)))));
+    for (long pos = 0; pos < total; pos += block)
+    {
+        const int n = (int) std::min<long>(block, total - pos);
+        double* ch[2] = { L + pos, R ? R + pos : nullptr };
+        convo::MKLNonUniformConvolver* cv[2] = { cl, cr };
+        for (int c = 0; c < (R ? 2 : 1); ++c)
+        {
+            if (!cv[c]) continue;
+            cv[c]->Add(ch[c], n);
+            const int got = cv[c]->Get(ch[c], n);
+            if (got < n) std::memset(ch[c] + std::max(got, 0), 0, sizeof(double) * (size_t) (n - std::max(got, 0)));
+            if (outer)
+                for (int i = 0; i < n; ++i)
+                {
+                    double v = ch[c][i];
+                    if (!(std::isfinite(v) && std::fabs(v) < 1.0e300)) v = 0.0;
+                    ch[c][i] = v * wetG;
+                }
+        }
+        if (e)
+        {
+            juce::dsp::AudioBlock<double> blk(ch, R ? 2u : 1u, (size_t) n);
+            e->proc.process(blk, e->params, e->cache.get());
+        }
+        if (epilogue)
+            for (int c = 0; c < (R ? 2 : 1); ++c)
+                for (int i = 0; i < n; ++i) ch[c][i] = (ch[c][i] * makeup) * 0.8912509381337456;
+    }
+}
+
 int cpqref_abi_version(void) { return 1; }
 }
