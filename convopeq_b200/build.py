@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcpq.so")
 SOURCES = [os.path.join(CSRC, "cpq_engine.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "cpq_kernels.cuh"), os.path.join(CSRC, "cpq_plan.hpp"),
+DEPS = SOURCES + [os.path.join(CSRC, "cpq_fft.cuh"), os.path.join(CSRC, "cpq_mac.cuh"), os.path.join(CSRC, "cpq_eq.cuh"),
+                  os.path.join(CSRC, "cpq_plan.hpp"),
                   os.path.join(HERE, "..", "include", "cpq.h")]
 
 NVCC_FLAGS = [

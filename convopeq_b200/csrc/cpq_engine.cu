@@ -15,7 +15,9 @@
 
 #include "../../include/cpq.h"
 #include "cpq_plan.hpp"
-#include "cpq_kernels.cuh"
+#include "cpq_fft.cuh"
+#include "cpq_mac.cuh"
+#include "cpq_eq.cuh"
 
 namespace cpq
 {
@@ -118,8 +120,20 @@ struct Engine
     DevBuf<double> uniforms, ditherZ;
     int64_t uniformsPerCh = 0;
 
-    // timing
+    // timing / pipelining
+    cudaStream_t sIn = nullptr, sOut = nullptr;   // H2D and D2H streams of the host entry point
     cudaEvent_t ev[8] {};
+    std::vector<cudaEvent_t> evPool;
+    cudaEvent_t poolEvent(size_t i)
+    {
+        while (evPool.size() <= i)
+        {
+            cudaEvent_t e = nullptr;
+            cudaEventCreate(&e);
+            evPool.push_back(e);
+        }
+        return evPool[i];
+    }
     cpq_timings timings {};
     int64_t launches = 0;
 
@@ -129,6 +143,10 @@ struct Engine
     {
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
+        for (auto& e : evPool)
+            if (e) cudaEventDestroy(e);
+        if (sIn) cudaStreamDestroy(sIn);
+        if (sOut) cudaStreamDestroy(sOut);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -139,7 +157,8 @@ struct Engine
     cpq_status ensureTwiddles(int li);
     cpq_status uploadEq(int64_t nCallbacks);
     cpq_status ensureGather(int64_t nCallbacks);
-    cpq_status processDevice(double* dIo, int64_t stride, int64_t T, unsigned stages);
+    cpq_status processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar);
+    cpq_status processDevice(double* dIo, int64_t stride, int64_t T, unsigned stages) { return processCore(dIo, stride, T, stages, nullptr); }
     cpq_status launchFwd(int log2P, const FwdArgs& a);
     cpq_status launchInv(int log2P, const InvArgs& a);
     cpq_status launchEq(EqArgs& a);
@@ -259,6 +278,8 @@ cpq_status Engine::init(const cpq_config* c)
         return CPQ_ERR_CUDA;
     }
     CPQ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CPQ_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
+    CPQ_CUDA(cudaStreamCreateWithFlags(&sOut, cudaStreamNonBlocking));
     for (auto& e : ev) CPQ_CUDA(cudaEventCreate(&e));
     nH = cfg.shared_ir ? cfg.n_channels : nSeq;
     haveImpulse.assign((size_t) nH, 0);
@@ -405,6 +426,14 @@ static void buildBandConstants(const cpq_svf_coeffs& c, double* out /* kEqcStrid
     // s' = A s + b v0   (EQProcessor.Processing.cpp:148-153 in affine form)
     const long double A[4] = { 2.0L * c.a1 - 1.0L, -2.0L * c.a2, 2.0L * c.a2, 1.0L - 2.0L * c.a3 };
     const long double b[2] = { 2.0L * c.a2, 2.0L * c.a3 };
+    {
+        // The fast pass relies on ||A^n|| <= 1 (true for every SVF the reference designs); arbitrary user
+        // coefficients that break it are always replayed with the exact per-sample semantics.
+        const double p = (double) (A[0] * A[0] + A[2] * A[2]), q = (double) (A[0] * A[1] + A[2] * A[3]);
+        const double r = (double) (A[1] * A[1] + A[3] * A[3]);
+        const double lmax = 0.5 * (p + r) + std::sqrt(0.25 * (p - r) * (p - r) + q * q);   // largest eigenvalue of A^T A
+        out[6] = (std::isfinite(lmax) && lmax <= 1.0 + 1e-9) ? 0.0 : 1.0;
+    }
     // w[j] = A^(15-j) b
     long double v[2] = { b[0], b[1] };
     for (int j = kEqL - 1; j >= 0; --j)
@@ -553,7 +582,7 @@ cpq_status Engine::launchEq(EqArgs& a)
     return CPQ_OK;
 }
 
-cpq_status Engine::processDevice(double* dIo, int64_t stride, int64_t T, unsigned stages)
+cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar)
 {
     if (!dIo || T <= 0 || T > cfg.max_samples || T % cfg.block_size != 0 || stride < T || (stride & 1))
     {
@@ -593,9 +622,10 @@ cpq_status Engine::processDevice(double* dIo, int64_t stride, int64_t T, unsigne
         cpq_status st = uploadEq(nCallbacks);
         if (st != CPQ_OK) return st;
     }
-    if (doEpi && ditherBits > 0 && uniformsPerCh < T)
+    const bool doDither = doEpi && ditherBits > 0;
+    if (doDither && uniformsPerCh != T)
     {
-        setError("process: dither enabled but cpq_set_dither_uniforms holds fewer than T samples per channel");
+        setError("process: dither enabled but cpq_set_dither_uniforms does not hold exactly T samples per channel");
         return CPQ_ERR_NOT_READY;
     }
 
@@ -618,11 +648,54 @@ cpq_status Engine::processDevice(double* dIo, int64_t stride, int64_t T, unsigne
         }
     }
 
+    // ---- sequence chunking: bounded spectra workspace, and >= ~8 chunks so host copies overlap compute ----
+    int64_t K[CPQ_MAX_LAYERS] = {};
+    int chunk = nSeq;
+    if (doConv)
+    {
+        size_t perSeq = 0;
+        for (int li = 0; li < plan.numLayers; ++li)
+        {
+            const LayerPlan& l = plan.layers[li];
+            K[li] = gplan.framesNeeded[li];
+            perSeq += (size_t) K[li] * l.bins * sizeof(double2) * 2;
+            if (li > 0) perSeq += (size_t) K[li] * l.partSize * sizeof(double);
+        }
+        chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) nSeq, cfg.workspace_bytes / std::max<size_t>(perSeq, 1)));
+    }
+    if (hostPlanar) chunk = std::max(1, std::min(chunk, (nSeq + 7) / 8));
+    if (doConv)
+        for (int li = 0; li < plan.numLayers; ++li)
+        {
+            const LayerPlan& l = plan.layers[li];
+            CPQ_CUDA(layer[li].X.ensure((size_t) chunk * K[li] * l.bins));
+            CPQ_CUDA(layer[li].Y.ensure((size_t) chunk * K[li] * l.bins));
+            if (li > 0) CPQ_CUDA(layer[li].tail.ensure((size_t) chunk * K[li] * l.partSize + 2));
+        }
+    const size_t nChunks = (size_t) ((nSeq + chunk - 1) / chunk);
+    // event pool layout: [c*6 + 0..4] stage boundaries on the compute stream, [c*6 + 5] H2D done on the copy-in stream
+    for (size_t i = 0; i < nChunks * 6 + 4; ++i) poolEvent(i);
+    cudaEvent_t evInBegin = evPool[nChunks * 6 + 0], evInEnd = evPool[nChunks * 6 + 1];
+    cudaEvent_t evOutBegin = evPool[nChunks * 6 + 2], evOutEnd = evPool[nChunks * 6 + 3];
+
     cudaEventRecord(ev[0], stream);
-    float fwdMs = 0.f, macMs = 0.f, invMs = 0.f, eqMs = 0.f;
+    if (hostPlanar)
+    {
+        // all H2D copies are queued up front on their own stream; compute waits per chunk
+        cudaStreamWaitEvent(sIn, ev[0], 0);
+        cudaEventRecord(evInBegin, sIn);
+        for (size_t c = 0; c < nChunks; ++c)
+        {
+            const int s0 = (int) c * chunk, ns = std::min(chunk, nSeq - s0);
+            for (int s = s0; s < s0 + ns; ++s)
+                CPQ_CUDA(cudaMemcpyAsync(dIo + (size_t) s * stride, hostPlanar[s], (size_t) T * sizeof(double), cudaMemcpyHostToDevice, sIn));
+            cudaEventRecord(evPool[c * 6 + 5], sIn);
+        }
+        cudaEventRecord(evInEnd, sIn);
+    }
 
     auto fillEqCommon = [&](EqArgs& a) {
-        a.blockSize = B;
+        a.blockLog2 = ilog2(B);
         a.T = T;
         a.ioStride = stride;
         a.doEq = doEq ? 1 : 0;
@@ -636,33 +709,18 @@ cpq_status Engine::processDevice(double* dIo, int64_t stride, int64_t T, unsigne
         a.applyHeadroom = (doEpi && ditherBits <= 0) ? 1 : 0;
         a.wetGain = equalPowerSin(1.0) * 1.0;   // CONVOLUTION_HEADROOM_GAIN = 1.0 (ConvolverProcessor.h:209)
     };
+    const bool deferredOuter = !doConv && outerPending;
 
-    if (doConv)
+    for (size_t c = 0; c < nChunks; ++c)
     {
-        // bytes of workspace per sequence
-        size_t perSeq = 0;
-        int64_t K[CPQ_MAX_LAYERS] = {};
-        for (int li = 0; li < plan.numLayers; ++li)
+        const int s0 = (int) c * chunk, ns = std::min(chunk, nSeq - s0);
+        double* ioC = dIo + (size_t) s0 * stride;
+        cudaEvent_t* ce = &evPool[c * 6];
+        if (hostPlanar) cudaStreamWaitEvent(stream, evPool[c * 6 + 5], 0);
+        cudaEventRecord(ce[0], stream);
+        if (doConv)
         {
-            const LayerPlan& l = plan.layers[li];
-            K[li] = gplan.framesNeeded[li];
-            perSeq += (size_t) K[li] * l.bins * sizeof(double2) * 2;
-            if (li > 0) perSeq += (size_t) K[li] * l.partSize * sizeof(double);
-        }
-        int chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) nSeq, cfg.workspace_bytes / std::max<size_t>(perSeq, 1)));
-        for (int li = 0; li < plan.numLayers; ++li)
-        {
-            const LayerPlan& l = plan.layers[li];
-            CPQ_CUDA(layer[li].X.ensure((size_t) chunk * K[li] * l.bins));
-            CPQ_CUDA(layer[li].Y.ensure((size_t) chunk * K[li] * l.bins));
-            if (li > 0) CPQ_CUDA(layer[li].tail.ensure((size_t) chunk * K[li] * l.partSize + 2));
-        }
-        for (int s0 = 0; s0 < nSeq; s0 += chunk)
-        {
-            const int ns = std::min(chunk, nSeq - s0);
-            double* ioC = dIo + (size_t) s0 * stride;
             // ---- forward FFTs of every layer (all read the untouched input) ----
-            cudaEventRecord(ev[1], stream);
             for (int li = 0; li < plan.numLayers; ++li)
             {
                 const LayerPlan& l = plan.layers[li];
@@ -684,7 +742,7 @@ cpq_status Engine::processDevice(double* dIo, int64_t stride, int64_t T, unsigne
                 cpq_status st = launchFwd(ilog2(l.partSize), a);
                 if (st != CPQ_OK) return st;
             }
-            cudaEventRecord(ev[2], stream);
+            cudaEventRecord(ce[1], stream);
             // ---- MAC ----
             for (int li = 0; li < plan.numLayers; ++li)
             {
@@ -708,15 +766,14 @@ cpq_status Engine::processDevice(double* dIo, int64_t stride, int64_t T, unsigne
                 a.qEnd = qe[li];
                 a.hSeqStride = (int64_t) l.numPartsIR * l.bins;
                 a.hSeqMod = cfg.shared_ir ? cfg.n_channels : 0;
-                // H rows are absolute sequence indices when not shared
-                if (!cfg.shared_ir) a.H += (size_t) s0 * a.hSeqStride;
+                if (!cfg.shared_ir) a.H += (size_t) s0 * a.hSeqStride;   // H rows are absolute sequence indices
                 constexpr int KT = 8, QT = 4;
                 dim3 grid((unsigned) ((l.bins + 127) / 128), (unsigned) ((K[li] + KT - 1) / KT), (unsigned) ns);
                 mac_kernel<KT, QT><<<grid, 128, 0, stream>>>(a);
                 ++launches;
                 CPQ_CUDA(cudaGetLastError());
             }
-            cudaEventRecord(ev[3], stream);
+            cudaEventRecord(ce[2], stream);
             // ---- inverse FFTs: L0 in place into io, tails into their stream buffers ----
             for (int li = 0; li < plan.numLayers; ++li)
             {
@@ -733,12 +790,20 @@ cpq_status Engine::processDevice(double* dIo, int64_t stride, int64_t T, unsigne
                 cpq_status st = launchInv(ilog2(l.partSize), a);
                 if (st != CPQ_OK) return st;
             }
-            cudaEventRecord(ev[4], stream);
-            // ---- assembly + EQ + epilogue for this chunk ----
-            EqArgs e {};
-            fillEqCommon(e);
-            e.io = ioC;
-            e.nSeq = ns;
+        }
+        else
+        {
+            cudaEventRecord(ce[1], stream);
+            cudaEventRecord(ce[2], stream);
+        }
+        cudaEventRecord(ce[3], stream);
+        // ---- assembly + EQ + epilogue for this chunk ----
+        EqArgs e {};
+        fillEqCommon(e);
+        e.io = ioC;
+        e.nSeq = ns;
+        if (doConv)
+        {
             e.assemble = 1;
             e.nTail = plan.numLayers - 1;
             for (int li = 1; li < plan.numLayers; ++li)
@@ -747,80 +812,74 @@ cpq_status Engine::processDevice(double* dIo, int64_t stride, int64_t T, unsigne
                 e.tailStride[li - 1] = (int64_t) K[li] * plan.layers[li].partSize;
                 e.tailSrc[li - 1] = layer[li].tailSrc.p;
                 e.blockMap[li - 1] = layer[li].hasBlockMap ? layer[li].blockMap.p : nullptr;
-                e.tailPart[li - 1] = plan.layers[li].partSize;
+                e.tailPartLog2[li - 1] = ilog2(plan.layers[li].partSize);
                 e.tailGain[li - 1] = plan.layers[li].gain;
             }
             e.outer = (cfg.conv_boundary == CPQ_CONV_OUTER && fullRange) ? 1 : 0;
-            e.bandMask = bandMask.p ? bandMask.p + s0 : nullptr;
-            e.setOfSeq = setOfSeq.p ? setOfSeq.p + s0 : nullptr;
-            e.stateOut = stateOut.p + (size_t) s0 * CPQ_NUM_BANDS * 2;
-            if (!cfg.shared_eq && e.setOfSeq)
-            {
-                // setOfSeq holds absolute set indices; eqc/sat/gain tables are indexed absolutely too
-            }
-            cpq_status st = launchEq(e);
-            if (st != CPQ_OK) return st;
-            cudaEventRecord(ev[5], stream);
-            CPQ_CUDA(cudaEventSynchronize(ev[5]));
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ev[1], ev[2]); fwdMs += ms;
-            cudaEventElapsedTime(&ms, ev[2], ev[3]); macMs += ms;
-            cudaEventElapsedTime(&ms, ev[3], ev[4]); invMs += ms;
-            cudaEventElapsedTime(&ms, ev[4], ev[5]); eqMs += ms;
         }
-        outerPending = (cfg.conv_boundary == CPQ_CONV_OUTER && !fullRange);
-    }
-    else
-    {
-        EqArgs e {};
-        fillEqCommon(e);
-        e.io = dIo;
-        e.nSeq = nSeq;
-        e.assemble = outerPending ? 1 : 0;   // no tails; only the deferred outer-boundary scrub + wet gain
-        e.nTail = 0;
-        e.outer = outerPending ? 1 : 0;
-        outerPending = false;
-        e.bandMask = bandMask.p;
-        e.setOfSeq = setOfSeq.p;
-        e.stateOut = stateOut.p;
-        cudaEventRecord(ev[4], stream);
+        else
+        {
+            e.assemble = deferredOuter ? 1 : 0;   // no tails; only the deferred outer-boundary scrub + wet gain
+            e.nTail = 0;
+            e.outer = deferredOuter ? 1 : 0;
+        }
+        e.bandMask = bandMask.p ? bandMask.p + s0 : nullptr;
+        e.setOfSeq = setOfSeq.p ? setOfSeq.p + s0 : nullptr;   // absolute set indices
+        e.stateOut = stateOut.p + (size_t) s0 * CPQ_NUM_BANDS * 2;
         cpq_status st = launchEq(e);
         if (st != CPQ_OK) return st;
-        cudaEventRecord(ev[5], stream);
-        CPQ_CUDA(cudaEventSynchronize(ev[5]));
-        cudaEventElapsedTime(&eqMs, ev[4], ev[5]);
-    }
-
-    if (doEpi && ditherBits > 0)
-    {
-        DitherArgs d {};
-        d.io = dIo;
-        d.ioStride = stride;
-        d.T = T;
-        d.nSeq = nSeq;
-        d.uniforms = uniforms.p;
-        ditherCoeffs(cfg.sample_rate, ditherBits, d.coeff);
-        d.scale = 1.0 / std::pow(2.0, ditherBits - 1);
-        d.invScale = std::pow(2.0, ditherBits - 1);
-        d.z = ditherZ.p;
-        if (uniformsPerCh != T)
+        if (doDither)
         {
-            setError("process: dither uniforms must be laid out for exactly T samples per channel");
-            return CPQ_ERR_INVALID;
+            DitherArgs d {};
+            d.io = ioC;
+            d.ioStride = stride;
+            d.T = T;
+            d.nSeq = ns;
+            d.uniforms = uniforms.p + (size_t) s0 * 2 * T;
+            ditherCoeffs(cfg.sample_rate, ditherBits, d.coeff);
+            d.scale = 1.0 / std::pow(2.0, ditherBits - 1);
+            d.invScale = std::pow(2.0, ditherBits - 1);
+            d.z = ditherZ.p + (size_t) s0 * 12;
+            dither_kernel<<<(unsigned) ((ns + 31) / 32), 32, 0, stream>>>(d);
+            ++launches;
+            CPQ_CUDA(cudaGetLastError());
         }
-        dither_kernel<<<(unsigned) ((nSeq + 31) / 32), 32, 0, stream>>>(d);
-        ++launches;
-        CPQ_CUDA(cudaGetLastError());
+        cudaEventRecord(ce[4], stream);
+        if (hostPlanar)
+        {
+            cudaStreamWaitEvent(sOut, ce[4], 0);
+            if (c == 0) cudaEventRecord(evOutBegin, sOut);
+            for (int s = s0; s < s0 + ns; ++s)
+                CPQ_CUDA(cudaMemcpyAsync(hostPlanar[s], dIo + (size_t) s * stride, (size_t) T * sizeof(double), cudaMemcpyDeviceToHost, sOut));
+        }
+    }
+    if (doConv) outerPending = (cfg.conv_boundary == CPQ_CONV_OUTER && !fullRange);
+    else outerPending = false;
+
+    if (hostPlanar)
+    {
+        cudaEventRecord(evOutEnd, sOut);
+        cudaStreamWaitEvent(stream, evOutEnd, 0);
     }
     cudaEventRecord(ev[6], stream);
     CPQ_CUDA(cudaEventSynchronize(ev[6]));
     unsigned tf[2] = {};
     CPQ_CUDA(cudaMemcpy(tf, ticketFault.p, sizeof(tf), cudaMemcpyDeviceToHost));
     cudaEventElapsedTime(&timings.total_ms, ev[0], ev[6]);
-    timings.fft_fwd_ms = fwdMs;
-    timings.mac_ms = macMs;
-    timings.fft_inv_ms = invMs;
-    timings.eq_ms = eqMs;
+    for (size_t c = 0; c < nChunks; ++c)
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, evPool[c * 6 + 0], evPool[c * 6 + 1]); timings.fft_fwd_ms += ms;
+        cudaEventElapsedTime(&ms, evPool[c * 6 + 1], evPool[c * 6 + 2]); timings.mac_ms += ms;
+        cudaEventElapsedTime(&ms, evPool[c * 6 + 2], evPool[c * 6 + 3]); timings.fft_inv_ms += ms;
+        cudaEventElapsedTime(&ms, evPool[c * 6 + 3], evPool[c * 6 + 4]); timings.eq_ms += ms;
+    }
+    if (hostPlanar)
+    {
+        cudaEventElapsedTime(&timings.h2d_ms, evInBegin, evInEnd);
+        cudaEventElapsedTime(&timings.d2h_ms, evOutBegin, evOutEnd);
+    }
+    timings.chunks = (int) nChunks;
     timings.kernel_launches = (int) launches - launches0;
     if (tf[1] != 0)
     {
@@ -1014,33 +1073,17 @@ cpq_status cpq_process(cpq_handle h, double* const* planar, int64_t T, unsigned 
         e->setError("process: T must be a positive multiple of block_size and <= max_samples");
         return CPQ_ERR_INVALID;
     }
+    for (int s = 0; s < e->nSeq; ++s)
+        if (!planar[s])
+        {
+            e->setError("process: null channel pointer");
+            return CPQ_ERR_INVALID;
+        }
     CPQ_CUDA(cudaSetDevice(e->cfg.device));
     const int64_t stride = (T + 1) & ~(int64_t) 1;
     CPQ_CUDA(e->io.ensure((size_t) e->nSeq * stride));
-    cudaEvent_t h0 = e->ev[7];
-    cudaEventRecord(h0, e->stream);
-    for (int s = 0; s < e->nSeq; ++s)
-    {
-        if (!planar[s]) { e->setError("process: null channel pointer"); return CPQ_ERR_INVALID; }
-        CPQ_CUDA(cudaMemcpyAsync(e->io.p + (size_t) s * stride, planar[s], (size_t) T * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    }
-    cudaEventRecord(e->ev[0], e->stream);
-    CPQ_CUDA(cudaEventSynchronize(e->ev[0]));
-    float h2d = 0.f;
-    cudaEventElapsedTime(&h2d, h0, e->ev[0]);
-    cpq_status st = e->processDevice(e->io.p, stride, T, stages);
-    if (st != CPQ_OK) return st;
-    cudaEventRecord(h0, e->stream);
-    for (int s = 0; s < e->nSeq; ++s)
-        CPQ_CUDA(cudaMemcpyAsync(planar[s], e->io.p + (size_t) s * stride, (size_t) T * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    cudaEventRecord(e->ev[0], e->stream);
-    CPQ_CUDA(cudaEventSynchronize(e->ev[0]));
-    float d2h = 0.f;
-    cudaEventElapsedTime(&d2h, h0, e->ev[0]);
-    e->timings.h2d_ms = h2d;
-    e->timings.d2h_ms = d2h;
-    e->timings.total_ms += h2d + d2h;
-    return CPQ_OK;
+    // H2D, kernels and D2H are pipelined per sequence chunk on three streams inside processCore
+    return e->processCore(e->io.p, stride, T, stages, planar);
 }
 
 cpq_status cpq_set_partition_range(cpq_handle h, int part_begin, int part_end)

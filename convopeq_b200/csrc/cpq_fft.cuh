@@ -1,0 +1,357 @@
+// cpq_fft.cuh -- batched FP64 real FFTs for the overlap-save frames (sm_100a).
+//
+//   fft_fwd_kernel   real -> CCS spectra of overlap-save frames (and of IR partitions at prepare)
+//                    = ProductionFft::forwardRealToCCS (FFTBackend.cpp:123-135) for every frame at once
+//   fft_inv_kernel   CCS -> real (1/N), keeps samples [P, 2P) = inverseCCSToR + ringWrite / tailOutputBuf
+//                    copy (MKLNonUniformConvolver.cpp:1327-1332, 1531-1540)
+//
+// A 2P-point real transform is a P-point complex transform of z[n] = x[2n] + i x[2n+1] plus a split
+// pass.  The complex transform is a Stockham autosort FFT: one radix-2/4 pass when log2 P is not a
+// multiple of 3, then radix-8 passes; each thread owns 8 points in registers per pass, passes exchange
+// through shared memory.  The first pass reads HBM directly (coalesced double2), the forward split pass and
+// the inverse's last pass write HBM directly, so every sample crosses HBM once in each direction.
+// Shared memory is indexed through pad(i) = i + (i >> 3): one 16-byte slot of padding per 8 keeps the
+// stride-8 writes of the first pass, the stride-1 accesses of later passes and the mirrored reads of the
+// split pass free of bank conflicts (ncu round 1: 51 % of shared wavefronts were conflicts without it).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace cpq
+{
+
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b)
+{
+    return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+// multiply by -i (SIGN = -1, forward) or +i (SIGN = +1, inverse)
+template <int SIGN>
+__device__ __forceinline__ double2 mul_i(double2 a)
+{
+    return SIGN < 0 ? make_double2(a.y, -a.x) : make_double2(-a.y, a.x);
+}
+
+__device__ __forceinline__ int fft_pad(int i) { return i + (i >> 3); }
+
+// W_P^idx from the layer table tw[t] = exp(-2 pi i t / (2P)), t = 0..P; SIGN > 0 conjugates.
+template <int SIGN>
+__device__ __forceinline__ double2 twiddleP(const double2* __restrict__ tw, int P, int idx)
+{
+    const int t = 2 * idx;
+    double2 w;
+    if (t <= P) w = __ldg(tw + t);
+    else
+    {
+        w = __ldg(tw + (t - P));
+        w.x = -w.x;
+        w.y = -w.y;
+    }
+    if (SIGN > 0) w.y = -w.y;
+    return w;
+}
+
+template <int SIGN>
+__device__ __forceinline__ void dft2(double2& a, double2& b)
+{
+    const double2 t = csub(a, b);
+    a = cadd(a, b);
+    b = t;
+}
+
+template <int SIGN>
+__device__ __forceinline__ void dft4(double2* v)
+{
+    const double2 b0 = cadd(v[0], v[2]), b2 = csub(v[0], v[2]);
+    const double2 b1 = cadd(v[1], v[3]), b3 = mul_i<SIGN>(csub(v[1], v[3]));
+    v[0] = cadd(b0, b1);
+    v[2] = csub(b0, b1);
+    v[1] = cadd(b2, b3);
+    v[3] = csub(b2, b3);
+}
+
+template <int SIGN>
+__device__ __forceinline__ void dft8(double2* v)
+{
+    constexpr double kS = 0.70710678118654752440;
+    const double2 a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
+    const double2 a1 = cadd(v[1], v[5]);
+    double2 a5 = csub(v[1], v[5]);
+    const double2 a2 = cadd(v[2], v[6]);
+    const double2 a6 = mul_i<SIGN>(csub(v[2], v[6]));
+    const double2 a3 = cadd(v[3], v[7]);
+    double2 a7 = csub(v[3], v[7]);
+    // W8^1 = (1 -+ i)/sqrt2, W8^3 = (-1 -+ i)/sqrt2   (upper sign: forward)
+    if (SIGN < 0)
+    {
+        a5 = make_double2((a5.x + a5.y) * kS, (a5.y - a5.x) * kS);
+        a7 = make_double2((a7.y - a7.x) * kS, -(a7.x + a7.y) * kS);
+    }
+    else
+    {
+        a5 = make_double2((a5.x - a5.y) * kS, (a5.x + a5.y) * kS);
+        a7 = make_double2(-(a7.x + a7.y) * kS, (a7.x - a7.y) * kS);
+    }
+    double2 e[4] = { a0, a1, a2, a3 };
+    double2 o[4] = { a4, a5, a6, a7 };
+    dft4<SIGN>(e);
+    dft4<SIGN>(o);
+    v[0] = e[0]; v[2] = e[1]; v[4] = e[2]; v[6] = e[3];
+    v[1] = o[0]; v[3] = o[1]; v[5] = o[2]; v[7] = o[3];
+}
+
+template <int R, int SIGN>
+__device__ __forceinline__ void dftR(double2* v)
+{
+    if (R == 2) dft2<SIGN>(v[0], v[1]);
+    else if (R == 4) dft4<SIGN>(v);
+    else dft8<SIGN>(v);
+}
+
+// One work item of a Stockham pass: n-point transform, sub-transform length Ns before the pass.
+// Reads in[j + r*n/R], twiddles by W_{Ns*R}^{k*r}, R-point DFT, result r goes to (j-k)*R + k + r*Ns.
+template <int R, int SIGN, class LoadF>
+__device__ __forceinline__ void stockham_load(double2* v, int j, int n, int Ns, const double2* __restrict__ tw, int P, LoadF ld)
+{
+    const int k = j & (Ns - 1);
+    const int stride = n / R;
+    const int tscale = n / (Ns * R);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+    {
+        double2 x = ld(j + r * stride);
+        if (r > 0 && Ns > 1) x = cmul(x, twiddleP<SIGN>(tw, P, k * r * tscale));
+        v[r] = x;
+    }
+    dftR<R, SIGN>(v);
+}
+
+template <int R>
+__device__ __forceinline__ int stockham_out_base(int j, int Ns)
+{
+    const int k = j & (Ns - 1);
+    return (j - k) * R + k;
+}
+
+struct FwdArgs
+{
+    const double* src;      // [nSeq][srcStride] real samples
+    int64_t srcStride;
+    int64_t frameStart0;    // sample index (within a sequence) where frame 0 starts (may be negative)
+    int64_t lo, hi;         // valid sample range [lo, hi); outside -> 0
+    int halfOnly;           // 1: only the first P samples of a frame are taken (IR partitions)
+    int framesPerSeq;       // K
+    int64_t totalFrames;    // nSeq * K
+    double2* out;           // [nSeq][outFramesPerSeq][P+1]
+    int outFramesPerSeq;    // >= K (row pitch of out per sequence, in frames)
+    int outFrameOffset;     // frame f is stored at row f + outFrameOffset
+    const double2* tw;      // [P+1]
+    double scale;           // applied when applyScale
+    int applyScale;
+    const double* gain;     // nullable [P+1]
+    const double* tilt;     // nullable [P+1]
+};
+
+template <int LOG2P>
+struct FftCfg
+{
+    static constexpr int P = 1 << LOG2P;
+    static constexpr int TPF = P / 8;                                // threads per FFT
+    static constexpr int THREADS = TPF >= 256 ? TPF : 256;
+    static constexpr int FPC = THREADS / TPF;                        // frames per CTA
+    static constexpr int R0 = 1 << (LOG2P % 3);                      // first-pass radix (1 = none)
+    static constexpr int NPASS8 = LOG2P / 3;
+    static constexpr int ROW = P + P / 8;                            // padded row, in double2
+    static constexpr size_t SMEM = (size_t) FPC * ROW * sizeof(double2);
+};
+
+template <int LOG2P>
+__global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS) fft_fwd_kernel(FwdArgs a)
+{
+    using C = FftCfg<LOG2P>;
+    constexpr int P = C::P, TPF = C::TPF;
+    extern __shared__ double2 smem_fft[];
+    const int fl = threadIdx.x / TPF;       // local frame
+    const int t = threadIdx.x % TPF;
+    const int64_t gf = (int64_t) blockIdx.x * C::FPC + fl;
+    const bool live = gf < a.totalFrames;
+    double2* buf = smem_fft + (size_t) fl * C::ROW;
+    const int64_t seq = live ? gf / a.framesPerSeq : 0;
+    const int f = live ? (int) (gf % a.framesPerSeq) : 0;
+    const double* src = a.src + seq * a.srcStride;
+    const int64_t base = a.frameStart0 + (int64_t) f * P;
+    const bool vec_ok = (a.halfOnly == 0);
+
+    auto gload = [&](int idx) -> double2 {
+        // z[idx] = x[2 idx] + i x[2 idx + 1]
+        const int64_t g = base + 2 * (int64_t) idx;
+        if (!live) return make_double2(0.0, 0.0);
+        if (a.halfOnly && 2 * idx >= P) return make_double2(0.0, 0.0);
+        if (vec_ok && g >= a.lo && g + 1 < a.hi) return __ldg(reinterpret_cast<const double2*>(src + g));
+        double2 z;
+        z.x = (g >= a.lo && g < a.hi) ? __ldg(src + g) : 0.0;
+        z.y = (g + 1 >= a.lo && g + 1 < a.hi) ? __ldg(src + g + 1) : 0.0;
+        return z;
+    };
+    auto sload = [&](int idx) -> double2 { return buf[fft_pad(idx)]; };
+
+    int Ns = 1;
+    if constexpr (C::R0 > 1)
+    {
+        constexpr int R = C::R0;
+        constexpr int ITEMS = 8 / R;
+        double2 v[ITEMS][R];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) stockham_load<R, -1>(v[i], t + i * TPF, P, 1, a.tw, P, gload);
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i)
+        {
+            const int ob = stockham_out_base<R>(t + i * TPF, 1);
+#pragma unroll
+            for (int r = 0; r < R; ++r) buf[fft_pad(ob + r)] = v[i][r];
+        }
+        Ns = R;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int p = 0; p < C::NPASS8; ++p)
+    {
+        double2 v[8];
+        if (p == 0 && C::R0 == 1) stockham_load<8, -1>(v, t, P, Ns, a.tw, P, gload);
+        else
+        {
+            stockham_load<8, -1>(v, t, P, Ns, a.tw, P, sload);
+            __syncthreads();
+        }
+        const int ob = stockham_out_base<8>(t, Ns);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) buf[fft_pad(ob + r * Ns)] = v[r];
+        Ns *= 8;
+        __syncthreads();
+    }
+
+    // ---- split pass: X[m] = E + W_N^m O, X[P-m] = conj(E - W_N^m O) ----
+    if (!live) return;
+    double2* out = a.out + ((size_t) seq * a.outFramesPerSeq + (size_t) (f + a.outFrameOffset)) * (size_t) (P + 1);
+    auto emit = [&](int m, double2 X) {
+        if (a.applyScale) { X.x *= a.scale; X.y *= a.scale; }
+        if (a.gain) { const double g = __ldg(a.gain + m); X.x *= g; X.y *= g; }
+        if (a.tilt) { const double g = __ldg(a.tilt + m); X.x *= g; X.y *= g; }
+        out[m] = X;
+    };
+    for (int m = t; m <= P / 2; m += TPF)
+    {
+        const double2 zm = buf[fft_pad(m)];
+        const double2 zc = cconj(buf[fft_pad((P - m) & (P - 1))]);
+        const double2 E = make_double2(0.5 * (zm.x + zc.x), 0.5 * (zm.y + zc.y));
+        const double2 D = make_double2(0.5 * (zm.x - zc.x), 0.5 * (zm.y - zc.y));
+        const double2 O = make_double2(D.y, -D.x);   // -i * D
+        const double2 w = __ldg(a.tw + m);
+        const double2 Tm = cmul(w, O);
+        if (m == 0)
+        {
+            emit(0, make_double2(E.x + O.x, 0.0));
+            emit(P, make_double2(E.x - O.x, 0.0));
+        }
+        else
+        {
+            emit(m, cadd(E, Tm));
+            if (m != P / 2) emit(P - m, cconj(csub(E, Tm)));
+        }
+    }
+}
+
+struct InvArgs
+{
+    const double2* in;      // [nSeq][framesPerSeq][P+1]
+    int framesPerSeq;       // K (row pitch of `in`)
+    int framesOut;          // frames f < framesOut are transformed per sequence
+    int64_t totalFrames;    // nSeq * framesOut
+    double* out;            // [nSeq][outStride]; frame f -> out[f*P .. (f+1)*P)
+    int64_t outStride;
+    const double2* tw;
+};
+
+template <int LOG2P>
+__global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS) fft_inv_kernel(InvArgs a)
+{
+    using C = FftCfg<LOG2P>;
+    constexpr int P = C::P, TPF = C::TPF;
+    extern __shared__ double2 smem_fft[];
+    const int fl = threadIdx.x / TPF;
+    const int t = threadIdx.x % TPF;
+    const int64_t gf = (int64_t) blockIdx.x * C::FPC + fl;
+    const bool live = gf < a.totalFrames;
+    double2* buf = smem_fft + (size_t) fl * C::ROW;
+    const int64_t seq = live ? gf / a.framesOut : 0;
+    const int f = live ? (int) (gf % a.framesOut) : 0;
+    const double2* Y = a.in + ((size_t) seq * a.framesPerSeq + (size_t) f) * (size_t) (P + 1);
+    const double invN = 1.0 / (double) (2 * P);
+
+    // Z[m] = ((Y[m] + conj Y[P-m]) + i conj(W_N^m) (Y[m] - conj Y[P-m])) / N
+    auto gload = [&](int m) -> double2 {
+        if (!live) return make_double2(0.0, 0.0);
+        double2 ym = __ldg(Y + m);
+        double2 yc = cconj(__ldg(Y + (P - m)));
+        if (m == 0) { ym.y = 0.0; yc.y = 0.0; }   // imaginary parts of bins 0 and P are ignored (CCS contract)
+        const double2 S = cadd(ym, yc);
+        const double2 D = csub(ym, yc);
+        const double2 wc = cconj(__ldg(a.tw + m));
+        const double2 Tm = cmul(wc, D);
+        return make_double2((S.x - Tm.y) * invN, (S.y + Tm.x) * invN);   // S + i Tm
+    };
+    auto sload = [&](int idx) -> double2 { return buf[fft_pad(idx)]; };
+
+    int Ns = 1;
+    if constexpr (C::R0 > 1)
+    {
+        constexpr int R = C::R0;
+        constexpr int ITEMS = 8 / R;
+        double2 v[ITEMS][R];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) stockham_load<R, +1>(v[i], t + i * TPF, P, 1, a.tw, P, gload);
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i)
+        {
+            const int ob = stockham_out_base<R>(t + i * TPF, 1);
+#pragma unroll
+            for (int r = 0; r < R; ++r) buf[fft_pad(ob + r)] = v[i][r];
+        }
+        Ns = R;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int p = 0; p < C::NPASS8; ++p)
+    {
+        double2 v[8];
+        if (p == 0 && C::R0 == 1) stockham_load<8, +1>(v, t, P, Ns, a.tw, P, gload);
+        else
+        {
+            stockham_load<8, +1>(v, t, P, Ns, a.tw, P, sload);
+            if (p != C::NPASS8 - 1) __syncthreads();
+        }
+        if (p == C::NPASS8 - 1)
+        {
+            // last pass: Ns == P/8, outputs at t + r*P/8; only z[P/2 ..) = y[P .. 2P) is kept.
+            if (live)
+            {
+                double2* o = reinterpret_cast<double2*>(a.out + seq * a.outStride + (int64_t) f * P);
+#pragma unroll
+                for (int r = 4; r < 8; ++r) o[t + (r - 4) * (P / 8)] = v[r];
+            }
+        }
+        else
+        {
+            const int ob = stockham_out_base<8>(t, Ns);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) buf[fft_pad(ob + r * Ns)] = v[r];
+            Ns *= 8;
+            __syncthreads();
+        }
+    }
+}
+
+} // namespace cpq
