@@ -8,6 +8,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -679,19 +680,36 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
     cudaEvent_t evOutBegin = evPool[nChunks * 6 + 2], evOutEnd = evPool[nChunks * 6 + 3];
 
     cudaEventRecord(ev[0], stream);
+    // Host rows at a constant pitch (one contiguous [n_seq][pitch] buffer) move as one 2-D copy per chunk;
+    // otherwise row by row.  H2D runs at most two chunks ahead of compute so the driver's launch queue never
+    // fills with copies (a full queue would stall the host before the first D2H is enqueued).
+    ptrdiff_t hostPitch = 0;
+    if (hostPlanar && nSeq > 1)
+    {
+        hostPitch = hostPlanar[1] - hostPlanar[0];
+        for (int s = 2; s < nSeq && hostPitch > 0; ++s)
+            if (hostPlanar[s] - hostPlanar[s - 1] != hostPitch) hostPitch = 0;
+        if (hostPitch < T) hostPitch = 0;
+    }
+    auto enqueueH2D = [&](size_t c) -> cudaError_t {
+        const int s0 = (int) c * chunk, ns = std::min(chunk, nSeq - s0);
+        cudaError_t e = cudaSuccess;
+        if (hostPitch > 0)
+            e = cudaMemcpy2DAsync(dIo + (size_t) s0 * stride, (size_t) stride * sizeof(double), hostPlanar[s0], (size_t) hostPitch * sizeof(double),
+                                  (size_t) T * sizeof(double), (size_t) ns, cudaMemcpyHostToDevice, sIn);
+        else
+            for (int s = s0; s < s0 + ns && e == cudaSuccess; ++s)
+                e = cudaMemcpyAsync(dIo + (size_t) s * stride, hostPlanar[s], (size_t) T * sizeof(double), cudaMemcpyHostToDevice, sIn);
+        if (e == cudaSuccess) e = cudaEventRecord(evPool[c * 6 + 5], sIn);
+        if (c + 1 == nChunks && e == cudaSuccess) e = cudaEventRecord(evInEnd, sIn);
+        return e;
+    };
+    constexpr size_t kH2DAhead = 2;
     if (hostPlanar)
     {
-        // all H2D copies are queued up front on their own stream; compute waits per chunk
         cudaStreamWaitEvent(sIn, ev[0], 0);
         cudaEventRecord(evInBegin, sIn);
-        for (size_t c = 0; c < nChunks; ++c)
-        {
-            const int s0 = (int) c * chunk, ns = std::min(chunk, nSeq - s0);
-            for (int s = s0; s < s0 + ns; ++s)
-                CPQ_CUDA(cudaMemcpyAsync(dIo + (size_t) s * stride, hostPlanar[s], (size_t) T * sizeof(double), cudaMemcpyHostToDevice, sIn));
-            cudaEventRecord(evPool[c * 6 + 5], sIn);
-        }
-        cudaEventRecord(evInEnd, sIn);
+        for (size_t c = 0; c < std::min(kH2DAhead, nChunks); ++c) CPQ_CUDA(enqueueH2D(c));
     }
 
     auto fillEqCommon = [&](EqArgs& a) {
@@ -849,8 +867,13 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         {
             cudaStreamWaitEvent(sOut, ce[4], 0);
             if (c == 0) cudaEventRecord(evOutBegin, sOut);
-            for (int s = s0; s < s0 + ns; ++s)
-                CPQ_CUDA(cudaMemcpyAsync(hostPlanar[s], dIo + (size_t) s * stride, (size_t) T * sizeof(double), cudaMemcpyDeviceToHost, sOut));
+            if (hostPitch > 0)
+                CPQ_CUDA(cudaMemcpy2DAsync(hostPlanar[s0], (size_t) hostPitch * sizeof(double), dIo + (size_t) s0 * stride, (size_t) stride * sizeof(double),
+                                           (size_t) T * sizeof(double), (size_t) ns, cudaMemcpyDeviceToHost, sOut));
+            else
+                for (int s = s0; s < s0 + ns; ++s)
+                    CPQ_CUDA(cudaMemcpyAsync(hostPlanar[s], dIo + (size_t) s * stride, (size_t) T * sizeof(double), cudaMemcpyDeviceToHost, sOut));
+            if (c + kH2DAhead < nChunks) CPQ_CUDA(enqueueH2D(c + kH2DAhead));
         }
     }
     if (doConv) outerPending = (cfg.conv_boundary == CPQ_CONV_OUTER && !fullRange);
@@ -881,6 +904,19 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
     }
     timings.chunks = (int) nChunks;
     timings.kernel_launches = (int) launches - launches0;
+    if (std::getenv("CPQ_TRACE"))
+    {
+        // per-chunk timeline relative to the start of the call: H2D done, compute begin/end
+        for (size_t c = 0; c < nChunks; ++c)
+        {
+            float tin = 0.f, tb = 0.f, te = 0.f;
+            if (hostPlanar) cudaEventElapsedTime(&tin, ev[0], evPool[c * 6 + 5]);
+            cudaEventElapsedTime(&tb, ev[0], evPool[c * 6 + 0]);
+            cudaEventElapsedTime(&te, ev[0], evPool[c * 6 + 4]);
+            std::fprintf(stderr, "[cpq] chunk %zu: h2d_done %.2f compute %.2f..%.2f ms\n", c, tin, tb, te);
+        }
+        std::fprintf(stderr, "[cpq] total %.2f ms, h2d span %.2f, d2h span %.2f\n", timings.total_ms, timings.h2d_ms, timings.d2h_ms);
+    }
     if (tf[1] != 0)
     {
         CPQ_CUDA(cudaMemset(ticketFault.p + 1, 0, sizeof(unsigned)));
