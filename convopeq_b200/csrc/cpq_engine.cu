@@ -71,6 +71,7 @@ struct LayerDev
 {
     DevBuf<double2> H;      // [nH][Q][M]
     DevBuf<double2> tw;     // [P+1]
+    DevBuf<double2> ptw;    // per-pass radix-8 twiddle tables
     DevBuf<double> gain;    // [M] spectrum filter gain (when a FilterSpec is given)
     DevBuf<double> tilt;    // [M]
     bool hasGain = false, hasTilt = false;
@@ -314,6 +315,26 @@ cpq_status Engine::ensureTwiddles(int li)
     }
     CPQ_CUDA(L.tw.ensure((size_t) P + 1));
     CPQ_CUDA(cudaMemcpyAsync(L.tw.p, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
+    // compact per-pass tables {W^k, W^2k, W^4k}, W = exp(-2 pi i / (8 Ns)), for the radix-8 passes (FftCfg::passOffset)
+    std::vector<double2> ptw;
+    {
+        const int log2P = ilog2(P);
+        int ns = 1 << (log2P % 3);
+        const long double twoPi = 2.0L * 3.141592653589793238462643383279502884L;
+        for (int p = 0; p < log2P / 3; ++p, ns *= 8)
+        {
+            if (ns <= 1) continue;
+            for (int c = 1; c <= 4; c *= 2)
+                for (int k = 0; k < ns; ++k)
+                {
+                    const long double ang = twoPi * (long double) (c * k) / (long double) (8 * ns);
+                    ptw.push_back(make_double2((double) cosl(ang), (double) -sinl(ang)));
+                }
+        }
+        if (ptw.empty()) ptw.push_back(make_double2(1.0, 0.0));
+    }
+    CPQ_CUDA(L.ptw.ensure(ptw.size()));
+    CPQ_CUDA(cudaMemcpyAsync(L.ptw.p, ptw.data(), ptw.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
     CPQ_CUDA(cudaStreamSynchronize(stream));
     return CPQ_OK;
 }
@@ -401,6 +422,7 @@ cpq_status Engine::setImpulse(int stream_, int ch, const double* ir, int len, do
         a.outFramesPerSeq = l.numPartsIR;
         a.outFrameOffset = 0;
         a.tw = L.tw.p;
+        a.ptw = L.ptw.p;
         a.scale = scale;
         a.applyScale = std::fabs(scale - 1.0) > 1e-12 ? 1 : 0;
         a.gain = dGain;
@@ -446,12 +468,6 @@ static void buildBandConstants(const cpq_svf_coeffs& c, double* out /* kEqcStrid
     }
     long double A16[4] = { 1, 0, 0, 1 };
     for (int i = 0; i < kEqL; ++i) matmul2(A16, A, A16);
-    long double Tl[4] = { 1, 0, 0, 1 };
-    for (int lane = 0; lane < 32; ++lane)
-    {
-        for (int i = 0; i < 4; ++i) out[kEqcTl + 4 * lane + i] = (double) Tl[i];
-        matmul2(Tl, A16, Tl);
-    }
     long double M[4] = { A16[0], A16[1], A16[2], A16[3] };
     for (int d = 0; d < 5; ++d)
     {
@@ -756,6 +772,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 a.outFramesPerSeq = (int) K[li];
                 a.outFrameOffset = 0;
                 a.tw = layer[li].tw.p;
+                a.ptw = layer[li].ptw.p;
                 a.scale = 1.0;
                 cpq_status st = launchFwd(ilog2(l.partSize), a);
                 if (st != CPQ_OK) return st;
@@ -805,6 +822,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 a.out = li == 0 ? ioC : layer[li].tail.p;
                 a.outStride = li == 0 ? stride : (int64_t) K[li] * l.partSize;
                 a.tw = layer[li].tw.p;
+                a.ptw = layer[li].ptw.p;
                 cpq_status st = launchInv(ilog2(l.partSize), a);
                 if (st != CPQ_OK) return st;
             }

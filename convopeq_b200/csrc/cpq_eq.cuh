@@ -39,11 +39,10 @@ constexpr int kEqWarps = kEqThreads / 32;
 // per (parameter set, band) constants, all double; built by buildBandConstants() in cpq_engine.cu
 constexpr int kEqcCoef = 0;      // a1,a2,a3,m0,m1,m2, forceExact(!=0), pad
 constexpr int kEqcW = 8;         // w[16][2]   zero-state weights, c = sum_j w[j] * v0[j]
-constexpr int kEqcTl = 40;       // Tl[32][4]  A^(16*lane), row-major 2x2
-constexpr int kEqcMs = 168;      // Ms[5][4]   A^(16*2^d)
-constexpr int kEqcMw = 188;      // A^512
-constexpr int kEqcMt = 192;      // A^4096
-constexpr int kEqcStride = 196;  // doubles per band
+constexpr int kEqcMs = 40;       // Ms[5][4]   A^(16*2^d), row-major 2x2
+constexpr int kEqcMw = 60;       // A^512
+constexpr int kEqcMt = 64;       // A^4096
+constexpr int kEqcStride = 68;   // doubles per band (all 20 bands of a set = 10.9 KB, staged in shared memory)
 
 struct EqChain
 {
@@ -162,12 +161,21 @@ __device__ __noinline__ bool eq_exact_block(double* s /* smem, stride-1 over 16 
     return reset;
 }
 
+__device__ __forceinline__ void matvec2(const double* __restrict__ m, double& p1, double& p2, double add1, double add2)
+{
+    const double n1 = fma(m[0], p1, fma(m[1], p2, add1));
+    const double n2 = fma(m[2], p1, fma(m[3], p2, add2));
+    p1 = n1;
+    p2 = n2;
+}
+
 __global__ void __launch_bounds__(kEqThreads, 2) eq_kernel(EqArgs a)
 {
-    __shared__ double tile[kEqTile + kEqTile / 16];
+    __shared__ __align__(16) double tile[kEqTile + kEqTile / 16];
+    __shared__ __align__(16) double cst[CPQ_NUM_BANDS * kEqcStride];   // this sequence's band constants
     __shared__ double warpAggBuf[2][kEqWarps][2];   // double-buffered by band parity
     __shared__ double sIn[2];
-    __shared__ double carry[CPQ_NUM_BANDS][2];
+    __shared__ double carry[2][CPQ_NUM_BANDS][2];   // double-buffered by tile parity (one-CTA-per-sequence mode)
     __shared__ unsigned sTicket;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -183,20 +191,27 @@ __global__ void __launch_bounds__(kEqThreads, 2) eq_kernel(EqArgs a)
     const int set = a.doEq ? a.setOfSeq[seq] : 0;
     const unsigned mask = a.doEq ? a.bandMask[seq] : 0u;
     const double sat = a.doEq ? a.sat[set] : 0.0;
-    const double oneMinusSat = 1.0 - sat;
-    const double thr = sat > 0.0 ? 4.5 : 100.0;   // below this the reference's clamps/scrubs are identities
-    const double* eqcSet = a.eqc + (size_t) set * CPQ_NUM_BANDS * kEqcStride;
+    // y = out*(1-sat) + tanh27/9(out)*sat  ==  out * (27 + x2*(9 - 8 sat)) / (27 + 9 x2)
+    const double nsat = fma(-8.0, sat, 9.0);
+    const unsigned thrHi = sat > 0.0 ? 0x40120000u : 0x40590000u;   // high words of 4.5 / 100.0
     const bool chained = a.tilesPerRun == 1 && a.nRuns > 1;
     const int bmask = (1 << a.blockLog2) - 1;
     double* myStash = tile + eq_sidx(tid * kEqL);   // 16 consecutive slots (no pad boundary inside a block)
 
-    if (tid < CPQ_NUM_BANDS * 2) (&carry[0][0])[tid] = 0.0;
+    if (a.doEq)
+    {
+        const double* __restrict__ src = a.eqc + (size_t) set * CPQ_NUM_BANDS * kEqcStride;
+        for (int i = tid; i < CPQ_NUM_BANDS * kEqcStride / 2; i += kEqThreads)
+            reinterpret_cast<double2*>(cst)[i] = __ldg(reinterpret_cast<const double2*>(src) + i);
+    }
+    if (tid < 2 * CPQ_NUM_BANDS * 2) (&carry[0][0][0])[tid] = 0.0;
     __syncthreads();
 
     for (int tl = 0; tl < a.tilesPerRun; ++tl)
     {
         const int tileIdx = run * a.tilesPerRun + tl;
         if (tileIdx >= a.nTiles) break;
+        const int tpar = tl & 1;
         const int64_t t0 = (int64_t) tileIdx * kEqTile;
         const int nValid = (int) min((int64_t) kEqTile, a.T - t0);
 
@@ -240,13 +255,14 @@ __global__ void __launch_bounds__(kEqThreads, 2) eq_kernel(EqArgs a)
         __syncthreads();
 
         double x[kEqL];
-        bool suspicious = false;   // raw input large enough that a state could reach 1e15
+        unsigned hiMax = 0;   // running max of |x|'s high word: raw input large enough that a state could reach 1e15?
 #pragma unroll
         for (int j = 0; j < kEqL; ++j)
         {
             x[j] = myStash[j];
-            suspicious |= !(fabs(x[j]) < 1.0e9);
+            hiMax = max(hiMax, (unsigned) __double2hiint(x[j]) & 0x7fffffffu);
         }
+        bool suspicious = hiMax >= 0x41cdcd65u;   // |x| >= 1e9 (or NaN/Inf)
 
         if (a.doEq)
         {
@@ -256,13 +272,13 @@ __global__ void __launch_bounds__(kEqThreads, 2) eq_kernel(EqArgs a)
                 if (!((mask >> b) & 1u)) continue;   // uniform per CTA
                 double (*warpAgg)[2] = warpAggBuf[parity];
                 parity ^= 1;
-                const double* __restrict__ bc = eqcSet + (size_t) b * kEqcStride;
+                const double* __restrict__ bc = cst + b * kEqcStride;
                 // ---- pass 1: zero-state response of this thread's 16 samples; stash the inputs ----
                 double c1 = 0.0, c2 = 0.0;
 #pragma unroll
                 for (int j = 0; j < kEqL; ++j)
                 {
-                    const double2 w = __ldg(reinterpret_cast<const double2*>(bc + kEqcW) + j);
+                    const double2 w = reinterpret_cast<const double2*>(bc + kEqcW)[j];
                     c1 = fma(w.x, x[j], c1);
                     c2 = fma(w.y, x[j], c2);
                     myStash[j] = x[j];
@@ -275,10 +291,9 @@ __global__ void __launch_bounds__(kEqThreads, 2) eq_kernel(EqArgs a)
                     const double p2 = __shfl_up_sync(0xffffffffu, c2, 1 << d);
                     if (lane >= (1 << d))
                     {
-                        const double2 m01 = __ldg(reinterpret_cast<const double2*>(bc + kEqcMs + 4 * d));
-                        const double2 m23 = __ldg(reinterpret_cast<const double2*>(bc + kEqcMs + 4 * d) + 1);
-                        c1 = fma(m01.x, p1, fma(m01.y, p2, c1));
-                        c2 = fma(m23.x, p1, fma(m23.y, p2, c2));
+                        const double* m = bc + kEqcMs + 4 * d;
+                        c1 = fma(m[0], p1, fma(m[1], p2, c1));
+                        c2 = fma(m[2], p1, fma(m[3], p2, c2));
                     }
                 }
                 if (lane == 31) { warpAgg[warp][0] = c1; warpAgg[warp][1] = c2; }
@@ -288,55 +303,52 @@ __global__ void __launch_bounds__(kEqThreads, 2) eq_kernel(EqArgs a)
                 if (lane == 0) { e1 = 0.0; e2 = 0.0; }
                 __syncthreads();
 
-                const double2 mw01 = __ldg(reinterpret_cast<const double2*>(bc + kEqcMw));
-                const double2 mw23 = __ldg(reinterpret_cast<const double2*>(bc + kEqcMw) + 1);
-                if (tid == 0)
+                double p1, p2;   // state at the start of the tile
+                if (chained)
                 {
-                    // tile aggregate with zero carry-in, then the carry-in itself
-                    double g1 = 0.0, g2 = 0.0;
-                    for (int w = 0; w < kEqWarps; ++w)
+                    if (tid == 0)
                     {
-                        const double n1 = fma(mw01.x, g1, fma(mw01.y, g2, warpAgg[w][0]));
-                        const double n2 = fma(mw23.x, g1, fma(mw23.y, g2, warpAgg[w][1]));
-                        g1 = n1; g2 = n2;
+                        // tile aggregate with zero carry-in, then the carry-in from the previous tile's CTA
+                        double g1 = 0.0, g2 = 0.0;
+                        for (int w = 0; w < kEqWarps; ++w) matvec2(bc + kEqcMw, g1, g2, warpAgg[w][0], warpAgg[w][1]);
+                        double s1 = 0.0, s2 = 0.0;
+                        if (run > 0)
+                        {
+                            const double* rec = a.chain.rec + ((size_t) ((size_t) seq * a.nRuns + (run - 1)) * CPQ_NUM_BANDS + b) * 4;
+                            const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(rec + 2);
+                            while (ld_acquire_u64(flag) != a.chain.epoch) { __nanosleep(20); }
+                            s1 = ld_cg_f64(rec);
+                            s2 = ld_cg_f64(rec + 1);
+                        }
+                        if (run + 1 < a.nRuns)
+                        {
+                            double o1 = s1, o2 = s2;
+                            matvec2(bc + kEqcMt, o1, o2, g1, g2);
+                            double* rec = a.chain.rec + ((size_t) ((size_t) seq * a.nRuns + run) * CPQ_NUM_BANDS + b) * 4;
+                            rec[0] = o1;
+                            rec[1] = o2;
+                            st_release_u64(reinterpret_cast<unsigned long long*>(rec + 2), a.chain.epoch);
+                        }
+                        sIn[0] = s1; sIn[1] = s2;
                     }
-                    double s1 = carry[b][0], s2 = carry[b][1];
-                    if (chained && tl == 0 && run > 0)
-                    {
-                        const double* rec = a.chain.rec + ((size_t) ((size_t) seq * a.nRuns + (run - 1)) * CPQ_NUM_BANDS + b) * 4;
-                        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(rec + 2);
-                        while (ld_acquire_u64(flag) != a.chain.epoch) { __nanosleep(20); }
-                        s1 = ld_cg_f64(rec);
-                        s2 = ld_cg_f64(rec + 1);
-                    }
-                    const double2 mt01 = __ldg(reinterpret_cast<const double2*>(bc + kEqcMt));
-                    const double2 mt23 = __ldg(reinterpret_cast<const double2*>(bc + kEqcMt) + 1);
-                    const double o1 = fma(mt01.x, s1, fma(mt01.y, s2, g1));
-                    const double o2 = fma(mt23.x, s1, fma(mt23.y, s2, g2));
-                    if (chained && run + 1 < a.nRuns)
-                    {
-                        double* rec = a.chain.rec + ((size_t) ((size_t) seq * a.nRuns + run) * CPQ_NUM_BANDS + b) * 4;
-                        rec[0] = o1;
-                        rec[1] = o2;
-                        st_release_u64(reinterpret_cast<unsigned long long*>(rec + 2), a.chain.epoch);
-                    }
-                    sIn[0] = s1; sIn[1] = s2;
-                    carry[b][0] = o1; carry[b][1] = o2;   // carry into the next tile of this run
+                    __syncthreads();
+                    p1 = sIn[0]; p2 = sIn[1];
                 }
-                __syncthreads();
+                else
+                {
+                    p1 = carry[tpar][b][0]; p2 = carry[tpar][b][1];
+                }
 
-                // ---- state before this warp, then before this thread ----
-                double p1 = sIn[0], p2 = sIn[1];
-                for (int w = 0; w < warp; ++w)
+                // ---- state before this warp, then before this thread: A^(16 lane) p + e ----
+                for (int w = 0; w < warp; ++w) matvec2(bc + kEqcMw, p1, p2, warpAgg[w][0], warpAgg[w][1]);
+#pragma unroll
+                for (int d = 0; d < 5; ++d)
                 {
-                    const double n1 = fma(mw01.x, p1, fma(mw01.y, p2, warpAgg[w][0]));
-                    const double n2 = fma(mw23.x, p1, fma(mw23.y, p2, warpAgg[w][1]));
-                    p1 = n1; p2 = n2;
+                    double n1 = p1, n2 = p2;
+                    matvec2(bc + kEqcMs + 4 * d, n1, n2, 0.0, 0.0);
+                    if ((lane >> d) & 1) { p1 = n1; p2 = n2; }
                 }
-                const double2 tl01 = __ldg(reinterpret_cast<const double2*>(bc + kEqcTl + 4 * lane));
-                const double2 tl23 = __ldg(reinterpret_cast<const double2*>(bc + kEqcTl + 4 * lane) + 1);
-                double ic1 = fma(tl01.x, p1, fma(tl01.y, p2, e1));
-                double ic2 = fma(tl23.x, p1, fma(tl23.y, p2, e2));
+                double ic1 = p1 + e1, ic2 = p2 + e2;
                 const double s1_0 = ic1, s2_0 = ic2;
 
                 // final state of the sequence = state at sample T (T is a multiple of 16)
@@ -351,9 +363,10 @@ __global__ void __launch_bounds__(kEqThreads, 2) eq_kernel(EqArgs a)
                 }
 
                 // ---- pass 2, fast path: the reference recurrence (processBandStereo association) ----
-                const double a1 = __ldg(bc + 0), a2 = __ldg(bc + 1), a3 = __ldg(bc + 2);
-                const double m0 = __ldg(bc + 3), m1 = __ldg(bc + 4), m2 = __ldg(bc + 5);
-                bool rare = suspicious | !(fabs(ic1) < 1.0e12) | !(fabs(ic2) < 1.0e12) | (__ldg(bc + 6) != 0.0);
+                const double a1 = bc[0], a2 = bc[1], a3 = bc[2], m0 = bc[3], m1 = bc[4], m2 = bc[5];
+                hiMax = max((unsigned) __double2hiint(ic1) & 0x7fffffffu, (unsigned) __double2hiint(ic2) & 0x7fffffffu);
+                bool rare = suspicious | (hiMax >= 0x426d1a94u) | (bc[6] != 0.0);   // |state| >= 1e12
+                hiMax = 0;
                 if (sat > 0.0)
                 {
 #pragma unroll
@@ -366,10 +379,9 @@ __global__ void __launch_bounds__(kEqThreads, 2) eq_kernel(EqArgs a)
                         ic1 = fma(2.0, v1, -ic1);
                         ic2 = fma(2.0, v2, -ic2);
                         const double out = fma(m0, v0, fma(m1, v1, m2 * v2));
-                        rare |= !(fabs(out) < thr);
+                        hiMax = max(hiMax, (unsigned) __double2hiint(out) & 0x7fffffffu);
                         const double x2 = out * out;
-                        const double th = div_nr(out * (27.0 + x2), fma(9.0, x2, 27.0));
-                        x[j] = fma(th, sat, out * oneMinusSat);
+                        x[j] = div_nr(out * fma(x2, nsat, 27.0), fma(9.0, x2, 27.0));
                     }
                 }
                 else
@@ -384,11 +396,12 @@ __global__ void __launch_bounds__(kEqThreads, 2) eq_kernel(EqArgs a)
                         ic1 = fma(2.0, v1, -ic1);
                         ic2 = fma(2.0, v2, -ic2);
                         const double out = fma(m0, v0, fma(m1, v1, m2 * v2));
-                        rare |= !(fabs(out) < thr);
+                        hiMax = max(hiMax, (unsigned) __double2hiint(out) & 0x7fffffffu);
                         x[j] = out;
                     }
                 }
-                suspicious = false;   // outputs of a band are bounded by 100 (or replayed exactly below)
+                rare |= hiMax >= thrHi;   // some |out| >= 4.5 (100 without saturation), or NaN
+                suspicious = false;       // outputs of a band are bounded by 100 (or replayed exactly below)
                 if (rare)
                 {
                     // exact replay from the stashed inputs and the same start state
@@ -398,10 +411,16 @@ __global__ void __launch_bounds__(kEqThreads, 2) eq_kernel(EqArgs a)
 #pragma unroll
                     for (int j = 0; j < kEqL; ++j) x[j] = myStash[j];
                 }
-                if (t0 + kEqTile >= a.T && a.stateOut && (a.T - t0) == kEqTile && tid == kEqThreads - 1)
+                if (tid == kEqThreads - 1)
                 {
-                    a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2] = ic1;
-                    a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2 + 1] = ic2;
+                    // state after the tile's last sample: carry into the next tile of this run / final state
+                    carry[tpar ^ 1][b][0] = ic1;
+                    carry[tpar ^ 1][b][1] = ic2;
+                    if (a.stateOut && (a.T - t0) == kEqTile)
+                    {
+                        a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2] = ic1;
+                        a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2 + 1] = ic2;
+                    }
                 }
             }
         }

@@ -37,23 +37,6 @@ __device__ __forceinline__ double2 mul_i(double2 a)
 
 __device__ __forceinline__ int fft_pad(int i) { return i + (i >> 3); }
 
-// W_P^idx from the layer table tw[t] = exp(-2 pi i t / (2P)), t = 0..P; SIGN > 0 conjugates.
-template <int SIGN>
-__device__ __forceinline__ double2 twiddleP(const double2* __restrict__ tw, int P, int idx)
-{
-    const int t = 2 * idx;
-    double2 w;
-    if (t <= P) w = __ldg(tw + t);
-    else
-    {
-        w = __ldg(tw + (t - P));
-        w.x = -w.x;
-        w.y = -w.y;
-    }
-    if (SIGN > 0) w.y = -w.y;
-    return w;
-}
-
 template <int SIGN>
 __device__ __forceinline__ void dft2(double2& a, double2& b)
 {
@@ -113,18 +96,23 @@ __device__ __forceinline__ void dftR(double2* v)
 
 // One work item of a Stockham pass: n-point transform, sub-transform length Ns before the pass.
 // Reads in[j + r*n/R], twiddles by W_{Ns*R}^{k*r}, R-point DFT, result r goes to (j-k)*R + k + r*Ns.
+// Radix-8 passes take W^k, W^2k, W^4k from a compact per-pass table (unit stride in k, so the loads of a warp
+// coalesce) and form the other four powers by multiplication; ptw = {T1[Ns], T2[Ns], T4[Ns]} for this pass.
 template <int R, int SIGN, class LoadF>
-__device__ __forceinline__ void stockham_load(double2* v, int j, int n, int Ns, const double2* __restrict__ tw, int P, LoadF ld)
+__device__ __forceinline__ void stockham_load(double2* v, int j, int n, int Ns, const double2* __restrict__ ptw, LoadF ld)
 {
     const int k = j & (Ns - 1);
     const int stride = n / R;
-    const int tscale = n / (Ns * R);
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int r = 0; r < R; ++r) v[r] = ld(j + r * stride);
+    if (R == 8 && Ns > 1)
     {
-        double2 x = ld(j + r * stride);
-        if (r > 0 && Ns > 1) x = cmul(x, twiddleP<SIGN>(tw, P, k * r * tscale));
-        v[r] = x;
+        double2 w1 = __ldg(ptw + k), w2 = __ldg(ptw + Ns + k), w4 = __ldg(ptw + 2 * Ns + k);
+        if (SIGN > 0) { w1.y = -w1.y; w2.y = -w2.y; w4.y = -w4.y; }
+        const double2 w3 = cmul(w1, w2), w5 = cmul(w1, w4), w6 = cmul(w2, w4);
+        const double2 w7 = cmul(w3, w4);
+        v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
+        v[5] = cmul(v[5], w5); v[6] = cmul(v[6], w6); v[7] = cmul(v[7], w7);
     }
     dftR<R, SIGN>(v);
 }
@@ -148,7 +136,8 @@ struct FwdArgs
     double2* out;           // [nSeq][outFramesPerSeq][P+1]
     int outFramesPerSeq;    // >= K (row pitch of out per sequence, in frames)
     int outFrameOffset;     // frame f is stored at row f + outFrameOffset
-    const double2* tw;      // [P+1]
+    const double2* tw;      // [P+1]  exp(-2 pi i t / 2P), split pass
+    const double2* ptw;     // per-pass radix-8 tables, see FftCfg::passOffset
     double scale;           // applied when applyScale
     int applyScale;
     const double* gain;     // nullable [P+1]
@@ -166,10 +155,20 @@ struct FftCfg
     static constexpr int NPASS8 = LOG2P / 3;
     static constexpr int ROW = P + P / 8;                            // padded row, in double2
     static constexpr size_t SMEM = (size_t) FPC * ROW * sizeof(double2);
+    static constexpr int MINBLOCKS = THREADS <= 256 ? 4 : (THREADS <= 512 ? 2 : 1);
+    // radix-8 pass p works on sub-transform length Ns = R0 * 8^p; its table {T1,T2,T4}[Ns] starts here
+    __host__ __device__ static constexpr int passNs(int p) { int ns = R0; for (int i = 0; i < p; ++i) ns *= 8; return ns; }
+    __host__ __device__ static constexpr int passOffset(int p)
+    {
+        int off = 0;
+        for (int i = 0; i < p; ++i) if (passNs(i) > 1) off += 3 * passNs(i);
+        return off;
+    }
+    static constexpr int PTW_SIZE = passOffset(NPASS8);
 };
 
 template <int LOG2P>
-__global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS) fft_fwd_kernel(FwdArgs a)
+__global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOCKS) fft_fwd_kernel(FwdArgs a)
 {
     using C = FftCfg<LOG2P>;
     constexpr int P = C::P, TPF = C::TPF;
@@ -205,7 +204,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS) fft_fwd_kernel(FwdArgs
         constexpr int ITEMS = 8 / R;
         double2 v[ITEMS][R];
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) stockham_load<R, -1>(v[i], t + i * TPF, P, 1, a.tw, P, gload);
+        for (int i = 0; i < ITEMS; ++i) stockham_load<R, -1>(v[i], t + i * TPF, P, 1, a.ptw, gload);
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i)
         {
@@ -220,10 +219,10 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS) fft_fwd_kernel(FwdArgs
     for (int p = 0; p < C::NPASS8; ++p)
     {
         double2 v[8];
-        if (p == 0 && C::R0 == 1) stockham_load<8, -1>(v, t, P, Ns, a.tw, P, gload);
+        if (p == 0 && C::R0 == 1) stockham_load<8, -1>(v, t, P, Ns, a.ptw + C::passOffset(p), gload);
         else
         {
-            stockham_load<8, -1>(v, t, P, Ns, a.tw, P, sload);
+            stockham_load<8, -1>(v, t, P, Ns, a.ptw + C::passOffset(p), sload);
             __syncthreads();
         }
         const int ob = stockham_out_base<8>(t, Ns);
@@ -273,10 +272,11 @@ struct InvArgs
     double* out;            // [nSeq][outStride]; frame f -> out[f*P .. (f+1)*P)
     int64_t outStride;
     const double2* tw;
+    const double2* ptw;
 };
 
 template <int LOG2P>
-__global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS) fft_inv_kernel(InvArgs a)
+__global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOCKS) fft_inv_kernel(InvArgs a)
 {
     using C = FftCfg<LOG2P>;
     constexpr int P = C::P, TPF = C::TPF;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS) fft_inv_kernel(InvArgs
         constexpr int ITEMS = 8 / R;
         double2 v[ITEMS][R];
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) stockham_load<R, +1>(v[i], t + i * TPF, P, 1, a.tw, P, gload);
+        for (int i = 0; i < ITEMS; ++i) stockham_load<R, +1>(v[i], t + i * TPF, P, 1, a.ptw, gload);
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i)
         {
@@ -327,10 +327,10 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS) fft_inv_kernel(InvArgs
     for (int p = 0; p < C::NPASS8; ++p)
     {
         double2 v[8];
-        if (p == 0 && C::R0 == 1) stockham_load<8, +1>(v, t, P, Ns, a.tw, P, gload);
+        if (p == 0 && C::R0 == 1) stockham_load<8, +1>(v, t, P, Ns, a.ptw + C::passOffset(p), gload);
         else
         {
-            stockham_load<8, +1>(v, t, P, Ns, a.tw, P, sload);
+            stockham_load<8, +1>(v, t, P, Ns, a.ptw + C::passOffset(p), sload);
             if (p != C::NPASS8 - 1) __syncthreads();
         }
         if (p == C::NPASS8 - 1)
