@@ -44,7 +44,8 @@ def up_to_date() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + SOURCES
+    extra = [f"-D{k}={v}" for k, v in os.environ.items() if k.startswith("CPQ_") and k.isupper() and v.isdigit()]   # tuning knobs
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", LIB] + SOURCES
     out = subprocess.run(cmd, capture_output=True, text=True)
     log = out.stdout + out.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:

@@ -169,7 +169,10 @@ __device__ __forceinline__ void matvec2(const double* __restrict__ m, double& p1
     p2 = n2;
 }
 
-__global__ void __launch_bounds__(kEqThreads, 2) eq_kernel(EqArgs a)
+#ifndef CPQ_EQ_MINBLOCKS
+#define CPQ_EQ_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs a)
 {
     __shared__ __align__(16) double tile[kEqTile + kEqTile / 16];
     __shared__ __align__(16) double cst[CPQ_NUM_BANDS * kEqcStride];   // this sequence's band constants
