@@ -69,7 +69,7 @@ struct EqSet
 
 struct LayerDev
 {
-    DevBuf<double2> H;      // [nH][Q][M]
+    DevBuf<double2> H;      // [nH][Q][P] packed spectra
     DevBuf<double2> tw;     // [P+1]
     DevBuf<double2> ptw;    // per-pass radix-8 twiddle tables
     DevBuf<double> gain;    // [M] spectrum filter gain (when a FilterSpec is given)
@@ -380,8 +380,8 @@ cpq_status Engine::setImpulse(int stream_, int ch, const double* ir, int len, do
             const LayerPlan& l = plan.layers[li];
             cpq_status st = ensureTwiddles(li);
             if (st != CPQ_OK) return st;
-            CPQ_CUDA(layer[li].H.ensure((size_t) nH * l.numPartsIR * l.bins));
-            CPQ_CUDA(cudaMemsetAsync(layer[li].H.p, 0, (size_t) nH * l.numPartsIR * l.bins * sizeof(double2), stream));
+            CPQ_CUDA(layer[li].H.ensure((size_t) nH * l.numPartsIR * l.partSize));
+            CPQ_CUDA(cudaMemsetAsync(layer[li].H.p, 0, (size_t) nH * l.numPartsIR * l.partSize * sizeof(double2), stream));
         }
     }
     // Per-bin gains depend on the FilterSpec, which may differ between channels only in ways that keep the
@@ -418,7 +418,7 @@ cpq_status Engine::setImpulse(int stream_, int ch, const double* ir, int len, do
         a.halfOnly = 1;
         a.framesPerSeq = l.numPartsIR;
         a.totalFrames = l.numPartsIR;
-        a.out = L.H.p + (size_t) row * l.numPartsIR * l.bins;
+        a.out = L.H.p + (size_t) row * l.numPartsIR * l.partSize;
         a.outFramesPerSeq = l.numPartsIR;
         a.outFrameOffset = 0;
         a.tw = L.tw.p;
@@ -675,7 +675,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         {
             const LayerPlan& l = plan.layers[li];
             K[li] = gplan.framesNeeded[li];
-            perSeq += (size_t) K[li] * l.bins * sizeof(double2) * 2;
+            perSeq += (size_t) K[li] * l.partSize * sizeof(double2) * 2;
             if (li > 0) perSeq += (size_t) K[li] * l.partSize * sizeof(double);
         }
         chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) nSeq, cfg.workspace_bytes / std::max<size_t>(perSeq, 1)));
@@ -685,8 +685,8 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         for (int li = 0; li < plan.numLayers; ++li)
         {
             const LayerPlan& l = plan.layers[li];
-            CPQ_CUDA(layer[li].X.ensure((size_t) chunk * K[li] * l.bins));
-            CPQ_CUDA(layer[li].Y.ensure((size_t) chunk * K[li] * l.bins));
+            CPQ_CUDA(layer[li].X.ensure((size_t) chunk * K[li] * l.partSize));
+            CPQ_CUDA(layer[li].Y.ensure((size_t) chunk * K[li] * l.partSize));
             if (li > 0) CPQ_CUDA(layer[li].tail.ensure((size_t) chunk * K[li] * l.partSize + 2));
         }
     const size_t nChunks = (size_t) ((nSeq + chunk - 1) / chunk);
@@ -795,16 +795,28 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 a.H = layer[li].H.p;
                 a.Y = layer[li].Y.p;
                 a.K = (int) K[li];
-                a.M = l.bins;
+                a.P = l.partSize;
                 a.Q = l.numPartsIR;
                 a.qBegin = qb[li];
                 a.qEnd = qe[li];
-                a.hSeqStride = (int64_t) l.numPartsIR * l.bins;
+                a.hSeqStride = (int64_t) l.numPartsIR * l.partSize;
                 a.hSeqMod = cfg.shared_ir ? cfg.n_channels : 0;
                 if (!cfg.shared_ir) a.H += (size_t) s0 * a.hSeqStride;   // H rows are absolute sequence indices
-                constexpr int KT = 8, QT = 4;
-                dim3 grid((unsigned) ((l.bins + 127) / 128), (unsigned) ((K[li] + KT - 1) / KT), (unsigned) ns);
-                mac_kernel<KT, QT><<<grid, 128, 0, stream>>>(a);
+                // enough CTAs to fill the GPU a few times over, each amortising its H tile over >= 128 frames when possible
+                const int binTiles = l.partSize / kMacBins;
+                const int step = kMacGroups * kMacKT;
+                int fpc = (int) ((K[li] + step - 1) / step) * step;
+                while (fpc > 4 * step && (int64_t) binTiles * ns * ((K[li] + fpc - 1) / fpc) < 4 * 148 * 2) fpc = ((fpc / 2 + step - 1) / step) * step;
+                a.framesPerCta = fpc;
+                const size_t smem = (size_t) (a.qEnd - a.qBegin) * kMacBins * sizeof(double2);
+                static size_t macSmemSet = 0;
+                if (smem > macSmemSet)
+                {
+                    CPQ_CUDA(cudaFuncSetAttribute(mac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 64 * 1024)));
+                    macSmemSet = std::max<size_t>(smem, 64 * 1024);
+                }
+                dim3 grid((unsigned) binTiles, (unsigned) ((K[li] + fpc - 1) / fpc), (unsigned) ns);
+                mac_kernel<<<grid, kMacThreads, smem, stream>>>(a);
                 ++launches;
                 CPQ_CUDA(cudaGetLastError());
             }

@@ -133,7 +133,7 @@ struct FwdArgs
     int halfOnly;           // 1: only the first P samples of a frame are taken (IR partitions)
     int framesPerSeq;       // K
     int64_t totalFrames;    // nSeq * K
-    double2* out;           // [nSeq][outFramesPerSeq][P+1]
+    double2* out;           // [nSeq][outFramesPerSeq][P]  packed: slot 0 = (Re X[0], Re X[P])
     int outFramesPerSeq;    // >= K (row pitch of out per sequence, in frames)
     int outFrameOffset;     // frame f is stored at row f + outFrameOffset
     const double2* tw;      // [P+1]  exp(-2 pi i t / 2P), split pass
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOC
 
     // ---- split pass: X[m] = E + W_N^m O, X[P-m] = conj(E - W_N^m O) ----
     if (!live) return;
-    double2* out = a.out + ((size_t) seq * a.outFramesPerSeq + (size_t) (f + a.outFrameOffset)) * (size_t) (P + 1);
+    double2* out = a.out + ((size_t) seq * a.outFramesPerSeq + (size_t) (f + a.outFrameOffset)) * (size_t) P;   // packed row
     auto emit = [&](int m, double2 X) {
         if (a.applyScale) { X.x *= a.scale; X.y *= a.scale; }
         if (a.gain) { const double g = __ldg(a.gain + m); X.x *= g; X.y *= g; }
@@ -252,8 +252,12 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOC
         const double2 Tm = cmul(w, O);
         if (m == 0)
         {
-            emit(0, make_double2(E.x + O.x, 0.0));
-            emit(P, make_double2(E.x - O.x, 0.0));
+            // bins 0 and P are real: packed into slot 0 as (Re X[0], Re X[P])
+            double r0 = E.x + O.x, rP = E.x - O.x;
+            if (a.applyScale) { r0 *= a.scale; rP *= a.scale; }
+            if (a.gain) { r0 *= __ldg(a.gain); rP *= __ldg(a.gain + P); }
+            if (a.tilt) { r0 *= __ldg(a.tilt); rP *= __ldg(a.tilt + P); }
+            out[0] = make_double2(r0, rP);
         }
         else
         {
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOC
 
 struct InvArgs
 {
-    const double2* in;      // [nSeq][framesPerSeq][P+1]
+    const double2* in;      // [nSeq][framesPerSeq][P] packed
     int framesPerSeq;       // K (row pitch of `in`)
     int framesOut;          // frames f < framesOut are transformed per sequence
     int64_t totalFrames;    // nSeq * framesOut
@@ -288,15 +292,24 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOC
     double2* buf = smem_fft + (size_t) fl * C::ROW;
     const int64_t seq = live ? gf / a.framesOut : 0;
     const int f = live ? (int) (gf % a.framesOut) : 0;
-    const double2* Y = a.in + ((size_t) seq * a.framesPerSeq + (size_t) f) * (size_t) (P + 1);
+    const double2* Y = a.in + ((size_t) seq * a.framesPerSeq + (size_t) f) * (size_t) P;   // packed row
     const double invN = 1.0 / (double) (2 * P);
 
     // Z[m] = ((Y[m] + conj Y[P-m]) + i conj(W_N^m) (Y[m] - conj Y[P-m])) / N
     auto gload = [&](int m) -> double2 {
         if (!live) return make_double2(0.0, 0.0);
-        double2 ym = __ldg(Y + m);
-        double2 yc = cconj(__ldg(Y + (P - m)));
-        if (m == 0) { ym.y = 0.0; yc.y = 0.0; }   // imaginary parts of bins 0 and P are ignored (CCS contract)
+        double2 ym, yc;
+        if (m == 0)
+        {
+            const double2 y0 = __ldg(Y);   // packed (Re Y[0], Re Y[P]); imaginary parts of bins 0 and P do not exist
+            ym = make_double2(y0.x, 0.0);
+            yc = make_double2(y0.y, 0.0);
+        }
+        else
+        {
+            ym = __ldg(Y + m);
+            yc = cconj(__ldg(Y + (P - m)));
+        }
         const double2 S = cadd(ym, yc);
         const double2 D = csub(ym, yc);
         const double2 wc = cconj(__ldg(a.tw + m));
