@@ -802,18 +802,19 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 a.hSeqStride = (int64_t) l.numPartsIR * l.partSize;
                 a.hSeqMod = cfg.shared_ir ? cfg.n_channels : 0;
                 if (!cfg.shared_ir) a.H += (size_t) s0 * a.hSeqStride;   // H rows are absolute sequence indices
-                // enough CTAs to fill the GPU a few times over, each amortising its H tile over >= 128 frames when possible
+                // enough CTAs to fill the GPU a few times over, each amortising its H tile and ring warm-up over as many frames as possible
                 const int binTiles = l.partSize / kMacBins;
-                const int step = kMacGroups * kMacKT;
+                const int step = kMacSuper;
                 int fpc = (int) ((K[li] + step - 1) / step) * step;
-                while (fpc > 4 * step && (int64_t) binTiles * ns * ((K[li] + fpc - 1) / fpc) < 4 * 148 * 2) fpc = ((fpc / 2 + step - 1) / step) * step;
+                while (fpc > 2 * step && (int64_t) binTiles * ns * ((K[li] + fpc - 1) / fpc) < 4 * 148 * 2) fpc = ((fpc / 2 + step - 1) / step) * step;
                 a.framesPerCta = fpc;
-                const size_t smem = (size_t) (a.qEnd - a.qBegin) * kMacBins * sizeof(double2);
+                a.ringRows = macRingRows(a.qEnd - a.qBegin);
+                const size_t smem = macSmemBytes(a.qEnd - a.qBegin, a.ringRows);
                 static size_t macSmemSet = 0;
                 if (smem > macSmemSet)
                 {
-                    CPQ_CUDA(cudaFuncSetAttribute(mac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 64 * 1024)));
-                    macSmemSet = std::max<size_t>(smem, 64 * 1024);
+                    CPQ_CUDA(cudaFuncSetAttribute(mac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+                    macSmemSet = smem;
                 }
                 dim3 grid((unsigned) binTiles, (unsigned) ((K[li] + fpc - 1) / fpc), (unsigned) ns);
                 mac_kernel<<<grid, kMacThreads, smem, stream>>>(a);

@@ -9,13 +9,14 @@
 // products are formed, not their sum.
 //
 // Spectra are stored "packed": P complex slots per frame, slot 0 = (Re X[0], Re X[P]) -- bins 0 and P of a real
-// signal's spectrum are real -- so a row is exactly P * 16 bytes and every 64-bin tile is full.
+// signal's spectrum are real -- so a row is exactly P * 16 bytes and every 32-bin tile is full.
 //
-// One CTA owns 64 bins of one sequence and a range of frames.  The IR spectra tile H[q][64 bins] is staged in
-// shared memory once (cp.async) and reused for every frame; four thread groups work on four runs of KT = 8
-// consecutive output frames at a time.  Each thread keeps its 8 accumulators and a sliding window of 8 input
-// spectra in registers: per tap it loads one H value (shared memory) and one new X value (global, one step
-// ahead), so the FP64 pipe sees 32 DFMAs per two 16-byte loads.
+// One CTA owns 32 bins of one sequence and a range of frames.  Both operands are staged in shared memory with
+// cp.async: the IR spectra tile H[q][32] once, and the input spectra X[f][32] through a ring of rows that is
+// refilled one super-step (64 output frames) ahead of the arithmetic, so each X and H element is fetched from
+// HBM/L2 once per CTA and no FP64 warp ever waits on a global load.  Eight thread groups work on eight runs of
+// KT = 8 consecutive output frames; each thread keeps 8 accumulators and a sliding window of 8 input spectra
+// in registers and per tap reads one H and one new X value from shared memory: 32 DFMAs per two LDS.128.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -33,89 +34,125 @@ struct MacArgs
     int qBegin, qEnd;
     int64_t hSeqStride;  // elements between sequences in H
     int hSeqMod;         // H row = seq % hSeqMod when the IR pair is shared by all streams; 0 = seq
-    int framesPerCta;    // multiple of 4*KT
+    int framesPerCta;    // multiple of kMacSuper
+    int ringRows;        // >= 2*kMacSuper + (qEnd - qBegin) - 1
 };
 
-constexpr int kMacBins = 64;
-constexpr int kMacGroups = 4;
-constexpr int kMacThreads = kMacBins * kMacGroups;
+constexpr int kMacBins = 32;
+constexpr int kMacGroups = 8;
+constexpr int kMacThreads = kMacBins * kMacGroups;   // 256
 constexpr int kMacKT = 8;
+constexpr int kMacSuper = kMacGroups * kMacKT;       // 64 output frames per super-step
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
     const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all()
-{
-    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+inline size_t macSmemBytes(int nq, int ringRows) { return (size_t) (nq + ringRows) * kMacBins * sizeof(double2); }
+inline int macRingRows(int nq) { return 2 * kMacSuper + nq - 1; }
 
 __global__ void __launch_bounds__(kMacThreads, 2) mac_kernel(MacArgs a)
 {
     constexpr int KT = kMacKT;
-    extern __shared__ __align__(16) double2 Hs[];   // [qEnd - qBegin][64]
+    extern __shared__ __align__(16) double2 mac_smem[];
+    const int nq = a.qEnd - a.qBegin;
+    const int R = a.ringRows;
+    double2* Hs = mac_smem;                       // [nq][32]
+    double2* ring = mac_smem + nq * kMacBins;     // [R][32], row of frame f lives in slot f mod R
     const int ml = threadIdx.x & (kMacBins - 1);
     const int g = threadIdx.x / kMacBins;
-    const int m = blockIdx.x * kMacBins + ml;        // P is a multiple of 64: always in range
+    const int m0 = blockIdx.x * kMacBins;          // P is a multiple of 32: tiles are always full
     const int seq = blockIdx.z;
     const int kc0 = blockIdx.y * a.framesPerCta;
     const int kc1 = min(a.K, kc0 + a.framesPerCta);
-    const int nq = a.qEnd - a.qBegin;
     const int hrow = a.hSeqMod > 0 ? (seq % a.hSeqMod) : seq;
+    const double2* __restrict__ X = a.X + (size_t) seq * a.K * a.P + m0;
+    double2* __restrict__ Y = a.Y + (size_t) seq * a.K * a.P + m0 + ml;
 
-    // ---- stage the IR spectra tile ----
+    auto slotOf = [&](int f) -> int { int s = f % R; return s < 0 ? s + R : s; };
+    // rows [f0, f1) of the input spectra -> ring (zero rows outside [0, K): the Reset history / beyond the end)
+    auto fillRows = [&](int f0, int f1) {
+        const int n = (f1 - f0) * kMacBins;
+        for (int i = threadIdx.x; i < n; i += kMacThreads)
+        {
+            const int f = f0 + i / kMacBins, c = i & (kMacBins - 1);
+            double2* dst = ring + slotOf(f) * kMacBins + c;
+            if (f >= 0 && f < a.K) cp_async16(dst, X + (size_t) f * a.P + c);
+            else *dst = make_double2(0.0, 0.0);
+        }
+    };
+
+    // ---- stage the IR spectra tile and the first super-step's input rows ----
     {
-        const double2* __restrict__ H = a.H + (size_t) hrow * a.hSeqStride + (size_t) a.qBegin * a.P + (size_t) blockIdx.x * kMacBins;
+        const double2* __restrict__ H = a.H + (size_t) hrow * a.hSeqStride + (size_t) a.qBegin * a.P + m0;
         for (int i = threadIdx.x; i < nq * kMacBins; i += kMacThreads)
             cp_async16(Hs + i, H + (size_t) (i / kMacBins) * a.P + (i & (kMacBins - 1)));
-        cp_async_wait_all();
     }
+    fillRows(kc0 - a.qBegin - (nq - 1), kc0 - a.qBegin + kMacSuper);
+    cp_async_commit();
+    cp_async_wait0();
     __syncthreads();
 
-    const double2* __restrict__ X = a.X + (size_t) seq * a.K * a.P + m;
-    double2* __restrict__ Y = a.Y + (size_t) seq * a.K * a.P + m;
-    const bool packed = (m == 0);   // slot 0 holds two real bins: (re*re, im*im) instead of a complex product
+    const bool packed = (m0 + ml == 0);   // slot 0 holds two real bins: (re*re, im*im) instead of a complex product
 
-    auto loadX = [&](int f) -> double2 { return (f >= 0 && f < a.K) ? __ldg(X + (size_t) f * a.P) : make_double2(0.0, 0.0); };
-
-    for (int ks = kc0 + g * KT; ks < kc1; ks += kMacGroups * KT)
+    for (int ks0 = kc0; ks0 < kc1; ks0 += kMacSuper)
     {
-        double2 acc[KT], w[KT];
-#pragma unroll
-        for (int i = 0; i < KT; ++i)
+        // prefetch the rows that only the next super-step needs
+        if (ks0 + kMacSuper < kc1)
         {
-            acc[i] = make_double2(0.0, 0.0);
-            w[i] = loadX(ks + i - a.qBegin);   // logical window for tap qBegin
+            fillRows(ks0 - a.qBegin + kMacSuper, ks0 - a.qBegin + 2 * kMacSuper);
+            cp_async_commit();
         }
-        double2 nxt = loadX(ks - a.qBegin - 1);   // next older frame, one tap ahead
-        for (int q0 = 0; q0 < nq; q0 += KT)
+        const int ks = ks0 + g * KT;
+        if (ks < kc1)
         {
+            double2 acc[KT], w[KT];
+            int slot = slotOf(ks - a.qBegin);
 #pragma unroll
-            for (int u = 0; u < KT; ++u)
+            for (int i = 0; i < KT; ++i)
             {
-                const int q = q0 + u;
-                if (q < nq)   // uniform
-                {
-                    const double2 h = Hs[q * kMacBins + ml];
-                    const double hA = h.x, hB = packed ? 0.0 : -h.y, hC = packed ? 0.0 : h.y, hD = packed ? h.y : h.x;
-                    const double2 incoming = nxt;
-                    nxt = loadX(ks - (a.qBegin + q) - 2);
+                acc[i] = make_double2(0.0, 0.0);
+                int s = slot + i;
+                if (s >= R) s -= R;
+                w[i] = ring[s * kMacBins + ml];   // logical window for the first tap: frame ks + i - qBegin
+            }
+            slot = slot == 0 ? R - 1 : slot - 1;   // slot of frame ks - qBegin - 1
+            double2 nxt = ring[slot * kMacBins + ml];
+            for (int q0 = 0; q0 < nq; q0 += KT)
+            {
 #pragma unroll
-                    for (int i = 0; i < KT; ++i)
+                for (int u = 0; u < KT; ++u)
+                {
+                    const int q = q0 + u;
+                    if (q < nq)   // uniform
                     {
-                        const double2 x = w[(i + KT - u) % KT];   // logical w[i] at tap q
-                        acc[i].x = fma(x.x, hA, fma(x.y, hB, acc[i].x));
-                        acc[i].y = fma(x.x, hC, fma(x.y, hD, acc[i].y));
+                        const double2 h = Hs[q * kMacBins + ml];
+                        const double hA = h.x, hB = packed ? 0.0 : -h.y, hC = packed ? 0.0 : h.y, hD = packed ? h.y : h.x;
+                        const double2 incoming = nxt;
+                        slot = slot == 0 ? R - 1 : slot - 1;
+                        nxt = ring[slot * kMacBins + ml];   // frame ks - qBegin - q - 2 (unused after the last tap)
+#pragma unroll
+                        for (int i = 0; i < KT; ++i)
+                        {
+                            const double2 x = w[(i + KT - u) % KT];   // logical w[i] at tap q
+                            acc[i].x = fma(x.x, hA, fma(x.y, hB, acc[i].x));
+                            acc[i].y = fma(x.x, hC, fma(x.y, hD, acc[i].y));
+                        }
+                        // slide: logical w[i] <- w[i-1], w[0] <- frame ks - qBegin - q - 1; freed physical slot is (KT-1-u)
+                        w[(KT - 1 - u) % KT] = incoming;
                     }
-                    // slide: logical w[i] <- w[i-1], w[0] <- frame ks - q - 1; the freed physical slot is (KT-1-u)
-                    w[(KT - 1 - u) % KT] = incoming;
                 }
             }
-        }
 #pragma unroll
-        for (int i = 0; i < KT; ++i)
-            if (ks + i < kc1) Y[(size_t) (ks + i) * a.P] = acc[i];
+            for (int i = 0; i < KT; ++i)
+                if (ks + i < kc1) Y[(size_t) (ks + i) * a.P] = acc[i];
+        }
+        cp_async_wait0();
+        __syncthreads();
     }
 }
 
