@@ -17,6 +17,7 @@
 #include "../../include/cpq.h"
 #include "cpq_plan.hpp"
 #include "cpq_fft.cuh"
+#include "cpq_fft_large.cuh"
 #include "cpq_mac.cuh"
 #include "cpq_eq.cuh"
 
@@ -162,6 +163,9 @@ struct Engine
     cpq_status processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar);
     cpq_status processDevice(double* dIo, int64_t stride, int64_t T, unsigned stages) { return processCore(dIo, stride, T, stages, nullptr); }
     cpq_status launchFwd(int log2P, const FwdArgs& a);
+    cpq_status launchFwdLarge(int log2P, const FwdArgs& a);
+    cpq_status launchInvLarge(int log2P, const InvArgs& a);
+    DevBuf<double2> irScratchC;         // complex scratch for layer-2 IR partitions (P > 8192)
     cpq_status launchInv(int log2P, const InvArgs& a);
     cpq_status launchEq(EqArgs& a);
 };
@@ -212,7 +216,7 @@ cpq_status Engine::launchFwd(int log2P, const FwdArgs& a)
         case 11: e = fwdLaunch<11>(a, stream); break;
         case 12: e = fwdLaunch<12>(a, stream); break;
         case 13: e = fwdLaunch<13>(a, stream); break;
-        default: setError("partition size outside 64..8192 is not built yet"); return CPQ_ERR_UNSUPPORTED;
+        default: return launchFwdLarge(log2P, a);
     }
     ++launches;
     CPQ_CUDA(e);
@@ -232,10 +236,89 @@ cpq_status Engine::launchInv(int log2P, const InvArgs& a)
         case 11: e = invLaunch<11>(a, stream); break;
         case 12: e = invLaunch<12>(a, stream); break;
         case 13: e = invLaunch<13>(a, stream); break;
-        default: setError("partition size outside 64..8192 is not built yet"); return CPQ_ERR_UNSUPPORTED;
+        default: return launchInvLarge(log2P, a);
     }
     ++launches;
     CPQ_CUDA(e);
+    return CPQ_OK;
+}
+
+// ---- P > 8192: one kernel per radix pass, ping-pong between two global buffers (cpq_fft_large.cuh) ----
+template <int SIGN>
+static cudaError_t largePasses(const LargeFftArgs& la, double2*& cur, double2*& other, int log2P, cudaStream_t s, int64_t& launches)
+{
+    const int P = 1 << log2P;
+    int Ns = 1;
+    const int r0 = 1 << (log2P % 3);
+    auto grid = [&](int64_t n) { return (unsigned) ((n + 255) / 256); };
+    if (r0 == 2) { gfft_pass_kernel<2, SIGN><<<grid(la.totalFrames * (P / 2)), 256, 0, s>>>(la, cur, other, Ns); Ns *= 2; std::swap(cur, other); ++launches; }
+    else if (r0 == 4) { gfft_pass_kernel<4, SIGN><<<grid(la.totalFrames * (P / 4)), 256, 0, s>>>(la, cur, other, Ns); Ns *= 4; std::swap(cur, other); ++launches; }
+    for (int p = 0; p < log2P / 3; ++p)
+    {
+        gfft_pass_kernel<8, SIGN><<<grid(la.totalFrames * (P / 8)), 256, 0, s>>>(la, cur, other, Ns);
+        Ns *= 8;
+        std::swap(cur, other);
+        ++launches;
+    }
+    return cudaGetLastError();
+}
+
+cpq_status Engine::launchFwdLarge(int log2P, const FwdArgs& a)
+{
+    if (log2P > 16 || !a.scratch)
+    {
+        setError("partition size > 65536 (FFT > 131072) is not supported");
+        return CPQ_ERR_UNSUPPORTED;
+    }
+    LargeFftArgs la {};
+    la.P = 1 << log2P;
+    la.totalFrames = a.totalFrames;
+    la.framesPerSeq = a.framesPerSeq;
+    la.src = a.src; la.srcStride = a.srcStride; la.frameStart0 = a.frameStart0; la.lo = a.lo; la.hi = a.hi; la.halfOnly = a.halfOnly;
+    la.rowPitchFrames = a.outFramesPerSeq; la.rowOffset = a.outFrameOffset;
+    la.tw = a.tw; la.scale = a.scale; la.applyScale = a.applyScale; la.gain = a.gain; la.tilt = a.tilt;
+    const int nPasses = (log2P % 3 ? 1 : 0) + log2P / 3;
+    // start in the buffer that makes the last pass land in a.out
+    double2* cur = (nPasses % 2 == 0) ? a.out : a.scratch;
+    double2* other = (nPasses % 2 == 0) ? a.scratch : a.out;
+    la.a = cur;
+    const int64_t n = la.totalFrames * la.P;
+    gfft_load_fwd_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(la);
+    ++launches;
+    CPQ_CUDA(cudaGetLastError());
+    CPQ_CUDA(largePasses<-1>(la, cur, other, log2P, stream, launches));
+    const int64_t h = la.totalFrames * (la.P / 2 + 1);
+    gfft_split_fwd_kernel<<<(unsigned) ((h + 255) / 256), 256, 0, stream>>>(la, cur);   // cur == a.out
+    ++launches;
+    CPQ_CUDA(cudaGetLastError());
+    return CPQ_OK;
+}
+
+cpq_status Engine::launchInvLarge(int log2P, const InvArgs& a)
+{
+    if (log2P > 16 || !a.scratch)
+    {
+        setError("partition size > 65536 (FFT > 131072) is not supported");
+        return CPQ_ERR_UNSUPPORTED;
+    }
+    LargeFftArgs la {};
+    la.P = 1 << log2P;
+    la.totalFrames = a.totalFrames;
+    la.framesPerSeq = a.framesOut;
+    la.rowPitchFrames = a.framesPerSeq; la.rowOffset = 0;
+    la.dst = a.out; la.dstStride = a.outStride;
+    la.tw = a.tw;
+    double2* cur = const_cast<double2*>(a.in);
+    double2* other = a.scratch;
+    const int64_t h = la.totalFrames * (la.P / 2 + 1);
+    gfft_pre_inv_kernel<<<(unsigned) ((h + 255) / 256), 256, 0, stream>>>(la, cur);
+    ++launches;
+    CPQ_CUDA(cudaGetLastError());
+    CPQ_CUDA(largePasses<+1>(la, cur, other, log2P, stream, launches));
+    const int64_t n = la.totalFrames * (la.P / 2);
+    gfft_store_inv_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(la, cur);
+    ++launches;
+    CPQ_CUDA(cudaGetLastError());
     return CPQ_OK;
 }
 
@@ -358,9 +441,9 @@ cpq_status Engine::setImpulse(int stream_, int ch, const double* ir, int len, do
         return CPQ_ERR_INVALID;
     }
     for (int li = 0; li < p.numLayers; ++li)
-        if (p.layers[li].partSize > 8192)
+        if (p.layers[li].partSize > 65536)
         {
-            setError("set_impulse: layer partition > 8192 (FFT > 16384) is not built yet");
+            setError("set_impulse: layer partition > 65536 (FFT > 131072) is not supported");
             return CPQ_ERR_UNSUPPORTED;
         }
     if (planSet && !plan.sameGeometry(p))
@@ -427,6 +510,11 @@ cpq_status Engine::setImpulse(int stream_, int ch, const double* ir, int len, do
         a.applyScale = std::fabs(scale - 1.0) > 1e-12 ? 1 : 0;
         a.gain = dGain;
         a.tilt = dTilt;
+        if (l.partSize > 8192)
+        {
+            CPQ_CUDA(irScratchC.ensure((size_t) l.numPartsIR * l.partSize));
+            a.scratch = irScratchC.p;
+        }
         cpq_status st = launchFwd(ilog2(l.partSize), a);
         if (st != CPQ_OK) return st;
         // the host vectors g/t must outlive the async copies
@@ -773,6 +861,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 a.outFrameOffset = 0;
                 a.tw = layer[li].tw.p;
                 a.ptw = layer[li].ptw.p;
+                a.scratch = layer[li].Y.p;   // free until the MAC writes it
                 a.scale = 1.0;
                 cpq_status st = launchFwd(ilog2(l.partSize), a);
                 if (st != CPQ_OK) return st;
@@ -836,6 +925,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 a.outStride = li == 0 ? stride : (int64_t) K[li] * l.partSize;
                 a.tw = layer[li].tw.p;
                 a.ptw = layer[li].ptw.p;
+                a.scratch = layer[li].X.p;   // the MAC has consumed it
                 cpq_status st = launchInv(ilog2(l.partSize), a);
                 if (st != CPQ_OK) return st;
             }

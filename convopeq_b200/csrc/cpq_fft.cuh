@@ -142,6 +142,7 @@ struct FwdArgs
     int applyScale;
     const double* gain;     // nullable [P+1]
     const double* tilt;     // nullable [P+1]
+    double2* scratch;       // only for P > 8192 (cpq_fft_large.cuh): same geometry as out
 };
 
 template <int LOG2P>
@@ -277,6 +278,7 @@ struct InvArgs
     int64_t outStride;
     const double2* tw;
     const double2* ptw;
+    double2* scratch;       // only for P > 8192: same geometry as in (which is overwritten)
 };
 
 template <int LOG2P>

@@ -45,15 +45,15 @@ CONV_CASES = [
     (70000, 512, 65536, 48000.0, dict(tail_mode=0, tail_start_seconds=0.03)),   # air absorption tilt
     (70000, 512, 32768, 48000.0, dict(tail_mode=2)),
     (262144, 512, 98304, 96000.0, dict(sample_rate=96000.0)),                   # cfg3 geometry
+    (262144, 256, 65536, 96000.0, dict(sample_rate=96000.0)),                   # cfg3 at B=256: 256 / 2048 / 16384 (large-FFT path)
+    (300000, 2048, 262144, 48000.0, None),                                      # P1 = 16384, irregular plan
+    (2097152, 512, 131072, 192000.0, dict(sample_rate=192000.0)),               # cfg5 geometry: L2 56 x 32768, D2 60416, g2 1.1
+    (1200000, 1024, 262144, 48000.0, None),                                     # P2 = 65536 (FFT 131072)
 ]
 
 
 @pytest.mark.parametrize("ir_len,block,T,sr,kw", CONV_CASES)
 def test_convolver_matches_reference(checker, ir_len, block, T, sr, kw):
-    from convopeq_b200.engine import plan_layout
-    lay, _ = plan_layout(ir_len, block, capi.default_filter_spec(**kw) if kw is not None else None, 8)
-    if any(lay.layers[i].part_size > 8192 for i in range(lay.num_layers)):
-        pytest.skip("partition > 8192 not built yet")
     ir_l, ir_r = signals.synth_ir(ir_len, 2), signals.synth_ir(ir_len, 3)
     x = np.stack([signals.noise(T, 1), signals.noise(T, 11)])
     y, _, ospec = _run_conv(ir_l, ir_r, x, block, sr, kw)
