@@ -1,0 +1,96 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL on B200, gloo in CPU tests).
+
+Two ways the hot path shards:
+
+* by stream -- every (stream, channel) has its own convolver state and every stream its own EQ state
+  (ConvolverProcessor.h:669, EQProcessor.h:637), so ranks own contiguous stream ranges and there is NO
+  data-path collective.  `stream_range` is all that is needed.
+* by partition range, for one very long IR (BASELINE config 5) -- the convolver is linear in the IR, so each
+  rank multiply-accumulates only its share of the flattened (layer, partition) list and produces a partial
+  time-domain signal; one sum over ranks (NCCL reduce-scatter by channel pair over NVLink, or all-reduce)
+  yields the wet signal, after which EQ + epilogue run on the owning rank.  EQ and dither are sequential in
+  time per channel and are never time-sharded.
+
+Nothing here touches the arithmetic: the kernels are the same single-GPU kernels.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+
+def stream_range(n_streams: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced [begin, end) of streams owned by `rank`."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, extra = divmod(n_streams, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def partition_ranges(parts_per_layer: List[int], world: int) -> List[Tuple[int, int]]:
+    """Split the flattened (layer, partition) list into `world` contiguous [begin, end) ranges balanced by
+    multiply-accumulate work: a partition of layer l costs (P_l + 1) bins per P_l samples, i.e. the same per
+    output sample for every layer, so the balance is by partition count.  Ranges may be empty when there are
+    more ranks than partitions."""
+    total = sum(parts_per_layer)
+    out = []
+    for r in range(world):
+        out.append((total * r // world, total * (r + 1) // world))
+    return out
+
+
+def layer_slices(parts_per_layer: List[int], begin: int, end: int) -> List[Tuple[int, int]]:
+    """Per-layer [q_begin, q_end) covered by the flattened range [begin, end) (what cpq_set_partition_range applies)."""
+    out, base = [], 0
+    for q in parts_per_layer:
+        out.append((min(max(begin - base, 0), q), min(max(end - base, 0), q)))
+        base += q
+    return out
+
+
+def reduce_partials(partial, op_group=None, owner_of_row=None):
+    """Sum the ranks' partial wet signals in place.
+
+    `partial` is a torch tensor [n_seq, T] (CUDA + NCCL on the box, CPU + gloo in tests).  With
+    `owner_of_row` = None every rank gets the full sum (all-reduce).  Otherwise rows are reduced to their owning
+    rank only (reduce per owner: the reduce-scatter-by-channel of SURVEY 8e) and other ranks' rows are left
+    undefined."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(op_group) == 1:
+        return partial
+    if owner_of_row is None:
+        dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=op_group)
+        return partial
+    world = dist.get_world_size(op_group)
+    for owner in range(world):
+        rows = [i for i, o in enumerate(owner_of_row) if o == owner]
+        if not rows:
+            continue
+        lo, hi = min(rows), max(rows) + 1
+        if rows != list(range(lo, hi)):
+            raise ValueError("rows of one owner must be contiguous")
+        dist.reduce(partial[lo:hi], dst=owner, op=dist.ReduceOp.SUM, group=op_group)
+    return partial
+
+
+def process_partition_sharded(engine, io_tensor, T: int, rank: int, world: int, owner_of_row=None, stages_after=None):
+    """cfg 5: convolve with this rank's partition range, sum the partials over ranks, then EQ + epilogue.
+
+    `engine` is a ConvoPeqEngine whose impulses are the *full* IRs (every rank prepares the same engine);
+    `io_tensor` is this rank's CUDA tensor [n_seq, stride] holding the full input (replicated)."""
+    from . import capi
+    parts = []
+    lay = engine.layout()
+    for li in range(lay.num_layers):
+        parts.append(lay.layers[li].num_parts_ir)
+    ranges = partition_ranges(parts, world)
+    b, e = ranges[rank]
+    engine.set_partition_range(b, e)
+    stride = io_tensor.stride(0)
+    engine.process_device(io_tensor.data_ptr(), stride, T, capi.STAGE_CONV)
+    reduce_partials(io_tensor, owner_of_row=owner_of_row)
+    after = capi.STAGE_EQ | capi.STAGE_EPILOGUE if stages_after is None else stages_after
+    if after:
+        engine.process_device(io_tensor.data_ptr(), stride, T, after)
+    engine.set_partition_range(0, -1)
+    return io_tensor

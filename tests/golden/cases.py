@@ -1,0 +1,57 @@
+"""Golden-vector case table shared by the generator and the tests (shortened versions of BASELINE.json's configs)."""
+import numpy as np
+
+from tests import signals
+
+CONV_CASES = {
+    # cfg1a: 65,536 taps, block 512 -> L0 12x512 + L1 15x4096 (g1 1.4375, D1 7168); reference nullptr FilterSpec
+    "cfg1a_nospec": dict(ir_len=65536, block=512, T=16384, spec=None, seed=1),
+    # cfg1 with the production default FilterSpec (HC/LC Natural)
+    "cfg1_default_spec": dict(ir_len=65536, block=512, T=16384, spec={}, seed=2),
+    # cfg3 geometry @96 kHz: L0 23x512 + L1 62x4096
+    "cfg3_96k": dict(ir_len=262144, block=512, T=16384, spec=dict(sample_rate=96000.0), seed=3),
+    # cfg4 geometry: 131,072 taps
+    "cfg4_131k": dict(ir_len=131072, block=512, T=16384, spec={}, seed=4),
+    # three layers 64/512/4096
+    "three_layer_b64": dict(ir_len=65536, block=64, T=8192, spec=None, seed=5),
+    # irregular plan (tail drops/starves): B=1024 default
+    "irregular_b1024": dict(ir_len=65536, block=1024, T=32768, spec=None, seed=6),
+    # air-absorption tail mode with tilt + IR scale
+    "tailmode0_scaled": dict(ir_len=70000, block=512, T=16384, spec=dict(tail_mode=0, tail_start_seconds=0.03), seed=7, scale=0.37),
+    # impulse at n = B-1 (layout / onset check)
+    "impulse_at_511": dict(ir_len=65536, block=512, T=16384, spec=None, seed=8, impulse_at=511),
+}
+
+EQ_CASES = {
+    "cfg2_default": dict(sr=48000.0, block=512, T=16384, bands=dict(seed=7)),
+    "cfg2_sat0": dict(sr=48000.0, block=512, T=16384, bands=dict(seed=7), kw=dict(saturation=0.0)),
+    "stress_q20": dict(sr=48000.0, block=512, T=16384, bands=dict(seed=7, stress=True)),
+    "modes_types": dict(sr=96000.0, block=256, T=8192, bands=dict(seed=8, modes=[i % 3 for i in range(20)], types=[i % 5 for i in range(20)])),
+    "gain_ramp": dict(sr=48000.0, block=512, T=16384, bands=dict(seed=7), kw=dict(total_gain_db=0.0, gain_change_db=-6.0, gain_change_at=512 * 8)),
+}
+
+CHAIN_CASES = {
+    "cfg4_chain": dict(sr=48000.0, block=512, T=16384, ir_len=131072, spec={}, makeup=1.3, seed=11),
+}
+
+
+def conv_inputs(c):
+    ir = signals.synth_ir(c["ir_len"], 1000 + c["seed"])
+    if "impulse_at" in c:
+        x = signals.impulse(c["T"], c["impulse_at"])
+    else:
+        x = signals.noise(c["T"], 2000 + c["seed"])
+    return ir, x
+
+
+def eq_inputs(c):
+    bands = signals.band_params(**c["bands"])
+    xl, xr = signals.log_sweep(c["T"], c["sr"])
+    return bands, xl, xr
+
+
+def chain_inputs(c):
+    irs = (signals.synth_ir(c["ir_len"], 3000 + c["seed"]), signals.synth_ir(c["ir_len"], 3001 + c["seed"]))
+    bands = signals.band_params(4000 + c["seed"])
+    x = np.stack([signals.noise(c["T"], 5000 + c["seed"]), signals.noise(c["T"], 5001 + c["seed"])])
+    return irs, bands, x

@@ -1,0 +1,72 @@
+"""The C restatement against the reference's own translation units (oracle/_ref), where they were compiled.
+Skipped where the reference tree is absent (the golden vectors pin the restatement there)."""
+import numpy as np
+import pytest
+
+from oracle.bindings import FilterSpec
+from tests import signals
+
+CASES = [
+    (4096, 512, None, 16384), (65536, 512, None, 32768), (65536, 512, {}, 32768), (65536, 256, {}, 16384),
+    (65536, 64, None, 8192), (65536, 1024, None, 65536), (30000, 480, None, 24000), (2049, 256, dict(sample_rate=96000.0), 4096),
+    (70000, 512, dict(tail_mode=0, tail_start_seconds=0.03), 32768), (70000, 512, dict(tail_enabled=0), 16384),
+    (300000, 512, dict(tail_l1l2_multiplier=2, tail_strength=1.7), 65536), (50, 128, None, 1024),
+    (65536, 512, dict(hc_mode=0, lc_mode=1), 16384), (65536, 512, dict(hc_mode=2, sample_rate=44100.0), 16384),
+]
+
+
+@pytest.mark.parametrize("ir_len,block,kw,T", CASES)
+def test_nuc_restatement_equals_reference(oracle, ref, ir_len, block, kw, T):
+    ir = signals.synth_ir(ir_len, 2)
+    x = signals.noise(T, 1)
+    spec = FilterSpec(**kw) if kw is not None else None
+    yo, lo = oracle.nuc_run(ir, x, block, spec=spec)
+    yr, lr = ref.nuc_run(ir, x, block, spec=spec)
+    assert lo == lr
+    assert np.abs(yo - yr).max() <= 1e-13
+
+
+def test_nuc_spectra_equal_reference(oracle, ref):
+    ir = signals.synth_ir(70000, 4)
+    for kw in (None, {}, dict(tail_mode=0)):
+        spec = FilterSpec(**kw) if kw is not None else None
+        so, _ = oracle.nuc_spectra(ir, 512, 0.5, spec)
+        sr_, _ = ref.nuc_spectra(ir, 512, 0.5, spec)
+        for a, b in zip(so, sr_):
+            assert np.abs(a - b).max() <= 1e-13
+
+
+def test_non_block_sized_calls(oracle, ref):
+    """Add/Get with call sizes different from the prepared block size (ring latency path)."""
+    ir = signals.synth_ir(20000, 5)
+    x = signals.noise(9600, 3)
+    for call in (480, 100, 512):
+        yo, _ = oracle.nuc_run(ir, x, 512, call=call)
+        yr, _ = ref.nuc_run(ir, x, 512, call=call)
+        assert np.abs(yo - yr).max() <= 1e-13
+
+
+@pytest.mark.parametrize("name,bkw,kw", [
+    ("default", dict(seed=7), {}), ("sat0", dict(seed=7), dict(saturation=0.0)), ("stress", dict(seed=7, stress=True), {}),
+    ("modes", dict(seed=8, modes=[i % 3 for i in range(20)]), {}), ("types", dict(seed=9, types=[i % 5 for i in range(20)]), {}),
+    ("gain", dict(seed=7), dict(total_gain_db=-3.0)), ("ramp", dict(seed=7), dict(gain_change_db=-6.0, gain_change_at=512 * 20)),
+])
+def test_eq_restatement_equals_reference(oracle, ref, name, bkw, kw):
+    sr, T = 48000.0, 48000
+    T = T // 512 * 512
+    bands = signals.to_eqband(signals.band_params(**bkw))
+    xl, xr = signals.log_sweep(T, sr)
+    lo, ro, so = oracle.eq_run(bands, xl, xr, sr, 512, **kw)
+    lr, rr, s_r = ref.eq_run(bands, xl, xr, sr, 512, **kw)
+    scale = max(1.0, np.abs(lr).max())
+    assert np.abs(lo - lr).max() <= 1e-13 * scale and np.abs(ro - rr).max() <= 1e-13 * scale
+    assert np.abs(so - s_r).max() <= 1e-12 * scale
+
+
+def test_eq_is_block_size_independent(ref):
+    """with a settled gain ramp the reference EQ output does not depend on the callback size."""
+    sr, T = 48000.0, 9216
+    bands = signals.to_eqband(signals.band_params(7))
+    xl, xr = signals.log_sweep(T, sr)
+    outs = [ref.eq_run(bands, xl, xr, sr, b)[0] for b in (64, 512, 4608)]
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
