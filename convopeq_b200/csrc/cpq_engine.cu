@@ -890,6 +890,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 a.qEnd = qe[li];
                 a.hSeqStride = (int64_t) l.numPartsIR * l.partSize;
                 a.hSeqMod = cfg.shared_ir ? cfg.n_channels : 0;
+                a.seqBase = s0;
                 if (!cfg.shared_ir) a.H += (size_t) s0 * a.hSeqStride;   // H rows are absolute sequence indices
                 // enough CTAs to fill the GPU a few times over, each amortising its H tile and ring warm-up over as many frames as possible
                 const int binTiles = l.partSize / kMacBins;

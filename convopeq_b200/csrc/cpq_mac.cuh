@@ -33,7 +33,8 @@ struct MacArgs
     int K, P, Q;
     int qBegin, qEnd;
     int64_t hSeqStride;  // elements between sequences in H
-    int hSeqMod;         // H row = seq % hSeqMod when the IR pair is shared by all streams; 0 = seq
+    int hSeqMod;         // H row = (seqBase + seq) % hSeqMod when the IR pair is shared by all streams; 0 = seq
+    int seqBase;         // absolute index of this launch's first sequence (sequence chunks)
     int framesPerCta;    // multiple of kMacSuper
     int ringRows;        // >= 2*kMacSuper + (qEnd - qBegin) - 1
 };
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(kMacThreads, 2) mac_kernel(MacArgs a)
     const int seq = blockIdx.z;
     const int kc0 = blockIdx.y * a.framesPerCta;
     const int kc1 = min(a.K, kc0 + a.framesPerCta);
-    const int hrow = a.hSeqMod > 0 ? (seq % a.hSeqMod) : seq;
+    const int hrow = a.hSeqMod > 0 ? ((a.seqBase + seq) % a.hSeqMod) : seq;
     const double2* __restrict__ X = a.X + (size_t) seq * a.K * a.P + m0;
     double2* __restrict__ Y = a.Y + (size_t) seq * a.K * a.P + m0 + ml;
 

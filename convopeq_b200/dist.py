@@ -89,6 +89,10 @@ def process_partition_sharded(engine, io_tensor, T: int, rank: int, world: int, 
     stride = io_tensor.stride(0)
     engine.process_device(io_tensor.data_ptr(), stride, T, capi.STAGE_CONV)
     reduce_partials(io_tensor, owner_of_row=owner_of_row)
+    if io_tensor.is_cuda:
+        # the collective runs on torch's stream, the engine on its own: order them before the EQ stage reads the sum
+        import torch
+        torch.cuda.current_stream(io_tensor.device).synchronize()
     after = capi.STAGE_EQ | capi.STAGE_EPILOGUE if stages_after is None else stages_after
     if after:
         engine.process_device(io_tensor.data_ptr(), stride, T, after)

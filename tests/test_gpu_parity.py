@@ -325,3 +325,23 @@ def test_eq_large_signal_takes_the_exact_path(checker):
     assert np.abs(wl).max() > 4.5
     # scalar vs SSE tanh differ for |y| >= 4.5 only in the reference's *mono* path; stereo path is what we mirror
     assert np.abs(y[0] - wl).max() <= 1e-9 and np.abs(y[1] - wr).max() <= 1e-9
+
+
+def test_shared_ir_and_eq_across_sequence_chunks(checker):
+    """One IR pair / one EQ shared by all streams; the host entry point splits the batch into sequence chunks,
+    so channel -> IR row mapping must use absolute sequence indices."""
+    sr, block, T, n_streams = 48000.0, 512, 8192, 5
+    irs = [signals.synth_ir(9000, 40), signals.synth_ir(9000, 41)]
+    x = np.stack([signals.noise(T, 700 + i) for i in range(2 * n_streams)])
+    eng = ConvoPeqEngine(n_streams, 2, sr, block, T, shared_ir=True, shared_eq=True)
+    for ch in range(2):
+        eng.set_impulse(-1, ch, irs[ch])
+    params = signals.band_params(5)
+    eng.set_eq(-1, signals.to_band(params))
+    y = x.copy()
+    eng.process(y, capi.STAGE_CONV | capi.STAGE_EQ)
+    eng.close()
+    for s in range(n_streams):
+        c = [checker.nuc_run(irs[ch], x[2 * s + ch], block)[0] for ch in range(2)]
+        wl, wr, _ = checker.eq_run(signals.to_eqband(params), c[0], c[1], sr, block)
+        assert np.abs(y[2 * s] - wl).max() <= TOL and np.abs(y[2 * s + 1] - wr).max() <= TOL
