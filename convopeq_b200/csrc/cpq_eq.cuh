@@ -170,7 +170,7 @@ __device__ __forceinline__ void matvec2(const double* __restrict__ m, double& p1
 }
 
 #ifndef CPQ_EQ_MINBLOCKS
-#define CPQ_EQ_MINBLOCKS 3
+#define CPQ_EQ_MINBLOCKS 4
 #endif
 __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs a)
 {
