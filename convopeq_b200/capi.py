@@ -119,6 +119,8 @@ def load() -> C.CDLL:
                                   C.POINTER(C.c_int64)]
     L.cpq_probe_dfma_tflops.argtypes = [C.c_int, C.c_int]
     L.cpq_probe_dfma_tflops.restype = C.c_double
+    L.cpq_probe_dfma_latency.argtypes = [C.c_int]
+    L.cpq_probe_dfma_latency.restype = C.c_double
     _lib = L
     return L
 

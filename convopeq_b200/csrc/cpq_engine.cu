@@ -753,7 +753,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         }
     }
 
-    // ---- sequence chunking: bounded spectra workspace, and >= ~8 chunks so host copies overlap compute ----
+    // ---- sequence chunking: bounded spectra workspace, and ~32 chunks so host copies overlap compute ----
     int64_t K[CPQ_MAX_LAYERS] = {};
     int chunk = nSeq;
     if (doConv)
@@ -768,7 +768,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         }
         chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) nSeq, cfg.workspace_bytes / std::max<size_t>(perSeq, 1)));
     }
-    if (hostPlanar) chunk = std::max(1, std::min(chunk, (nSeq + 7) / 8));
+    if (hostPlanar) chunk = std::max(1, std::min(chunk, (nSeq + 31) / 32));   // short pipeline fill/drain
     if (doConv)
         for (int li = 0; li < plan.numLayers; ++li)
         {
@@ -1329,6 +1329,23 @@ cpq_status cpq_plan_layout(int ir_len, int block_size, const cpq_filter_spec* sp
         for (int li = 1; li < plan.numLayers; ++li)
             std::memcpy(src_offsets + (size_t) (li - 1) * n_callbacks, g.tailSrc[li].data(), (size_t) n_callbacks * sizeof(int64_t));
     return CPQ_OK;
+}
+
+/* Dependent DFMA latency in SM cycles (one warp, one chain). */
+double cpq_probe_dfma_latency(int device)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    double* d = nullptr;
+    long long* c = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess || cudaMalloc(&c, 8) != cudaSuccess) return -1.0;
+    const int iters = 1 << 16;
+    cpq::dfma_latency_kernel<<<1, 32>>>(d, c, iters);
+    cpq::dfma_latency_kernel<<<1, 32>>>(d, c, iters);
+    long long cyc = 0;
+    cudaMemcpy(&cyc, c, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    cudaFree(c);
+    return cudaGetLastError() == cudaSuccess ? (double) cyc / iters : -1.0;
 }
 
 /* DFMA throughput probe used by bench.py for the FP64-pipe roofline (not part of the reference path). */

@@ -521,4 +521,17 @@ __global__ void dfma_probe_kernel(double* out, int iters)
     if (s == 123.456) out[0] = s;
 }
 
+// Dependent-issue latency of DFMA: one warp, one chain.
+__global__ void dfma_latency_kernel(double* out, long long* cycles, int iters)
+{
+    double a = 1.0 + 1e-9 * threadIdx.x;
+    const double m = 1.0000001, c = 1e-12;
+    const long long t0 = clock64();
+#pragma unroll 16
+    for (int it = 0; it < iters; ++it) a = fma(a, m, c);
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+    if (a == 123.456) out[0] = a;
+}
+
 } // namespace cpq
