@@ -544,6 +544,7 @@ static void buildBandConstants(const cpq_svf_coeffs& c, double* out /* kEqcStrid
         const double r = (double) (A[1] * A[1] + A[3] * A[3]);
         const double lmax = 0.5 * (p + r) + std::sqrt(0.25 * (p - r) * (p - r) + q * q);   // largest eigenvalue of A^T A
         out[6] = (std::isfinite(lmax) && lmax <= 1.0 + 1e-9) ? 0.0 : 1.0;
+        out[7] = (c.m0 == 1.0 && c.m2 == 0.0) ? 1.0 : 0.0;   // Peaking pattern: out = v0 + m1 v1
     }
     // w[j] = A^(15-j) b
     long double v[2] = { b[0], b[1] };

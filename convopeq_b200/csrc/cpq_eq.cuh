@@ -37,7 +37,7 @@ constexpr int kEqTile = kEqThreads * kEqL;     // 4096
 constexpr int kEqWarps = kEqThreads / 32;
 
 // per (parameter set, band) constants, all double; built by buildBandConstants() in cpq_engine.cu
-constexpr int kEqcCoef = 0;      // a1,a2,a3,m0,m1,m2, forceExact(!=0), pad
+constexpr int kEqcCoef = 0;      // a1,a2,a3,m0,m1,m2, forceExact(!=0), peakingPattern(!=0)
 constexpr int kEqcW = 8;         // w[16][2]   zero-state weights, c = sum_j w[j] * v0[j]
 constexpr int kEqcMs = 40;       // Ms[5][4]   A^(16*2^d), row-major 2x2
 constexpr int kEqcMw = 60;       // A^512
@@ -169,6 +169,39 @@ __device__ __forceinline__ void matvec2(const double* __restrict__ m, double& p1
     p2 = n2;
 }
 
+// Pass 2 (fast path) over one thread's block.  SAT: fused saturation
+//   out*(1-s) + tanh27/9(out)*s  ==  out * (alpha + gamma / (out^2 + 3)),  alpha = (9-8s)/9, gamma = 8s/3
+// with 1/(out^2+3) from the hardware seed refined to ~2^-60 (r0 (1 + e + e^2)); the correction term is <= 18 % of the
+// result, so even the seed's 2^-20 would leave < 1e-12.  PEAK: bands with m0 == 1, m2 == 0 (every Peaking band) need
+// only out = v0 + m1 v1.
+template <bool SAT, bool PEAK>
+__device__ __forceinline__ void eq_pass2(double (&x)[kEqL], double& ic1, double& ic2, double a1, double a2, double a3, double m0,
+                                         double m1, double m2, double alpha, double gamma, unsigned& hiMax)
+{
+#pragma unroll
+    for (int j = 0; j < kEqL; ++j)
+    {
+        const double v0 = x[j];
+        const double v3 = v0 - ic2;
+        const double v1 = fma(a1, ic1, a2 * v3);
+        const double v2 = fma(a2, ic1, fma(a3, v3, ic2));
+        ic1 = fma(2.0, v1, -ic1);
+        ic2 = fma(2.0, v2, -ic2);
+        const double out = PEAK ? fma(m1, v1, v0) : fma(m0, v0, fma(m1, v1, m2 * v2));
+        hiMax = max(hiMax, (unsigned) __double2hiint(out) & 0x7fffffffu);
+        if (SAT)
+        {
+            const double d = fma(out, out, 3.0);
+            double r0;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+            const double e = fma(-d, r0, 1.0);
+            const double r = fma(r0, fma(e, e, e), r0);
+            x[j] = out * fma(gamma, r, alpha);
+        }
+        else x[j] = out;
+    }
+}
+
 #ifndef CPQ_EQ_MINBLOCKS
 #define CPQ_EQ_MINBLOCKS 4
 #endif
@@ -194,8 +227,7 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
     const int set = a.doEq ? a.setOfSeq[seq] : 0;
     const unsigned mask = a.doEq ? a.bandMask[seq] : 0u;
     const double sat = a.doEq ? a.sat[set] : 0.0;
-    // y = out*(1-sat) + tanh27/9(out)*sat  ==  out * (27 + x2*(9 - 8 sat)) / (27 + 9 x2)
-    const double nsat = fma(-8.0, sat, 9.0);
+    const double alpha = fma(-8.0, sat, 9.0) / 9.0, gamma = 8.0 * sat / 3.0;
     const unsigned thrHi = sat > 0.0 ? 0x40120000u : 0x40590000u;   // high words of 4.5 / 100.0
     const bool chained = a.tilesPerRun == 1 && a.nRuns > 1;
     const int bmask = (1 << a.blockLog2) - 1;
@@ -370,38 +402,16 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                 hiMax = max((unsigned) __double2hiint(ic1) & 0x7fffffffu, (unsigned) __double2hiint(ic2) & 0x7fffffffu);
                 bool rare = suspicious | (hiMax >= 0x426d1a94u) | (bc[6] != 0.0);   // |state| >= 1e12
                 hiMax = 0;
+                const bool peak = bc[7] != 0.0;   // m0 == 1 && m2 == 0
                 if (sat > 0.0)
                 {
-#pragma unroll
-                    for (int j = 0; j < kEqL; ++j)
-                    {
-                        const double v0 = x[j];
-                        const double v3 = v0 - ic2;
-                        const double v1 = fma(a1, ic1, a2 * v3);
-                        const double v2 = fma(a2, ic1, fma(a3, v3, ic2));
-                        ic1 = fma(2.0, v1, -ic1);
-                        ic2 = fma(2.0, v2, -ic2);
-                        const double out = fma(m0, v0, fma(m1, v1, m2 * v2));
-                        hiMax = max(hiMax, (unsigned) __double2hiint(out) & 0x7fffffffu);
-                        const double x2 = out * out;
-                        x[j] = div_nr(out * fma(x2, nsat, 27.0), fma(9.0, x2, 27.0));
-                    }
+                    if (peak) eq_pass2<true, true>(x, ic1, ic2, a1, a2, a3, m0, m1, m2, alpha, gamma, hiMax);
+                    else eq_pass2<true, false>(x, ic1, ic2, a1, a2, a3, m0, m1, m2, alpha, gamma, hiMax);
                 }
                 else
                 {
-#pragma unroll
-                    for (int j = 0; j < kEqL; ++j)
-                    {
-                        const double v0 = x[j];
-                        const double v3 = v0 - ic2;
-                        const double v1 = fma(a1, ic1, a2 * v3);
-                        const double v2 = fma(a2, ic1, fma(a3, v3, ic2));
-                        ic1 = fma(2.0, v1, -ic1);
-                        ic2 = fma(2.0, v2, -ic2);
-                        const double out = fma(m0, v0, fma(m1, v1, m2 * v2));
-                        hiMax = max(hiMax, (unsigned) __double2hiint(out) & 0x7fffffffu);
-                        x[j] = out;
-                    }
+                    if (peak) eq_pass2<false, true>(x, ic1, ic2, a1, a2, a3, m0, m1, m2, alpha, gamma, hiMax);
+                    else eq_pass2<false, false>(x, ic1, ic2, a1, a2, a3, m0, m1, m2, alpha, gamma, hiMax);
                 }
                 rare |= hiMax >= thrHi;   // some |out| >= 4.5 (100 without saturation), or NaN
                 suspicious = false;       // outputs of a band are bounded by 100 (or replayed exactly below)

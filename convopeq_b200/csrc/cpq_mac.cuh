@@ -56,9 +56,107 @@ __device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_g
 inline size_t macSmemBytes(int nq, int ringRows) { return (size_t) (nq + ringRows) * kMacBins * sizeof(double2); }
 inline int macRingRows(int nq) { return 2 * kMacSuper + nq - 1; }
 
-__global__ void __launch_bounds__(kMacThreads, 2) mac_kernel(MacArgs a)
+// PACKED = this CTA's tile contains slot 0, which holds two real bins: its product is (re*re, im*im) instead of a
+// complex product.  Only the first bin tile pays for the operand selects.
+template <bool PACKED>
+__device__ __forceinline__ void mac_body(const MacArgs& a, double2* __restrict__ Hs, double2* __restrict__ ring, int nq, int R,
+                                         int ml, int g, int kc0, int kc1, double2* __restrict__ Y, const double2* __restrict__ X,
+                                         int m0)
 {
     constexpr int KT = kMacKT;
+    const int rowBytes = kMacBins * (int) sizeof(double2);
+    const int ringBytes = R * rowBytes;
+    const char* ringB = reinterpret_cast<const char*>(ring) + ml * (int) sizeof(double2);
+    const char* hsB = reinterpret_cast<const char*>(Hs) + ml * (int) sizeof(double2);
+    const bool slot0 = PACKED && (m0 + ml == 0);
+
+    auto slotOf = [&](int f) -> int { int s = f % R; return s < 0 ? s + R : s; };
+    auto fillRows = [&](int f0, int f1) {
+        const int n = (f1 - f0) * kMacBins;
+        for (int i = threadIdx.x; i < n; i += kMacThreads)
+        {
+            const int f = f0 + i / kMacBins, c = i & (kMacBins - 1);
+            double2* dst = ring + slotOf(f) * kMacBins + c;
+            if (f >= 0 && f < a.K) cp_async16(dst, X + (size_t) f * a.P + c);
+            else *dst = make_double2(0.0, 0.0);
+        }
+    };
+
+    for (int ks0 = kc0; ks0 < kc1; ks0 += kMacSuper)
+    {
+        // prefetch the rows that only the next super-step needs
+        if (ks0 + kMacSuper < kc1)
+        {
+            fillRows(ks0 - a.qBegin + kMacSuper, ks0 - a.qBegin + 2 * kMacSuper);
+            cp_async_commit();
+        }
+        const int ks = ks0 + g * KT;
+        if (ks < kc1)
+        {
+            double2 acc[KT], w[KT];
+            int off = slotOf(ks - a.qBegin) * rowBytes;   // byte offset of frame ks - qBegin in the ring
+#pragma unroll
+            for (int i = 0; i < KT; ++i)
+            {
+                acc[i] = make_double2(0.0, 0.0);
+                int o = off + i * rowBytes;
+                if (o >= ringBytes) o -= ringBytes;
+                w[i] = *reinterpret_cast<const double2*>(ringB + o);   // logical window for the first tap: frame ks + i - qBegin
+            }
+            off -= rowBytes;
+            if (off < 0) off += ringBytes;
+            double2 nxt = *reinterpret_cast<const double2*>(ringB + off);   // frame ks - qBegin - 1
+            for (int q0 = 0; q0 < nq; q0 += KT)
+            {
+#pragma unroll
+                for (int u = 0; u < KT; ++u)
+                {
+                    const int q = q0 + u;
+                    if (q < nq)   // uniform
+                    {
+                        const double2 h = *reinterpret_cast<const double2*>(hsB + q * rowBytes);
+                        const double2 incoming = nxt;
+                        off -= rowBytes;
+                        if (off < 0) off += ringBytes;
+                        nxt = *reinterpret_cast<const double2*>(ringB + off);   // frame ks - qBegin - q - 2 (unused after the last tap)
+                        if (PACKED)
+                        {
+                            const double hA = h.x, hB = slot0 ? 0.0 : -h.y, hC = slot0 ? 0.0 : h.y, hD = slot0 ? h.y : h.x;
+#pragma unroll
+                            for (int i = 0; i < KT; ++i)
+                            {
+                                const double2 x = w[(i + KT - u) % KT];
+                                acc[i].x = fma(x.x, hA, fma(x.y, hB, acc[i].x));
+                                acc[i].y = fma(x.x, hC, fma(x.y, hD, acc[i].y));
+                            }
+                        }
+                        else
+                        {
+                            const double nhy = -h.y;
+#pragma unroll
+                            for (int i = 0; i < KT; ++i)
+                            {
+                                const double2 x = w[(i + KT - u) % KT];   // logical w[i] at tap q
+                                acc[i].x = fma(x.x, h.x, fma(x.y, nhy, acc[i].x));
+                                acc[i].y = fma(x.x, h.y, fma(x.y, h.x, acc[i].y));
+                            }
+                        }
+                        // slide: logical w[i] <- w[i-1], w[0] <- frame ks - qBegin - q - 1; freed physical slot is (KT-1-u)
+                        w[(KT - 1 - u) % KT] = incoming;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < KT; ++i)
+                if (ks + i < kc1) Y[(size_t) (ks + i) * a.P] = acc[i];
+        }
+        cp_async_wait0();
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kMacThreads, 2) mac_kernel(MacArgs a)
+{
     extern __shared__ __align__(16) double2 mac_smem[];
     const int nq = a.qEnd - a.qBegin;
     const int R = a.ringRows;
@@ -74,87 +172,29 @@ __global__ void __launch_bounds__(kMacThreads, 2) mac_kernel(MacArgs a)
     const double2* __restrict__ X = a.X + (size_t) seq * a.K * a.P + m0;
     double2* __restrict__ Y = a.Y + (size_t) seq * a.K * a.P + m0 + ml;
 
-    auto slotOf = [&](int f) -> int { int s = f % R; return s < 0 ? s + R : s; };
-    // rows [f0, f1) of the input spectra -> ring (zero rows outside [0, K): the Reset history / beyond the end)
-    auto fillRows = [&](int f0, int f1) {
-        const int n = (f1 - f0) * kMacBins;
-        for (int i = threadIdx.x; i < n; i += kMacThreads)
-        {
-            const int f = f0 + i / kMacBins, c = i & (kMacBins - 1);
-            double2* dst = ring + slotOf(f) * kMacBins + c;
-            if (f >= 0 && f < a.K) cp_async16(dst, X + (size_t) f * a.P + c);
-            else *dst = make_double2(0.0, 0.0);
-        }
-    };
-
     // ---- stage the IR spectra tile and the first super-step's input rows ----
     {
         const double2* __restrict__ H = a.H + (size_t) hrow * a.hSeqStride + (size_t) a.qBegin * a.P + m0;
         for (int i = threadIdx.x; i < nq * kMacBins; i += kMacThreads)
             cp_async16(Hs + i, H + (size_t) (i / kMacBins) * a.P + (i & (kMacBins - 1)));
+        const int f0 = kc0 - a.qBegin - (nq - 1), f1 = kc0 - a.qBegin + kMacSuper;
+        const int n = (f1 - f0) * kMacBins;
+        for (int i = threadIdx.x; i < n; i += kMacThreads)
+        {
+            const int f = f0 + i / kMacBins, c = i & (kMacBins - 1);
+            int s = f % R;
+            if (s < 0) s += R;
+            double2* dst = ring + s * kMacBins + c;
+            if (f >= 0 && f < a.K) cp_async16(dst, X + (size_t) f * a.P + c);
+            else *dst = make_double2(0.0, 0.0);
+        }
     }
-    fillRows(kc0 - a.qBegin - (nq - 1), kc0 - a.qBegin + kMacSuper);
     cp_async_commit();
     cp_async_wait0();
     __syncthreads();
 
-    const bool packed = (m0 + ml == 0);   // slot 0 holds two real bins: (re*re, im*im) instead of a complex product
-
-    for (int ks0 = kc0; ks0 < kc1; ks0 += kMacSuper)
-    {
-        // prefetch the rows that only the next super-step needs
-        if (ks0 + kMacSuper < kc1)
-        {
-            fillRows(ks0 - a.qBegin + kMacSuper, ks0 - a.qBegin + 2 * kMacSuper);
-            cp_async_commit();
-        }
-        const int ks = ks0 + g * KT;
-        if (ks < kc1)
-        {
-            double2 acc[KT], w[KT];
-            int slot = slotOf(ks - a.qBegin);
-#pragma unroll
-            for (int i = 0; i < KT; ++i)
-            {
-                acc[i] = make_double2(0.0, 0.0);
-                int s = slot + i;
-                if (s >= R) s -= R;
-                w[i] = ring[s * kMacBins + ml];   // logical window for the first tap: frame ks + i - qBegin
-            }
-            slot = slot == 0 ? R - 1 : slot - 1;   // slot of frame ks - qBegin - 1
-            double2 nxt = ring[slot * kMacBins + ml];
-            for (int q0 = 0; q0 < nq; q0 += KT)
-            {
-#pragma unroll
-                for (int u = 0; u < KT; ++u)
-                {
-                    const int q = q0 + u;
-                    if (q < nq)   // uniform
-                    {
-                        const double2 h = Hs[q * kMacBins + ml];
-                        const double hA = h.x, hB = packed ? 0.0 : -h.y, hC = packed ? 0.0 : h.y, hD = packed ? h.y : h.x;
-                        const double2 incoming = nxt;
-                        slot = slot == 0 ? R - 1 : slot - 1;
-                        nxt = ring[slot * kMacBins + ml];   // frame ks - qBegin - q - 2 (unused after the last tap)
-#pragma unroll
-                        for (int i = 0; i < KT; ++i)
-                        {
-                            const double2 x = w[(i + KT - u) % KT];   // logical w[i] at tap q
-                            acc[i].x = fma(x.x, hA, fma(x.y, hB, acc[i].x));
-                            acc[i].y = fma(x.x, hC, fma(x.y, hD, acc[i].y));
-                        }
-                        // slide: logical w[i] <- w[i-1], w[0] <- frame ks - qBegin - q - 1; freed physical slot is (KT-1-u)
-                        w[(KT - 1 - u) % KT] = incoming;
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < KT; ++i)
-                if (ks + i < kc1) Y[(size_t) (ks + i) * a.P] = acc[i];
-        }
-        cp_async_wait0();
-        __syncthreads();
-    }
+    if (m0 == 0) mac_body<true>(a, Hs, ring, nq, R, ml, g, kc0, kc1, Y, X, m0);
+    else mac_body<false>(a, Hs, ring, nq, R, ml, g, kc0, kc1, Y, X, m0);
 }
 
 } // namespace cpq
