@@ -544,7 +544,13 @@ static void buildBandConstants(const cpq_svf_coeffs& c, double* out /* kEqcStrid
         const double r = (double) (A[1] * A[1] + A[3] * A[3]);
         const double lmax = 0.5 * (p + r) + std::sqrt(0.25 * (p - r) * (p - r) + q * q);   // largest eigenvalue of A^T A
         out[6] = (std::isfinite(lmax) && lmax <= 1.0 + 1e-9) ? 0.0 : 1.0;
-        out[7] = (c.m0 == 1.0 && c.m2 == 0.0) ? 1.0 : 0.0;   // Peaking pattern: out = v0 + m1 v1
+        // TPT consistency (calcSVFCoeffs: a2 = g a1, a3 = g a2): lets pass 2 use v2 = ic2 + g v1.  g is recovered from
+        // the coefficients themselves so that raw cpq_set_eq input is classified the same way as designed bands.
+        const double g = (c.a1 != 0.0) ? c.a2 / c.a1 : 0.0;
+        const bool tpt = c.a1 != 0.0 && std::isfinite(g) && std::fabs(c.a3 - g * c.a2) <= 8.0 * 2.220446049250313e-16 * std::fabs(c.a3);
+        out[7] = !tpt ? 0.0 : ((c.m0 == 1.0 && c.m2 == 0.0) ? 1.0 : 2.0);   // 1: Peaking pattern, out = v0 + m1 v1
+        out[8] = g;
+        out[9] = 2.0 * g;
     }
     // w[j] = A^(15-j) b
     long double v[2] = { b[0], b[1] };
@@ -557,16 +563,33 @@ static void buildBandConstants(const cpq_svf_coeffs& c, double* out /* kEqcStrid
     }
     long double A16[4] = { 1, 0, 0, 1 };
     for (int i = 0; i < kEqL; ++i) matmul2(A16, A, A16);
+    // Plo[j] = A^(16 j), j < 8;  Phi[j] = A^(128 j), j < 4
+    {
+        long double M[4] = { 1, 0, 0, 1 };
+        for (int j = 0; j < 8; ++j)
+        {
+            for (int i = 0; i < 4; ++i) out[kEqcPlo + 4 * j + i] = (double) M[i];
+            matmul2(M, A16, M);
+        }
+        long double A128[4] = { M[0], M[1], M[2], M[3] };   // A^(16*8)
+        long double H[4] = { 1, 0, 0, 1 };
+        for (int j = 0; j < 4; ++j)
+        {
+            for (int i = 0; i < 4; ++i) out[kEqcPhi + 4 * j + i] = (double) H[i];
+            matmul2(H, A128, H);
+        }
+    }
     long double M[4] = { A16[0], A16[1], A16[2], A16[3] };
     for (int d = 0; d < 5; ++d)
     {
         for (int i = 0; i < 4; ++i) out[kEqcMs + 4 * d + i] = (double) M[i];
         matmul2(M, M, M);
     }
-    // M is now A^(16*32) = A^512
+    // M is now A^(16*32) = A^512 (one warp); a tile is kEqCWarps warps
     for (int i = 0; i < 4; ++i) out[kEqcMw + i] = (double) M[i];
-    for (int d = 0; d < 3; ++d) matmul2(M, M, M);   // ^8 -> A^4096
-    for (int i = 0; i < 4; ++i) out[kEqcMt + i] = (double) M[i];
+    long double Mt[4] = { 1, 0, 0, 1 };
+    for (int w = 0; w < kEqCWarps; ++w) matmul2(Mt, M, Mt);
+    for (int i = 0; i < 4; ++i) out[kEqcMt + i] = (double) Mt[i];
 }
 
 cpq_status Engine::uploadEq(int64_t nCallbacks)
@@ -664,25 +687,23 @@ cpq_status Engine::ensureGather(int64_t nCallbacks)
 
 cpq_status Engine::launchEq(EqArgs& a)
 {
-    a.nTiles = (int) ((a.T + kEqTile - 1) / kEqTile);
-    // one CTA per sequence when the batch alone fills the GPU, else one CTA per tile chained through
-    // (sequence, run, band) records
-    const bool wide = a.nSeq >= 888;   // 148 SMs x 3 resident CTAs x 2
-    a.tilesPerRun = (wide || !a.doEq) ? (a.doEq ? a.nTiles : 1) : 1;
-    a.nRuns = (a.nTiles + a.tilesPerRun - 1) / a.tilesPerRun;
+    // one CTA per (sequence, 3584-sample tile); tiles of a sequence are chained through (sequence, tile, band) records
+    a.nRuns = (int) ((a.T + kEqTile - 1) / kEqTile);
     ++epoch;
     a.chain.epoch = epoch;
     a.chain.ticket = ticketFault.p;
     a.fault = ticketFault.p + 1;
-    if (a.doEq && a.tilesPerRun == 1 && a.nRuns > 1)
-    {
-        CPQ_CUDA(chainRec.ensure((size_t) a.nSeq * a.nRuns * CPQ_NUM_BANDS * 4));
-        if (epoch == 1 || chainRec.n == 0) {}
-    }
+    if (a.doEq && a.nRuns > 1) CPQ_CUDA(chainRec.ensure((size_t) a.nSeq * a.nRuns * CPQ_NUM_BANDS * 4));
     a.chain.rec = chainRec.p;
+    static bool attrDone = false;
+    if (!attrDone)
+    {
+        CPQ_CUDA(cudaFuncSetAttribute(eq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytes));
+        attrDone = true;
+    }
     CPQ_CUDA(cudaMemsetAsync(ticketFault.p, 0, sizeof(unsigned), stream));
     const unsigned grid = (unsigned) a.nSeq * (unsigned) a.nRuns;
-    eq_kernel<<<grid, kEqThreads, 0, stream>>>(a);
+    eq_kernel<<<grid, kEqThreads, kEqSmemBytes, stream>>>(a);
     ++launches;
     CPQ_CUDA(cudaGetLastError());
     return CPQ_OK;

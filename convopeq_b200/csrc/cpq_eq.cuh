@@ -7,17 +7,28 @@
 //   dither_kernel  PsychoacousticDither::processStereoBlock (PsychoacousticDither.h:293-355)
 //
 // The band recurrence is linear in its 2-element state (the tanh saturation only touches the band *output*,
-// Processing.cpp:148-168), so each band is a blocked scan: every thread owns 16 consecutive samples in
-// registers, computes the zero-state response of its block with 16 precomputed weight vectors (pass 1), a
-// warp-shuffle + cross-warp prefix composes the per-block affine maps (all blocks share A^16), and pass 2
-// re-runs the reference recurrence from the exact start state.  Bands are processed in order on the same
-// registers, so a 4096-sample tile crosses HBM once for all 20 bands.  Across tiles the state is carried
-// either inside the CTA (one CTA per sequence when the batch fills the GPU) or through per-(sequence, tile,
-// band) records with release/acquire flags, tiles taking their index from an atomic ticket so that a
-// predecessor is always already running.
+// Processing.cpp:148-168), so each band is a blocked scan.  A CTA owns one 3584-sample tile of one sequence:
+// seven compute warps hold 16 consecutive samples per thread in registers, an eighth "chain" warp carries the
+// state between tiles.  Per band: pass 1 = zero-state response of each thread's block by 16 precomputed weight
+// vectors, warp-shuffle scan of s -> A^16 s + c, ONE CTA barrier, Horner fold over the preceding warps'
+// aggregates, a two-level table lookup for A^(16 lane), then pass 2 = the band recurrence from the exact start
+// state.  Bands are processed in order on the same registers, so a tile crosses HBM once for all 20 bands.
+//
+// Chain between tiles: tile r of a sequence needs, for every band, the state after tile r-1.  The chain warp
+// fetches record (seq, r-1, band) -- published by the predecessor CTA with release/acquire flags -- *before*
+// the band's barrier (while the compute warps are still busy with the previous band), and publishes
+// A^3584 s_in + (tile aggregate) for the successor after it.  The compute warps therefore never wait on global
+// memory.  Tiles take their index from an atomic ticket in run-major order, so a predecessor is always already
+// running (or done) when a CTA starts.
+//
+// Pass 2 arithmetic.  The reference designs every band as a TPT SVF (a2 = g a1, a3 = g a2,
+// EQProcessor.Coefficients.cpp:101-130), which gives v2 = ic2 + g v1 and ic2' = ic2 + 2 g v1; with
+// v1 = a1 ic1 - a2 ic2 + a2 v0 a Peaking band (m0 = 1, m2 = 0) costs 6 FP64 instructions per sample instead of the
+// 8 of the literal form, other TPT bands 8 instead of 10.  Coefficient sets that are not TPT-consistent (raw
+// cpq_set_eq input) run the literal form.  Differences to the reference's association are O(1e-16) relative.
 //
 // Fast path / exact path: with |out| < 4.5 before saturation the reference's clamps and scrubs are
-// identities, so pass 2 runs without them and ORs a per-thread flag; a flagged thread replays its block
+// identities, so pass 2 runs without them and tracks a per-thread maximum; a flagged thread replays its block
 // from the stashed inputs with the reference's full per-sample semantics.  If a *state* leaves the
 // reference's valid range (|ic| >= 1e15 or non-finite, where the reference zeroes it, :174-175/:257-258) the
 // scan's linearity assumption is void and the kernel raises `fault`; the host reports CPQ_ERR_UNSUPPORTED.
@@ -32,17 +43,24 @@ namespace cpq
 {
 
 constexpr int kEqThreads = 256;
-constexpr int kEqL = 16;                       // samples per thread
-constexpr int kEqTile = kEqThreads * kEqL;     // 4096
-constexpr int kEqWarps = kEqThreads / 32;
+constexpr int kEqCWarps = 7;                     // compute warps; warp 7 is the chain warp
+constexpr int kEqCThreads = kEqCWarps * 32;      // 224
+constexpr int kEqL = 16;                         // samples per compute thread
+constexpr int kEqTile = kEqCThreads * kEqL;      // 3584
+constexpr int kEqPad = kEqL + 2;                 // shared-memory doubles per thread block (keeps 16-byte alignment)
 
 // per (parameter set, band) constants, all double; built by buildBandConstants() in cpq_engine.cu
-constexpr int kEqcCoef = 0;      // a1,a2,a3,m0,m1,m2, forceExact(!=0), peakingPattern(!=0)
-constexpr int kEqcW = 8;         // w[16][2]   zero-state weights, c = sum_j w[j] * v0[j]
-constexpr int kEqcMs = 40;       // Ms[5][4]   A^(16*2^d), row-major 2x2
-constexpr int kEqcMw = 60;       // A^512
-constexpr int kEqcMt = 64;       // A^4096
-constexpr int kEqcStride = 68;   // doubles per band (all 20 bands of a set = 10.9 KB, staged in shared memory)
+constexpr int kEqcCoef = 0;      // a1,a2,a3,m0,m1,m2, forceExact(!=0), kind (0 literal, 1 TPT peaking, 2 TPT), g, 2g
+constexpr int kEqcW = 12;        // w[16][2]   zero-state weights, c = sum_j w[j] * v0[j]
+constexpr int kEqcMs = 44;       // Ms[5][4]   A^(16*2^d), row-major 2x2
+constexpr int kEqcPlo = 64;      // Plo[8][4]  A^(16*j)
+constexpr int kEqcPhi = 96;      // Phi[4][4]  A^(128*j)
+constexpr int kEqcMw = 112;      // A^512   (one warp)
+constexpr int kEqcMt = 116;      // A^3584  (one tile)
+constexpr int kEqcStride = 120;  // doubles per band (20 bands = 19.2 KB, staged in shared memory)
+
+constexpr int kEqSmemDoubles = kEqCThreads * kEqPad + CPQ_NUM_BANDS * kEqcStride + 2 * 8 * 2 + CPQ_NUM_BANDS * 2;
+constexpr size_t kEqSmemBytes = (size_t) kEqSmemDoubles * sizeof(double) + 16;
 
 struct EqChain
 {
@@ -57,9 +75,7 @@ struct EqArgs
     int64_t ioStride;
     int64_t T;              // samples per sequence
     int nSeq;
-    int nTiles;             // ceil(T / 4096)
-    int tilesPerRun;        // 1 (chained) or nTiles (one CTA per sequence)
-    int nRuns;
+    int nRuns;              // tiles per sequence = ceil(T / 3584); grid = nSeq * nRuns
     // assembly
     int assemble;           // add tails / apply the outer boundary
     int nTail;              // number of tail layers (0..2)
@@ -106,30 +122,19 @@ __device__ __forceinline__ double ld_cg_f64(const double* p)
     asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
-
-// num/den to < 1 ulp for den in [27, 210]: hardware reciprocal seed (~2^-20), one Newton step (~2^-40),
-// then a residual correction of the quotient (~2^-80 before rounding).  5 FP64-pipe instructions.
-__device__ __forceinline__ double div_nr(double num, double den)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
-    const double e = fma(-den, r, 1.0);
-    r = fma(r, e, r);
-    const double q = num * r;
-    const double rem = fma(-den, q, num);
-    return fma(rem, r, q);
-}
+// CTA barrier of the band loop (id 1): compute warps and the chain warp arrive from different code paths
+__device__ __forceinline__ void eq_band_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEqThreads) : "memory"); }
 
 __device__ __forceinline__ bool eq_valid(double v) { return fabs(v) < 1.0e15; }   // false for NaN / Inf too
 
-// padded shared index: 17-double stride per 16 samples keeps both the coalesced pass (consecutive t) and
-// the per-thread pass (16 consecutive samples per lane) free of bank conflicts
-__device__ __forceinline__ int eq_sidx(int t) { return t + (t >> 4); }
+// padded shared index: 18-double stride per 16 samples keeps every thread's block 16-byte aligned and both the
+// coalesced pass (consecutive t) and the per-thread LDS.128/STS.128 pass free of bank conflicts
+__device__ __forceinline__ int eq_sidx(int t) { return t + 2 * (t >> 4); }
 
 // The reference's per-sample semantics (processBandStereo) for one thread's block, run from shared memory.
 // Used only by threads whose fast pass saw |out| >= 4.5 / suspicious state.  Returns true if a state had to be
 // reset (which the scan cannot represent).
-__device__ __noinline__ bool eq_exact_block(double* s /* smem, stride-1 over 16 padded slots */, double& ic1, double& ic2,
+__device__ __noinline__ bool eq_exact_block(double* s /* smem, 16 consecutive slots */, double& ic1, double& ic2,
                                             double a1, double a2, double a3, double m0, double m1, double m2, double sat)
 {
     bool reset = false;
@@ -163,42 +168,70 @@ __device__ __noinline__ bool eq_exact_block(double* s /* smem, stride-1 over 16 
 
 __device__ __forceinline__ void matvec2(const double* __restrict__ m, double& p1, double& p2, double add1, double add2)
 {
-    const double n1 = fma(m[0], p1, fma(m[1], p2, add1));
-    const double n2 = fma(m[2], p1, fma(m[3], p2, add2));
+    const double2 r0 = *reinterpret_cast<const double2*>(m), r1 = *reinterpret_cast<const double2*>(m + 2);
+    const double n1 = fma(r0.x, p1, fma(r0.y, p2, add1));
+    const double n2 = fma(r1.x, p1, fma(r1.y, p2, add2));
     p1 = n1;
     p2 = n2;
 }
 
-// Pass 2 (fast path) over one thread's block.  SAT: fused saturation
-//   out*(1-s) + tanh27/9(out)*s  ==  out * (alpha + gamma / (out^2 + 3)),  alpha = (9-8s)/9, gamma = 8s/3
-// with 1/(out^2+3) from the hardware seed refined to ~2^-60 (r0 (1 + e + e^2)); the correction term is <= 18 % of the
-// result, so even the seed's 2^-20 would leave < 1e-12.  PEAK: bands with m0 == 1, m2 == 0 (every Peaking band) need
-// only out = v0 + m1 v1.
-template <bool SAT, bool PEAK>
-__device__ __forceinline__ void eq_pass2(double (&x)[kEqL], double& ic1, double& ic2, double a1, double a2, double a3, double m0,
-                                         double m1, double m2, double alpha, double gamma, unsigned& hiMax)
+// Pass 2 (fast path) over one thread's block.
+//   KIND 1  TPT Peaking  v1 = a1 ic1 - a2 ic2 + a2 v0;  out = v0 + m1 v1;  ic1' = 2 v1 - ic1;  ic2' = ic2 + 2g v1
+//   KIND 2  TPT general  ... v2 = ic2 + g v1;  out = m0 v0 + m1 v1 + m2 v2;  ic2' = 2 v2 - ic2
+//   KIND 0  literal processBandStereo form (coefficients that are not TPT-consistent)
+// SAT: fused saturation  out*(1-s) + tanh27/9(out)*s  ==  out * (alpha + gamma / (out^2 + 3)),  alpha = (9-8s)/9,
+// gamma = 8s/3, with 1/(out^2+3) from the hardware seed (2^-23) and one Newton step (2^-46); the correction term is
+// <= 18 % of the result.  hiMax tracks the high word of d = out^2 + 3 (SAT; d >= 23.25 <=> |out| >= 4.5 up to rounding,
+// NaN/Inf compare high) or of |out| (no SAT).
+template <bool SAT, int KIND>
+__device__ __forceinline__ void eq_pass2(double (&x)[kEqL], double& ic1, double& ic2, const double* __restrict__ bc, double alpha,
+                                         double gamma, unsigned& hiMax)
 {
+    const double a1 = bc[0], a2 = bc[1], a3 = bc[2], m0 = bc[3], m1 = bc[4], m2 = bc[5], g = bc[8], g2 = bc[9];
 #pragma unroll
     for (int j = 0; j < kEqL; ++j)
     {
         const double v0 = x[j];
-        const double v3 = v0 - ic2;
-        const double v1 = fma(a1, ic1, a2 * v3);
-        const double v2 = fma(a2, ic1, fma(a3, v3, ic2));
-        ic1 = fma(2.0, v1, -ic1);
-        ic2 = fma(2.0, v2, -ic2);
-        const double out = PEAK ? fma(m1, v1, v0) : fma(m0, v0, fma(m1, v1, m2 * v2));
-        hiMax = max(hiMax, (unsigned) __double2hiint(out) & 0x7fffffffu);
+        double out;
+        if (KIND == 1)
+        {
+            const double v1 = fma(a1, ic1, fma(-a2, ic2, a2 * v0));
+            out = fma(m1, v1, v0);
+            ic1 = fma(2.0, v1, -ic1);
+            ic2 = fma(g2, v1, ic2);
+        }
+        else if (KIND == 2)
+        {
+            const double v1 = fma(a1, ic1, fma(-a2, ic2, a2 * v0));
+            const double v2 = fma(g, v1, ic2);
+            out = fma(m0, v0, fma(m1, v1, m2 * v2));
+            ic1 = fma(2.0, v1, -ic1);
+            ic2 = fma(2.0, v2, -ic2);
+        }
+        else
+        {
+            const double v3 = v0 - ic2;
+            const double v1 = fma(a1, ic1, a2 * v3);
+            const double v2 = fma(a2, ic1, fma(a3, v3, ic2));
+            ic1 = fma(2.0, v1, -ic1);
+            ic2 = fma(2.0, v2, -ic2);
+            out = fma(m0, v0, fma(m1, v1, m2 * v2));
+        }
         if (SAT)
         {
             const double d = fma(out, out, 3.0);
+            hiMax = max(hiMax, (unsigned) __double2hiint(d));
             double r0;
             asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
             const double e = fma(-d, r0, 1.0);
-            const double r = fma(r0, fma(e, e, e), r0);
+            const double r = fma(r0, e, r0);
             x[j] = out * fma(gamma, r, alpha);
         }
-        else x[j] = out;
+        else
+        {
+            hiMax = max(hiMax, (unsigned) __double2hiint(out) & 0x7fffffffu);
+            x[j] = out;
+        }
     }
 }
 
@@ -207,18 +240,18 @@ __device__ __forceinline__ void eq_pass2(double (&x)[kEqL], double& ic1, double&
 #endif
 __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs a)
 {
-    __shared__ __align__(16) double tile[kEqTile + kEqTile / 16];
-    __shared__ __align__(16) double cst[CPQ_NUM_BANDS * kEqcStride];   // this sequence's band constants
-    __shared__ double warpAggBuf[2][kEqWarps][2];   // double-buffered by band parity
-    __shared__ double sIn[2];
-    __shared__ double carry[2][CPQ_NUM_BANDS][2];   // double-buffered by tile parity (one-CTA-per-sequence mode)
-    __shared__ unsigned sTicket;
+    extern __shared__ __align__(16) double eq_smem[];
+    double* tile = eq_smem;                                        // [224][18]
+    double* cst = tile + kEqCThreads * kEqPad;                     // this sequence's band constants
+    double2* warpAgg = reinterpret_cast<double2*>(cst + CPQ_NUM_BANDS * kEqcStride);   // [2][8], double-buffered by band parity
+    double2* sIn = warpAgg + 2 * 8;                                // [20] state at the start of the tile, per band
+    unsigned* sTicket = reinterpret_cast<unsigned*>(sIn + CPQ_NUM_BANDS);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) sTicket = atomicAdd(a.chain.ticket, 1u);
+    if (tid == 0) *sTicket = atomicAdd(a.chain.ticket, 1u);
     __syncthreads();
-    const unsigned ticket = sTicket;
-    // run-major ticket order: every predecessor (same sequence, previous run) holds a smaller ticket
+    const unsigned ticket = *sTicket;
+    // run-major ticket order: the predecessor (same sequence, previous tile) always holds a smaller ticket
     const int run = (int) (ticket / (unsigned) a.nSeq);
     const int seq = (int) (ticket % (unsigned) a.nSeq);
     if (run >= a.nRuns) return;
@@ -227,11 +260,9 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
     const int set = a.doEq ? a.setOfSeq[seq] : 0;
     const unsigned mask = a.doEq ? a.bandMask[seq] : 0u;
     const double sat = a.doEq ? a.sat[set] : 0.0;
-    const double alpha = fma(-8.0, sat, 9.0) / 9.0, gamma = 8.0 * sat / 3.0;
-    const unsigned thrHi = sat > 0.0 ? 0x40120000u : 0x40590000u;   // high words of 4.5 / 100.0
-    const bool chained = a.tilesPerRun == 1 && a.nRuns > 1;
     const int bmask = (1 << a.blockLog2) - 1;
-    double* myStash = tile + eq_sidx(tid * kEqL);   // 16 consecutive slots (no pad boundary inside a block)
+    const int64_t t0 = (int64_t) run * kEqTile;
+    const int nValid = (int) min((int64_t) kEqTile, a.T - t0);
 
     if (a.doEq)
     {
@@ -239,74 +270,115 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
         for (int i = tid; i < CPQ_NUM_BANDS * kEqcStride / 2; i += kEqThreads)
             reinterpret_cast<double2*>(cst)[i] = __ldg(reinterpret_cast<const double2*>(src) + i);
     }
-    if (tid < 2 * CPQ_NUM_BANDS * 2) (&carry[0][0][0])[tid] = 0.0;
-    __syncthreads();
 
-    for (int tl = 0; tl < a.tilesPerRun; ++tl)
+    // ---- coalesced load + layer assembly (Get) ----
+#pragma unroll 2
+    for (int i = tid; i < kEqTile; i += kEqThreads)
     {
-        const int tileIdx = run * a.tilesPerRun + tl;
-        if (tileIdx >= a.nTiles) break;
-        const int tpar = tl & 1;
-        const int64_t t0 = (int64_t) tileIdx * kEqTile;
-        const int nValid = (int) min((int64_t) kEqTile, a.T - t0);
-
-        // ---- coalesced load + layer assembly (Get) ----
-#pragma unroll 4
-        for (int i = tid; i < kEqTile; i += kEqThreads)
+        double v = 0.0;
+        if (i < nValid)
         {
-            double v = 0.0;
-            if (i < nValid)
+            const int64_t t = t0 + i;
+            v = io[t];
+            if (a.assemble)
             {
-                const int64_t t = t0 + i;
-                v = io[t];
-                if (a.assemble)
+                const int64_t c = t >> a.blockLog2;
+                const int off = (int) t & bmask;
+                for (int l = 0; l < a.nTail; ++l)
                 {
-                    const int64_t c = t >> a.blockLog2;
-                    const int off = (int) t & bmask;
-                    for (int l = 0; l < a.nTail; ++l)
+                    const int64_t s = __ldg(a.tailSrc[l] + c);
+                    if (s >= 0)
                     {
-                        const int64_t s = __ldg(a.tailSrc[l] + c);
-                        if (s >= 0)
+                        int64_t pos = s + off;
+                        if (a.blockMap[l])
                         {
-                            int64_t pos = s + off;
-                            if (a.blockMap[l])
-                            {
-                                const int64_t j = pos >> a.tailPartLog2[l];
-                                pos = ((int64_t) __ldg(a.blockMap[l] + j) << a.tailPartLog2[l]) + (pos - (j << a.tailPartLog2[l]));
-                            }
-                            const double tv = __ldg(a.tail[l] + (size_t) seq * a.tailStride[l] + pos);
-                            v += tv * a.tailGain[l];
+                            const int64_t j = pos >> a.tailPartLog2[l];
+                            pos = ((int64_t) __ldg(a.blockMap[l] + j) << a.tailPartLog2[l]) + (pos - (j << a.tailPartLog2[l]));
                         }
-                    }
-                    if (a.outer)
-                    {
-                        if (!(fabs(v) < 1.0e300)) v = 0.0;
-                        v *= a.wetGain;
+                        const double tv = __ldg(a.tail[l] + (size_t) seq * a.tailStride[l] + pos);
+                        v += tv * a.tailGain[l];
                     }
                 }
+                if (a.outer)
+                {
+                    if (!(fabs(v) < 1.0e300)) v = 0.0;
+                    v *= a.wetGain;
+                }
             }
-            tile[eq_sidx(i)] = v;
         }
-        __syncthreads();
+        tile[eq_sidx(i)] = v;
+    }
+    __syncthreads();
 
-        double x[kEqL];
-        unsigned hiMax = 0;   // running max of |x|'s high word: raw input large enough that a state could reach 1e15?
-#pragma unroll
-        for (int j = 0; j < kEqL; ++j)
-        {
-            x[j] = myStash[j];
-            hiMax = max(hiMax, (unsigned) __double2hiint(x[j]) & 0x7fffffffu);
-        }
-        bool suspicious = hiMax >= 0x41cdcd65u;   // |x| >= 1e9 (or NaN/Inf)
-
+    if (warp == kEqCWarps)
+    {
+        // ================= chain warp: state hand-over between the tiles of a sequence =================
         if (a.doEq)
         {
             int parity = 0;
             for (int b = 0; b < CPQ_NUM_BANDS; ++b)
             {
                 if (!((mask >> b) & 1u)) continue;   // uniform per CTA
-                double (*warpAgg)[2] = warpAggBuf[parity];
+                const double* __restrict__ bc = cst + b * kEqcStride;
+                double s1 = 0.0, s2 = 0.0;
+                if (lane == 0)
+                {
+                    if (run > 0)
+                    {
+                        const double* rec = a.chain.rec + ((size_t) ((size_t) seq * a.nRuns + (run - 1)) * CPQ_NUM_BANDS + b) * 4;
+                        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(rec + 2);
+                        while (ld_acquire_u64(flag) != a.chain.epoch) { __nanosleep(32); }
+                        s1 = ld_cg_f64(rec);
+                        s2 = ld_cg_f64(rec + 1);
+                    }
+                    sIn[b] = make_double2(s1, s2);
+                }
+                __syncwarp();
+                eq_band_barrier();   // band b: warp aggregates are in warpAgg[parity], sIn[b] is visible to the compute warps
+                if (lane == 0 && run + 1 < a.nRuns)
+                {
+                    double g1 = 0.0, g2 = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kEqCWarps; ++w)
+                    {
+                        const double2 ag = warpAgg[parity * 8 + w];
+                        matvec2(bc + kEqcMw, g1, g2, ag.x, ag.y);
+                    }
+                    matvec2(bc + kEqcMt, s1, s2, g1, g2);
+                    double* rec = a.chain.rec + ((size_t) ((size_t) seq * a.nRuns + run) * CPQ_NUM_BANDS + b) * 4;
+                    rec[0] = s1;
+                    rec[1] = s2;
+                    st_release_u64(reinterpret_cast<unsigned long long*>(rec + 2), a.chain.epoch);
+                }
+                __syncwarp();
                 parity ^= 1;
+            }
+        }
+    }
+    else
+    {
+        // ================= compute warps =================
+        double* myStash = tile + tid * kEqPad;   // 16 consecutive slots
+        double x[kEqL];
+        unsigned hiMax = 0;   // running max of |x|'s high word: raw input large enough that a state could reach 1e15?
+#pragma unroll
+        for (int j = 0; j < kEqL / 2; ++j)
+        {
+            const double2 v = reinterpret_cast<const double2*>(myStash)[j];
+            x[2 * j] = v.x;
+            x[2 * j + 1] = v.y;
+            hiMax = max(hiMax, max((unsigned) __double2hiint(v.x) & 0x7fffffffu, (unsigned) __double2hiint(v.y) & 0x7fffffffu));
+        }
+        bool suspicious = hiMax >= 0x41cdcd65u;   // |x| >= 1e9 (or NaN/Inf)
+
+        if (a.doEq)
+        {
+            const double alpha = fma(-8.0, sat, 9.0) / 9.0, gamma = 8.0 * sat / 3.0;
+            const unsigned thrHi = sat > 0.0 ? 0x40374000u : 0x40590000u;   // high words of 4.5^2 + 3 / of 100.0
+            int parity = 0;
+            for (int b = 0; b < CPQ_NUM_BANDS; ++b)
+            {
+                if (!((mask >> b) & 1u)) continue;   // uniform per CTA
                 const double* __restrict__ bc = cst + b * kEqcStride;
                 // ---- pass 1: zero-state response of this thread's 16 samples; stash the inputs ----
                 double c1 = 0.0, c2 = 0.0;
@@ -316,8 +388,9 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                     const double2 w = reinterpret_cast<const double2*>(bc + kEqcW)[j];
                     c1 = fma(w.x, x[j], c1);
                     c2 = fma(w.y, x[j], c2);
-                    myStash[j] = x[j];
                 }
+#pragma unroll
+                for (int j = 0; j < kEqL / 2; ++j) reinterpret_cast<double2*>(myStash)[j] = make_double2(x[2 * j], x[2 * j + 1]);
                 // ---- warp inclusive scan of s -> A^16 s + c ----
 #pragma unroll
                 for (int d = 0; d < 5; ++d)
@@ -326,70 +399,43 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                     const double p2 = __shfl_up_sync(0xffffffffu, c2, 1 << d);
                     if (lane >= (1 << d))
                     {
-                        const double* m = bc + kEqcMs + 4 * d;
-                        c1 = fma(m[0], p1, fma(m[1], p2, c1));
-                        c2 = fma(m[2], p1, fma(m[3], p2, c2));
+                        const double2 r0 = reinterpret_cast<const double2*>(bc + kEqcMs + 4 * d)[0];
+                        const double2 r1 = reinterpret_cast<const double2*>(bc + kEqcMs + 4 * d)[1];
+                        c1 = fma(r0.x, p1, fma(r0.y, p2, c1));
+                        c2 = fma(r1.x, p1, fma(r1.y, p2, c2));
                     }
                 }
-                if (lane == 31) { warpAgg[warp][0] = c1; warpAgg[warp][1] = c2; }
+                if (lane == 31) warpAgg[parity * 8 + warp] = make_double2(c1, c2);
                 // exclusive value (state contribution before this thread, relative to the warp start)
                 double e1 = __shfl_up_sync(0xffffffffu, c1, 1);
                 double e2 = __shfl_up_sync(0xffffffffu, c2, 1);
                 if (lane == 0) { e1 = 0.0; e2 = 0.0; }
-                __syncthreads();
+                eq_band_barrier();
 
-                double p1, p2;   // state at the start of the tile
-                if (chained)
+                // ---- state at the start of the tile -> of this warp (Horner over the preceding warps) -> of this thread ----
+                double p1, p2;
                 {
-                    if (tid == 0)
-                    {
-                        // tile aggregate with zero carry-in, then the carry-in from the previous tile's CTA
-                        double g1 = 0.0, g2 = 0.0;
-                        for (int w = 0; w < kEqWarps; ++w) matvec2(bc + kEqcMw, g1, g2, warpAgg[w][0], warpAgg[w][1]);
-                        double s1 = 0.0, s2 = 0.0;
-                        if (run > 0)
-                        {
-                            const double* rec = a.chain.rec + ((size_t) ((size_t) seq * a.nRuns + (run - 1)) * CPQ_NUM_BANDS + b) * 4;
-                            const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(rec + 2);
-                            while (ld_acquire_u64(flag) != a.chain.epoch) { __nanosleep(20); }
-                            s1 = ld_cg_f64(rec);
-                            s2 = ld_cg_f64(rec + 1);
-                        }
-                        if (run + 1 < a.nRuns)
-                        {
-                            double o1 = s1, o2 = s2;
-                            matvec2(bc + kEqcMt, o1, o2, g1, g2);
-                            double* rec = a.chain.rec + ((size_t) ((size_t) seq * a.nRuns + run) * CPQ_NUM_BANDS + b) * 4;
-                            rec[0] = o1;
-                            rec[1] = o2;
-                            st_release_u64(reinterpret_cast<unsigned long long*>(rec + 2), a.chain.epoch);
-                        }
-                        sIn[0] = s1; sIn[1] = s2;
-                    }
-                    __syncthreads();
-                    p1 = sIn[0]; p2 = sIn[1];
+                    const double2 s = sIn[b];
+                    p1 = s.x;
+                    p2 = s.y;
                 }
-                else
-                {
-                    p1 = carry[tpar][b][0]; p2 = carry[tpar][b][1];
-                }
-
-                // ---- state before this warp, then before this thread: A^(16 lane) p + e ----
-                for (int w = 0; w < warp; ++w) matvec2(bc + kEqcMw, p1, p2, warpAgg[w][0], warpAgg[w][1]);
 #pragma unroll
-                for (int d = 0; d < 5; ++d)
-                {
-                    double n1 = p1, n2 = p2;
-                    matvec2(bc + kEqcMs + 4 * d, n1, n2, 0.0, 0.0);
-                    if ((lane >> d) & 1) { p1 = n1; p2 = n2; }
-                }
-                double ic1 = p1 + e1, ic2 = p2 + e2;
-                const double s1_0 = ic1, s2_0 = ic2;
+                for (int w = 0; w < kEqCWarps - 1; ++w)
+                    if (w < warp)
+                    {
+                        const double2 ag = warpAgg[parity * 8 + w];
+                        matvec2(bc + kEqcMw, p1, p2, ag.x, ag.y);
+                    }
+                parity ^= 1;
+                matvec2(bc + kEqcPlo + 4 * (lane & 7), p1, p2, 0.0, 0.0);    // A^(16 (lane & 7))
+                matvec2(bc + kEqcPhi + 4 * (lane >> 3), p1, p2, e1, e2);     // A^(128 (lane >> 3)) ... + e
+                double ic1 = p1, ic2 = p2;
+                reinterpret_cast<double2*>(myStash)[kEqL / 2] = make_double2(ic1, ic2);   // start state, for the exact replay (pad slots)
 
                 // final state of the sequence = state at sample T (T is a multiple of 16)
                 if (t0 + kEqTile >= a.T && a.stateOut)
                 {
-                    const int64_t rem = a.T - t0;   // 1..4096
+                    const int64_t rem = a.T - t0;   // 1..3584
                     if (rem < kEqTile && tid == (int) (rem / kEqL))
                     {
                         a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2] = ic1;
@@ -397,75 +443,70 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                     }
                 }
 
-                // ---- pass 2, fast path: the reference recurrence (processBandStereo association) ----
-                const double a1 = bc[0], a2 = bc[1], a3 = bc[2], m0 = bc[3], m1 = bc[4], m2 = bc[5];
+                // ---- pass 2, fast path ----
                 hiMax = max((unsigned) __double2hiint(ic1) & 0x7fffffffu, (unsigned) __double2hiint(ic2) & 0x7fffffffu);
                 bool rare = suspicious | (hiMax >= 0x426d1a94u) | (bc[6] != 0.0);   // |state| >= 1e12
                 hiMax = 0;
-                const bool peak = bc[7] != 0.0;   // m0 == 1 && m2 == 0
+                const int kind = (int) bc[7];
                 if (sat > 0.0)
                 {
-                    if (peak) eq_pass2<true, true>(x, ic1, ic2, a1, a2, a3, m0, m1, m2, alpha, gamma, hiMax);
-                    else eq_pass2<true, false>(x, ic1, ic2, a1, a2, a3, m0, m1, m2, alpha, gamma, hiMax);
+                    if (kind == 1) eq_pass2<true, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                    else if (kind == 2) eq_pass2<true, 2>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                    else eq_pass2<true, 0>(x, ic1, ic2, bc, alpha, gamma, hiMax);
                 }
                 else
                 {
-                    if (peak) eq_pass2<false, true>(x, ic1, ic2, a1, a2, a3, m0, m1, m2, alpha, gamma, hiMax);
-                    else eq_pass2<false, false>(x, ic1, ic2, a1, a2, a3, m0, m1, m2, alpha, gamma, hiMax);
+                    if (kind == 1) eq_pass2<false, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                    else if (kind == 2) eq_pass2<false, 2>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                    else eq_pass2<false, 0>(x, ic1, ic2, bc, alpha, gamma, hiMax);
                 }
                 rare |= hiMax >= thrHi;   // some |out| >= 4.5 (100 without saturation), or NaN
                 suspicious = false;       // outputs of a band are bounded by 100 (or replayed exactly below)
                 if (rare)
                 {
                     // exact replay from the stashed inputs and the same start state
-                    ic1 = s1_0;
-                    ic2 = s2_0;
-                    if (eq_exact_block(myStash, ic1, ic2, a1, a2, a3, m0, m1, m2, sat)) atomicExch(a.fault, 1u);
+                    ic1 = myStash[kEqL];
+                    ic2 = myStash[kEqL + 1];
+                    if (eq_exact_block(myStash, ic1, ic2, bc[0], bc[1], bc[2], bc[3], bc[4], bc[5], sat)) atomicExch(a.fault, 1u);
 #pragma unroll
                     for (int j = 0; j < kEqL; ++j) x[j] = myStash[j];
                 }
-                if (tid == kEqThreads - 1)
+                if (tid == kEqCThreads - 1 && a.stateOut && (a.T - t0) == kEqTile)
                 {
-                    // state after the tile's last sample: carry into the next tile of this run / final state
-                    carry[tpar ^ 1][b][0] = ic1;
-                    carry[tpar ^ 1][b][1] = ic2;
-                    if (a.stateOut && (a.T - t0) == kEqTile)
-                    {
-                        a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2] = ic1;
-                        a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2 + 1] = ic2;
-                    }
+                    // state after the tile's last sample = final state when the last tile is full
+                    a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2] = ic1;
+                    a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2 + 1] = ic2;
                 }
             }
         }
-
-        // ---- store: total gain ramp, makeup, headroom ----
 #pragma unroll
-        for (int j = 0; j < kEqL; ++j) myStash[j] = x[j];
-        __syncthreads();
-#pragma unroll 4
-        for (int i = tid; i < nValid; i += kEqThreads)
+        for (int j = 0; j < kEqL / 2; ++j) reinterpret_cast<double2*>(myStash)[j] = make_double2(x[2 * j], x[2 * j + 1]);
+    }
+    __syncthreads();
+
+    // ---- store: total gain ramp, makeup, headroom ----
+#pragma unroll 2
+    for (int i = tid; i < nValid; i += kEqThreads)
+    {
+        double v = tile[eq_sidx(i)];
+        const int64_t t = t0 + i;
+        if (a.doEq)
         {
-            double v = tile[eq_sidx(i)];
-            const int64_t t = t0 + i;
-            if (a.doEq)
+            if (a.gainTab)
             {
-                if (a.gainTab)
-                {
-                    const int64_t c = t >> a.blockLog2;
-                    const int off = (int) t & bmask;
-                    const double2 g = __ldg(reinterpret_cast<const double2*>(a.gainTab) + (size_t) set * a.nCallbacks + c);
-                    v *= fma((double) off, g.y, g.x);
-                }
-                else v *= __ldg(a.gainConst + set);
+                const int64_t c = t >> a.blockLog2;
+                const int off = (int) t & bmask;
+                const double2 g = __ldg(reinterpret_cast<const double2*>(a.gainTab) + (size_t) set * a.nCallbacks + c);
+                v *= fma((double) off, g.y, g.x);
             }
-            if (a.doEpilogue)
-            {
-                v *= a.makeup;
-                if (a.applyHeadroom) v *= 0.8912509381337456;
-            }
-            io[t] = v;
+            else v *= __ldg(a.gainConst + set);
         }
-        __syncthreads();
+        if (a.doEpilogue)
+        {
+            v *= a.makeup;
+            if (a.applyHeadroom) v *= 0.8912509381337456;
+        }
+        io[t] = v;
     }
 }
 

@@ -11,12 +11,15 @@
 // Spectra are stored "packed": P complex slots per frame, slot 0 = (Re X[0], Re X[P]) -- bins 0 and P of a real
 // signal's spectrum are real -- so a row is exactly P * 16 bytes and every 32-bin tile is full.
 //
-// One CTA owns 32 bins of one sequence and a range of frames.  Both operands are staged in shared memory with
-// cp.async: the IR spectra tile H[q][32] once, and the input spectra X[f][32] through a ring of rows that is
-// refilled one super-step (64 output frames) ahead of the arithmetic, so each X and H element is fetched from
-// HBM/L2 once per CTA and no FP64 warp ever waits on a global load.  Eight thread groups work on eight runs of
-// KT = 8 consecutive output frames; each thread keeps 8 accumulators and a sliding window of 8 input spectra
-// in registers and per tap reads one H and one new X value from shared memory: 32 DFMAs per two LDS.128.
+// One CTA owns 32 bins of one sequence and a range of frames.  Both operands are staged in shared memory by the
+// TMA engine (cp.async.bulk, one 512-byte row per copy, completion on an mbarrier): the IR spectra tile H[q][32]
+// once, and the input spectra X[f][32] through a ring of rows that is refilled one super-step (64 output frames)
+// ahead of the arithmetic (eight rows per warp), so each X and H element is fetched from HBM/L2 once per CTA, no FP64 warp
+// ever waits on a global load and no thread spends instructions on per-element copy addressing.  Eight thread
+// groups work on eight runs of KT = 8 consecutive output frames; each thread keeps 8 accumulators and a sliding
+// window of 8 input spectra in registers and per tap reads one H and one new X value from shared memory: 32 DFMAs
+// per two LDS.128.  Taps are consumed in fully unrolled blocks of 8 (one full rotation of the register window, so
+// the rotation costs no moves) plus one compile-time-sized remainder block.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -44,157 +47,209 @@ constexpr int kMacGroups = 8;
 constexpr int kMacThreads = kMacBins * kMacGroups;   // 256
 constexpr int kMacKT = 8;
 constexpr int kMacSuper = kMacGroups * kMacKT;       // 64 output frames per super-step
+constexpr int kMacRowBytes = kMacBins * (int) sizeof(double2);   // 512
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
-{
-    const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-inline size_t macSmemBytes(int nq, int ringRows) { return (size_t) (nq + ringRows) * kMacBins * sizeof(double2); }
+inline size_t macSmemBytes(int nq, int ringRows) { return (size_t) (nq + ringRows) * kMacRowBytes + 16; }
 inline int macRingRows(int nq) { return 2 * kMacSuper + nq - 1; }
 
+// ---- mbarrier / bulk-copy (TMA engine) primitives ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dstSmem, const void* srcGlobal, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dstSmem)),
+                 "l"(srcGlobal), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// NT consecutive taps starting at H row q0, window in canonical order at entry (w[i] = frame ks + i - qBegin - q0,
+// nxt = the frame before w[0]); canonical again on exit iff NT == KT.
 // PACKED = this CTA's tile contains slot 0, which holds two real bins: its product is (re*re, im*im) instead of a
 // complex product.  Only the first bin tile pays for the operand selects.
-template <bool PACKED>
-__device__ __forceinline__ void mac_body(const MacArgs& a, double2* __restrict__ Hs, double2* __restrict__ ring, int nq, int R,
-                                         int ml, int g, int kc0, int kc1, double2* __restrict__ Y, const double2* __restrict__ X,
-                                         int m0)
+template <int NT, bool PACKED>
+__device__ __forceinline__ void mac_taps(double2 (&acc)[kMacKT], double2 (&w)[kMacKT], double2& nxt, const char* __restrict__ hsRow,
+                                         const char* __restrict__ ringB, int& off, int ringBytes, bool slot0)
 {
     constexpr int KT = kMacKT;
-    const int rowBytes = kMacBins * (int) sizeof(double2);
-    const int ringBytes = R * rowBytes;
-    const char* ringB = reinterpret_cast<const char*>(ring) + ml * (int) sizeof(double2);
-    const char* hsB = reinterpret_cast<const char*>(Hs) + ml * (int) sizeof(double2);
-    const bool slot0 = PACKED && (m0 + ml == 0);
-
-    auto slotOf = [&](int f) -> int { int s = f % R; return s < 0 ? s + R : s; };
-    auto fillRows = [&](int f0, int f1) {
-        const int n = (f1 - f0) * kMacBins;
-        for (int i = threadIdx.x; i < n; i += kMacThreads)
-        {
-            const int f = f0 + i / kMacBins, c = i & (kMacBins - 1);
-            double2* dst = ring + slotOf(f) * kMacBins + c;
-            if (f >= 0 && f < a.K) cp_async16(dst, X + (size_t) f * a.P + c);
-            else *dst = make_double2(0.0, 0.0);
-        }
-    };
-
-    for (int ks0 = kc0; ks0 < kc1; ks0 += kMacSuper)
+#pragma unroll
+    for (int u = 0; u < NT; ++u)
     {
-        // prefetch the rows that only the next super-step needs
-        if (ks0 + kMacSuper < kc1)
+        const double2 h = *reinterpret_cast<const double2*>(hsRow + u * kMacRowBytes);
+        const double2 incoming = nxt;
+        off -= kMacRowBytes;
+        if (off < 0) off += ringBytes;
+        nxt = *reinterpret_cast<const double2*>(ringB + off);   // two frames before w[0] of this tap (unused after the last tap)
+        if (PACKED)
         {
-            fillRows(ks0 - a.qBegin + kMacSuper, ks0 - a.qBegin + 2 * kMacSuper);
-            cp_async_commit();
-        }
-        const int ks = ks0 + g * KT;
-        if (ks < kc1)
-        {
-            double2 acc[KT], w[KT];
-            int off = slotOf(ks - a.qBegin) * rowBytes;   // byte offset of frame ks - qBegin in the ring
+            const double hA = h.x, hB = slot0 ? 0.0 : -h.y, hC = slot0 ? 0.0 : h.y, hD = slot0 ? h.y : h.x;
 #pragma unroll
             for (int i = 0; i < KT; ++i)
             {
-                acc[i] = make_double2(0.0, 0.0);
-                int o = off + i * rowBytes;
-                if (o >= ringBytes) o -= ringBytes;
-                w[i] = *reinterpret_cast<const double2*>(ringB + o);   // logical window for the first tap: frame ks + i - qBegin
+                const double2 x = w[(i + KT - u) % KT];
+                acc[i].x = fma(x.x, hA, fma(x.y, hB, acc[i].x));
+                acc[i].y = fma(x.x, hC, fma(x.y, hD, acc[i].y));
             }
-            off -= rowBytes;
-            if (off < 0) off += ringBytes;
-            double2 nxt = *reinterpret_cast<const double2*>(ringB + off);   // frame ks - qBegin - 1
-            for (int q0 = 0; q0 < nq; q0 += KT)
-            {
-#pragma unroll
-                for (int u = 0; u < KT; ++u)
-                {
-                    const int q = q0 + u;
-                    if (q < nq)   // uniform
-                    {
-                        const double2 h = *reinterpret_cast<const double2*>(hsB + q * rowBytes);
-                        const double2 incoming = nxt;
-                        off -= rowBytes;
-                        if (off < 0) off += ringBytes;
-                        nxt = *reinterpret_cast<const double2*>(ringB + off);   // frame ks - qBegin - q - 2 (unused after the last tap)
-                        if (PACKED)
-                        {
-                            const double hA = h.x, hB = slot0 ? 0.0 : -h.y, hC = slot0 ? 0.0 : h.y, hD = slot0 ? h.y : h.x;
-#pragma unroll
-                            for (int i = 0; i < KT; ++i)
-                            {
-                                const double2 x = w[(i + KT - u) % KT];
-                                acc[i].x = fma(x.x, hA, fma(x.y, hB, acc[i].x));
-                                acc[i].y = fma(x.x, hC, fma(x.y, hD, acc[i].y));
-                            }
-                        }
-                        else
-                        {
-                            const double nhy = -h.y;
-#pragma unroll
-                            for (int i = 0; i < KT; ++i)
-                            {
-                                const double2 x = w[(i + KT - u) % KT];   // logical w[i] at tap q
-                                acc[i].x = fma(x.x, h.x, fma(x.y, nhy, acc[i].x));
-                                acc[i].y = fma(x.x, h.y, fma(x.y, h.x, acc[i].y));
-                            }
-                        }
-                        // slide: logical w[i] <- w[i-1], w[0] <- frame ks - qBegin - q - 1; freed physical slot is (KT-1-u)
-                        w[(KT - 1 - u) % KT] = incoming;
-                    }
-                }
-            }
+        }
+        else
+        {
 #pragma unroll
             for (int i = 0; i < KT; ++i)
-                if (ks + i < kc1) Y[(size_t) (ks + i) * a.P] = acc[i];
+            {
+                const double2 x = w[(i + KT - u) % KT];   // logical w[i] at tap u
+                acc[i].x = fma(x.x, h.x, fma(-x.y, h.y, acc[i].x));
+                acc[i].y = fma(x.x, h.y, fma(x.y, h.x, acc[i].y));
+            }
         }
-        cp_async_wait0();
-        __syncthreads();
+        // slide: logical w[i] <- w[i-1], w[0] <- incoming; the freed physical slot is (KT-1-u)
+        w[(KT - 1 - u) % KT] = incoming;
+    }
+}
+
+template <bool PACKED>
+__device__ __forceinline__ void mac_run(double2 (&acc)[kMacKT], const char* __restrict__ hsB, const char* __restrict__ ringB, int off,
+                                        int ringBytes, int nq, bool slot0)
+{
+    constexpr int KT = kMacKT;
+    double2 w[KT];
+#pragma unroll
+    for (int i = 0; i < KT; ++i)
+    {
+        acc[i] = make_double2(0.0, 0.0);
+        int o = off + i * kMacRowBytes;
+        if (o >= ringBytes) o -= ringBytes;
+        w[i] = *reinterpret_cast<const double2*>(ringB + o);   // frame ks + i - qBegin
+    }
+    off -= kMacRowBytes;
+    if (off < 0) off += ringBytes;
+    double2 nxt = *reinterpret_cast<const double2*>(ringB + off);   // frame ks - qBegin - 1
+    const int nFull = nq & ~(KT - 1);
+    for (int q0 = 0; q0 < nFull; q0 += KT) mac_taps<KT, PACKED>(acc, w, nxt, hsB + q0 * kMacRowBytes, ringB, off, ringBytes, slot0);
+    const char* hsT = hsB + nFull * kMacRowBytes;
+    switch (nq & (KT - 1))
+    {
+        case 1: mac_taps<1, PACKED>(acc, w, nxt, hsT, ringB, off, ringBytes, slot0); break;
+        case 2: mac_taps<2, PACKED>(acc, w, nxt, hsT, ringB, off, ringBytes, slot0); break;
+        case 3: mac_taps<3, PACKED>(acc, w, nxt, hsT, ringB, off, ringBytes, slot0); break;
+        case 4: mac_taps<4, PACKED>(acc, w, nxt, hsT, ringB, off, ringBytes, slot0); break;
+        case 5: mac_taps<5, PACKED>(acc, w, nxt, hsT, ringB, off, ringBytes, slot0); break;
+        case 6: mac_taps<6, PACKED>(acc, w, nxt, hsT, ringB, off, ringBytes, slot0); break;
+        case 7: mac_taps<7, PACKED>(acc, w, nxt, hsT, ringB, off, ringBytes, slot0); break;
+        default: break;
     }
 }
 
 __global__ void __launch_bounds__(kMacThreads, 2) mac_kernel(MacArgs a)
 {
-    extern __shared__ __align__(16) double2 mac_smem[];
+    extern __shared__ __align__(128) unsigned char mac_smem[];
     const int nq = a.qEnd - a.qBegin;
     const int R = a.ringRows;
-    double2* Hs = mac_smem;                       // [nq][32]
-    double2* ring = mac_smem + nq * kMacBins;     // [R][32], row of frame f lives in slot f mod R
-    const int ml = threadIdx.x & (kMacBins - 1);
-    const int g = threadIdx.x / kMacBins;
+    double2* Hs = reinterpret_cast<double2*>(mac_smem);   // [nq][32]
+    double2* ring = Hs + nq * kMacBins;                   // [R][32], row of frame f lives in slot f mod R
+    uint64_t* bar = reinterpret_cast<uint64_t*>(ring + (size_t) R * kMacBins);
+    const int tid = threadIdx.x;
+    const int ml = tid & (kMacBins - 1);
+    const int g = tid / kMacBins;       // thread group == warp
     const int m0 = blockIdx.x * kMacBins;          // P is a multiple of 32: tiles are always full
     const int seq = blockIdx.z;
     const int kc0 = blockIdx.y * a.framesPerCta;
     const int kc1 = min(a.K, kc0 + a.framesPerCta);
     const int hrow = a.hSeqMod > 0 ? ((a.seqBase + seq) % a.hSeqMod) : seq;
     const double2* __restrict__ X = a.X + (size_t) seq * a.K * a.P + m0;
+    const double2* __restrict__ H = a.H + (size_t) hrow * a.hSeqStride + (size_t) a.qBegin * a.P + m0;
     double2* __restrict__ Y = a.Y + (size_t) seq * a.K * a.P + m0 + ml;
+    const int ringBytes = R * kMacRowBytes;
 
-    // ---- stage the IR spectra tile and the first super-step's input rows ----
-    {
-        const double2* __restrict__ H = a.H + (size_t) hrow * a.hSeqStride + (size_t) a.qBegin * a.P + m0;
-        for (int i = threadIdx.x; i < nq * kMacBins; i += kMacThreads)
-            cp_async16(Hs + i, H + (size_t) (i / kMacBins) * a.P + (i & (kMacBins - 1)));
-        const int f0 = kc0 - a.qBegin - (nq - 1), f1 = kc0 - a.qBegin + kMacSuper;
-        const int n = (f1 - f0) * kMacBins;
-        for (int i = threadIdx.x; i < n; i += kMacThreads)
+    if (tid == 0) mbar_init(bar, 1);
+
+    // Stage rows [f0, f1) of X into the ring (and, with withH, the H tile): frames before 0 are the zero history of a
+    // Reset engine (plain stores by all threads), frames in [0, K) one bulk copy each, issued by warp 0.
+    auto stage = [&](int f0, int f1, bool withH) {
+        const int z1 = min(f1, 0);
+        if (f0 < z1)
         {
-            const int f = f0 + i / kMacBins, c = i & (kMacBins - 1);
-            int s = f % R;
-            if (s < 0) s += R;
-            double2* dst = ring + s * kMacBins + c;
-            if (f >= 0 && f < a.K) cp_async16(dst, X + (size_t) f * a.P + c);
-            else *dst = make_double2(0.0, 0.0);
+            const int n = (z1 - f0) * kMacBins;
+            for (int i = tid; i < n; i += kMacThreads)
+            {
+                int s = (f0 + i / kMacBins) % R;
+                if (s < 0) s += R;
+                ring[s * kMacBins + (i & (kMacBins - 1))] = make_double2(0.0, 0.0);
+            }
+            fence_proxy_async();
         }
-    }
-    cp_async_commit();
-    cp_async_wait0();
-    __syncthreads();
+        // bulk copies: 8 rows per warp (lanes 0..7), H rows on lanes 8..15; the expected byte count is posted by thread 0
+        // (the transaction count may run negative until then, the phase cannot complete before that arrive)
+        const int c0 = max(f0, 0), c1 = min(f1, a.K);
+        const int nRows = max(c1 - c0, 0);
+        if (tid == 0) mbar_arrive_expect_tx(bar, (unsigned) (nRows + (withH ? nq : 0)) * kMacRowBytes);
+        if (ml < 8)
+        {
+            for (int i = g * 8 + ml; i < nRows; i += 8 * kMacGroups)
+            {
+                const int f = c0 + i;
+                bulk_g2s(ring + (f % R) * kMacBins, X + (size_t) f * a.P, kMacRowBytes, bar);
+            }
+        }
+        else if (withH && ml < 16)
+        {
+            for (int i = g * 8 + ml - 8; i < nq; i += 8 * kMacGroups) bulk_g2s(Hs + i * kMacBins, H + (size_t) i * a.P, kMacRowBytes, bar);
+        }
+    };
 
-    if (m0 == 0) mac_body<true>(a, Hs, ring, nq, R, ml, g, kc0, kc1, Y, X, m0);
-    else mac_body<false>(a, Hs, ring, nq, R, ml, g, kc0, kc1, Y, X, m0);
+    __syncthreads();   // mbarrier initialised
+    stage(kc0 - a.qBegin - (nq - 1), kc0 - a.qBegin + kMacSuper, true);
+    mbar_wait(bar, 0);
+    __syncthreads();   // zero rows written by other threads
+
+    const char* ringB = reinterpret_cast<const char*>(ring) + ml * (int) sizeof(double2);
+    const char* hsB = reinterpret_cast<const char*>(Hs) + ml * (int) sizeof(double2);
+    const bool packedTile = (m0 == 0);
+    const bool slot0 = packedTile && ml == 0;
+    unsigned phase = 0;
+    for (int ks0 = kc0; ks0 < kc1; ks0 += kMacSuper)
+    {
+        const bool more = ks0 + kMacSuper < kc1;
+        // prefetch the rows that only the next super-step needs
+        if (more) stage(ks0 - a.qBegin + kMacSuper, ks0 - a.qBegin + 2 * kMacSuper, false);
+        const int ks = ks0 + g * kMacKT;
+        if (ks < kc1)
+        {
+            double2 acc[kMacKT];
+            int s = (ks - a.qBegin) % R;
+            if (s < 0) s += R;
+            if (packedTile) mac_run<true>(acc, hsB, ringB, s * kMacRowBytes, ringBytes, nq, slot0);
+            else mac_run<false>(acc, hsB, ringB, s * kMacRowBytes, ringBytes, nq, slot0);
+#pragma unroll
+            for (int i = 0; i < kMacKT; ++i)
+                if (ks + i < kc1) Y[(size_t) (ks + i) * a.P] = acc[i];
+        }
+        if (more)
+        {
+            phase ^= 1u;
+            mbar_wait(bar, phase);
+        }
+        __syncthreads();
+    }
 }
 
 } // namespace cpq
