@@ -41,12 +41,17 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, defines: dict | None = None) -> str:
+    """Build libcpq.so.  `out` + `defines` build a tuning variant elsewhere (selected at run time with CPQ_LIB)."""
+    if out is None and not force and up_to_date():
         return LIB
     extra = [f"-D{k}={v}" for k, v in os.environ.items() if k.startswith("CPQ_") and k.isupper() and v.isdigit()]   # tuning knobs
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", LIB] + SOURCES
-    out = subprocess.run(cmd, capture_output=True, text=True)
+    extra += [f"-D{k}={v}" for k, v in (defines or {}).items()]
+    target = out or LIB
+    os.makedirs(os.path.dirname(target), exist_ok=True)
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", target] + SOURCES
+    out_ = subprocess.run(cmd, capture_output=True, text=True)
+    out = out_
     log = out.stdout + out.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
@@ -54,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print(log[-8000:])
     if out.returncode != 0:
         raise RuntimeError("nvcc failed building libcpq.so")
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

@@ -74,7 +74,8 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()          # no-op when up to date; raises when nvcc is unavailable and no .so exists
+    # CPQ_LIB selects another build of the same library (tuning experiments: scripts/build_variant.py)
+    path = os.environ.get("CPQ_LIB") or _build.build()   # no-op when up to date; raises when nvcc is unavailable and no .so exists
     if not os.path.exists(path):
         raise RuntimeError("libcpq.so missing: the CUDA extension is mandatory (no CPU fallback)")
     L = C.CDLL(path)

@@ -7,19 +7,21 @@
 //   dither_kernel  PsychoacousticDither::processStereoBlock (PsychoacousticDither.h:293-355)
 //
 // The band recurrence is linear in its 2-element state (the tanh saturation only touches the band *output*,
-// Processing.cpp:148-168), so each band is a blocked scan.  A CTA owns one 3584-sample tile of one sequence:
-// seven compute warps hold 16 consecutive samples per thread in registers, an eighth "chain" warp carries the
-// state between tiles.  Per band: pass 1 = zero-state response of each thread's block by 16 precomputed weight
-// vectors, warp-shuffle scan of s -> A^16 s + c, ONE CTA barrier, Horner fold over the preceding warps'
-// aggregates, a two-level table lookup for A^(16 lane), then pass 2 = the band recurrence from the exact start
-// state.  Bands are processed in order on the same registers, so a tile crosses HBM once for all 20 bands.
+// Processing.cpp:148-168), so each band is a blocked scan.  A CTA owns one 3584-sample tile of one sequence, split
+// into seven 512-sample segments, one per compute warp, 16 consecutive samples per thread in registers.  Per band
+// a warp runs: pass 1 = zero-state response of each thread's block by 16 precomputed weight vectors, warp-shuffle
+// scan of s -> A^16 s + c, the *link* (below), a two-level table lookup for A^(16 lane), and pass 2 = the band
+// recurrence from the exact start state.  Bands are processed in order on the same registers, so a tile crosses
+// HBM once for all 20 bands.
 //
-// Chain between tiles: tile r of a sequence needs, for every band, the state after tile r-1.  The chain warp
-// fetches record (seq, r-1, band) -- published by the predecessor CTA with release/acquire flags -- *before*
-// the band's barrier (while the compute warps are still busy with the previous band), and publishes
-// A^3584 s_in + (tile aggregate) for the successor after it.  The compute warps therefore never wait on global
-// memory.  Tiles take their index from an atomic ticket in run-major order, so a predecessor is always already
-// running (or done) when a CTA starts.
+// Links instead of barriers: the warps of a CTA are a chain.  Warp w takes the state at the start of its segment
+// for band b from a shared-memory mailbox st[b][w] (flag fl[b][w]), and its lane 31 posts A^512 s_in + (segment
+// aggregate) into st[b][w+1] right after the warp scan.  There is no CTA barrier in the band loop: warps run
+// skewed by one link latency and otherwise independently, and each warp loads/stores its own segment.  The
+// eighth warp is the chain warp: one thread moves states between tiles -- it polls the record (seq, tile-1, band)
+// published by the predecessor CTA with release/acquire flags into st[b][0], and publishes st[b][7] for the
+// successor -- so no compute warp ever waits on global memory.  Tiles take their index from an atomic ticket in
+// run-major order, so a predecessor CTA is always already running (or done) when a CTA starts.
 //
 // Pass 2 arithmetic.  The reference designs every band as a TPT SVF (a2 = g a1, a3 = g a2,
 // EQProcessor.Coefficients.cpp:101-130), which gives v2 = ic2 + g v1 and ic2' = ic2 + 2 g v1; with
@@ -59,7 +61,9 @@ constexpr int kEqcMw = 112;      // A^512   (one warp)
 constexpr int kEqcMt = 116;      // A^3584  (one tile)
 constexpr int kEqcStride = 120;  // doubles per band (20 bands = 19.2 KB, staged in shared memory)
 
-constexpr int kEqSmemDoubles = kEqCThreads * kEqPad + CPQ_NUM_BANDS * kEqcStride + 2 * 8 * 2 + CPQ_NUM_BANDS * 2;
+constexpr int kEqSeg = 32 * kEqL;                // 512 samples per warp segment
+// shared memory: segment tiles | band constants | mailboxes st[20][8] (double2) | flags fl[20][8] (int) | ticket
+constexpr int kEqSmemDoubles = kEqCThreads * kEqPad + CPQ_NUM_BANDS * kEqcStride + CPQ_NUM_BANDS * 8 * 2 + CPQ_NUM_BANDS * 8 / 2;
 constexpr size_t kEqSmemBytes = (size_t) kEqSmemDoubles * sizeof(double) + 16;
 
 struct EqChain
@@ -122,8 +126,22 @@ __device__ __forceinline__ double ld_cg_f64(const double* p)
     asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
-// CTA barrier of the band loop (id 1): compute warps and the chain warp arrive from different code paths
-__device__ __forceinline__ void eq_band_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEqThreads) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds_volatile(const int* p)
+{
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned) __cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_volatile(int* p, int v)
+{
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((unsigned) __cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ bool eq_valid(double v) { return fabs(v) < 1.0e15; }   // false for NaN / Inf too
 
@@ -241,14 +259,15 @@ __device__ __forceinline__ void eq_pass2(double (&x)[kEqL], double& ic1, double&
 __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs a)
 {
     extern __shared__ __align__(16) double eq_smem[];
-    double* tile = eq_smem;                                        // [224][18]
+    double* tile = eq_smem;                                        // [7 warps][32 lanes][18]
     double* cst = tile + kEqCThreads * kEqPad;                     // this sequence's band constants
-    double2* warpAgg = reinterpret_cast<double2*>(cst + CPQ_NUM_BANDS * kEqcStride);   // [2][8], double-buffered by band parity
-    double2* sIn = warpAgg + 2 * 8;                                // [20] state at the start of the tile, per band
-    unsigned* sTicket = reinterpret_cast<unsigned*>(sIn + CPQ_NUM_BANDS);
+    double2* st = reinterpret_cast<double2*>(cst + CPQ_NUM_BANDS * kEqcStride);   // [20][8] state at the start of segment w (8 = after the tile)
+    int* fl = reinterpret_cast<int*>(st + CPQ_NUM_BANDS * 8);                     // [20][8] mailbox flags
+    unsigned* sTicket = reinterpret_cast<unsigned*>(fl + CPQ_NUM_BANDS * 8);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) *sTicket = atomicAdd(a.chain.ticket, 1u);
+    if (tid < CPQ_NUM_BANDS * 8) fl[tid] = 0;
     __syncthreads();
     const unsigned ticket = *sTicket;
     // run-major ticket order: the predecessor (same sequence, previous tile) always holds a smaller ticket
@@ -259,10 +278,7 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
     double* io = a.io + (size_t) seq * a.ioStride;
     const int set = a.doEq ? a.setOfSeq[seq] : 0;
     const unsigned mask = a.doEq ? a.bandMask[seq] : 0u;
-    const double sat = a.doEq ? a.sat[set] : 0.0;
-    const int bmask = (1 << a.blockLog2) - 1;
     const int64_t t0 = (int64_t) run * kEqTile;
-    const int nValid = (int) min((int64_t) kEqTile, a.T - t0);
 
     if (a.doEq)
     {
@@ -270,26 +286,139 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
         for (int i = tid; i < CPQ_NUM_BANDS * kEqcStride / 2; i += kEqThreads)
             reinterpret_cast<double2*>(cst)[i] = __ldg(reinterpret_cast<const double2*>(src) + i);
     }
+    __syncthreads();   // constants + cleared flags visible; the only CTA-wide barrier besides the ticket
+
+    if (warp == kEqCWarps)
+    {
+        // ================= chain warp: one thread moves band states between the tiles of a sequence =================
+        if (lane != 0 || !a.doEq || mask == 0u) return;
+        const bool last = run + 1 >= a.nRuns;
+        const bool fullLast = last && (a.T - t0) == kEqTile;
+        auto nextBand = [&](int b) { ++b; while (b < CPQ_NUM_BANDS && !((mask >> b) & 1u)) ++b; return b; };
+        int bi = nextBand(-1), bo = bi;   // next band whose input state is still to be delivered / whose output is still to be forwarded
+        while (bo < CPQ_NUM_BANDS)
+        {
+            bool progress = false;
+            if (bi < CPQ_NUM_BANDS)
+            {
+                double s1 = 0.0, s2 = 0.0;
+                bool ready = true;
+                if (run > 0)
+                {
+                    const double* rec = a.chain.rec + ((size_t) ((size_t) seq * a.nRuns + (run - 1)) * CPQ_NUM_BANDS + bi) * 4;
+                    ready = ld_relaxed_u64(reinterpret_cast<const unsigned long long*>(rec + 2)) == a.chain.epoch;
+                    if (ready)
+                    {
+                        __threadfence();   // acquire: the record was written before its flag
+                        s1 = ld_cg_f64(rec);
+                        s2 = ld_cg_f64(rec + 1);
+                    }
+                }
+                if (ready)
+                {
+                    st[bi * 8] = make_double2(s1, s2);
+                    __threadfence_block();
+                    sts_volatile(fl + bi * 8, 1);
+                    bi = nextBand(bi);
+                    progress = true;
+                }
+            }
+            if (bo < bi && lds_volatile(fl + bo * 8 + kEqCWarps) != 0)
+            {
+                __threadfence_block();
+                const double2 s = st[bo * 8 + kEqCWarps];   // state after the tile's last sample
+                if (!last)
+                {
+                    double* rec = a.chain.rec + ((size_t) ((size_t) seq * a.nRuns + run) * CPQ_NUM_BANDS + bo) * 4;
+                    rec[0] = s.x;
+                    rec[1] = s.y;
+                    st_release_u64(reinterpret_cast<unsigned long long*>(rec + 2), a.chain.epoch);
+                }
+                else if (fullLast && a.stateOut)
+                {
+                    a.stateOut[((size_t) seq * CPQ_NUM_BANDS + bo) * 2] = s.x;
+                    a.stateOut[((size_t) seq * CPQ_NUM_BANDS + bo) * 2 + 1] = s.y;
+                }
+                bo = nextBand(bo);
+                progress = true;
+            }
+            if (!progress) __nanosleep(64);
+        }
+        return;
+    }
+
+    // ================= compute warps: one 512-sample segment each =================
+    const double sat = a.doEq ? a.sat[set] : 0.0;
+    const int bmask = (1 << a.blockLog2) - 1;
+    const int64_t w0 = t0 + (int64_t) warp * kEqSeg;                       // first sample of this warp's segment
+    const int nValid = (int) max((int64_t) 0, min((int64_t) kEqSeg, a.T - w0));
+    double* wtile = tile + warp * 32 * kEqPad;
+    double* myStash = wtile + lane * kEqPad;   // 16 consecutive slots + 2 pad slots
 
     // ---- coalesced load + layer assembly (Get) ----
-#pragma unroll 2
-    for (int i = tid; i < kEqTile; i += kEqThreads)
+    // Fast path: callbacks are whole multiples of the 512-sample segment (block >= 512) and the tail streams are
+    // stored in stream order (regular plans), so the tail source position is one lookup per (layer, segment).
+    const bool segFast = a.assemble && a.blockLog2 >= 9 && a.blockMap[0] == nullptr && a.blockMap[1] == nullptr;
+    if (!a.assemble || segFast)
     {
-        double v = 0.0;
-        if (i < nValid)
+        const double* tp[2] = { nullptr, nullptr };
+        double tg[2] = { 0.0, 0.0 };
+        if (segFast && nValid > 0)
         {
-            const int64_t t = t0 + i;
-            v = io[t];
-            if (a.assemble)
+            const int64_t c = w0 >> a.blockLog2;
+            const int64_t off = w0 & (int64_t) bmask;
+#pragma unroll
+            for (int l = 0; l < 2; ++l)
+                if (l < a.nTail)
+                {
+                    const int64_t sp = __ldg(a.tailSrc[l] + c);
+                    if (sp >= 0)
+                    {
+                        tp[l] = a.tail[l] + (size_t) seq * a.tailStride[l] + sp + off;
+                        tg[l] = a.tailGain[l];
+                    }
+                }
+        }
+        const double* ip = io + w0;
+        const bool outer = a.assemble && a.outer;
+        const double wet = a.wetGain;
+#pragma unroll
+        for (int k = 0; k < kEqL; ++k)
+        {
+            const int i = lane + 32 * k;
+            double v = 0.0;
+            if (i < nValid)
             {
+                v = ip[i];
+                if (tp[0]) v += __ldg(tp[0] + i) * tg[0];
+                if (tp[1]) v += __ldg(tp[1] + i) * tg[1];
+                if (outer)
+                {
+                    if (!(fabs(v) < 1.0e300)) v = 0.0;
+                    v *= wet;
+                }
+            }
+            wtile[eq_sidx(i)] = v;
+        }
+    }
+    else
+    {
+        // generic path: per-sample callback lookup (block < 512) and block-mapped tail streams (irregular plans)
+        for (int i = lane; i < kEqSeg; i += 32)
+        {
+            double v = 0.0;
+            if (i < nValid)
+            {
+                const int64_t t = w0 + i;
+                v = io[t];
                 const int64_t c = t >> a.blockLog2;
                 const int off = (int) t & bmask;
                 for (int l = 0; l < a.nTail; ++l)
                 {
-                    const int64_t s = __ldg(a.tailSrc[l] + c);
-                    if (s >= 0)
+                    const int64_t sp = __ldg(a.tailSrc[l] + c);
+                    if (sp >= 0)
                     {
-                        int64_t pos = s + off;
+                        int64_t pos = sp + off;
                         if (a.blockMap[l])
                         {
                             const int64_t j = pos >> a.tailPartLog2[l];
@@ -305,208 +434,175 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                     v *= a.wetGain;
                 }
             }
+            wtile[eq_sidx(i)] = v;
         }
-        tile[eq_sidx(i)] = v;
     }
-    __syncthreads();
+    __syncwarp();
 
-    if (warp == kEqCWarps)
-    {
-        // ================= chain warp: state hand-over between the tiles of a sequence =================
-        if (a.doEq)
-        {
-            int parity = 0;
-            for (int b = 0; b < CPQ_NUM_BANDS; ++b)
-            {
-                if (!((mask >> b) & 1u)) continue;   // uniform per CTA
-                const double* __restrict__ bc = cst + b * kEqcStride;
-                double s1 = 0.0, s2 = 0.0;
-                if (lane == 0)
-                {
-                    if (run > 0)
-                    {
-                        const double* rec = a.chain.rec + ((size_t) ((size_t) seq * a.nRuns + (run - 1)) * CPQ_NUM_BANDS + b) * 4;
-                        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(rec + 2);
-                        while (ld_acquire_u64(flag) != a.chain.epoch) { __nanosleep(32); }
-                        s1 = ld_cg_f64(rec);
-                        s2 = ld_cg_f64(rec + 1);
-                    }
-                    sIn[b] = make_double2(s1, s2);
-                }
-                __syncwarp();
-                eq_band_barrier();   // band b: warp aggregates are in warpAgg[parity], sIn[b] is visible to the compute warps
-                if (lane == 0 && run + 1 < a.nRuns)
-                {
-                    double g1 = 0.0, g2 = 0.0;
+    double x[kEqL];
+    unsigned hiMax = 0;   // running max of |x|'s high word: raw input large enough that a state could reach 1e15?
 #pragma unroll
-                    for (int w = 0; w < kEqCWarps; ++w)
-                    {
-                        const double2 ag = warpAgg[parity * 8 + w];
-                        matvec2(bc + kEqcMw, g1, g2, ag.x, ag.y);
-                    }
-                    matvec2(bc + kEqcMt, s1, s2, g1, g2);
-                    double* rec = a.chain.rec + ((size_t) ((size_t) seq * a.nRuns + run) * CPQ_NUM_BANDS + b) * 4;
-                    rec[0] = s1;
-                    rec[1] = s2;
-                    st_release_u64(reinterpret_cast<unsigned long long*>(rec + 2), a.chain.epoch);
+    for (int j = 0; j < kEqL / 2; ++j)
+    {
+        const double2 v = reinterpret_cast<const double2*>(myStash)[j];
+        x[2 * j] = v.x;
+        x[2 * j + 1] = v.y;
+        hiMax = max(hiMax, max((unsigned) __double2hiint(v.x) & 0x7fffffffu, (unsigned) __double2hiint(v.y) & 0x7fffffffu));
+    }
+    bool suspicious = hiMax >= 0x41cdcd65u;   // |x| >= 1e9 (or NaN/Inf)
+
+    if (a.doEq)
+    {
+        const double alpha = fma(-8.0, sat, 9.0) / 9.0, gamma = 8.0 * sat / 3.0;
+        const unsigned thrHi = sat > 0.0 ? 0x40374000u : 0x40590000u;   // high words of 4.5^2 + 3 / of 100.0
+        // the thread whose block starts at sample T holds the sequence's final state when the last tile is partial
+        const int64_t remT = a.T - t0;
+        const bool ownsFinal = a.stateOut && remT < kEqTile && remT >= 0 && tid == (int) (remT / kEqL);
+        for (int b = 0; b < CPQ_NUM_BANDS; ++b)
+        {
+            if (!((mask >> b) & 1u)) continue;   // uniform per CTA
+            const double* __restrict__ bc = cst + b * kEqcStride;
+            // ---- pass 1: zero-state response of this thread's 16 samples (four accumulation chains); stash the inputs ----
+            double c1 = 0.0, c2 = 0.0, d1 = 0.0, d2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < kEqL; j += 2)
+            {
+                const double2 wa = reinterpret_cast<const double2*>(bc + kEqcW)[j];
+                const double2 wb = reinterpret_cast<const double2*>(bc + kEqcW)[j + 1];
+                c1 = fma(wa.x, x[j], c1);
+                c2 = fma(wa.y, x[j], c2);
+                d1 = fma(wb.x, x[j + 1], d1);
+                d2 = fma(wb.y, x[j + 1], d2);
+            }
+            c1 += d1;
+            c2 += d2;
+#pragma unroll
+            for (int j = 0; j < kEqL / 2; ++j) reinterpret_cast<double2*>(myStash)[j] = make_double2(x[2 * j], x[2 * j + 1]);
+            // ---- warp inclusive scan of s -> A^16 s + c ----
+#pragma unroll
+            for (int d = 0; d < 5; ++d)
+            {
+                const double p1 = __shfl_up_sync(0xffffffffu, c1, 1 << d);
+                const double p2 = __shfl_up_sync(0xffffffffu, c2, 1 << d);
+                if (lane >= (1 << d))
+                {
+                    const double2 r0 = reinterpret_cast<const double2*>(bc + kEqcMs + 4 * d)[0];
+                    const double2 r1 = reinterpret_cast<const double2*>(bc + kEqcMs + 4 * d)[1];
+                    c1 = fma(r0.x, p1, fma(r0.y, p2, c1));
+                    c2 = fma(r1.x, p1, fma(r1.y, p2, c2));
                 }
-                __syncwarp();
-                parity ^= 1;
+            }
+            // exclusive value (state contribution before this thread, relative to the segment start)
+            double e1 = __shfl_up_sync(0xffffffffu, c1, 1);
+            double e2 = __shfl_up_sync(0xffffffffu, c2, 1);
+            if (lane == 0) { e1 = 0.0; e2 = 0.0; }
+
+            // ---- link: state at the start of this segment from the previous warp (or the chain warp) ----
+            {
+                const int* f = fl + b * 8 + warp;
+                while (lds_volatile(f) == 0) { }
+                __threadfence_block();
+            }
+            double p1, p2;
+            {
+                const double2 s = st[b * 8 + warp];
+                p1 = s.x;
+                p2 = s.y;
+            }
+            if (lane == 31)
+            {
+                double o1 = p1, o2 = p2;
+                matvec2(bc + kEqcMw, o1, o2, c1, c2);   // state after this segment
+                st[b * 8 + warp + 1] = make_double2(o1, o2);
+                __threadfence_block();
+                sts_volatile(fl + b * 8 + warp + 1, 1);
+            }
+            // ---- state at the start of this thread's block: A^(16 lane) s_in + e ----
+            matvec2(bc + kEqcPlo + 4 * (lane & 7), p1, p2, 0.0, 0.0);    // A^(16 (lane & 7))
+            matvec2(bc + kEqcPhi + 4 * (lane >> 3), p1, p2, e1, e2);     // A^(128 (lane >> 3)) ... + e
+            double ic1 = p1, ic2 = p2;
+            reinterpret_cast<double2*>(myStash)[kEqL / 2] = make_double2(ic1, ic2);   // start state, for the exact replay (pad slots)
+            if (ownsFinal)
+            {
+                a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2] = ic1;
+                a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2 + 1] = ic2;
+            }
+
+            // ---- pass 2, fast path ----
+            hiMax = max((unsigned) __double2hiint(ic1) & 0x7fffffffu, (unsigned) __double2hiint(ic2) & 0x7fffffffu);
+            bool rare = suspicious | (hiMax >= 0x426d1a94u) | (bc[6] != 0.0);   // |state| >= 1e12
+            hiMax = 0;
+            const int kind = (int) bc[7];
+            if (sat > 0.0)
+            {
+                if (kind == 1) eq_pass2<true, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                else if (kind == 2) eq_pass2<true, 2>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                else eq_pass2<true, 0>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+            }
+            else
+            {
+                if (kind == 1) eq_pass2<false, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                else if (kind == 2) eq_pass2<false, 2>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                else eq_pass2<false, 0>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+            }
+            rare |= hiMax >= thrHi;   // some |out| >= 4.5 (100 without saturation), or NaN
+            suspicious = false;       // outputs of a band are bounded by 100 (or replayed exactly below)
+            if (rare)
+            {
+                // exact replay from the stashed inputs and the same start state
+                ic1 = myStash[kEqL];
+                ic2 = myStash[kEqL + 1];
+                if (eq_exact_block(myStash, ic1, ic2, bc[0], bc[1], bc[2], bc[3], bc[4], bc[5], sat)) atomicExch(a.fault, 1u);
+#pragma unroll
+                for (int j = 0; j < kEqL; ++j) x[j] = myStash[j];
             }
         }
     }
-    else
+#pragma unroll
+    for (int j = 0; j < kEqL / 2; ++j) reinterpret_cast<double2*>(myStash)[j] = make_double2(x[2 * j], x[2 * j + 1]);
+    __syncwarp();
+
+    // ---- store: total gain ramp, makeup, headroom (three separate roundings, as the reference applies them) ----
     {
-        // ================= compute warps =================
-        double* myStash = tile + tid * kEqPad;   // 16 consecutive slots
-        double x[kEqL];
-        unsigned hiMax = 0;   // running max of |x|'s high word: raw input large enough that a state could reach 1e15?
-#pragma unroll
-        for (int j = 0; j < kEqL / 2; ++j)
+        double* op = io + w0;
+        const double gconst = (a.doEq && !a.gainTab) ? __ldg(a.gainConst + set) : 1.0;
+        const double mk = a.doEpilogue ? a.makeup : 1.0;
+        const double hr = (a.doEpilogue && a.applyHeadroom) ? 0.8912509381337456 : 1.0;
+        if (a.doEq && a.gainTab)
         {
-            const double2 v = reinterpret_cast<const double2*>(myStash)[j];
-            x[2 * j] = v.x;
-            x[2 * j + 1] = v.y;
-            hiMax = max(hiMax, max((unsigned) __double2hiint(v.x) & 0x7fffffffu, (unsigned) __double2hiint(v.y) & 0x7fffffffu));
-        }
-        bool suspicious = hiMax >= 0x41cdcd65u;   // |x| >= 1e9 (or NaN/Inf)
-
-        if (a.doEq)
-        {
-            const double alpha = fma(-8.0, sat, 9.0) / 9.0, gamma = 8.0 * sat / 3.0;
-            const unsigned thrHi = sat > 0.0 ? 0x40374000u : 0x40590000u;   // high words of 4.5^2 + 3 / of 100.0
-            int parity = 0;
-            for (int b = 0; b < CPQ_NUM_BANDS; ++b)
+            for (int i = lane; i < nValid; i += 32)
             {
-                if (!((mask >> b) & 1u)) continue;   // uniform per CTA
-                const double* __restrict__ bc = cst + b * kEqcStride;
-                // ---- pass 1: zero-state response of this thread's 16 samples; stash the inputs ----
-                double c1 = 0.0, c2 = 0.0;
-#pragma unroll
-                for (int j = 0; j < kEqL; ++j)
-                {
-                    const double2 w = reinterpret_cast<const double2*>(bc + kEqcW)[j];
-                    c1 = fma(w.x, x[j], c1);
-                    c2 = fma(w.y, x[j], c2);
-                }
-#pragma unroll
-                for (int j = 0; j < kEqL / 2; ++j) reinterpret_cast<double2*>(myStash)[j] = make_double2(x[2 * j], x[2 * j + 1]);
-                // ---- warp inclusive scan of s -> A^16 s + c ----
-#pragma unroll
-                for (int d = 0; d < 5; ++d)
-                {
-                    const double p1 = __shfl_up_sync(0xffffffffu, c1, 1 << d);
-                    const double p2 = __shfl_up_sync(0xffffffffu, c2, 1 << d);
-                    if (lane >= (1 << d))
-                    {
-                        const double2 r0 = reinterpret_cast<const double2*>(bc + kEqcMs + 4 * d)[0];
-                        const double2 r1 = reinterpret_cast<const double2*>(bc + kEqcMs + 4 * d)[1];
-                        c1 = fma(r0.x, p1, fma(r0.y, p2, c1));
-                        c2 = fma(r1.x, p1, fma(r1.y, p2, c2));
-                    }
-                }
-                if (lane == 31) warpAgg[parity * 8 + warp] = make_double2(c1, c2);
-                // exclusive value (state contribution before this thread, relative to the warp start)
-                double e1 = __shfl_up_sync(0xffffffffu, c1, 1);
-                double e2 = __shfl_up_sync(0xffffffffu, c2, 1);
-                if (lane == 0) { e1 = 0.0; e2 = 0.0; }
-                eq_band_barrier();
-
-                // ---- state at the start of the tile -> of this warp (Horner over the preceding warps) -> of this thread ----
-                double p1, p2;
-                {
-                    const double2 s = sIn[b];
-                    p1 = s.x;
-                    p2 = s.y;
-                }
-#pragma unroll
-                for (int w = 0; w < kEqCWarps - 1; ++w)
-                    if (w < warp)
-                    {
-                        const double2 ag = warpAgg[parity * 8 + w];
-                        matvec2(bc + kEqcMw, p1, p2, ag.x, ag.y);
-                    }
-                parity ^= 1;
-                matvec2(bc + kEqcPlo + 4 * (lane & 7), p1, p2, 0.0, 0.0);    // A^(16 (lane & 7))
-                matvec2(bc + kEqcPhi + 4 * (lane >> 3), p1, p2, e1, e2);     // A^(128 (lane >> 3)) ... + e
-                double ic1 = p1, ic2 = p2;
-                reinterpret_cast<double2*>(myStash)[kEqL / 2] = make_double2(ic1, ic2);   // start state, for the exact replay (pad slots)
-
-                // final state of the sequence = state at sample T (T is a multiple of 16)
-                if (t0 + kEqTile >= a.T && a.stateOut)
-                {
-                    const int64_t rem = a.T - t0;   // 1..3584
-                    if (rem < kEqTile && tid == (int) (rem / kEqL))
-                    {
-                        a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2] = ic1;
-                        a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2 + 1] = ic2;
-                    }
-                }
-
-                // ---- pass 2, fast path ----
-                hiMax = max((unsigned) __double2hiint(ic1) & 0x7fffffffu, (unsigned) __double2hiint(ic2) & 0x7fffffffu);
-                bool rare = suspicious | (hiMax >= 0x426d1a94u) | (bc[6] != 0.0);   // |state| >= 1e12
-                hiMax = 0;
-                const int kind = (int) bc[7];
-                if (sat > 0.0)
-                {
-                    if (kind == 1) eq_pass2<true, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
-                    else if (kind == 2) eq_pass2<true, 2>(x, ic1, ic2, bc, alpha, gamma, hiMax);
-                    else eq_pass2<true, 0>(x, ic1, ic2, bc, alpha, gamma, hiMax);
-                }
-                else
-                {
-                    if (kind == 1) eq_pass2<false, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
-                    else if (kind == 2) eq_pass2<false, 2>(x, ic1, ic2, bc, alpha, gamma, hiMax);
-                    else eq_pass2<false, 0>(x, ic1, ic2, bc, alpha, gamma, hiMax);
-                }
-                rare |= hiMax >= thrHi;   // some |out| >= 4.5 (100 without saturation), or NaN
-                suspicious = false;       // outputs of a band are bounded by 100 (or replayed exactly below)
-                if (rare)
-                {
-                    // exact replay from the stashed inputs and the same start state
-                    ic1 = myStash[kEqL];
-                    ic2 = myStash[kEqL + 1];
-                    if (eq_exact_block(myStash, ic1, ic2, bc[0], bc[1], bc[2], bc[3], bc[4], bc[5], sat)) atomicExch(a.fault, 1u);
-#pragma unroll
-                    for (int j = 0; j < kEqL; ++j) x[j] = myStash[j];
-                }
-                if (tid == kEqCThreads - 1 && a.stateOut && (a.T - t0) == kEqTile)
-                {
-                    // state after the tile's last sample = final state when the last tile is full
-                    a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2] = ic1;
-                    a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2 + 1] = ic2;
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < kEqL / 2; ++j) reinterpret_cast<double2*>(myStash)[j] = make_double2(x[2 * j], x[2 * j + 1]);
-    }
-    __syncthreads();
-
-    // ---- store: total gain ramp, makeup, headroom ----
-#pragma unroll 2
-    for (int i = tid; i < nValid; i += kEqThreads)
-    {
-        double v = tile[eq_sidx(i)];
-        const int64_t t = t0 + i;
-        if (a.doEq)
-        {
-            if (a.gainTab)
-            {
+                double v = wtile[eq_sidx(i)];
+                const int64_t t = w0 + i;
                 const int64_t c = t >> a.blockLog2;
                 const int off = (int) t & bmask;
                 const double2 g = __ldg(reinterpret_cast<const double2*>(a.gainTab) + (size_t) set * a.nCallbacks + c);
                 v *= fma((double) off, g.y, g.x);
+                if (a.doEpilogue)
+                {
+                    v *= mk;
+                    if (a.applyHeadroom) v *= hr;
+                }
+                op[i] = v;
             }
-            else v *= __ldg(a.gainConst + set);
         }
-        if (a.doEpilogue)
+        else
         {
-            v *= a.makeup;
-            if (a.applyHeadroom) v *= 0.8912509381337456;
+            const bool mulG = a.doEq != 0, mulM = a.doEpilogue != 0, mulH = a.doEpilogue && a.applyHeadroom;
+#pragma unroll
+            for (int k = 0; k < kEqL; ++k)
+            {
+                const int i = lane + 32 * k;
+                if (i < nValid)
+                {
+                    double v = wtile[eq_sidx(i)];
+                    if (mulG) v *= gconst;
+                    if (mulM) v *= mk;
+                    if (mulH) v *= hr;
+                    op[i] = v;
+                }
+            }
         }
-        io[t] = v;
     }
 }
 
