@@ -552,7 +552,7 @@ static void buildBandConstants(const cpq_svf_coeffs& c, double* out /* kEqcStrid
         out[8] = g;
         out[9] = 2.0 * g;
     }
-    // w[j] = A^(15-j) b
+    // w[j] = A^(L-1-j) b
     long double v[2] = { b[0], b[1] };
     for (int j = kEqL - 1; j >= 0; --j)
     {
@@ -561,35 +561,32 @@ static void buildBandConstants(const cpq_svf_coeffs& c, double* out /* kEqcStrid
         const long double n0 = A[0] * v[0] + A[1] * v[1], n1 = A[2] * v[0] + A[3] * v[1];
         v[0] = n0; v[1] = n1;
     }
-    long double A16[4] = { 1, 0, 0, 1 };
-    for (int i = 0; i < kEqL; ++i) matmul2(A16, A, A16);
-    // Plo[j] = A^(16 j), j < 8;  Phi[j] = A^(128 j), j < 4
+    long double AL[4] = { 1, 0, 0, 1 };
+    for (int i = 0; i < kEqL; ++i) matmul2(AL, A, AL);
+    // Plo[j] = A^(L j), j < 8;  Phi[j] = A^(8L j), j < 4
     {
         long double M[4] = { 1, 0, 0, 1 };
         for (int j = 0; j < 8; ++j)
         {
             for (int i = 0; i < 4; ++i) out[kEqcPlo + 4 * j + i] = (double) M[i];
-            matmul2(M, A16, M);
+            matmul2(M, AL, M);
         }
-        long double A128[4] = { M[0], M[1], M[2], M[3] };   // A^(16*8)
+        long double A8L[4] = { M[0], M[1], M[2], M[3] };
         long double H[4] = { 1, 0, 0, 1 };
         for (int j = 0; j < 4; ++j)
         {
             for (int i = 0; i < 4; ++i) out[kEqcPhi + 4 * j + i] = (double) H[i];
-            matmul2(H, A128, H);
+            matmul2(H, A8L, H);
         }
     }
-    long double M[4] = { A16[0], A16[1], A16[2], A16[3] };
+    long double M[4] = { AL[0], AL[1], AL[2], AL[3] };
     for (int d = 0; d < 5; ++d)
     {
         for (int i = 0; i < 4; ++i) out[kEqcMs + 4 * d + i] = (double) M[i];
         matmul2(M, M, M);
     }
-    // M is now A^(16*32) = A^512 (one warp); a tile is kEqCWarps warps
+    // M is now A^(32 L): one warp segment
     for (int i = 0; i < 4; ++i) out[kEqcMw + i] = (double) M[i];
-    long double Mt[4] = { 1, 0, 0, 1 };
-    for (int w = 0; w < kEqCWarps; ++w) matmul2(Mt, M, Mt);
-    for (int i = 0; i < 4; ++i) out[kEqcMt + i] = (double) Mt[i];
 }
 
 cpq_status Engine::uploadEq(int64_t nCallbacks)

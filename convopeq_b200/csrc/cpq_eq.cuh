@@ -44,22 +44,25 @@
 namespace cpq
 {
 
+#ifndef CPQ_EQ_L
+#define CPQ_EQ_L 32
+#endif
 constexpr int kEqThreads = 256;
 constexpr int kEqCWarps = 7;                     // compute warps; warp 7 is the chain warp
 constexpr int kEqCThreads = kEqCWarps * 32;      // 224
-constexpr int kEqL = 16;                         // samples per compute thread
-constexpr int kEqTile = kEqCThreads * kEqL;      // 3584
+constexpr int kEqL = CPQ_EQ_L;                   // samples per compute thread (16 or 32)
+constexpr int kEqTile = kEqCThreads * kEqL;      // 3584 (7168)
 constexpr int kEqPad = kEqL + 2;                 // shared-memory doubles per thread block (keeps 16-byte alignment)
+static_assert(kEqL == 16 || kEqL == 32, "samples per thread");
 
 // per (parameter set, band) constants, all double; built by buildBandConstants() in cpq_engine.cu
-constexpr int kEqcCoef = 0;      // a1,a2,a3,m0,m1,m2, forceExact(!=0), kind (0 literal, 1 TPT peaking, 2 TPT), g, 2g
-constexpr int kEqcW = 12;        // w[16][2]   zero-state weights, c = sum_j w[j] * v0[j]
-constexpr int kEqcMs = 44;       // Ms[5][4]   A^(16*2^d), row-major 2x2
-constexpr int kEqcPlo = 64;      // Plo[8][4]  A^(16*j)
-constexpr int kEqcPhi = 96;      // Phi[4][4]  A^(128*j)
-constexpr int kEqcMw = 112;      // A^512   (one warp)
-constexpr int kEqcMt = 116;      // A^3584  (one tile)
-constexpr int kEqcStride = 120;  // doubles per band (20 bands = 19.2 KB, staged in shared memory)
+constexpr int kEqcCoef = 0;                      // a1,a2,a3,m0,m1,m2, forceExact(!=0), kind (0 literal, 1 TPT peaking, 2 TPT), g, 2g
+constexpr int kEqcW = 12;                        // w[L][2]    zero-state weights, c = sum_j w[j] * v0[j]
+constexpr int kEqcMs = kEqcW + 2 * kEqL;         // Ms[5][4]   A^(L*2^d), row-major 2x2
+constexpr int kEqcPlo = kEqcMs + 20;             // Plo[8][4]  A^(L*j)
+constexpr int kEqcPhi = kEqcPlo + 32;            // Phi[4][4]  A^(8L*j)
+constexpr int kEqcMw = kEqcPhi + 16;             // A^(32L)    (one warp segment)
+constexpr int kEqcStride = kEqcMw + 4;           // doubles per band, staged in shared memory for all 20 bands
 
 constexpr int kEqSeg = 32 * kEqL;                // 512 samples per warp segment
 // shared memory: segment tiles | band constants | mailboxes st[20][8] (double2) | flags fl[20][8] (int) | ticket
@@ -147,19 +150,20 @@ __device__ __forceinline__ bool eq_valid(double v) { return fabs(v) < 1.0e15; } 
 
 // padded shared index: 18-double stride per 16 samples keeps every thread's block 16-byte aligned and both the
 // coalesced pass (consecutive t) and the per-thread LDS.128/STS.128 pass free of bank conflicts
-__device__ __forceinline__ int eq_sidx(int t) { return t + 2 * (t >> 4); }
+__device__ __forceinline__ int eq_sidx(int t) { return t + 2 * (t / kEqL); }
 
-// The reference's per-sample semantics (processBandStereo) for one thread's block, run from shared memory.
-// Used only by threads whose fast pass saw |out| >= 4.5 / suspicious state.  Returns true if a state had to be
-// reset (which the scan cannot represent).
-__device__ __noinline__ bool eq_exact_block(double* s /* smem, 16 consecutive slots */, double& ic1, double& ic2,
-                                            double a1, double a2, double a3, double m0, double m1, double m2, double sat)
+// The reference's per-sample semantics (processBandStereo, EQProcessor.Processing.cpp:191-276) over one thread's block,
+// in registers: literal recurrence, clamped tanh 27/9 with a true division, scrubs and the +-100 clamp.  Used by warps
+// in exact mode only.  Returns true if a state had to be reset (which the scan cannot represent).
+__device__ __forceinline__ bool eq_pass2_exact(double (&x)[kEqL], double& ic1, double& ic2, const double* __restrict__ bc, double sat)
 {
+    const double a1 = bc[0], a2 = bc[1], a3 = bc[2], m0 = bc[3], m1 = bc[4], m2 = bc[5];
     bool reset = false;
     const double oneMinusSat = 1.0 - sat;
+#pragma unroll
     for (int j = 0; j < kEqL; ++j)
     {
-        const double v0 = s[j];
+        const double v0 = x[j];
         const double v3 = v0 - ic2;
         const double v1 = fma(a1, ic1, a2 * v3);
         const double v2 = fma(a2, ic1, fma(a3, v3, ic2));
@@ -179,7 +183,7 @@ __device__ __noinline__ bool eq_exact_block(double* s /* smem, 16 consecutive sl
         if (!eq_valid(ic2)) { ic2 = 0.0; reset = true; }
         out = (out > -100.0) ? out : -100.0;
         out = (out < 100.0) ? out : 100.0;
-        s[j] = out;
+        x[j] = out;
     }
     return reset;
 }
@@ -254,7 +258,7 @@ __device__ __forceinline__ void eq_pass2(double (&x)[kEqL], double& ic1, double&
 }
 
 #ifndef CPQ_EQ_MINBLOCKS
-#define CPQ_EQ_MINBLOCKS 4
+#define CPQ_EQ_MINBLOCKS (CPQ_EQ_L == 16 ? 3 : 2)
 #endif
 __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs a)
 {
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                 bo = nextBand(bo);
                 progress = true;
             }
-            if (!progress) __nanosleep(64);
+            if (!progress) __nanosleep(200);
         }
         return;
     }
@@ -356,49 +360,54 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
     double* myStash = wtile + lane * kEqPad;   // 16 consecutive slots + 2 pad slots
 
     // ---- coalesced load + layer assembly (Get) ----
-    // Fast path: callbacks are whole multiples of the 512-sample segment (block >= 512) and the tail streams are
-    // stored in stream order (regular plans), so the tail source position is one lookup per (layer, segment).
+    // Fast path: callbacks are whole multiples of 512 samples and the tail streams are stored in stream order
+    // (regular plans), so the tail source position is one lookup per (layer, 512-sample sub-block).
     const bool segFast = a.assemble && a.blockLog2 >= 9 && a.blockMap[0] == nullptr && a.blockMap[1] == nullptr;
     if (!a.assemble || segFast)
     {
-        const double* tp[2] = { nullptr, nullptr };
-        double tg[2] = { 0.0, 0.0 };
-        if (segFast && nValid > 0)
-        {
-            const int64_t c = w0 >> a.blockLog2;
-            const int64_t off = w0 & (int64_t) bmask;
-#pragma unroll
-            for (int l = 0; l < 2; ++l)
-                if (l < a.nTail)
-                {
-                    const int64_t sp = __ldg(a.tailSrc[l] + c);
-                    if (sp >= 0)
-                    {
-                        tp[l] = a.tail[l] + (size_t) seq * a.tailStride[l] + sp + off;
-                        tg[l] = a.tailGain[l];
-                    }
-                }
-        }
-        const double* ip = io + w0;
         const bool outer = a.assemble && a.outer;
         const double wet = a.wetGain;
 #pragma unroll
-        for (int k = 0; k < kEqL; ++k)
+        for (int sb = 0; sb < kEqSeg / 512; ++sb)
         {
-            const int i = lane + 32 * k;
-            double v = 0.0;
-            if (i < nValid)
+            const int64_t ws = w0 + sb * 512;
+            const double* tp[2] = { nullptr, nullptr };
+            double tg[2] = { 0.0, 0.0 };
+            if (segFast && sb * 512 < nValid)
             {
-                v = ip[i];
-                if (tp[0]) v += __ldg(tp[0] + i) * tg[0];
-                if (tp[1]) v += __ldg(tp[1] + i) * tg[1];
-                if (outer)
-                {
-                    if (!(fabs(v) < 1.0e300)) v = 0.0;
-                    v *= wet;
-                }
+                const int64_t c = ws >> a.blockLog2;
+                const int64_t off = ws & (int64_t) bmask;
+#pragma unroll
+                for (int l = 0; l < 2; ++l)
+                    if (l < a.nTail)
+                    {
+                        const int64_t sp = __ldg(a.tailSrc[l] + c);
+                        if (sp >= 0)
+                        {
+                            tp[l] = a.tail[l] + (size_t) seq * a.tailStride[l] + sp + off;
+                            tg[l] = a.tailGain[l];
+                        }
+                    }
             }
-            wtile[eq_sidx(i)] = v;
+            const double* ip = io + ws;
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+            {
+                const int i = lane + 32 * k;
+                double v = 0.0;
+                if (sb * 512 + i < nValid)
+                {
+                    v = ip[i];
+                    if (tp[0]) v += __ldg(tp[0] + i) * tg[0];
+                    if (tp[1]) v += __ldg(tp[1] + i) * tg[1];
+                    if (outer)
+                    {
+                        if (!(fabs(v) < 1.0e300)) v = 0.0;
+                        v *= wet;
+                    }
+                }
+                wtile[eq_sidx(sb * 512 + i)] = v;
+            }
         }
     }
     else
@@ -440,16 +449,18 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
     __syncwarp();
 
     double x[kEqL];
-    unsigned hiMax = 0;   // running max of |x|'s high word: raw input large enough that a state could reach 1e15?
+    auto loadBlock = [&](unsigned& hi) {
 #pragma unroll
-    for (int j = 0; j < kEqL / 2; ++j)
-    {
-        const double2 v = reinterpret_cast<const double2*>(myStash)[j];
-        x[2 * j] = v.x;
-        x[2 * j + 1] = v.y;
-        hiMax = max(hiMax, max((unsigned) __double2hiint(v.x) & 0x7fffffffu, (unsigned) __double2hiint(v.y) & 0x7fffffffu));
-    }
-    bool suspicious = hiMax >= 0x41cdcd65u;   // |x| >= 1e9 (or NaN/Inf)
+        for (int j = 0; j < kEqL / 2; ++j)
+        {
+            const double2 v = reinterpret_cast<const double2*>(myStash)[j];
+            x[2 * j] = v.x;
+            x[2 * j + 1] = v.y;
+            hi = max(hi, max((unsigned) __double2hiint(v.x) & 0x7fffffffu, (unsigned) __double2hiint(v.y) & 0x7fffffffu));
+        }
+    };
+    unsigned hiIn = 0;   // max of |x|'s high word over the raw input
+    loadBlock(hiIn);
 
     if (a.doEq)
     {
@@ -458,11 +469,11 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
         // the thread whose block starts at sample T holds the sequence's final state when the last tile is partial
         const int64_t remT = a.T - t0;
         const bool ownsFinal = a.stateOut && remT < kEqTile && remT >= 0 && tid == (int) (remT / kEqL);
-        for (int b = 0; b < CPQ_NUM_BANDS; ++b)
-        {
-            if (!((mask >> b) & 1u)) continue;   // uniform per CTA
-            const double* __restrict__ bc = cst + b * kEqcStride;
-            // ---- pass 1: zero-state response of this thread's 16 samples (four accumulation chains); stash the inputs ----
+
+        // Everything of one band up to the start state of this thread's block.  `link`: take part in the chain (wait for
+        // the mailbox, post the successor's); a replayed band finds its mailbox already filled and posts nothing.
+        auto bandStart = [&](int b, const double* __restrict__ bc, bool link, double& ic1, double& ic2) {
+            // ---- pass 1: zero-state response of this thread's samples (four accumulation chains) ----
             double c1 = 0.0, c2 = 0.0, d1 = 0.0, d2 = 0.0;
 #pragma unroll
             for (int j = 0; j < kEqL; j += 2)
@@ -476,9 +487,7 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
             }
             c1 += d1;
             c2 += d2;
-#pragma unroll
-            for (int j = 0; j < kEqL / 2; ++j) reinterpret_cast<double2*>(myStash)[j] = make_double2(x[2 * j], x[2 * j + 1]);
-            // ---- warp inclusive scan of s -> A^16 s + c ----
+            // ---- warp inclusive scan of s -> A^L s + c ----
 #pragma unroll
             for (int d = 0; d < 5; ++d)
             {
@@ -498,18 +507,19 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
             if (lane == 0) { e1 = 0.0; e2 = 0.0; }
 
             // ---- link: state at the start of this segment from the previous warp (or the chain warp) ----
+            if (link)
             {
                 const int* f = fl + b * 8 + warp;
-                while (lds_volatile(f) == 0) { }
+                while (lds_volatile(f) == 0) { __nanosleep(40); }   // a spinning warp would steal issue slots from the FP64 warps
                 __threadfence_block();
             }
             double p1, p2;
             {
-                const double2 s = st[b * 8 + warp];
-                p1 = s.x;
-                p2 = s.y;
+                const double2 sv = st[b * 8 + warp];
+                p1 = sv.x;
+                p2 = sv.y;
             }
-            if (lane == 31)
+            if (link && lane == 31)
             {
                 double o1 = p1, o2 = p2;
                 matvec2(bc + kEqcMw, o1, o2, c1, c2);   // state after this segment
@@ -517,47 +527,71 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                 __threadfence_block();
                 sts_volatile(fl + b * 8 + warp + 1, 1);
             }
-            // ---- state at the start of this thread's block: A^(16 lane) s_in + e ----
-            matvec2(bc + kEqcPlo + 4 * (lane & 7), p1, p2, 0.0, 0.0);    // A^(16 (lane & 7))
-            matvec2(bc + kEqcPhi + 4 * (lane >> 3), p1, p2, e1, e2);     // A^(128 (lane >> 3)) ... + e
-            double ic1 = p1, ic2 = p2;
-            reinterpret_cast<double2*>(myStash)[kEqL / 2] = make_double2(ic1, ic2);   // start state, for the exact replay (pad slots)
+            // ---- state at the start of this thread's block: A^(L lane) s_in + e ----
+            matvec2(bc + kEqcPlo + 4 * (lane & 7), p1, p2, 0.0, 0.0);    // A^(L (lane & 7))
+            matvec2(bc + kEqcPhi + 4 * (lane >> 3), p1, p2, e1, e2);     // A^(8L (lane >> 3)) ... + e
+            ic1 = p1;
+            ic2 = p2;
             if (ownsFinal)
             {
                 a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2] = ic1;
                 a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2 + 1] = ic2;
             }
+        };
 
-            // ---- pass 2, fast path ----
-            hiMax = max((unsigned) __double2hiint(ic1) & 0x7fffffffu, (unsigned) __double2hiint(ic2) & 0x7fffffffu);
-            bool rare = suspicious | (hiMax >= 0x426d1a94u) | (bc[6] != 0.0);   // |state| >= 1e12
-            hiMax = 0;
-            const int kind = (int) bc[7];
-            if (sat > 0.0)
+        // ---- fast mode: bands in order until some lane leaves the regime where the reference's clamps are identities ----
+        bool exactMode = __any_sync(0xffffffffu, hiIn >= 0x41cdcd65u);   // |x| >= 1e9 (or NaN/Inf) in the raw input
+        int linked = -1;                                                 // last band whose link this warp has served
+        if (!exactMode)
+        {
+            for (int b = 0; b < CPQ_NUM_BANDS; ++b)
             {
-                if (kind == 1) eq_pass2<true, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
-                else if (kind == 2) eq_pass2<true, 2>(x, ic1, ic2, bc, alpha, gamma, hiMax);
-                else eq_pass2<true, 0>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                if (!((mask >> b) & 1u)) continue;   // uniform per CTA
+                const double* __restrict__ bc = cst + b * kEqcStride;
+                double ic1, ic2;
+                bandStart(b, bc, true, ic1, ic2);
+                linked = b;
+                unsigned hiMax = max((unsigned) __double2hiint(ic1) & 0x7fffffffu, (unsigned) __double2hiint(ic2) & 0x7fffffffu);
+                bool rare = (hiMax >= 0x426d1a94u) | (bc[6] != 0.0);   // |state| >= 1e12, or coefficients outside the fast path's contract
+                hiMax = 0;
+                const int kind = (int) bc[7];
+                if (sat > 0.0)
+                {
+                    if (kind == 1) eq_pass2<true, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                    else if (kind == 2) eq_pass2<true, 2>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                    else eq_pass2<true, 0>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                }
+                else
+                {
+                    if (kind == 1) eq_pass2<false, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                    else if (kind == 2) eq_pass2<false, 2>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                    else eq_pass2<false, 0>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                }
+                rare |= hiMax >= thrHi;   // some |out| >= 4.5 (100 without saturation), or NaN
+                if (__any_sync(0xffffffffu, rare))
+                {
+                    exactMode = true;
+                    break;
+                }
             }
-            else
+        }
+        // ---- exact mode: the whole segment again from the tile input with the reference's per-sample semantics; bands
+        // whose link was already served are replayed (same states up to rounding), the others take part in the chain ----
+        if (exactMode)
+        {
+            unsigned dummy = 0;
+            loadBlock(dummy);
+            for (int b = 0; b < CPQ_NUM_BANDS; ++b)
             {
-                if (kind == 1) eq_pass2<false, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
-                else if (kind == 2) eq_pass2<false, 2>(x, ic1, ic2, bc, alpha, gamma, hiMax);
-                else eq_pass2<false, 0>(x, ic1, ic2, bc, alpha, gamma, hiMax);
-            }
-            rare |= hiMax >= thrHi;   // some |out| >= 4.5 (100 without saturation), or NaN
-            suspicious = false;       // outputs of a band are bounded by 100 (or replayed exactly below)
-            if (rare)
-            {
-                // exact replay from the stashed inputs and the same start state
-                ic1 = myStash[kEqL];
-                ic2 = myStash[kEqL + 1];
-                if (eq_exact_block(myStash, ic1, ic2, bc[0], bc[1], bc[2], bc[3], bc[4], bc[5], sat)) atomicExch(a.fault, 1u);
-#pragma unroll
-                for (int j = 0; j < kEqL; ++j) x[j] = myStash[j];
+                if (!((mask >> b) & 1u)) continue;
+                const double* __restrict__ bc = cst + b * kEqcStride;
+                double ic1, ic2;
+                bandStart(b, bc, b > linked, ic1, ic2);
+                if (eq_pass2_exact(x, ic1, ic2, bc, sat)) atomicExch(a.fault, 1u);
             }
         }
     }
+    __syncwarp();
 #pragma unroll
     for (int j = 0; j < kEqL / 2; ++j) reinterpret_cast<double2*>(myStash)[j] = make_double2(x[2 * j], x[2 * j + 1]);
     __syncwarp();
