@@ -323,20 +323,27 @@ def main():
         achieved = alg_bytes_per_launch / (dur_ms * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(names[dom])
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            # measured dram bytes per launch at the profiled launch size, scaled to this run's launch size
+            traffic = tj[names[dom]] / tj["_channel_samples_per_launch"] * (cs_rank / chunks)
         except Exception:
             pass
         dfma = capi.load().cpq_probe_dfma_tflops(local, 20000)
-        # FP64 instruction model per channel-sample: EQ 20 bands x ~56 flop, MAC 8*(12+31), FFT ~2x5*log2
-        flop_model = {"eq_kernel": 20 * 56.0, "mac_kernel": 8.0 * (12 + 31), "fft_fwd_kernel": 5.0 * (9 + 12) + 16, "fft_inv_kernel": 5.0 * (9 + 12) + 16}
+        # FP64 instruction model per channel-sample (FMA = 2 flop): EQ 20 bands x ~14 instr, MAC 4 DFMA x (12+31)
+        # taps, FFT ~ 2.5 N log2 N flop per real transform of N = 2P points -> 5 log2(2P) flop per output sample
+        flop_model = {"eq_kernel": 20 * 14.0 * 2, "mac_kernel": 8.0 * (12 + 31), "fft_fwd_kernel": 5.0 * (10 + 13), "fft_inv_kernel": 5.0 * (10 + 13)}
         roofline = {"kernel": names[dom], "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launch_ms": dur_ms,
                     "launches_per_step": chunks * launches_per_chunk,
                     "stage_ms_per_step": dict(zip(names, [float(v) for v in st[:4]])),
+                    "whole_path": {"achieved": 16.0 * value / world / 1e9, "frac": 16.0 * value / world / 1e9 / hbm_peak,
+                                   "note": "16 B per channel-sample x channel-samples/s of the whole step on one GPU"},
                     "fp64": {"probe_dfma_tflops": dfma,
                              "achieved_tflops": flop_model[names[dom]] * cs_rank / (st[dom] * 1e-3) / 1e12,
-                             "note": "this path is FP64-pipe bound when fused (SURVEY 8d); the HBM fraction uses the compulsory 16 B/channel-sample"}}
+                             "note": "FP64 instruction model of the dominant kernel vs the measured DFMA probe; this path is bound by "
+                                     "the FP64 pipe and shared-memory issue, not HBM (SURVEY 8d); the HBM fraction uses the compulsory "
+                                     "16 B/channel-sample"}}
         cpu = None
         if not args.no_cpu and world == 1:
             v, info = cpu_reference_run(args.cpu_seconds, min(T, 96000 // BLOCK * BLOCK))

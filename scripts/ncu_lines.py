@@ -26,14 +26,15 @@ stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 def num(x):
     try: return int(x)
     except: return 0
-base = None; agg = collections.defaultdict(lambda: [0, 0, collections.Counter()]); tot = 0; seen = set()
+base = None; agg = collections.defaultdict(lambda: [0, 0, collections.Counter()]); tot = 0; inst = -1
+want = int(os.environ.get("INSTANCE", "0"))      # which launch of the kernel in the report
 for r in rows[1:]:
     if len(r) < len(hdr): continue
     try: addr = int(r[ix["Address"]], 16)
     except: continue
     if base is None: base = addr
-    if addr in seen: continue      # the csv repeats the listing per kernel instance
-    seen.add(addr)
+    if addr == base: inst += 1       # the csv repeats the listing per kernel instance
+    if inst != want: continue
     key = line_of.get(addr - base)
     s = num(r[ix["# Samples"]]); tot += s
     a = agg[key]; a[0] += s; a[1] += num(r[ix["Instructions Executed"]])
