@@ -389,24 +389,47 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                         }
                     }
             }
+            // Loads are issued in unconditional batches of eight per array (clamped index instead of a branch), so one
+            // memory round trip serves eight samples; a branch per sample would serialise them.
             const double* ip = io + ws;
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
+            const int nv = nValid - sb * 512;            // valid samples of this sub-block (uniform per warp)
+            if (nv <= 0)
             {
-                const int i = lane + 32 * k;
-                double v = 0.0;
-                if (sb * 512 + i < nValid)
+#pragma unroll
+                for (int k = 0; k < 16; ++k) wtile[eq_sidx(sb * 512 + lane + 32 * k)] = 0.0;
+                continue;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+            {
+                double va[8], vb[8], vc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) va[k] = ip[min(lane + 32 * (8 * h + k), nv - 1)];
+                if (tp[0])
                 {
-                    v = ip[i];
-                    if (tp[0]) v += __ldg(tp[0] + i) * tg[0];
-                    if (tp[1]) v += __ldg(tp[1] + i) * tg[1];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) vb[k] = __ldg(tp[0] + min(lane + 32 * (8 * h + k), nv - 1));
+                }
+                if (tp[1])
+                {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) vc[k] = __ldg(tp[1] + min(lane + 32 * (8 * h + k), nv - 1));
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                {
+                    const int i = lane + 32 * (8 * h + k);
+                    double v = va[k];
+                    if (tp[0]) v += vb[k] * tg[0];
+                    if (tp[1]) v += vc[k] * tg[1];
                     if (outer)
                     {
                         if (!(fabs(v) < 1.0e300)) v = 0.0;
                         v *= wet;
                     }
+                    if (i >= nv) v = 0.0;
+                    wtile[eq_sidx(sb * 512 + i)] = v;
                 }
-                wtile[eq_sidx(sb * 512 + i)] = v;
             }
         }
     }
