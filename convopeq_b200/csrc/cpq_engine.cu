@@ -115,7 +115,6 @@ struct Engine
     bool haveGainTab = false;
     DevBuf<double> chainRec;
     DevBuf<unsigned> ticketFault;       // [0] ticket, [1] fault
-    unsigned long long epoch = 0;
 
     // epilogue
     double makeup = 1.0;
@@ -684,14 +683,18 @@ cpq_status Engine::ensureGather(int64_t nCallbacks)
 
 cpq_status Engine::launchEq(EqArgs& a)
 {
-    // one CTA per (sequence, 3584-sample tile); tiles of a sequence are chained through (sequence, tile, band) records
+    // one CTA per (sequence, kEqTile-sample tile); tiles of a sequence are chained through (sequence, tile, band) records
+    // whose payload is its own flag: all-ones = not written yet
     a.nRuns = (int) ((a.T + kEqTile - 1) / kEqTile);
-    ++epoch;
-    a.chain.epoch = epoch;
     a.chain.ticket = ticketFault.p;
     a.fault = ticketFault.p + 1;
-    if (a.doEq && a.nRuns > 1) CPQ_CUDA(chainRec.ensure((size_t) a.nSeq * a.nRuns * CPQ_NUM_BANDS * 4));
-    a.chain.rec = chainRec.p;
+    if (a.doEq && a.nRuns > 1)
+    {
+        const size_t n = (size_t) a.nSeq * a.nRuns * CPQ_NUM_BANDS * 2;
+        CPQ_CUDA(chainRec.ensure(n));
+        CPQ_CUDA(cudaMemsetAsync(chainRec.p, 0xff, n * sizeof(double), stream));
+    }
+    a.chain.rec = reinterpret_cast<double2*>(chainRec.p);
     static bool attrDone = false;
     if (!attrDone)
     {

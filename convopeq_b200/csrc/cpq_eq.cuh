@@ -7,21 +7,24 @@
 //   dither_kernel  PsychoacousticDither::processStereoBlock (PsychoacousticDither.h:293-355)
 //
 // The band recurrence is linear in its 2-element state (the tanh saturation only touches the band *output*,
-// Processing.cpp:148-168), so each band is a blocked scan.  A CTA owns one 3584-sample tile of one sequence, split
-// into seven 512-sample segments, one per compute warp, 16 consecutive samples per thread in registers.  Per band
-// a warp runs: pass 1 = zero-state response of each thread's block by 16 precomputed weight vectors, warp-shuffle
-// scan of s -> A^16 s + c, the *link* (below), a two-level table lookup for A^(16 lane), and pass 2 = the band
-// recurrence from the exact start state.  Bands are processed in order on the same registers, so a tile crosses
-// HBM once for all 20 bands.
+// Processing.cpp:148-168), so each band is a blocked scan.  A CTA owns one 8192-sample tile of one sequence, split
+// into eight 1024-sample segments, one per warp, 32 consecutive samples per thread in registers.  Per band a warp
+// runs: pass 1 = zero-state response of each thread's block by 32 precomputed weight vectors, warp-shuffle scan of
+// s -> A^32 s + c, the *link* (below), a two-level table lookup for A^(32 lane), and pass 2 = the band recurrence
+// from the exact start state.  Bands are processed in order on the same registers, so a tile crosses HBM once for
+// all 20 bands.
 //
 // Links instead of barriers: the warps of a CTA are a chain.  Warp w takes the state at the start of its segment
-// for band b from a shared-memory mailbox st[b][w] (flag fl[b][w]), and its lane 31 posts A^512 s_in + (segment
+// for band b from a shared-memory mailbox st[b][w] (flag fl[b][w]), and its lane 31 posts A^1024 s_in + (segment
 // aggregate) into st[b][w+1] right after the warp scan.  There is no CTA barrier in the band loop: warps run
-// skewed by one link latency and otherwise independently, and each warp loads/stores its own segment.  The
-// eighth warp is the chain warp: one thread moves states between tiles -- it polls the record (seq, tile-1, band)
-// published by the predecessor CTA with release/acquire flags into st[b][0], and publishes st[b][7] for the
-// successor -- so no compute warp ever waits on global memory.  Tiles take their index from an atomic ticket in
-// run-major order, so a predecessor CTA is always already running (or done) when a CTA starts.
+// skewed by one link latency and otherwise independently, and each warp loads/stores its own segment.  Tiles of a
+// sequence are chained the same way through 16-byte records (seq, tile, band) in global memory whose payload is its
+// own flag (the host fills them with all-ones before the launch): the last warp writes the state after the tile,
+// the first warp of the next tile reads it -- one band ahead of its use, so the L2 round trip is hidden and all
+// eight warps compute (a dedicated chain warp left one SM sub-partition with half the warps of the others:
+// measured 67 % vs 77 % FP64-pipe ceiling for the band loops, scripts/probes/eq_inner_probe.cu).  Tiles take
+// their index from an atomic ticket in run-major order, so a predecessor CTA is always already running (or done)
+// when a CTA starts.
 //
 // Pass 2 arithmetic.  The reference designs every band as a TPT SVF (a2 = g a1, a3 = g a2,
 // EQProcessor.Coefficients.cpp:101-130), which gives v2 = ic2 + g v1 and ic2' = ic2 + 2 g v1; with
@@ -48,10 +51,10 @@ namespace cpq
 #define CPQ_EQ_L 32
 #endif
 constexpr int kEqThreads = 256;
-constexpr int kEqCWarps = 7;                     // compute warps; warp 7 is the chain warp
-constexpr int kEqCThreads = kEqCWarps * 32;      // 224
+constexpr int kEqCWarps = 8;                     // every warp computes (an idle chain warp would leave one SM sub-partition half empty)
+constexpr int kEqCThreads = kEqCWarps * 32;      // 256
 constexpr int kEqL = CPQ_EQ_L;                   // samples per compute thread (16 or 32)
-constexpr int kEqTile = kEqCThreads * kEqL;      // 3584 (7168)
+constexpr int kEqTile = kEqCThreads * kEqL;      // 4096 (8192)
 constexpr int kEqPad = kEqL + 2;                 // shared-memory doubles per thread block (keeps 16-byte alignment)
 static_assert(kEqL == 16 || kEqL == 32, "samples per thread");
 
@@ -71,9 +74,8 @@ constexpr size_t kEqSmemBytes = (size_t) kEqSmemDoubles * sizeof(double) + 16;
 
 struct EqChain
 {
-    double* rec;          // [(seq*nRuns + run)*20 + band] x {s1, s2, epoch-as-u64, pad}
+    double2* rec;         // [(seq*nRuns + run)*20 + band] = band state after the tile; all-ones words = not written yet
     unsigned* ticket;     // CTA ticket counter
-    unsigned long long epoch;
 };
 
 struct EqArgs
@@ -82,7 +84,7 @@ struct EqArgs
     int64_t ioStride;
     int64_t T;              // samples per sequence
     int nSeq;
-    int nRuns;              // tiles per sequence = ceil(T / 3584); grid = nSeq * nRuns
+    int nRuns;              // tiles per sequence = ceil(T / kEqTile); grid = nSeq * nRuns
     // assembly
     int assemble;           // add tails / apply the outer boundary
     int nTail;              // number of tail layers (0..2)
@@ -135,6 +137,20 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// 16-byte record whose payload is its own flag: each 8-byte half is written atomically and is valid iff it is not the
+// all-ones sentinel the host fills the records with before every launch
+__device__ __forceinline__ double2 ld_volatile_f64x2(const double2* p)
+{
+    double2 v;
+    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_f64x2(double2* p, double2 v)
+{
+    asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ bool rec_pending(double2 v) { return __double2hiint(v.x) == -1 || __double2hiint(v.y) == -1; }
+__device__ __forceinline__ double rec_clean(double v) { return __double2hiint(v) == -1 ? __longlong_as_double(0x7ff8000000000000ll) : v; }
 __device__ __forceinline__ int lds_volatile(const int* p)
 {
     int v;
@@ -292,63 +308,20 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
     }
     __syncthreads();   // constants + cleared flags visible; the only CTA-wide barrier besides the ticket
 
-    if (warp == kEqCWarps)
+    // ---- tile-to-tile chain: records (seq, tile, band) in global memory, written by the last warp of a tile and read by
+    // the first warp of the next one.  The read of band b+1's record is issued while band b is computed, so its L2 round
+    // trip is never on the critical path; the predecessor tile started earlier (ticket order) and is normally far ahead.
+    const bool lastTile = run + 1 >= a.nRuns;
+    const bool fullLast = lastTile && (a.T - t0) == kEqTile;
+    const double2* recIn = (a.doEq && run > 0) ? a.chain.rec + (size_t) ((size_t) seq * a.nRuns + (run - 1)) * CPQ_NUM_BANDS : nullptr;
+    double2* recOut = (a.doEq && !lastTile) ? a.chain.rec + (size_t) ((size_t) seq * a.nRuns + run) * CPQ_NUM_BANDS : nullptr;
+    auto nextBand = [&](int b) { ++b; while (b < CPQ_NUM_BANDS && !((mask >> b) & 1u)) ++b; return b; };
+    double2 pre = make_double2(0.0, 0.0);   // warp 0: prefetched inbound record of band preBand
+    int preBand = -1;
+    if (warp == 0 && recIn)
     {
-        // ================= chain warp: one thread moves band states between the tiles of a sequence =================
-        if (lane != 0 || !a.doEq || mask == 0u) return;
-        const bool last = run + 1 >= a.nRuns;
-        const bool fullLast = last && (a.T - t0) == kEqTile;
-        auto nextBand = [&](int b) { ++b; while (b < CPQ_NUM_BANDS && !((mask >> b) & 1u)) ++b; return b; };
-        int bi = nextBand(-1), bo = bi;   // next band whose input state is still to be delivered / whose output is still to be forwarded
-        while (bo < CPQ_NUM_BANDS)
-        {
-            bool progress = false;
-            if (bi < CPQ_NUM_BANDS)
-            {
-                double s1 = 0.0, s2 = 0.0;
-                bool ready = true;
-                if (run > 0)
-                {
-                    const double* rec = a.chain.rec + ((size_t) ((size_t) seq * a.nRuns + (run - 1)) * CPQ_NUM_BANDS + bi) * 4;
-                    ready = ld_relaxed_u64(reinterpret_cast<const unsigned long long*>(rec + 2)) == a.chain.epoch;
-                    if (ready)
-                    {
-                        __threadfence();   // acquire: the record was written before its flag
-                        s1 = ld_cg_f64(rec);
-                        s2 = ld_cg_f64(rec + 1);
-                    }
-                }
-                if (ready)
-                {
-                    st[bi * 8] = make_double2(s1, s2);
-                    __threadfence_block();
-                    sts_volatile(fl + bi * 8, 1);
-                    bi = nextBand(bi);
-                    progress = true;
-                }
-            }
-            if (bo < bi && lds_volatile(fl + bo * 8 + kEqCWarps) != 0)
-            {
-                __threadfence_block();
-                const double2 s = st[bo * 8 + kEqCWarps];   // state after the tile's last sample
-                if (!last)
-                {
-                    double* rec = a.chain.rec + ((size_t) ((size_t) seq * a.nRuns + run) * CPQ_NUM_BANDS + bo) * 4;
-                    rec[0] = s.x;
-                    rec[1] = s.y;
-                    st_release_u64(reinterpret_cast<unsigned long long*>(rec + 2), a.chain.epoch);
-                }
-                else if (fullLast && a.stateOut)
-                {
-                    a.stateOut[((size_t) seq * CPQ_NUM_BANDS + bo) * 2] = s.x;
-                    a.stateOut[((size_t) seq * CPQ_NUM_BANDS + bo) * 2 + 1] = s.y;
-                }
-                bo = nextBand(bo);
-                progress = true;
-            }
-            if (!progress) __nanosleep(200);
-        }
-        return;
+        preBand = nextBand(-1);
+        if (preBand < CPQ_NUM_BANDS) pre = ld_volatile_f64x2(recIn + preBand);
     }
 
     // ================= compute warps: one 512-sample segment each =================
@@ -529,12 +502,32 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
             double e2 = __shfl_up_sync(0xffffffffu, c2, 1);
             if (lane == 0) { e1 = 0.0; e2 = 0.0; }
 
-            // ---- link: state at the start of this segment from the previous warp (or the chain warp) ----
+            // ---- link: state at the start of this segment from the previous warp (warp 0: from the previous tile) ----
             if (link)
             {
-                const int* f = fl + b * 8 + warp;
-                while (lds_volatile(f) == 0) { __nanosleep(40); }   // a spinning warp would steal issue slots from the FP64 warps
-                __threadfence_block();
+                if (warp == 0)
+                {
+                    double2 sv = make_double2(0.0, 0.0);   // Reset state for the first tile
+                    if (recIn)
+                    {
+                        sv = (preBand == b) ? pre : ld_volatile_f64x2(recIn + b);
+                        while (rec_pending(sv))
+                        {
+                            __nanosleep(100);
+                            sv = ld_volatile_f64x2(recIn + b);
+                        }
+                        preBand = nextBand(b);
+                        if (preBand < CPQ_NUM_BANDS) pre = ld_volatile_f64x2(recIn + preBand);
+                    }
+                    if (lane == 0) st[b * 8] = sv;   // kept for an exact-mode replay of this band
+                    __syncwarp();
+                }
+                else
+                {
+                    const int* f = fl + b * 8 + warp;
+                    while (lds_volatile(f) == 0) { __nanosleep(40); }   // a spinning warp would steal issue slots from the FP64 warps
+                    __threadfence_block();
+                }
             }
             double p1, p2;
             {
@@ -546,9 +539,19 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
             {
                 double o1 = p1, o2 = p2;
                 matvec2(bc + kEqcMw, o1, o2, c1, c2);   // state after this segment
-                st[b * 8 + warp + 1] = make_double2(o1, o2);
-                __threadfence_block();
-                sts_volatile(fl + b * 8 + warp + 1, 1);
+                if (warp + 1 < kEqCWarps)
+                {
+                    st[b * 8 + warp + 1] = make_double2(o1, o2);
+                    __threadfence_block();
+                    sts_volatile(fl + b * 8 + warp + 1, 1);
+                }
+                else if (recOut)
+                    st_volatile_f64x2(recOut + b, make_double2(rec_clean(o1), rec_clean(o2)));   // state after the tile
+                else if (fullLast && a.stateOut)
+                {
+                    a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2] = o1;
+                    a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2 + 1] = o2;
+                }
             }
             // ---- state at the start of this thread's block: A^(L lane) s_in + e ----
             matvec2(bc + kEqcPlo + 4 * (lane & 7), p1, p2, 0.0, 0.0);    // A^(L (lane & 7))
