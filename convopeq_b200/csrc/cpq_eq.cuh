@@ -221,9 +221,12 @@ __device__ __forceinline__ void matvec2(const double* __restrict__ m, double& p1
 // gamma = 8s/3, with 1/(out^2+3) from the hardware seed (2^-23) and one Newton step (2^-46); the correction term is
 // <= 18 % of the result.  hiMax tracks the high word of d = out^2 + 3 (SAT; d >= 23.25 <=> |out| >= 4.5 up to rounding,
 // NaN/Inf compare high) or of |out| (no SAT).
-template <bool SAT, int KIND>
+// FUSE: pass 1 of the next band (c += w_next[j] * out[j], two accumulator pairs) rides along, so its independent DFMAs and
+// weight loads fill the issue slots the recurrence's dependency chain leaves empty.
+struct EqAcc { double c1, c2, d1, d2; };
+template <bool SAT, int KIND, bool FUSE = false>
 __device__ __forceinline__ void eq_pass2(double (&x)[kEqL], double& ic1, double& ic2, const double* __restrict__ bc, double alpha,
-                                         double gamma, unsigned& hiMax)
+                                         double gamma, unsigned& hiMax, const double* __restrict__ wNext = nullptr, EqAcc* acc = nullptr)
 {
     const double a1 = bc[0], a2 = bc[1], a3 = bc[2], m0 = bc[3], m1 = bc[4], m2 = bc[5], g = bc[8], g2 = bc[9];
 #pragma unroll
@@ -269,6 +272,20 @@ __device__ __forceinline__ void eq_pass2(double (&x)[kEqL], double& ic1, double&
         {
             hiMax = max(hiMax, (unsigned) __double2hiint(out) & 0x7fffffffu);
             x[j] = out;
+        }
+        if (FUSE)
+        {
+            const double2 w = reinterpret_cast<const double2*>(wNext)[j];
+            if (j & 1)
+            {
+                acc->d1 = fma(w.x, x[j], acc->d1);
+                acc->d2 = fma(w.y, x[j], acc->d2);
+            }
+            else
+            {
+                acc->c1 = fma(w.x, x[j], acc->c1);
+                acc->c2 = fma(w.y, x[j], acc->c2);
+            }
         }
     }
 }
@@ -370,6 +387,46 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
             {
 #pragma unroll
                 for (int k = 0; k < 16; ++k) wtile[eq_sidx(sb * 512 + lane + 32 * k)] = 0.0;
+                continue;
+            }
+            // 16-byte path: the whole 512-sample sub-block of every array in one batch of eight LDG.128 per lane
+            const bool vec16 = (nv & 1) == 0 && ((reinterpret_cast<uintptr_t>(ip) | reinterpret_cast<uintptr_t>(tp[0]) | reinterpret_cast<uintptr_t>(tp[1])) & 15) == 0;
+            if (vec16)
+            {
+                const double2* ip2 = reinterpret_cast<const double2*>(ip);
+                const double2* t02 = reinterpret_cast<const double2*>(tp[0]);
+                const double2* t12 = reinterpret_cast<const double2*>(tp[1]);
+                const int last2 = nv / 2 - 1;
+                double2 va[8], vb[8], vc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) va[k] = ip2[min(lane + 32 * k, last2)];
+                if (tp[0])
+                {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) vb[k] = __ldg(t02 + min(lane + 32 * k, last2));
+                }
+                if (tp[1])
+                {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) vc[k] = __ldg(t12 + min(lane + 32 * k, last2));
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                {
+                    const int i2 = lane + 32 * k;
+                    double2 v = va[k];
+                    if (tp[0]) { v.x += vb[k].x * tg[0]; v.y += vb[k].y * tg[0]; }
+                    if (tp[1]) { v.x += vc[k].x * tg[1]; v.y += vc[k].y * tg[1]; }
+                    if (outer)
+                    {
+                        if (!(fabs(v.x) < 1.0e300)) v.x = 0.0;
+                        if (!(fabs(v.y) < 1.0e300)) v.y = 0.0;
+                        v.x *= wet;
+                        v.y *= wet;
+                    }
+                    if (i2 > last2) v = make_double2(0.0, 0.0);
+                    *reinterpret_cast<double2*>(wtile + eq_sidx(sb * 512 + 2 * i2)) = v;
+                }
                 continue;
             }
 #pragma unroll
@@ -649,6 +706,23 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
         else
         {
             const bool mulG = a.doEq != 0, mulM = a.doEpilogue != 0, mulH = a.doEpilogue && a.applyHeadroom;
+            if ((nValid & 1) == 0 && (reinterpret_cast<uintptr_t>(op) & 15) == 0)
+            {
+#pragma unroll
+                for (int k = 0; k < kEqL / 2; ++k)
+                {
+                    const int i = 2 * (lane + 32 * k);
+                    if (i < nValid)
+                    {
+                        double2 v = *reinterpret_cast<const double2*>(wtile + eq_sidx(i));
+                        if (mulG) { v.x *= gconst; v.y *= gconst; }
+                        if (mulM) { v.x *= mk; v.y *= mk; }
+                        if (mulH) { v.x *= hr; v.y *= hr; }
+                        *reinterpret_cast<double2*>(op + i) = v;
+                    }
+                }
+            }
+            else
 #pragma unroll
             for (int k = 0; k < kEqL; ++k)
             {

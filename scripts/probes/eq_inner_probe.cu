@@ -7,7 +7,7 @@
 #include "convopeq_b200/csrc/cpq_eq.cuh"
 using namespace cpq;
 
-template <int MODE>   // 0: pass 2 only, 1: pass 1 + scan + matvecs + pass 2
+template <int MODE>   // 0: pass 2 only, 1: pass 1 + scan + matvecs + pass 2, 2: as 1 with the next band's pass 1 fused into pass 2
 __global__ void __launch_bounds__(256, 2) probe(const double* cstG, double* out, int reps)
 {
     extern __shared__ __align__(16) double sm[];
@@ -20,13 +20,15 @@ __global__ void __launch_bounds__(256, 2) probe(const double* cstG, double* out,
     unsigned hiMax = 0;
     const double sat = 0.20000000298023224, alpha = fma(-8.0, sat, 9.0) / 9.0, gamma = 8.0 * sat / 3.0;
     double ic1 = 0.0, ic2 = 0.0;
+    EqAcc acc { 0.0, 0.0, 0.0, 0.0 };
     for (int r = 0; r < reps; ++r)
         for (int b = 0; b < CPQ_NUM_BANDS; ++b)
         {
             const double* bc = sm + b * kEqcStride;
-            if (MODE == 1)
+            if (MODE >= 1)
             {
-                double c1 = 0.0, c2 = 0.0, d1 = 0.0, d2 = 0.0;
+                double c1 = acc.c1, c2 = acc.c2, d1 = acc.d1, d2 = acc.d2;
+                if (MODE == 1)
 #pragma unroll
                 for (int j = 0; j < kEqL; j += 2)
                 {
@@ -56,7 +58,9 @@ __global__ void __launch_bounds__(256, 2) probe(const double* cstG, double* out,
                 matvec2(bc + kEqcPhi + 4 * (lane >> 3), p1, p2, e1, e2);
                 ic1 = p1; ic2 = p2;
             }
-            eq_pass2<true, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+            acc = EqAcc { 0.0, 0.0, 0.0, 0.0 };
+            if (MODE == 2) eq_pass2<true, 1, true>(x, ic1, ic2, bc, alpha, gamma, hiMax, sm + ((b + 1) % CPQ_NUM_BANDS) * kEqcStride + kEqcW, &acc);
+            else eq_pass2<true, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
         }
     double s = ic1 + ic2 + hiMax;
 #pragma unroll
@@ -81,13 +85,14 @@ int main()
     const size_t smem = c.size() * 8;
     cudaFuncSetAttribute(probe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     cudaFuncSetAttribute(probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute(probe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int reps = 40;
-    for (int mode = 0; mode < 2; ++mode)
+    for (int mode = 0; mode < 3; ++mode)
         for (int threads : {128, 224, 256})
             for (int ctas : {1, 2})
             {
-                auto launch = [&] { if (mode == 0) probe<0><<<148 * ctas, threads, smem>>>(dc, dout, reps); else probe<1><<<148 * ctas, threads, smem>>>(dc, dout, reps); };
+                auto launch = [&] { if (mode == 0) probe<0><<<148 * ctas, threads, smem>>>(dc, dout, reps); else if (mode == 2) probe<2><<<148 * ctas, threads, smem>>>(dc, dout, reps); else probe<1><<<148 * ctas, threads, smem>>>(dc, dout, reps); };
                 launch();
                 cudaEventRecord(e0); launch(); cudaEventRecord(e1); cudaEventSynchronize(e1);
                 float ms; cudaEventElapsedTime(&ms, e0, e1);
