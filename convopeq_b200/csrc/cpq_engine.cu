@@ -178,12 +178,15 @@ static cudaError_t fwdLaunch(const FwdArgs& a, cudaStream_t s)
     using C = FftCfg<LOG2P>;
     if (!g_attrDone[LOG2P][0])
     {
-        cudaError_t e = cudaFuncSetAttribute(fft_fwd_kernel<LOG2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(fft_fwd_kernel<LOG2P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fft_fwd_kernel<LOG2P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
         if (e != cudaSuccess) return e;
         g_attrDone[LOG2P][0] = true;
     }
     const unsigned grid = (unsigned) ((a.totalFrames + C::FPC - 1) / C::FPC);
-    fft_fwd_kernel<LOG2P><<<grid, C::THREADS, C::SMEM, s>>>(a);
+    const bool ir = a.halfOnly || a.applyScale || a.gain || a.tilt;   // prepare-time variant
+    if (ir) fft_fwd_kernel<LOG2P, true><<<grid, C::THREADS, C::SMEM, s>>>(a);
+    else fft_fwd_kernel<LOG2P, false><<<grid, C::THREADS, C::SMEM, s>>>(a);
     return cudaGetLastError();
 }
 template <int LOG2P>
@@ -382,8 +385,9 @@ cpq_status Engine::ensureTwiddles(int li)
 {
     LayerDev& L = layer[li];
     const int P = plan.layers[li].partSize;
-    if (L.tw.p && L.tw.n == (size_t) P + 1) return CPQ_OK;
-    std::vector<double2> tw((size_t) P + 1);
+    if (L.tw.p && L.tw.n == 3 * ((size_t) P + 1)) return CPQ_OK;
+    // three tables of P+1 entries: W = exp(-2 pi i t / 2P); -i/2 W (forward split pass); i conj(W) / 2P (inverse pre-pass)
+    std::vector<double2> tw(3 * ((size_t) P + 1));
     const long double twoPiOverN = 2.0L * 3.141592653589793238462643383279502884L / (long double) (2 * P);
     for (int t = 0; t <= P; ++t)
     {
@@ -393,9 +397,12 @@ cpq_status Engine::ensureTwiddles(int li)
         else if (t == P) { c = -1.0L; s = 0.0L; }
         else if (2 * t == P) { c = 0.0L; s = 1.0L; }
         else { c = cosl(twoPiOverN * t); s = sinl(twoPiOverN * t); }
-        tw[(size_t) t] = make_double2((double) c, (double) -s);
+        const double2 w = make_double2((double) c, (double) -s);
+        tw[(size_t) t] = w;
+        tw[(size_t) (P + 1) + t] = make_double2(0.5 * w.y, -0.5 * w.x);
+        tw[2 * (size_t) (P + 1) + t] = make_double2(w.y / (double) (2 * P), w.x / (double) (2 * P));
     }
-    CPQ_CUDA(L.tw.ensure((size_t) P + 1));
+    CPQ_CUDA(L.tw.ensure(tw.size()));
     CPQ_CUDA(cudaMemcpyAsync(L.tw.p, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
     // compact per-pass tables {W^k, W^2k, W^4k}, W = exp(-2 pi i / (8 Ns)), for the radix-8 passes (FftCfg::passOffset)
     std::vector<double2> ptw;
@@ -919,8 +926,10 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 const int step = kMacSuper;
                 int fpc = (int) ((K[li] + step - 1) / step) * step;
                 while (fpc > 2 * step && (int64_t) binTiles * ns * ((K[li] + fpc - 1) / fpc) < 4 * 148 * 2) fpc = ((fpc / 2 + step - 1) / step) * step;
+                static const int fpcEnv = [] { const char* e = getenv("CPQ_MAC_FPC"); return e ? atoi(e) : 0; }();   // tuning knob
+                if (fpcEnv > 0 && fpcEnv % step == 0 && fpcEnv < fpc && K[li] <= 2 * step) fpc = fpcEnv;   // short layers only
                 a.framesPerCta = fpc;
-                a.ringRows = macRingRows(a.qEnd - a.qBegin);
+                a.ringRows = fpc <= step ? step + (a.qEnd - a.qBegin) - 1 : macRingRows(a.qEnd - a.qBegin);
                 const size_t smem = macSmemBytes(a.qEnd - a.qBegin, a.ringRows);
                 static size_t macSmemSet = 0;
                 if (smem > macSmemSet)

@@ -168,7 +168,16 @@ struct FftCfg
     static constexpr int PTW_SIZE = passOffset(NPASS8);
 };
 
-template <int LOG2P>
+// Frames of one CTA never exchange data: each frame's TPF threads (whole warps) meet at their own named barrier.
+template <int TPF, int THREADS>
+__device__ __forceinline__ void fft_sync(int fl)
+{
+    if constexpr (TPF == THREADS || (TPF % 32) != 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(fl + 1), "n"(TPF) : "memory");
+}
+
+// IR = prepare-time variant (half frames, scale, spectrum gain / tilt); the streaming variant carries none of that.
+template <int LOG2P, bool IR>
 __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOCKS) fft_fwd_kernel(FwdArgs a)
 {
     using C = FftCfg<LOG2P>;
@@ -183,14 +192,18 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOC
     const int f = live ? (int) (gf % a.framesPerSeq) : 0;
     const double* src = a.src + seq * a.srcStride;
     const int64_t base = a.frameStart0 + (int64_t) f * P;
-    const bool vec_ok = (a.halfOnly == 0);
+    const bool vec_ok = !IR || (a.halfOnly == 0);
+    // whole frame inside the valid range and 16-byte aligned: no per-element checks (uniform per frame)
+    const bool inside = !IR && live && base >= a.lo && base + 2 * P <= a.hi && ((reinterpret_cast<uintptr_t>(src + base) & 15) == 0);
+    const double2* src2 = reinterpret_cast<const double2*>(src + base);
 
     auto gload = [&](int idx) -> double2 {
         // z[idx] = x[2 idx] + i x[2 idx + 1]
+        if (inside) return __ldg(src2 + idx);
         const int64_t g = base + 2 * (int64_t) idx;
         if (!live) return make_double2(0.0, 0.0);
-        if (a.halfOnly && 2 * idx >= P) return make_double2(0.0, 0.0);
-        if (vec_ok && g >= a.lo && g + 1 < a.hi) return __ldg(reinterpret_cast<const double2*>(src + g));
+        if (IR && a.halfOnly && 2 * idx >= P) return make_double2(0.0, 0.0);
+        if (vec_ok && g >= a.lo && g + 1 < a.hi && ((reinterpret_cast<uintptr_t>(src + g) & 15) == 0)) return __ldg(reinterpret_cast<const double2*>(src + g));
         double2 z;
         z.x = (g >= a.lo && g < a.hi) ? __ldg(src + g) : 0.0;
         z.y = (g + 1 >= a.lo && g + 1 < a.hi) ? __ldg(src + g + 1) : 0.0;
@@ -214,7 +227,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOC
             for (int r = 0; r < R; ++r) buf[fft_pad(ob + r)] = v[i][r];
         }
         Ns = R;
-        __syncthreads();
+        fft_sync<TPF, C::THREADS>(fl);
     }
 #pragma unroll
     for (int p = 0; p < C::NPASS8; ++p)
@@ -224,47 +237,55 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOC
         else
         {
             stockham_load<8, -1>(v, t, P, Ns, a.ptw + C::passOffset(p), sload);
-            __syncthreads();
+            fft_sync<TPF, C::THREADS>(fl);
         }
         const int ob = stockham_out_base<8>(t, Ns);
 #pragma unroll
         for (int r = 0; r < 8; ++r) buf[fft_pad(ob + r * Ns)] = v[r];
         Ns *= 8;
-        __syncthreads();
+        fft_sync<TPF, C::THREADS>(fl);
     }
 
     // ---- split pass: X[m] = E + W_N^m O, X[P-m] = conj(E - W_N^m O) ----
     if (!live) return;
     double2* out = a.out + ((size_t) seq * a.outFramesPerSeq + (size_t) (f + a.outFrameOffset)) * (size_t) P;   // packed row
     auto emit = [&](int m, double2 X) {
-        if (a.applyScale) { X.x *= a.scale; X.y *= a.scale; }
-        if (a.gain) { const double g = __ldg(a.gain + m); X.x *= g; X.y *= g; }
-        if (a.tilt) { const double g = __ldg(a.tilt + m); X.x *= g; X.y *= g; }
+        if constexpr (IR)
+        {
+            if (a.applyScale) { X.x *= a.scale; X.y *= a.scale; }
+            if (a.gain) { const double g = __ldg(a.gain + m); X.x *= g; X.y *= g; }
+            if (a.tilt) { const double g = __ldg(a.tilt + m); X.x *= g; X.y *= g; }
+        }
         out[m] = X;
     };
-    for (int m = t; m <= P / 2; m += TPF)
+    // with S = z[m] + conj z[P-m], D = z[m] - conj z[P-m] and the table twF[m] = -i/2 W_N^m:  T = twF[m] D,
+    // X[m] = S/2 + T, X[P-m] = conj(S/2 - T)
+    const double2* __restrict__ twF = a.tw + (P + 1);
+#pragma unroll
+    for (int i = 0; i <= (P / 2) / TPF; ++i)
     {
+        const int m = t + i * TPF;
+        if (m > P / 2) break;
         const double2 zm = buf[fft_pad(m)];
-        const double2 zc = cconj(buf[fft_pad((P - m) & (P - 1))]);
-        const double2 E = make_double2(0.5 * (zm.x + zc.x), 0.5 * (zm.y + zc.y));
-        const double2 D = make_double2(0.5 * (zm.x - zc.x), 0.5 * (zm.y - zc.y));
-        const double2 O = make_double2(D.y, -D.x);   // -i * D
-        const double2 w = __ldg(a.tw + m);
-        const double2 Tm = cmul(w, O);
         if (m == 0)
         {
             // bins 0 and P are real: packed into slot 0 as (Re X[0], Re X[P])
-            double r0 = E.x + O.x, rP = E.x - O.x;
-            if (a.applyScale) { r0 *= a.scale; rP *= a.scale; }
-            if (a.gain) { r0 *= __ldg(a.gain); rP *= __ldg(a.gain + P); }
-            if (a.tilt) { r0 *= __ldg(a.tilt); rP *= __ldg(a.tilt + P); }
+            double r0 = zm.x + zm.y, rP = zm.x - zm.y;
+            if constexpr (IR)
+            {
+                if (a.applyScale) { r0 *= a.scale; rP *= a.scale; }
+                if (a.gain) { r0 *= __ldg(a.gain); rP *= __ldg(a.gain + P); }
+                if (a.tilt) { r0 *= __ldg(a.tilt); rP *= __ldg(a.tilt + P); }
+            }
             out[0] = make_double2(r0, rP);
+            continue;
         }
-        else
-        {
-            emit(m, cadd(E, Tm));
-            if (m != P / 2) emit(P - m, cconj(csub(E, Tm)));
-        }
+        const double2 zp = buf[fft_pad(P - m)];
+        const double2 S = make_double2(zm.x + zp.x, zm.y - zp.y);
+        const double2 D = make_double2(zm.x - zp.x, zm.y + zp.y);
+        const double2 T = cmul(__ldg(twF + m), D);
+        emit(m, make_double2(fma(0.5, S.x, T.x), fma(0.5, S.y, T.y)));
+        if (m != P / 2) emit(P - m, make_double2(fma(0.5, S.x, -T.x), fma(-0.5, S.y, T.y)));
     }
 }
 
@@ -297,7 +318,8 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOC
     const double2* Y = a.in + ((size_t) seq * a.framesPerSeq + (size_t) f) * (size_t) P;   // packed row
     const double invN = 1.0 / (double) (2 * P);
 
-    // Z[m] = ((Y[m] + conj Y[P-m]) + i conj(W_N^m) (Y[m] - conj Y[P-m])) / N
+    // Z[m] = ((Y[m] + conj Y[P-m]) + i conj(W_N^m) (Y[m] - conj Y[P-m])) / N = S/N + twI[m] D,  twI[m] = i conj(W_N^m) / N
+    const double2* __restrict__ twI = a.tw + 2 * (P + 1);
     auto gload = [&](int m) -> double2 {
         if (!live) return make_double2(0.0, 0.0);
         double2 ym, yc;
@@ -314,9 +336,8 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOC
         }
         const double2 S = cadd(ym, yc);
         const double2 D = csub(ym, yc);
-        const double2 wc = cconj(__ldg(a.tw + m));
-        const double2 Tm = cmul(wc, D);
-        return make_double2((S.x - Tm.y) * invN, (S.y + Tm.x) * invN);   // S + i Tm
+        const double2 T = cmul(__ldg(twI + m), D);
+        return make_double2(fma(S.x, invN, T.x), fma(S.y, invN, T.y));
     };
     auto sload = [&](int idx) -> double2 { return buf[fft_pad(idx)]; };
 
@@ -336,7 +357,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOC
             for (int r = 0; r < R; ++r) buf[fft_pad(ob + r)] = v[i][r];
         }
         Ns = R;
-        __syncthreads();
+        fft_sync<TPF, C::THREADS>(fl);
     }
 #pragma unroll
     for (int p = 0; p < C::NPASS8; ++p)
@@ -346,7 +367,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOC
         else
         {
             stockham_load<8, +1>(v, t, P, Ns, a.ptw + C::passOffset(p), sload);
-            if (p != C::NPASS8 - 1) __syncthreads();
+            if (p != C::NPASS8 - 1) fft_sync<TPF, C::THREADS>(fl);
         }
         if (p == C::NPASS8 - 1)
         {
@@ -364,7 +385,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOC
 #pragma unroll
             for (int r = 0; r < 8; ++r) buf[fft_pad(ob + r * Ns)] = v[r];
             Ns *= 8;
-            __syncthreads();
+            fft_sync<TPF, C::THREADS>(fl);
         }
     }
 }
