@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcpq.so")
 SOURCES = [os.path.join(CSRC, "cpq_engine.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "cpq_fft.cuh"), os.path.join(CSRC, "cpq_mac.cuh"), os.path.join(CSRC, "cpq_eq.cuh"),
+DEPS = SOURCES + [os.path.join(CSRC, "cpq_fft.cuh"), os.path.join(CSRC, "cpq_fft16.cuh"), os.path.join(CSRC, "cpq_fft_large.cuh"), os.path.join(CSRC, "cpq_mac.cuh"), os.path.join(CSRC, "cpq_eq.cuh"),
                   os.path.join(CSRC, "cpq_plan.hpp"),
                   os.path.join(HERE, "..", "include", "cpq.h")]
 

@@ -17,6 +17,7 @@
 #include "../../include/cpq.h"
 #include "cpq_plan.hpp"
 #include "cpq_fft.cuh"
+#include "cpq_fft16.cuh"
 #include "cpq_fft_large.cuh"
 #include "cpq_mac.cuh"
 #include "cpq_eq.cuh"
@@ -204,10 +205,49 @@ static cudaError_t invLaunch(const InvArgs& a, cudaStream_t s)
     return cudaGetLastError();
 }
 
+// sixteen-points-per-thread kernels (cpq_fft16.cuh) for the streaming transforms at P = 512 / 4096
+static const bool g_fft16 = [] { const char* e = getenv("CPQ_FFT16"); return !e || atoi(e) != 0; }();
+template <int LOG2P>
+static cudaError_t fwd16Launch(const FwdArgs& a, cudaStream_t s)
+{
+    using C = Fft16Cfg<LOG2P>;
+    static bool attr = false;
+    if (!attr)
+    {
+        cudaError_t e = cudaFuncSetAttribute(fft_fwd16_kernel<LOG2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    fft_fwd16_kernel<LOG2P><<<(unsigned) ((a.totalFrames + C::FPC - 1) / C::FPC), C::THREADS, C::SMEM, s>>>(a);
+    return cudaGetLastError();
+}
+template <int LOG2P>
+static cudaError_t inv16Launch(const InvArgs& a, cudaStream_t s)
+{
+    using C = Fft16Cfg<LOG2P>;
+    static bool attr = false;
+    if (!attr)
+    {
+        cudaError_t e = cudaFuncSetAttribute(fft_inv16_kernel<LOG2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    fft_inv16_kernel<LOG2P><<<(unsigned) ((a.totalFrames + C::FPC - 1) / C::FPC), C::THREADS, C::SMEM, s>>>(a);
+    return cudaGetLastError();
+}
+
 cpq_status Engine::launchFwd(int log2P, const FwdArgs& a)
 {
     if (a.totalFrames <= 0) return CPQ_OK;
     cudaError_t e;
+    const bool ir = a.halfOnly || a.applyScale || a.gain || a.tilt;
+    if (g_fft16 && !ir && (log2P == 9 || log2P == 12))
+    {
+        e = log2P == 9 ? fwd16Launch<9>(a, stream) : fwd16Launch<12>(a, stream);
+        ++launches;
+        CPQ_CUDA(e);
+        return CPQ_OK;
+    }
     switch (log2P)
     {
         case 6: e = fwdLaunch<6>(a, stream); break;
@@ -228,6 +268,13 @@ cpq_status Engine::launchInv(int log2P, const InvArgs& a)
 {
     if (a.totalFrames <= 0) return CPQ_OK;
     cudaError_t e;
+    if (g_fft16 && (log2P == 9 || log2P == 12))
+    {
+        e = log2P == 9 ? inv16Launch<9>(a, stream) : inv16Launch<12>(a, stream);
+        ++launches;
+        CPQ_CUDA(e);
+        return CPQ_OK;
+    }
     switch (log2P)
     {
         case 6: e = invLaunch<6>(a, stream); break;
