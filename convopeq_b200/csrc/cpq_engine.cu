@@ -159,6 +159,11 @@ struct Engine
     cpq_status setImpulse(int stream_, int ch, const double* ir, int len, double scale, const cpq_filter_spec* spec);
     cpq_status ensureTwiddles(int li);
     cpq_status uploadEq(int64_t nCallbacks);
+    cpq_status uploadPost();
+    struct OutCfg { int filterEnabled = 0, convIsLast = 0, hc = 1, lc = 0, lp = 1; double dcCutoff = 0.0; int finalClamp = 0; } outCfg;
+    bool postDirty = true;
+    unsigned postIdentity = 0;          // output-filter stages whose coefficients are the identity (skipped)
+    DevBuf<double> postc, postState;
     cpq_status ensureGather(int64_t nCallbacks);
     cpq_status processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar);
     cpq_status processDevice(double* dIo, int64_t stride, int64_t T, unsigned stages) { return processCore(dIo, stride, T, stages, nullptr); }
@@ -583,6 +588,8 @@ static void matmul2(const long double* a, const long double* b, long double* c)
     for (int i = 0; i < 4; ++i) c[i] = r[i];
 }
 
+static void buildScanTables(const long double A[4], const long double b[2], double* out);
+
 static void buildBandConstants(const cpq_svf_coeffs& c, double* out /* kEqcStride */)
 {
     std::memset(out, 0, sizeof(double) * kEqcStride);
@@ -605,6 +612,13 @@ static void buildBandConstants(const cpq_svf_coeffs& c, double* out /* kEqcStrid
         out[8] = g;
         out[9] = 2.0 * g;
     }
+    buildScanTables(A, b, out);
+}
+
+// Tables of the blocked scan of s' = A s + b x (cpq_eq.cuh): zero-state weights and the powers of A the warp scan,
+// the lane lookup and the segment link need; long double so that A^1024 is correctly rounded to double.
+static void buildScanTables(const long double A[4], const long double b[2], double* out)
+{
     // w[j] = A^(L-1-j) b
     long double v[2] = { b[0], b[1] };
     for (int j = kEqL - 1; j >= 0; --j)
@@ -640,6 +654,117 @@ static void buildBandConstants(const cpq_svf_coeffs& c, double* out /* kEqcStrid
     }
     // M is now A^(32 L): one warp segment
     for (int i = 0; i < 4; ++i) out[kEqcMw + i] = (double) M[i];
+}
+
+// ---- linear output stages: OutputFilter (OutputFilter.cpp:28-112) and the output DC blocker (UltraHighRateDCBlocker.h:60-90) ----
+struct BiquadC { double b0 = 1.0, b1 = 0.0, b2 = 0.0, a1 = 0.0, a2 = 0.0; };
+static BiquadC makeLPF(double fc, double Q, double fs)   // OutputFilter::makeLPF, :28-48 (RBJ, a0-normalised)
+{
+    BiquadC c;
+    const double nyq = fs * 0.4999;
+    if (fc >= nyq || Q <= 0.0 || fs <= 0.0) return c;
+    const double w0 = 2.0 * 3.14159265358979323846 * fc / fs;
+    const double sn = std::sin(w0), cs = std::cos(w0);
+    const double alpha = sn / (2.0 * Q);
+    const double a0inv = 1.0 / (1.0 + alpha);
+    c.b0 = (1.0 - cs) * 0.5 * a0inv;
+    c.b1 = (1.0 - cs) * a0inv;
+    c.b2 = (1.0 - cs) * 0.5 * a0inv;
+    c.a1 = (-2.0 * cs) * a0inv;
+    c.a2 = (1.0 - alpha) * a0inv;
+    return c;
+}
+static BiquadC makeHPF(double fc, double Q, double fs)   // OutputFilter::makeHPF, :50-70
+{
+    BiquadC c;
+    const double nyq = fs * 0.4999;
+    if (fc <= 0.0 || fc >= nyq || Q <= 0.0 || fs <= 0.0) return c;
+    const double w0 = 2.0 * 3.14159265358979323846 * fc / fs;
+    const double sn = std::sin(w0), cs = std::cos(w0);
+    const double alpha = sn / (2.0 * Q);
+    const double a0inv = 1.0 / (1.0 + alpha);
+    c.b0 = (1.0 + cs) * 0.5 * a0inv;
+    c.b1 = -(1.0 + cs) * a0inv;
+    c.b2 = (1.0 + cs) * 0.5 * a0inv;
+    c.a1 = (-2.0 * cs) * a0inv;
+    c.a2 = (1.0 - alpha) * a0inv;
+    return c;
+}
+// the three cascaded stages OutputFilter::process runs, in order (OutputFilter.cpp:160-166 / :290-296; prepare :80-112)
+static void outputFilterStages(double sr, int convIsLast, int hcMode, int lcMode, int lpMode, BiquadC out[3])
+{
+    const double fcHc = (sr <= 48000.0) ? 19000.0 : 22000.0;
+    const double fcLp = (sr <= 48000.0) ? 19000.0 : 24000.0;
+    if (convIsLast)
+    {
+        out[0] = lcMode == 1 ? makeHPF(15.0, 0.5, sr) : makeHPF(18.0, 0.70711, sr);
+        if (hcMode == 0) { out[1] = makeLPF(fcHc, 0.54120, sr); out[2] = makeLPF(fcHc, 1.30656, sr); }
+        else if (hcMode == 2) { out[1] = makeLPF(fcHc, 0.5, sr); out[2] = BiquadC {}; }
+        else { out[1] = makeLPF(fcHc, 0.70711, sr); out[2] = makeLPF(fcHc, 0.70711, sr); }
+    }
+    else
+    {
+        out[0] = makeHPF(20.0, 0.70711, sr);
+        const double q = lpMode == 0 ? 1.0 : (lpMode == 2 ? 0.5 : 0.70711);
+        out[1] = makeLPF(fcLp, q, sr);
+        out[2] = makeLPF(fcLp, q, sr);
+    }
+}
+static void dcBlockerAlphas(double sr, double cutoffHz, double alpha[2])   // UltraHighRateDCBlocker::init, :60-90
+{
+    alpha[0] = alpha[1] = 1.0e-6;
+    if (!std::isfinite(sr) || sr <= 0.0 || !std::isfinite(cutoffHz) || cutoffHz <= 0.0) return;
+    const double ratios[2] = { 1.0 - 0.1, 1.0 + 0.1 };
+    for (int i = 0; i < 2; ++i)
+    {
+        const double omega = 2.0 * 3.14159265358979323846 * (cutoffHz * ratios[i]) / sr;
+        double a = -std::expm1(-omega);
+        if (!std::isfinite(a) || a <= 0.0 || a >= 1.0) a = 1.0e-6;
+        alpha[i] = a;
+    }
+}
+static void buildBiquadConstants(const BiquadC& c, double* out)
+{
+    std::memset(out, 0, sizeof(double) * kEqcStride);
+    out[0] = c.b0; out[1] = c.b1; out[2] = c.b2; out[3] = c.a1; out[4] = c.a2;
+    out[7] = 3.0;
+    // DF2T: y = b0 x + w1; w1' = b1 x - a1 y + w2; w2' = b2 x - a2 y  ->  s' = A s + b x
+    const long double A[4] = { -(long double) c.a1, 1.0L, -(long double) c.a2, 0.0L };
+    const long double b[2] = { (long double) c.b1 - (long double) c.a1 * c.b0, (long double) c.b2 - (long double) c.a2 * c.b0 };
+    buildScanTables(A, b, out);
+}
+static void buildDcConstants(const double alpha[2], double* out)
+{
+    std::memset(out, 0, sizeof(double) * kEqcStride);
+    out[0] = alpha[0]; out[1] = alpha[1];
+    out[7] = 4.0;
+    // s0' = (1-a0) s0 + a0 x;  x1 = x - s0';  s1' = (1-a1) s1 + a1 x1
+    const long double a0 = alpha[0], a1 = alpha[1];
+    const long double A[4] = { 1.0L - a0, 0.0L, -a1 * (1.0L - a0), 1.0L - a1 };
+    const long double b[2] = { a0, a1 * (1.0L - a0) };
+    buildScanTables(A, b, out);
+}
+
+cpq_status Engine::uploadPost()
+{
+    if (!postDirty) return CPQ_OK;
+    std::vector<double> host((size_t) kEqPostStages * kEqcStride, 0.0);
+    BiquadC st[3];
+    outputFilterStages(cfg.sample_rate, outCfg.convIsLast, outCfg.hc, outCfg.lc, outCfg.lp, st);
+    postIdentity = 0;
+    for (int i = 0; i < 3; ++i)
+    {
+        buildBiquadConstants(st[i], host.data() + (size_t) i * kEqcStride);
+        if (st[i].b0 == 1.0 && st[i].b1 == 0.0 && st[i].b2 == 0.0 && st[i].a1 == 0.0 && st[i].a2 == 0.0) postIdentity |= 1u << i;
+    }
+    double alpha[2];
+    dcBlockerAlphas(cfg.sample_rate, outCfg.dcCutoff, alpha);
+    buildDcConstants(alpha, host.data() + (size_t) 3 * kEqcStride);
+    CPQ_CUDA(postc.ensure(host.size()));
+    CPQ_CUDA(cudaMemcpyAsync(postc.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CPQ_CUDA(cudaStreamSynchronize(stream));
+    postDirty = false;
+    return CPQ_OK;
 }
 
 cpq_status Engine::uploadEq(int64_t nCallbacks)
@@ -742,9 +867,9 @@ cpq_status Engine::launchEq(EqArgs& a)
     a.nRuns = (int) ((a.T + kEqTile - 1) / kEqTile);
     a.chain.ticket = ticketFault.p;
     a.fault = ticketFault.p + 1;
-    if (a.doEq && a.nRuns > 1)
+    if ((a.doEq || a.postMask) && a.nRuns > 1)
     {
-        const size_t n = (size_t) a.nSeq * a.nRuns * CPQ_NUM_BANDS * 2;
+        const size_t n = (size_t) a.nSeq * a.nRuns * kEqStages * 2;
         CPQ_CUDA(chainRec.ensure(n));
         CPQ_CUDA(cudaMemsetAsync(chainRec.p, 0xff, n * sizeof(double), stream));
     }
@@ -752,12 +877,14 @@ cpq_status Engine::launchEq(EqArgs& a)
     static bool attrDone = false;
     if (!attrDone)
     {
-        CPQ_CUDA(cudaFuncSetAttribute(eq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytes));
+        CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytes));
+        CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
         attrDone = true;
     }
     CPQ_CUDA(cudaMemsetAsync(ticketFault.p, 0, sizeof(unsigned), stream));
     const unsigned grid = (unsigned) a.nSeq * (unsigned) a.nRuns;
-    eq_kernel<<<grid, kEqThreads, kEqSmemBytes, stream>>>(a);
+    if (a.postMask || a.finalClamp) eq_kernel<true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
+    else eq_kernel<false><<<grid, kEqThreads, kEqSmemBytes, stream>>>(a);
     ++launches;
     CPQ_CUDA(cudaGetLastError());
     return CPQ_OK;
@@ -770,7 +897,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         setError("process: T must be a positive multiple of block_size <= max_samples; stride even and >= T");
         return CPQ_ERR_INVALID;
     }
-    if ((stages & ~CPQ_STAGE_ALL) || stages == 0)
+    if ((stages & ~CPQ_STAGE_FULL) || stages == 0)
     {
         setError("process: bad stage mask");
         return CPQ_ERR_INVALID;
@@ -802,6 +929,17 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
     {
         cpq_status st = uploadEq(nCallbacks);
         if (st != CPQ_OK) return st;
+    }
+    // linear output stages: OutputFilter between the EQ and the makeup gain, DC blocker inside the epilogue
+    unsigned postMask = 0;
+    if ((stages & CPQ_STAGE_OUTPUT_FILTER) && outCfg.filterEnabled) postMask |= 7u;
+    if (doEpi && outCfg.dcCutoff > 0.0) postMask |= 8u;
+    if (postMask)
+    {
+        cpq_status st = uploadPost();
+        if (st != CPQ_OK) return st;
+        postMask &= ~postIdentity;
+        CPQ_CUDA(postState.ensure((size_t) nSeq * kEqPostStages * 2));
     }
     const bool doDither = doEpi && ditherBits > 0;
     if (doDither && uniformsPerCh != T)
@@ -905,6 +1043,9 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         a.doEpilogue = doEpi ? 1 : 0;
         a.makeup = makeup;
         a.applyHeadroom = (doEpi && ditherBits <= 0) ? 1 : 0;
+        a.postc = postc.p;
+        a.postMask = postMask;
+        a.finalClamp = (doEpi && outCfg.finalClamp && ditherBits <= 0) ? 1 : 0;   // with dither the dither kernel clamps
         a.wetGain = equalPowerSin(1.0) * 1.0;   // CONVOLUTION_HEADROOM_GAIN = 1.0 (ConvolverProcessor.h:209)
     };
     const bool deferredOuter = !doConv && outerPending;
@@ -1044,6 +1185,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         e.bandMask = bandMask.p ? bandMask.p + s0 : nullptr;
         e.setOfSeq = setOfSeq.p ? setOfSeq.p + s0 : nullptr;   // absolute set indices
         e.stateOut = stateOut.p + (size_t) s0 * CPQ_NUM_BANDS * 2;
+        e.postStateOut = postMask ? postState.p + (size_t) s0 * kEqPostStages * 2 : nullptr;
         cpq_status st = launchEq(e);
         if (st != CPQ_OK) return st;
         if (doDither)
@@ -1058,6 +1200,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             d.scale = 1.0 / std::pow(2.0, ditherBits - 1);
             d.invScale = std::pow(2.0, ditherBits - 1);
             d.z = ditherZ.p + (size_t) s0 * 12;
+            d.finalClamp = outCfg.finalClamp;
             dither_kernel<<<(unsigned) ((ns + 31) / 32), 32, 0, stream>>>(d);
             ++launches;
             CPQ_CUDA(cudaGetLastError());
@@ -1270,6 +1413,37 @@ cpq_status cpq_set_epilogue(cpq_handle h, double makeup_gain, int dither_bits)
     h->makeup = makeup_gain;
     h->ditherBits = dither_bits < 0 ? 0 : dither_bits;
     return CPQ_OK;
+}
+
+cpq_status cpq_set_output_filter(cpq_handle h, int enabled, int conv_is_last, int hc_mode, int lc_mode, int lp_mode)
+{
+    if (!h || hc_mode < 0 || hc_mode > 2 || lc_mode < 0 || lc_mode > 1 || lp_mode < 0 || lp_mode > 2) return CPQ_ERR_INVALID;
+    h->outCfg.filterEnabled = enabled ? 1 : 0;
+    h->outCfg.convIsLast = conv_is_last ? 1 : 0;
+    h->outCfg.hc = hc_mode;
+    h->outCfg.lc = lc_mode;
+    h->outCfg.lp = lp_mode;
+    h->postDirty = true;
+    return CPQ_OK;
+}
+
+cpq_status cpq_set_output_stage(cpq_handle h, double dc_cutoff_hz, int hard_clamp)
+{
+    if (!h || !(dc_cutoff_hz >= 0.0) || !std::isfinite(dc_cutoff_hz)) return CPQ_ERR_INVALID;
+    h->outCfg.dcCutoff = dc_cutoff_hz;
+    h->outCfg.finalClamp = hard_clamp ? 1 : 0;
+    h->postDirty = true;
+    return CPQ_OK;
+}
+
+void cpq_output_filter_design(double sample_rate, int conv_is_last, int hc_mode, int lc_mode, int lp_mode, double out[15])
+{
+    cpq::BiquadC st[3];
+    cpq::outputFilterStages(sample_rate, conv_is_last, hc_mode, lc_mode, lp_mode, st);
+    for (int i = 0; i < 3; ++i)
+    {
+        out[5 * i] = st[i].b0; out[5 * i + 1] = st[i].b1; out[5 * i + 2] = st[i].b2; out[5 * i + 3] = st[i].a1; out[5 * i + 4] = st[i].a2;
+    }
 }
 
 cpq_status cpq_set_dither_uniforms(cpq_handle h, const double* uniforms, int64_t samples_per_channel)

@@ -60,6 +60,7 @@ static_assert(kEqL == 16 || kEqL == 32, "samples per thread");
 
 // per (parameter set, band) constants, all double; built by buildBandConstants() in cpq_engine.cu
 constexpr int kEqcCoef = 0;                      // a1,a2,a3,m0,m1,m2, forceExact(!=0), kind (0 literal, 1 TPT peaking, 2 TPT), g, 2g
+                                                 // kind 3 (DF2T biquad): b0,b1,b2,a1,a2 in [0..4]; kind 4 (DC blocker): alpha0, alpha1 in [0..1]
 constexpr int kEqcW = 12;                        // w[L][2]    zero-state weights, c = sum_j w[j] * v0[j]
 constexpr int kEqcMs = kEqcW + 2 * kEqL;         // Ms[5][4]   A^(L*2^d), row-major 2x2
 constexpr int kEqcPlo = kEqcMs + 20;             // Plo[8][4]  A^(L*j)
@@ -68,9 +69,18 @@ constexpr int kEqcMw = kEqcPhi + 16;             // A^(32L)    (one warp segment
 constexpr int kEqcStride = kEqcMw + 4;           // doubles per band, staged in shared memory for all 20 bands
 
 constexpr int kEqSeg = 32 * kEqL;                // 512 samples per warp segment
+// Stages of the scan pipeline: the 20 EQ bands, then the linear output stages of DSPCore::processDouble --
+// OutputFilter's three DF2T biquads (OutputFilter.cpp:199-421) and the two-section output DC blocker
+// (UltraHighRateDCBlocker.h:98-126) -- each a 2-state linear recurrence handled by the same scan machinery.
+constexpr int kEqPostStages = 4;                 // 0..2 OutputFilter biquads, 3 DC blocker
+constexpr int kEqStages = CPQ_NUM_BANDS + kEqPostStages;
+constexpr int kEqStageDc = CPQ_NUM_BANDS + 3;
 // shared memory: segment tiles | band constants | mailboxes st[20][8] (double2) | flags fl[20][8] (int) | ticket
-constexpr int kEqSmemDoubles = kEqCThreads * kEqPad + CPQ_NUM_BANDS * kEqcStride + CPQ_NUM_BANDS * 8 * 2 + CPQ_NUM_BANDS * 8 / 2;
-constexpr size_t kEqSmemBytes = (size_t) kEqSmemDoubles * sizeof(double) + 16;
+// shared memory: segment tiles | EQ band constants | mailboxes st[stage][8] (double2) | flags fl[stage][8] (int) | ticket |
+// output-stage constants (only allocated when such a stage runs)
+constexpr int kEqSmemDoubles = kEqCThreads * kEqPad + CPQ_NUM_BANDS * kEqcStride + kEqStages * 8 * 2 + kEqStages * 8 / 2 + 2;
+constexpr size_t kEqSmemBytes = (size_t) kEqSmemDoubles * sizeof(double);
+constexpr size_t kEqSmemBytesPost = kEqSmemBytes + (size_t) kEqPostStages * kEqcStride * sizeof(double);
 
 struct EqChain
 {
@@ -104,6 +114,11 @@ struct EqArgs
     const int* setOfSeq;    // [nSeq]
     const double* sat;      // [nSets]
     double* stateOut;       // [nSeq][20][2] final states
+    // linear output stages (stage index 20..23); run when postMask != 0, also without the EQ bands
+    const double* postc;    // [kEqPostStages][kEqcStride]
+    unsigned postMask;      // bit i = post stage i enabled
+    double* postStateOut;   // nullable [nSeq][kEqPostStages][2] final states of the output stages
+    int finalClamp;         // scrub (non-finite or |x| >= 1e300 -> 0) + clamp to +-kOutputHeadroom after the headroom multiply
     const double* gainTab;  // nullable [nSets][nCallbacks][2] (start, inc)
     const double* gainConst;// [nSets] settled total gain (used when gainTab == nullptr)
     int64_t nCallbacks;
@@ -293,18 +308,22 @@ __device__ __forceinline__ void eq_pass2(double (&x)[kEqL], double& ic1, double&
 #ifndef CPQ_EQ_MINBLOCKS
 #define CPQ_EQ_MINBLOCKS (CPQ_EQ_L == 16 ? 3 : 2)
 #endif
+// POST = the launch runs output stages / the output clamp; the plain conv -> EQ -> gain launch carries none of that code.
+template <bool POST>
 __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs a)
 {
+    const unsigned postMask = POST ? a.postMask : 0u;
     extern __shared__ __align__(16) double eq_smem[];
     double* tile = eq_smem;                                        // [7 warps][32 lanes][18]
     double* cst = tile + kEqCThreads * kEqPad;                     // this sequence's band constants
-    double2* st = reinterpret_cast<double2*>(cst + CPQ_NUM_BANDS * kEqcStride);   // [20][8] state at the start of segment w (8 = after the tile)
-    int* fl = reinterpret_cast<int*>(st + CPQ_NUM_BANDS * 8);                     // [20][8] mailbox flags
-    unsigned* sTicket = reinterpret_cast<unsigned*>(fl + CPQ_NUM_BANDS * 8);
+    double2* st = reinterpret_cast<double2*>(cst + CPQ_NUM_BANDS * kEqcStride);   // [stage][8] state at the start of segment w
+    int* fl = reinterpret_cast<int*>(st + kEqStages * 8);                         // [stage][8] mailbox flags
+    unsigned* sTicket = reinterpret_cast<unsigned*>(fl + kEqStages * 8);
+    double* cstPost = eq_smem + kEqSmemDoubles;                                   // output-stage constants (present iff postMask)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) *sTicket = atomicAdd(a.chain.ticket, 1u);
-    if (tid < CPQ_NUM_BANDS * 8) fl[tid] = 0;
+    if (tid < kEqStages * 8) fl[tid] = 0;
     __syncthreads();
     const unsigned ticket = *sTicket;
     // run-major ticket order: the predecessor (same sequence, previous tile) always holds a smaller ticket
@@ -314,7 +333,8 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
 
     double* io = a.io + (size_t) seq * a.ioStride;
     const int set = a.doEq ? a.setOfSeq[seq] : 0;
-    const unsigned mask = a.doEq ? a.bandMask[seq] : 0u;
+    // stages this sequence runs: its active EQ bands (bits 0..19) and the enabled output stages (bits 20..23)
+    const unsigned mask = (a.doEq ? a.bandMask[seq] : 0u) | (postMask << CPQ_NUM_BANDS);
     const int64_t t0 = (int64_t) run * kEqTile;
 
     if (a.doEq)
@@ -323,6 +343,9 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
         for (int i = tid; i < CPQ_NUM_BANDS * kEqcStride / 2; i += kEqThreads)
             reinterpret_cast<double2*>(cst)[i] = __ldg(reinterpret_cast<const double2*>(src) + i);
     }
+    if (postMask)
+        for (int i = tid; i < kEqPostStages * kEqcStride / 2; i += kEqThreads)
+            reinterpret_cast<double2*>(cstPost)[i] = __ldg(reinterpret_cast<const double2*>(a.postc) + i);
     __syncthreads();   // constants + cleared flags visible; the only CTA-wide barrier besides the ticket
 
     // ---- tile-to-tile chain: records (seq, tile, band) in global memory, written by the last warp of a tile and read by
@@ -330,15 +353,21 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
     // trip is never on the critical path; the predecessor tile started earlier (ticket order) and is normally far ahead.
     const bool lastTile = run + 1 >= a.nRuns;
     const bool fullLast = lastTile && (a.T - t0) == kEqTile;
-    const double2* recIn = (a.doEq && run > 0) ? a.chain.rec + (size_t) ((size_t) seq * a.nRuns + (run - 1)) * CPQ_NUM_BANDS : nullptr;
-    double2* recOut = (a.doEq && !lastTile) ? a.chain.rec + (size_t) ((size_t) seq * a.nRuns + run) * CPQ_NUM_BANDS : nullptr;
-    auto nextBand = [&](int b) { ++b; while (b < CPQ_NUM_BANDS && !((mask >> b) & 1u)) ++b; return b; };
+    const double2* recIn = (mask && run > 0) ? a.chain.rec + (size_t) ((size_t) seq * a.nRuns + (run - 1)) * kEqStages : nullptr;
+    double2* recOut = (mask && !lastTile) ? a.chain.rec + (size_t) ((size_t) seq * a.nRuns + run) * kEqStages : nullptr;
+    auto nextBand = [&](int b) { ++b; while (b < kEqStages && !((mask >> b) & 1u)) ++b; return b; };
+    // final state of stage b (EQ bands -> stateOut, output stages -> postStateOut)
+    auto storeFinal = [&](int b, double s1, double s2) {
+        double* dst = b < CPQ_NUM_BANDS ? (a.stateOut ? a.stateOut + ((size_t) seq * CPQ_NUM_BANDS + b) * 2 : nullptr)
+                                        : (a.postStateOut ? a.postStateOut + ((size_t) seq * kEqPostStages + (b - CPQ_NUM_BANDS)) * 2 : nullptr);
+        if (dst) { dst[0] = s1; dst[1] = s2; }
+    };
     double2 pre = make_double2(0.0, 0.0);   // warp 0: prefetched inbound record of band preBand
     int preBand = -1;
     if (warp == 0 && recIn)
     {
         preBand = nextBand(-1);
-        if (preBand < CPQ_NUM_BANDS) pre = ld_volatile_f64x2(recIn + preBand);
+        if (preBand < kEqStages) pre = ld_volatile_f64x2(recIn + preBand);
     }
 
     // ================= compute warps: one 512-sample segment each =================
@@ -515,13 +544,18 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
     unsigned hiIn = 0;   // max of |x|'s high word over the raw input
     loadBlock(hiIn);
 
-    if (a.doEq)
+    // gains the reference applies between the EQ bands and the output stages are applied in registers when such a stage
+    // runs: total gain (Processing.cpp:1262-1274) before OutputFilter / DC blocker, makeup (DSPCoreDouble.cpp:465-469)
+    // before the DC blocker; the store stage then skips them
+    const bool gainInReg = a.doEq && (postMask != 0u);
+    const bool makeupInReg = a.doEpilogue && ((postMask >> 3) & 1u);
+    if (mask)
     {
         const double alpha = fma(-8.0, sat, 9.0) / 9.0, gamma = 8.0 * sat / 3.0;
         const unsigned thrHi = sat > 0.0 ? 0x40374000u : 0x40590000u;   // high words of 4.5^2 + 3 / of 100.0
         // the thread whose block starts at sample T holds the sequence's final state when the last tile is partial
         const int64_t remT = a.T - t0;
-        const bool ownsFinal = a.stateOut && remT < kEqTile && remT >= 0 && tid == (int) (remT / kEqL);
+        const bool ownsFinal = remT < kEqTile && remT >= 0 && tid == (int) (remT / kEqL);
 
         // Everything of one band up to the start state of this thread's block.  `link`: take part in the chain (wait for
         // the mailbox, post the successor's); a replayed band finds its mailbox already filled and posts nothing.
@@ -574,7 +608,7 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                             sv = ld_volatile_f64x2(recIn + b);
                         }
                         preBand = nextBand(b);
-                        if (preBand < CPQ_NUM_BANDS) pre = ld_volatile_f64x2(recIn + preBand);
+                        if (preBand < kEqStages) pre = ld_volatile_f64x2(recIn + preBand);
                     }
                     if (lane == 0) st[b * 8] = sv;   // kept for an exact-mode replay of this band
                     __syncwarp();
@@ -604,27 +638,78 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                 }
                 else if (recOut)
                     st_volatile_f64x2(recOut + b, make_double2(rec_clean(o1), rec_clean(o2)));   // state after the tile
-                else if (fullLast && a.stateOut)
-                {
-                    a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2] = o1;
-                    a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2 + 1] = o2;
-                }
+                else if (fullLast)
+                    storeFinal(b, o1, o2);
             }
             // ---- state at the start of this thread's block: A^(L lane) s_in + e ----
             matvec2(bc + kEqcPlo + 4 * (lane & 7), p1, p2, 0.0, 0.0);    // A^(L (lane & 7))
             matvec2(bc + kEqcPhi + 4 * (lane >> 3), p1, p2, e1, e2);     // A^(8L (lane >> 3)) ... + e
             ic1 = p1;
             ic2 = p2;
-            if (ownsFinal)
+            if (ownsFinal) storeFinal(b, ic1, ic2);
+        };
+
+        auto preStage = [&](int b, bool& gainDone, bool& makeupDone) {
+            if (b >= CPQ_NUM_BANDS && gainInReg && !gainDone)
             {
-                a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2] = ic1;
-                a.stateOut[((size_t) seq * CPQ_NUM_BANDS + b) * 2 + 1] = ic2;
+                gainDone = true;
+                if (a.gainTab)
+                {
+                    const int64_t tb = w0 + (int64_t) lane * kEqL;   // a thread's block never straddles a callback (block >= 64)
+                    const double2 g = __ldg(reinterpret_cast<const double2*>(a.gainTab) + (size_t) set * a.nCallbacks + (tb >> a.blockLog2));
+                    const int off0 = (int) tb & bmask;
+#pragma unroll
+                    for (int j = 0; j < kEqL; ++j) x[j] *= fma((double) (off0 + j), g.y, g.x);
+                }
+                else
+                {
+                    const double gc = __ldg(a.gainConst + set);
+#pragma unroll
+                    for (int j = 0; j < kEqL; ++j) x[j] *= gc;
+                }
+            }
+            if (b == kEqStageDc && makeupInReg && !makeupDone)
+            {
+                makeupDone = true;
+#pragma unroll
+                for (int j = 0; j < kEqL; ++j) x[j] *= a.makeup;
+            }
+        };
+        // pass 2 of the linear output stages (no clamps or scrubs in the reference: one code path for fast and exact mode)
+        auto postPass2 = [&](const double* __restrict__ bc, double& s1, double& s2) {
+            if ((int) bc[7] == 3)
+            {
+                // DF2T biquad with the reference's FMA association (OutputFilter.cpp:118-137)
+                const double b0 = bc[0], b1 = bc[1], b2 = bc[2], a1 = bc[3], a2 = bc[4];
+#pragma unroll
+                for (int j = 0; j < kEqL; ++j)
+                {
+                    const double xi = x[j];
+                    const double y = fma(b0, xi, s1);
+                    s1 = fma(b1, xi, fma(-a1, y, s2));
+                    s2 = fma(-a2, y, b2 * xi);
+                    x[j] = y;
+                }
+            }
+            else
+            {
+                // two one-pole sections (UltraHighRateDCBlocker.h:98-126)
+                const double al0 = bc[0], al1 = bc[1];
+#pragma unroll
+                for (int j = 0; j < kEqL; ++j)
+                {
+                    double v = x[j];
+                    s1 = fma(al0, v - s1, s1);
+                    v -= s1;
+                    s2 = fma(al1, v - s2, s2);
+                    x[j] = v - s2;
+                }
             }
         };
 
         // ---- fast mode: bands in order until some lane leaves the regime where the reference's clamps are identities ----
-        bool exactMode = __any_sync(0xffffffffu, hiIn >= 0x41cdcd65u);   // |x| >= 1e9 (or NaN/Inf) in the raw input
-        int linked = -1;                                                 // last band whose link this warp has served
+        bool exactMode = a.doEq && __any_sync(0xffffffffu, hiIn >= 0x41cdcd65u);   // |x| >= 1e9 (or NaN/Inf) in the raw input
+        int linked = -1;                                                            // last band whose link this warp has served
         if (!exactMode)
         {
             for (int b = 0; b < CPQ_NUM_BANDS; ++b)
@@ -673,19 +758,46 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                 if (eq_pass2_exact(x, ic1, ic2, bc, sat)) atomicExch(a.fault, 1u);
             }
         }
+        // ---- linear output stages (kept out of the band loop so that the hot loop's code is not disturbed) ----
+        if (postMask)
+        {
+            bool gainDone = false, makeupDone = false;
+            for (int b = CPQ_NUM_BANDS; b < kEqStages; ++b)
+            {
+                if (!((mask >> b) & 1u)) continue;
+                const double* __restrict__ bc = cstPost + (b - CPQ_NUM_BANDS) * kEqcStride;
+                double ic1, ic2;
+                preStage(b, gainDone, makeupDone);
+                bandStart(b, bc, true, ic1, ic2);
+                postPass2(bc, ic1, ic2);
+            }
+        }
     }
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < kEqL / 2; ++j) reinterpret_cast<double2*>(myStash)[j] = make_double2(x[2 * j], x[2 * j + 1]);
     __syncwarp();
 
-    // ---- store: total gain ramp, makeup, headroom (three separate roundings, as the reference applies them) ----
+    // ---- store: total gain ramp, makeup, headroom (three separate roundings, as the reference applies them), then the
+    // optional output scrub + hard clamp of processOutputDouble (DSPCoreDouble.cpp:665-691, 712-737) ----
     {
         double* op = io + w0;
-        const double gconst = (a.doEq && !a.gainTab) ? __ldg(a.gainConst + set) : 1.0;
-        const double mk = a.doEpilogue ? a.makeup : 1.0;
-        const double hr = (a.doEpilogue && a.applyHeadroom) ? 0.8912509381337456 : 1.0;
-        if (a.doEq && a.gainTab)
+        const bool mulG = a.doEq && !gainInReg, mulM = a.doEpilogue && !makeupInReg, mulH = a.doEpilogue && a.applyHeadroom;
+        const bool clampOut = POST && a.doEpilogue && a.finalClamp;
+        const double gconst = (mulG && !a.gainTab) ? __ldg(a.gainConst + set) : 1.0;
+        const double mk = a.makeup;
+        constexpr double hr = 0.8912509381337456;
+        auto finish = [&](double v) {
+            if (mulM) v *= mk;
+            if (mulH) v *= hr;
+            if (clampOut)
+            {
+                if (!(fabs(v) < 1.0e300)) v = 0.0;
+                v = fmin(fmax(v, -hr), hr);
+            }
+            return v;
+        };
+        if (mulG && a.gainTab)
         {
             for (int i = lane; i < nValid; i += 32)
             {
@@ -695,34 +807,27 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                 const int off = (int) t & bmask;
                 const double2 g = __ldg(reinterpret_cast<const double2*>(a.gainTab) + (size_t) set * a.nCallbacks + c);
                 v *= fma((double) off, g.y, g.x);
-                if (a.doEpilogue)
+                op[i] = finish(v);
+            }
+        }
+        else if ((nValid & 1) == 0 && (reinterpret_cast<uintptr_t>(op) & 15) == 0)
+        {
+#pragma unroll
+            for (int k = 0; k < kEqL / 2; ++k)
+            {
+                const int i = 2 * (lane + 32 * k);
+                if (i < nValid)
                 {
-                    v *= mk;
-                    if (a.applyHeadroom) v *= hr;
+                    double2 v = *reinterpret_cast<const double2*>(wtile + eq_sidx(i));
+                    if (mulG) { v.x *= gconst; v.y *= gconst; }
+                    v.x = finish(v.x);
+                    v.y = finish(v.y);
+                    *reinterpret_cast<double2*>(op + i) = v;
                 }
-                op[i] = v;
             }
         }
         else
         {
-            const bool mulG = a.doEq != 0, mulM = a.doEpilogue != 0, mulH = a.doEpilogue && a.applyHeadroom;
-            if ((nValid & 1) == 0 && (reinterpret_cast<uintptr_t>(op) & 15) == 0)
-            {
-#pragma unroll
-                for (int k = 0; k < kEqL / 2; ++k)
-                {
-                    const int i = 2 * (lane + 32 * k);
-                    if (i < nValid)
-                    {
-                        double2 v = *reinterpret_cast<const double2*>(wtile + eq_sidx(i));
-                        if (mulG) { v.x *= gconst; v.y *= gconst; }
-                        if (mulM) { v.x *= mk; v.y *= mk; }
-                        if (mulH) { v.x *= hr; v.y *= hr; }
-                        *reinterpret_cast<double2*>(op + i) = v;
-                    }
-                }
-            }
-            else
 #pragma unroll
             for (int k = 0; k < kEqL; ++k)
             {
@@ -731,9 +836,7 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                 {
                     double v = wtile[eq_sidx(i)];
                     if (mulG) v *= gconst;
-                    if (mulM) v *= mk;
-                    if (mulH) v *= hr;
-                    op[i] = v;
+                    op[i] = finish(v);
                 }
             }
         }
@@ -753,6 +856,7 @@ struct DitherArgs
     double coeff[12];
     double scale, invScale;
     double* z;                // [nSeq][12] error history (carried)
+    int finalClamp;           // scrub + clamp to +-kOutputHeadroom after the quantiser (DSPCoreDouble.cpp:665-691, 712-737)
 };
 
 __global__ void dither_kernel(DitherArgs a)
@@ -778,7 +882,13 @@ __global__ void dither_kernel(DitherArgs a)
 #pragma unroll
         for (int t = 11; t > 0; --t) z[t] = z[t - 1];
         z[0] = err;
-        d[i] = q;
+        double o = q;
+        if (a.finalClamp)
+        {
+            if (!(fabs(o) < 1.0e300)) o = 0.0;
+            o = fmin(fmax(o, -0.8912509381337456), 0.8912509381337456);
+        }
+        d[i] = o;
     }
 #pragma unroll
     for (int i = 0; i < 12; ++i) a.z[(size_t) seq * 12 + i] = z[i];

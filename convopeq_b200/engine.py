@@ -142,6 +142,14 @@ class ConvoPeqEngine:
         return self.lib.cpq_total_partitions(self.h)
 
     # ---- process ----
+    def set_output_filter(self, enabled: bool = True, conv_is_last: bool = False, hc_mode: int = 1, lc_mode: int = 0, lp_mode: int = 1):
+        """OutputFilter::process(block, convIsLast, hcMode, lcMode, lpMode) (OutputFilter.h:108-131); runs with STAGE_OUTPUT_FILTER."""
+        self._check(self.lib.cpq_set_output_filter(self.h, int(enabled), int(conv_is_last), hc_mode, lc_mode, lp_mode))
+
+    def set_output_stage(self, dc_cutoff_hz: float = 3.0, hard_clamp: bool = True):
+        """Output DC blocker (AudioEngine.h:643-651 uses 3 Hz) and the scrub + +-kOutputHeadroom clamp of processOutputDouble."""
+        self._check(self.lib.cpq_set_output_stage(self.h, dc_cutoff_hz, int(hard_clamp)))
+
     def process(self, x: np.ndarray, stages: int = capi.STAGE_ALL) -> np.ndarray:
         """In place on a host array [n_seq, T] (rows = stream*n_channels + ch). H2D/D2H inside."""
         assert x.dtype == np.float64 and x.ndim == 2 and x.shape[0] == self.n_seq and x.flags["C_CONTIGUOUS"]

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define CPQ_ABI_VERSION 1
+#define CPQ_ABI_VERSION 2
 #define CPQ_NUM_BANDS 20        /* EQProcessor::NUM_BANDS, eqprocessor/EQProcessor.h:153 */
 #define CPQ_MAX_LAYERS 3        /* MKLNonUniformConvolver::kNumLayers, MKLNonUniformConvolver.h:391 */
 #define CPQ_NS_ORDER 12         /* PsychoacousticDither::NS_ORDER, PsychoacousticDither.h:60 */
@@ -75,7 +75,9 @@ enum
     CPQ_STAGE_CONV = 1u,      /* convolverRt().process */
     CPQ_STAGE_EQ = 2u,        /* eqRt().process(block, params, cache) */
     CPQ_STAGE_EPILOGUE = 4u,  /* makeup gain (:465-469) + processOutputDouble headroom / dither (:581,:644-663) */
-    CPQ_STAGE_ALL = 7u
+    CPQ_STAGE_ALL = 7u,       /* the north-star path: conv -> EQ -> gain / dither */
+    CPQ_STAGE_OUTPUT_FILTER = 8u, /* outputFilter.process between the EQ and the makeup gain (:460-462), see cpq_set_output_filter */
+    CPQ_STAGE_FULL = 15u
 };
 
 typedef struct cpq_config
@@ -161,6 +163,20 @@ cpq_status cpq_schedule_total_gain(cpq_handle h, int stream, int64_t at_callback
  * reference's MKL VSL ring. */
 cpq_status cpq_set_epilogue(cpq_handle h, double makeup_gain, int dither_bits);
 cpq_status cpq_set_dither_uniforms(cpq_handle h, const double* uniforms, int64_t samples_per_channel);
+
+/* convo::OutputFilter::prepare(sr) + process(block, convIsLast, hcMode, lcMode, lpMode) (OutputFilter.h:108-131,
+ * OutputFilter.cpp:72-112,139-421): three cascaded DF2T biquads between the EQ and the makeup gain
+ * (AudioEngine.Processing.DSPCoreDouble.cpp:452-463).  conv_is_last: low cut (lc_mode) + high cut (hc_mode, two
+ * stages); otherwise 20 Hz high-pass + low-pass (lp_mode, two stages).  Runs when CPQ_STAGE_OUTPUT_FILTER is requested. */
+cpq_status cpq_set_output_filter(cpq_handle h, int enabled, int conv_is_last, int hc_mode, int lc_mode, int lp_mode);
+/* The rest of processOutputDouble around the headroom / dither step, inside CPQ_STAGE_EPILOGUE:
+ * dc_cutoff_hz > 0: the output UltraHighRateDCBlocker pair (UltraHighRateDCBlocker.h:60-126; the engine uses 3.0 Hz,
+ * AudioEngine.h:643-651) after the makeup gain; hard_clamp: the 1e300 / non-finite scrub and the
+ * +-kOutputHeadroom clamp (DSPCoreDouble.cpp:665-691, 712-737).  SimplePeakLimiter (:700-710) sits between the two and is
+ * the identity while |y| <= 0.7870 (threshold - knee/2); it is not part of this path. */
+cpq_status cpq_set_output_stage(cpq_handle h, double dc_cutoff_hz, int hard_clamp);
+/* Host-only: the three stages' normalised coefficients {b0,b1,b2,a1,a2} x 3 as OutputFilter::prepare computes them. */
+void cpq_output_filter_design(double sample_rate, int conv_is_last, int hc_mode, int lc_mode, int lp_mode, double out[15]);
 
 /* EQProcessor::calcSVFCoeffs (eqprocessor/EQProcessor.Coefficients.cpp:101-130,431-618), host-side:
  * float parameters clamped then promoted to double exactly like the reference.

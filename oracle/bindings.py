@@ -146,6 +146,26 @@ class _Base:
         return {"num_layers": n, "gains": [g[i] for i in range(3)],
                 "layers": [dict(zip(keys, [lay[l * 8 + i] for i in range(8)])) for l in range(n)]}
 
+    # ---- output stages ------------------------------------------------------------------------
+    def output_design(self, sr: float, conv_is_last: bool, hc: int = 1, lc: int = 0, lp: int = 1) -> np.ndarray:
+        """The three OutputFilter stages' {b0,b1,b2,a1,a2}, in processing order."""
+        out = np.zeros(15)
+        self._f("out_design")(sr, int(conv_is_last), hc, lc, lp, _p(out))
+        return out.reshape(3, 5)
+
+    def output_run(self, x: np.ndarray, sr: float, block: int, use_filter: bool = True, conv_is_last: bool = False, hc: int = 1,
+                   lc: int = 0, lp: int = 1, makeup: float = 1.0, dc_cutoff: float = 3.0, headroom: bool = True,
+                   clamp: bool = True) -> np.ndarray:
+        """[OutputFilter] -> makeup -> [DC blocker] -> [headroom] -> [scrub + clamp] per callback on x[channels][T]."""
+        y = np.ascontiguousarray(x, dtype=np.float64).copy()
+        h = self._f("out_create")(sr, dc_cutoff if dc_cutoff > 0 else 1.0)
+        try:
+            self._f("out_process")(h, _p(y[0]), _p(y[1]) if y.shape[0] > 1 else None, y.shape[1], block, int(use_filter),
+                                   int(conv_is_last), hc, lc, lp, makeup, int(dc_cutoff > 0), int(headroom), int(clamp))
+        finally:
+            self._f("out_destroy")(h)
+        return y
+
     # ---- EQ ----------------------------------------------------------------------------------
     def eq_design(self, type_: int, f: float, gain_db: float, q: float, sr: float) -> np.ndarray:
         out = np.zeros(6)
@@ -169,6 +189,15 @@ def _common_sigs(lib, pre, nuc_set_impulse_extra):
     f("chain_process").restype = None
     f("eq_destroy").argtypes = [vp]
     f("eq_destroy").restype = None
+    f("out_create").restype = vp
+    f("out_create").argtypes = [C.c_double, C.c_double]
+    f("out_destroy").argtypes = [vp]
+    f("out_destroy").restype = None
+    f("out_design").argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, _dp]
+    f("out_design").restype = None
+    f("out_process").argtypes = [vp, _dp, _dp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                 C.c_int, C.c_int, C.c_int]
+    f("out_process").restype = None
 
 
 class Oracle(_Base):

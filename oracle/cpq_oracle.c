@@ -1038,4 +1038,158 @@ void cpqo_chain_process(cpqo_nuc* nl, cpqo_nuc* nr, cpqo_eq* eq, double* L, doub
     }
 }
 
-int cpqo_abi_version(void) { return 1; }
+/* ------------------------------------------------------------------------------------------------
+ * Output stages of DSPCore::processDouble around the path: OutputFilter (src/OutputFilter.cpp), makeup gain
+ * (AudioEngine.Processing.DSPCoreDouble.cpp:465-469), output DC blocker (src/UltraHighRateDCBlocker.h), headroom,
+ * scrub and hard clamp (DSPCoreDouble.cpp:655-691, 712-737).  SimplePeakLimiter (:700-710) is the identity for
+ * |y| <= 0.787 and is not restated.
+ * ------------------------------------------------------------------------------------------------ */
+static void cpqo_biquad_identity(double* c) { c[0] = 1.0; c[1] = c[2] = c[3] = c[4] = 0.0; }
+
+/* OutputFilter::makeLPF / makeHPF, OutputFilter.cpp:28-70: RBJ cookbook, normalised by a0; {b0,b1,b2,a1,a2} */
+static void cpqo_biquad_lpf(double fc, double q, double fs, double* c)
+{
+    const double nyq = fs * 0.4999;
+    if (fc >= nyq || q <= 0.0 || fs <= 0.0) { cpqo_biquad_identity(c); return; }
+    const double w0 = 2.0 * 3.14159265358979323846 * fc / fs;
+    const double sn = sin(w0), cs = cos(w0);
+    const double alpha = sn / (2.0 * q);
+    const double a0inv = 1.0 / (1.0 + alpha);
+    c[0] = (1.0 - cs) * 0.5 * a0inv;
+    c[1] = (1.0 - cs) * a0inv;
+    c[2] = (1.0 - cs) * 0.5 * a0inv;
+    c[3] = (-2.0 * cs) * a0inv;
+    c[4] = (1.0 - alpha) * a0inv;
+}
+static void cpqo_biquad_hpf(double fc, double q, double fs, double* c)
+{
+    const double nyq = fs * 0.4999;
+    if (fc <= 0.0 || fc >= nyq || q <= 0.0 || fs <= 0.0) { cpqo_biquad_identity(c); return; }
+    const double w0 = 2.0 * 3.14159265358979323846 * fc / fs;
+    const double sn = sin(w0), cs = cos(w0);
+    const double alpha = sn / (2.0 * q);
+    const double a0inv = 1.0 / (1.0 + alpha);
+    c[0] = (1.0 + cs) * 0.5 * a0inv;
+    c[1] = -(1.0 + cs) * a0inv;
+    c[2] = (1.0 + cs) * 0.5 * a0inv;
+    c[3] = (-2.0 * cs) * a0inv;
+    c[4] = (1.0 - alpha) * a0inv;
+}
+
+/* The three stages OutputFilter::process cascades, in processing order (prepare :72-112, process :160-166, :290-296). */
+void cpqo_out_design(double sr, int conv_is_last, int hc, int lc, int lp, double* out15)
+{
+    const double fc_hc = (sr <= 48000.0) ? 19000.0 : 22000.0;
+    const double fc_lp = (sr <= 48000.0) ? 19000.0 : 24000.0;
+    if (conv_is_last)
+    {
+        if (lc == 1) cpqo_biquad_hpf(15.0, 0.5, sr, out15);
+        else cpqo_biquad_hpf(18.0, 0.70711, sr, out15);
+        if (hc == 0) { cpqo_biquad_lpf(fc_hc, 0.54120, sr, out15 + 5); cpqo_biquad_lpf(fc_hc, 1.30656, sr, out15 + 10); }
+        else if (hc == 2) { cpqo_biquad_lpf(fc_hc, 0.5, sr, out15 + 5); cpqo_biquad_identity(out15 + 10); }
+        else { cpqo_biquad_lpf(fc_hc, 0.70711, sr, out15 + 5); cpqo_biquad_lpf(fc_hc, 0.70711, sr, out15 + 10); }
+    }
+    else
+    {
+        const double q = lp == 0 ? 1.0 : (lp == 2 ? 0.5 : 0.70711);
+        cpqo_biquad_hpf(20.0, 0.70711, sr, out15);
+        cpqo_biquad_lpf(fc_lp, q, sr, out15 + 5);
+        cpqo_biquad_lpf(fc_lp, q, sr, out15 + 10);
+    }
+}
+
+typedef struct cpqo_out
+{
+    double sr;
+    double w[2][3][2];   /* [ch][stage][w1,w2] */
+    double dc_alpha[2];
+    double dc_state[2][2];
+} cpqo_out;
+
+cpqo_out* cpqo_out_create(double sr, double dc_cutoff)
+{
+    cpqo_out* o = (cpqo_out*) calloc(1, sizeof(cpqo_out));
+    o->sr = sr;
+    /* UltraHighRateDCBlocker::init, :60-90 */
+    o->dc_alpha[0] = o->dc_alpha[1] = 1.0e-6;
+    if (isfinite(sr) && sr > 0.0 && isfinite(dc_cutoff) && dc_cutoff > 0.0)
+    {
+        const double ratios[2] = { 1.0 - 0.1, 1.0 + 0.1 };
+        for (int i = 0; i < 2; ++i)
+        {
+            const double omega = 2.0 * 3.14159265358979323846 * (dc_cutoff * ratios[i]) / sr;
+            double a = -expm1(-omega);
+            if (!isfinite(a) || a <= 0.0 || a >= 1.0) a = 1.0e-6;
+            o->dc_alpha[i] = a;
+        }
+    }
+    return o;
+}
+void cpqo_out_destroy(cpqo_out* o) { free(o); }
+
+/* One DF2T step with the association of biquadStep128_FMA (OutputFilter.cpp:118-137), incl. its |w| < 1e-20 flush. */
+static double cpqo_biquad_step(double x, const double* c, double* w)
+{
+    const double y = fma(c[0], x, w[0]);
+    double n1 = fma(c[1], x, fma(-c[3], y, w[1]));
+    double n2 = fma(-c[4], y, c[2] * x);
+    if (fabs(n1) < 1.0e-20) n1 = 0.0;
+    if (fabs(n2) < 1.0e-20) n2 = 0.0;
+    w[0] = n1;
+    w[1] = n2;
+    return y;
+}
+
+/* Per callback: [OutputFilter] -> makeup -> [DC blocker] -> [headroom] -> [scrub + clamp]. */
+void cpqo_out_process(cpqo_out* o, double* L, double* R, long total, int block, int use_filter, int conv_is_last, int hc, int lc,
+                      int lp, double makeup, int use_dc, int headroom, int clamp)
+{
+    const double hr = 0.8912509381337456;
+    double c[15];
+    cpqo_out_design(o->sr, conv_is_last, hc, lc, lp, c);
+    for (long pos = 0; pos < total; pos += block)
+    {
+        const int n = (int) ((total - pos) < block ? (total - pos) : block);
+        double* ch[2] = { L + pos, R ? R + pos : NULL };
+        for (int k = 0; k < (R ? 2 : 1); ++k)
+        {
+            double* d = ch[k];
+            if (use_filter)
+                for (int i = 0; i < n; ++i)
+                {
+                    double v = d[i];
+                    for (int s = 0; s < 3; ++s) v = cpqo_biquad_step(v, c + 5 * s, o->w[k][s]);
+                    d[i] = v;
+                }
+            for (int i = 0; i < n; ++i) d[i] *= makeup;
+            if (use_dc)
+            {
+                /* UltraHighRateDCBlocker::process, :98-126 */
+                double s0 = o->dc_state[k][0], s1 = o->dc_state[k][1];
+                for (int i = 0; i < n; ++i)
+                {
+                    double x = d[i];
+                    s0 = fma(o->dc_alpha[0], x - s0, s0);
+                    x = x - s0;
+                    s1 = fma(o->dc_alpha[1], x - s1, s1);
+                    x = x - s1;
+                    d[i] = x;
+                }
+                o->dc_state[k][0] = (isfinite(s0) && fabs(s0) < 1.0e15) ? s0 : 0.0;
+                o->dc_state[k][1] = (isfinite(s1) && fabs(s1) < 1.0e15) ? s1 : 0.0;
+            }
+            if (headroom)
+                for (int i = 0; i < n; ++i) d[i] *= hr;
+            if (clamp)
+                for (int i = 0; i < n; ++i)
+                {
+                    double v = d[i];
+                    if (!(isfinite(v) && fabs(v) < 1.0e300)) v = 0.0;
+                    v = v < -hr ? -hr : (v > hr ? hr : v);
+                    d[i] = v;
+                }
+        }
+    }
+}
+
+int cpqo_abi_version(void) { return 2; }

@@ -35,8 +35,10 @@
 #define protected public
 #include "MKLNonUniformConvolver.h"
 #include "eqprocessor/EQProcessor.h"
+#include "OutputFilter.h"
 #undef private
 #undef protected
+#include "UltraHighRateDCBlocker.h"
 
 // ---- members normally provided by EQProcessor.Core.cpp -----------------------------------
 EQProcessor::EQProcessor()
@@ -276,5 +278,70 @@ void cpqref_chain_process(void* nucL, void* nucR, void* eq, double* L, double* R
     }
 }
 
-int cpqref_abi_version(void) { return 1; }
+// ---- output stages: the reference's own OutputFilter (src/OutputFilter.cpp) and UltraHighRateDCBlocker, driven per
+// callback in the order of DSPCore::processDouble (DSPCoreDouble.cpp:452-469) and processOutputDouble (:600-602,
+// 655-737, SimplePeakLimiter left out); the headroom multiply, scrub and clamp loops are three-liners restated here
+// because AudioEngine.Processing.DSPCoreDouble.cpp itself needs the whole JUCE application to compile.
+struct RefOut
+{
+    convo::OutputFilter filt;
+    convo::UltraHighRateDCBlocker dcL, dcR;
+};
+void* cpqref_out_create(double sr, double dc_cutoff)
+{
+    auto* o = new RefOut;
+    o->filt.prepare(sr);
+    o->dcL.init(sr, dc_cutoff);
+    o->dcR.init(sr, dc_cutoff);
+    return o;
+}
+void cpqref_out_destroy(void* h) { delete static_cast<RefOut*>(h); }
+void cpqref_out_design(double sr, int conv_is_last, int hc, int lc, int lp, double* out15)
+{
+    convo::OutputFilter f;
+    f.prepare(sr);
+    const convo::BiquadCoeff* st[3];
+    if (conv_is_last) { st[0] = &f.lcCoeff[lc]; st[1] = &f.hcCoeff[hc][0]; st[2] = &f.hcCoeff[hc][1]; }
+    else { st[0] = &f.hpfCoeff; st[1] = &f.lpCoeff[lp][0]; st[2] = &f.lpCoeff[lp][1]; }
+    for (int i = 0; i < 3; ++i)
+    {
+        out15[5 * i] = st[i]->b0; out15[5 * i + 1] = st[i]->b1; out15[5 * i + 2] = st[i]->b2;
+        out15[5 * i + 3] = st[i]->a1; out15[5 * i + 4] = st[i]->a2;
+    }
+}
+void cpqref_out_process(void* h, double* L, double* R, long total, int block, int use_filter, int conv_is_last, int hc, int lc,
+                        int lp, double makeup, int use_dc, int headroom, int clamp)
+{
+    auto* o = static_cast<RefOut*>(h);
+    juce::ScopedNoDenormals nd;
+    constexpr double kOutputHeadroom = 0.8912509381337456;
+    for (long pos = 0; pos < total; pos += block)
+    {
+        const int n = (int) std::min<long>(block, total - pos);
+        double* ch[2] = { L + pos, R ? R + pos : nullptr };
+        const int nch = R ? 2 : 1;
+        if (use_filter)
+        {
+            juce::dsp::AudioBlock<double> blk(ch, (size_t) nch, (size_t) n);
+            o->filt.process(blk, conv_is_last != 0, static_cast<convo::HCMode>(hc), static_cast<convo::LCMode>(lc), static_cast<convo::HCMode>(lp));
+        }
+        for (int c = 0; c < nch; ++c)
+            for (int i = 0; i < n; ++i) ch[c][i] *= makeup;
+        if (use_dc) o->dcL.processStereo(ch[0], ch[1], n, o->dcR);
+        for (int c = 0; c < nch; ++c)
+        {
+            if (headroom)
+                for (int i = 0; i < n; ++i) ch[c][i] *= kOutputHeadroom;
+            if (clamp)
+                for (int i = 0; i < n; ++i)
+                {
+                    double v = ch[c][i];
+                    if (!(std::isfinite(v) && std::fabs(v) < 1.0e300)) v = 0.0;
+                    ch[c][i] = std::min(std::max(v, -kOutputHeadroom), kOutputHeadroom);
+                }
+        }
+    }
+}
+
+int cpqref_abi_version(void) { return 2; }
 }

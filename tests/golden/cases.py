@@ -35,6 +35,22 @@ CHAIN_CASES = {
 }
 
 
+# output stages (OutputFilter -> makeup -> DC blocker -> headroom -> scrub + clamp) on their own, and behind conv -> EQ
+OUTPUT_CASES = {
+    "eq_last_natural": dict(sr=48000.0, block=512, T=16384, kw=dict(conv_is_last=False, lp=1, makeup=1.2, dc_cutoff=3.0), amp=3.0, seed=21),
+    "conv_last_sharp_96k": dict(sr=96000.0, block=256, T=16384, kw=dict(conv_is_last=True, hc=0, lc=1, makeup=0.8, dc_cutoff=3.0), amp=1.0, seed=22),
+    "conv_last_soft_no_dc": dict(sr=48000.0, block=512, T=8192, kw=dict(conv_is_last=True, hc=2, lc=0, dc_cutoff=0.0, clamp=False), amp=1.0, seed=23),
+}
+FULL_CHAIN_CASES = {
+    "cfg4_full_chain": dict(sr=48000.0, block=512, T=16384, ir_len=131072, spec={}, makeup=1.3, seed=12,
+                            out=dict(conv_is_last=False, lp=1, dc_cutoff=3.0)),
+}
+
+
+def output_inputs(c):
+    return np.stack([signals.noise(c["T"], 6000 + c["seed"]), signals.noise(c["T"], 6500 + c["seed"])]) * c["amp"] + 0.05
+
+
 def conv_inputs(c):
     ir = signals.synth_ir(c["ir_len"], 1000 + c["seed"])
     if "impulse_at" in c:

@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle.bindings import Ref, Oracle, FilterSpec  # noqa: E402
 from tests import signals  # noqa: E402
-from tests.golden.cases import CONV_CASES, EQ_CASES, CHAIN_CASES, conv_inputs, eq_inputs, chain_inputs  # noqa: E402
+from tests.golden.cases import (CONV_CASES, EQ_CASES, CHAIN_CASES, OUTPUT_CASES, FULL_CHAIN_CASES, conv_inputs, eq_inputs,  # noqa: E402
+                                chain_inputs, output_inputs)
 
 
 def main():
@@ -38,6 +39,16 @@ def main():
         irs, bands, x = chain_inputs(c)
         y = ref.chain_run(irs, signals.to_eqband(bands), x, c["sr"], c["block"], FilterSpec(**c["spec"]), makeup=c["makeup"])
         out["chain/" + name] = y
+    for name, c in OUTPUT_CASES.items():
+        out["output/" + name] = ref.output_run(output_inputs(c), c["sr"], c["block"], **c["kw"])
+        out["output_design/" + name] = ref.output_design(c["sr"], c["kw"].get("conv_is_last", False), c["kw"].get("hc", 1),
+                                                         c["kw"].get("lc", 0), c["kw"].get("lp", 1))
+    for name, c in FULL_CHAIN_CASES.items():
+        # conv -> wet gain -> EQ (reference chain, no epilogue), then the reference output stages; the stages have no
+        # feedback into each other, so running them one after the other over the whole signal equals the per-callback chain
+        irs, bands, x = chain_inputs(c)
+        y = ref.chain_run(irs, signals.to_eqband(bands), x, c["sr"], c["block"], FilterSpec(**c["spec"]), do_epilogue=False)
+        out["full_chain/" + name] = ref.output_run(y, c["sr"], c["block"], makeup=c["makeup"], **c["out"])
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(out), "arrays")

@@ -345,3 +345,83 @@ def test_shared_ir_and_eq_across_sequence_chunks(checker):
         c = [checker.nuc_run(irs[ch], x[2 * s + ch], block)[0] for ch in range(2)]
         wl, wr, _ = checker.eq_run(signals.to_eqband(params), c[0], c[1], sr, block)
         assert np.abs(y[2 * s] - wl).max() <= TOL and np.abs(y[2 * s + 1] - wr).max() <= TOL
+
+
+# ---- output stages: OutputFilter -> makeup -> DC blocker -> headroom -> scrub + clamp ----
+from tests.golden.cases import OUTPUT_CASES as _GOUT, FULL_CHAIN_CASES as _GFULL, output_inputs
+
+
+def _gpu_output(x, sr, block, stages, conv_is_last=False, hc=1, lc=0, lp=1, makeup=1.0, dc_cutoff=3.0, clamp=True, use_filter=True,
+                n_channels=2):
+    T = x.shape[1]
+    eng = ConvoPeqEngine(x.shape[0] // n_channels, n_channels, sr, block, T)
+    eng.set_output_filter(use_filter, conv_is_last, hc, lc, lp)
+    eng.set_output_stage(dc_cutoff, clamp)
+    eng.set_epilogue(makeup, 0)
+    y = x.copy()
+    eng.process(y, stages)
+    eng.close()
+    return y
+
+
+@pytest.mark.parametrize("name", sorted(_GOUT))
+def test_output_stage_matches_golden(name):
+    c = _GOUT[name]
+    y = _gpu_output(output_inputs(c), c["sr"], c["block"], capi.STAGE_OUTPUT_FILTER | capi.STAGE_EPILOGUE, **c["kw"])
+    assert np.abs(y - _GOLD["output/" + name]).max() <= TOL
+    d = np.zeros(15)
+    kw = c["kw"]
+    capi.load().cpq_output_filter_design(c["sr"], int(kw.get("conv_is_last", False)), kw.get("hc", 1), kw.get("lc", 0), kw.get("lp", 1),
+                                         d.ctypes.data_as(capi.C.POINTER(capi.C.c_double)))
+    assert np.array_equal(d.reshape(3, 5), _GOLD["output_design/" + name])   # same libm sin/cos as OutputFilter::prepare
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(conv_is_last=True, hc=0, lc=1), dict(conv_is_last=True, hc=2, makeup=1.7),
+                                dict(lp=0, dc_cutoff=0.0), dict(use_filter=False), dict(clamp=False)])
+@pytest.mark.parametrize("T,block,sr", [(8192 * 5 + 512, 512, 48000.0), (96000, 64, 192000.0)])
+def test_output_stage_matches_reference_across_tiles(checker, kw, T, block, sr):
+    """Several 8192-sample tiles (tile-to-tile chain of the output stages), a partial last tile, mono and stereo streams."""
+    x = np.stack([signals.noise(T, 700 + i) for i in range(4)]) * 2.0 + 0.02
+    y = _gpu_output(x, sr, block, capi.STAGE_OUTPUT_FILTER | capi.STAGE_EPILOGUE, **kw)
+    for s in range(2):
+        want = checker.output_run(x[2 * s:2 * s + 2], sr, block, **kw)
+        assert np.abs(y[2 * s:2 * s + 2] - want).max() <= TOL
+    ym = _gpu_output(x[:1], sr, block, capi.STAGE_OUTPUT_FILTER | capi.STAGE_EPILOGUE, n_channels=1, **kw)
+    assert np.abs(ym - checker.output_run(x[:1], sr, block, **kw)).max() <= TOL
+
+
+@pytest.mark.parametrize("name", sorted(_GFULL))
+def test_full_chain_matches_golden(name):
+    """conv -> wet gain -> EQ -> total gain -> OutputFilter -> makeup -> DC blocker -> headroom -> scrub + clamp in one call."""
+    c = _GFULL[name]
+    irs, bands, x = chain_inputs(c)
+    eng = ConvoPeqEngine(1, 2, c["sr"], c["block"], c["T"], conv_boundary=capi.CONV_OUTER)
+    for ch in range(2):
+        eng.set_impulse(0, ch, irs[ch], 1.0, capi.default_filter_spec(**c["spec"]))
+    eng.set_eq(0, signals.to_band(bands))
+    eng.set_epilogue(c["makeup"], 0)
+    eng.set_output_filter(True, c["out"]["conv_is_last"], 1, 0, c["out"]["lp"])
+    eng.set_output_stage(c["out"]["dc_cutoff"], True)
+    y = x.copy()
+    eng.process(y, capi.STAGE_FULL)
+    eng.close()
+    assert np.abs(y - _GOLD["full_chain/" + name]).max() <= TOL
+
+
+def test_output_filter_after_total_gain_ramp(checker):
+    """The total-gain ramp sits between the EQ bands and OutputFilter: it is applied in registers before the output stages."""
+    sr, block, T = 48000.0, 512, 512 * 60
+    params = signals.band_params(seed=9)
+    xl, xr = signals.log_sweep(T, sr)
+    eng = ConvoPeqEngine(1, 2, sr, block, T)
+    eng.set_eq(0, signals.to_band(params), 0.2, 0.0)
+    eng.schedule_total_gain(0, 20, -6.0)
+    eng.set_output_filter(True, False, 1, 0, 2)
+    eng.set_output_stage(3.0, True)
+    eng.set_epilogue(1.1, 0)
+    y = np.stack([xl, xr]).copy()
+    eng.process(y, capi.STAGE_EQ | capi.STAGE_OUTPUT_FILTER | capi.STAGE_EPILOGUE)
+    eng.close()
+    wl, wr, _ = checker.eq_run(signals.to_eqband(params), xl, xr, sr, block, gain_change_db=-6.0, gain_change_at=20 * block)
+    want = checker.output_run(np.stack([wl, wr]), sr, block, lp=2, makeup=1.1)
+    assert np.abs(y - want).max() <= TOL

@@ -7,7 +7,8 @@ import pytest
 
 from oracle.bindings import FilterSpec
 from tests import signals
-from tests.golden.cases import CONV_CASES, EQ_CASES, CHAIN_CASES, conv_inputs, eq_inputs, chain_inputs
+from tests.golden.cases import (CONV_CASES, EQ_CASES, CHAIN_CASES, OUTPUT_CASES, FULL_CHAIN_CASES, conv_inputs, eq_inputs, chain_inputs,
+                                output_inputs)
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden.npz"))
 TOL = 1e-12   # restatement vs reference: same algorithm, different FFT rounding (SURVEY 8c measured 5.8e-15)
@@ -82,3 +83,33 @@ def test_epilogue_headroom_and_dither_determinism(oracle):
     lsb = 1.0 / 2 ** 15
     assert np.allclose(q1 / lsb, np.round(q1 / lsb))          # quantised to the 16-bit grid
     assert np.abs(q1 - tmp).max() <= 0.5 * lsb + 1e-15         # round-to-nearest of the pre-quantiser value
+
+
+@pytest.mark.parametrize("name", sorted(OUTPUT_CASES))
+def test_output_stage_restatement_matches_golden(oracle, name):
+    """OutputFilter -> makeup -> DC blocker -> headroom -> scrub + clamp against the reference's own OutputFilter.cpp /
+    UltraHighRateDCBlocker.h (stereo path: same FMA association, so the restatement is bit-identical)."""
+    c = OUTPUT_CASES[name]
+    kw = c["kw"]
+    got = oracle.output_design(c["sr"], kw.get("conv_is_last", False), kw.get("hc", 1), kw.get("lc", 0), kw.get("lp", 1))
+    assert np.array_equal(got, GOLD["output_design/" + name])
+    y = oracle.output_run(output_inputs(c), c["sr"], c["block"], **kw)
+    assert np.abs(y - GOLD["output/" + name]).max() <= TOL
+
+
+@pytest.mark.parametrize("name", sorted(FULL_CHAIN_CASES))
+def test_full_chain_restatement_matches_golden(oracle, name):
+    c = FULL_CHAIN_CASES[name]
+    irs, bands, x = chain_inputs(c)
+    y = oracle.chain_run(irs, signals.to_eqband(bands), x, c["sr"], c["block"], FilterSpec(**c["spec"]), do_epilogue=False)
+    y = oracle.output_run(y, c["sr"], c["block"], makeup=c["makeup"], **c["out"])
+    assert np.abs(y - GOLD["full_chain/" + name]).max() <= TOL
+
+
+def test_output_filter_is_block_size_independent_and_clamps(oracle):
+    c = OUTPUT_CASES["eq_last_natural"]
+    x = output_inputs(c)
+    a = oracle.output_run(x, c["sr"], 512, **c["kw"])
+    b = oracle.output_run(x, c["sr"], 64, **c["kw"])
+    assert np.array_equal(a, b)
+    assert np.abs(a).max() == 0.8912509381337456   # the 3x noise input overshoots: the hard clamp is exercised

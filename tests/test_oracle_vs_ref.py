@@ -70,3 +70,20 @@ def test_eq_is_block_size_independent(ref):
     xl, xr = signals.log_sweep(T, sr)
     outs = [ref.eq_run(bands, xl, xr, sr, b)[0] for b in (64, 512, 4608)]
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(conv_is_last=True, hc=0, lc=1), dict(conv_is_last=True, hc=2), dict(lp=0, makeup=1.7),
+                                dict(use_filter=False), dict(dc_cutoff=0.0, clamp=False, headroom=False)])
+@pytest.mark.parametrize("sr", [44100.0, 48000.0, 192000.0])
+def test_output_stage_restatement_equals_reference(oracle, ref, kw, sr):
+    """OutputFilter.cpp + UltraHighRateDCBlocker.h compiled from the reference tree vs oracle/cpq_oracle.c."""
+    x = np.stack([signals.noise(24000, 31), signals.noise(24000, 32)]) * 2.0 + 0.03
+    for m in range(3):
+        assert np.array_equal(oracle.output_design(sr, True, m, m % 2, m), ref.output_design(sr, True, m, m % 2, m))
+        assert np.array_equal(oracle.output_design(sr, False, m, m % 2, m), ref.output_design(sr, False, m, m % 2, m))
+    a, b = oracle.output_run(x, sr, 480, **kw), ref.output_run(x, sr, 480, **kw)
+    assert np.abs(a - b).max() <= 1e-13
+    # mono path of the reference uses the scalar BiquadState::process (different association): 1e-16-level differences
+    # amplified by the 20 Hz high-pass pole radius
+    am, bm = oracle.output_run(x[:1], sr, 480, **kw), ref.output_run(x[:1], sr, 480, **kw)
+    assert np.abs(am - bm).max() <= 1e-11
