@@ -123,6 +123,15 @@ public:
 
     /// outputMakeupGain + dither bit depth (0 = the no-dither kOutputHeadroom branch).
     bool setOutputStage(double makeupGain, int ditherBitDepth = 0) { return ok(cpq_set_epilogue(h_, makeupGain, ditherBitDepth)); }
+    /// convo::OutputFilter::process(block, convIsLast, hcMode, lcMode, lpMode) (OutputFilter.h:108-131): runs when
+    /// CPQ_STAGE_OUTPUT_FILTER is requested.  Mode values as convo::HCMode / convo::LCMode.
+    bool setOutputFilter(bool enabled, bool convIsLast, int hcMode = 1, int lcMode = 0, int lpMode = 1)
+    {
+        return ok(cpq_set_output_filter(h_, enabled ? 1 : 0, convIsLast ? 1 : 0, hcMode, lcMode, lpMode));
+    }
+    /// Output DC blocker (the engine initialises it at 3 Hz, AudioEngine.h:643-651; 0 = off) and processOutputDouble's
+    /// scrub + +-kOutputHeadroom hard clamp, both inside CPQ_STAGE_EPILOGUE.
+    bool setOutputProtection(double dcCutoffHz, bool hardClamp) { return ok(cpq_set_output_stage(h_, dcCutoffHz, hardClamp ? 1 : 0)); }
     bool setDitherUniforms(std::span<const double> uniforms, std::int64_t samplesPerChannel)
     {
         return ok(cpq_set_dither_uniforms(h_, uniforms.data(), samplesPerChannel));
