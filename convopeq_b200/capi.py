@@ -17,6 +17,7 @@ MAX_LAYERS = 3
 OK, ERR_INVALID, ERR_NOT_READY, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_GEOMETRY = range(7)
 STAGE_CONV, STAGE_EQ, STAGE_EPILOGUE, STAGE_ALL = 1, 2, 4, 7
 STAGE_OUTPUT_FILTER, STAGE_FULL = 8, 15
+ORDER_EQ_THEN_CONV = 16
 CONV_INNER, CONV_OUTER = 0, 1
 
 
@@ -58,7 +59,7 @@ class Timings(C.Structure):
 EXPORTS = [
     "cpq_abi_version", "cpq_status_string", "cpq_last_error", "cpq_filter_spec_default", "cpq_config_default",
     "cpq_create", "cpq_destroy", "cpq_reset", "cpq_set_impulse", "cpq_set_eq", "cpq_schedule_total_gain",
-    "cpq_set_epilogue", "cpq_set_dither_uniforms", "cpq_set_output_filter", "cpq_set_output_stage", "cpq_output_filter_design", "cpq_design_band", "cpq_db_to_gain", "cpq_equal_power_sin",
+    "cpq_set_epilogue", "cpq_set_dither_uniforms", "cpq_set_output_filter", "cpq_set_output_stage", "cpq_set_conv_input_trim", "cpq_output_filter_design", "cpq_design_band", "cpq_db_to_gain", "cpq_equal_power_sin",
     "cpq_process", "cpq_process_device", "cpq_set_partition_range", "cpq_total_partitions", "cpq_get_layout",
     "cpq_latency", "cpq_get_timings", "cpq_get_eq_state", "cpq_cuda_stream", "cpq_kernel_launch_count",
     "cpq_plan_layout",
@@ -102,6 +103,7 @@ def load() -> C.CDLL:
     L.cpq_set_dither_uniforms.argtypes = [vp, dp, C.c_int64]
     L.cpq_set_output_filter.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.cpq_set_output_stage.argtypes = [vp, C.c_double, C.c_int]
+    L.cpq_set_conv_input_trim.argtypes = [vp, C.c_double]
     L.cpq_output_filter_design.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, dp]
     L.cpq_output_filter_design.restype = None
     L.cpq_design_band.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_double, C.POINTER(SvfCoeffs)]

@@ -161,6 +161,7 @@ struct Engine
     cpq_status uploadEq(int64_t nCallbacks);
     cpq_status uploadPost();
     struct OutCfg { int filterEnabled = 0, convIsLast = 0, hc = 1, lc = 0, lp = 1; double dcCutoff = 0.0; int finalClamp = 0; } outCfg;
+    double convInputTrim = 1.0;         // state.convolverInputTrimGain (EQThenConvolver order only)
     bool postDirty = true;
     unsigned postIdentity = 0;          // output-filter stages whose coefficients are the identity (skipped)
     DevBuf<double> postc, postState;
@@ -394,7 +395,6 @@ cpq_status Engine::init(const cpq_config* c)
         setError("max_samples must be a multiple of block_size");
         return CPQ_ERR_INVALID;
     }
-    if (cfg.workspace_bytes == 0) cfg.workspace_bytes = (size_t) 4 << 30;
     nSeq = cfg.n_streams * cfg.n_channels;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
@@ -415,6 +415,15 @@ cpq_status Engine::init(const cpq_config* c)
     {
         setError("device is not sm_100 class (B200 required)");
         return CPQ_ERR_CUDA;
+    }
+    if (cfg.workspace_bytes == 0)
+    {
+        // default: a quarter of the device memory that is free now, within 4..16 GiB (measured on cfg4: 2 GiB 78.0 ms,
+        // 4 GiB 74.7 ms, 8 GiB 73.4 ms, 16 GiB 73.2 ms per step -- fewer, larger launches have shorter tails)
+        size_t freeB = 0, totalB = 0;
+        cfg.workspace_bytes = (size_t) 4 << 30;
+        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess)
+            cfg.workspace_bytes = std::min<size_t>((size_t) 16 << 30, std::max<size_t>((size_t) 4 << 30, freeB / 4));
     }
     CPQ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CPQ_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
@@ -897,7 +906,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         setError("process: T must be a positive multiple of block_size <= max_samples; stride even and >= T");
         return CPQ_ERR_INVALID;
     }
-    if ((stages & ~CPQ_STAGE_FULL) || stages == 0)
+    if ((stages & ~(CPQ_STAGE_FULL | CPQ_ORDER_EQ_THEN_CONV)) || (stages & CPQ_STAGE_FULL) == 0)
     {
         setError("process: bad stage mask");
         return CPQ_ERR_INVALID;
@@ -1049,6 +1058,9 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         a.wetGain = equalPowerSin(1.0) * 1.0;   // CONVOLUTION_HEADROOM_GAIN = 1.0 (ConvolverProcessor.h:209)
     };
     const bool deferredOuter = !doConv && outerPending;
+    // ProcessingOrder::EQThenConvolver (DSPCoreDouble.cpp:415-451): EQ (with its total-gain ramp) on the raw input, the
+    // convolver input trim, then the convolver; the final launch then only assembles the layers and runs the output stages
+    const bool eqFirst = (stages & CPQ_ORDER_EQ_THEN_CONV) && doConv && doEq;
 
     for (size_t c = 0; c < nChunks; ++c)
     {
@@ -1057,6 +1069,23 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         cudaEvent_t* ce = &evPool[c * 6];
         if (hostPlanar) cudaStreamWaitEvent(stream, evPool[c * 6 + 5], 0);
         cudaEventRecord(ce[0], stream);
+        if (eqFirst)
+        {
+            EqArgs p {};
+            fillEqCommon(p);
+            p.io = ioC;
+            p.nSeq = ns;
+            p.bandMask = bandMask.p + s0;
+            p.setOfSeq = setOfSeq.p + s0;
+            p.stateOut = stateOut.p + (size_t) s0 * CPQ_NUM_BANDS * 2;
+            p.postMask = 0;
+            p.finalClamp = 0;
+            p.applyHeadroom = 0;
+            p.doEpilogue = std::fabs(convInputTrim - 1.0) > 1e-12 ? 1 : 0;   // scaleBlockFallback(ptr, n, convolverInputTrimGain), :438-445
+            p.makeup = convInputTrim;
+            cpq_status st = launchEq(p);
+            if (st != CPQ_OK) return st;
+        }
         if (doConv)
         {
             // ---- forward FFTs of every layer (all read the untouched input) ----
@@ -1181,6 +1210,11 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             e.assemble = deferredOuter ? 1 : 0;   // no tails; only the deferred outer-boundary scrub + wet gain
             e.nTail = 0;
             e.outer = deferredOuter ? 1 : 0;
+        }
+        if (eqFirst)
+        {
+            e.doEq = 0;
+            e.gainTab = nullptr;
         }
         e.bandMask = bandMask.p ? bandMask.p + s0 : nullptr;
         e.setOfSeq = setOfSeq.p ? setOfSeq.p + s0 : nullptr;   // absolute set indices
@@ -1424,6 +1458,13 @@ cpq_status cpq_set_output_filter(cpq_handle h, int enabled, int conv_is_last, in
     h->outCfg.lc = lc_mode;
     h->outCfg.lp = lp_mode;
     h->postDirty = true;
+    return CPQ_OK;
+}
+
+cpq_status cpq_set_conv_input_trim(cpq_handle h, double gain)
+{
+    if (!h || !std::isfinite(gain)) return CPQ_ERR_INVALID;
+    h->convInputTrim = gain;
     return CPQ_OK;
 }
 

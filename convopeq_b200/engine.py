@@ -146,6 +146,10 @@ class ConvoPeqEngine:
         """OutputFilter::process(block, convIsLast, hcMode, lcMode, lpMode) (OutputFilter.h:108-131); runs with STAGE_OUTPUT_FILTER."""
         self._check(self.lib.cpq_set_output_filter(self.h, int(enabled), int(conv_is_last), hc_mode, lc_mode, lp_mode))
 
+    def set_conv_input_trim(self, gain: float):
+        """convolverInputTrimGain of the EQThenConvolver order (DSPCoreDouble.cpp:438-445)."""
+        self._check(self.lib.cpq_set_conv_input_trim(self.h, gain))
+
     def set_output_stage(self, dc_cutoff_hz: float = 3.0, hard_clamp: bool = True):
         """Output DC blocker (AudioEngine.h:643-651 uses 3 Hz) and the scrub + +-kOutputHeadroom clamp of processOutputDouble."""
         self._check(self.lib.cpq_set_output_stage(self.h, dc_cutoff_hz, int(hard_clamp)))

@@ -77,7 +77,10 @@ enum
     CPQ_STAGE_EPILOGUE = 4u,  /* makeup gain (:465-469) + processOutputDouble headroom / dither (:581,:644-663) */
     CPQ_STAGE_ALL = 7u,       /* the north-star path: conv -> EQ -> gain / dither */
     CPQ_STAGE_OUTPUT_FILTER = 8u, /* outputFilter.process between the EQ and the makeup gain (:460-462), see cpq_set_output_filter */
-    CPQ_STAGE_FULL = 15u
+    CPQ_STAGE_FULL = 15u,
+    /* ProcessingOrder::EQThenConvolver (:415-451) instead of ConvolverThenEQ: EQ -> convolverInputTrimGain -> convolver
+     * -> (output filter with conv_is_last) -> epilogue.  Only meaningful together with CPQ_STAGE_CONV | CPQ_STAGE_EQ. */
+    CPQ_ORDER_EQ_THEN_CONV = 16u
 };
 
 typedef struct cpq_config
@@ -92,7 +95,7 @@ typedef struct cpq_config
     int32_t shared_ir;     /* 1: one IR pair (per channel) shared by all streams */
     int32_t shared_eq;     /* 1: one EQ setting shared by all streams */
     int32_t reserved_;
-    size_t workspace_bytes;/* upper bound for the per-call spectra workspace; 0 = default (4 GiB) */
+    size_t workspace_bytes;/* upper bound for the per-call spectra workspace; 0 = default (free memory / 4 within 4..16 GiB) */
 } cpq_config;
 
 /* cpq_get_layout: what SetImpulse decided (MKLNonUniformConvolver.cpp:738-758,988-994,1004-1024) plus the
@@ -175,6 +178,9 @@ cpq_status cpq_set_output_filter(cpq_handle h, int enabled, int conv_is_last, in
  * +-kOutputHeadroom clamp (DSPCoreDouble.cpp:665-691, 712-737).  SimplePeakLimiter (:700-710) sits between the two and is
  * the identity while |y| <= 0.7870 (threshold - knee/2); it is not part of this path. */
 cpq_status cpq_set_output_stage(cpq_handle h, double dc_cutoff_hz, int hard_clamp);
+/* state.convolverInputTrimGain: applied between the EQ and the convolver in the EQThenConvolver order when it differs from
+ * 1 by more than 1e-12 (DSPCoreDouble.cpp:438-445). */
+cpq_status cpq_set_conv_input_trim(cpq_handle h, double gain);
 /* Host-only: the three stages' normalised coefficients {b0,b1,b2,a1,a2} x 3 as OutputFilter::prepare computes them. */
 void cpq_output_filter_design(double sample_rate, int conv_is_last, int hc_mode, int lc_mode, int lp_mode, double out[15]);
 

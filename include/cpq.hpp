@@ -131,6 +131,8 @@ public:
     }
     /// Output DC blocker (the engine initialises it at 3 Hz, AudioEngine.h:643-651; 0 = off) and processOutputDouble's
     /// scrub + +-kOutputHeadroom hard clamp, both inside CPQ_STAGE_EPILOGUE.
+    /// convolverInputTrimGain (EQThenConvolver order: pass CPQ_ORDER_EQ_THEN_CONV in `stages`).
+    bool setConvolverInputTrim(double gain) { return ok(cpq_set_conv_input_trim(h_, gain)); }
     bool setOutputProtection(double dcCutoffHz, bool hardClamp) { return ok(cpq_set_output_stage(h_, dcCutoffHz, hardClamp ? 1 : 0)); }
     bool setDitherUniforms(std::span<const double> uniforms, std::int64_t samplesPerChannel)
     {

@@ -425,3 +425,31 @@ def test_output_filter_after_total_gain_ramp(checker):
     wl, wr, _ = checker.eq_run(signals.to_eqband(params), xl, xr, sr, block, gain_change_db=-6.0, gain_change_at=20 * block)
     want = checker.output_run(np.stack([wl, wr]), sr, block, lp=2, makeup=1.1)
     assert np.abs(y - want).max() <= TOL
+
+
+@pytest.mark.parametrize("trim", [1.0, 0.7079457843841379])
+def test_eq_then_convolver_order(checker, oracle, trim):
+    """ProcessingOrder::EQThenConvolver: EQ -> input trim -> convolver (outer boundary) -> OutputFilter(convIsLast) -> epilogue."""
+    sr, block, T, ir_len = 48000.0, 512, 24576, 65536
+    x = np.stack([signals.noise(T, 810), signals.noise(T, 811)])
+    irs = [signals.synth_ir(ir_len, 820), signals.synth_ir(ir_len, 821)]
+    params = signals.band_params(830)
+    cspec, ospec = capi.default_filter_spec(), OFilterSpec()
+    eng = ConvoPeqEngine(1, 2, sr, block, T, conv_boundary=capi.CONV_OUTER)
+    for ch in range(2):
+        eng.set_impulse(0, ch, irs[ch], 1.0, cspec)
+    eng.set_eq(0, signals.to_band(params))
+    eng.set_conv_input_trim(trim)
+    eng.set_output_filter(True, True, 1, 0, 1)
+    eng.set_output_stage(3.0, True)
+    eng.set_epilogue(1.2, 0)
+    y = x.copy()
+    eng.process(y, capi.STAGE_FULL | capi.ORDER_EQ_THEN_CONV)
+    eng.close()
+    wl, wr, _ = checker.eq_run(signals.to_eqband(params), x[0], x[1], sr, block)
+    w = []
+    for ch, v in enumerate((wl, wr)):
+        c, _ = checker.nuc_run(irs[ch], v * trim, block, spec=ospec)
+        w.append(oracle.outer_wet(c, 1.0))
+    want = checker.output_run(np.stack(w), sr, block, conv_is_last=True, makeup=1.2)
+    assert np.abs(y - want).max() <= TOL
