@@ -159,7 +159,10 @@ __device__ __forceinline__ void mac_run(double2 (&acc)[kMacKT], const char* __re
     }
 }
 
-__global__ void __launch_bounds__(kMacThreads, 2) mac_kernel(MacArgs a)
+#ifndef CPQ_MAC_MINBLOCKS
+#define CPQ_MAC_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(kMacThreads, CPQ_MAC_MINBLOCKS) mac_kernel(MacArgs a)
 {
     extern __shared__ __align__(128) unsigned char mac_smem[];
     const int nq = a.qEnd - a.qBegin;
