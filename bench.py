@@ -74,12 +74,19 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []      # (arrival time, csv line)
+        self.windows = []    # [t0, t1] timed regions (perf_counter)
+
+    def begin(self):
+        self.windows.append([time.perf_counter(), None])
+
+    def end(self):
+        self.windows[-1][1] = time.perf_counter()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -87,7 +94,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -98,7 +105,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
-        for ln in self.lines:
+        # nvidia-smi is started before the warm-up (it needs ~1 s to deliver its first line); only the samples that
+        # arrived inside a timed region (device-resident steps, e2e steps) count
+        for ts, ln in self.lines:
+            if not any(w[0] <= ts <= (w[1] if w[1] is not None else ts) for w in self.windows):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -111,7 +122,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "window": "samples taken every 100 ms inside the timed regions (device-resident steps + e2e steps)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -253,11 +265,12 @@ def main():
         e1.synchronize()
         return e0.elapsed_time(e1)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.begin()
     launches0 = eng.kernel_launch_count()
     step_ms, stage = [], []
     for _ in range(args.steps):
@@ -266,7 +279,7 @@ def main():
         stage.append((t.fft_fwd_ms, t.mac_ms, t.fft_inv_ms, t.eq_ms, t.chunks))
     launches = eng.kernel_launch_count() - launches0
     barrier()
-    clocks = sampler.stop()
+    sampler.end()
     ms_local = sum(step_ms) / len(step_ms)
     ms = torch.tensor([ms_local], device=dev, dtype=torch.float64)
     if world > 1:
@@ -292,8 +305,10 @@ def main():
 
         step_host()
         barrier()
+        sampler.begin()
         e_ms = [step_host() for _ in range(args.steps)]
         barrier()
+        sampler.end()
         em = torch.tensor([sum(e_ms) / len(e_ms)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(em, op=dist.ReduceOp.MAX)
@@ -303,6 +318,7 @@ def main():
                "ms_per_step": float(em.item()), "h2d_ms": te.h2d_ms, "d2h_ms": te.d2h_ms,
                "note": "steps run in place on the pinned host buffer (each step's output is the next step's input)"}
         del host
+    clocks = sampler.stop()
 
     if rank == 0:
         peaks = {}
