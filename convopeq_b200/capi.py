@@ -62,7 +62,7 @@ EXPORTS = [
     "cpq_set_epilogue", "cpq_set_dither_uniforms", "cpq_set_output_filter", "cpq_set_output_stage", "cpq_set_conv_input_trim", "cpq_output_filter_design", "cpq_design_band", "cpq_db_to_gain", "cpq_equal_power_sin",
     "cpq_process", "cpq_process_device", "cpq_set_partition_range", "cpq_total_partitions", "cpq_get_layout",
     "cpq_latency", "cpq_get_timings", "cpq_get_eq_state", "cpq_cuda_stream", "cpq_kernel_launch_count",
-    "cpq_plan_layout",
+    "cpq_plan_layout", "cpq_set_eq_mode", "cpq_band_node_active", "cpq_get_agc_state",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -99,6 +99,9 @@ def load() -> C.CDLL:
     L.cpq_set_eq.argtypes = [vp, C.c_int, C.POINTER(SvfCoeffs), C.POINTER(C.c_uint8), C.POINTER(C.c_int32),
                              C.c_double, C.c_double]
     L.cpq_schedule_total_gain.argtypes = [vp, C.c_int, C.c_int64, C.c_double]
+    L.cpq_set_eq_mode.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8)]
+    L.cpq_band_node_active.argtypes = [C.c_int, C.c_float, C.c_int, C.c_double]
+    L.cpq_get_agc_state.argtypes = [vp, C.c_int, dp]
     L.cpq_set_epilogue.argtypes = [vp, C.c_double, C.c_int]
     L.cpq_set_dither_uniforms.argtypes = [vp, dp, C.c_int64]
     L.cpq_set_output_filter.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]

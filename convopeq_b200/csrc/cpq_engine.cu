@@ -67,6 +67,10 @@ struct EqSet
     double totalGain = 1.0;
     bool set = false;
     std::vector<GainEvent> events;
+    int structure = 0;                       // EQParameters::filterStructure: 0 Serial, 1 Parallel
+    int agc = 0;                             // EQParameters::agcEnabled
+    uint8_t nodeActive[CPQ_NUM_BANDS];       // BandNode::active, used instead of `active` when the node path runs (Mid/Side)
+    bool hasNodeActive = false;
 };
 
 struct LayerDev
@@ -116,6 +120,15 @@ struct Engine
     bool haveGainTab = false;
     DevBuf<double> chainRec;
     DevBuf<unsigned> ticketFault;       // [0] ticket, [1] fault
+    // EQ modes beyond Serial / Stereo|Left|Right
+    bool anyPar = false, anyAgc = false, anyMs = false;
+    unsigned msSplitMask = 0;                        // bands that are Mid/Side in at least one stream
+    std::vector<int> msStreams[CPQ_NUM_BANDS];       // sorted streams whose band b is Mid/Side
+    DevBuf<int> msStreamsDev[CPQ_NUM_BANDS], msSetDev[CPQ_NUM_BANDS];
+    DevBuf<unsigned> msMaskDev[CPQ_NUM_BANDS];       // [2 * count]: bit b on the Mid row or on the Side row
+    DevBuf<double> msScratch, sumsq, agcTab, agcState;
+    DevBuf<uint8_t> agcOnDev;
+    cpq_status runEq(EqArgs e, int s0, int ns);
 
     // epilogue
     double makeup = 1.0;
@@ -797,19 +810,31 @@ cpq_status Engine::uploadEq(int64_t nCallbacks)
         }
         std::vector<unsigned> mask((size_t) nSeq);
         std::vector<int> sos((size_t) nSeq);
+        anyPar = anyAgc = anyMs = false;
+        msSplitMask = 0;
+        for (auto& v : msStreams) v.clear();
         for (int q = 0; q < nSeq; ++q)
         {
             const int st = q / cfg.n_channels, ch = q % cfg.n_channels;
             const EqSet& e = eqSets[cfg.shared_eq ? 0 : (size_t) st];
+            // An active Mid/Side band sends the reference to its node path (Processing.cpp:1037-1044), where BandNode::active
+            // (with createBandNode's 0-dB skip) decides which bands run instead of EQCoeffCache::bandActive
+            bool nodePath = false;
+            for (int b = 0; b < CPQ_NUM_BANDS; ++b) nodePath |= e.active[b] && e.mode[b] >= 3;
+            const uint8_t* on_ = (nodePath && e.hasNodeActive) ? e.nodeActive : e.active;
             unsigned m = 0;
             for (int b = 0; b < CPQ_NUM_BANDS; ++b)
             {
-                if (!e.active[b]) continue;
+                if (!on_[b]) continue;
                 const int mode = e.mode[b];
                 // Processing.cpp:1239-1252: Stereo -> both; Left -> ch 0; Right -> ch 1
                 const bool on = (mode == 0) || (mode == 1 && ch == 0) || (mode == 2 && ch == 1);
                 if (on) m |= 1u << b;
+                if (mode >= 3 && ch == 0) msStreams[b].push_back(st);   // ascending stream order
             }
+            if (e.structure == 1) m |= 1u << 31;   // Parallel structure flag, read by eq_kernel<.., PAR>
+            anyPar |= e.structure == 1;
+            anyAgc |= e.agc != 0;
             mask[(size_t) q] = m;
             sos[(size_t) q] = cfg.shared_eq ? 0 : st;
         }
@@ -823,12 +848,57 @@ cpq_status Engine::uploadEq(int64_t nCallbacks)
         CPQ_CUDA(cudaMemcpyAsync(gainConst.p, gc.data(), nSets * sizeof(double), cudaMemcpyHostToDevice, stream));
         CPQ_CUDA(cudaMemcpyAsync(bandMask.p, mask.data(), mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice, stream));
         CPQ_CUDA(cudaMemcpyAsync(setOfSeq.p, sos.data(), sos.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        // Mid/Side bands: per band the compact list of streams, the scratch rows' band masks and parameter sets
+        for (int b = 0; b < CPQ_NUM_BANDS; ++b)
+        {
+            const std::vector<int>& L = msStreams[b];
+            if (L.empty()) continue;
+            anyMs = true;
+            msSplitMask |= 1u << b;
+            std::vector<unsigned> mm(2 * L.size(), 0u);
+            std::vector<int> ss(2 * L.size());
+            for (size_t i = 0; i < L.size(); ++i)
+            {
+                const EqSet& e = eqSets[cfg.shared_eq ? 0 : (size_t) L[i]];
+                mm[2 * i + (e.mode[b] == 3 ? 0 : 1)] = 1u << b;   // Mid -> row 0, Side -> row 1
+                ss[2 * i] = ss[2 * i + 1] = cfg.shared_eq ? 0 : L[i];
+            }
+            CPQ_CUDA(msStreamsDev[b].ensure(L.size()));
+            CPQ_CUDA(msMaskDev[b].ensure(mm.size()));
+            CPQ_CUDA(msSetDev[b].ensure(ss.size()));
+            CPQ_CUDA(cudaMemcpyAsync(msStreamsDev[b].p, L.data(), L.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+            CPQ_CUDA(cudaMemcpyAsync(msMaskDev[b].p, mm.data(), mm.size() * sizeof(unsigned), cudaMemcpyHostToDevice, stream));
+            CPQ_CUDA(cudaMemcpyAsync(msSetDev[b].p, ss.data(), ss.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        }
+        if (anyAgc)
+        {
+            std::vector<uint8_t> on((size_t) cfg.n_streams);
+            for (int st = 0; st < cfg.n_streams; ++st) on[(size_t) st] = eqSets[cfg.shared_eq ? 0 : (size_t) st].agc ? 1 : 0;
+            CPQ_CUDA(agcOnDev.ensure(on.size()));
+            CPQ_CUDA(agcState.ensure(on.size() * 3));
+            CPQ_CUDA(cudaMemcpyAsync(agcOnDev.p, on.data(), on.size(), cudaMemcpyHostToDevice, stream));
+        }
         CPQ_CUDA(cudaStreamSynchronize(stream));
         eqDirty = false;
         gainTabCallbacks = -1;
     }
+    if (anyMs && cfg.n_channels != 2)
+    {
+        setError("Mid/Side bands need a stereo handle (n_channels = 2)");
+        return CPQ_ERR_UNSUPPORTED;
+    }
+    if (anyMs && anyPar)
+    {
+        setError("Mid/Side bands together with the Parallel structure (node path :751-865 with its structure cross-fade) are not part of this path");
+        return CPQ_ERR_UNSUPPORTED;
+    }
     bool anyEvents = false;
     for (auto& e : eqSets) anyEvents |= !e.events.empty();
+    if (anyEvents && anyAgc)
+    {
+        setError("total-gain events and AGC in one handle: with AGC the reference never applies the total-gain ramp (Processing.cpp:1255-1274)");
+        return CPQ_ERR_UNSUPPORTED;
+    }
     haveGainTab = anyEvents;
     if (anyEvents && gainTabCallbacks != nCallbacks)
     {
@@ -888,15 +958,129 @@ cpq_status Engine::launchEq(EqArgs& a)
     {
         CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytes));
         CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
+        CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
+        CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
         attrDone = true;
     }
     CPQ_CUDA(cudaMemsetAsync(ticketFault.p, 0, sizeof(unsigned), stream));
     const unsigned grid = (unsigned) a.nSeq * (unsigned) a.nRuns;
-    if (a.postMask || a.finalClamp) eq_kernel<true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
+    if (a.doEq && anyPar) eq_kernel<true, true, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
+    else if (a.sumsqIn || a.sumsqOut) eq_kernel<true, false, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
+    else if (a.postMask || a.finalClamp) eq_kernel<true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
     else eq_kernel<false><<<grid, kEqThreads, kEqSmemBytes, stream>>>(a);
     ++launches;
     CPQ_CUDA(cudaGetLastError());
     return CPQ_OK;
+}
+
+// The EQ stage of one sequence chunk.  Serial / Parallel structure without AGC and without Mid/Side bands is the single
+// fused launch.  Mid/Side bands split the band sequence: plain bands up to and including a split band run in one launch
+// (a stream for which that band is Mid/Side has it masked out), then the band runs on the encoded Mid or Side row of the
+// streams that want it (Processing.cpp:690-740).  AGC needs the statistics of whole callbacks before the gain can be
+// applied (:1119-1131, :343-445): bands + statistics, the block-rate recurrence, then a launch that applies the gain
+// ramp together with the output stages and the epilogue.
+cpq_status Engine::runEq(EqArgs e, int s0, int ns)
+{
+    const bool agc = e.doEq && anyAgc, ms = e.doEq && anyMs;
+    if (!agc && !ms) return launchEq(e);
+    const int nch = cfg.n_channels;
+    const int st0 = s0 / nch, nst = ns / nch;
+    double* sqIn = sumsq.p;
+    double* sqOut = sumsq.p + (size_t) ns * e.nCallbacks;
+    if (agc) CPQ_CUDA(cudaMemsetAsync(sumsq.p, 0, (size_t) 2 * ns * e.nCallbacks * sizeof(double), stream));
+    auto strip = [](EqArgs& g) {   // bands only
+        g.doGain = 0;
+        g.gainTab = nullptr;
+        g.postMask = 0;
+        g.postStateOut = nullptr;
+        g.doEpilogue = 0;
+        g.finalClamp = 0;
+        g.applyHeadroom = 0;
+    };
+    int lo = 0;
+    for (int b = 0; b <= CPQ_NUM_BANDS; ++b)
+    {
+        const bool final_ = b == CPQ_NUM_BANDS;
+        if (!final_ && !(ms && ((msSplitMask >> b) & 1u))) continue;
+        // plain bands lo..b (b included: it is masked out per sequence where it is Mid/Side)
+        EqArgs g = e;
+        const int hi = final_ ? CPQ_NUM_BANDS - 1 : b;
+        g.bandSelect = hi >= lo ? (((1u << (hi + 1)) - 1u) & ~((1u << lo) - 1u)) : 0u;
+        if (lo > 0)
+        {
+            g.assemble = 0;
+            g.nTail = 0;
+            g.outer = 0;
+        }
+        if (!final_ || agc) strip(g);
+        if (agc && lo == 0) g.sumsqIn = sqIn;
+        if (agc && final_) g.sumsqOut = sqOut;
+        cpq_status st = launchEq(g);
+        if (st != CPQ_OK) return st;
+        lo = b + 1;
+        if (final_) break;
+        // the Mid/Side band b of this chunk's streams
+        const std::vector<int>& L = msStreams[b];
+        const size_t i0 = (size_t) (std::lower_bound(L.begin(), L.end(), st0) - L.begin());
+        const size_t i1 = (size_t) (std::lower_bound(L.begin(), L.end(), st0 + nst) - L.begin());
+        if (i1 <= i0) continue;
+        const int cnt = (int) (i1 - i0);
+        MsArgs m {};
+        m.io = e.io;
+        m.ioStride = e.ioStride;
+        m.ms = msScratch.p;
+        m.streams = msStreamsDev[b].p + i0;
+        m.streamBase = st0;
+        m.T = e.T;
+        const dim3 mg((unsigned) std::min<int64_t>(64, (e.T / 2 + 255) / 256), (unsigned) cnt);
+        ms_kernel<true><<<mg, 256, 0, stream>>>(m);
+        ++launches;
+        EqArgs q = e;
+        strip(q);
+        q.assemble = 0;
+        q.nTail = 0;
+        q.outer = 0;
+        q.io = msScratch.p;
+        q.nSeq = 2 * cnt;
+        q.bandMask = msMaskDev[b].p + 2 * i0;
+        q.setOfSeq = msSetDev[b].p + 2 * i0;
+        q.bandSelect = 1u << b;
+        q.stateOut = nullptr;
+        st = launchEq(q);
+        if (st != CPQ_OK) return st;
+        ms_kernel<false><<<mg, 256, 0, stream>>>(m);
+        ++launches;
+        CPQ_CUDA(cudaGetLastError());
+    }
+    if (!agc) return CPQ_OK;
+    AgcArgs a {};
+    a.sumsqIn = sqIn;
+    a.sumsqOut = sqOut;
+    a.gainTab = agcTab.p;
+    a.agcOn = agcOnDev.p + st0;
+    a.gainConst = gainConst.p;
+    a.setOfSeq = e.setOfSeq;
+    a.stateOut = agcState.p + (size_t) st0 * 3;
+    a.nStreams = nst;
+    a.nch = nch;
+    a.nCallbacks = e.nCallbacks;
+    const double n = (double) cfg.block_size, sr = cfg.sample_rate;
+    a.blockN = n;
+    a.attack = 1.0 - std::exp(-n / (sr * 0.2));    // AGC_ATTACK_TIME_SEC   (EQProcessor.h:167-169, Core.cpp:781-783)
+    a.release = 1.0 - std::exp(-n / (sr * 2.0));   // AGC_RELEASE_TIME_SEC
+    a.smooth = 1.0 - std::exp(-n / (sr * 0.2));    // AGC_SMOOTH_TIME_SEC
+    agc_kernel<<<(unsigned) ((nst + 63) / 64), 64, 0, stream>>>(a);
+    ++launches;
+    CPQ_CUDA(cudaGetLastError());
+    EqArgs f = e;   // gain ramp + output stages + epilogue
+    f.assemble = 0;
+    f.nTail = 0;
+    f.outer = 0;
+    f.doEq = 0;
+    f.doGain = 1;
+    f.gainTab = agcTab.p;
+    f.gainBySeq = nch;
+    return launchEq(f);
 }
 
 cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar)
@@ -992,6 +1176,19 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) nSeq, cfg.workspace_bytes / std::max<size_t>(perSeq, 1)));
     }
     if (hostPlanar) chunk = std::max(1, std::min(chunk, (nSeq + 31) / 32));   // short pipeline fill/drain
+    if (doEq && (anyAgc || anyMs))
+    {
+        // AGC statistics and Mid/Side bands couple the channels of a stream: whole streams per chunk, scratch rows bounded
+        const int nch = cfg.n_channels;
+        if (anyMs) chunk = (int) std::min<size_t>((size_t) chunk, std::max<size_t>((size_t) nch, cfg.workspace_bytes / ((size_t) stride * sizeof(double))));
+        chunk = std::max(nch, chunk / nch * nch);
+        if (anyMs) CPQ_CUDA(msScratch.ensure((size_t) chunk * stride));
+        if (anyAgc)
+        {
+            CPQ_CUDA(sumsq.ensure((size_t) 2 * chunk * nCallbacks));
+            CPQ_CUDA(agcTab.ensure((size_t) (chunk / nch) * nCallbacks * 2));
+        }
+    }
     if (doConv)
         for (int li = 0; li < plan.numLayers; ++li)
         {
@@ -1047,6 +1244,8 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         a.eqc = eqc.p;
         a.sat = satDev.p;
         a.gainTab = (doEq && haveGainTab) ? gainTab.p : nullptr;
+        a.doGain = a.doEq;
+        a.bandSelect = (1u << CPQ_NUM_BANDS) - 1u;
         a.gainConst = gainConst.p;
         a.nCallbacks = nCallbacks;
         a.doEpilogue = doEpi ? 1 : 0;
@@ -1083,7 +1282,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             p.applyHeadroom = 0;
             p.doEpilogue = std::fabs(convInputTrim - 1.0) > 1e-12 ? 1 : 0;   // scaleBlockFallback(ptr, n, convolverInputTrimGain), :438-445
             p.makeup = convInputTrim;
-            cpq_status st = launchEq(p);
+            cpq_status st = runEq(p, s0, ns);
             if (st != CPQ_OK) return st;
         }
         if (doConv)
@@ -1214,13 +1413,14 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         if (eqFirst)
         {
             e.doEq = 0;
+            e.doGain = 0;
             e.gainTab = nullptr;
         }
         e.bandMask = bandMask.p ? bandMask.p + s0 : nullptr;
         e.setOfSeq = setOfSeq.p ? setOfSeq.p + s0 : nullptr;   // absolute set indices
         e.stateOut = stateOut.p + (size_t) s0 * CPQ_NUM_BANDS * 2;
         e.postStateOut = postMask ? postState.p + (size_t) s0 * kEqPostStages * 2 : nullptr;
-        cpq_status st = launchEq(e);
+        cpq_status st = runEq(e, s0, ns);
         if (st != CPQ_OK) return st;
         if (doDither)
         {
@@ -1411,12 +1611,12 @@ cpq_status cpq_set_eq(cpq_handle h, int stream, const cpq_svf_coeffs coeffs[CPQ_
     }
     for (int b = 0; b < CPQ_NUM_BANDS; ++b)
     {
-        if (active[b] && chan_mode[b] >= 3)
+        if (active[b] && (chan_mode[b] < 0 || chan_mode[b] > 4)) return CPQ_ERR_INVALID;
+        if (active[b] && chan_mode[b] >= 3 && h->cfg.n_channels != 2)
         {
-            h->setError("set_eq: Mid/Side channel modes take the reference's other process() path (Processing.cpp:1037-1044)");
+            h->setError("set_eq: Mid/Side bands need a stereo handle (n_channels = 2)");
             return CPQ_ERR_UNSUPPORTED;
         }
-        if (active[b] && chan_mode[b] < 0) return CPQ_ERR_INVALID;
     }
     if (!(saturation >= 0.0) || !std::isfinite(total_gain_lin)) return CPQ_ERR_INVALID;
     cpq::EqSet& e = h->eqSets[h->cfg.shared_eq ? 0 : (size_t) stream];
@@ -1429,6 +1629,42 @@ cpq_status cpq_set_eq(cpq_handle h, int stream, const cpq_svf_coeffs coeffs[CPQ_
     e.events.clear();
     h->eqDirty = true;
     return CPQ_OK;
+}
+
+cpq_status cpq_set_eq_mode(cpq_handle h, int stream, int filter_structure, int agc_enabled, const uint8_t node_active[CPQ_NUM_BANDS])
+{
+    if (!h || filter_structure < 0 || filter_structure > 1) return CPQ_ERR_INVALID;
+    if (h->cfg.shared_eq ? (stream != -1 && stream != 0) : (stream < 0 || stream >= h->cfg.n_streams))
+    {
+        h->setError("set_eq_mode: stream out of range");
+        return CPQ_ERR_INVALID;
+    }
+    cpq::EqSet& e = h->eqSets[h->cfg.shared_eq ? 0 : (size_t) stream];
+    e.structure = filter_structure;
+    e.agc = agc_enabled ? 1 : 0;
+    e.hasNodeActive = node_active != nullptr;
+    if (node_active) std::memcpy(e.nodeActive, node_active, sizeof(e.nodeActive));
+    h->eqDirty = true;
+    return CPQ_OK;
+}
+
+cpq_status cpq_get_agc_state(cpq_handle h, int stream, double out[3])
+{
+    if (!h || !out || stream < 0 || stream >= h->cfg.n_streams) return CPQ_ERR_INVALID;
+    if (!h->anyAgc || !h->agcState.p) return CPQ_ERR_NOT_READY;
+    Engine* e = h;
+    auto setError = [&](const std::string& s) { e->setError(s); };
+    CPQ_CUDA(cudaSetDevice(e->cfg.device));
+    CPQ_CUDA(cudaMemcpy(out, e->agcState.p + (size_t) stream * 3, 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    return CPQ_OK;
+}
+
+int cpq_band_node_active(int type, float gain_db, int enabled, double sample_rate)
+{
+    // createBandNode, EQProcessor.Coefficients.cpp:27-58
+    if (!enabled || !(sample_rate > 0.0)) return 0;
+    if (type != 3 && type != 4 && std::fabs(gain_db) < 0.01f) return 0;
+    return 1;
 }
 
 cpq_status cpq_schedule_total_gain(cpq_handle h, int stream, int64_t at_callback, double new_gain_lin)

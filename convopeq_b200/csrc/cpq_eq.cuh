@@ -119,9 +119,16 @@ struct EqArgs
     unsigned postMask;      // bit i = post stage i enabled
     double* postStateOut;   // nullable [nSeq][kEqPostStages][2] final states of the output stages
     int finalClamp;         // scrub (non-finite or |x| >= 1e300 -> 0) + clamp to +-kOutputHeadroom after the headroom multiply
-    const double* gainTab;  // nullable [nSets][nCallbacks][2] (start, inc)
+    const double* gainTab;  // nullable [rows][nCallbacks][2] (start, inc); row = parameter set, or stream when gainBySeq
     const double* gainConst;// [nSets] settled total gain (used when gainTab == nullptr)
     int64_t nCallbacks;
+    int doGain;             // apply the total gain (Processing.cpp:1262-1274) / the AGC gain ramp (:441-444) in this launch
+    int gainBySeq;          // > 0: gainTab row = seq / gainBySeq (per-stream AGC table built by agc_kernel)
+    unsigned bandSelect;    // bands this launch may run (a band sequence split around Mid/Side bands runs in several launches)
+    // AGC block statistics (calculateRMS, Processing.cpp:21-52): per-callback sums of squares of the EQ input / of the band
+    // output before the gain, [nSeq][nCallbacks]; nullable
+    double* sumsqIn;
+    double* sumsqOut;
     // epilogue
     int doEpilogue;
     double makeup;
@@ -309,8 +316,10 @@ __device__ __forceinline__ void eq_pass2(double (&x)[kEqL], double& ic1, double&
 #define CPQ_EQ_MINBLOCKS (CPQ_EQ_L == 16 ? 3 : 2)
 #endif
 // POST = the launch runs output stages / the output clamp; the plain conv -> EQ -> gain launch carries none of that code.
-template <bool POST>
-__global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs a)
+// PAR  = FilterStructure::Parallel: every band filters the tile *input* and the differences are summed (a second block of
+//        registers per thread, hence one CTA per SM).   STATS = the launch accumulates the AGC block statistics.
+template <bool POST, bool PAR = false, bool STATS = false>
+__global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs a)
 {
     const unsigned postMask = POST ? a.postMask : 0u;
     extern __shared__ __align__(16) double eq_smem[];
@@ -332,9 +341,10 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
     if (run >= a.nRuns) return;
 
     double* io = a.io + (size_t) seq * a.ioStride;
-    const int set = a.doEq ? a.setOfSeq[seq] : 0;
+    const int set = (a.doEq || a.doGain) ? a.setOfSeq[seq] : 0;
     // stages this sequence runs: its active EQ bands (bits 0..19) and the enabled output stages (bits 20..23)
-    const unsigned mask = (a.doEq ? a.bandMask[seq] : 0u) | (postMask << CPQ_NUM_BANDS);
+    const unsigned bandBits = a.doEq ? a.bandMask[seq] : 0u;   // bits 0..19 bands, bit 31 = Parallel structure
+    const unsigned mask = (bandBits & a.bandSelect & ((1u << CPQ_NUM_BANDS) - 1u)) | (postMask << CPQ_NUM_BANDS);
     const int64_t t0 = (int64_t) run * kEqTile;
 
     if (a.doEq)
@@ -543,11 +553,25 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
     };
     unsigned hiIn = 0;   // max of |x|'s high word over the raw input
     loadBlock(hiIn);
+    // AGC block statistics: sum of squares per callback.  A thread's block never straddles a callback (block >= 64); the
+    // lanes of one callback are reduced by shuffles and one lane adds the partial sum (several warps share a callback
+    // only when block > 1024).
+    auto blockStats = [&](double* dst) {
+        double sq = 0.0;
+#pragma unroll
+        for (int j = 0; j < kEqL; ++j) sq = fma(x[j], x[j], sq);
+        const int lanesPerCb = min(32, (1 << a.blockLog2) / kEqL);
+        for (int o = 1; o < lanesPerCb; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const int64_t tb = w0 + (int64_t) lane * kEqL;
+        if ((lane & (lanesPerCb - 1)) == 0 && tb < a.T) atomicAdd(dst + (size_t) seq * a.nCallbacks + (tb >> a.blockLog2), sq);
+    };
+    if (STATS && a.sumsqIn) blockStats(a.sumsqIn);
 
     // gains the reference applies between the EQ bands and the output stages are applied in registers when such a stage
     // runs: total gain (Processing.cpp:1262-1274) before OutputFilter / DC blocker, makeup (DSPCoreDouble.cpp:465-469)
     // before the DC blocker; the store stage then skips them
-    const bool gainInReg = a.doEq && (postMask != 0u);
+    const bool gainInReg = a.doGain && (postMask != 0u);
+    const int gainRow = a.gainBySeq > 0 ? seq / a.gainBySeq : set;
     const bool makeupInReg = a.doEpilogue && ((postMask >> 3) & 1u);
     if (mask)
     {
@@ -656,7 +680,7 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                 if (a.gainTab)
                 {
                     const int64_t tb = w0 + (int64_t) lane * kEqL;   // a thread's block never straddles a callback (block >= 64)
-                    const double2 g = __ldg(reinterpret_cast<const double2*>(a.gainTab) + (size_t) set * a.nCallbacks + (tb >> a.blockLog2));
+                    const double2 g = __ldg(reinterpret_cast<const double2*>(a.gainTab) + (size_t) gainRow * a.nCallbacks + (tb >> a.blockLog2));
                     const int off0 = (int) tb & bmask;
 #pragma unroll
                     for (int j = 0; j < kEqL; ++j) x[j] *= fma((double) (off0 + j), g.y, g.x);
@@ -710,7 +734,72 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
         // ---- fast mode: bands in order until some lane leaves the regime where the reference's clamps are identities ----
         bool exactMode = a.doEq && __any_sync(0xffffffffu, hiIn >= 0x41cdcd65u);   // |x| >= 1e9 (or NaN/Inf) in the raw input
         int linked = -1;                                                            // last band whose link this warp has served
-        if (!exactMode)
+        if (PAR && (bandBits >> 31))
+        {
+            // Parallel structure: every band starts from the tile input (kept in shared memory), so the fast / exact decision
+            // is per band; acc follows the reference's two roundings per band, accum = (accum + work) - src (:1194-1197).
+            double acc[kEqL];
+#pragma unroll
+            for (int j = 0; j < kEqL; ++j) acc[j] = 0.0;
+            bool first = true;
+            for (int b = 0; b < CPQ_NUM_BANDS; ++b)
+            {
+                if (!((mask >> b) & 1u)) continue;
+                const double* __restrict__ bc = cst + b * kEqcStride;
+                unsigned dummy = 0;
+                if (!first) loadBlock(dummy);
+                first = false;
+                double ic1, ic2;
+                bandStart(b, bc, true, ic1, ic2);
+                const double s1 = ic1, s2 = ic2;
+                unsigned hiMax = max((unsigned) __double2hiint(ic1) & 0x7fffffffu, (unsigned) __double2hiint(ic2) & 0x7fffffffu);
+                bool rare = exactMode | (hiMax >= 0x426d1a94u) | (bc[6] != 0.0);
+                if (!__any_sync(0xffffffffu, rare))
+                {
+                    hiMax = 0;
+                    const int kind = (int) bc[7];
+                    if (sat > 0.0)
+                    {
+                        if (kind == 1) eq_pass2<true, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                        else if (kind == 2) eq_pass2<true, 2>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                        else eq_pass2<true, 0>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                    }
+                    else
+                    {
+                        if (kind == 1) eq_pass2<false, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                        else if (kind == 2) eq_pass2<false, 2>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                        else eq_pass2<false, 0>(x, ic1, ic2, bc, alpha, gamma, hiMax);
+                    }
+                    rare = hiMax >= thrHi;
+                }
+                if (__any_sync(0xffffffffu, rare))
+                {
+                    loadBlock(dummy);
+                    ic1 = s1;
+                    ic2 = s2;
+                    if (eq_pass2_exact(x, ic1, ic2, bc, sat)) atomicExch(a.fault, 1u);
+                }
+#pragma unroll
+                for (int j = 0; j < kEqL / 2; ++j)
+                {
+                    const double2 v = reinterpret_cast<const double2*>(myStash)[j];
+                    acc[2 * j] = __dadd_rn(__dadd_rn(acc[2 * j], x[2 * j]), -v.x);
+                    acc[2 * j + 1] = __dadd_rn(__dadd_rn(acc[2 * j + 1], x[2 * j + 1]), -v.y);
+                }
+            }
+            if (mask & ((1u << CPQ_NUM_BANDS) - 1u))
+            {
+#pragma unroll
+                for (int j = 0; j < kEqL / 2; ++j)
+                {
+                    const double2 v = reinterpret_cast<const double2*>(myStash)[j];
+                    x[2 * j] = v.x + acc[2 * j];
+                    x[2 * j + 1] = v.y + acc[2 * j + 1];
+                }
+            }
+            exactMode = false;
+        }
+        else if (!exactMode)
         {
             for (int b = 0; b < CPQ_NUM_BANDS; ++b)
             {
@@ -773,6 +862,7 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
             }
         }
     }
+    if (STATS && a.sumsqOut) blockStats(a.sumsqOut);   // a STATS launch never runs output stages: x is the band output
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < kEqL / 2; ++j) reinterpret_cast<double2*>(myStash)[j] = make_double2(x[2 * j], x[2 * j + 1]);
@@ -782,7 +872,7 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
     // optional output scrub + hard clamp of processOutputDouble (DSPCoreDouble.cpp:665-691, 712-737) ----
     {
         double* op = io + w0;
-        const bool mulG = a.doEq && !gainInReg, mulM = a.doEpilogue && !makeupInReg, mulH = a.doEpilogue && a.applyHeadroom;
+        const bool mulG = a.doGain && !gainInReg, mulM = a.doEpilogue && !makeupInReg, mulH = a.doEpilogue && a.applyHeadroom;
         const bool clampOut = POST && a.doEpilogue && a.finalClamp;
         const double gconst = (mulG && !a.gainTab) ? __ldg(a.gainConst + set) : 1.0;
         const double mk = a.makeup;
@@ -805,7 +895,7 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                 const int64_t t = w0 + i;
                 const int64_t c = t >> a.blockLog2;
                 const int off = (int) t & bmask;
-                const double2 g = __ldg(reinterpret_cast<const double2*>(a.gainTab) + (size_t) set * a.nCallbacks + c);
+                const double2 g = __ldg(reinterpret_cast<const double2*>(a.gainTab) + (size_t) gainRow * a.nCallbacks + c);
                 v *= fma((double) off, g.y, g.x);
                 op[i] = finish(v);
             }
@@ -839,6 +929,112 @@ __global__ void __launch_bounds__(kEqThreads, CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs
                     op[i] = finish(v);
                 }
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// AGC (EQProcessor::processAGC + calculateAGCGain, EQProcessor.Processing.cpp:343-445): a block-rate scalar recurrence
+// per stream over the callback statistics the EQ launch left behind; one thread per stream writes the gain ramp
+// (start, increment) of every callback, which a second eq_kernel launch applies (applyGainRamp, :441-444).
+// ---------------------------------------------------------------------------------------------
+struct AgcArgs
+{
+    const double* sumsqIn;    // [nStreams * nch][nCallbacks]
+    const double* sumsqOut;
+    double* gainTab;          // [nStreams][nCallbacks][2]
+    const uint8_t* agcOn;     // [nStreams]; streams without AGC get their settled total gain
+    const double* gainConst;  // [nSets]
+    const int* setOfSeq;      // [nStreams * nch]
+    double* stateOut;         // nullable [nStreams][3] envIn, envOut, gain after the last callback
+    int nStreams, nch;
+    int64_t nCallbacks;
+    double blockN;            // samples per callback
+    double attack, release, smooth;   // 1 - exp(-n / (sr tau)) (EQProcessor.Core.cpp:776-785)
+};
+
+__global__ void agc_kernel(AgcArgs a)
+{
+    const int st = blockIdx.x * blockDim.x + threadIdx.x;
+    if (st >= a.nStreams) return;
+    double2* tab = reinterpret_cast<double2*>(a.gainTab) + (size_t) st * a.nCallbacks;
+    if (!a.agcOn[st])
+    {
+        const double g = a.gainConst[a.setOfSeq[(size_t) st * a.nch]];
+        for (int64_t c = 0; c < a.nCallbacks; ++c) tab[c] = make_double2(g, 0.0);
+        return;
+    }
+    double envIn = 0.0, envOut = 0.0, cur = 1.0;   // rtAgc*Shadow after the reset prepareToPlay requests
+    for (int64_t c = 0; c < a.nCallbacks; ++c)
+    {
+        double inRms = 0.0, outRms = 0.0;
+        for (int ch = 0; ch < a.nch; ++ch)
+        {
+            const size_t q = ((size_t) st * a.nch + ch) * a.nCallbacks + c;
+            inRms = fmax(inRms, __dsqrt_rn(__ddiv_rn(a.sumsqIn[q], a.blockN)));     // NaN-free maximum like `if (rms > max)`
+            outRms = fmax(outRms, __dsqrt_rn(__ddiv_rn(a.sumsqOut[q], a.blockN)));
+        }
+        if (!(fabs(inRms) <= 1000.0)) inRms = 1000.0;    // non-finite or > MAX_ENV_VALUE
+        if (!(fabs(outRms) <= 1000.0)) outRms = 1000.0;
+        const double aIn = inRms > envIn ? a.attack : a.release, aOut = outRms > envOut ? a.attack : a.release;
+        envIn = __dadd_rn(__dmul_rn(envIn, 1.0 - aIn), __dmul_rn(inRms, aIn));
+        envOut = __dadd_rn(__dmul_rn(envOut, 1.0 - aOut), __dmul_rn(outRms, aOut));
+        if (envIn < 1.0e-20) envIn = 0.0;
+        if (envOut < 1.0e-20) envOut = 0.0;
+        double target = 1.0;
+        if (!(envOut < 1.0e-6))
+        {
+            const double ratio = __ddiv_rn(envIn, envOut);
+            if (!(ratio > 1.0 / 1.059 && ratio < 1.059)) target = fmin(fmax(ratio, (double) 0.06f), (double) 16.0f);
+        }
+        const double next = __dadd_rn(__dmul_rn(cur, 1.0 - a.smooth), __dmul_rn(target, a.smooth));
+        tab[c] = make_double2(cur, __ddiv_rn(next - cur, a.blockN));
+        cur = next;
+    }
+    if (a.stateOut)
+    {
+        a.stateOut[(size_t) st * 3] = envIn;
+        a.stateOut[(size_t) st * 3 + 1] = envOut;
+        a.stateOut[(size_t) st * 3 + 2] = cur;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mid/Side bands (node path, EQProcessor.Processing.cpp:690-740): encode (L+R)/2, (L-R)/2 of the listed streams into a
+// scratch pair of rows, run the band on one of them with eq_kernel, decode L = M+S, R = M-S.
+// ---------------------------------------------------------------------------------------------
+struct MsArgs
+{
+    double* io;          // this chunk's [nSeq][ioStride]
+    int64_t ioStride;
+    double* ms;          // [2 * nStreams][ioStride]: Mid row, Side row per listed stream
+    const int* streams;  // [nStreams] absolute stream indices
+    int streamBase;      // first stream of the chunk
+    int64_t T;
+};
+
+template <bool ENCODE>
+__global__ void ms_kernel(MsArgs a)
+{
+    const int st = a.streams[blockIdx.y] - a.streamBase;
+    double2* L = reinterpret_cast<double2*>(a.io + (size_t) (2 * st) * a.ioStride);
+    double2* R = reinterpret_cast<double2*>(a.io + (size_t) (2 * st + 1) * a.ioStride);
+    double2* M = reinterpret_cast<double2*>(a.ms + (size_t) (2 * blockIdx.y) * a.ioStride);
+    double2* S = reinterpret_cast<double2*>(a.ms + (size_t) (2 * blockIdx.y + 1) * a.ioStride);
+    const int64_t n2 = a.T / 2;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t) gridDim.x * blockDim.x)
+    {
+        if (ENCODE)
+        {
+            const double2 l = L[i], r = R[i];
+            M[i] = make_double2((l.x + r.x) * 0.5, (l.y + r.y) * 0.5);
+            S[i] = make_double2((l.x - r.x) * 0.5, (l.y - r.y) * 0.5);
+        }
+        else
+        {
+            const double2 m = M[i], sd = S[i];
+            L[i] = make_double2(m.x + sd.x, m.y + sd.y);
+            R[i] = make_double2(m.x - sd.x, m.y - sd.y);
         }
     }
 }

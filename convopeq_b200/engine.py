@@ -99,9 +99,11 @@ class ConvoPeqEngine:
         self._check(self.lib.cpq_set_impulse(self.h, stream, channel, ir.ctypes.data_as(_dp), ir.size, scale,
                                              C.byref(spec) if spec is not None else None))
 
-    def set_eq(self, stream: int, bands: Sequence[Band], saturation: float = 0.2, total_gain_db: float = 0.0):
+    def set_eq(self, stream: int, bands: Sequence[Band], saturation: float = 0.2, total_gain_db: float = 0.0,
+               structure: int = 0, agc: bool = False):
         """createCoeffCache(params) + EQParameters (ProcessingCache.cpp:56-96). saturation/total gain are float in
-        the reference and promoted to double before use."""
+        the reference and promoted to double before use.  structure: 0 Serial, 1 Parallel
+        (EQParameters::filterStructure); agc: EQParameters::agcEnabled.  Band channel modes 3/4 are Mid/Side."""
         assert len(bands) == capi.NUM_BANDS
         co = (capi.SvfCoeffs * capi.NUM_BANDS)()
         act = (C.c_uint8 * capi.NUM_BANDS)()
@@ -114,6 +116,15 @@ class ConvoPeqEngine:
         sat = float(np.float32(saturation))
         gain = self.lib.cpq_db_to_gain(C.c_float(total_gain_db))
         self._check(self.lib.cpq_set_eq(self.h, stream, co, act, mode, sat, gain))
+        node = (C.c_uint8 * capi.NUM_BANDS)(*[self.lib.cpq_band_node_active(int(b.type), C.c_float(b.gain), int(bool(b.enabled)),
+                                                                             self.sample_rate) for b in bands])
+        self._check(self.lib.cpq_set_eq_mode(self.h, stream, int(structure), int(agc), node))
+
+    def agc_state(self, stream: int) -> np.ndarray:
+        """(envIn, envOut, gain) of the stream's AGC after the last process call."""
+        out = np.zeros(3)
+        self._check(self.lib.cpq_get_agc_state(self.h, stream, out.ctypes.data_as(_dp)))
+        return out
 
     def set_eq_raw(self, stream: int, coeffs: np.ndarray, active: Sequence[int], modes: Sequence[int],
                    saturation: float, total_gain_lin: float):

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define CPQ_ABI_VERSION 2
+#define CPQ_ABI_VERSION 3
 #define CPQ_NUM_BANDS 20        /* EQProcessor::NUM_BANDS, eqprocessor/EQProcessor.h:153 */
 #define CPQ_MAX_LAYERS 3        /* MKLNonUniformConvolver::kNumLayers, MKLNonUniformConvolver.h:391 */
 #define CPQ_NS_ORDER 12         /* PsychoacousticDither::NS_ORDER, PsychoacousticDither.h:60 */
@@ -36,7 +36,7 @@ typedef enum cpq_status
     CPQ_ERR_NOT_READY = 2,    /* process before every stream-channel has an impulse / EQ */
     CPQ_ERR_CUDA = 3,         /* CUDA runtime error or no usable device */
     CPQ_ERR_OOM = 4,
-    CPQ_ERR_UNSUPPORTED = 5,  /* reference feature outside the hot path (M/S modes, AGC, parallel EQ ...) */
+    CPQ_ERR_UNSUPPORTED = 5,  /* reference feature outside the hot path (Mid/Side bands inside the Parallel structure ...) */
     CPQ_ERR_GEOMETRY = 6      /* stream-channels of one handle must share the layer geometry */
 } cpq_status;
 
@@ -146,13 +146,26 @@ cpq_status cpq_set_impulse(cpq_handle h, int stream, int channel, const double* 
                            const cpq_filter_spec* spec);
 
 /* EQCoeffCache + EQParameters as consumed by EQProcessor::process(block, params, cache)
- * (eqprocessor/EQProcessor.h:121-138, ProcessingCache.cpp:56-96, Processing.cpp:1019-1276), Serial structure,
- * AGC off.  chan_mode: 0 Stereo, 1 Left, 2 Right (>= 3 = Mid/Side -> CPQ_ERR_UNSUPPORTED).
+ * (eqprocessor/EQProcessor.h:121-138, ProcessingCache.cpp:56-96, Processing.cpp:1019-1276); Serial structure and AGC
+ * off unless cpq_set_eq_mode says otherwise.  chan_mode: 0 Stereo, 1 Left, 2 Right, 3 Mid, 4 Side (EQChannelMode,
+ * EQProcessor.h:55-62; an active Mid/Side band sends the reference to its node path, Processing.cpp:1037-1044, 690-740,
+ * which this library reproduces for the Serial structure on stereo handles).
  * saturation is the already-promoted double, e.g. (double)0.2f.  total_gain_lin is
  * Decibels::decibelsToGain((double)totalGainDb) (settled LinearRamp). stream = -1 with cfg.shared_eq. */
 cpq_status cpq_set_eq(cpq_handle h, int stream, const cpq_svf_coeffs coeffs[CPQ_NUM_BANDS],
                       const uint8_t active[CPQ_NUM_BANDS], const int32_t chan_mode[CPQ_NUM_BANDS],
                       double saturation, double total_gain_lin);
+
+/* EQParameters::filterStructure (0 Serial, 1 Parallel: Processing.cpp:1132-1228, out = src + sum_b (band_b(src) - src))
+ * and EQParameters::agcEnabled (block-rate AGC, Processing.cpp:1119-1131 + processAGC :343-445; replaces the total-gain
+ * ramp).  node_active (nullable): BandNode::active per band as createBandNode computes it (EQProcessor.Coefficients.cpp:
+ * 27-58, see cpq_band_node_active) -- the band set of the node path, consulted only when an active band is Mid/Side;
+ * NULL = same as cpq_set_eq's `active`.  Call after cpq_set_eq (which does not change these).  stream = -1 with shared_eq. */
+cpq_status cpq_set_eq_mode(cpq_handle h, int stream, int filter_structure, int agc_enabled, const uint8_t node_active[CPQ_NUM_BANDS]);
+/* Host-only: createBandNode's activity rule: enabled, sample rate > 0, and not a shelf / peaking band with |gain| < 0.01 dB. */
+int cpq_band_node_active(int type, float gain_db, int enabled, double sample_rate);
+/* rtAgcEnvInputShadow, rtAgcEnvOutputShadow, rtAgcCurrentGainShadow after the last cpq_process (AGC streams). */
+cpq_status cpq_get_agc_state(cpq_handle h, int stream, double out[3]);
 
 /* EQProcessor::setTotalGain at a callback boundary (EQProcessor.Parameters.cpp:109): from callback index
  * `at_callback` of the next cpq_process the total gain ramps to new_gain_lin over 50 ms

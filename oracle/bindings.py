@@ -56,6 +56,16 @@ class EqBand(C.Structure):
                 ("enabled", C.c_int), ("type", C.c_int), ("channel_mode", C.c_int)]
 
 
+def node_active(b: "EqBand", sr: float) -> bool:
+    """BandNode::active (createBandNode, EQProcessor.Coefficients.cpp:27-58): enabled, a prepared sample rate, and not a
+    shelf/peaking band within 0.01 dB of flat.  Only the node path (taken when an active band is Mid/Side) uses it."""
+    if not b.enabled or not sr > 0:
+        return False
+    if b.type not in (3, 4) and abs(np.float32(b.gain_db)) < np.float32(0.01):
+        return False
+    return True
+
+
 def build(verbose: bool = False) -> None:
     """Compile the checkers (oracle always; _ref only where the reference tree is mounted)."""
     env = dict(os.environ, CONVOPEQ_REF=REFERENCE_ROOT)
@@ -218,6 +228,10 @@ class Oracle(_Base):
         L.cpqo_eq_destroy.argtypes = [C.c_void_p]
         L.cpqo_eq_set_band.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_int]
         L.cpqo_eq_set_saturation.argtypes = [C.c_void_p, C.c_float]
+        L.cpqo_eq_set_node_active.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.cpqo_eq_set_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.cpqo_eq_get_agc.argtypes = [C.c_void_p, _dp]
+        L.cpqo_eq_get_ms_state.argtypes = [C.c_void_p, _dp]
         L.cpqo_eq_set_total_gain.argtypes = [C.c_void_p, C.c_float]
         L.cpqo_eq_process.argtypes = [C.c_void_p, _dp, _dp, C.c_long, C.c_int]
         L.cpqo_eq_get_state.argtypes = [C.c_void_p, _dp]
@@ -236,7 +250,7 @@ class Oracle(_Base):
 
     def eq_run(self, bands: Sequence[EqBand], xl: np.ndarray, xr: Optional[np.ndarray], sr: float, block: int,
                saturation: float = 0.2, total_gain_db: float = 0.0, gain_change_db: Optional[float] = None,
-               gain_change_at: int = 0):
+               gain_change_at: int = 0, structure: int = 0, agc: bool = False):
         """createCoeffCache + process(block, params, cache) over the signal; returns (L, R, state[2][20][2])."""
         L = self.lib
         e = L.cpqo_eq_create(sr, C.c_float(total_gain_db))
@@ -245,7 +259,9 @@ class Oracle(_Base):
                 active = bool(b.enabled) and sr > 0
                 co = self.eq_design(b.type, b.frequency, b.gain_db, b.q, sr) if active else np.zeros(6)
                 L.cpqo_eq_set_band(e, i, _p(co), int(active), int(b.channel_mode))
+                L.cpqo_eq_set_node_active(e, i, int(node_active(b, sr)))
             L.cpqo_eq_set_saturation(e, C.c_float(saturation))
+            L.cpqo_eq_set_mode(e, int(structure), int(agc))
             l = np.ascontiguousarray(xl, dtype=np.float64).copy()
             r = None if xr is None else np.ascontiguousarray(xr, dtype=np.float64).copy()
             if gain_change_db is None:
@@ -305,12 +321,12 @@ class Ref(_Base):
                                                C.byref(spec) if spec is not None else None)
 
     def eq_run(self, bands: Sequence[EqBand], xl, xr, sr, block, saturation=0.2, total_gain_db=0.0,
-               gain_change_db=None, gain_change_at=0):
+               gain_change_db=None, gain_change_at=0, structure=0, agc=False):
         L = self.lib
         e = L.cpqref_eq_create(sr, max(block, 1), C.c_float(total_gain_db))
         try:
             arr = (EqBand * 20)(*bands)
-            if not L.cpqref_eq_set_params(e, arr, C.c_float(saturation), 0, 0):
+            if not L.cpqref_eq_set_params(e, arr, C.c_float(saturation), int(structure), int(agc)):
                 raise RuntimeError("createCoeffCache failed")
             l = np.ascontiguousarray(xl, dtype=np.float64).copy()
             r = None if xr is None else np.ascontiguousarray(xr, dtype=np.float64).copy()
@@ -330,7 +346,8 @@ class Ref(_Base):
         return l, r, st
 
 
-def _chain_run(self, irs, bands, x, sr, block, spec, saturation, total_gain_db, makeup, outer, do_eq, do_epilogue):
+def _chain_run(self, irs, bands, x, sr, block, spec, saturation, total_gain_db, makeup, outer, do_eq, do_epilogue,
+               structure=0, agc=False):
     """One stream through the per-callback ConvolverThenEQ chain (conv -> wet gain -> EQ -> makeup*headroom).
     irs: (irL, irR) or None; x: [2, T] (copied). Returns y [2, T]. Releases the GIL inside the C call."""
     L = self.lib
@@ -348,14 +365,16 @@ def _chain_run(self, irs, bands, x, sr, block, spec, saturation, total_gain_db, 
             if pre == "cpqref_":
                 eq = L.cpqref_eq_create(sr, block, C.c_float(total_gain_db))
                 arr = (EqBand * 20)(*bands)
-                L.cpqref_eq_set_params(eq, arr, C.c_float(saturation), 0, 0)
+                L.cpqref_eq_set_params(eq, arr, C.c_float(saturation), int(structure), int(agc))
             else:
                 eq = L.cpqo_eq_create(sr, C.c_float(total_gain_db))
                 for i, b in enumerate(bands):
                     active = bool(b.enabled) and sr > 0
                     co = self.eq_design(b.type, b.frequency, b.gain_db, b.q, sr) if active else np.zeros(6)
                     L.cpqo_eq_set_band(eq, i, _p(co), int(active), int(b.channel_mode))
+                    L.cpqo_eq_set_node_active(eq, i, int(node_active(b, sr)))
                 L.cpqo_eq_set_saturation(eq, C.c_float(saturation))
+                L.cpqo_eq_set_mode(eq, int(structure), int(agc))
         self._f("chain_process")(nucs[0], nucs[1], eq, _p(y[0]), _p(y[1]), y.shape[1], block, int(outer),
                                  float(makeup), int(do_epilogue))
     finally:
@@ -404,8 +423,9 @@ def _chain_free(self, handles):
 def _install_chain():
     for cls in (Oracle, Ref):
         def chain_run(self, irs, bands, x, sr, block, spec=None, saturation=0.2, total_gain_db=0.0, makeup=1.0,
-                      outer=True, do_eq=True, do_epilogue=True):
-            return _chain_run(self, irs, bands, x, sr, block, spec, saturation, total_gain_db, makeup, outer, do_eq, do_epilogue)
+                      outer=True, do_eq=True, do_epilogue=True, structure=0, agc=False):
+            return _chain_run(self, irs, bands, x, sr, block, spec, saturation, total_gain_db, makeup, outer, do_eq, do_epilogue,
+                              structure, agc)
         cls.chain_run = chain_run
         cls.chain_prepare = _chain_prepare
         cls.chain_process_prepared = _chain_process_prepared

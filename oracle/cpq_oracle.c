@@ -862,12 +862,17 @@ typedef struct { double current, target, step; int remaining, total_steps; } cpq
 typedef struct
 {
     double coeffs[20][6];
-    int active[20];
-    int mode[20];        /* 0 Stereo, 1 Left, 2 Right */
+    int active[20];      /* EQCoeffCache::bandActive = enabled && sr > 0 (ProcessingCache.cpp:56-96) */
+    int node_active[20]; /* BandNode::active = enabled && !(0-dB skip) (Coefficients.cpp:27-58); used by the node path only */
+    int mode[20];        /* 0 Stereo, 1 Left, 2 Right, 3 Mid, 4 Side */
     double saturation;   /* already promoted: (double)(float) */
-    double state[2][20][2];
+    double state[4][20][2]; /* filterState[kFilterChannels]: L, R, Mid, Side (EQProcessor.h:155,637) */
     cpqo_ramp gain;
     double total_gain_target; /* linear; EQProcessor::totalGainTarget */
+    int structure;       /* 0 Serial, 1 Parallel */
+    int agc;             /* EQParameters::agcEnabled */
+    double sr;
+    double agc_env_in, agc_env_out, agc_gain; /* rtAgcEnvInputShadow / OutputShadow / CurrentGainShadow */
 } cpqo_eq;
 
 cpqo_eq* cpqo_eq_create(double sr, float total_gain_db)
@@ -878,6 +883,8 @@ cpqo_eq* cpqo_eq_create(double sr, float total_gain_db)
     e->gain.current = e->gain.target = cpqo_db_to_gain(total_gain_db);
     e->total_gain_target = e->gain.current;
     e->saturation = (double) 0.2f;
+    e->sr = sr;
+    e->agc_gain = 1.0;
     return e;
 }
 void cpqo_eq_destroy(cpqo_eq* e) { free(e); }
@@ -886,36 +893,186 @@ void cpqo_eq_set_band(cpqo_eq* e, int band, const double* coeffs6, int active, i
 {
     memcpy(e->coeffs[band], coeffs6, sizeof(double) * 6);
     e->active[band] = active;
+    e->node_active[band] = active;
     e->mode[band] = mode;
 }
+/* BandNode::active for the node path; differs from `active` by createBandNode's 0-dB skip (Coefficients.cpp:49-53) */
+void cpqo_eq_set_node_active(cpqo_eq* e, int band, int node_active) { e->node_active[band] = node_active; }
+/* EQParameters::filterStructure (0 Serial, 1 Parallel) and agcEnabled */
+void cpqo_eq_set_mode(cpqo_eq* e, int structure, int agc) { e->structure = structure; e->agc = agc; }
+void cpqo_eq_get_agc(const cpqo_eq* e, double* out3) { out3[0] = e->agc_env_in; out3[1] = e->agc_env_out; out3[2] = e->agc_gain; }
+void cpqo_eq_get_ms_state(const cpqo_eq* e, double* out) { memcpy(out, e->state[2], sizeof(double) * 2 * 20 * 2); }
 void cpqo_eq_set_saturation(cpqo_eq* e, float sat) { e->saturation = (double) sat; }
 void cpqo_eq_set_total_gain(cpqo_eq* e, float db) { e->total_gain_target = cpqo_db_to_gain(db); }
-void cpqo_eq_get_state(const cpqo_eq* e, double* out) { memcpy(out, e->state, sizeof(e->state)); }
+void cpqo_eq_get_state(const cpqo_eq* e, double* out) { memcpy(out, e->state, sizeof(double) * 2 * 20 * 2); }
 
-/* EQProcessor::process(block, params, cache), Serial structure, AGC off: Processing.cpp:1019-1276.
- * Returns 0 on success, -1 if a band uses a Mid/Side mode (reference falls back to another path). */
+/* calculateRMS, Processing.cpp:21-52 (AVX2 build: four FMA lanes, lane sum left to right, scalar remainder) */
+static double cpqo_rms(const double* d, int n)
+{
+    if (!d || n <= 0) return 0.0;
+    double lane[4] = { 0.0, 0.0, 0.0, 0.0 };
+    int i = 0;
+    const int vend = n / 4 * 4;
+    for (; i < vend; i += 4)
+        for (int k = 0; k < 4; ++k) lane[k] = fma(d[i + k], d[i + k], lane[k]);
+    double sum = lane[0] + lane[1] + lane[2] + lane[3];
+    for (; i < n; ++i) sum += d[i] * d[i];
+    return sqrt(sum / (double) n);
+}
+
+/* processAGC + calculateAGCGain, Processing.cpp:343-445; block-rate coefficients 1 - exp(-n / (sr * tau)) from the
+ * tables prepareToPlay fills (EQProcessor.Core.cpp:776-785; AGC_ATTACK/RELEASE/SMOOTH_TIME_SEC = 0.2 / 2.0 / 0.2) */
+static void cpqo_agc(cpqo_eq* e, double* L, double* R, int n, double input_rms)
+{
+    const double dn = (double) n;
+    const double att = 1.0 - exp(-dn / (e->sr * 0.2)), rel = 1.0 - exp(-dn / (e->sr * 2.0)), smo = 1.0 - exp(-dn / (e->sr * 0.2));
+    double in_rms = input_rms, out_rms = 0.0;
+    const double rl = cpqo_rms(L, n);
+    if (rl > out_rms) out_rms = rl;
+    if (R)
+    {
+        const double rr = cpqo_rms(R, n);
+        if (rr > out_rms) out_rms = rr;
+    }
+    if (!isfinite(in_rms) || in_rms > 1000.0) in_rms = 1000.0;
+    if (!isfinite(out_rms) || out_rms > 1000.0) out_rms = 1000.0;
+    double env_in = e->agc_env_in, env_out = e->agc_env_out, cur = e->agc_gain;
+    if (!isfinite(env_in)) env_in = 0.0;
+    if (!isfinite(env_out)) env_out = 0.0;
+    if (!isfinite(cur)) cur = 1.0;
+    const double a_in = in_rms > env_in ? att : rel, a_out = out_rms > env_out ? att : rel;
+    env_in = env_in * (1.0 - a_in) + in_rms * a_in;
+    env_out = env_out * (1.0 - a_out) + out_rms * a_out;
+    if (env_in < 1.0e-20) env_in = 0.0;
+    if (env_out < 1.0e-20) env_out = 0.0;
+    double target = 1.0;
+    if (!(env_out < 1e-6))
+    {
+        const double ratio = env_in / env_out;
+        if (ratio > 1.0 / 1.059 && ratio < 1.059) target = 1.0;
+        else
+        {
+            const double lo = (double) 0.06f, hi = (double) 16.0f;   /* jlimit(AGC_MIN_GAIN, AGC_MAX_GAIN, ratio) */
+            target = ratio < lo ? lo : (hi < ratio ? hi : ratio);
+        }
+    }
+    const double next = cur * (1.0 - smo) + target * smo;
+    e->agc_env_in = env_in;
+    e->agc_env_out = env_out;
+    e->agc_gain = next;
+    const double inc = (next - cur) / dn;
+    for (int i = 0; i < n; ++i)
+    {
+        const double g = cur + (double) i * inc;
+        L[i] *= g;
+        if (R) R[i] *= g;
+    }
+}
+
+/* EQProcessor::process(block, params, cache): Processing.cpp:1019-1276 (Serial :1231-1253, Parallel :1132-1228, AGC
+ * :1119-1131 + processAGC, total-gain ramp :1262-1274).  When an active band is Mid/Side the reference falls back to
+ * the node path process(block) (:1037-1044 -> :484-1017): BandNode::active decides which bands run, Mid/Side bands are
+ * encoded / processed / decoded per band (:690-740).  Returns 0 on success, -1 for Parallel together with Mid/Side
+ * (the node path's structure cross-fade state is outside this restatement). */
 int cpqo_eq_process(cpqo_eq* e, double* L, double* R, long total, int block)
 {
     const int nch = R ? 2 : 1;
+    int node_path = 0;
     for (int b = 0; b < 20; ++b)
-        if (e->active[b] && e->mode[b] >= 3) return -1;
+        if (e->active[b] && e->mode[b] >= 3) node_path = 1;
+    if (node_path && e->structure != 0) return -1;
+    const int* on = node_path ? e->node_active : e->active;
+    double* src = (double*) malloc(sizeof(double) * (size_t) block * 6);
+    double *srcL = src, *srcR = src + block, *workL = src + 2 * block, *workR = src + 3 * block, *accL = src + 4 * block,
+           *accR = src + 5 * block;
     for (long pos = 0; pos < total; pos += block)
     {
         const int n = (int) ((total - pos) < block ? (total - pos) : block);
-        for (int b = 0; b < 20; ++b)
+        double* bl = L + pos;
+        double* br = R ? R + pos : NULL;
+        double input_rms = 0.0;
+        if (e->agc)
         {
-            if (!e->active[b]) continue;
-            const int mode = e->mode[b];
-            if (mode == 0 && nch >= 2)
+            const double r0 = cpqo_rms(bl, n);
+            if (r0 > input_rms) input_rms = r0;
+            if (br)
             {
-                cpqo_band(L + pos, n, e->coeffs[b], e->state[0][b], e->saturation, 1);
-                cpqo_band(R + pos, n, e->coeffs[b], e->state[1][b], e->saturation, 1);
+                const double r1 = cpqo_rms(br, n);
+                if (r1 > input_rms) input_rms = r1;
             }
-            else
+        }
+        if (e->structure == 1)
+        {
+            memcpy(srcL, bl, sizeof(double) * (size_t) n);
+            if (br) memcpy(srcR, br, sizeof(double) * (size_t) n);
+            memset(accL, 0, sizeof(double) * (size_t) n);
+            memset(accR, 0, sizeof(double) * (size_t) n);
+            for (int b = 0; b < 20; ++b)
             {
-                if (mode == 0 || mode == 1) cpqo_band(L + pos, n, e->coeffs[b], e->state[0][b], e->saturation, 0);
-                if ((mode == 0 || mode == 2) && nch > 1) cpqo_band(R + pos, n, e->coeffs[b], e->state[1][b], e->saturation, 0);
+                if (!on[b]) continue;
+                const int mode = e->mode[b];
+                const int doL = (mode == 0 || mode == 1), doR = (mode == 0 || mode == 2) && nch > 1;
+                const int sv = (mode == 0 && nch >= 2);
+                if (doL)
+                {
+                    memcpy(workL, srcL, sizeof(double) * (size_t) n);
+                    cpqo_band(workL, n, e->coeffs[b], e->state[0][b], e->saturation, sv);
+                    for (int i = 0; i < n; ++i) { accL[i] = accL[i] + workL[i]; accL[i] = accL[i] - srcL[i]; }
+                }
+                if (doR)
+                {
+                    memcpy(workR, srcR, sizeof(double) * (size_t) n);
+                    cpqo_band(workR, n, e->coeffs[b], e->state[1][b], e->saturation, sv);
+                    for (int i = 0; i < n; ++i) { accR[i] = accR[i] + workR[i]; accR[i] = accR[i] - srcR[i]; }
+                }
             }
+            for (int i = 0; i < n; ++i) bl[i] = srcL[i] + accL[i];
+            if (br)
+                for (int i = 0; i < n; ++i) br[i] = srcR[i] + accR[i];
+        }
+        else
+        {
+            for (int b = 0; b < 20; ++b)
+            {
+                if (!on[b]) continue;
+                const int mode = e->mode[b];
+                if (mode == 0 && nch >= 2)
+                {
+                    cpqo_band(bl, n, e->coeffs[b], e->state[0][b], e->saturation, 1);
+                    cpqo_band(br, n, e->coeffs[b], e->state[1][b], e->saturation, 1);
+                }
+                else if (mode == 3 || mode == 4)
+                {
+                    if (nch < 2)
+                    {
+                        if (mode == 3) cpqo_band(bl, n, e->coeffs[b], e->state[2][b], e->saturation, 0);   /* Mono -> Mid */
+                        else memset(bl, 0, sizeof(double) * (size_t) n);                                    /* Mono -> Side = 0 */
+                        continue;
+                    }
+                    for (int i = 0; i < n; ++i)
+                    {
+                        workL[i] = (bl[i] + br[i]) * 0.5;   /* msWork[0..n) = Mid */
+                        workR[i] = (bl[i] - br[i]) * 0.5;   /* msWork[n..2n) = Side */
+                    }
+                    if (mode == 3) cpqo_band(workL, n, e->coeffs[b], e->state[2][b], e->saturation, 0);
+                    else cpqo_band(workR, n, e->coeffs[b], e->state[3][b], e->saturation, 0);
+                    for (int i = 0; i < n; ++i)
+                    {
+                        bl[i] = workL[i] + workR[i];
+                        br[i] = workL[i] - workR[i];
+                    }
+                }
+                else
+                {
+                    if (mode == 0 || mode == 1) cpqo_band(bl, n, e->coeffs[b], e->state[0][b], e->saturation, 0);
+                    if ((mode == 0 || mode == 2) && nch > 1) cpqo_band(br, n, e->coeffs[b], e->state[1][b], e->saturation, 0);
+                }
+            }
+        }
+        if (e->agc)
+        {
+            cpqo_agc(e, bl, br, n, input_rms);
+            continue;
         }
         /* total gain ramp, :1262-1274 + applyGainRamp_AVX2 :279-337 (gain(i) = start + i*inc) */
         cpqo_ramp* r = &e->gain;
@@ -939,6 +1096,7 @@ int cpqo_eq_process(cpqo_eq* e, double* L, double* R, long total, int block)
             for (int i = 0; i < n; ++i) d[i] *= start + (double) i * inc;
         }
     }
+    free(src);
     return 0;
 }
 

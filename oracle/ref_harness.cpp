@@ -176,10 +176,36 @@ void* cpqref_eq_create(double sr, int max_block, float total_gain_db)
     p.parallelWorkBuffer = convo::makeAlignedArray<double>((size_t) channelRequired);
     p.parallelAccumBuffer = convo::makeAlignedArray<double>((size_t) channelRequired);
     p.parallelBufferCapacity = channelRequired;
+    p.msWorkBuffer = convo::makeAlignedArray<double>((size_t) channelRequired);   // prepareToPlay: Mid/Side scratch of the node path
+    // AGC block-rate coefficients (EQProcessor.Core.cpp:744-792)
+    p.agcAttackCoeffTable = convo::makeAlignedArray<double>((size_t) max_block + 1);
+    p.agcReleaseCoeffTable = convo::makeAlignedArray<double>((size_t) max_block + 1);
+    p.agcSmoothCoeffTable = convo::makeAlignedArray<double>((size_t) max_block + 1);
+    p.agcCoeffTableCapacity = max_block + 1;
+    p.agcAttackCoeff.store(std::exp(-1.0 / (sr * EQProcessor::AGC_ATTACK_TIME_SEC)));
+    p.agcReleaseCoeff.store(std::exp(-1.0 / (sr * EQProcessor::AGC_RELEASE_TIME_SEC)));
+    p.agcSmoothCoeff.store(std::exp(-1.0 / (sr * EQProcessor::AGC_SMOOTH_TIME_SEC)));
+    for (int i = 0; i <= max_block; ++i)
+    {
+        const double n = static_cast<double>(i);
+        p.agcAttackCoeffTable[i] = 1.0 - std::exp(-n / (sr * EQProcessor::AGC_ATTACK_TIME_SEC));
+        p.agcReleaseCoeffTable[i] = 1.0 - std::exp(-n / (sr * EQProcessor::AGC_RELEASE_TIME_SEC));
+        p.agcSmoothCoeffTable[i] = 1.0 - std::exp(-n / (sr * EQProcessor::AGC_SMOOTH_TIME_SEC));
+    }
+    p.rtAgcCurrentGainShadow.store(1.0);
+    p.rtAgcEnvInputShadow.store(0.0);
+    p.rtAgcEnvOutputShadow.store(0.0);
     return e;
 }
 
-void cpqref_eq_destroy(void* h) { delete static_cast<RefEq*>(h); }
+void cpqref_eq_destroy(void* h)
+{
+    auto* e = static_cast<RefEq*>(h);
+    if (!e) return;
+    delete e->proc.exchangeCurrentState(nullptr);
+    for (int i = 0; i < 20; ++i) delete e->proc.exchangeBandNode(i, nullptr);
+    delete e;
+}
 
 int cpqref_eq_set_params(void* h, const cpqref_eq_band* bands /*[20]*/, float saturation, int structure, int agc)
 {
@@ -198,6 +224,25 @@ int cpqref_eq_set_params(void* h, const cpqref_eq_band* bands /*[20]*/, float sa
     e->params.filterStructure = structure;
     e->params.agcEnabled = agc != 0;
     e->cache.reset(EQProcessor::createCoeffCache(e->params, e->sr, e->maxBlock, 1));
+    // The node path (process(block), which process(block, params, cache) falls back to for Mid/Side bands,
+    // Processing.cpp:1037-1044) reads the published EQState and the per-band BandNodes (createBandNode,
+    // EQProcessor.Coefficients.cpp:27-58, incl. its 0-dB skip): publish both the way setBand*/prepareToPlay would.
+    auto* st = new EQProcessor::EQState();
+    for (int i = 0; i < 20; ++i)
+    {
+        st->bands[(size_t) i].frequency = bands[i].frequency;
+        st->bands[(size_t) i].gain = bands[i].gain_db;
+        st->bands[(size_t) i].q = bands[i].q;
+        st->bands[(size_t) i].enabled = bands[i].enabled != 0;
+        st->bandTypes[(size_t) i] = static_cast<EQBandType>(bands[i].type);
+        st->bandChannelModes[(size_t) i] = static_cast<EQChannelMode>(bands[i].channel_mode);
+    }
+    st->agcEnabled = agc != 0;
+    st->nonlinearSaturation = saturation;
+    st->filterStructure = structure;
+    delete e->proc.exchangeCurrentState(st);
+    for (int i = 0; i < 20; ++i) delete e->proc.exchangeBandNode(i, e->proc.createBandNode(i, *st));
+    e->proc.rtActiveStructureShadow.store(static_cast<EQProcessor::FilterStructure>(structure));
     return e->cache ? 1 : 0;
 }
 

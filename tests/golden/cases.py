@@ -28,6 +28,14 @@ EQ_CASES = {
     "stress_q20": dict(sr=48000.0, block=512, T=16384, bands=dict(seed=7, stress=True)),
     "modes_types": dict(sr=96000.0, block=256, T=8192, bands=dict(seed=8, modes=[i % 3 for i in range(20)], types=[i % 5 for i in range(20)])),
     "gain_ramp": dict(sr=48000.0, block=512, T=16384, bands=dict(seed=7), kw=dict(total_gain_db=0.0, gain_change_db=-6.0, gain_change_at=512 * 8)),
+    # Parallel structure, block-rate AGC, Mid/Side bands (node path, incl. createBandNode's 0-dB skip)
+    "parallel": dict(sr=48000.0, block=512, T=16384, bands=dict(seed=7), kw=dict(structure=1)),
+    "parallel_modes": dict(sr=96000.0, block=256, T=8192, bands=dict(seed=8, modes=[i % 3 for i in range(20)], types=[i % 5 for i in range(20)]),
+                           kw=dict(structure=1, saturation=0.0)),
+    "agc": dict(sr=48000.0, block=512, T=32768, bands=dict(seed=7), kw=dict(agc=True), amp=3.0),
+    "agc_parallel_b64": dict(sr=44100.0, block=64, T=16384, bands=dict(seed=9), kw=dict(agc=True, structure=1), amp=0.02),
+    "mid_side": dict(sr=48000.0, block=512, T=16384, bands=dict(seed=7, modes=[0, 3, 4, 1, 2] * 4, flat=[5, 6, 7])),
+    "mid_side_agc": dict(sr=48000.0, block=1024, T=16384, bands=dict(seed=10, modes=[3, 4] * 10), kw=dict(agc=True)),
 }
 
 CHAIN_CASES = {
@@ -63,6 +71,9 @@ def conv_inputs(c):
 def eq_inputs(c):
     bands = signals.band_params(**c["bands"])
     xl, xr = signals.log_sweep(c["T"], c["sr"])
+    if "amp" in c:   # decorrelated channels at another level (AGC, Mid/Side)
+        xl = xl * (2.0 * c["amp"]) + signals.noise(c["T"], 77, 0.05 * c["amp"])
+        xr = xr * c["amp"]
     return bands, xl, xr
 
 

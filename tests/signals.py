@@ -37,7 +37,7 @@ def synth_ir(n: int, seed: int) -> np.ndarray:
     return g.standard_normal(n) / np.sqrt(n) * np.exp(-np.arange(n) / (n / 6.0))
 
 
-def band_params(seed: int, stress: bool = False, modes=None, types=None, enabled=None):
+def band_params(seed: int, stress: bool = False, modes=None, types=None, enabled=None, flat=None):
     """20 bands at DEFAULT_FREQS: band 0 LowShelf, 1..18 Peaking, 19 HighShelf; gains U(-6,6) dB, Q U(0.5,4).
     stress: Q = 20, +-24 dB alternating. Returns list of dicts."""
     g = np.random.default_rng(seed)
@@ -51,6 +51,8 @@ def band_params(seed: int, stress: bool = False, modes=None, types=None, enabled
         if stress:
             gain = 24.0 if i % 2 == 0 else -24.0
             q = 20.0
+        if flat is not None and i in flat:
+            gain = 0.004 * (1 if i % 2 else -1)   # inside createBandNode's 0.01 dB skip window (node path only)
         out.append(dict(frequency=DEFAULT_FREQS[i], gain=gain, q=q, enabled=True if enabled is None else bool(enabled[i]),
                         type=t, channel_mode=0 if modes is None else modes[i]))
     return out

@@ -127,6 +127,71 @@ def test_eq_matches_reference(checker, name, bkw, kw, T):
     assert np.abs(state - wstate).max() <= 1e-9
 
 
+EQ_MODE_CASES = [
+    ("parallel", dict(seed=7), dict(structure=1)),
+    ("parallel_sat0_lr", dict(seed=8, modes=[i % 3 for i in range(20)]), dict(structure=1, saturation=0.0)),
+    ("parallel_stress", dict(seed=7, stress=True), dict(structure=1)),
+    ("agc", dict(seed=7), dict(agc=True)),
+    ("agc_parallel", dict(seed=11), dict(agc=True, structure=1)),
+    ("mid_side", dict(seed=7, modes=[0, 3, 4, 1, 2] * 4, flat=[5, 6, 7]), dict()),
+    ("mid_side_all", dict(seed=12, modes=[3, 4] * 10), dict(saturation=0.0)),
+    ("mid_side_agc", dict(seed=10, modes=[4, 0, 3, 0] * 5), dict(agc=True)),
+]
+
+
+@pytest.mark.parametrize("name,bkw,kw", EQ_MODE_CASES)
+@pytest.mark.parametrize("block,T", [(512, 512 * 50), (64, 64 * 300), (2048, 2048 * 13)])
+def test_eq_modes_match_reference(checker, name, bkw, kw, block, T):
+    """Parallel structure (Processing.cpp:1132-1228), AGC (:343-445), Mid/Side bands (:690-740)."""
+    sr = 48000.0
+    params = signals.band_params(**bkw)
+    xl, xr = signals.log_sweep(T, sr)
+    xl = 1.7 * xl + signals.noise(T, 5, 0.2)      # decorrelated, different levels: Mid != Side != 0, AGC has work to do
+    xr = 0.4 * xr
+    eng = ConvoPeqEngine(1, 2, sr, block, T)
+    eng.set_eq(0, signals.to_band(params), kw.get("saturation", 0.2), 0.0, kw.get("structure", 0), kw.get("agc", False))
+    y = np.stack([xl, xr]).copy()
+    eng.process(y, capi.STAGE_EQ)
+    agc = eng.agc_state(0) if kw.get("agc") else None
+    eng.close()
+    wl, wr, _ = checker.eq_run(signals.to_eqband(params), xl, xr, sr, block, **kw)
+    scale = max(1.0, np.abs(wl).max(), np.abs(wr).max())
+    assert np.abs(y[0] - wl).max() <= TOL * scale and np.abs(y[1] - wr).max() <= TOL * scale
+    if agc is not None:
+        assert 0.06 <= agc[2] <= 16.0 and agc[2] != 1.0
+
+
+def test_eq_modes_batch_mixed_streams(checker):
+    """Several streams with different structures / AGC / Mid-Side settings in one handle, conv -> EQ -> epilogue, odd chunking."""
+    sr, block, T, ir_len = 48000.0, 512, 16384, 20000
+    settings = [dict(), dict(structure=1), dict(agc=True), dict(agc=True, structure=1), dict(), dict(agc=True), dict()]
+    bkws = [dict(seed=40), dict(seed=41), dict(seed=42, modes=[3, 0, 4, 1, 2] * 4), dict(seed=43), dict(seed=44, modes=[4] * 20),
+            dict(seed=45), dict(seed=46, modes=[0, 0, 3] + [0] * 17)]
+    n = len(settings)
+    # the third/fifth/seventh streams carry Mid/Side bands: together with a Parallel stream the handle is rejected
+    eng = ConvoPeqEngine(n, 2, sr, block, T, conv_boundary=capi.CONV_OUTER, workspace_bytes=3 * 2 * (T // block + 40) * 512 * 16 * 5)
+    x = np.stack([signals.noise(T, 500 + i, 0.3) for i in range(2 * n)])
+    irs = [signals.synth_ir(ir_len, 600 + i) for i in range(2 * n)]
+    for s in range(n):
+        for ch in range(2):
+            eng.set_impulse(s, ch, irs[2 * s + ch], 1.0, None)
+        eng.set_eq(s, signals.to_band(signals.band_params(**bkws[s])), 0.2, 0.0, settings[s].get("structure", 0), settings[s].get("agc", False))
+    eng.set_epilogue(1.1, 0)
+    y = x.copy()
+    with pytest.raises(capi.CpqError):
+        eng.process(y, capi.STAGE_ALL)
+    for s in (1, 3):   # make the Parallel streams Serial: now everything is supported
+        eng.set_eq(s, signals.to_band(signals.band_params(**bkws[s])), 0.2, 0.0, 0, settings[s].get("agc", False))
+        settings[s] = dict(settings[s], structure=0)
+    y = x.copy()
+    eng.process(y, capi.STAGE_ALL)
+    eng.close()
+    for s in range(n):
+        want = checker.chain_run((irs[2 * s], irs[2 * s + 1]), signals.to_eqband(signals.band_params(**bkws[s])), x[2 * s:2 * s + 2], sr, block,
+                                 None, makeup=1.1, **settings[s])
+        assert np.abs(y[2 * s:2 * s + 2] - want).max() <= TOL, s
+
+
 def test_eq_mono_stream(checker):
     sr, block, T = 48000.0, 512, 40960
     params = signals.band_params(seed=12, modes=[i % 3 for i in range(20)])
@@ -253,7 +318,8 @@ def test_eq_matches_golden(name):
     bands, xl, xr = eq_inputs(c)
     kw = c.get("kw", {})
     eng = ConvoPeqEngine(1, 2, c["sr"], c["block"], c["T"])
-    eng.set_eq(0, signals.to_band(bands), kw.get("saturation", 0.2), kw.get("total_gain_db", 0.0))
+    eng.set_eq(0, signals.to_band(bands), kw.get("saturation", 0.2), kw.get("total_gain_db", 0.0), kw.get("structure", 0),
+               kw.get("agc", False))
     if "gain_change_db" in kw:
         eng.schedule_total_gain(0, kw["gain_change_at"] // c["block"], kw["gain_change_db"])
     y = np.stack([xl, xr]).copy()
@@ -287,8 +353,14 @@ def test_error_paths_fail_loudly():
     with pytest.raises(capi.CpqError):
         eng.process(np.zeros((2, 1000)), capi.STAGE_EQ)   # T not a multiple of the block
     bands = signals.to_band(signals.band_params(1, modes=[3] * 20))
+    mono = ConvoPeqEngine(1, 1, 48000.0, 512, 4096)
     with pytest.raises(capi.CpqError) as e:
-        eng.set_eq(0, bands)                       # Mid/Side modes take the reference's other path
+        mono.set_eq(0, bands)                      # Mid/Side bands need both channels of a stream
+    assert e.value.status == capi.ERR_UNSUPPORTED
+    mono.close()
+    eng.set_eq(0, bands, structure=1)              # Mid/Side inside the Parallel structure: refused at process time
+    with pytest.raises(capi.CpqError) as e:
+        eng.process(np.zeros((2, 4096)), capi.STAGE_EQ)
     assert e.value.status == capi.ERR_UNSUPPORTED
     eng.set_impulse(0, 0, signals.synth_ir(4096, 1))
     with pytest.raises(capi.CpqError) as e:

@@ -63,6 +63,42 @@ def test_eq_restatement_equals_reference(oracle, ref, name, bkw, kw):
     assert np.abs(so - s_r).max() <= 1e-12 * scale
 
 
+@pytest.mark.parametrize("name,bkw,kw", [
+    ("parallel", dict(seed=7), dict(structure=1)),
+    ("parallel_lr_sat0", dict(seed=8, modes=[i % 3 for i in range(20)]), dict(structure=1, saturation=0.0)),
+    ("agc", dict(seed=7), dict(agc=True)),
+    ("agc_parallel", dict(seed=11), dict(agc=True, structure=1)),
+    ("mid_side", dict(seed=7, modes=[0, 3, 4, 1, 2] * 4, flat=[5, 6, 7]), {}),
+    ("mid_side_agc", dict(seed=10, modes=[3, 4] * 10), dict(agc=True)),
+])
+@pytest.mark.parametrize("block", [64, 512, 1000])
+def test_eq_modes_restatement_equals_reference(oracle, ref, name, bkw, kw, block):
+    """Parallel structure, AGC and Mid/Side bands of the restatement against the reference's own
+    process(block, params, cache) / process(block)."""
+    sr, T = 48000.0, 24000
+    bands = signals.to_eqband(signals.band_params(**bkw))
+    xl, xr = signals.log_sweep(T, sr)
+    xl = 1.7 * xl + signals.noise(T, 5, 0.2)
+    xr = 0.4 * xr
+    lo, ro, _ = oracle.eq_run(bands, xl, xr, sr, block, **kw)
+    lr, rr, _ = ref.eq_run(bands, xl, xr, sr, block, **kw)
+    scale = max(1.0, np.abs(lr).max())
+    assert np.abs(lo - lr).max() <= 1e-13 * scale and np.abs(ro - rr).max() <= 1e-13 * scale
+    assert np.abs(lr - xl).max() > 1e-3      # the EQ did something
+
+
+def test_node_path_skips_flat_bands(ref, oracle):
+    """A Mid/Side band switches the reference to BandNode::active, which drops shelf/peaking bands within 0.01 dB of flat
+    (EQProcessor.Coefficients.cpp:49-53) -- unlike EQCoeffCache::bandActive.  The outputs differ measurably."""
+    sr, T = 48000.0, 8192
+    xl, xr = signals.log_sweep(T, sr)
+    p_ms = signals.band_params(seed=7, modes=[3] + [0] * 19, flat=[5])
+    p_st = signals.band_params(seed=7, flat=[5])
+    for p in (p_ms, p_st):
+        a, b = oracle.eq_run(signals.to_eqband(p), xl, xr, sr, 512), ref.eq_run(signals.to_eqband(p), xl, xr, sr, 512)
+        assert np.abs(a[0] - b[0]).max() <= 1e-13 and np.abs(a[1] - b[1]).max() <= 1e-13
+
+
 def test_eq_is_block_size_independent(ref):
     """with a settled gain ramp the reference EQ output does not depend on the callback size."""
     sr, T = 48000.0, 9216
