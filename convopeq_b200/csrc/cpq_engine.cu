@@ -1218,7 +1218,9 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
     auto enqueueH2D = [&](size_t c) -> cudaError_t {
         const int s0 = (int) c * chunk, ns = std::min(chunk, nSeq - s0);
         cudaError_t e = cudaSuccess;
-        if (hostPitch > 0)
+        if (hostPitch == T && stride == T)   // both sides dense: one linear copy
+            e = cudaMemcpyAsync(dIo + (size_t) s0 * stride, hostPlanar[s0], (size_t) ns * T * sizeof(double), cudaMemcpyHostToDevice, sIn);
+        else if (hostPitch > 0)
             e = cudaMemcpy2DAsync(dIo + (size_t) s0 * stride, (size_t) stride * sizeof(double), hostPlanar[s0], (size_t) hostPitch * sizeof(double),
                                   (size_t) T * sizeof(double), (size_t) ns, cudaMemcpyHostToDevice, sIn);
         else
@@ -1444,7 +1446,9 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         {
             cudaStreamWaitEvent(sOut, ce[4], 0);
             if (c == 0) cudaEventRecord(evOutBegin, sOut);
-            if (hostPitch > 0)
+            if (hostPitch == T && stride == T)
+                CPQ_CUDA(cudaMemcpyAsync(hostPlanar[s0], dIo + (size_t) s0 * stride, (size_t) ns * T * sizeof(double), cudaMemcpyDeviceToHost, sOut));
+            else if (hostPitch > 0)
                 CPQ_CUDA(cudaMemcpy2DAsync(hostPlanar[s0], (size_t) hostPitch * sizeof(double), dIo + (size_t) s0 * stride, (size_t) stride * sizeof(double),
                                            (size_t) T * sizeof(double), (size_t) ns, cudaMemcpyDeviceToHost, sOut));
             else

@@ -232,6 +232,9 @@ __device__ __forceinline__ void mac_run(double2 (&acc)[kMacKT], const char* __re
     }
 }
 
+#ifndef CPQ_MAC_STAGE1
+#define CPQ_MAC_STAGE1 0   // one issuing lane per warp instead of eight: measured slower (MAC 18.6 vs 17.2 ms per step)
+#endif
 #ifndef CPQ_MAC_GAUSS
 #define CPQ_MAC_GAUSS 1
 #endif
@@ -281,6 +284,32 @@ __global__ void __launch_bounds__(kMacThreads, CPQ_MAC_MINBLOCKS) mac_kernel(Mac
         const int c0 = max(f0, 0), c1 = min(f1, a.K);
         const int nRows = max(c1 - c0, 0);
         if (tid == 0) mbar_arrive_expect_tx(bar, (unsigned) (nRows + (withH ? nq : 0)) * kMacRowBytes);
+#if CPQ_MAC_STAGE1
+        // one lane per warp issues the warp's share: rows c0 + [g*per, (g+1)*per), ring slot advanced with a wrap instead of
+        // a modulo per row (a divergent multi-lane issue costs an ELECT loop of eight instructions per copy)
+        if (ml == 0)
+        {
+            const int per = (nRows + kMacGroups - 1) / kMacGroups;
+            const int i0 = g * per, i1 = min(nRows, i0 + per);
+            if (i0 < i1)
+            {
+                int slot = (c0 + i0) % R;
+                const double2* src = X + (size_t) (c0 + i0) * a.P;
+                for (int i = i0; i < i1; ++i)
+                {
+                    bulk_g2s(ring + slot * kMacBins, src, kMacRowBytes, bar);
+                    src += a.P;
+                    if (++slot == R) slot = 0;
+                }
+            }
+            if (withH)
+            {
+                const int perH = (nq + kMacGroups - 1) / kMacGroups;
+                const int h1 = min(nq, (g + 1) * perH);
+                for (int i = g * perH; i < h1; ++i) bulk_g2s(Hs + i * kMacBins, H + (size_t) i * a.P, kMacRowBytes, bar);
+            }
+        }
+#else
         if (ml < 8)
         {
             for (int i = g * 8 + ml; i < nRows; i += 8 * kMacGroups)
@@ -293,6 +322,7 @@ __global__ void __launch_bounds__(kMacThreads, CPQ_MAC_MINBLOCKS) mac_kernel(Mac
         {
             for (int i = g * 8 + ml - 8; i < nq; i += 8 * kMacGroups) bulk_g2s(Hs + i * kMacBins, H + (size_t) i * a.P, kMacRowBytes, bar);
         }
+#endif
     };
 
     __syncthreads();   // mbarrier initialised

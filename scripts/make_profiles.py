@@ -40,7 +40,7 @@ doc = {"_source": f"{os.path.basename(rep)} ({tag}): dram__bytes_read.sum + dram
        "_channel_samples_per_launch": 118 * 480256,
        **{k: sum(v) / len(v) for k, v in fam.items()}, "_per_kernel": out}
 json.dump(doc, open(os.path.join(prof, "traffic.json"), "w"), indent=1)
-for kern, mangled in (("eq_kernel", "_ZN3cpq9eq_kernelILb0EEEvNS_6EqArgsE"), ("mac_kernel", "_ZN3cpq10mac_kernelENS_7MacArgsE")):
+for kern, mangled in (("eq_kernel", "_ZN3cpq9eq_kernelILb0ELb0ELb0EEEvNS_6EqArgsE"), ("mac_kernel", "_ZN3cpq10mac_kernelENS_7MacArgsE")):
     if kern not in fam: continue
     txt = run(py, os.path.join(root, "scripts", "ncu_stalls.py"), rep, kern, "0", "25")
     txt += "\n# per CUDA source line (needs the libcpq.so of the same build)\n" + run(py, os.path.join(root, "scripts", "ncu_lines.py"), rep, kern, mangled, "30")
