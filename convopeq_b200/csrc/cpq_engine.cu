@@ -651,7 +651,12 @@ static void buildScanTables(const long double A[4], const long double b[2], doub
         v[0] = n0; v[1] = n1;
     }
     long double AL[4] = { 1, 0, 0, 1 };
-    for (int i = 0; i < kEqL; ++i) matmul2(AL, A, AL);
+    for (int i = 0; i < kEqL; ++i)
+    {
+        if (i == kEqL / 2)
+            for (int k = 0; k < 4; ++k) out[kEqcMh + k] = (double) AL[k];   // A^(L/2): half-block step of the two-chain pass 2
+        matmul2(AL, A, AL);
+    }
     // Plo[j] = A^(L j), j < 8;  Phi[j] = A^(8L j), j < 4
     {
         long double M[4] = { 1, 0, 0, 1 };

@@ -66,7 +66,8 @@ constexpr int kEqcMs = kEqcW + 2 * kEqL;         // Ms[5][4]   A^(L*2^d), row-ma
 constexpr int kEqcPlo = kEqcMs + 20;             // Plo[8][4]  A^(L*j)
 constexpr int kEqcPhi = kEqcPlo + 32;            // Phi[4][4]  A^(8L*j)
 constexpr int kEqcMw = kEqcPhi + 16;             // A^(32L)    (one warp segment)
-constexpr int kEqcStride = kEqcMw + 4;           // doubles per band, staged in shared memory for all 20 bands
+constexpr int kEqcMh = kEqcMw + 4;               // A^(L/2)    (half a thread block: start state of the second pass-2 chain)
+constexpr int kEqcStride = kEqcMh + 4;           // doubles per band, staged in shared memory for all 20 bands
 
 constexpr int kEqSeg = 32 * kEqL;                // 512 samples per warp segment
 // Stages of the scan pipeline: the 20 EQ bands, then the linear output stages of DSPCore::processDouble --
@@ -312,6 +313,66 @@ __device__ __forceinline__ void eq_pass2(double (&x)[kEqL], double& ic1, double&
     }
 }
 
+// Pass 2 as two interleaved chains: samples [0, L/2) from the block's start state and [L/2, L) from the state half a block
+// later (A^(L/2) s + the first half's zero-state response, which pass 1 accumulates separately anyway).  One recurrence is
+// a chain of three dependent DFMAs per sample (8 cycles each); two independent chains per thread halve the time a warp
+// spends waiting on its own results (the kernel's dominant stall, profiles/r01h_stalls_eq_kernel.txt).
+template <bool SAT, int KIND>
+__device__ __forceinline__ void eq_pass2x2(double (&x)[kEqL], double sA1, double sA2, double sB1, double sB2, const double* __restrict__ bc,
+                                           double alpha, double gamma, unsigned& hiMax)
+{
+    const double a1 = bc[0], a2 = bc[1], a3 = bc[2], m0 = bc[3], m1 = bc[4], m2 = bc[5], g = bc[8], g2 = bc[9];
+    constexpr int H = kEqL / 2;
+    auto step = [&](double v0, double& ic1, double& ic2) -> double {
+        double out;
+        if (KIND == 1)
+        {
+            const double v1 = fma(a1, ic1, fma(-a2, ic2, a2 * v0));
+            out = fma(m1, v1, v0);
+            ic1 = fma(2.0, v1, -ic1);
+            ic2 = fma(g2, v1, ic2);
+        }
+        else if (KIND == 2)
+        {
+            const double v1 = fma(a1, ic1, fma(-a2, ic2, a2 * v0));
+            const double v2 = fma(g, v1, ic2);
+            out = fma(m0, v0, fma(m1, v1, m2 * v2));
+            ic1 = fma(2.0, v1, -ic1);
+            ic2 = fma(2.0, v2, -ic2);
+        }
+        else
+        {
+            const double v3 = v0 - ic2;
+            const double v1 = fma(a1, ic1, a2 * v3);
+            const double v2 = fma(a2, ic1, fma(a3, v3, ic2));
+            ic1 = fma(2.0, v1, -ic1);
+            ic2 = fma(2.0, v2, -ic2);
+            out = fma(m0, v0, fma(m1, v1, m2 * v2));
+        }
+        if (SAT)
+        {
+            const double d = fma(out, out, 3.0);
+            hiMax = max(hiMax, (unsigned) __double2hiint(d));
+            double r0;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+            const double e = fma(-d, r0, 1.0);
+            const double r = fma(r0, e, r0);
+            return out * fma(gamma, r, alpha);
+        }
+        hiMax = max(hiMax, (unsigned) __double2hiint(out) & 0x7fffffffu);
+        return out;
+    };
+#pragma unroll
+    for (int j = 0; j < H; ++j)
+    {
+        x[j] = step(x[j], sA1, sA2);
+        x[j + H] = step(x[j + H], sB1, sB2);
+    }
+}
+
+#ifndef CPQ_EQ_ILP2
+#define CPQ_EQ_ILP2 1
+#endif
 #ifndef CPQ_EQ_MINBLOCKS
 #define CPQ_EQ_MINBLOCKS (CPQ_EQ_L == 16 ? 3 : 2)
 #endif
@@ -583,8 +644,25 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
 
         // Everything of one band up to the start state of this thread's block.  `link`: take part in the chain (wait for
         // the mailbox, post the successor's); a replayed band finds its mailbox already filled and posts nothing.
+        double mid1 = 0.0, mid2 = 0.0;   // state half a block after (ic1, ic2): start of the second pass-2 chain
         auto bandStart = [&](int b, const double* __restrict__ bc, bool link, double& ic1, double& ic2) {
             // ---- pass 1: zero-state response of this thread's samples (four accumulation chains) ----
+#if CPQ_EQ_ILP2
+            // per half block, with the same 16 weights A^(L/2-1-j) b: c = A^(L/2) lo + hi
+            double lo1 = 0.0, lo2 = 0.0, c1 = 0.0, c2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < kEqL / 2; ++j)
+            {
+                const double2 w = reinterpret_cast<const double2*>(bc + kEqcW)[j + kEqL / 2];
+                lo1 = fma(w.x, x[j], lo1);
+                lo2 = fma(w.y, x[j], lo2);
+                c1 = fma(w.x, x[j + kEqL / 2], c1);
+                c2 = fma(w.y, x[j + kEqL / 2], c2);
+            }
+            const double2 mh0 = *reinterpret_cast<const double2*>(bc + kEqcMh), mh1 = *reinterpret_cast<const double2*>(bc + kEqcMh + 2);
+            c1 = fma(mh0.x, lo1, fma(mh0.y, lo2, c1));
+            c2 = fma(mh1.x, lo1, fma(mh1.y, lo2, c2));
+#else
             double c1 = 0.0, c2 = 0.0, d1 = 0.0, d2 = 0.0;
 #pragma unroll
             for (int j = 0; j < kEqL; j += 2)
@@ -598,6 +676,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
             }
             c1 += d1;
             c2 += d2;
+#endif
             // ---- warp inclusive scan of s -> A^L s + c ----
 #pragma unroll
             for (int d = 0; d < 5; ++d)
@@ -670,6 +749,10 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
             matvec2(bc + kEqcPhi + 4 * (lane >> 3), p1, p2, e1, e2);     // A^(8L (lane >> 3)) ... + e
             ic1 = p1;
             ic2 = p2;
+#if CPQ_EQ_ILP2
+            mid1 = fma(mh0.x, p1, fma(mh0.y, p2, lo1));
+            mid2 = fma(mh1.x, p1, fma(mh1.y, p2, lo2));
+#endif
             if (ownsFinal) storeFinal(b, ic1, ic2);
         };
 
@@ -758,6 +841,20 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                 {
                     hiMax = 0;
                     const int kind = (int) bc[7];
+#if CPQ_EQ_ILP2
+                    if (sat > 0.0)
+                    {
+                        if (kind == 1) eq_pass2x2<true, 1>(x, ic1, ic2, mid1, mid2, bc, alpha, gamma, hiMax);
+                        else if (kind == 2) eq_pass2x2<true, 2>(x, ic1, ic2, mid1, mid2, bc, alpha, gamma, hiMax);
+                        else eq_pass2x2<true, 0>(x, ic1, ic2, mid1, mid2, bc, alpha, gamma, hiMax);
+                    }
+                    else
+                    {
+                        if (kind == 1) eq_pass2x2<false, 1>(x, ic1, ic2, mid1, mid2, bc, alpha, gamma, hiMax);
+                        else if (kind == 2) eq_pass2x2<false, 2>(x, ic1, ic2, mid1, mid2, bc, alpha, gamma, hiMax);
+                        else eq_pass2x2<false, 0>(x, ic1, ic2, mid1, mid2, bc, alpha, gamma, hiMax);
+                    }
+#else
                     if (sat > 0.0)
                     {
                         if (kind == 1) eq_pass2<true, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
@@ -770,6 +867,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                         else if (kind == 2) eq_pass2<false, 2>(x, ic1, ic2, bc, alpha, gamma, hiMax);
                         else eq_pass2<false, 0>(x, ic1, ic2, bc, alpha, gamma, hiMax);
                     }
+#endif
                     rare = hiMax >= thrHi;
                 }
                 if (__any_sync(0xffffffffu, rare))
@@ -812,6 +910,20 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                 bool rare = (hiMax >= 0x426d1a94u) | (bc[6] != 0.0);   // |state| >= 1e12, or coefficients outside the fast path's contract
                 hiMax = 0;
                 const int kind = (int) bc[7];
+#if CPQ_EQ_ILP2
+                if (sat > 0.0)
+                {
+                    if (kind == 1) eq_pass2x2<true, 1>(x, ic1, ic2, mid1, mid2, bc, alpha, gamma, hiMax);
+                    else if (kind == 2) eq_pass2x2<true, 2>(x, ic1, ic2, mid1, mid2, bc, alpha, gamma, hiMax);
+                    else eq_pass2x2<true, 0>(x, ic1, ic2, mid1, mid2, bc, alpha, gamma, hiMax);
+                }
+                else
+                {
+                    if (kind == 1) eq_pass2x2<false, 1>(x, ic1, ic2, mid1, mid2, bc, alpha, gamma, hiMax);
+                    else if (kind == 2) eq_pass2x2<false, 2>(x, ic1, ic2, mid1, mid2, bc, alpha, gamma, hiMax);
+                    else eq_pass2x2<false, 0>(x, ic1, ic2, mid1, mid2, bc, alpha, gamma, hiMax);
+                }
+#else
                 if (sat > 0.0)
                 {
                     if (kind == 1) eq_pass2<true, 1>(x, ic1, ic2, bc, alpha, gamma, hiMax);
@@ -824,6 +936,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                     else if (kind == 2) eq_pass2<false, 2>(x, ic1, ic2, bc, alpha, gamma, hiMax);
                     else eq_pass2<false, 0>(x, ic1, ic2, bc, alpha, gamma, hiMax);
                 }
+#endif
                 rare |= hiMax >= thrHi;   // some |out| >= 4.5 (100 without saturation), or NaN
                 if (__any_sync(0xffffffffu, rare))
                 {
