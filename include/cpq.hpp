@@ -38,12 +38,14 @@ struct EQBandParams
     int channelMode = 0;  // 0 Stereo, 1 Left, 2 Right
 };
 
-// convo::EQParameters (src/core/EQParameters.h:23-49), Serial structure / AGC off are the only supported values
+// convo::EQParameters (src/core/EQParameters.h:23-49); band channelMode 0 Stereo, 1 Left, 2 Right, 3 Mid, 4 Side
 struct EQParameters
 {
     std::array<EQBandParams, CPQ_NUM_BANDS> bands {};
     float totalGainDb = 0.0f;
+    bool agcEnabled = false;
     float nonlinearSaturation = 0.2f;
+    int filterStructure = 0;   // 0 Serial, 1 Parallel
 
     EQParameters()
     {
@@ -180,15 +182,19 @@ private:
             cpq_svf_coeffs co[CPQ_NUM_BANDS] {};
             std::uint8_t active[CPQ_NUM_BANDS] {};
             std::int32_t mode[CPQ_NUM_BANDS] {};
+            std::uint8_t nodeActive[CPQ_NUM_BANDS] {};
             for (int b = 0; b < CPQ_NUM_BANDS; ++b)
             {
                 const EQBandParams& bp = eq_[s].bands[(size_t) b];
                 active[b] = (bp.enabled && cfg_.sample_rate > 0.0) ? 1 : 0;
+                nodeActive[b] = (std::uint8_t) cpq_band_node_active(bp.type, bp.gain, bp.enabled ? 1 : 0, cfg_.sample_rate);
                 mode[b] = bp.channelMode;
                 if (active[b] && cpq_design_band(bp.type, bp.frequency, bp.gain, bp.q, cfg_.sample_rate, &co[b]) != CPQ_OK) return ok(CPQ_ERR_INVALID);
             }
             const double sat = static_cast<double>(eq_[s].nonlinearSaturation);   // float -> double like Processing.cpp:1114
-            if (!ok(cpq_set_eq(h_, cfg_.shared_eq ? -1 : (int) s, co, active, mode, sat, cpq_db_to_gain(eq_[s].totalGainDb)))) return false;
+            const int st = cfg_.shared_eq ? -1 : (int) s;
+            if (!ok(cpq_set_eq(h_, st, co, active, mode, sat, cpq_db_to_gain(eq_[s].totalGainDb)))) return false;
+            if (!ok(cpq_set_eq_mode(h_, st, eq_[s].filterStructure, eq_[s].agcEnabled ? 1 : 0, nodeActive))) return false;
         }
         dirty_ = false;
         return true;
