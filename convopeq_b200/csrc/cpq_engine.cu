@@ -175,6 +175,9 @@ struct Engine
     cpq_status uploadPost();
     struct OutCfg { int filterEnabled = 0, convIsLast = 0, hc = 1, lc = 0, lp = 1; double dcCutoff = 0.0; int finalClamp = 0; } outCfg;
     double convInputTrim = 1.0;         // state.convolverInputTrimGain (EQThenConvolver order only)
+    double mix = 1.0;                   // (double) mixTarget of ConvolverProcessor::process (CPQ_CONV_OUTER only)
+    int dryDelay = 0;                   // latency-compensation delay of the dry path, samples
+    DevBuf<double> dryBuf;              // copy of the convolver input for the dry path (mix < 0.999)
     bool postDirty = true;
     unsigned postIdentity = 0;          // output-filter stages whose coefficients are the identity (skipped)
     DevBuf<double> postc, postState;
@@ -1261,9 +1264,19 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         a.postc = postc.p;
         a.postMask = postMask;
         a.finalClamp = (doEpi && outCfg.finalClamp && ditherBits <= 0) ? 1 : 0;   // with dither the dither kernel clamps
-        a.wetGain = equalPowerSin(1.0) * 1.0;   // CONVOLUTION_HEADROOM_GAIN = 1.0 (ConvolverProcessor.h:209)
+        a.wetGain = equalPowerSin(cfg.conv_boundary == CPQ_CONV_OUTER ? mix : 1.0) * 1.0;   // CONVOLUTION_HEADROOM_GAIN = 1.0 (ConvolverProcessor.h:209)
     };
     const bool deferredOuter = !doConv && outerPending;
+    // ConvolverProcessor::process with mix < 1 (Runtime.cpp:367-377): the dry path needs the convolver's input, kept in a
+    // copy because the L0 inverse transform overwrites io; mix <= 0.001 is the dry-only fast path (no convolution at all)
+    const bool outerMix = doConv && cfg.conv_boundary == CPQ_CONV_OUTER;
+    const bool needsDry = outerMix && mix < 0.999, dryOnly = outerMix && !(mix > 0.001);
+    if (needsDry && !fullRange)
+    {
+        setError("process: mix < 1 together with a partition range (the dry path belongs to the rank that owns the sum)");
+        return CPQ_ERR_UNSUPPORTED;
+    }
+    if (needsDry) CPQ_CUDA(dryBuf.ensure((size_t) chunk * stride));
     // ProcessingOrder::EQThenConvolver (DSPCoreDouble.cpp:415-451): EQ (with its total-gain ramp) on the raw input, the
     // convolver input trim, then the convolver; the final launch then only assembles the layers and runs the output stages
     const bool eqFirst = (stages & CPQ_ORDER_EQ_THEN_CONV) && doConv && doEq;
@@ -1292,7 +1305,10 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             cpq_status st = runEq(p, s0, ns);
             if (st != CPQ_OK) return st;
         }
-        if (doConv)
+        if (needsDry)
+            CPQ_CUDA(cudaMemcpy2DAsync(dryBuf.p, (size_t) stride * sizeof(double), ioC, (size_t) stride * sizeof(double), (size_t) T * sizeof(double),
+                                       (size_t) ns, cudaMemcpyDeviceToDevice, stream));
+        if (doConv && !dryOnly)
         {
             // ---- forward FFTs of every layer (all read the untouched input) ----
             for (int li = 0; li < plan.numLayers; ++li)
@@ -1396,7 +1412,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         fillEqCommon(e);
         e.io = ioC;
         e.nSeq = ns;
-        if (doConv)
+        if (doConv && !dryOnly)
         {
             e.assemble = 1;
             e.nTail = plan.numLayers - 1;
@@ -1427,6 +1443,38 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         e.setOfSeq = setOfSeq.p ? setOfSeq.p + s0 : nullptr;   // absolute set indices
         e.stateOut = stateOut.p + (size_t) s0 * CPQ_NUM_BANDS * 2;
         e.postStateOut = postMask ? postState.p + (size_t) s0 * kEqPostStages * 2 : nullptr;
+        if (needsDry)
+        {
+            // assembly + scrub + wet gain on their own, then the dry path, then the remaining stages without assembly
+            if (!dryOnly)
+            {
+                EqArgs w = e;
+                w.doEq = 0;
+                w.doGain = 0;
+                w.gainTab = nullptr;
+                w.postMask = 0;
+                w.postStateOut = nullptr;
+                w.doEpilogue = 0;
+                w.finalClamp = 0;
+                w.applyHeadroom = 0;
+                cpq_status stw = launchEq(w);
+                if (stw != CPQ_OK) return stw;
+            }
+            MixArgs m {};
+            m.io = ioC;
+            m.dry = dryBuf.p;
+            m.stride = stride;
+            m.T = T;
+            m.delay = dryDelay;
+            m.dryGain = equalPowerSin(1.0 - mix);
+            m.dryOnly = dryOnly ? 1 : 0;
+            mix_kernel<<<dim3((unsigned) std::min<int64_t>(256, (T + 255) / 256), (unsigned) ns), 256, 0, stream>>>(m);
+            ++launches;
+            CPQ_CUDA(cudaGetLastError());
+            e.assemble = 0;
+            e.nTail = 0;
+            e.outer = 0;
+        }
         cpq_status st = runEq(e, s0, ns);
         if (st != CPQ_OK) return st;
         if (doDither)
@@ -1704,6 +1752,44 @@ cpq_status cpq_set_output_filter(cpq_handle h, int enabled, int conv_is_last, in
     h->outCfg.lp = lp_mode;
     h->postDirty = true;
     return CPQ_OK;
+}
+
+cpq_status cpq_set_mix(cpq_handle h, float mix, int dry_delay_samples)
+{
+    if (!h || !(mix >= 0.0f && mix <= 1.0f) || dry_delay_samples < 0 || dry_delay_samples > 2097152 + 524288) return CPQ_ERR_INVALID;
+    h->mix = static_cast<double>(mix);
+    h->dryDelay = dry_delay_samples;
+    return CPQ_OK;
+}
+
+int cpq_ir_peak_latency(const double* ir_l, const double* ir_r, int len)
+{
+    // estimatePeakLatencySamples, convolver/ConvolverProcessor.LoaderThread.cpp:149-207
+    if (len <= 0 || (!ir_l && !ir_r)) return 0;
+    double maxCentroid = 0.0;
+    for (const double* d : { ir_l, ir_r })
+    {
+        if (!d) continue;
+        double total = 0.0;
+        for (int i = 0; i < len; ++i) total += d[i] * d[i];
+        if (total < 1e-12) continue;
+        double cum = 0.0;
+        int cutoff = len - 1;
+        for (int i = 0; i < len; ++i)
+        {
+            cum += d[i] * d[i];
+            if (cum >= total * 0.999) { cutoff = i; break; }
+        }
+        double sumE = 0.0, sumW = 0.0;
+        for (int i = 0; i <= cutoff; ++i)
+        {
+            const double e = d[i] * d[i];
+            sumE += e;
+            sumW += static_cast<double>(i) * e;
+        }
+        maxCentroid = std::max(maxCentroid, sumE > 0.0 ? sumW / sumE : 0.0);
+    }
+    return std::clamp(static_cast<int>(std::floor(maxCentroid + 0.5)), 0, len - 1);
 }
 
 cpq_status cpq_set_conv_input_trim(cpq_handle h, double gain)

@@ -1113,6 +1113,32 @@ __global__ void agc_kernel(AgcArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Dry path of ConvolverProcessor::process in its settled state (ConvolverProcessor.Runtime.cpp:551-568, 573-584, 675-677,
+// 748): io already holds scrub(wet) * wetGain (eq_kernel's load stage); add the input delayed by the latency-compensation
+// delay times equalPowerSin(1 - mix), or -- dry-only fast path, mix <= 0.001 -- replace io by the delayed input.
+// ---------------------------------------------------------------------------------------------
+struct MixArgs
+{
+    double* io;          // [nSeq][stride]
+    const double* dry;   // [nSeq][stride] copy of the convolver input
+    int64_t stride, T;
+    int delay;           // samples; the delay ring starts zeroed
+    double dryGain;
+    int dryOnly;
+};
+
+__global__ void mix_kernel(MixArgs a)
+{
+    double* io = a.io + (size_t) blockIdx.y * a.stride;
+    const double* dry = a.dry + (size_t) blockIdx.y * a.stride;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < a.T; i += (int64_t) gridDim.x * blockDim.x)
+    {
+        const double d = i >= a.delay ? dry[i - a.delay] : 0.0;
+        io[i] = a.dryOnly ? d : __dadd_rn(io[i], __dmul_rn(d, a.dryGain));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Mid/Side bands (node path, EQProcessor.Processing.cpp:690-740): encode (L+R)/2, (L-R)/2 of the listed streams into a
 // scratch pair of rows, run the band on one of them with eq_kernel, decode L = M+S, R = M-S.
 // ---------------------------------------------------------------------------------------------

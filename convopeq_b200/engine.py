@@ -157,6 +157,10 @@ class ConvoPeqEngine:
         """OutputFilter::process(block, convIsLast, hcMode, lcMode, lpMode) (OutputFilter.h:108-131); runs with STAGE_OUTPUT_FILTER."""
         self._check(self.lib.cpq_set_output_filter(self.h, int(enabled), int(conv_is_last), hc_mode, lc_mode, lp_mode))
 
+    def set_mix(self, mix: float, dry_delay_samples: int):
+        """ConvolverProcessor's dry/wet mix (float mixTarget) and the latency-compensation delay of its dry path."""
+        self._check(self.lib.cpq_set_mix(self.h, C.c_float(mix), int(dry_delay_samples)))
+
     def set_conv_input_trim(self, gain: float):
         """convolverInputTrimGain of the EQThenConvolver order (DSPCoreDouble.cpp:438-445)."""
         self._check(self.lib.cpq_set_conv_input_trim(self.h, gain))
@@ -205,6 +209,13 @@ class ConvoPeqEngine:
 
     def kernel_launch_count(self) -> int:
         return int(self.lib.cpq_kernel_launch_count(self.h))
+
+
+def ir_peak_latency(ir_l: np.ndarray, ir_r: Optional[np.ndarray] = None) -> int:
+    """LoaderThread::estimatePeakLatencySamples (host-only helper of the C ABI)."""
+    a = np.ascontiguousarray(ir_l, dtype=np.float64)
+    b = None if ir_r is None else np.ascontiguousarray(ir_r, dtype=np.float64)
+    return int(capi.load().cpq_ir_peak_latency(a.ctypes.data_as(_dp), b.ctypes.data_as(_dp) if b is not None else None, a.size))
 
 
 def plan_layout(ir_len: int, block_size: int, spec: Optional[capi.FilterSpec], n_callbacks: int):

@@ -194,6 +194,16 @@ cpq_status cpq_set_output_stage(cpq_handle h, double dc_cutoff_hz, int hard_clam
 /* state.convolverInputTrimGain: applied between the EQ and the convolver in the EQThenConvolver order when it differs from
  * 1 by more than 1e-12 (DSPCoreDouble.cpp:438-445). */
 cpq_status cpq_set_conv_input_trim(cpq_handle h, double gain);
+/* ConvolverProcessor::process with its smoothers settled (ConvolverProcessor.Runtime.cpp:367-377, 551-588, 675-677, 748;
+ * cfg.conv_boundary = CPQ_CONV_OUTER): out = scrub(wet) * equalPowerSin(mix) + dry * equalPowerSin(1 - mix), dry = the
+ * convolver's input delayed by dry_delay_samples (the reference's latency compensation: min(getLatency(), MAX_BLOCK_SIZE) +
+ * min(irLatency, MAX_IR_LATENCY), see cpq_latency and cpq_ir_peak_latency); mix >= 0.999 drops the dry path, mix <= 0.001 is the
+ * dry-only fast path (delayed input, no gain, no convolution).  mix is the float mixTarget.  Default 1.0 / 0. */
+cpq_status cpq_set_mix(cpq_handle h, float mix, int dry_delay_samples);
+/* Host-only: LoaderThread::estimatePeakLatencySamples (convolver/ConvolverProcessor.LoaderThread.cpp:149-207), the irLatency
+ * StereoConvolver::init receives as peakDelay: energy centroid of the first 99.9 % of the energy, maximum over channels
+ * (ir_r nullable), rounded, clamped to [0, len - 1]. */
+int cpq_ir_peak_latency(const double* ir_l, const double* ir_r, int len);
 /* Host-only: the three stages' normalised coefficients {b0,b1,b2,a1,a2} x 3 as OutputFilter::prepare computes them. */
 void cpq_output_filter_design(double sample_rate, int conv_is_last, int hc_mode, int lc_mode, int lp_mode, double out[15]);
 

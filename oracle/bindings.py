@@ -239,6 +239,9 @@ class Oracle(_Base):
         L.cpqo_epilogue.restype = None
         L.cpqo_outer_wet.argtypes = [_dp, C.c_long, C.c_double]
         L.cpqo_outer_wet.restype = None
+        L.cpqo_outer_mix.argtypes = [_dp, _dp, C.c_long, C.c_float, C.c_int]
+        L.cpqo_outer_mix.restype = None
+        L.cpqo_ir_peak_latency.argtypes = [_dp, _dp, C.c_int]
         L.cpqo_equal_power_sin.argtypes = [C.c_double]
         L.cpqo_equal_power_sin.restype = C.c_double
         L.cpqo_db_to_gain.argtypes = [C.c_float]
@@ -288,6 +291,18 @@ class Oracle(_Base):
         tmp = np.zeros_like(d)
         self.lib.cpqo_epilogue(_p(d), d.size, makeup_gain, sr, bit_depth, _p(uniforms), _p(z), _p(tmp))
         return d, tmp, z
+
+    def outer_mix(self, wet: np.ndarray, dry_in: np.ndarray, mix: float, delay: int) -> np.ndarray:
+        """ConvolverProcessor::process, settled: scrub(wet) * sin-gain(mix) + delayed dry * sin-gain(1 - mix) (restated, unpinned)."""
+        d = np.ascontiguousarray(wet, dtype=np.float64).copy()
+        x = np.ascontiguousarray(dry_in, dtype=np.float64)
+        self.lib.cpqo_outer_mix(_p(d), _p(x), d.size, C.c_float(mix), int(delay))
+        return d
+
+    def ir_peak_latency(self, ir_l: np.ndarray, ir_r: Optional[np.ndarray] = None) -> int:
+        a = np.ascontiguousarray(ir_l, dtype=np.float64)
+        b = None if ir_r is None else np.ascontiguousarray(ir_r, dtype=np.float64)
+        return int(self.lib.cpqo_ir_peak_latency(_p(a), _p(b), a.size))
 
     def outer_wet(self, x: np.ndarray, mix: float = 1.0) -> np.ndarray:
         d = np.ascontiguousarray(x, dtype=np.float64).copy()

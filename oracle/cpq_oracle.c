@@ -742,6 +742,67 @@ void cpqo_outer_wet(double* data, long n, double mix)
     }
 }
 
+/* ConvolverProcessor::process in its settled state (mix and latency smoothers at their targets, no bypass):
+ * ConvolverProcessor.Runtime.cpp:367-377 (needsConvolution = mix > 0.001, needsDrySignal = mix < 0.999), :551-568 (dry =
+ * input delayed by round(totalLatency) through a zero-initialised ring), :573-584 (dry-only fast path copies the dry signal,
+ * no gain), :675-677 + :748 (out = scrub(wet) * equalPowerSin(mix) * CONVOLUTION_HEADROOM_GAIN + dry * equalPowerSin(1 - mix),
+ * two products and one sum).  mix is the float mixTarget promoted to double.  PARITY UNPINNED: ConvolverProcessor needs
+ * the JUCE application to compile, so this part restates the source and is not checked against the running reference. */
+void cpqo_outer_mix(double* wet_io, const double* dry_in, long n, float mix, int delay)
+{
+    const double m = (double) mix;
+    const int needs_conv = m > 0.001, needs_dry = m < 0.999;
+    const double wg = cpqo_equal_power_sin(m) * 1.0;
+    const double dg = needs_dry ? cpqo_equal_power_sin(1.0 - m) : 0.0;
+    for (long i = 0; i < n; ++i)
+    {
+        const double dry = (i >= delay) ? dry_in[i - delay] : 0.0;
+        if (!needs_conv) { wet_io[i] = dry; continue; }
+        double v = wet_io[i];
+        if (!(isfinite(v) && fabs(v) < 1.0e300)) v = 0.0;
+        const double a = v * wg, b = dry * dg;
+        wet_io[i] = a + b;
+    }
+}
+
+/* estimatePeakLatencySamples, convolver/ConvolverProcessor.LoaderThread.cpp:149-207: energy centroid of the first 99.9 % of
+ * each channel's energy, maximum over channels, rounded half up and clamped to [0, len - 1].  This is the irLatency the
+ * dry path is delayed by (on top of the algorithm latency). */
+int cpqo_ir_peak_latency(const double* ir_l, const double* ir_r, int len)
+{
+    if (len <= 0) return 0;
+    double max_centroid = 0.0;
+    const double* chans[2] = { ir_l, ir_r };
+    for (int c = 0; c < 2; ++c)
+    {
+        const double* d = chans[c];
+        if (!d) continue;
+        double total = 0.0;
+        for (int i = 0; i < len; ++i) total += d[i] * d[i];
+        if (total < 1e-12) continue;
+        double cum = 0.0;
+        int cutoff = len - 1;
+        for (int i = 0; i < len; ++i)
+        {
+            cum += d[i] * d[i];
+            if (cum >= total * 0.999) { cutoff = i; break; }
+        }
+        double se = 0.0, sw = 0.0;
+        for (int i = 0; i <= cutoff; ++i)
+        {
+            const double e = d[i] * d[i];
+            se += e;
+            sw += (double) i * e;
+        }
+        const double centroid = se > 0.0 ? sw / se : 0.0;
+        if (centroid > max_centroid) max_centroid = centroid;
+    }
+    int lat = (int) floor(max_centroid + 0.5);
+    if (lat < 0) lat = 0;
+    if (lat > len - 1) lat = len - 1;
+    return lat;
+}
+
 /* ------------------------------------------------------------------------------------------
  * 20-band EQ.  eqprocessor/EQProcessor.{Coefficients,Processing,ProcessingCache}.cpp
  * ------------------------------------------------------------------------------------------ */

@@ -89,6 +89,37 @@ def test_outer_boundary_wet_gain(checker, oracle):
     assert np.abs(y[0] - want).max() <= TOL
 
 
+@pytest.mark.parametrize("mix", [1.0, 0.9995, 0.35, 0.0005, 0.0])
+def test_outer_dry_wet_mix(checker, oracle, mix):
+    """SURVEY 8f-4: ConvolverProcessor::process with mix < 1 (settled smoothers): wet * sin-gain(mix) + latency-compensated
+    dry * sin-gain(1 - mix); dry-only fast path at mix <= 0.001.  The outer boundary is restated only (parity unpinned)."""
+    from convopeq_b200.engine import ir_peak_latency
+    sr, block, T, ir_len = 48000.0, 512, 32768, 30000
+    irs = [signals.synth_ir(ir_len, 70), np.roll(signals.synth_ir(ir_len, 71), 333)]
+    x = np.stack([signals.noise(T, 72), signals.noise(T, 73)])
+    eng = ConvoPeqEngine(1, 2, sr, block, T, conv_boundary=capi.CONV_OUTER)
+    for ch in range(2):
+        eng.set_impulse(0, ch, irs[ch], 1.0, None)
+    delay = eng.latency() + ir_peak_latency(irs[0], irs[1])
+    assert delay == block + oracle.ir_peak_latency(irs[0], irs[1]) and delay > block
+    eng.set_mix(mix, delay)
+    eng.set_eq(0, signals.to_band(signals.band_params(74)))
+    y = x.copy()
+    eng.process(y, capi.STAGE_CONV)
+    z = x.copy()
+    eng.process(z, capi.STAGE_CONV | capi.STAGE_EQ)
+    eng.close()
+    w = []
+    for ch in range(2):
+        wet, _ = checker.nuc_run(irs[ch], x[ch], block)
+        w.append(oracle.outer_mix(wet, x[ch], mix, delay))
+        assert np.abs(y[ch] - w[ch]).max() <= TOL, (ch, mix)
+    if mix <= 0.001:
+        assert np.array_equal(y[0][delay:], x[0][:T - delay]) and not y[0][:delay].any()
+    wl, wr, _ = checker.eq_run(signals.to_eqband(signals.band_params(74)), w[0], w[1], sr, block)
+    assert np.abs(z[0] - wl).max() <= TOL and np.abs(z[1] - wr).max() <= TOL
+
+
 def test_ir_scale(checker):
     ir = signals.synth_ir(20000, 4)
     T = 16384

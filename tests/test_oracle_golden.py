@@ -113,3 +113,33 @@ def test_output_filter_is_block_size_independent_and_clamps(oracle):
     b = oracle.output_run(x, c["sr"], 64, **c["kw"])
     assert np.array_equal(a, b)
     assert np.abs(a).max() == 0.8912509381337456   # the 3x noise input overshoots: the hard clamp is exercised
+
+
+def test_outer_mix_restatement_and_peak_latency(oracle):
+    """ConvolverProcessor's settled dry/wet mix (restated, unpinned) against its formula, and estimatePeakLatencySamples of the
+    oracle against the product's host-only helper (no device needed)."""
+    from convopeq_b200.engine import ir_peak_latency
+    rng = np.random.default_rng(3)
+    wet, dry = rng.standard_normal(4096), rng.standard_normal(4096)
+    wet[7] = np.inf
+    wet[9] = 2e300
+    eps = lambda v: oracle.lib.cpqo_equal_power_sin(float(v))
+    for mix, delay in ((1.0, 0), (0.9995, 100), (0.5, 777), (0.0005, 64), (0.0, 512)):
+        got = oracle.outer_mix(wet, dry, mix, delay)
+        d = np.concatenate([np.zeros(delay), dry[:4096 - delay]])
+        m = float(np.float32(mix))
+        if m <= 0.001:
+            want = d
+        else:
+            w = np.where(np.isfinite(wet) & (np.abs(wet) < 1e300), wet, 0.0)
+            want = w * eps(m) + d * (eps(1.0 - m) if m < 0.999 else 0.0)
+        assert np.array_equal(got, want), mix
+    assert np.array_equal(oracle.outer_mix(wet, dry, 1.0, 0), oracle.outer_wet(wet, 1.0))
+    for n, seed in ((1000, 1), (65536, 2), (30000, 3)):
+        a, b = signals.synth_ir(n, seed), np.roll(signals.synth_ir(n, seed + 10), n // 7)
+        assert ir_peak_latency(a, b) == oracle.ir_peak_latency(a, b) > 0
+        assert ir_peak_latency(a) == oracle.ir_peak_latency(a)
+    assert ir_peak_latency(np.zeros(100)) == 0
+    one = np.zeros(500)
+    one[123] = 1.0
+    assert ir_peak_latency(one) == 123
