@@ -63,7 +63,7 @@ EXPORTS = [
     "cpq_process", "cpq_process_device", "cpq_set_partition_range", "cpq_total_partitions", "cpq_get_layout",
     "cpq_latency", "cpq_get_timings", "cpq_get_eq_state", "cpq_cuda_stream", "cpq_kernel_launch_count",
     "cpq_plan_layout", "cpq_set_eq_mode", "cpq_band_node_active", "cpq_get_agc_state",
-    "cpq_set_mix", "cpq_ir_peak_latency",
+    "cpq_set_mix", "cpq_ir_peak_latency", "cpq_set_direct_head",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -109,6 +109,7 @@ def load() -> C.CDLL:
     L.cpq_set_output_stage.argtypes = [vp, C.c_double, C.c_int]
     L.cpq_set_conv_input_trim.argtypes = [vp, C.c_double]
     L.cpq_set_mix.argtypes = [vp, C.c_float, C.c_int]
+    L.cpq_set_direct_head.argtypes = [vp, C.c_int]
     L.cpq_ir_peak_latency.argtypes = [dp, dp, C.c_int]
     L.cpq_output_filter_design.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, dp]
     L.cpq_output_filter_design.restype = None

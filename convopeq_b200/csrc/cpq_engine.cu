@@ -177,7 +177,9 @@ struct Engine
     double convInputTrim = 1.0;         // state.convolverInputTrimGain (EQThenConvolver order only)
     double mix = 1.0;                   // (double) mixTarget of ConvolverProcessor::process (CPQ_CONV_OUTER only)
     int dryDelay = 0;                   // latency-compensation delay of the dry path, samples
-    DevBuf<double> dryBuf;              // copy of the convolver input for the dry path (mix < 0.999)
+    DevBuf<double> dryBuf;              // copy of the convolver input for the dry path (mix < 0.999) / the direct-form head
+    int directHead = 0;                 // enableDirectHead of SetImpulse (experimental in the reference)
+    DevBuf<double> directTaps;          // [nH][32] reversed, scaled head taps
     bool postDirty = true;
     unsigned postIdentity = 0;          // output-filter stages whose coefficients are the identity (skipped)
     DevBuf<double> postc, postState;
@@ -555,6 +557,18 @@ cpq_status Engine::setImpulse(int stream_, int ch, const double* ir, int len, do
     const int row = hRowOf(stream_ < 0 ? 0 : stream_, ch);
     CPQ_CUDA(irScratch.ensure((size_t) len + 2));
     CPQ_CUDA(cudaMemcpyAsync(irScratch.p, ir, (size_t) len * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (directHead)
+    {
+        // m_directTapCount = min(irLen, min(nextPow2(max(block, 64)), 32)) = min(irLen, 32); m_directIRRev[i] = impulse[taps-1-i] * scale
+        // (:689-718); the partitions are built from the impulse with those taps zeroed (:730-731)
+        const int taps = std::min(len, 32);
+        double rev[32] = {};
+        for (int i = 0; i < taps; ++i) rev[32 - taps + i] = ir[taps - 1 - i] * scale;
+        CPQ_CUDA(directTaps.ensure((size_t) nH * 32));
+        CPQ_CUDA(cudaMemcpyAsync(directTaps.p + (size_t) row * 32, rev, sizeof(rev), cudaMemcpyHostToDevice, stream));
+        CPQ_CUDA(cudaMemsetAsync(irScratch.p, 0, (size_t) taps * sizeof(double), stream));
+        CPQ_CUDA(cudaStreamSynchronize(stream));   // rev is on the stack
+    }
     for (int li = 0; li < p.numLayers; ++li)
     {
         const LayerPlan& l = p.layers[li];
@@ -1276,7 +1290,9 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         setError("process: mix < 1 together with a partition range (the dry path belongs to the rank that owns the sum)");
         return CPQ_ERR_UNSUPPORTED;
     }
-    if (needsDry) CPQ_CUDA(dryBuf.ensure((size_t) chunk * stride));
+    // the direct-form head belongs to the rank that holds partition 0 of layer 0
+    const bool direct = doConv && directHead && !dryOnly && qb[0] == 0 && qe[0] > 0;
+    if (needsDry || direct) CPQ_CUDA(dryBuf.ensure((size_t) chunk * stride));
     // ProcessingOrder::EQThenConvolver (DSPCoreDouble.cpp:415-451): EQ (with its total-gain ramp) on the raw input, the
     // convolver input trim, then the convolver; the final launch then only assembles the layers and runs the output stages
     const bool eqFirst = (stages & CPQ_ORDER_EQ_THEN_CONV) && doConv && doEq;
@@ -1305,7 +1321,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             cpq_status st = runEq(p, s0, ns);
             if (st != CPQ_OK) return st;
         }
-        if (needsDry)
+        if (needsDry || direct)
             CPQ_CUDA(cudaMemcpy2DAsync(dryBuf.p, (size_t) stride * sizeof(double), ioC, (size_t) stride * sizeof(double), (size_t) T * sizeof(double),
                                        (size_t) ns, cudaMemcpyDeviceToDevice, stream));
         if (doConv && !dryOnly)
@@ -1405,6 +1421,20 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         {
             cudaEventRecord(ce[1], stream);
             cudaEventRecord(ce[2], stream);
+        }
+        if (direct)
+        {
+            DirectArgs d {};
+            d.io = ioC;
+            d.x = dryBuf.p;
+            d.taps = directTaps.p;
+            d.stride = stride;
+            d.T = T;
+            d.hSeqMod = cfg.shared_ir ? cfg.n_channels : 0;
+            d.seqBase = s0;
+            direct_head_kernel<<<dim3((unsigned) std::min<int64_t>(128, (T + 255) / 256), (unsigned) ns), 256, 0, stream>>>(d);
+            ++launches;
+            CPQ_CUDA(cudaGetLastError());
         }
         cudaEventRecord(ce[3], stream);
         // ---- assembly + EQ + epilogue for this chunk ----
@@ -1751,6 +1781,18 @@ cpq_status cpq_set_output_filter(cpq_handle h, int enabled, int conv_is_last, in
     h->outCfg.lc = lc_mode;
     h->outCfg.lp = lp_mode;
     h->postDirty = true;
+    return CPQ_OK;
+}
+
+cpq_status cpq_set_direct_head(cpq_handle h, int enable)
+{
+    if (!h) return CPQ_ERR_INVALID;
+    if (h->planSet && (enable != 0) != (h->directHead != 0))
+    {
+        h->setError("set_direct_head: call before the first cpq_set_impulse (the head taps are removed from the partitions at SetImpulse time)");
+        return CPQ_ERR_INVALID;
+    }
+    h->directHead = enable ? 1 : 0;
     return CPQ_OK;
 }
 

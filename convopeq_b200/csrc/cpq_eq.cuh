@@ -1139,6 +1139,47 @@ __global__ void mix_kernel(MixArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Experimental direct-form head (MKLNonUniformConvolver::processDirectBlock, MKLNonUniformConvolver.cpp:1169-1232; added
+// to the L0 output in Get, :1604-1616): io += FIR of the first <= 32 taps over the convolver input, accumulated like the
+// reference (two 4-lane FMA accumulators over reversed taps, lanes summed (v0 + v2) + (v1 + v3)); |y| < 1e-20 or
+// non-finite -> 0.  Those taps are zeroed in the impulse the partitions were built from (:730-731) and bypass the
+// spectrum filter, so with a FilterSpec the head changes the result beyond rounding.
+// ---------------------------------------------------------------------------------------------
+struct DirectArgs
+{
+    double* io;            // [nSeq][stride]: L0 output so far
+    const double* x;       // [nSeq][stride]: the convolver input (copy)
+    const double* taps;    // [nH][32]: hrev[k] = h[31 - k] * scale, zero padded at the front for shorter heads
+    int64_t stride, T;
+    int hSeqMod, seqBase;  // row = (seqBase + seq) % hSeqMod when the IR pair is shared; 0 = seqBase + seq
+};
+
+__global__ void direct_head_kernel(DirectArgs a)
+{
+    __shared__ double h[32];
+    const int seq = blockIdx.y;
+    const int row = a.hSeqMod > 0 ? (a.seqBase + seq) % a.hSeqMod : a.seqBase + seq;
+    if (threadIdx.x < 32) h[threadIdx.x] = a.taps[(size_t) row * 32 + threadIdx.x];
+    __syncthreads();
+    double* io = a.io + (size_t) seq * a.stride;
+    const double* x = a.x + (size_t) seq * a.stride;
+    for (int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < a.T; t += (int64_t) gridDim.x * blockDim.x)
+    {
+        double s[8] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+        {
+            const int64_t src = t - 31 + k;
+            const double v = src >= 0 ? x[src] : 0.0;
+            s[k & 7] = fma(h[k], v, s[k & 7]);
+        }
+        double y = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[4]), __dadd_rn(s[2], s[6])), __dadd_rn(__dadd_rn(s[1], s[5]), __dadd_rn(s[3], s[7])));
+        if (!(fabs(y) >= 1.0e-20 && fabs(y) <= 1.79769313486231570815e308)) y = 0.0;
+        io[t] += y;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Mid/Side bands (node path, EQProcessor.Processing.cpp:690-740): encode (L+R)/2, (L-R)/2 of the listed streams into a
 // scratch pair of rows, run the band on one of them with eq_kernel, decode L = M+S, R = M-S.
 // ---------------------------------------------------------------------------------------------

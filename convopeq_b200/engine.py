@@ -157,6 +157,10 @@ class ConvoPeqEngine:
         """OutputFilter::process(block, convIsLast, hcMode, lcMode, lpMode) (OutputFilter.h:108-131); runs with STAGE_OUTPUT_FILTER."""
         self._check(self.lib.cpq_set_output_filter(self.h, int(enabled), int(conv_is_last), hc_mode, lc_mode, lp_mode))
 
+    def set_direct_head(self, enable: bool = True):
+        """enableDirectHead of SetImpulse (experimental direct-form head); call before set_impulse."""
+        self._check(self.lib.cpq_set_direct_head(self.h, int(enable)))
+
     def set_mix(self, mix: float, dry_delay_samples: int):
         """ConvolverProcessor's dry/wet mix (float mixTarget) and the latency-compensation delay of its dry path."""
         self._check(self.lib.cpq_set_mix(self.h, C.c_float(mix), int(dry_delay_samples)))

@@ -145,6 +145,13 @@ cpq_status cpq_reset(cpq_handle h);
 cpq_status cpq_set_impulse(cpq_handle h, int stream, int channel, const double* ir, int ir_len, double scale,
                            const cpq_filter_spec* spec);
 
+/* enableDirectHead of SetImpulse / StereoConvolver::init (MKLNonUniformConvolver.h:197-200, ConvolverProcessor.h:741-744;
+ * "experimental" in the reference, default off): the first min(irLen, 32) taps run as a direct-form FIR
+ * (processDirectBlock, MKLNonUniformConvolver.cpp:1169-1232) added to the L0 output in Get (:1604-1616), and are removed from
+ * the impulse the partitions are built from (:730-731), so they also bypass the spectrum filter.  Applies to every
+ * cpq_set_impulse that follows: call it before the first one. */
+cpq_status cpq_set_direct_head(cpq_handle h, int enable);
+
 /* EQCoeffCache + EQParameters as consumed by EQProcessor::process(block, params, cache)
  * (eqprocessor/EQProcessor.h:121-138, ProcessingCache.cpp:56-96, Processing.cpp:1019-1276); Serial structure and AGC
  * off unless cpq_set_eq_mode says otherwise.  chan_mode: 0 Stereo, 1 Left, 2 Right, 3 Mid, 4 Side (EQChannelMode,

@@ -135,6 +135,8 @@ public:
     /// scrub + +-kOutputHeadroom hard clamp, both inside CPQ_STAGE_EPILOGUE.
     /// convolverInputTrimGain (EQThenConvolver order: pass CPQ_ORDER_EQ_THEN_CONV in `stages`).
     bool setConvolverInputTrim(double gain) { return ok(cpq_set_conv_input_trim(h_, gain)); }
+    /// enableDirectHead of SetImpulse / StereoConvolver::init; call before the first SetImpulse.
+    bool setDirectHeadEnabled(bool enable) { return ok(cpq_set_direct_head(h_, enable ? 1 : 0)); }
     /// ConvolverProcessor::setMix (Runtime.cpp:816) + the dry path's latency compensation (settled state).
     bool setMix(float mix, int dryDelaySamples) { return ok(cpq_set_mix(h_, mix, dryDelaySamples)); }
     bool setOutputProtection(double dcCutoffHz, bool hardClamp) { return ok(cpq_set_output_stage(h_, dcCutoffHz, hardClamp ? 1 : 0)); }

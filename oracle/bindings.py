@@ -91,14 +91,14 @@ class _Base:
 
     # ---- convolver -------------------------------------------------------------------------
     def nuc_run(self, ir: np.ndarray, x: np.ndarray, block: int, scale: float = 1.0,
-                spec: Optional[FilterSpec] = None, call: Optional[int] = None):
+                spec: Optional[FilterSpec] = None, call: Optional[int] = None, direct_head: bool = False):
         """SetImpulse + (Add, Get) loop over x in calls of `call` (default = block) samples."""
         ir = np.ascontiguousarray(ir, dtype=np.float64)
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.zeros_like(x)
         h = self._nuc_create()
         try:
-            ok = self._nuc_set_impulse(h, ir, block, scale, spec)
+            ok = self._nuc_set_impulse(h, ir, block, scale, spec, direct_head)
             if not ok:
                 raise RuntimeError("SetImpulse failed")
             layout = self._nuc_layout(h)
@@ -223,6 +223,7 @@ class Oracle(_Base):
         L = self.lib
         _common_sigs(L, self.prefix, None)
         L.cpqo_nuc_set_impulse.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, C.c_double, C.POINTER(FilterSpec)]
+        L.cpqo_nuc_set_impulse_ex.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(FilterSpec)]
         L.cpqo_eq_create.restype = C.c_void_p
         L.cpqo_eq_create.argtypes = [C.c_double, C.c_float]
         L.cpqo_eq_destroy.argtypes = [C.c_void_p]
@@ -248,8 +249,9 @@ class Oracle(_Base):
         L.cpqo_db_to_gain.restype = C.c_double
         L.cpqo_dither_coeffs.argtypes = [C.c_double, C.c_int, _dp]
 
-    def _nuc_set_impulse(self, h, ir, block, scale, spec):
-        return self.lib.cpqo_nuc_set_impulse(h, _p(ir), ir.size, block, scale, C.byref(spec) if spec is not None else None)
+    def _nuc_set_impulse(self, h, ir, block, scale, spec, direct_head=False):
+        return self.lib.cpqo_nuc_set_impulse_ex(h, _p(ir), ir.size, block, scale, int(direct_head),
+                                                C.byref(spec) if spec is not None else None)
 
     def eq_run(self, bands: Sequence[EqBand], xl: np.ndarray, xr: Optional[np.ndarray], sr: float, block: int,
                saturation: float = 0.2, total_gain_db: float = 0.0, gain_change_db: Optional[float] = None,
@@ -331,8 +333,8 @@ class Ref(_Base):
         L.cpqref_eq_process.argtypes = [C.c_void_p, _dp, _dp, C.c_long, C.c_int]
         L.cpqref_eq_get_state.argtypes = [C.c_void_p, _dp]
 
-    def _nuc_set_impulse(self, h, ir, block, scale, spec):
-        return self.lib.cpqref_nuc_set_impulse(h, _p(ir), ir.size, block, scale, 0,
+    def _nuc_set_impulse(self, h, ir, block, scale, spec, direct_head=False):
+        return self.lib.cpqref_nuc_set_impulse(h, _p(ir), ir.size, block, scale, int(direct_head),
                                                C.byref(spec) if spec is not None else None)
 
     def eq_run(self, bands: Sequence[EqBand], xl, xr, sr, block, saturation=0.2, total_gain_db=0.0,

@@ -197,6 +197,10 @@ typedef struct
     int ring_size, ring_mask, ring_w, ring_r, ring_avail;
     int ready, tail_enabled, max_block;
     double layer_gain[3];
+    /* direct-form head (enableDirectHead, :689-718, 1169-1232, 1604-1616) */
+    int direct_taps, direct_pending;
+    double direct_ir_rev[32], direct_hist[32];
+    double* direct_out;
 } cpqo_nuc;
 
 static double cpqo_clampd(double lo, double hi, double v) { return v < lo ? lo : (hi < v ? hi : v); }
@@ -226,6 +230,7 @@ void cpqo_nuc_destroy(cpqo_nuc* c)
 {
     if (!c) return;
     cpqo_nuc_release(c);
+    free(c->direct_out);
     free(c);
 }
 
@@ -291,14 +296,43 @@ static void cpqo_apply_spectrum_filter(cpqo_nuc* c, const cpqo_filter_spec* spec
     }
 }
 
-/* SetImpulse, MKLNonUniformConvolver.cpp:610-1149 (direct head, :689-718, is not restated: the
- * hot path runs with enableDirectHead=false). Returns 1 on success. */
+int cpqo_nuc_set_impulse_ex(cpqo_nuc* c, const double* impulse_in, int ir_len, int block_size, double scale, int direct_head,
+                            const cpqo_filter_spec* fs);
 int cpqo_nuc_set_impulse(cpqo_nuc* c, const double* impulse, int ir_len, int block_size, double scale,
                          const cpqo_filter_spec* fs)
 {
+    return cpqo_nuc_set_impulse_ex(c, impulse, ir_len, block_size, scale, 0, fs);
+}
+
+/* SetImpulse, MKLNonUniformConvolver.cpp:610-1149, including the experimental direct-form head (:689-718, :730-731): the
+ * first min(irLen, 32) taps run as a direct FIR (scaled, NOT passed through the spectrum filter) and are zeroed in the
+ * impulse the partitions are built from.  Returns 1 on success. */
+int cpqo_nuc_set_impulse_ex(cpqo_nuc* c, const double* impulse_in, int ir_len, int block_size, double scale, int direct_head,
+                            const cpqo_filter_spec* fs)
+{
     c->ready = 0;
-    if (!impulse || ir_len <= 0 || block_size <= 0) return 0;
+    if (!impulse_in || ir_len <= 0 || block_size <= 0) return 0;
     cpqo_nuc_release(c);
+    free(c->direct_out);
+    c->direct_out = NULL;
+    c->direct_taps = 0;
+    c->direct_pending = 0;
+    double* impulse_copy = NULL;
+    const double* impulse = impulse_in;
+    if (direct_head)
+    {
+        const int direct_part = cpqo_next_pow2(block_size > 64 ? block_size : 64);
+        int taps = direct_part < 32 ? direct_part : 32;   /* kMaxDirectTaps */
+        if (ir_len < taps) taps = ir_len;
+        c->direct_taps = taps;
+        memset(c->direct_hist, 0, sizeof(c->direct_hist));
+        for (int i = 0; i < taps; ++i) c->direct_ir_rev[i] = impulse_in[taps - 1 - i] * scale;
+        c->direct_out = (double*) calloc((size_t) (block_size > 1 ? block_size : 1), sizeof(double));
+        impulse_copy = (double*) malloc(sizeof(double) * (size_t) ir_len);
+        memcpy(impulse_copy, impulse_in, sizeof(double) * (size_t) ir_len);
+        memset(impulse_copy, 0, sizeof(double) * (size_t) taps);
+        impulse = impulse_copy;
+    }
 
     /* tail-mode table, :626-684 */
     const int tail_mode = fs ? cpqo_clampi(0, 2, fs->tail_mode) : 1;
@@ -438,7 +472,7 @@ int cpqo_nuc_set_impulse(cpqo_nuc* c, const double* impulse, int ir_len, int blo
         ++c->num_layers;
         prev_total += lens[li];
     }
-    if (c->num_layers == 0) return 0;
+    if (c->num_layers == 0) { free(impulse_copy); return 0; }
 
     /* L0 output ring, :1033-1053 */
     {
@@ -483,8 +517,42 @@ int cpqo_nuc_set_impulse(cpqo_nuc* c, const double* impulse, int ir_len, int blo
             }
         }
     }
+    free(impulse_copy);
     c->ready = 1;
     return 1;
+}
+
+/* processDirectBlock, :1169-1232: y[n] = sum_k hrev[k] * window[n + k] with two 4-lane FMA accumulators over blocks of eight
+ * taps, lanes summed as (v0 + v2) + (v1 + v3), remainder taps added one by one; |y| < 1e-20 or non-finite -> 0. */
+static void cpqo_direct_block(cpqo_nuc* c, const double* input, int n)
+{
+    const int taps = c->direct_taps, hist = taps - 1;
+    double* win = (double*) malloc(sizeof(double) * (size_t) (hist + n));
+    memcpy(win, c->direct_hist, sizeof(double) * (size_t) hist);
+    if (input) memcpy(win + hist, input, sizeof(double) * (size_t) n);
+    else memset(win + hist, 0, sizeof(double) * (size_t) n);
+    const int v8 = taps / 8 * 8;
+    for (int i = 0; i < n; ++i)
+    {
+        const double* x = win + i;
+        double s0[4] = { 0, 0, 0, 0 }, s1[4] = { 0, 0, 0, 0 };
+        int k = 0;
+        for (; k < v8; k += 8)
+            for (int j = 0; j < 4; ++j)
+            {
+                s0[j] = fma(c->direct_ir_rev[k + j], x[k + j], s0[j]);
+                s1[j] = fma(c->direct_ir_rev[k + 4 + j], x[k + 4 + j], s1[j]);
+            }
+        double v[4];
+        for (int j = 0; j < 4; ++j) v[j] = s0[j] + s1[j];
+        double y = (v[0] + v[2]) + (v[1] + v[3]);
+        for (; k < taps; ++k) y += c->direct_ir_rev[k] * x[k];
+        if (!(isfinite(y) && !(fabs(y) < 1.0e-20))) y = 0.0;
+        c->direct_out[i] = y;
+    }
+    memcpy(c->direct_hist, win + n, sizeof(double) * (size_t) hist);
+    free(win);
+    c->direct_pending = n;
 }
 
 /* accumulateSplitComplex, :150-195 (separate multiplies and adds) */
@@ -613,6 +681,11 @@ static void cpqo_delay_read_add(cpqo_layer* l, double* dst, int n, double gain) 
 void cpqo_nuc_add(cpqo_nuc* c, const double* input, int n)
 {
     if (!c->ready || n <= 0) return;
+    if (c->direct_taps > 0)
+    {
+        if (n > c->max_block) c->direct_pending = 0;   /* :1174-1179: a call longer than the block drops the direct output */
+        else cpqo_direct_block(c, input, n);
+    }
     for (int li = 0; li < c->num_layers; ++li)
     {
         cpqo_layer* l = &c->layers[li];
@@ -675,6 +748,17 @@ int cpqo_nuc_get(cpqo_nuc* c, double* out, int n)
         return 0;
     }
     const int got = cpqo_ring_read(c, out, n);
+    if (c->direct_taps > 0)
+    {
+        const int to_add = n < c->direct_pending ? n : c->direct_pending;
+        if (to_add > 0)
+        {
+            if (out)
+                for (int i = 0; i < to_add; ++i) out[i] += c->direct_out[i];
+            memset(c->direct_out, 0, sizeof(double) * (size_t) to_add);
+            c->direct_pending = 0;
+        }
+    }
     for (int li = 1; li < c->num_layers; ++li)
     {
         cpqo_layer* l = &c->layers[li];

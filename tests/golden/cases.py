@@ -18,6 +18,8 @@ CONV_CASES = {
     "irregular_b1024": dict(ir_len=65536, block=1024, T=32768, spec=None, seed=6),
     # air-absorption tail mode with tilt + IR scale
     "tailmode0_scaled": dict(ir_len=70000, block=512, T=16384, spec=dict(tail_mode=0, tail_start_seconds=0.03), seed=7, scale=0.37),
+    # experimental direct-form head: first 32 taps as a direct FIR that bypasses the spectrum filter
+    "direct_head_spec": dict(ir_len=65536, block=512, T=16384, spec={}, seed=9, scale=0.8, direct_head=True),
     # impulse at n = B-1 (layout / onset check)
     "impulse_at_511": dict(ir_len=65536, block=512, T=16384, spec=None, seed=8, impulse_at=511),
 }

@@ -25,7 +25,7 @@ def main():
     for name, c in CONV_CASES.items():
         ir, x = conv_inputs(c)
         spec = FilterSpec(**c["spec"]) if c["spec"] is not None else None
-        y, lay = ref.nuc_run(ir, x, c["block"], scale=c.get("scale", 1.0), spec=spec)
+        y, lay = ref.nuc_run(ir, x, c["block"], scale=c.get("scale", 1.0), spec=spec, direct_head=c.get("direct_head", False))
         out["conv/" + name] = y
         out["conv_layout/" + name] = np.array([[l["part_size"], l["num_parts_ir"], l["parts_per_callback"], l["output_delay_samples"]]
                                                for l in lay["layers"]], dtype=np.int64)

@@ -120,6 +120,30 @@ def test_outer_dry_wet_mix(checker, oracle, mix):
     assert np.abs(z[0] - wl).max() <= TOL and np.abs(z[1] - wr).max() <= TOL
 
 
+@pytest.mark.parametrize("ir_len,block,T,kw,shared", [(65536, 512, 32768, {}, False), (65536, 512, 16384, None, True), (20, 64, 4096, {}, False),
+                                                      (131072, 1024, 65536, dict(tail_mode=0), False)])
+def test_direct_head_matches_reference(checker, ir_len, block, T, kw, shared):
+    """SetImpulse(..., enableDirectHead = true): the first <= 32 taps as a direct-form FIR outside the spectrum filter."""
+    ospec, cspec = _specs(kw)
+    n_streams = 3
+    irs = [signals.synth_ir(ir_len, 80 + i) for i in range(2 if shared else 2 * n_streams)]
+    x = np.stack([signals.noise(T, 90 + i) for i in range(2 * n_streams)])
+    eng = ConvoPeqEngine(n_streams, 2, 48000.0, block, T, shared_ir=shared)
+    eng.set_direct_head(True)
+    for s in range(1 if shared else n_streams):
+        for ch in range(2):
+            eng.set_impulse(-1 if shared else s, ch, irs[2 * s + ch], 0.7, cspec)
+    with pytest.raises(capi.CpqError):
+        eng.set_direct_head(False)          # the head was already removed from the partitions
+    y = x.copy()
+    eng.process(y, capi.STAGE_CONV)
+    eng.close()
+    for q in range(2 * n_streams):
+        ir = irs[q % 2] if shared else irs[q]
+        want, _ = checker.nuc_run(ir, x[q], block, scale=0.7, spec=ospec, direct_head=True)
+        assert np.abs(y[q] - want).max() <= TOL, q
+
+
 def test_ir_scale(checker):
     ir = signals.synth_ir(20000, 4)
     T = 16384
@@ -327,10 +351,12 @@ _GOLD = np.load(_os.path.join(_os.path.dirname(__file__), "golden", "golden.npz"
 
 @pytest.mark.parametrize("name", sorted(_GCONV))
 def test_convolver_matches_golden(name):
+    # (direct_head cases set the handle flag before the impulses)
     c = _GCONV[name]
     ir, x = conv_inputs(c)
     cspec = capi.default_filter_spec(**c["spec"]) if c["spec"] is not None else None
     eng = ConvoPeqEngine(1, 1, 48000.0, c["block"], c["T"])
+    eng.set_direct_head(c.get("direct_head", False))
     eng.set_impulse(0, 0, ir, c.get("scale", 1.0), cspec)
     y = x[None, :].copy()
     eng.process(y, capi.STAGE_CONV)

@@ -19,7 +19,7 @@ def test_convolver_restatement_matches_golden(oracle, name):
     c = CONV_CASES[name]
     ir, x = conv_inputs(c)
     spec = FilterSpec(**c["spec"]) if c["spec"] is not None else None
-    y, lay = oracle.nuc_run(ir, x, c["block"], scale=c.get("scale", 1.0), spec=spec)
+    y, lay = oracle.nuc_run(ir, x, c["block"], scale=c.get("scale", 1.0), spec=spec, direct_head=c.get("direct_head", False))
     assert np.abs(y - GOLD["conv/" + name]).max() <= TOL
     got = np.array([[l["part_size"], l["num_parts_ir"], l["parts_per_callback"], l["output_delay_samples"]] for l in lay["layers"]])
     assert np.array_equal(got, GOLD["conv_layout/" + name])

@@ -36,6 +36,20 @@ def test_nuc_spectra_equal_reference(oracle, ref):
             assert np.abs(a - b).max() <= 1e-13
 
 
+@pytest.mark.parametrize("ir_len,block,spec,call", [(65536, 512, None, None), (20000, 512, {}, None), (20, 64, {}, None),
+                                                   (9000, 256, None, 100), (65536, 1024, {}, None), (40000, 128, dict(tail_mode=0), None)])
+def test_direct_head_restatement_equals_reference(oracle, ref, ir_len, block, spec, call):
+    """enableDirectHead = true: direct FIR of the first <= 32 taps + partitions built without them."""
+    ir, x = signals.synth_ir(ir_len, 3), signals.noise(8192, 4)
+    sp = FilterSpec(**spec) if spec is not None else None
+    yo, _ = oracle.nuc_run(ir, x, block, 0.7, sp, call, direct_head=True)
+    yr, _ = ref.nuc_run(ir, x, block, 0.7, sp, call, direct_head=True)
+    assert np.abs(yo - yr).max() <= 1e-13
+    if spec is not None:   # the head bypasses the spectrum filter: a different result, not a rounding difference
+        yp, _ = ref.nuc_run(ir, x, block, 0.7, sp, call, direct_head=False)
+        assert np.abs(yr - yp).max() > 1e-6
+
+
 def test_non_block_sized_calls(oracle, ref):
     """Add/Get with call sizes different from the prepared block size (ring latency path)."""
     ir = signals.synth_ir(20000, 5)
