@@ -31,6 +31,11 @@ class SvfCoeffs(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("a1", "a2", "a3", "m0", "m1", "m2")]
 
 
+class EqBandParams(C.Structure):
+    _fields_ = [("frequency", C.c_float), ("gain_db", C.c_float), ("q", C.c_float),
+                ("enabled", C.c_int32), ("type", C.c_int32), ("channel_mode", C.c_int32)]
+
+
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("n_streams", C.c_int32), ("n_channels", C.c_int32),
                 ("block_size", C.c_int32), ("sample_rate", C.c_double), ("max_samples", C.c_int64),
@@ -63,7 +68,7 @@ EXPORTS = [
     "cpq_process", "cpq_process_device", "cpq_set_partition_range", "cpq_total_partitions", "cpq_get_layout",
     "cpq_latency", "cpq_get_timings", "cpq_get_eq_state", "cpq_cuda_stream", "cpq_kernel_launch_count",
     "cpq_plan_layout", "cpq_set_eq_mode", "cpq_band_node_active", "cpq_get_agc_state",
-    "cpq_set_mix", "cpq_ir_peak_latency", "cpq_set_direct_head",
+    "cpq_set_mix", "cpq_ir_peak_latency", "cpq_set_direct_head", "cpq_parse_eq_preset",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -110,6 +115,7 @@ def load() -> C.CDLL:
     L.cpq_set_conv_input_trim.argtypes = [vp, C.c_double]
     L.cpq_set_mix.argtypes = [vp, C.c_float, C.c_int]
     L.cpq_set_direct_head.argtypes = [vp, C.c_int]
+    L.cpq_parse_eq_preset.argtypes = [C.c_char_p, C.POINTER(EqBandParams), C.POINTER(C.c_float)]
     L.cpq_ir_peak_latency.argtypes = [dp, dp, C.c_int]
     L.cpq_output_filter_design.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, dp]
     L.cpq_output_filter_design.restype = None

@@ -1784,6 +1784,12 @@ cpq_status cpq_set_output_filter(cpq_handle h, int enabled, int conv_is_last, in
     return CPQ_OK;
 }
 
+int cpq_parse_eq_preset(const char* text, cpq_eq_band_params bands[CPQ_NUM_BANDS], float* total_gain_db)
+{
+    if (!text || !bands || !total_gain_db) return -1;
+    return cpq::parseEqPreset(text, bands, total_gain_db);
+}
+
 cpq_status cpq_set_direct_head(cpq_handle h, int enable)
 {
     if (!h) return CPQ_ERR_INVALID;

@@ -17,6 +17,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cctype>
+#include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "../../include/cpq.h"
@@ -417,6 +420,123 @@ inline bool designBand(int type, float freq, float gainDb, float q, double sr, c
         default: out->m0 = 1.0; out->m1 = -k; out->m2 = -1.0; break;
     }
     return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// EQ preset text (EqualizerAPO / AutoEq "ParametricEq.txt"): EQProcessor::loadFromTextFile,
+// eqprocessor/EQProcessor.Core.cpp:300-495.  Host-only; fills the same parameter fields the reference's setters would.
+// ------------------------------------------------------------------------------------------------
+namespace preset
+{
+inline bool startsWithNoCase(const std::string& s, const char* p)
+{
+    size_t i = 0;
+    for (; p[i]; ++i)
+        if (i >= s.size() || std::tolower((unsigned char) s[i]) != std::tolower((unsigned char) p[i])) return false;
+    return true;
+}
+inline bool equalsNoCase(const std::string& s, const char* p)
+{
+    size_t i = 0;
+    for (; p[i]; ++i)
+        if (i >= s.size() || std::tolower((unsigned char) s[i]) != std::tolower((unsigned char) p[i])) return false;
+    return i == s.size();
+}
+// juce::String::getFloatValue: the leading number of the token (0 when there is none), narrowed to float
+inline float floatValue(const std::string& s) { return (float) std::strtod(s.c_str(), nullptr); }
+}   // namespace preset
+
+inline int parseEqPreset(const char* text, cpq_eq_band_params bands[CPQ_NUM_BANDS], float* totalGainDb)
+{
+    using namespace preset;
+    for (int i = 0; i < CPQ_NUM_BANDS; ++i)   // :305-310
+    {
+        bands[i].enabled = 0;
+        bands[i].channel_mode = 0;
+        bands[i].gain_db = 0.0f;
+    }
+    int filterIndex = 0, ignored = 0, mode = 0;
+    const std::string all(text ? text : "");
+    size_t pos = 0;
+    while (pos <= all.size())
+    {
+        size_t eol = all.find('\n', pos);
+        if (eol == std::string::npos) eol = all.size();
+        std::string line = all.substr(pos, eol - pos);
+        pos = eol + 1;
+        line = line.substr(0, line.find('#'));     // upToFirstOccurrenceOf("#"), then ";" (:320-322)
+        line = line.substr(0, line.find(';'));
+        std::vector<std::string> tok;
+        for (size_t i = 0; i < line.size();)
+        {
+            while (i < line.size() && std::isspace((unsigned char) line[i])) ++i;
+            size_t j = i;
+            while (j < line.size() && !std::isspace((unsigned char) line[j])) ++j;
+            if (j > i) tok.push_back(line.substr(i, j - i));
+            i = j;
+        }
+        if (tok.empty()) continue;
+        if (startsWithNoCase(tok[0], "Preamp"))   // :339-350: the first later token that contains a digit, '-' or '.'
+        {
+            for (size_t i = 1; i < tok.size(); ++i)
+                if (tok[i].find_first_of("0123456789-.") != std::string::npos)
+                {
+                    *totalGainDb = clampv(-48.0f, 48.0f, floatValue(tok[i]));   // setTotalGain clamps (Parameters.cpp:106)
+                    break;
+                }
+        }
+        else if (startsWithNoCase(tok[0], "Channel"))   // :351-374
+        {
+            bool hasL = false, hasR = false;
+            for (std::string t : tok)
+            {
+                if (startsWithNoCase(t, "Channel")) t = t.substr(7);
+                std::string u;
+                for (char c : t)
+                    if (c != ':' && c != ',') u.push_back(c);
+                if (equalsNoCase(u, "L") || equalsNoCase(u, "Left")) hasL = true;
+                else if (equalsNoCase(u, "R") || equalsNoCase(u, "Right")) hasR = true;
+            }
+            mode = (hasL && hasR) ? 0 : (hasL ? 1 : (hasR ? 2 : 0));
+        }
+        else if (startsWithNoCase(tok[0], "Filter"))   // :375-486
+        {
+            if (filterIndex >= CPQ_NUM_BANDS) { ++ignored; continue; }
+            cpq_eq_band_params& b = bands[filterIndex];
+            bool enabled = true, typeFound = false, qFound = false;
+            float freq = 0.0f, gain = 0.0f, q = 0.707f;
+            for (size_t i = 1; i < tok.size(); ++i)
+            {
+                const std::string& t = tok[i];
+                if (equalsNoCase(t, "ON")) { enabled = true; continue; }
+                if (equalsNoCase(t, "OFF")) { enabled = false; continue; }
+                if (!typeFound)
+                {
+                    int type = -1;
+                    if (equalsNoCase(t, "LSC") || equalsNoCase(t, "LowShelf")) type = 0;
+                    else if (equalsNoCase(t, "PK") || equalsNoCase(t, "Peaking")) type = 1;
+                    else if (equalsNoCase(t, "HSC") || equalsNoCase(t, "HighShelf")) type = 2;
+                    else if (equalsNoCase(t, "LP") || equalsNoCase(t, "LowPass")) type = 3;
+                    else if (equalsNoCase(t, "HP") || equalsNoCase(t, "HighPass")) type = 4;
+                    if (type >= 0) { b.type = type; typeFound = true; continue; }
+                }
+                if (i + 1 < tok.size())
+                {
+                    if (equalsNoCase(t, "Fc")) freq = floatValue(tok[i + 1]);
+                    else if (equalsNoCase(t, "Gain")) gain = floatValue(tok[i + 1]);
+                    else if (equalsNoCase(t, "Q")) { q = floatValue(tok[i + 1]); qFound = true; }
+                }
+            }
+            if (!typeFound) b.type = 1;
+            b.enabled = enabled ? 1 : 0;
+            if (freq > 0.0f) b.frequency = freq;
+            b.gain_db = gain;
+            b.q = (qFound && q > 0.0f) ? q : 0.707f;
+            b.channel_mode = mode;
+            ++filterIndex;
+        }
+    }
+    return ignored;
 }
 
 inline double dbToGain(float db)

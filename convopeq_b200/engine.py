@@ -215,6 +215,25 @@ class ConvoPeqEngine:
         return int(self.lib.cpq_kernel_launch_count(self.h))
 
 
+DEFAULT_FREQS = (20.0, 32.0, 50.0, 80.0, 125.0, 200.0, 315.0, 500.0, 800.0, 1250.0, 2000.0, 3150.0, 5000.0, 8000.0, 12500.0,
+                 16000.0, 19000.0, 20000.0, 22000.0, 24000.0)   # convo::EQParameters defaults (core/EQParameters.h:32-37)
+
+
+def load_eq_preset(text: str, bands: Optional[Sequence[Band]] = None, total_gain_db: float = 0.0):
+    """EQProcessor::loadFromTextFile on the contents of an EqualizerAPO / AutoEq preset; returns (bands, total_gain_db,
+    ignored_filter_lines).  `bands` is the state before loading (default: convo::EQParameters{})."""
+    arr = (capi.EqBandParams * capi.NUM_BANDS)()
+    start = list(bands) if bands is not None else [Band(frequency=f) for f in DEFAULT_FREQS]
+    for i, b in enumerate(start):
+        arr[i] = capi.EqBandParams(b.frequency, b.gain, b.q, int(b.enabled), int(b.type), int(b.channel_mode))
+    g = C.c_float(total_gain_db)
+    ignored = capi.load().cpq_parse_eq_preset(text.encode("utf-8", "replace"), arr, C.byref(g))
+    if ignored < 0:
+        raise ValueError("cpq_parse_eq_preset")
+    out = [Band(a.frequency, a.gain_db, a.q, bool(a.enabled), a.type, a.channel_mode) for a in arr]
+    return out, float(g.value), ignored
+
+
 def ir_peak_latency(ir_l: np.ndarray, ir_r: Optional[np.ndarray] = None) -> int:
     """LoaderThread::estimatePeakLatencySamples (host-only helper of the C ABI)."""
     a = np.ascontiguousarray(ir_l, dtype=np.float64)

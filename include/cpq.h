@@ -214,6 +214,20 @@ int cpq_ir_peak_latency(const double* ir_l, const double* ir_r, int len);
 /* Host-only: the three stages' normalised coefficients {b0,b1,b2,a1,a2} x 3 as OutputFilter::prepare computes them. */
 void cpq_output_filter_design(double sample_rate, int conv_is_last, int hc_mode, int lc_mode, int lp_mode, double out[15]);
 
+/* convo::EQBandParams (core/EQParameters.h:11-20) as plain C. */
+typedef struct cpq_eq_band_params
+{
+    float frequency, gain_db, q;
+    int32_t enabled, type, channel_mode;   /* type: 0 LowShelf 1 Peaking 2 HighShelf 3 LowPass 4 HighPass */
+} cpq_eq_band_params;
+
+/* Host-only: EQProcessor::loadFromTextFile (eqprocessor/EQProcessor.Core.cpp:300-495), the EqualizerAPO / AutoEq
+ * "ParametricEq.txt" format ("Preamp: -6.5 dB", "Channel: L R", "Filter 1: ON PK Fc 100 Hz Gain -3 dB Q 1.41").  `text` is
+ * the file's contents.  bands / total_gain_db are in/out like the processor's state: every band is first disabled, set to
+ * Stereo and 0 dB; frequency, Q and type of bands the text does not mention keep what the caller put there.  Returns the
+ * number of "Filter" lines beyond band 20 that were ignored (the reference shows a warning box), or -1 on a NULL argument. */
+int cpq_parse_eq_preset(const char* text, cpq_eq_band_params bands[CPQ_NUM_BANDS], float* total_gain_db);
+
 /* EQProcessor::calcSVFCoeffs (eqprocessor/EQProcessor.Coefficients.cpp:101-130,431-618), host-side:
  * float parameters clamped then promoted to double exactly like the reference.
  * type: 0 LowShelf 1 Peaking 2 HighShelf 3 LowPass 4 HighPass. */

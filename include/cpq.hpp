@@ -121,6 +121,21 @@ public:
     void setBandChannelMode(int stream, int band, int m) { if (valid(stream, band)) { p(stream).bands[(size_t) band].channelMode = m; dirty_ = true; } }
     void setTotalGain(int stream, float db) { if (valid(stream, 0)) { p(stream).totalGainDb = db; dirty_ = true; } }
     void setNonlinearSaturation(int stream, float s) { if (valid(stream, 0)) { p(stream).nonlinearSaturation = s; dirty_ = true; } }
+    /// EQProcessor::loadFromTextFile on the contents of an EqualizerAPO / AutoEq preset (EQProcessor.Core.cpp:300-495).
+    bool loadFromText(int stream, const std::string& text)
+    {
+        if (!valid(stream, 0)) return false;
+        cpq_eq_band_params b[CPQ_NUM_BANDS];
+        EQParameters& q = p(stream);
+        for (int i = 0; i < CPQ_NUM_BANDS; ++i)
+            b[i] = { q.bands[(size_t) i].frequency, q.bands[(size_t) i].gain, q.bands[(size_t) i].q, q.bands[(size_t) i].enabled ? 1 : 0,
+                     q.bands[(size_t) i].type, q.bands[(size_t) i].channelMode };
+        if (cpq_parse_eq_preset(text.c_str(), b, &q.totalGainDb) < 0) return false;
+        for (int i = 0; i < CPQ_NUM_BANDS; ++i)
+            q.bands[(size_t) i] = { b[i].frequency, b[i].gain_db, b[i].q, b[i].enabled != 0, b[i].type, b[i].channel_mode };
+        dirty_ = true;
+        return true;
+    }
     void setEQParameters(int stream, const EQParameters& params) { if (valid(stream, 0)) { p(stream) = params; dirty_ = true; } }
 
     /// outputMakeupGain + dither bit depth (0 = the no-dither kOutputHeadroom branch).

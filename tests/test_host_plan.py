@@ -118,3 +118,52 @@ def test_design_band_matches_checker(checker):
                 b = checker.eq_design(ty, f, g, q, sr)
                 got = np.array([a.a1, a.a2, a.a3, a.m0, a.m1, a.m2])
                 assert np.allclose(got, b, rtol=4e-16, atol=1e-300), (ty, f, g, q, sr, got, b)
+
+
+PRESET = """# made-up preset in the EqualizerAPO / AutoEq "ParametricEq.txt" format
+Preamp: -5.25 dB   ; trailing comment
+Filter 1: ON LSC Fc 105 Hz Gain 4.5 dB Q 0.70
+Filter 2: ON PK Fc 63.5 Hz Gain -2.25 dB Q 1.41
+Filter 3: OFF PK Fc 250 Hz Gain 3 dB Q 2
+Channel: L
+Filter 4: ON HSC Fc 9000 Hz Gain -1.5 dB
+Filter: ON LP Fc 18000 Hz Q 0.5
+channel: R, L
+Filter 6: on highpass fc 30 hz q 0   # q <= 0 -> default Q
+Channel: Right
+Filter 7: ON Fc 1000 Hz Gain 1 dB Q 3.3
+Filter 8: ON PK Gain 2 dB Q 1
+"""
+
+
+def test_eq_preset_text_parser():
+    """EQProcessor::loadFromTextFile (EQProcessor.Core.cpp:300-495) restated host-side (cpq_parse_eq_preset)."""
+    from convopeq_b200.engine import load_eq_preset, DEFAULT_FREQS
+    bands, gain, ignored = load_eq_preset(PRESET)
+    f32 = lambda v: float(np.float32(v))
+    assert ignored == 0 and gain == f32(-5.25)
+    want = [  # (freq, gain, q, enabled, type, mode)
+        (105.0, 4.5, 0.70, True, 0, 0), (63.5, -2.25, 1.41, True, 1, 0), (250.0, 3.0, 2.0, False, 1, 0),
+        (9000.0, -1.5, 0.707, True, 2, 1), (18000.0, 0.0, 0.5, True, 3, 1), (30.0, 0.0, 0.707, True, 4, 0),
+        (1000.0, 1.0, 3.3, True, 1, 2), (DEFAULT_FREQS[7], 2.0, 1.0, True, 1, 2)]
+    for b, w in zip(bands, want):
+        assert (b.frequency, b.gain, b.q, b.enabled, b.type, b.channel_mode) == (f32(w[0]), f32(w[1]), f32(w[2]), w[3], w[4], w[5]), (b, w)
+    for i in range(8, 20):   # untouched bands: disabled, Stereo, 0 dB, frequency kept
+        assert not bands[i].enabled and bands[i].gain == 0.0 and bands[i].channel_mode == 0 and bands[i].frequency == DEFAULT_FREQS[i]
+    many = "Preamp: -60 dB\n" + "".join(f"Filter {i}: ON PK Fc {100 + i} Hz Gain 1 dB Q 1\n" for i in range(1, 24))
+    bands, gain, ignored = load_eq_preset(many)
+    assert ignored == 3 and gain == -48.0 and all(b.enabled for b in bands)      # setTotalGain clamps to +-48 dB
+
+
+def test_eq_preset_reference_fixture():
+    """The reference's own sample preset (sampledata/*ParametricEq.txt), when the reference tree is mounted."""
+    import glob, os
+    from convopeq_b200.engine import load_eq_preset
+    files = glob.glob("/root/reference/sampledata/*ParametricEq.txt")
+    if not files:
+        pytest.skip("reference tree absent")
+    text = open(files[0], encoding="utf-8", errors="replace").read()
+    bands, gain, ignored = load_eq_preset(text)
+    n_filters = sum(1 for ln in text.splitlines() if ln.strip().lower().startswith("filter"))
+    assert ignored == max(0, n_filters - 20) and sum(b.enabled for b in bands) == min(n_filters, 20)
+    assert gain < 0.0 and bands[0].type == 0 and bands[0].enabled and all(b.q > 0 for b in bands)
