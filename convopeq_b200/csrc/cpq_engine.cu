@@ -127,6 +127,10 @@ struct Engine
     DevBuf<int> msStreamsDev[CPQ_NUM_BANDS], msSetDev[CPQ_NUM_BANDS];
     DevBuf<unsigned> msMaskDev[CPQ_NUM_BANDS];       // [2 * count]: bit b on the Mid row or on the Side row
     DevBuf<double> msScratch, sumsq, agcTab, agcState;
+    std::vector<int> parMsStreams;                   // sorted streams in the Parallel structure that have Mid/Side bands
+    DevBuf<int> parMsStreamsDev, parMsSetDev;
+    DevBuf<unsigned> parMsMaskDev;                   // [2 * count]: all Mid bands on the Mid row, all Side bands on the Side row, | 1 << 31
+    DevBuf<double> parMsScratch;
     DevBuf<uint8_t> agcOnDev;
     cpq_status runEq(EqArgs e, int s0, int ns);
 
@@ -835,6 +839,7 @@ cpq_status Engine::uploadEq(int64_t nCallbacks)
         anyPar = anyAgc = anyMs = false;
         msSplitMask = 0;
         for (auto& v : msStreams) v.clear();
+        parMsStreams.clear();
         for (int q = 0; q < nSeq; ++q)
         {
             const int st = q / cfg.n_channels, ch = q % cfg.n_channels;
@@ -852,7 +857,8 @@ cpq_status Engine::uploadEq(int64_t nCallbacks)
                 // Processing.cpp:1239-1252: Stereo -> both; Left -> ch 0; Right -> ch 1
                 const bool on = (mode == 0) || (mode == 1 && ch == 0) || (mode == 2 && ch == 1);
                 if (on) m |= 1u << b;
-                if (mode >= 3 && ch == 0) msStreams[b].push_back(st);   // ascending stream order
+                if (mode >= 3 && ch == 0 && e.structure != 1) msStreams[b].push_back(st);   // ascending stream order
+                if (mode >= 3 && ch == 0 && e.structure == 1 && (parMsStreams.empty() || parMsStreams.back() != st)) parMsStreams.push_back(st);
             }
             if (e.structure == 1) m |= 1u << 31;   // Parallel structure flag, read by eq_kernel<.., PAR>
             anyPar |= e.structure == 1;
@@ -892,6 +898,34 @@ cpq_status Engine::uploadEq(int64_t nCallbacks)
             CPQ_CUDA(cudaMemcpyAsync(msMaskDev[b].p, mm.data(), mm.size() * sizeof(unsigned), cudaMemcpyHostToDevice, stream));
             CPQ_CUDA(cudaMemcpyAsync(msSetDev[b].p, ss.data(), ss.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
         }
+        if (!parMsStreams.empty())
+        {
+            anyMs = true;
+            const std::vector<int>& L = parMsStreams;
+            std::vector<unsigned> mm(2 * L.size(), 0u);
+            std::vector<int> ss(2 * L.size());
+            for (size_t i = 0; i < L.size(); ++i)
+            {
+                const EqSet& e = eqSets[cfg.shared_eq ? 0 : (size_t) L[i]];
+                const uint8_t* on_ = e.hasNodeActive ? e.nodeActive : e.active;   // a Mid/Side band is active: node path
+                unsigned mMid = 1u << 31, mSide = 1u << 31;
+                for (int b = 0; b < CPQ_NUM_BANDS; ++b)
+                {
+                    if (!on_[b]) continue;
+                    if (e.mode[b] == 3) mMid |= 1u << b;
+                    if (e.mode[b] == 4) mSide |= 1u << b;
+                }
+                mm[2 * i] = mMid;
+                mm[2 * i + 1] = mSide;
+                ss[2 * i] = ss[2 * i + 1] = cfg.shared_eq ? 0 : L[i];
+            }
+            CPQ_CUDA(parMsStreamsDev.ensure(L.size()));
+            CPQ_CUDA(parMsMaskDev.ensure(mm.size()));
+            CPQ_CUDA(parMsSetDev.ensure(ss.size()));
+            CPQ_CUDA(cudaMemcpyAsync(parMsStreamsDev.p, L.data(), L.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+            CPQ_CUDA(cudaMemcpyAsync(parMsMaskDev.p, mm.data(), mm.size() * sizeof(unsigned), cudaMemcpyHostToDevice, stream));
+            CPQ_CUDA(cudaMemcpyAsync(parMsSetDev.p, ss.data(), ss.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        }
         if (anyAgc)
         {
             std::vector<uint8_t> on((size_t) cfg.n_streams);
@@ -907,11 +941,6 @@ cpq_status Engine::uploadEq(int64_t nCallbacks)
     if (anyMs && cfg.n_channels != 2)
     {
         setError("Mid/Side bands need a stereo handle (n_channels = 2)");
-        return CPQ_ERR_UNSUPPORTED;
-    }
-    if (anyMs && anyPar)
-    {
-        setError("Mid/Side bands together with the Parallel structure (node path :751-865 with its structure cross-fade) are not part of this path");
         return CPQ_ERR_UNSUPPORTED;
     }
     bool anyEvents = false;
@@ -1019,6 +1048,52 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
         g.finalClamp = 0;
         g.applyHeadroom = 0;
     };
+    // streams of this chunk in the Parallel structure with Mid/Side bands (Processing.cpp:790-832): every band works on the
+    // band input, so Mid and Side rows are encoded once from the input, all Mid bands run on the Mid row and all Side bands
+    // on the Side row in one Parallel launch, the rows are reduced to the summed differences D_M, D_S, and after the plain
+    // bands L += D_M + D_S, R += D_M - D_S
+    const size_t p0 = (size_t) (std::lower_bound(parMsStreams.begin(), parMsStreams.end(), st0) - parMsStreams.begin());
+    const size_t p1 = (size_t) (std::lower_bound(parMsStreams.begin(), parMsStreams.end(), st0 + nst) - parMsStreams.begin());
+    const int parCnt = ms ? (int) (p1 - p0) : 0;
+    MsArgs pm {};
+    dim3 pg(1, 1);
+    if (parCnt > 0)
+    {
+        if (e.assemble)
+        {
+            // the rows are encoded from the assembled convolver output: assemble first, on its own
+            EqArgs w = e;
+            strip(w);
+            w.doEq = 0;
+            cpq_status st = launchEq(w);
+            if (st != CPQ_OK) return st;
+            e.assemble = 0;
+            e.nTail = 0;
+            e.outer = 0;
+        }
+        pm.io = e.io;
+        pm.ioStride = e.ioStride;
+        pm.ms = parMsScratch.p;
+        pm.streams = parMsStreamsDev.p + p0;
+        pm.streamBase = st0;
+        pm.T = e.T;
+        pg = dim3((unsigned) std::min<int64_t>(64, (e.T / 2 + 255) / 256), (unsigned) parCnt);
+        ms_kernel<0><<<pg, 256, 0, stream>>>(pm);
+        ++launches;
+        EqArgs q = e;
+        strip(q);
+        q.io = parMsScratch.p;
+        q.nSeq = 2 * parCnt;
+        q.bandMask = parMsMaskDev.p + 2 * p0;
+        q.setOfSeq = parMsSetDev.p + 2 * p0;
+        q.stateOut = nullptr;
+        cpq_status st = launchEq(q);
+        if (st != CPQ_OK) return st;
+        ms_kernel<2><<<pg, 256, 0, stream>>>(pm);
+        ++launches;
+        CPQ_CUDA(cudaGetLastError());
+    }
+    const bool needFinal = agc || parCnt > 0;   // the gain has to wait for whole-callback statistics / for the Mid-Side differences
     int lo = 0;
     for (int b = 0; b <= CPQ_NUM_BANDS; ++b)
     {
@@ -1028,15 +1103,16 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
         EqArgs g = e;
         const int hi = final_ ? CPQ_NUM_BANDS - 1 : b;
         g.bandSelect = hi >= lo ? (((1u << (hi + 1)) - 1u) & ~((1u << lo) - 1u)) : 0u;
+        g.bandSelectPar = lo == 0 ? (1u << CPQ_NUM_BANDS) - 1u : 0u;   // Parallel sequences run all their bands in the first launch
         if (lo > 0)
         {
             g.assemble = 0;
             g.nTail = 0;
             g.outer = 0;
         }
-        if (!final_ || agc) strip(g);
+        if (!final_ || needFinal) strip(g);
         if (agc && lo == 0) g.sumsqIn = sqIn;
-        if (agc && final_) g.sumsqOut = sqOut;
+        if (agc && final_ && parCnt == 0) g.sumsqOut = sqOut;
         cpq_status st = launchEq(g);
         if (st != CPQ_OK) return st;
         lo = b + 1;
@@ -1055,7 +1131,7 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
         m.streamBase = st0;
         m.T = e.T;
         const dim3 mg((unsigned) std::min<int64_t>(64, (e.T / 2 + 255) / 256), (unsigned) cnt);
-        ms_kernel<true><<<mg, 256, 0, stream>>>(m);
+        ms_kernel<0><<<mg, 256, 0, stream>>>(m);
         ++launches;
         EqArgs q = e;
         strip(q);
@@ -1070,11 +1146,39 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
         q.stateOut = nullptr;
         st = launchEq(q);
         if (st != CPQ_OK) return st;
-        ms_kernel<false><<<mg, 256, 0, stream>>>(m);
+        ms_kernel<1><<<mg, 256, 0, stream>>>(m);
         ++launches;
         CPQ_CUDA(cudaGetLastError());
     }
-    if (!agc) return CPQ_OK;
+    if (parCnt > 0)
+    {
+        ms_kernel<3><<<pg, 256, 0, stream>>>(pm);
+        ++launches;
+        CPQ_CUDA(cudaGetLastError());
+        if (agc)
+        {
+            // the output statistics need the Mid/Side differences: a statistics-only pass
+            EqArgs w = e;
+            strip(w);
+            w.assemble = 0;
+            w.nTail = 0;
+            w.outer = 0;
+            w.doEq = 0;
+            w.sumsqOut = sqOut;
+            cpq_status st = launchEq(w);
+            if (st != CPQ_OK) return st;
+        }
+    }
+    if (!needFinal) return CPQ_OK;
+    if (!agc)
+    {
+        EqArgs f = e;   // total gain + output stages + epilogue
+        f.assemble = 0;
+        f.nTail = 0;
+        f.outer = 0;
+        f.doEq = 0;
+        return launchEq(f);
+    }
     AgcArgs a {};
     a.sumsqIn = sqIn;
     a.sumsqOut = sqOut;
@@ -1205,6 +1309,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         if (anyMs) chunk = (int) std::min<size_t>((size_t) chunk, std::max<size_t>((size_t) nch, cfg.workspace_bytes / ((size_t) stride * sizeof(double))));
         chunk = std::max(nch, chunk / nch * nch);
         if (anyMs) CPQ_CUDA(msScratch.ensure((size_t) chunk * stride));
+        if (!parMsStreams.empty()) CPQ_CUDA(parMsScratch.ensure((size_t) chunk * stride));
         if (anyAgc)
         {
             CPQ_CUDA(sumsq.ensure((size_t) 2 * chunk * nCallbacks));
@@ -1270,6 +1375,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         a.gainTab = (doEq && haveGainTab) ? gainTab.p : nullptr;
         a.doGain = a.doEq;
         a.bandSelect = (1u << CPQ_NUM_BANDS) - 1u;
+        a.bandSelectPar = a.bandSelect;
         a.gainConst = gainConst.p;
         a.nCallbacks = nCallbacks;
         a.doEpilogue = doEpi ? 1 : 0;

@@ -126,6 +126,7 @@ struct EqArgs
     int doGain;             // apply the total gain (Processing.cpp:1262-1274) / the AGC gain ramp (:441-444) in this launch
     int gainBySeq;          // > 0: gainTab row = seq / gainBySeq (per-stream AGC table built by agc_kernel)
     unsigned bandSelect;    // bands this launch may run (a band sequence split around Mid/Side bands runs in several launches)
+    unsigned bandSelectPar; // the same for sequences in the Parallel structure (all their bands must share one launch)
     // AGC block statistics (calculateRMS, Processing.cpp:21-52): per-callback sums of squares of the EQ input / of the band
     // output before the gain, [nSeq][nCallbacks]; nullable
     double* sumsqIn;
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
     const int set = (a.doEq || a.doGain) ? a.setOfSeq[seq] : 0;
     // stages this sequence runs: its active EQ bands (bits 0..19) and the enabled output stages (bits 20..23)
     const unsigned bandBits = a.doEq ? a.bandMask[seq] : 0u;   // bits 0..19 bands, bit 31 = Parallel structure
-    const unsigned mask = (bandBits & a.bandSelect & ((1u << CPQ_NUM_BANDS) - 1u)) | (postMask << CPQ_NUM_BANDS);
+    const unsigned mask = (bandBits & ((bandBits >> 31) ? a.bandSelectPar : a.bandSelect) & ((1u << CPQ_NUM_BANDS) - 1u)) | (postMask << CPQ_NUM_BANDS);
     const int64_t t0 = (int64_t) run * kEqTile;
 
     if (a.doEq)
@@ -1193,7 +1194,9 @@ struct MsArgs
     int64_t T;
 };
 
-template <bool ENCODE>
+// MODE 0 encode (M, S) <- (L, R);  1 decode (L, R) <- (M, S);  and for Mid/Side bands inside the Parallel structure, where the
+// rows carry the bands' summed differences:  2 rows -= encode(L, R);  3 (L, R) += (M + S, M - S).
+template <int MODE>
 __global__ void ms_kernel(MsArgs a)
 {
     const int st = a.streams[blockIdx.y] - a.streamBase;
@@ -1204,17 +1207,37 @@ __global__ void ms_kernel(MsArgs a)
     const int64_t n2 = a.T / 2;
     for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t) gridDim.x * blockDim.x)
     {
-        if (ENCODE)
+        if (MODE == 0 || MODE == 2)
         {
             const double2 l = L[i], r = R[i];
-            M[i] = make_double2((l.x + r.x) * 0.5, (l.y + r.y) * 0.5);
-            S[i] = make_double2((l.x - r.x) * 0.5, (l.y - r.y) * 0.5);
+            const double2 m = make_double2((l.x + r.x) * 0.5, (l.y + r.y) * 0.5);
+            const double2 sd = make_double2((l.x - r.x) * 0.5, (l.y - r.y) * 0.5);
+            if (MODE == 0)
+            {
+                M[i] = m;
+                S[i] = sd;
+            }
+            else
+            {
+                const double2 pm = M[i], ps = S[i];
+                M[i] = make_double2(pm.x - m.x, pm.y - m.y);
+                S[i] = make_double2(ps.x - sd.x, ps.y - sd.y);
+            }
         }
         else
         {
             const double2 m = M[i], sd = S[i];
-            L[i] = make_double2(m.x + sd.x, m.y + sd.y);
-            R[i] = make_double2(m.x - sd.x, m.y - sd.y);
+            if (MODE == 1)
+            {
+                L[i] = make_double2(m.x + sd.x, m.y + sd.y);
+                R[i] = make_double2(m.x - sd.x, m.y - sd.y);
+            }
+            else
+            {
+                const double2 l = L[i], r = R[i];
+                L[i] = make_double2(l.x + (m.x + sd.x), l.y + (m.y + sd.y));
+                R[i] = make_double2(r.x + (m.x - sd.x), r.y + (m.y - sd.y));
+            }
         }
     }
 }

@@ -36,7 +36,7 @@ typedef enum cpq_status
     CPQ_ERR_NOT_READY = 2,    /* process before every stream-channel has an impulse / EQ */
     CPQ_ERR_CUDA = 3,         /* CUDA runtime error or no usable device */
     CPQ_ERR_OOM = 4,
-    CPQ_ERR_UNSUPPORTED = 5,  /* reference feature outside the hot path (Mid/Side bands inside the Parallel structure ...) */
+    CPQ_ERR_UNSUPPORTED = 5,  /* reference feature outside the hot path (host blocks that are not a power of two ...) */
     CPQ_ERR_GEOMETRY = 6      /* stream-channels of one handle must share the layer geometry */
 } cpq_status;
 
@@ -156,7 +156,7 @@ cpq_status cpq_set_direct_head(cpq_handle h, int enable);
  * (eqprocessor/EQProcessor.h:121-138, ProcessingCache.cpp:56-96, Processing.cpp:1019-1276); Serial structure and AGC
  * off unless cpq_set_eq_mode says otherwise.  chan_mode: 0 Stereo, 1 Left, 2 Right, 3 Mid, 4 Side (EQChannelMode,
  * EQProcessor.h:55-62; an active Mid/Side band sends the reference to its node path, Processing.cpp:1037-1044, 690-740,
- * which this library reproduces for the Serial structure on stereo handles).
+ * which this library reproduces on stereo handles, in the Serial and in the Parallel structure).
  * saturation is the already-promoted double, e.g. (double)0.2f.  total_gain_lin is
  * Decibels::decibelsToGain((double)totalGainDb) (settled LinearRamp). stream = -1 with cfg.shared_eq. */
 cpq_status cpq_set_eq(cpq_handle h, int stream, const cpq_svf_coeffs coeffs[CPQ_NUM_BANDS],

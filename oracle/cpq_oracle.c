@@ -1117,15 +1117,16 @@ static void cpqo_agc(cpqo_eq* e, double* L, double* R, int n, double input_rms)
 /* EQProcessor::process(block, params, cache): Processing.cpp:1019-1276 (Serial :1231-1253, Parallel :1132-1228, AGC
  * :1119-1131 + processAGC, total-gain ramp :1262-1274).  When an active band is Mid/Side the reference falls back to
  * the node path process(block) (:1037-1044 -> :484-1017): BandNode::active decides which bands run, Mid/Side bands are
- * encoded / processed / decoded per band (:690-740).  Returns 0 on success, -1 for Parallel together with Mid/Side
- * (the node path's structure cross-fade state is outside this restatement). */
+ * encoded / processed / decoded per band (:690-740; inside the Parallel structure :790-832, from the band input, with
+ * accum += work - src).  The node path's structure cross-fade (:866-940) only runs when the structure changes while
+ * playing; a prepared engine starts in its requested structure.  Returns 0. */
 int cpqo_eq_process(cpqo_eq* e, double* L, double* R, long total, int block)
 {
     const int nch = R ? 2 : 1;
     int node_path = 0;
     for (int b = 0; b < 20; ++b)
         if (e->active[b] && e->mode[b] >= 3) node_path = 1;
-    if (node_path && e->structure != 0) return -1;
+
     const int* on = node_path ? e->node_active : e->active;
     double* src = (double*) malloc(sizeof(double) * (size_t) block * 6);
     double *srcL = src, *srcR = src + block, *workL = src + 2 * block, *workR = src + 3 * block, *accL = src + 4 * block,
@@ -1156,6 +1157,39 @@ int cpqo_eq_process(cpqo_eq* e, double* L, double* R, long total, int block)
             {
                 if (!on[b]) continue;
                 const int mode = e->mode[b];
+                if (mode == 3 || mode == 4)
+                {
+                    if (nch < 2)
+                    {
+                        if (mode == 3)   /* Mono -> Mid: the band on the one channel with the Mid state */
+                        {
+                            memcpy(workL, srcL, sizeof(double) * (size_t) n);
+                            cpqo_band(workL, n, e->coeffs[b], e->state[2][b], e->saturation, 0);
+                            for (int i = 0; i < n; ++i) { accL[i] = accL[i] + workL[i]; accL[i] = accL[i] - srcL[i]; }
+                        }
+                        continue;
+                    }
+                    double* ms = (double*) malloc(sizeof(double) * (size_t) n * 2);
+                    for (int i = 0; i < n; ++i)
+                    {
+                        ms[i] = (srcL[i] + srcR[i]) * 0.5;
+                        ms[n + i] = (srcL[i] - srcR[i]) * 0.5;
+                    }
+                    if (mode == 3) cpqo_band(ms, n, e->coeffs[b], e->state[2][b], e->saturation, 0);
+                    else cpqo_band(ms + n, n, e->coeffs[b], e->state[3][b], e->saturation, 0);
+                    for (int i = 0; i < n; ++i)
+                    {
+                        workL[i] = ms[i] + ms[n + i];
+                        workR[i] = ms[i] - ms[n + i];
+                    }
+                    for (int i = 0; i < n; ++i)
+                    {
+                        accL[i] += workL[i] - srcL[i];
+                        accR[i] += workR[i] - srcR[i];
+                    }
+                    free(ms);
+                    continue;
+                }
                 const int doL = (mode == 0 || mode == 1), doR = (mode == 0 || mode == 2) && nch > 1;
                 const int sv = (mode == 0 && nch >= 2);
                 if (doL)

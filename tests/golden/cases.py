@@ -37,6 +37,7 @@ EQ_CASES = {
     "agc": dict(sr=48000.0, block=512, T=32768, bands=dict(seed=7), kw=dict(agc=True), amp=3.0),
     "agc_parallel_b64": dict(sr=44100.0, block=64, T=16384, bands=dict(seed=9), kw=dict(agc=True, structure=1), amp=0.02),
     "mid_side": dict(sr=48000.0, block=512, T=16384, bands=dict(seed=7, modes=[0, 3, 4, 1, 2] * 4, flat=[5, 6, 7])),
+    "parallel_mid_side": dict(sr=48000.0, block=512, T=16384, bands=dict(seed=7, modes=[0, 3, 4, 1, 2] * 4), kw=dict(structure=1), amp=1.0),
     "mid_side_agc": dict(sr=48000.0, block=1024, T=16384, bands=dict(seed=10, modes=[3, 4] * 10), kw=dict(agc=True)),
 }
 

@@ -191,6 +191,8 @@ EQ_MODE_CASES = [
     ("mid_side", dict(seed=7, modes=[0, 3, 4, 1, 2] * 4, flat=[5, 6, 7]), dict()),
     ("mid_side_all", dict(seed=12, modes=[3, 4] * 10), dict(saturation=0.0)),
     ("mid_side_agc", dict(seed=10, modes=[4, 0, 3, 0] * 5), dict(agc=True)),
+    ("parallel_mid_side", dict(seed=7, modes=[0, 3, 4, 1, 2] * 4, flat=[5, 6]), dict(structure=1)),
+    ("parallel_mid_side_only_agc", dict(seed=9, modes=[3, 4] * 10), dict(structure=1, agc=True)),
 ]
 
 
@@ -219,11 +221,11 @@ def test_eq_modes_match_reference(checker, name, bkw, kw, block, T):
 def test_eq_modes_batch_mixed_streams(checker):
     """Several streams with different structures / AGC / Mid-Side settings in one handle, conv -> EQ -> epilogue, odd chunking."""
     sr, block, T, ir_len = 48000.0, 512, 16384, 20000
-    settings = [dict(), dict(structure=1), dict(agc=True), dict(agc=True, structure=1), dict(), dict(agc=True), dict()]
-    bkws = [dict(seed=40), dict(seed=41), dict(seed=42, modes=[3, 0, 4, 1, 2] * 4), dict(seed=43), dict(seed=44, modes=[4] * 20),
-            dict(seed=45), dict(seed=46, modes=[0, 0, 3] + [0] * 17)]
+    settings = [dict(), dict(structure=1), dict(agc=True), dict(agc=True, structure=1), dict(), dict(agc=True), dict(), dict(structure=1)]
+    bkws = [dict(seed=40), dict(seed=41), dict(seed=42, modes=[3, 0, 4, 1, 2] * 4), dict(seed=43, modes=[0, 4, 3, 0] * 5), dict(seed=44, modes=[4] * 20),
+            dict(seed=45), dict(seed=46, modes=[0, 0, 3] + [0] * 17), dict(seed=47, modes=[2, 3] * 10)]
     n = len(settings)
-    # the third/fifth/seventh streams carry Mid/Side bands: together with a Parallel stream the handle is rejected
+    # serial and Parallel streams, with and without Mid/Side bands and AGC, share one handle
     eng = ConvoPeqEngine(n, 2, sr, block, T, conv_boundary=capi.CONV_OUTER, workspace_bytes=3 * 2 * (T // block + 40) * 512 * 16 * 5)
     x = np.stack([signals.noise(T, 500 + i, 0.3) for i in range(2 * n)])
     irs = [signals.synth_ir(ir_len, 600 + i) for i in range(2 * n)]
@@ -232,12 +234,6 @@ def test_eq_modes_batch_mixed_streams(checker):
             eng.set_impulse(s, ch, irs[2 * s + ch], 1.0, None)
         eng.set_eq(s, signals.to_band(signals.band_params(**bkws[s])), 0.2, 0.0, settings[s].get("structure", 0), settings[s].get("agc", False))
     eng.set_epilogue(1.1, 0)
-    y = x.copy()
-    with pytest.raises(capi.CpqError):
-        eng.process(y, capi.STAGE_ALL)
-    for s in (1, 3):   # make the Parallel streams Serial: now everything is supported
-        eng.set_eq(s, signals.to_band(signals.band_params(**bkws[s])), 0.2, 0.0, 0, settings[s].get("agc", False))
-        settings[s] = dict(settings[s], structure=0)
     y = x.copy()
     eng.process(y, capi.STAGE_ALL)
     eng.close()
@@ -415,7 +411,8 @@ def test_error_paths_fail_loudly():
         mono.set_eq(0, bands)                      # Mid/Side bands need both channels of a stream
     assert e.value.status == capi.ERR_UNSUPPORTED
     mono.close()
-    eng.set_eq(0, bands, structure=1)              # Mid/Side inside the Parallel structure: refused at process time
+    eng.set_eq(0, bands, agc=True)
+    eng.schedule_total_gain(0, 2, -3.0)            # with AGC the reference never applies the total-gain ramp: refused
     with pytest.raises(capi.CpqError) as e:
         eng.process(np.zeros((2, 4096)), capi.STAGE_EQ)
     assert e.value.status == capi.ERR_UNSUPPORTED

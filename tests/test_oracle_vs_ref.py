@@ -84,6 +84,8 @@ def test_eq_restatement_equals_reference(oracle, ref, name, bkw, kw):
     ("agc_parallel", dict(seed=11), dict(agc=True, structure=1)),
     ("mid_side", dict(seed=7, modes=[0, 3, 4, 1, 2] * 4, flat=[5, 6, 7]), {}),
     ("mid_side_agc", dict(seed=10, modes=[3, 4] * 10), dict(agc=True)),
+    ("parallel_mid_side", dict(seed=7, modes=[0, 3, 4, 1, 2] * 4, flat=[5, 6]), dict(structure=1)),
+    ("parallel_mid_side_agc", dict(seed=9, modes=[3, 4] * 10), dict(structure=1, agc=True)),
 ])
 @pytest.mark.parametrize("block", [64, 512, 1000])
 def test_eq_modes_restatement_equals_reference(oracle, ref, name, bkw, kw, block):
