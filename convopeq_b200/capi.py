@@ -36,6 +36,10 @@ class EqBandParams(C.Structure):
                 ("enabled", C.c_int32), ("type", C.c_int32), ("channel_mode", C.c_int32)]
 
 
+class IrScale(C.Structure):
+    _fields_ = [("scale_factor", C.c_double), ("has_scale_factor", C.c_int32), ("additional_attenuation_db", C.c_float)]
+
+
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("n_streams", C.c_int32), ("n_channels", C.c_int32),
                 ("block_size", C.c_int32), ("sample_rate", C.c_double), ("max_samples", C.c_int64),
@@ -69,6 +73,7 @@ EXPORTS = [
     "cpq_latency", "cpq_get_timings", "cpq_get_eq_state", "cpq_cuda_stream", "cpq_kernel_launch_count",
     "cpq_plan_layout", "cpq_set_eq_mode", "cpq_band_node_active", "cpq_get_agc_state",
     "cpq_set_mix", "cpq_ir_peak_latency", "cpq_set_direct_head", "cpq_parse_eq_preset",
+    "cpq_ir_scale_factor", "cpq_ir_freq_peak_gain",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -115,6 +120,9 @@ def load() -> C.CDLL:
     L.cpq_set_conv_input_trim.argtypes = [vp, C.c_double]
     L.cpq_set_mix.argtypes = [vp, C.c_float, C.c_int]
     L.cpq_set_direct_head.argtypes = [vp, C.c_int]
+    L.cpq_ir_scale_factor.argtypes = [dp, dp, C.c_int, dp, dp, C.c_int, C.c_double, C.POINTER(IrScale)]
+    L.cpq_ir_freq_peak_gain.argtypes = [dp, dp, C.c_int]
+    L.cpq_ir_freq_peak_gain.restype = C.c_double
     L.cpq_parse_eq_preset.argtypes = [C.c_char_p, C.POINTER(EqBandParams), C.POINTER(C.c_float)]
     L.cpq_ir_peak_latency.argtypes = [dp, dp, C.c_int]
     L.cpq_output_filter_design.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, dp]

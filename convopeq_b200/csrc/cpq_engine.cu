@@ -1890,6 +1890,23 @@ cpq_status cpq_set_output_filter(cpq_handle h, int enabled, int conv_is_last, in
     return CPQ_OK;
 }
 
+cpq_status cpq_ir_scale_factor(const double* ir_l, const double* ir_r, int len, const double* cur_l, const double* cur_r, int cur_len,
+                               double cur_scale, cpq_ir_scale* out)
+{
+    if (!out || len < 0 || (len > 0 && !ir_l)) return CPQ_ERR_INVALID;
+    const double* ch[2] = { ir_l, ir_r };
+    const double* cur[2] = { cur_l, cur_r };
+    cpq::irScaleFactor(ch, ir_l ? (ir_r ? 2 : 1) : 0, len, cur_l ? cur : nullptr, cur_l ? (cur_r ? 2 : 1) : 0, cur_len, cur_scale, out);
+    return CPQ_OK;
+}
+
+double cpq_ir_freq_peak_gain(const double* ir_l, const double* ir_r, int len)
+{
+    if (!ir_l || len <= 0) return 1.0;
+    const double* ch[2] = { ir_l, ir_r };
+    return cpq::irFreqPeakGain(ch, ir_r ? 2 : 1, len);
+}
+
 int cpq_parse_eq_preset(const char* text, cpq_eq_band_params bands[CPQ_NUM_BANDS], float* total_gain_db)
 {
     if (!text || !bands || !total_gain_db) return -1;

@@ -18,7 +18,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cctype>
+#include <complex>
 #include <cstdlib>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -420,6 +422,149 @@ inline bool designBand(int type, float freq, float gainDb, float q, double sr, c
         default: out->m0 = 1.0; out->m1 = -k; out->m2 = -1.0; break;
     }
     return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// IR preparation (host, one-time): IRConverter::computeScaleFactor (IRConverter.cpp:13-196) with
+// IRAnalyzer::estimateMaxFrequencyResponseGain (IRAnalyzer.cpp:63-155).
+// ------------------------------------------------------------------------------------------------
+inline double irFreqPeakGain(const double* const* ch, int nch, int len)
+{
+    if (len <= 0 || nch <= 0) return 1.0;
+    const int copyLen = std::min(len, 65536);   // kMaxAnalysisWindow
+    int n = 1;
+    while (n < copyLen) n <<= 1;
+    if (n < 2) return 1.0;
+    // Tukey window, alpha = 0.5, defined over the FFT length; coherent gain = its mean over the copied samples
+    const double span = 0.5 * (double) (n - 1), taper = 0.5 * span;
+    std::vector<double> win((size_t) n);
+    for (int i = 0; i < n; ++i)
+    {
+        const double t = (double) i;
+        if (t < taper) win[(size_t) i] = 0.5 * (1.0 + std::cos(2.0 * kPi * t / span - kPi));
+        else if (t > (double) (n - 1) - taper) win[(size_t) i] = 0.5 * (1.0 + std::cos(2.0 * kPi * (t - ((double) (n - 1) - taper)) / span));
+        else win[(size_t) i] = 1.0;
+    }
+    double mean = 0.0;
+    for (int i = 0; i < copyLen; ++i) mean += win[(size_t) i];
+    mean /= (double) copyLen;
+    if (mean < 1e-18) return 1.0;
+    int log2n = 0;
+    while ((1 << log2n) < n) ++log2n;
+    std::vector<std::complex<double>> tw((size_t) n / 2), z((size_t) n);
+    for (int k = 0; k < n / 2; ++k) tw[(size_t) k] = std::polar(1.0, -2.0 * kPi * (double) k / (double) n);
+    std::vector<double> mag((size_t) n / 2 + 1);
+    double best = 0.0;
+    for (int c = 0; c < nch; ++c)
+    {
+        if (!ch[c]) continue;
+        for (int i = 0; i < n; ++i)
+        {
+            unsigned r = 0;
+            for (int b = 0; b < log2n; ++b) r |= ((unsigned) i >> b & 1u) << (log2n - 1 - b);
+            z[r] = i < copyLen ? ch[c][i] * win[(size_t) i] : 0.0;
+        }
+        for (int half = 1; half < n; half <<= 1)
+            for (int i = 0; i < n; i += 2 * half)
+                for (int j = 0; j < half; ++j)
+                {
+                    const std::complex<double> t = tw[(size_t) j * (size_t) (n / (2 * half))] * z[(size_t) (i + j + half)];
+                    const std::complex<double> u = z[(size_t) (i + j)];
+                    z[(size_t) (i + j)] = u + t;
+                    z[(size_t) (i + j + half)] = u - t;
+                }
+        const int nb = n / 2;
+        for (int b = 0; b <= nb; ++b)
+        {
+            mag[(size_t) b] = (b == 0 || b == nb) ? std::fabs(z[(size_t) b].real()) : std::abs(z[(size_t) b]);
+            best = std::max(best, mag[(size_t) b]);
+        }
+        for (int b = 1; b < nb - 1; ++b)   // three-point log-parabolic refinement of local maxima
+        {
+            const double ym = mag[(size_t) b - 1], y0 = mag[(size_t) b], yp = mag[(size_t) b + 1];
+            if (!(y0 > ym && y0 > yp && y0 > 1e-18 && ym > 1e-18 && yp > 1e-18)) continue;
+            const double lm = std::log(ym), l0 = std::log(y0), lp = std::log(yp), den = lm - 2.0 * l0 + lp;
+            if (std::fabs(den) > 1e-18) best = std::max(best, y0 * std::exp(-(0.5 * (lm - lp) / den) * (l0 - lm)));
+        }
+    }
+    best /= mean;
+    return best > 1e-18 ? best : 1.0;
+}
+
+inline void irPeakAndRms(const double* const* ch, int nch, int len, double scale, double& peak, double& rms)
+{
+    double e = 0.0;
+    peak = 0.0;
+    for (int c = 0; c < nch; ++c)
+        for (int i = 0; i < len; ++i)
+        {
+            const double v = ch[c][i] * scale;
+            peak = std::max(peak, std::fabs(v));
+            e += v * v;
+        }
+    rms = (nch * len > 0) ? std::sqrt(e / (double) (nch * len)) : 0.0;
+}
+
+inline void irScaleFactor(const double* const* ch, int nch, int len, const double* const* cur, int curCh, int curLen, double curScale,
+                          cpq_ir_scale* out)
+{
+    out->scale_factor = 1.0;
+    out->has_scale_factor = 0;
+    out->additional_attenuation_db = 0.0f;
+    double scale = 1.0;
+    if (len > 0 && nch > 0)
+    {
+        double maxEnergy = 0.0;   // computeEnergyScale: loudest channel to unit energy, then -6 dB
+        for (int c = 0; c < nch; ++c)
+        {
+            double e = 0.0;
+            for (int i = 0; i < len; ++i) e += ch[c][i] * ch[c][i];
+            if (std::isfinite(e) && e > 1.0e-18) maxEnergy = std::max(maxEnergy, e);
+        }
+        if (maxEnergy > 1.0e-18 && std::isfinite(maxEnergy)) scale = (1.0 / std::sqrt(maxEnergy)) * 0.5011872336272722;
+    }
+    if (!(scale > 0.0) || !std::isfinite(scale)) return;
+    out->has_scale_factor = 1;
+    double result = scale, peak = 0.0, rms = 0.0;
+    if (len > 0 && nch > 0) irPeakAndRms(ch, nch, len, 1.0, peak, rms);
+    const double fgain = (len > 0 && nch > 0) ? irFreqPeakGain(ch, nch, len) : 1.0;   // of the unscaled IR, like analyzeIR
+    double attDb = 0.0;
+    if (peak * scale > 0.5)   // kMaxEffectivePeak
+    {
+        const double k = 0.5 / (peak * scale);
+        result *= k;
+        scale *= k;
+        attDb += -20.0 * std::log10(k);
+    }
+    if (rms * scale > 0.25)   // kMaxEffectiveRms, judged after the peak clamp
+    {
+        const double k = 0.25 / (rms * scale);
+        result *= k;
+        attDb += -20.0 * std::log10(k);
+    }
+    if (fgain > 1.41)         // kMaxEffectiveFreqResponse (+3 dB)
+    {
+        const double k = 1.41 / fgain;
+        result *= k;
+        attDb += -20.0 * std::log10(k);
+    }
+    out->additional_attenuation_db = (float) attDb;
+    if (cur && curCh > 0 && curLen > 0)   // jump protection against the IR that is playing
+    {
+        double cp, cr, np_, nr;
+        irPeakAndRms(cur, curCh, curLen, curScale, cp, cr);
+        irPeakAndRms(ch, nch, len, result, np_, nr);
+        const bool peakJump = cp > 1.0e-9 && np_ > cp * 4.0 && np_ > 0.5, rmsJump = cr > 1.0e-9 && nr > cr * 4.0 && nr > 0.25;
+        if (peakJump || rmsJump)
+        {
+            double kp = std::numeric_limits<double>::infinity(), kr = kp;
+            if (np_ > 1.0e-12 && cp > 1.0e-12) kp = cp * 4.0 / np_;
+            if (nr > 1.0e-12 && cr > 1.0e-12) kr = cr * 4.0 / nr;
+            const double k = std::min(kp, kr);
+            if (std::isfinite(k) && k > 0.0 && k < 1.0) result *= k;
+        }
+    }
+    out->scale_factor = result;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -234,6 +234,25 @@ def load_eq_preset(text: str, bands: Optional[Sequence[Band]] = None, total_gain
     return out, float(g.value), ignored
 
 
+def ir_scale_factor(ir_l: np.ndarray, ir_r: Optional[np.ndarray] = None, cur_l: Optional[np.ndarray] = None,
+                    cur_r: Optional[np.ndarray] = None, cur_scale: float = 1.0):
+    """IRConverter::computeScaleFactor (host-only) -> (scale_factor, has_scale_factor, additional_attenuation_db)."""
+    arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (ir_l, ir_r, cur_l, cur_r)]
+    ptr = lambda a: a.ctypes.data_as(_dp) if a is not None else None
+    out = capi.IrScale()
+    st = capi.load().cpq_ir_scale_factor(ptr(arrs[0]), ptr(arrs[1]), arrs[0].size, ptr(arrs[2]), ptr(arrs[3]),
+                                         0 if arrs[2] is None else arrs[2].size, cur_scale, C.byref(out))
+    if st != capi.OK:
+        raise capi.CpqError(st, "cpq_ir_scale_factor")
+    return float(out.scale_factor), bool(out.has_scale_factor), float(out.additional_attenuation_db)
+
+
+def ir_freq_peak_gain(ir_l: np.ndarray, ir_r: Optional[np.ndarray] = None) -> float:
+    a = np.ascontiguousarray(ir_l, dtype=np.float64)
+    b = None if ir_r is None else np.ascontiguousarray(ir_r, dtype=np.float64)
+    return float(capi.load().cpq_ir_freq_peak_gain(a.ctypes.data_as(_dp), b.ctypes.data_as(_dp) if b is not None else None, a.size))
+
+
 def ir_peak_latency(ir_l: np.ndarray, ir_r: Optional[np.ndarray] = None) -> int:
     """LoaderThread::estimatePeakLatencySamples (host-only helper of the C ABI)."""
     a = np.ascontiguousarray(ir_l, dtype=np.float64)

@@ -211,6 +211,20 @@ cpq_status cpq_set_mix(cpq_handle h, float mix, int dry_delay_samples);
  * StereoConvolver::init receives as peakDelay: energy centroid of the first 99.9 % of the energy, maximum over channels
  * (ir_r nullable), rounded, clamped to [0, len - 1]. */
 int cpq_ir_peak_latency(const double* ir_l, const double* ir_r, int len);
+/* Host-only: IRConverter::computeScaleFactor (IRConverter.cpp:13-196; ScaleFactorResult IRConverter.h) -- the `scale`
+ * StereoConvolver::init passes to SetImpulse: loudest channel to unit energy with a -6 dB margin, then the peak (0.5), RMS
+ * (0.25) and frequency-response (+3 dB, IRAnalyzer::estimateMaxFrequencyResponseGain, IRAnalyzer.cpp:63-155) clamps, then the
+ * jump protection against the IR that is currently playing (cur_* nullable / 0).  ir_r / cur_r nullable (mono). */
+typedef struct cpq_ir_scale
+{
+    double scale_factor;
+    int32_t has_scale_factor;
+    float additional_attenuation_db;
+} cpq_ir_scale;
+cpq_status cpq_ir_scale_factor(const double* ir_l, const double* ir_r, int len, const double* cur_l, const double* cur_r, int cur_len,
+                               double cur_scale, cpq_ir_scale* out);
+/* Host-only: IRAnalyzer::estimateMaxFrequencyResponseGain on its own (linear gain; 1.0 for an empty IR). */
+double cpq_ir_freq_peak_gain(const double* ir_l, const double* ir_r, int len);
 /* Host-only: the three stages' normalised coefficients {b0,b1,b2,a1,a2} x 3 as OutputFilter::prepare computes them. */
 void cpq_output_filter_design(double sample_rate, int conv_is_last, int hc_mode, int lc_mode, int lp_mode, double out[15]);
 

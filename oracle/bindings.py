@@ -176,6 +176,16 @@ class _Base:
             self._f("out_destroy")(h)
         return y
 
+    # ---- IR preparation ----------------------------------------------------------------------
+    def ir_freq_peak_gain(self, ir_l: np.ndarray, ir_r: Optional[np.ndarray] = None) -> float:
+        """IRAnalyzer::estimateMaxFrequencyResponseGain."""
+        a = np.ascontiguousarray(ir_l, dtype=np.float64)
+        b = None if ir_r is None else np.ascontiguousarray(ir_r, dtype=np.float64)
+        f = self._f("ir_freq_peak_gain")
+        f.argtypes = [_dp, _dp, C.c_int]
+        f.restype = C.c_double
+        return float(f(_p(a), _p(b), a.size))
+
     # ---- EQ ----------------------------------------------------------------------------------
     def eq_design(self, type_: int, f: float, gain_db: float, q: float, sr: float) -> np.ndarray:
         out = np.zeros(6)
@@ -243,6 +253,10 @@ class Oracle(_Base):
         L.cpqo_outer_mix.argtypes = [_dp, _dp, C.c_long, C.c_float, C.c_int]
         L.cpqo_outer_mix.restype = None
         L.cpqo_ir_peak_latency.argtypes = [_dp, _dp, C.c_int]
+        L.cpqo_ir_freq_peak_gain.argtypes = [_dp, _dp, C.c_int]
+        L.cpqo_ir_freq_peak_gain.restype = C.c_double
+        L.cpqo_ir_scale_factor.argtypes = [_dp, _dp, C.c_int, _dp, _dp, C.c_int, C.c_double, _dp]
+        L.cpqo_ir_scale_factor.restype = None
         L.cpqo_equal_power_sin.argtypes = [C.c_double]
         L.cpqo_equal_power_sin.restype = C.c_double
         L.cpqo_db_to_gain.argtypes = [C.c_float]
@@ -305,6 +319,16 @@ class Oracle(_Base):
         a = np.ascontiguousarray(ir_l, dtype=np.float64)
         b = None if ir_r is None else np.ascontiguousarray(ir_r, dtype=np.float64)
         return int(self.lib.cpqo_ir_peak_latency(_p(a), _p(b), a.size))
+
+    def ir_scale_factor(self, ir_l, ir_r=None, cur_l=None, cur_r=None, cur_scale: float = 1.0):
+        """IRConverter::computeScaleFactor -> (scaleFactor, hasScaleFactor, additionalAttenuationDb)."""
+        a = np.ascontiguousarray(ir_l, dtype=np.float64)
+        b = None if ir_r is None else np.ascontiguousarray(ir_r, dtype=np.float64)
+        c = None if cur_l is None else np.ascontiguousarray(cur_l, dtype=np.float64)
+        d = None if cur_r is None else np.ascontiguousarray(cur_r, dtype=np.float64)
+        out = np.zeros(3)
+        self.lib.cpqo_ir_scale_factor(_p(a), _p(b), a.size, _p(c), _p(d), 0 if c is None else c.size, cur_scale, _p(out))
+        return float(out[0]), bool(out[1]), float(out[2])
 
     def outer_wet(self, x: np.ndarray, mix: float = 1.0) -> np.ndarray:
         d = np.ascontiguousarray(x, dtype=np.float64).copy()

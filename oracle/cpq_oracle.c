@@ -887,6 +887,178 @@ int cpqo_ir_peak_latency(const double* ir_l, const double* ir_r, int len)
     return lat;
 }
 
+/* IRAnalyzer::estimateMaxFrequencyResponseGain, IRAnalyzer.cpp:63-155: Tukey(0.5)-windowed radix-2 FFT of the first
+ * min(len, 65536) samples (twiddles by repeated multiplication, like simpleRealFFT :14-59), largest bin magnitude over the
+ * channels refined by the three-point log-parabolic interpolation, divided by the window's mean over the copied samples. */
+double cpqo_ir_freq_peak_gain(const double* ir_l, const double* ir_r, int len)
+{
+    if (len <= 0 || !ir_l) return 1.0;
+    const int copy_len = len < 65536 ? len : 65536;
+    const int n = cpqo_next_pow2(copy_len);
+    if (n < 2) return 1.0;
+    const double pi = CPQO_PI, alpha = 0.5;
+    const double taper = alpha * (double) (n - 1) * 0.5;
+    double* win = (double*) malloc(sizeof(double) * (size_t) n);
+    for (int i = 0; i < n; ++i)
+    {
+        const double t = (double) i;
+        if (t < taper) win[i] = 0.5 * (1.0 + cos((2.0 * pi * t) / (alpha * (double) (n - 1)) - pi));
+        else if (t > (double) (n - 1) - taper) win[i] = 0.5 * (1.0 + cos((2.0 * pi * (t - ((double) (n - 1) - taper))) / (alpha * (double) (n - 1))));
+        else win[i] = 1.0;
+    }
+    double wsum = 0.0;
+    for (int i = 0; i < copy_len; ++i) wsum += win[i];
+    const double wmean = wsum / (double) copy_len;
+    if (wmean < 1e-18) { free(win); return 1.0; }
+    double* re = (double*) malloc(sizeof(double) * (size_t) n);
+    double* im = (double*) malloc(sizeof(double) * (size_t) n);
+    double* mags = (double*) malloc(sizeof(double) * (size_t) (n / 2 + 1));
+    double max_mag = 0.0;
+    const double* chans[2] = { ir_l, ir_r };
+    for (int c = 0; c < 2; ++c)
+    {
+        const double* src = chans[c];
+        if (!src) continue;
+        for (int i = 0; i < n; ++i) { re[i] = i < copy_len ? src[i] * win[i] : 0.0; im[i] = 0.0; }
+        for (int i = 1, j = 0; i < n; ++i)
+        {
+            int bit = n >> 1;
+            while (j & bit) { j ^= bit; bit >>= 1; }
+            j ^= bit;
+            if (i < j) { const double t = re[i]; re[i] = re[j]; re[j] = t; }
+        }
+        for (int l = 2; l <= n; l <<= 1)
+        {
+            const double ang = -2.0 * pi / (double) l, wr = cos(ang), wi = sin(ang);
+            for (int i = 0; i < n; i += l)
+            {
+                double tr = 1.0, ti = 0.0;
+                for (int j = 0; j < l / 2; ++j)
+                {
+                    const int i1 = i + j, i2 = i + j + l / 2;
+                    const double xr = tr * re[i2] - ti * im[i2], xi = tr * im[i2] + ti * re[i2];
+                    const double ur = re[i1], ui = im[i1];
+                    re[i1] = ur + xr; im[i1] = ui + xi;
+                    re[i2] = ur - xr; im[i2] = ui - xi;
+                    const double nr = tr * wr - ti * wi, ni = tr * wi + ti * wr;
+                    tr = nr; ti = ni;
+                }
+            }
+        }
+        const int nb = n / 2;
+        for (int b = 0; b <= nb; ++b)
+        {
+            /* the CCS packing keeps only the real parts of bins 0 and N/2 */
+            mags[b] = (b == 0 || b == nb) ? fabs(re[b]) : sqrt(re[b] * re[b] + im[b] * im[b]);
+            if (mags[b] > max_mag) max_mag = mags[b];
+        }
+        for (int b = 1; b < nb - 1; ++b)
+        {
+            const double ym1 = mags[b - 1], y0 = mags[b], yp1 = mags[b + 1];
+            if (y0 > ym1 && y0 > yp1 && y0 > 1e-18 && ym1 > 1e-18 && yp1 > 1e-18)
+            {
+                const double lm = log(ym1), l0 = log(y0), lp = log(yp1);
+                const double den = lm - 2.0 * l0 + lp;
+                if (fabs(den) > 1e-18)
+                {
+                    const double delta = 0.5 * (lm - lp) / den;
+                    const double v = y0 * exp(-delta * (l0 - lm));
+                    if (v > max_mag) max_mag = v;
+                }
+            }
+        }
+    }
+    free(win); free(re); free(im); free(mags);
+    max_mag /= wmean;
+    return max_mag > 1e-18 ? max_mag : 1.0;
+}
+
+/* IRConverter::computeScaleFactor, IRConverter.cpp:13-196: energy normalisation with a -6 dB margin, peak / RMS / frequency
+ * response clamps, and the jump protection against the IR that is playing.  out = { scaleFactor, hasScaleFactor,
+ * additionalAttenuationDb (float in the reference) }.  cur_* nullable.  PARITY: the FFT stage is pinned against the
+ * reference's IRAnalyzer.cpp; the arithmetic around it restates IRConverter.cpp (which needs JUCE's file classes). */
+void cpqo_ir_scale_factor(const double* ir_l, const double* ir_r, int len, const double* cur_l, const double* cur_r, int cur_len,
+                          double cur_scale, double* out3)
+{
+    out3[0] = 1.0; out3[1] = 0.0; out3[2] = 0.0;
+    if (len <= 0 || !ir_l) { out3[1] = 1.0; return; }   /* computeEnergyScale returns 1.0 for an empty buffer */
+    const double* chans[2] = { ir_l, ir_r };
+    const int nch = ir_r ? 2 : 1;
+    double max_energy = 0.0;
+    for (int c = 0; c < nch; ++c)
+    {
+        double e = 0.0;
+        for (int i = 0; i < len; ++i) e += chans[c][i] * chans[c][i];
+        if (isfinite(e) && e > 1.0e-18 && e > max_energy) max_energy = e;
+    }
+    double scale = 1.0;
+    if (max_energy > 1.0e-18 && isfinite(max_energy)) scale = (1.0 / sqrt(max_energy)) * 0.5011872336272722;
+    if (scale <= 0.0 || !isfinite(scale)) return;
+    double result = scale;
+    out3[1] = 1.0;
+    double peak = 0.0, esum = 0.0;
+    for (int c = 0; c < nch; ++c)
+        for (int i = 0; i < len; ++i)
+        {
+            const double v = chans[c][i];
+            if (fabs(v) > peak) peak = fabs(v);
+            esum += v * v;
+        }
+    const double rms = sqrt(esum / (double) (nch * len));
+    const double fgain = cpqo_ir_freq_peak_gain(ir_l, ir_r, len);
+    double peak_db = 0.0, rms_db = 0.0, freq_db = 0.0;
+    if (peak * scale > 0.5)
+    {
+        const double k = 0.5 / (peak * scale);
+        result *= k; scale *= k;
+        peak_db = -20.0 * log10(k);
+    }
+    if (rms * scale > 0.25)
+    {
+        const double k = 0.25 / (rms * scale);
+        result *= k;
+        rms_db = -20.0 * log10(k);
+    }
+    if (fgain > 1.41)
+    {
+        const double k = 1.41 / fgain;
+        result *= k;
+        freq_db = -20.0 * log10(k);
+    }
+    out3[2] = (double) (float) (peak_db + rms_db + freq_db);
+    if (cur_l && cur_len > 0)
+    {
+        const double* cc[2] = { cur_l, cur_r };
+        const int cn = cur_r ? 2 : 1;
+        double cpk = 0.0, cen = 0.0, npk = 0.0, nen = 0.0;
+        for (int c = 0; c < cn; ++c)
+            for (int i = 0; i < cur_len; ++i)
+            {
+                const double v = cc[c][i] * cur_scale;
+                if (fabs(v) > cpk) cpk = fabs(v);
+                cen += v * v;
+            }
+        for (int c = 0; c < nch; ++c)
+            for (int i = 0; i < len; ++i)
+            {
+                const double v = chans[c][i] * result;
+                if (fabs(v) > npk) npk = fabs(v);
+                nen += v * v;
+            }
+        const double crms = sqrt(cen / (double) (cn * cur_len)), nrms = sqrt(nen / (double) (nch * len));
+        const int pj = cpk > 1.0e-9 && npk > cpk * 4.0 && npk > 0.5, rj = crms > 1.0e-9 && nrms > crms * 4.0 && nrms > 0.25;
+        if (pj || rj)
+        {
+            double kp = INFINITY, kr = INFINITY;
+            if (npk > 1.0e-12 && cpk > 1.0e-12) kp = (cpk * 4.0) / npk;
+            if (nrms > 1.0e-12 && crms > 1.0e-12) kr = (crms * 4.0) / nrms;
+            const double k = kp < kr ? kp : kr;
+            if (isfinite(k) && k > 0.0 && k < 1.0) result *= k;
+        }
+    }
+    out3[0] = result;
+}
+
 /* ------------------------------------------------------------------------------------------
  * 20-band EQ.  eqprocessor/EQProcessor.{Coefficients,Processing,ProcessingCache}.cpp
  * ------------------------------------------------------------------------------------------ */

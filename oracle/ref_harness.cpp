@@ -39,6 +39,7 @@
 #undef private
 #undef protected
 #include "UltraHighRateDCBlocker.h"
+#include "IRAnalyzer.h"
 
 // ---- members normally provided by EQProcessor.Core.cpp -----------------------------------
 EQProcessor::EQProcessor()
@@ -388,5 +389,14 @@ void cpqref_out_process(void* h, double* L, double* R, long total, int block, in
     }
 }
 
-int cpqref_abi_version(void) { return 2; }
+// IRAnalyzer::estimateMaxFrequencyResponseGain (src/IRAnalyzer.cpp:63-155), the FFT stage of IRConverter::computeScaleFactor
+// (IRConverter.cpp itself needs JUCE's audio-format classes and is not compiled).
+double cpqref_ir_freq_peak_gain(const double* l, const double* r, int n)
+{
+    double* ch[2] = { const_cast<double*>(l), const_cast<double*>(r) };
+    juce::AudioBuffer<double> buf(ch, r ? 2 : 1, n);
+    return IRAnalyzer::estimateMaxFrequencyResponseGain(buf);
+}
+
+int cpqref_abi_version(void) { return 3; }
 }

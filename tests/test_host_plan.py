@@ -167,3 +167,29 @@ def test_eq_preset_reference_fixture():
     n_filters = sum(1 for ln in text.splitlines() if ln.strip().lower().startswith("filter"))
     assert ignored == max(0, n_filters - 20) and sum(b.enabled for b in bands) == min(n_filters, 20)
     assert gain < 0.0 and bands[0].type == 0 and bands[0].enabled and all(b.q > 0 for b in bands)
+
+
+def test_ir_scale_factor_matches_restatement(oracle):
+    """IRConverter::computeScaleFactor: the product's host helper against the restatement (whose FFT stage is pinned to the
+    reference's IRAnalyzer.cpp in tests/test_oracle_vs_ref.py); clamps and jump protection exercised."""
+    from convopeq_b200.engine import ir_scale_factor, ir_freq_peak_gain
+    t = np.arange(20000)
+    ring = np.sin(2 * np.pi * 0.0123 * t) * np.exp(-t / 5000.0)                 # narrow resonance: frequency clamp
+    spike = np.zeros(4000); spike[10] = 1.0; spike[500:] = 1e-3                # peak clamp after the energy scale
+    cases = [(signals.synth_ir(1000, 1), None), (signals.synth_ir(65536, 2), np.roll(signals.synth_ir(65536, 3), 900)),
+             (signals.synth_ir(100000, 4), signals.synth_ir(100000, 5)), (ring, None), (spike, 0.5 * spike), (np.ones(7), None)]
+    for a, b in cases:
+        g, w = ir_freq_peak_gain(a, b), oracle.ir_freq_peak_gain(a, b)
+        assert abs(g - w) <= 1e-10 * w
+        got, want = ir_scale_factor(a, b), oracle.ir_scale_factor(a, b)
+        assert got[1] and want[1] and abs(got[0] - want[0]) <= 1e-10 * want[0] and abs(got[2] - want[2]) <= 1e-4
+    assert ir_scale_factor(ring)[2] > 50.0 and ir_scale_factor(spike)[2] > 0.0
+    # jump protection against the playing IR: after the peak / RMS clamps the new IR never exceeds 0.5 / 0.25, which are
+    # also the protection's absolute thresholds, so it cannot lower the scale further -- same answer with and without
+    loud = signals.synth_ir(3000, 6) * 50.0
+    quiet = signals.synth_ir(3000, 7)
+    free = ir_scale_factor(loud)
+    held = ir_scale_factor(loud, None, quiet, None, 0.01)
+    want = oracle.ir_scale_factor(loud, None, quiet, None, 0.01)
+    assert abs(held[0] - want[0]) <= 1e-10 * want[0] and abs(held[0] - free[0]) <= 1e-12 * free[0]
+    assert ir_scale_factor(np.zeros(100)) == (1.0, True, 0.0)

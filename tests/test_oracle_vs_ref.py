@@ -139,3 +139,14 @@ def test_output_stage_restatement_equals_reference(oracle, ref, kw, sr):
     # amplified by the 20 Hz high-pass pole radius
     am, bm = oracle.output_run(x[:1], sr, 480, **kw), ref.output_run(x[:1], sr, 480, **kw)
     assert np.abs(am - bm).max() <= 1e-11
+
+
+def test_ir_frequency_peak_gain_restatement_equals_reference(oracle, ref):
+    """IRAnalyzer::estimateMaxFrequencyResponseGain (src/IRAnalyzer.cpp compiled in place) -- the FFT stage of
+    IRConverter::computeScaleFactor (SURVEY 8f-2)."""
+    t = np.arange(20000)
+    ring = np.sin(2 * np.pi * 0.0123 * t) * np.exp(-t / 5000.0)
+    for a, b in [(signals.synth_ir(1000, 1), None), (signals.synth_ir(65536, 2), np.roll(signals.synth_ir(65536, 3), 900)),
+                 (signals.synth_ir(100000, 4), signals.synth_ir(100000, 5)), (signals.synth_ir(3, 6), None), (ring, None)]:
+        x, y = oracle.ir_freq_peak_gain(a, b), ref.ir_freq_peak_gain(a, b)
+        assert abs(x - y) <= 1e-12 * y
