@@ -1900,6 +1900,12 @@ cpq_status cpq_ir_scale_factor(const double* ir_l, const double* ir_r, int len, 
     return CPQ_OK;
 }
 
+cpq_status cpq_ir_min_phase(const double* ir, int len, double* out)
+{
+    if (!ir || !out || len <= 0) return CPQ_ERR_INVALID;
+    return cpq::irMinimumPhase(ir, len, out) ? CPQ_OK : CPQ_ERR_UNSUPPORTED;
+}
+
 double cpq_ir_freq_peak_gain(const double* ir_l, const double* ir_r, int len)
 {
     if (!ir_l || len <= 0) return 1.0;

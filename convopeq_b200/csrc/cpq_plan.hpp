@@ -491,6 +491,70 @@ inline double irFreqPeakGain(const double* const* ch, int nch, int len)
     return best > 1e-18 ? best : 1.0;
 }
 
+// In-place radix-2 complex FFT (host, prepare-time only); sign -1 forward, +1 backward (unscaled).
+inline void hostFft(std::vector<std::complex<double>>& z, const std::vector<std::complex<double>>& tw, int sign)
+{
+    const size_t n = z.size();
+    for (size_t i = 1, j = 0; i < n; ++i)
+    {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(z[i], z[j]);
+    }
+    for (size_t half = 1; half < n; half <<= 1)
+    {
+        const size_t step = n / (2 * half);
+        for (size_t i = 0; i < n; i += 2 * half)
+            for (size_t j = 0; j < half; ++j)
+            {
+                const std::complex<double> w = sign < 0 ? tw[j * step] : std::conj(tw[j * step]);
+                const std::complex<double> t = w * z[i + j + half], u = z[i + j];
+                z[i + j] = u + t;
+                z[i + j + half] = u - t;
+            }
+    }
+}
+
+// convertToMinimumPhase, convolver/ConvolverProcessor.ResampleAndFallback.cpp:333-460: homomorphic (real-cepstrum folding)
+// minimum-phase reconstruction on an FFT of nextPow2(4 len) points.  Returns false where the reference returns an empty
+// buffer (FFT above 2^23 points, non-finite result), in which case the loader keeps the linear-phase IR.
+inline bool irMinimumPhase(const double* ir, int len, double* out)
+{
+    if (!ir || !out || len <= 0) return false;
+    size_t n = 1;
+    while (n < (size_t) len * 4) n <<= 1;
+    if (n > 8388608) return false;   // MAX_MINPHASE_FFT_SIZE
+    std::vector<std::complex<double>> tw(n / 2), z(n);
+    for (size_t k = 0; k < n / 2; ++k) tw[k] = std::polar(1.0, -2.0 * kPi * (double) k / (double) n);
+    for (size_t i = 0; i < n; ++i) z[i] = i < (size_t) len ? ir[i] : 0.0;
+    hostFft(z, tw, -1);
+    for (auto& v : z) v = std::log(std::max(std::abs(v), 1.0e-300));   // log magnitude, zero phase
+    hostFft(z, tw, +1);
+    const double inv = 1.0 / (double) n;
+    const size_t half = n / 2;
+    for (size_t i = 0; i < n; ++i)   // fold the real cepstrum onto its causal part
+    {
+        const double c = z[i].real() * inv;
+        z[i] = (i == 0 || i == half) ? c : (i < half ? 2.0 * c : 0.0);
+    }
+    hostFft(z, tw, -1);
+    for (auto& v : z)
+    {
+        v = std::exp(std::complex<double>(clampv(-50.0, 50.0, v.real()), clampv(-50.0, 50.0, v.imag())));
+        if (!std::isfinite(v.real()) || !std::isfinite(v.imag())) return false;
+    }
+    hostFft(z, tw, +1);
+    for (int i = 0; i < len; ++i)
+    {
+        double v = z[(size_t) i].real() * inv;
+        if (!std::isfinite(v)) return false;
+        if (std::fabs(v) < 1.0e-18) v = 0.0;
+        out[i] = v;
+    }
+    return true;
+}
+
 inline void irPeakAndRms(const double* const* ch, int nch, int len, double scale, double& peak, double& rms)
 {
     double e = 0.0;

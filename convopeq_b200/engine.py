@@ -247,6 +247,18 @@ def ir_scale_factor(ir_l: np.ndarray, ir_r: Optional[np.ndarray] = None, cur_l: 
     return float(out.scale_factor), bool(out.has_scale_factor), float(out.additional_attenuation_db)
 
 
+def ir_min_phase(ir: np.ndarray) -> Optional[np.ndarray]:
+    """convertToMinimumPhase for one channel (host-only); None where the reference keeps the linear-phase IR."""
+    a = np.ascontiguousarray(ir, dtype=np.float64)
+    out = np.zeros_like(a)
+    st = capi.load().cpq_ir_min_phase(a.ctypes.data_as(_dp), a.size, out.ctypes.data_as(_dp))
+    if st == capi.ERR_UNSUPPORTED:
+        return None
+    if st != capi.OK:
+        raise capi.CpqError(st, "cpq_ir_min_phase")
+    return out
+
+
 def ir_freq_peak_gain(ir_l: np.ndarray, ir_r: Optional[np.ndarray] = None) -> float:
     a = np.ascontiguousarray(ir_l, dtype=np.float64)
     b = None if ir_r is None else np.ascontiguousarray(ir_r, dtype=np.float64)

@@ -223,6 +223,11 @@ typedef struct cpq_ir_scale
 } cpq_ir_scale;
 cpq_status cpq_ir_scale_factor(const double* ir_l, const double* ir_r, int len, const double* cur_l, const double* cur_r, int cur_len,
                                double cur_scale, cpq_ir_scale* out);
+/* Host-only: convertToMinimumPhase (convolver/ConvolverProcessor.ResampleAndFallback.cpp:333-460) for one channel:
+ * homomorphic minimum-phase reconstruction (log magnitude -> real cepstrum folded onto its causal half -> exp) on an FFT of
+ * nextPow2(4 len) points, written to out[len].  CPQ_ERR_UNSUPPORTED where the reference gives up and keeps the
+ * linear-phase IR (FFT above 2^23 points, non-finite spectrum). */
+cpq_status cpq_ir_min_phase(const double* ir, int len, double* out);
 /* Host-only: IRAnalyzer::estimateMaxFrequencyResponseGain on its own (linear gain; 1.0 for an empty IR). */
 double cpq_ir_freq_peak_gain(const double* ir_l, const double* ir_r, int len);
 /* Host-only: the three stages' normalised coefficients {b0,b1,b2,a1,a2} x 3 as OutputFilter::prepare computes them. */

@@ -193,3 +193,27 @@ def test_ir_scale_factor_matches_restatement(oracle):
     want = oracle.ir_scale_factor(loud, None, quiet, None, 0.01)
     assert abs(held[0] - want[0]) <= 1e-10 * want[0] and abs(held[0] - free[0]) <= 1e-12 * free[0]
     assert ir_scale_factor(np.zeros(100)) == (1.0, True, 0.0)
+
+
+def test_ir_minimum_phase_conversion():
+    """convertToMinimumPhase (ResampleAndFallback.cpp:333-460) restated host-side: same steps in numpy, plus what a
+    minimum-phase version must satisfy (same magnitude response, energy moved to the front)."""
+    from convopeq_b200.engine import ir_min_phase
+    for n, seed in ((300, 1), (4096, 2), (20000, 3)):
+        ir = np.roll(signals.synth_ir(n, seed), n // 3)          # delayed: far from minimum phase
+        got = ir_min_phase(ir)
+        N = 1 << int(np.ceil(np.log2(4 * n)))
+        X = np.fft.fft(ir, N)
+        c = np.fft.ifft(np.log(np.maximum(np.abs(X), 1e-300))).real
+        fold = np.zeros(N)
+        fold[0], fold[N // 2] = c[0], c[N // 2]
+        fold[1:N // 2] = 2.0 * c[1:N // 2]
+        S = np.fft.fft(fold)
+        want = np.fft.ifft(np.exp(np.clip(S.real, -50, 50) + 1j * np.clip(S.imag, -50, 50))).real[:n]
+        want[np.abs(want) < 1e-18] = 0.0
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+        G = np.abs(np.fft.rfft(got, N))
+        assert np.abs(G - np.abs(X[:N // 2 + 1])).max() <= 2e-2 * np.abs(X).max()     # truncation to n samples only
+        e_in, e_out = np.cumsum(ir ** 2), np.cumsum(got ** 2)
+        assert np.all(e_out[: n // 2] >= e_in[: n // 2] - 1e-12) and e_out[n // 8] > 0.5 * e_out[-1]
+    assert ir_min_phase(np.zeros(3 * 1024 * 1024)) is None      # FFT would exceed 2^23 points: the reference skips too
