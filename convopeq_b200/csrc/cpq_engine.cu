@@ -1490,7 +1490,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 static const int fpcEnv = [] { const char* e = getenv("CPQ_MAC_FPC"); return e ? atoi(e) : 0; }();   // tuning knob
                 if (fpcEnv > 0 && fpcEnv % step == 0 && fpcEnv < fpc && K[li] <= 2 * step) fpc = fpcEnv;   // short layers only
                 a.framesPerCta = fpc;
-                a.ringRows = fpc <= step ? step + (a.qEnd - a.qBegin) - 1 : macRingRows(a.qEnd - a.qBegin);
+                a.ringRows = fpc <= step ? (step + (a.qEnd - a.qBegin) - 1 + kMacKT - 1) / kMacKT * kMacKT : macRingRows(a.qEnd - a.qBegin);
                 const size_t smem = macSmemBytes(a.qEnd - a.qBegin, a.ringRows);
                 static size_t macSmemSet = 0;
                 if (smem > macSmemSet)

@@ -50,7 +50,7 @@ constexpr int kMacSuper = kMacGroups * kMacKT;       // 64 output frames per sup
 constexpr int kMacRowBytes = kMacBins * (int) sizeof(double2);   // 512
 
 inline size_t macSmemBytes(int nq, int ringRows) { return (size_t) (nq + ringRows) * kMacRowBytes + 16; }
-inline int macRingRows(int nq) { return 2 * kMacSuper + nq - 1; }
+inline int macRingRows(int nq) { return (2 * kMacSuper + nq - 1 + kMacKT - 1) / kMacKT * kMacKT; }   // a multiple of KT: mac_taps3<.., ALIGNED>
 
 // ---- mbarrier / bulk-copy (TMA engine) primitives ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
@@ -132,9 +132,14 @@ __device__ __forceinline__ void mac_taps(double2 (&acc)[kMacKT], double2 (&w)[kM
 // (d - c, c + d of the H value; s of the spectrum that enters the window) instead of 32 DFMA.  The rounding error bound is
 // that of the four-multiplication form times a small constant (|c||a+b| + |b||c+d| against |ac| + |bd|).
 struct MacW3 { double a, b, s; };
-template <int NT>
-__device__ __forceinline__ void mac_taps3(double (&k1)[kMacKT], double (&k2)[kMacKT], double (&k3)[kMacKT], MacW3 (&w)[kMacKT], double2& nxt,
-                                          const char* __restrict__ hsRow, const char* __restrict__ ringB, int& off, int ringBytes)
+// NT consecutive taps; rowOff = byte offset of the ring row holding the frame before logical w[0].  The window slides by
+// loading that row straight into the slot whose frame has just left the window (no staging registers, no moves): the slot
+// is consumed first in tap u (logical i = KT-1) and its new content last in tap u+1 (logical i = 0), which gives the load
+// a whole tap of arithmetic to land.  ALIGNED: the ring has a multiple of eight rows and the run starts on a multiple of
+// eight, so the eight rows of a block never wrap and their addresses are immediates.
+template <int NT, bool ALIGNED>
+__device__ __forceinline__ void mac_taps3(double (&k1)[kMacKT], double (&k2)[kMacKT], double (&k3)[kMacKT], MacW3 (&w)[kMacKT],
+                                          const char* __restrict__ hsRow, const char* __restrict__ ringB, int& rowOff, int ringBytes)
 {
     constexpr int KT = kMacKT;
 #pragma unroll
@@ -142,25 +147,36 @@ __device__ __forceinline__ void mac_taps3(double (&k1)[kMacKT], double (&k2)[kMa
     {
         const double2 h = *reinterpret_cast<const double2*>(hsRow + u * kMacRowBytes);
         const double dmc = h.y - h.x, cpd = h.x + h.y;
-        MacW3 incoming;
-        incoming.a = nxt.x;
-        incoming.b = nxt.y;
-        incoming.s = nxt.x + nxt.y;
-        off -= kMacRowBytes;
-        if (off < 0) off += ringBytes;
-        nxt = *reinterpret_cast<const double2*>(ringB + off);
 #pragma unroll
-        for (int i = 0; i < KT; ++i)
+        for (int ii = 0; ii < KT; ++ii)
         {
-            const MacW3 x = w[(i + KT - u) % KT];
+            const int i = KT - 1 - ii;
+            const MacW3& x = w[(i + KT - u) % KT];
             k1[i] = fma(h.x, x.s, k1[i]);
             k2[i] = fma(x.a, dmc, k2[i]);
             k3[i] = fma(x.b, cpd, k3[i]);
         }
-        w[(KT - 1 - u) % KT] = incoming;
+        double2 v;
+        if (ALIGNED) v = *reinterpret_cast<const double2*>(ringB + rowOff - u * kMacRowBytes);
+        else
+        {
+            v = *reinterpret_cast<const double2*>(ringB + rowOff);
+            rowOff -= kMacRowBytes;
+            if (rowOff < 0) rowOff += ringBytes;
+        }
+        MacW3& slot = w[(KT - 1 - u) % KT];
+        slot.a = v.x;
+        slot.b = v.y;
+        slot.s = v.x + v.y;
+    }
+    if (ALIGNED)
+    {
+        rowOff -= NT * kMacRowBytes;
+        if (rowOff < 0) rowOff += ringBytes;
     }
 }
 
+template <bool ALIGNED>
 __device__ __forceinline__ void mac_run3(double2 (&acc)[kMacKT], const char* __restrict__ hsB, const char* __restrict__ ringB, int off,
                                          int ringBytes, int nq)
 {
@@ -172,27 +188,26 @@ __device__ __forceinline__ void mac_run3(double2 (&acc)[kMacKT], const char* __r
     {
         k1[i] = k2[i] = k3[i] = 0.0;
         int o = off + i * kMacRowBytes;
-        if (o >= ringBytes) o -= ringBytes;
+        if (!ALIGNED && o >= ringBytes) o -= ringBytes;
         const double2 v = *reinterpret_cast<const double2*>(ringB + o);
         w[i].a = v.x;
         w[i].b = v.y;
         w[i].s = v.x + v.y;
     }
-    off -= kMacRowBytes;
-    if (off < 0) off += ringBytes;
-    double2 nxt = *reinterpret_cast<const double2*>(ringB + off);
+    int rowOff = off - kMacRowBytes;
+    if (rowOff < 0) rowOff += ringBytes;
     const int nFull = nq & ~(KT - 1);
-    for (int q0 = 0; q0 < nFull; q0 += KT) mac_taps3<KT>(k1, k2, k3, w, nxt, hsB + q0 * kMacRowBytes, ringB, off, ringBytes);
+    for (int q0 = 0; q0 < nFull; q0 += KT) mac_taps3<KT, ALIGNED>(k1, k2, k3, w, hsB + q0 * kMacRowBytes, ringB, rowOff, ringBytes);
     const char* hsT = hsB + nFull * kMacRowBytes;
     switch (nq & (KT - 1))
     {
-        case 1: mac_taps3<1>(k1, k2, k3, w, nxt, hsT, ringB, off, ringBytes); break;
-        case 2: mac_taps3<2>(k1, k2, k3, w, nxt, hsT, ringB, off, ringBytes); break;
-        case 3: mac_taps3<3>(k1, k2, k3, w, nxt, hsT, ringB, off, ringBytes); break;
-        case 4: mac_taps3<4>(k1, k2, k3, w, nxt, hsT, ringB, off, ringBytes); break;
-        case 5: mac_taps3<5>(k1, k2, k3, w, nxt, hsT, ringB, off, ringBytes); break;
-        case 6: mac_taps3<6>(k1, k2, k3, w, nxt, hsT, ringB, off, ringBytes); break;
-        case 7: mac_taps3<7>(k1, k2, k3, w, nxt, hsT, ringB, off, ringBytes); break;
+        case 1: mac_taps3<1, ALIGNED>(k1, k2, k3, w, hsT, ringB, rowOff, ringBytes); break;
+        case 2: mac_taps3<2, ALIGNED>(k1, k2, k3, w, hsT, ringB, rowOff, ringBytes); break;
+        case 3: mac_taps3<3, ALIGNED>(k1, k2, k3, w, hsT, ringB, rowOff, ringBytes); break;
+        case 4: mac_taps3<4, ALIGNED>(k1, k2, k3, w, hsT, ringB, rowOff, ringBytes); break;
+        case 5: mac_taps3<5, ALIGNED>(k1, k2, k3, w, hsT, ringB, rowOff, ringBytes); break;
+        case 6: mac_taps3<6, ALIGNED>(k1, k2, k3, w, hsT, ringB, rowOff, ringBytes); break;
+        case 7: mac_taps3<7, ALIGNED>(k1, k2, k3, w, hsT, ringB, rowOff, ringBytes); break;
         default: break;
     }
 #pragma unroll
@@ -232,6 +247,9 @@ __device__ __forceinline__ void mac_run(double2 (&acc)[kMacKT], const char* __re
     }
 }
 
+#ifndef CPQ_MAC_ALIGNED
+#define CPQ_MAC_ALIGNED 1
+#endif
 #ifndef CPQ_MAC_STAGE1
 #define CPQ_MAC_STAGE1 0   // one issuing lane per warp instead of eight: measured slower (MAC 18.6 vs 17.2 ms per step)
 #endif
@@ -333,6 +351,7 @@ __global__ void __launch_bounds__(kMacThreads, CPQ_MAC_MINBLOCKS) mac_kernel(Mac
     const char* ringB = reinterpret_cast<const char*>(ring) + ml * (int) sizeof(double2);
     const char* hsB = reinterpret_cast<const char*>(Hs) + ml * (int) sizeof(double2);
     const bool packedTile = (m0 == 0);
+    const bool alignedRing = CPQ_MAC_ALIGNED && (R % kMacKT) == 0 && (a.qBegin % kMacKT) == 0;   // see mac_taps3
     const bool slot0 = packedTile && ml == 0;
     unsigned phase = 0;
     for (int ks0 = kc0; ks0 < kc1; ks0 += kMacSuper)
@@ -348,7 +367,8 @@ __global__ void __launch_bounds__(kMacThreads, CPQ_MAC_MINBLOCKS) mac_kernel(Mac
             if (s < 0) s += R;
             if (packedTile) mac_run<true>(acc, hsB, ringB, s * kMacRowBytes, ringBytes, nq, slot0);
 #if CPQ_MAC_GAUSS
-            else mac_run3(acc, hsB, ringB, s * kMacRowBytes, ringBytes, nq);
+            else if (alignedRing) mac_run3<true>(acc, hsB, ringB, s * kMacRowBytes, ringBytes, nq);
+            else mac_run3<false>(acc, hsB, ringB, s * kMacRowBytes, ringBytes, nq);
 #else
             else mac_run<false>(acc, hsB, ringB, s * kMacRowBytes, ringBytes, nq, slot0);
 #endif
