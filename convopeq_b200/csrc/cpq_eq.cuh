@@ -371,6 +371,9 @@ __device__ __forceinline__ void eq_pass2x2(double (&x)[kEqL], double sA1, double
     }
 }
 
+#ifndef CPQ_EQ_SLEEP
+#define CPQ_EQ_SLEEP 40
+#endif
 #ifndef CPQ_EQ_ILP2
 #define CPQ_EQ_ILP2 1
 #endif
@@ -720,7 +723,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                 else
                 {
                     const int* f = fl + b * 8 + warp;
-                    while (lds_volatile(f) == 0) { __nanosleep(40); }   // a spinning warp would steal issue slots from the FP64 warps
+                    while (lds_volatile(f) == 0) { __nanosleep(CPQ_EQ_SLEEP); }   // a spinning warp would steal issue slots from the FP64 warps
                     __threadfence_block();
                 }
             }
