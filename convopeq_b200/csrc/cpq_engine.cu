@@ -181,6 +181,10 @@ struct Engine
     double convInputTrim = 1.0;         // state.convolverInputTrimGain (EQThenConvolver order only)
     double mix = 1.0;                   // (double) mixTarget of ConvolverProcessor::process (CPQ_CONV_OUTER only)
     int dryDelay = 0;                   // latency-compensation delay of the dry path, samples
+    int winFirst = 0, winCount = -1;    // stream window of process calls (cpq_set_stream_window); -1 = all streams
+    int nPeers = 0;                     // partition-range sharding: every rank's partial buffer, summed in the EQ launch's load
+    const double* peers[CPQ_MAX_PEERS] {};
+    int convBypassed = 0;               // runtimeSnapshot.bypassed: processBypassWithLatencyCompensation (Runtime.cpp:123-186)
     DevBuf<double> dryBuf;              // copy of the convolver input for the dry path (mix < 0.999) / the direct-form head
     int directHead = 0;                 // enableDirectHead of SetImpulse (experimental in the reference)
     DevBuf<double> directTaps;          // [nH][32] reversed, scaled head taps
@@ -1016,7 +1020,7 @@ cpq_status Engine::launchEq(EqArgs& a)
     CPQ_CUDA(cudaMemsetAsync(ticketFault.p, 0, sizeof(unsigned), stream));
     const unsigned grid = (unsigned) a.nSeq * (unsigned) a.nRuns;
     if (a.doEq && anyPar) eq_kernel<true, true, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
-    else if (a.sumsqIn || a.sumsqOut) eq_kernel<true, false, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
+    else if (a.sumsqIn || a.sumsqOut || a.nPeers > 0) eq_kernel<true, false, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
     else if (a.postMask || a.finalClamp) eq_kernel<true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
     else eq_kernel<false><<<grid, kEqThreads, kEqSmemBytes, stream>>>(a);
     ++launches;
@@ -1034,6 +1038,25 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
 {
     const bool agc = e.doEq && anyAgc, ms = e.doEq && anyMs;
     if (!agc && !ms) return launchEq(e);
+    if (e.nPeers > 0)
+    {
+        // several launches follow: sum the peers' partials (and apply the deferred outer boundary) on their own first
+        EqArgs w = e;
+        w.doEq = 0;
+        w.doGain = 0;
+        w.gainTab = nullptr;
+        w.postMask = 0;
+        w.postStateOut = nullptr;
+        w.doEpilogue = 0;
+        w.finalClamp = 0;
+        w.applyHeadroom = 0;
+        cpq_status st = launchEq(w);
+        if (st != CPQ_OK) return st;
+        e.nPeers = 0;
+        e.assemble = 0;
+        e.nTail = 0;
+        e.outer = 0;
+    }
     const int nch = cfg.n_channels;
     const int st0 = s0 / nch, nst = ns / nch;
     double* sqIn = sumsq.p;
@@ -1287,6 +1310,15 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
     }
 
     // ---- sequence chunking: bounded spectra workspace, and ~32 chunks so host copies overlap compute ----
+    // stream window (partition-range sharding: a rank convolves every stream but finishes only its own)
+    const int seqLo = std::min(std::max(winFirst, 0), cfg.n_streams) * cfg.n_channels;
+    const int nSeqAll = this->nSeq;
+    const int nSeq = (winCount < 0 ? nSeqAll - seqLo : std::min(winCount * cfg.n_channels, nSeqAll - seqLo));
+    if (nSeq <= 0)
+    {
+        setError("process: empty stream window");
+        return CPQ_ERR_INVALID;
+    }
     int64_t K[CPQ_MAX_LAYERS] = {};
     int chunk = nSeq;
     if (doConv)
@@ -1335,15 +1367,15 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
     // otherwise row by row.  H2D runs at most two chunks ahead of compute so the driver's launch queue never
     // fills with copies (a full queue would stall the host before the first D2H is enqueued).
     ptrdiff_t hostPitch = 0;
-    if (hostPlanar && nSeq > 1)
+    if (hostPlanar && nSeqAll > 1)
     {
         hostPitch = hostPlanar[1] - hostPlanar[0];
-        for (int s = 2; s < nSeq && hostPitch > 0; ++s)
+        for (int s = 2; s < nSeqAll && hostPitch > 0; ++s)
             if (hostPlanar[s] - hostPlanar[s - 1] != hostPitch) hostPitch = 0;
         if (hostPitch < T) hostPitch = 0;
     }
     auto enqueueH2D = [&](size_t c) -> cudaError_t {
-        const int s0 = (int) c * chunk, ns = std::min(chunk, nSeq - s0);
+        const int s0 = seqLo + (int) c * chunk, ns = std::min(chunk, seqLo + nSeq - s0);
         cudaError_t e = cudaSuccess;
         if (hostPitch == T && stride == T)   // both sides dense: one linear copy
             e = cudaMemcpyAsync(dIo + (size_t) s0 * stride, hostPlanar[s0], (size_t) ns * T * sizeof(double), cudaMemcpyHostToDevice, sIn);
@@ -1384,13 +1416,14 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         a.postc = postc.p;
         a.postMask = postMask;
         a.finalClamp = (doEpi && outCfg.finalClamp && ditherBits <= 0) ? 1 : 0;   // with dither the dither kernel clamps
+        a.nPeers = 0;
         a.wetGain = equalPowerSin(cfg.conv_boundary == CPQ_CONV_OUTER ? mix : 1.0) * 1.0;   // CONVOLUTION_HEADROOM_GAIN = 1.0 (ConvolverProcessor.h:209)
     };
     const bool deferredOuter = !doConv && outerPending;
     // ConvolverProcessor::process with mix < 1 (Runtime.cpp:367-377): the dry path needs the convolver's input, kept in a
     // copy because the L0 inverse transform overwrites io; mix <= 0.001 is the dry-only fast path (no convolution at all)
     const bool outerMix = doConv && cfg.conv_boundary == CPQ_CONV_OUTER;
-    const bool needsDry = outerMix && mix < 0.999, dryOnly = outerMix && !(mix > 0.001);
+    const bool needsDry = outerMix && (convBypassed || mix < 0.999), dryOnly = outerMix && (convBypassed || !(mix > 0.001));
     if (needsDry && !fullRange)
     {
         setError("process: mix < 1 together with a partition range (the dry path belongs to the rank that owns the sum)");
@@ -1405,7 +1438,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
 
     for (size_t c = 0; c < nChunks; ++c)
     {
-        const int s0 = (int) c * chunk, ns = std::min(chunk, nSeq - s0);
+        const int s0 = seqLo + (int) c * chunk, ns = std::min(chunk, seqLo + nSeq - s0);
         double* ioC = dIo + (size_t) s0 * stride;
         cudaEvent_t* ce = &evPool[c * 6];
         if (hostPlanar) cudaStreamWaitEvent(stream, evPool[c * 6 + 5], 0);
@@ -1548,6 +1581,12 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         fillEqCommon(e);
         e.io = ioC;
         e.nSeq = ns;
+        if (!doConv && nPeers > 0)
+        {
+            // the ranks' convolver partials are summed (rank order) while this launch loads its tiles
+            e.nPeers = nPeers;
+            for (int p = 0; p < nPeers; ++p) e.peer[p] = peers[p] + (size_t) s0 * stride;
+        }
         if (doConv && !dryOnly)
         {
             e.assemble = 1;
@@ -1936,6 +1975,32 @@ cpq_status cpq_set_mix(cpq_handle h, float mix, int dry_delay_samples)
     if (!h || !(mix >= 0.0f && mix <= 1.0f) || dry_delay_samples < 0 || dry_delay_samples > 2097152 + 524288) return CPQ_ERR_INVALID;
     h->mix = static_cast<double>(mix);
     h->dryDelay = dry_delay_samples;
+    return CPQ_OK;
+}
+
+cpq_status cpq_set_partial_sources(cpq_handle h, int n, const double* const* device_ptrs)
+{
+    if (!h || n < 0 || n > CPQ_MAX_PEERS || (n > 0 && !device_ptrs)) return CPQ_ERR_INVALID;
+    for (int p = 0; p < n; ++p)
+        if (!device_ptrs[p]) return CPQ_ERR_INVALID;
+    h->nPeers = n;
+    for (int p = 0; p < n; ++p) h->peers[p] = device_ptrs[p];
+    return CPQ_OK;
+}
+
+cpq_status cpq_set_stream_window(cpq_handle h, int first_stream, int n_streams)
+{
+    if (!h || first_stream < 0 || first_stream >= h->cfg.n_streams || n_streams == 0 || n_streams < -1) return CPQ_ERR_INVALID;
+    if (n_streams > 0 && first_stream + n_streams > h->cfg.n_streams) return CPQ_ERR_INVALID;
+    h->winFirst = first_stream;
+    h->winCount = n_streams;
+    return CPQ_OK;
+}
+
+cpq_status cpq_set_convolver_bypass(cpq_handle h, int bypassed)
+{
+    if (!h) return CPQ_ERR_INVALID;
+    h->convBypassed = bypassed ? 1 : 0;
     return CPQ_OK;
 }
 

@@ -50,6 +50,9 @@ namespace cpq
 #ifndef CPQ_EQ_L
 #define CPQ_EQ_L 32
 #endif
+#ifndef CPQ_MAX_PEERS
+#define CPQ_MAX_PEERS 8
+#endif
 constexpr int kEqThreads = 256;
 constexpr int kEqCWarps = 8;                     // every warp computes (an idle chain warp would leave one SM sub-partition half empty)
 constexpr int kEqCThreads = kEqCWarps * 32;      // 256
@@ -131,6 +134,11 @@ struct EqArgs
     // output before the gain, [nSeq][nCallbacks]; nullable
     double* sumsqIn;
     double* sumsqOut;
+    // Partition-range sharding: the convolver partials of all ranks, summed in rank order while the tile is
+    // loaded -- peer[p] is rank p's buffer in the layout of io (this rank's own buffer included), mapped into this process
+    // over NVLink.  The reduce step of the collective is this load; there is no separate pass and no staging copy.
+    int nPeers;                     // 0 = io only
+    const double* peer[CPQ_MAX_PEERS];
     // epilogue
     int doEpilogue;
     double makeup;
@@ -499,11 +507,33 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
             {
                 const double2* ip2 = reinterpret_cast<const double2*>(ip);
                 const double2* t02 = reinterpret_cast<const double2*>(tp[0]);
+                const int64_t ioOff = ip - a.io;   // element offset of this sub-block, the same in every peer's buffer
                 const double2* t12 = reinterpret_cast<const double2*>(tp[1]);
                 const int last2 = nv / 2 - 1;
                 double2 va[8], vb[8], vc[8];
+                if (STATS && a.nPeers > 0)
+                {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) va[k] = ip2[min(lane + 32 * k, last2)];
+                    for (int k = 0; k < 8; ++k) va[k] = make_double2(0.0, 0.0);
+                    for (int p = 0; p < a.nPeers; ++p)
+                    {
+                        const double2* pp = reinterpret_cast<const double2*>(a.peer[p] + ioOff);
+                        double2 vp[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) vp[k] = pp[min(lane + 32 * k, last2)];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                        {
+                            va[k].x = p == 0 ? vp[k].x : va[k].x + vp[k].x;
+                            va[k].y = p == 0 ? vp[k].y : va[k].y + vp[k].y;
+                        }
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) va[k] = ip2[min(lane + 32 * k, last2)];
+                }
                 if (tp[0])
                 {
 #pragma unroll
@@ -538,7 +568,16 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
             {
                 double va[8], vb[8], vc[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) va[k] = ip[min(lane + 32 * (8 * h + k), nv - 1)];
+                for (int k = 0; k < 8; ++k)
+                {
+                    const int idx = min(lane + 32 * (8 * h + k), nv - 1);
+                    va[k] = ip[idx];
+                    if (STATS && a.nPeers > 0)
+                    {
+                        va[k] = a.peer[0][(ip - a.io) + idx];
+                        for (int p = 1; p < a.nPeers; ++p) va[k] += a.peer[p][(ip - a.io) + idx];
+                    }
+                }
                 if (tp[0])
                 {
 #pragma unroll
@@ -577,6 +616,11 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
             {
                 const int64_t t = w0 + i;
                 v = io[t];
+                if (STATS && a.nPeers > 0)
+                {
+                    v = a.peer[0][(io - a.io) + t];
+                    for (int p = 1; p < a.nPeers; ++p) v += a.peer[p][(io - a.io) + t];
+                }
                 const int64_t c = t >> a.blockLog2;
                 const int off = (int) t & bmask;
                 for (int l = 0; l < a.nTail; ++l)

@@ -73,6 +73,35 @@ def reduce_partials(partial, op_group=None, owner_of_row=None):
     return partial
 
 
+def process_partition_sharded_fused(engine, symm_tensor, peer_ptrs, T: int, rank: int, world: int, owned_streams, barrier,
+                                    stages_after=None):
+    """cfg 5 without a separate collective: every rank convolves its partition range into its own symmetric-memory buffer,
+    then finishes the streams it owns while its EQ launch loads -- and sums, in rank order -- the tiles of ALL ranks'
+    buffers over NVLink (cpq_set_partial_sources).  The reduce-scatter is the load stage of the consumer kernel.
+
+    symm_tensor  this rank's [n_seq, stride] CUDA tensor allocated from torch symmetric memory, holding the full input
+    peer_ptrs    device addresses of every rank's buffer in this process (rank order, own included)
+    owned_streams (first, count) of the streams this rank finishes
+    barrier      callable ordering the ranks' device work (e.g. the symmetric-memory handle's barrier)"""
+    from . import capi
+    lay = engine.layout()
+    parts = [lay.layers[li].num_parts_ir for li in range(lay.num_layers)]
+    b, e = partition_ranges(parts, world)[rank]
+    engine.set_partition_range(b, e)
+    stride = symm_tensor.stride(0)
+    engine.process_device(symm_tensor.data_ptr(), stride, T, capi.STAGE_CONV)   # returns after the kernels have completed
+    barrier()                                                                   # every rank's partial is in place
+    engine.set_partition_range(0, -1)
+    engine.set_partial_sources(list(peer_ptrs))
+    engine.set_stream_window(*owned_streams)
+    after = capi.STAGE_EQ | capi.STAGE_EPILOGUE if stages_after is None else stages_after
+    engine.process_device(symm_tensor.data_ptr(), stride, T, after)
+    engine.set_partial_sources([])
+    engine.set_stream_window(0, -1)
+    barrier()                                                                   # peers are done reading this rank's partial
+    return symm_tensor
+
+
 def process_partition_sharded(engine, io_tensor, T: int, rank: int, world: int, owner_of_row=None, stages_after=None):
     """cfg 5: convolve with this rank's partition range, sum the partials over ranks, then EQ + epilogue.
 

@@ -149,6 +149,14 @@ class ConvoPeqEngine:
     def set_partition_range(self, begin: int, end: int):
         self._check(self.lib.cpq_set_partition_range(self.h, begin, end))
 
+    def set_partial_sources(self, device_ptrs: Sequence[int]):
+        """Every rank's partial buffer (device addresses valid in this process, rank order, own buffer included); [] clears."""
+        arr = (C.c_void_p * max(len(device_ptrs), 1))(*[C.c_void_p(int(p)) for p in device_ptrs])
+        self._check(self.lib.cpq_set_partial_sources(self.h, len(device_ptrs), arr))
+
+    def set_stream_window(self, first_stream: int = 0, n_streams: int = -1):
+        self._check(self.lib.cpq_set_stream_window(self.h, first_stream, n_streams))
+
     def total_partitions(self) -> int:
         return self.lib.cpq_total_partitions(self.h)
 
@@ -164,6 +172,10 @@ class ConvoPeqEngine:
     def set_mix(self, mix: float, dry_delay_samples: int):
         """ConvolverProcessor's dry/wet mix (float mixTarget) and the latency-compensation delay of its dry path."""
         self._check(self.lib.cpq_set_mix(self.h, C.c_float(mix), int(dry_delay_samples)))
+
+    def set_convolver_bypass(self, bypassed: bool = True):
+        """ConvolverProcessor bypass: the convolver stage becomes the latency-compensating delay (set_mix's dry delay)."""
+        self._check(self.lib.cpq_set_convolver_bypass(self.h, int(bypassed)))
 
     def set_conv_input_trim(self, gain: float):
         """convolverInputTrimGain of the EQThenConvolver order (DSPCoreDouble.cpp:438-445)."""

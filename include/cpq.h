@@ -207,6 +207,10 @@ cpq_status cpq_set_conv_input_trim(cpq_handle h, double gain);
  * min(irLatency, MAX_IR_LATENCY), see cpq_latency and cpq_ir_peak_latency); mix >= 0.999 drops the dry path, mix <= 0.001 is the
  * dry-only fast path (delayed input, no gain, no convolution).  mix is the float mixTarget.  Default 1.0 / 0. */
 cpq_status cpq_set_mix(cpq_handle h, float mix, int dry_delay_samples);
+/* ConvolverProcessor::setBypass as seen by process (runtimeSnapshot.bypassed -> processBypassWithLatencyCompensation,
+ * ConvolverProcessor.Runtime.cpp:123-186, 257-261): the convolver stage outputs its input delayed by the dry_delay_samples of
+ * cpq_set_mix (the reference uses latency + irLatency, latency = 0 with the direct head), whatever the mix.  CPQ_CONV_OUTER only. */
+cpq_status cpq_set_convolver_bypass(cpq_handle h, int bypassed);
 /* Host-only: LoaderThread::estimatePeakLatencySamples (convolver/ConvolverProcessor.LoaderThread.cpp:149-207), the irLatency
  * StereoConvolver::init receives as peakDelay: energy centroid of the first 99.9 % of the energy, maximum over channels
  * (ir_r nullable), rounded, clamped to [0, len - 1]. */
@@ -270,6 +274,18 @@ cpq_status cpq_process_device(cpq_handle h, double* d_io, int64_t stride, int64_
  * partials (NCCL) and runs the remaining stages with cpq_process_device(..., CPQ_STAGE_EQ|EPILOGUE). */
 cpq_status cpq_set_partition_range(cpq_handle h, int part_begin, int part_end);
 int cpq_total_partitions(cpq_handle h);
+/* The reduce step without a separate collective: device pointers (valid in this process: peer memory mapped over NVLink,
+ * e.g. torch symmetric memory or CUDA IPC) of every rank's partial buffer, this rank's own included, in rank order and in
+ * the layout / stride of the d_io passed to cpq_process_device.  While set, a cpq_process_device call WITHOUT CPQ_STAGE_CONV
+ * sums the n buffers in that order as it loads its tiles (the same order on every rank, so all ranks see identical sums)
+ * and writes the result into d_io.  The caller orders the ranks (a barrier after every rank's CPQ_STAGE_CONV call, and
+ * before the buffers are reused).  n = 0 clears.  At most CPQ_MAX_PEERS (8). */
+#define CPQ_MAX_PEERS 8
+cpq_status cpq_set_partial_sources(cpq_handle h, int n, const double* const* device_ptrs);
+/* Restrict the following cpq_process / cpq_process_device calls to streams [first_stream, first_stream + n_streams)
+ * (n_streams = -1: through the last stream): with partition-range sharding every rank convolves all streams but finishes
+ * (EQ, output stages) only the streams it owns.  Buffers keep their full layout. */
+cpq_status cpq_set_stream_window(cpq_handle h, int first_stream, int n_streams);
 
 /* ---- introspection ----------------------------------------------------------------------- */
 cpq_status cpq_get_layout(cpq_handle h, cpq_layout* out);

@@ -150,6 +150,8 @@ public:
     /// scrub + +-kOutputHeadroom hard clamp, both inside CPQ_STAGE_EPILOGUE.
     /// convolverInputTrimGain (EQThenConvolver order: pass CPQ_ORDER_EQ_THEN_CONV in `stages`).
     bool setConvolverInputTrim(double gain) { return ok(cpq_set_conv_input_trim(h_, gain)); }
+    /// ConvolverProcessor::setBypass: the convolver stage only delays by the dry path's latency compensation.
+    bool setConvolverBypass(bool bypassed) { return ok(cpq_set_convolver_bypass(h_, bypassed ? 1 : 0)); }
     /// enableDirectHead of SetImpulse / StereoConvolver::init; call before the first SetImpulse.
     bool setDirectHeadEnabled(bool enable) { return ok(cpq_set_direct_head(h_, enable ? 1 : 0)); }
     /// ConvolverProcessor::setMix (Runtime.cpp:816) + the dry path's latency compensation (settled state).

@@ -116,6 +116,23 @@ def test_outer_dry_wet_mix(checker, oracle, mix):
         assert np.abs(y[ch] - w[ch]).max() <= TOL, (ch, mix)
     if mix <= 0.001:
         assert np.array_equal(y[0][delay:], x[0][:T - delay]) and not y[0][:delay].any()
+    if mix == 0.35:
+        # bypassed convolver (processBypassWithLatencyCompensation, Runtime.cpp:123-186): the delayed input whatever the mix,
+        # followed by the EQ as usual
+        eng2 = ConvoPeqEngine(1, 2, sr, block, T, conv_boundary=capi.CONV_OUTER)
+        for ch in range(2):
+            eng2.set_impulse(0, ch, irs[ch], 1.0, None)
+        eng2.set_mix(mix, delay)
+        eng2.set_convolver_bypass(True)
+        eng2.set_eq(0, signals.to_band(signals.band_params(74)))
+        b = x.copy()
+        eng2.process(b, capi.STAGE_CONV)
+        assert np.array_equal(b[:, delay:], x[:, :T - delay]) and not b[:, :delay].any()
+        b2 = x.copy()
+        eng2.process(b2, capi.STAGE_CONV | capi.STAGE_EQ)
+        eng2.close()
+        bl, br, _ = checker.eq_run(signals.to_eqband(signals.band_params(74)), b[0], b[1], sr, block)
+        assert np.abs(b2[0] - bl).max() <= TOL and np.abs(b2[1] - br).max() <= TOL
     wl, wr, _ = checker.eq_run(signals.to_eqband(signals.band_params(74)), w[0], w[1], sr, block)
     assert np.abs(z[0] - wl).max() <= TOL and np.abs(z[1] - wr).max() <= TOL
 
@@ -336,6 +353,45 @@ def test_partition_range_partials_sum_to_full(checker):
     eng.close()
     want, _ = checker.nuc_run(ir, x[0], block)
     assert np.abs(acc[0] - want).max() <= TOL
+
+
+@pytest.mark.parametrize("agc", [False, True])
+def test_partials_summed_in_the_eq_load(checker, agc):
+    """SURVEY 8e, fused reduce: three ranks' convolver partials sit in three buffers (here on one GPU); every 'rank' finishes
+    only its stream window, summing the buffers in rank order while its EQ launch loads the tiles (cpq_set_partial_sources +
+    cpq_set_stream_window).  The result equals the reference chain, and no rank ever forms the full sum in a separate pass."""
+    import torch
+    sr, block, T, ir_len, n_streams, ranks = 48000.0, 512, 32768, 100000, 3, 3
+    irs = [signals.synth_ir(ir_len, 20 + ch) for ch in range(2)]
+    x = np.stack([signals.noise(T, 30 + i) for i in range(2 * n_streams)])
+    bkw = [dict(seed=50), dict(seed=51, modes=[0, 3, 4, 0] * 5), dict(seed=52)]
+    # (inner boundary: on one handle the deferred outer step of a partial convolution is armed once per call pair, which
+    # this single-process emulation of three ranks would consume with the first window)
+    eng = ConvoPeqEngine(n_streams, 2, sr, block, T, shared_ir=True)
+    for ch in range(2):
+        eng.set_impulse(-1, ch, irs[ch], 1.0, capi.default_filter_spec())
+    for st in range(n_streams):
+        eng.set_eq(st, signals.to_band(signals.band_params(**bkw[st])), agc=agc)
+    eng.set_epilogue(1.2, 0)
+    total = eng.total_partitions()
+    bufs = [torch.from_numpy(x).cuda() for _ in range(ranks)]
+    for r in range(ranks):                                   # every rank: its partition range, all streams
+        eng.set_partition_range(total * r // ranks, total * (r + 1) // ranks)
+        eng.process_device(bufs[r].data_ptr(), T, T, capi.STAGE_CONV)
+    eng.set_partition_range(0, -1)
+    eng.set_partial_sources([b.data_ptr() for b in bufs])
+    for r in range(ranks):                                   # every rank: finish the stream it owns, reading all partials
+        eng.set_stream_window(r, 1)
+        eng.process_device(bufs[r].data_ptr(), T, T, capi.STAGE_EQ | capi.STAGE_EPILOGUE)
+    eng.set_partial_sources([])
+    eng.set_stream_window(0, -1)
+    torch.cuda.synchronize()
+    eng.close()
+    for st in range(n_streams):
+        got = bufs[st][2 * st:2 * st + 2].cpu().numpy()
+        want = checker.chain_run(irs, signals.to_eqband(signals.band_params(**bkw[st])), x[2 * st:2 * st + 2], sr, block, OFilterSpec(),
+                                 makeup=1.2, agc=agc, outer=False)
+        assert np.abs(got - want).max() <= TOL, st
 
 
 # ---- golden vectors produced by the reference's own code (tests/golden/make_golden.py) ----
