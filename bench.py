@@ -222,6 +222,12 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # one process per GPU, every rank streaming over PCIe in the e2e leg: keep this rank's pinned buffers and threads on
+        # the GPU's own NUMA node
+        from convopeq_b200.dist import bind_to_gpu_numa_node
+        numa_cpus = bind_to_gpu_numa_node(local)
+    else:
+        numa_cpus = None
 
     S, T = args.streams, args.samples // BLOCK * BLOCK
     n_seq = 2 * S
@@ -370,7 +376,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(S, T), "streams_per_gpu": S, "samples_per_channel": T, "ir_taps": IR_LEN,
                        "block": BLOCK, "l2_policy": "inputs (7.9 GB/GPU at 1024 streams) far exceed the 126 MB L2; no flush needed",
-                       "prepare_s": t_prep, "parallelism": f"stream-sharded x{world}, no collective"},
+                       "prepare_s": t_prep, "parallelism": f"stream-sharded x{world}, no collective",
+                       "numa": (f"rank 0 bound to {len(numa_cpus)} CPUs of its GPU's NUMA node" if numa_cpus else "not bound")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))

@@ -27,6 +27,39 @@ def stream_range(n_streams: int, rank: int, world: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < extra else 0)
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, BEFORE it allocates pinned host buffers (first touch
+    then places them next to the GPU's PCIe root).  With one process per GPU and host <-> device streaming on every rank,
+    buffers on the far socket halve the transfer rate.  Returns the cpu list it bound to, or None when the topology is not
+    exposed (then nothing changes)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:      # nvml prints an 8-digit domain, sysfs uses 4
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def partition_ranges(parts_per_layer: List[int], world: int) -> List[Tuple[int, int]]:
     """Split the flattened (layer, partition) list into `world` contiguous [begin, end) ranges balanced by
     multiply-accumulate work: a partition of layer l costs (P_l + 1) bins per P_l samples, i.e. the same per
