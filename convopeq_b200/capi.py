@@ -44,7 +44,7 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("n_streams", C.c_int32), ("n_channels", C.c_int32),
                 ("block_size", C.c_int32), ("sample_rate", C.c_double), ("max_samples", C.c_int64),
                 ("conv_boundary", C.c_int32), ("shared_ir", C.c_int32), ("shared_eq", C.c_int32),
-                ("reserved_", C.c_int32), ("workspace_bytes", C.c_size_t)]
+                ("uniform_partitions", C.c_int32), ("workspace_bytes", C.c_size_t)]
 
 
 class LayerLayout(C.Structure):

@@ -528,10 +528,15 @@ cpq_status Engine::setImpulse(int stream_, int ch, const double* ir, int len, do
         return CPQ_ERR_INVALID;
     }
     ConvPlan p;
-    if (!makeConvPlan(len, cfg.block_size, spec, p))
+    if (!makeConvPlan(len, cfg.block_size, spec, p, cfg.uniform_partitions != 0))
     {
         setError("set_impulse: SetImpulse would reject these parameters");
         return CPQ_ERR_INVALID;
+    }
+    if (cfg.uniform_partitions && p.layers[0].numPartsIR > 160)
+    {
+        setError("set_impulse: the uniform-partition extension holds at most 160 partitions (the MAC kernel's shared-memory tile)");
+        return CPQ_ERR_UNSUPPORTED;
     }
     for (int li = 0; li < p.numLayers; ++li)
         if (p.layers[li].partSize > 65536)

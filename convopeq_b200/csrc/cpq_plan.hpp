@@ -97,7 +97,11 @@ inline void filterSpecDefault(cpq_filter_spec* s)
 }
 
 // SetImpulse's parameter table and layer plan.  Returns false for the inputs SetImpulse rejects.
-inline bool makeConvPlan(int irLen, int blockSize, const cpq_filter_spec* fs, ConvPlan& out)
+// uniformExtension: BASELINE config 1's "uniform partitioned convolution" beyond what the reference can express -- its L0 is
+// capped at 32 partitions (kL0MaxParts, :744-747), so 65,536 taps never run as 128 uniform 512-sample partitions there.  With
+// the flag the whole IR is one immediate layer of ceil(irLen / P0) partitions (no tails, no layer gains): an extension,
+// checked against linear convolution instead of the reference.
+inline bool makeConvPlan(int irLen, int blockSize, const cpq_filter_spec* fs, ConvPlan& out, bool uniformExtension = false)
 {
     if (irLen <= 0 || blockSize <= 0) return false;
     out = ConvPlan {};
@@ -144,10 +148,10 @@ inline bool makeConvPlan(int irLen, int blockSize, const cpq_filter_spec* fs, Co
     const int l0MaxLen = 32 * l0Part;
     const int l0ByTail = (int) std::llround(tailStart * srTail);
     const int l0Target = clampv(l0Part, l0MaxLen, l0ByTail);
-    const int l0Len = std::min(irLen, tailEnabled ? l0Target : l0MaxLen);
+    const int l0Len = uniformExtension ? irLen : std::min(irLen, tailEnabled ? l0Target : l0MaxLen);
     const long long l1Cap = 64LL * l1PartLL;
-    const int l1Len = tailEnabled ? (int) std::max(0LL, std::min((long long) irLen - l0Len, l1Cap)) : 0;
-    const int l2Len = tailEnabled ? std::max(0, irLen - l0Len - l1Len) : 0;
+    const int l1Len = (tailEnabled && !uniformExtension) ? (int) std::max(0LL, std::min((long long) irLen - l0Len, l1Cap)) : 0;
+    const int l2Len = (tailEnabled && !uniformExtension) ? std::max(0, irLen - l0Len - l1Len) : 0;
 
     const int offs[3] = { 0, l0Len, l0Len + l1Len };
     const int lens[3] = { l0Len, l1Len, l2Len };

@@ -51,7 +51,7 @@ class ConvoPeqEngine:
 
     def __init__(self, n_streams: int = 1, n_channels: int = 2, sample_rate: float = 48000.0, block_size: int = 512,
                  max_samples: int = 480000 // 512 * 512, device: int = 0, conv_boundary: int = capi.CONV_INNER,
-                 shared_ir: bool = False, shared_eq: bool = False, workspace_bytes: int = 0):
+                 shared_ir: bool = False, shared_eq: bool = False, workspace_bytes: int = 0, uniform_partitions: bool = False):
         self.lib = capi.load()
         cfg = capi.Config()
         self.lib.cpq_config_default(C.byref(cfg))
@@ -65,6 +65,7 @@ class ConvoPeqEngine:
         cfg.shared_ir = int(shared_ir)
         cfg.shared_eq = int(shared_eq)
         cfg.workspace_bytes = workspace_bytes
+        cfg.uniform_partitions = int(uniform_partitions)
         self.cfg = cfg
         self.h = C.c_void_p()
         st = self.lib.cpq_create(C.byref(cfg), C.byref(self.h))

@@ -94,7 +94,9 @@ typedef struct cpq_config
     int32_t conv_boundary; /* cpq_conv_boundary */
     int32_t shared_ir;     /* 1: one IR pair (per channel) shared by all streams */
     int32_t shared_eq;     /* 1: one EQ setting shared by all streams */
-    int32_t reserved_;
+    int32_t uniform_partitions; /* 1: EXTENSION (BASELINE config 1 "uniform partitioned convolution"): the whole IR as one
+                                   layer of ceil(len / block) uniform partitions, which the reference cannot express beyond
+                                   32 partitions (kL0MaxParts); checked against linear convolution, not the reference */
     size_t workspace_bytes;/* upper bound for the per-call spectra workspace; 0 = default (free memory / 4 within 4..16 GiB) */
 } cpq_config;
 

@@ -91,14 +91,16 @@ class _Base:
 
     # ---- convolver -------------------------------------------------------------------------
     def nuc_run(self, ir: np.ndarray, x: np.ndarray, block: int, scale: float = 1.0,
-                spec: Optional[FilterSpec] = None, call: Optional[int] = None, direct_head: bool = False):
+                spec: Optional[FilterSpec] = None, call: Optional[int] = None, direct_head: bool = False, uniform: bool = False):
         """SetImpulse + (Add, Get) loop over x in calls of `call` (default = block) samples."""
         ir = np.ascontiguousarray(ir, dtype=np.float64)
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.zeros_like(x)
         h = self._nuc_create()
         try:
-            ok = self._nuc_set_impulse(h, ir, block, scale, spec, direct_head)
+            if uniform and self.prefix != "cpqo_":
+                raise ValueError("the uniform-partition extension is not a reference mode")
+            ok = self._nuc_set_impulse(h, ir, block, scale, spec, int(direct_head) | (2 if uniform else 0))
             if not ok:
                 raise RuntimeError("SetImpulse failed")
             layout = self._nuc_layout(h)

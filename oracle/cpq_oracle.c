@@ -319,7 +319,7 @@ int cpqo_nuc_set_impulse_ex(cpqo_nuc* c, const double* impulse_in, int ir_len, i
     c->direct_pending = 0;
     double* impulse_copy = NULL;
     const double* impulse = impulse_in;
-    if (direct_head)
+    if (direct_head & 1)
     {
         const int direct_part = cpqo_next_pow2(block_size > 64 ? block_size : 64);
         int taps = direct_part < 32 ? direct_part : 32;   /* kMaxDirectTaps */
@@ -373,7 +373,9 @@ int cpqo_nuc_set_impulse_ex(cpqo_nuc* c, const double* impulse_in, int ir_len, i
     const int l0_max = 32 * l0_part;
     const int l0_by_tail = (int) llround(tail_start * sr_tail);
     const int l0_target = cpqo_clampi(l0_part, l0_max, l0_by_tail);
-    const int l0_len = ir_len < (tail_enabled ? l0_target : l0_max) ? ir_len : (tail_enabled ? l0_target : l0_max);
+    /* direct_head bit 1 = the uniform-partition extension of the product (not a reference mode): the whole IR in layer 0 */
+    const int uniform_ext = (direct_head & 2) != 0;
+    const int l0_len = uniform_ext ? ir_len : (ir_len < (tail_enabled ? l0_target : l0_max) ? ir_len : (tail_enabled ? l0_target : l0_max));
     int l1_len = 0, l2_len = 0;
     if (tail_enabled)
     {

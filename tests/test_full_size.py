@@ -41,6 +41,26 @@ def test_cfg1_stereo_65536_taps_10s_noise(checker):
         assert np.abs(y[ch] - want).max() <= TOL, ch
 
 
+def test_cfg1b_uniform_extension_10s_noise():
+    """configs[0] as worded: 65,536 taps in 128 uniform partitions of 512 (cfg.uniform_partitions, our extension): 10 s of
+    noise against linear convolution."""
+    from scipy.signal import fftconvolve
+    sr, T = 48000.0, _whole(480000)
+    irs = [signals.synth_ir(65536, 2 + ch) for ch in range(2)]
+    x = np.stack([signals.noise(T, 1 + 10 * ch) for ch in range(2)])
+    eng = ConvoPeqEngine(1, 2, sr, BLOCK, T, uniform_partitions=True)
+    for ch in range(2):
+        eng.set_impulse(0, ch, irs[ch], 1.0, None)
+    lay = eng.layout()
+    assert lay.num_layers == 1 and lay.layers[0].num_parts_ir == 128
+    y = x.copy()
+    eng.process(y, capi.STAGE_CONV)
+    eng.close()
+    for ch in range(2):
+        lin = fftconvolve(x[ch], irs[ch])[:T]
+        assert np.abs(y[ch] - lin).max() <= 1e-12 * max(1.0, np.abs(lin).max()), ch
+
+
 @pytest.mark.parametrize("sat", [0.2, 0.0])
 def test_cfg2_eq_only_60s_sweep(checker, sat):
     """configs[1]: stereo 48 kHz, 20-band peaking/shelf cascade only, 60 s log sweep."""

@@ -161,6 +161,29 @@ def test_direct_head_matches_reference(checker, ir_len, block, T, kw, shared):
         assert np.abs(y[q] - want).max() <= TOL, q
 
 
+def test_uniform_partition_extension(oracle):
+    """BASELINE config 1 wording, "uniform partitioned convolution block 512" for 65,536 taps = 128 x 512: not expressible in the
+    reference (L0 is capped at 32 partitions), offered as cfg.uniform_partitions.  Checked against linear convolution and
+    against the restatement with the same cap lifted."""
+    from scipy.signal import fftconvolve
+    ir_len, block, T = 65536, 512, 65536
+    irs = [signals.synth_ir(ir_len, 2), signals.synth_ir(ir_len, 3)]
+    x = np.stack([signals.noise(T, 1), signals.noise(T, 11)])
+    eng = ConvoPeqEngine(1, 2, 48000.0, block, T, uniform_partitions=True)
+    for ch in range(2):
+        eng.set_impulse(0, ch, irs[ch], 1.0, None)
+    lay = eng.layout()
+    assert lay.num_layers == 1 and lay.layers[0].num_parts_ir == 128 and lay.layers[0].part_size == 512
+    y = x.copy()
+    eng.process(y, capi.STAGE_CONV)
+    eng.close()
+    for ch in range(2):
+        lin = fftconvolve(x[ch], irs[ch])[:T]
+        assert np.abs(y[ch] - lin).max() <= 1e-12 * max(1.0, np.abs(lin).max())
+        want, lo = oracle.nuc_run(irs[ch], x[ch], block, uniform=True)
+        assert lo["num_layers"] == 1 and np.abs(y[ch] - want).max() <= TOL
+
+
 def test_ir_scale(checker):
     ir = signals.synth_ir(20000, 4)
     T = 16384

@@ -143,3 +143,13 @@ def test_outer_mix_restatement_and_peak_latency(oracle):
     one = np.zeros(500)
     one[123] = 1.0
     assert ir_peak_latency(one) == 123
+
+
+def test_uniform_extension_restatement_is_linear_convolution(oracle):
+    """The restatement with the L0 cap lifted (the product's uniform-partition extension, BASELINE config 1 wording) is plain
+    linear convolution."""
+    from scipy.signal import fftconvolve
+    ir, x = signals.synth_ir(40000, 5), signals.noise(16384, 6)
+    y, lay = oracle.nuc_run(ir, x, 512, uniform=True)
+    assert lay["num_layers"] == 1 and lay["layers"][0]["num_parts_ir"] == 79
+    assert np.abs(y - fftconvolve(x, ir)[:16384]).max() <= 1e-13
