@@ -83,8 +83,9 @@ struct LayerDev
     bool hasGain = false, hasTilt = false;
     DevBuf<double2> X, Y;   // workspace spectra for a chunk of sequences
     DevBuf<double> tail;    // [chunk][K*P] (layers >= 1)
-    DevBuf<int64_t> tailSrc;
+    DevBuf<int64_t> tailSrc;   // layers >= 1: delay-line position per callback; layer 0: ring position per callback (l0Src)
     DevBuf<int32_t> blockMap;
+    DevBuf<int32_t> l0Count;   // layer 0 only: samples the ring delivers per callback (non-power-of-two host blocks)
     bool hasBlockMap = false;
 };
 
@@ -411,9 +412,12 @@ cpq_status Engine::init(const cpq_config* c)
         setError("invalid config");
         return CPQ_ERR_INVALID;
     }
-    if (cfg.block_size < 64 || cfg.block_size > 8192 || (cfg.block_size & (cfg.block_size - 1)) != 0)
+    // Power-of-two host blocks are the reference's regular case (L0 partition == block, zero latency).  Other host blocks run
+    // like the application does: SetImpulse gets the block rounded up to a power of two (knownBlockSize) while Add/Get are
+    // called with the host block (preferredCallSize), LoaderThread.cpp:230,239-245 -- L0 then goes through its output ring.
+    if (cfg.block_size < 64 || cfg.block_size > 8192 || (cfg.block_size % 32) != 0)
     {
-        setError("block_size must be a power of two in 64..8192");
+        setError("block_size must be in 64..8192 and a multiple of 32 (a power of two, or e.g. 480 / 960)");
         return CPQ_ERR_UNSUPPORTED;
     }
     if (cfg.max_samples % cfg.block_size != 0)
@@ -528,7 +532,11 @@ cpq_status Engine::setImpulse(int stream_, int ch, const double* ir, int len, do
         return CPQ_ERR_INVALID;
     }
     ConvPlan p;
-    if (!makeConvPlan(len, cfg.block_size, spec, p, cfg.uniform_partitions != 0))
+    int knownBlock = 64;
+    while (knownBlock < cfg.block_size) knownBlock <<= 1;   // juce::nextPowerOfTwo(host block)
+    const bool planOk = makeConvPlan(len, knownBlock, spec, p, cfg.uniform_partitions != 0);
+    p.callSize = cfg.block_size;
+    if (!planOk)
     {
         setError("set_impulse: SetImpulse would reject these parameters");
         return CPQ_ERR_INVALID;
@@ -981,6 +989,13 @@ cpq_status Engine::ensureGather(int64_t nCallbacks)
 {
     if (gplanCallbacks == nCallbacks) return CPQ_OK;
     simulateCallbacks(plan, nCallbacks, gplan);
+    if (!gplan.l0Identity)
+    {
+        CPQ_CUDA(layer[0].tailSrc.ensure((size_t) nCallbacks));
+        CPQ_CUDA(layer[0].l0Count.ensure((size_t) nCallbacks));
+        CPQ_CUDA(cudaMemcpyAsync(layer[0].tailSrc.p, gplan.l0Src.data(), (size_t) nCallbacks * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+        CPQ_CUDA(cudaMemcpyAsync(layer[0].l0Count.p, gplan.l0Count.data(), (size_t) nCallbacks * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    }
     for (int li = 1; li < plan.numLayers; ++li)
     {
         LayerDev& L = layer[li];
@@ -1324,6 +1339,14 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         setError("process: empty stream window");
         return CPQ_ERR_INVALID;
     }
+    // host block != L0 partition: the L0 output goes through the reference's output ring, i.e. to its own buffer, and the
+    // EQ launch gathers it per callback; io keeps the input until then
+    const bool l0Ring = doConv && !gplan.l0Identity;
+    if (l0Ring && (directHead || !fullRange || nPeers > 0))
+    {
+        setError("process: a host block that is not a power of two cannot be combined with the direct-form head or partition-range sharding");
+        return CPQ_ERR_UNSUPPORTED;
+    }
     int64_t K[CPQ_MAX_LAYERS] = {};
     int chunk = nSeq;
     if (doConv)
@@ -1334,7 +1357,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             const LayerPlan& l = plan.layers[li];
             K[li] = gplan.framesNeeded[li];
             perSeq += (size_t) K[li] * l.partSize * sizeof(double2) * 2;
-            if (li > 0) perSeq += (size_t) K[li] * l.partSize * sizeof(double);
+            if (li > 0 || l0Ring) perSeq += (size_t) K[li] * l.partSize * sizeof(double);
         }
         chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) nSeq, cfg.workspace_bytes / std::max<size_t>(perSeq, 1)));
     }
@@ -1359,7 +1382,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             const LayerPlan& l = plan.layers[li];
             CPQ_CUDA(layer[li].X.ensure((size_t) chunk * K[li] * l.partSize));
             CPQ_CUDA(layer[li].Y.ensure((size_t) chunk * K[li] * l.partSize));
-            if (li > 0) CPQ_CUDA(layer[li].tail.ensure((size_t) chunk * K[li] * l.partSize + 2));
+            if (li > 0 || l0Ring) CPQ_CUDA(layer[li].tail.ensure((size_t) chunk * K[li] * l.partSize + 2));
         }
     const size_t nChunks = (size_t) ((nSeq + chunk - 1) / chunk);
     // event pool layout: [c*6 + 0..4] stage boundaries on the compute stream, [c*6 + 5] H2D done on the copy-in stream
@@ -1403,7 +1426,8 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
     }
 
     auto fillEqCommon = [&](EqArgs& a) {
-        a.blockLog2 = ilog2(B);
+        a.blockLog2 = (B & (B - 1)) == 0 ? ilog2(B) : -1;
+        a.blockSize = B;
         a.T = T;
         a.ioStride = stride;
         a.doEq = doEq ? 1 : 0;
@@ -1552,8 +1576,8 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 a.framesPerSeq = (int) K[li];
                 a.framesOut = (int) K[li];
                 a.totalFrames = (int64_t) ns * K[li];
-                a.out = li == 0 ? ioC : layer[li].tail.p;
-                a.outStride = li == 0 ? stride : (int64_t) K[li] * l.partSize;
+                a.out = (li == 0 && !l0Ring) ? ioC : layer[li].tail.p;
+                a.outStride = (li == 0 && !l0Ring) ? stride : (int64_t) K[li] * l.partSize;
                 a.tw = layer[li].tw.p;
                 a.ptw = layer[li].ptw.p;
                 a.scratch = layer[li].X.p;   // the MAC has consumed it
@@ -1606,6 +1630,13 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 e.tailGain[li - 1] = plan.layers[li].gain;
             }
             e.outer = (cfg.conv_boundary == CPQ_CONV_OUTER && fullRange) ? 1 : 0;
+            if (l0Ring)
+            {
+                e.l0 = layer[0].tail.p;
+                e.l0Stride = (int64_t) K[0] * plan.layers[0].partSize;
+                e.l0Src = layer[0].tailSrc.p;
+                e.l0Count = layer[0].l0Count.p;
+            }
         }
         else
         {

@@ -108,7 +108,14 @@ struct EqArgs
     const int32_t* blockMap[2];    // nullable: stream block -> frame
     int tailPartLog2[2];
     double tailGain[2];
-    int blockLog2;          // log2(block size)
+    int blockLog2;          // log2(block size), or -1 when the host block is not a power of two (then blockSize divides)
+    int blockSize;          // samples per callback
+    // L0 through the reference's output ring when the host block differs from the L0 partition (non-power-of-two hosts:
+    // SetImpulse gets the block rounded up, Add/Get run with the host block): out[c B + i] = l0[l0Src[c] + i] for i < l0Count[c]
+    const double* l0;       // nullable [nSeq][l0Stride]; then io holds the convolver input, not the L0 output
+    int64_t l0Stride;
+    const int64_t* l0Src;
+    const int32_t* l0Count;
     int outer;              // CPQ_CONV_OUTER: scrub + wet gain
     double wetGain;
     // EQ
@@ -455,7 +462,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
 
     // ================= compute warps: one 512-sample segment each =================
     const double sat = a.doEq ? a.sat[set] : 0.0;
-    const int bmask = (1 << a.blockLog2) - 1;
+    const int bmask = a.blockLog2 >= 0 ? (1 << a.blockLog2) - 1 : 0;   // fast path only (power-of-two blocks)
     const int64_t w0 = t0 + (int64_t) warp * kEqSeg;                       // first sample of this warp's segment
     const int nValid = (int) max((int64_t) 0, min((int64_t) kEqSeg, a.T - w0));
     double* wtile = tile + warp * 32 * kEqPad;
@@ -464,7 +471,8 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
     // ---- coalesced load + layer assembly (Get) ----
     // Fast path: callbacks are whole multiples of 512 samples and the tail streams are stored in stream order
     // (regular plans), so the tail source position is one lookup per (layer, 512-sample sub-block).
-    const bool segFast = a.assemble && a.blockLog2 >= 9 && a.blockMap[0] == nullptr && a.blockMap[1] == nullptr;
+    const bool segFast = a.assemble && a.blockLog2 >= 9 && a.blockMap[0] == nullptr && a.blockMap[1] == nullptr && a.l0 == nullptr;
+    auto cbOf = [&](int64_t t) -> int64_t { return a.blockLog2 >= 0 ? (t >> a.blockLog2) : t / a.blockSize; };
     if (!a.assemble || segFast)
     {
         const bool outer = a.assemble && a.outer;
@@ -621,8 +629,9 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                     v = a.peer[0][(io - a.io) + t];
                     for (int p = 1; p < a.nPeers; ++p) v += a.peer[p][(io - a.io) + t];
                 }
-                const int64_t c = t >> a.blockLog2;
-                const int off = (int) t & bmask;
+                const int64_t c = cbOf(t);
+                const int off = (int) (t - c * a.blockSize);
+                if (a.l0) v = off < __ldg(a.l0Count + c) ? __ldg(a.l0 + (size_t) seq * a.l0Stride + __ldg(a.l0Src + c) + off) : 0.0;
                 for (int l = 0; l < a.nTail; ++l)
                 {
                     const int64_t sp = __ldg(a.tailSrc[l] + c);
@@ -669,9 +678,15 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
         double sq = 0.0;
 #pragma unroll
         for (int j = 0; j < kEqL; ++j) sq = fma(x[j], x[j], sq);
+        const int64_t tb = w0 + (int64_t) lane * kEqL;
+        if (a.blockLog2 < 0)
+        {
+            // host block not a power of two (a multiple of 32): the lanes of a callback are not an aligned group
+            if (tb < a.T) atomicAdd(dst + (size_t) seq * a.nCallbacks + tb / a.blockSize, sq);
+            return;
+        }
         const int lanesPerCb = min(32, (1 << a.blockLog2) / kEqL);
         for (int o = 1; o < lanesPerCb; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        const int64_t tb = w0 + (int64_t) lane * kEqL;
         if ((lane & (lanesPerCb - 1)) == 0 && tb < a.T) atomicAdd(dst + (size_t) seq * a.nCallbacks + (tb >> a.blockLog2), sq);
     };
     if (STATS && a.sumsqIn) blockStats(a.sumsqIn);
@@ -811,8 +826,9 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                 if (a.gainTab)
                 {
                     const int64_t tb = w0 + (int64_t) lane * kEqL;   // a thread's block never straddles a callback (block >= 64)
-                    const double2 g = __ldg(reinterpret_cast<const double2*>(a.gainTab) + (size_t) gainRow * a.nCallbacks + (tb >> a.blockLog2));
-                    const int off0 = (int) tb & bmask;
+                    const int64_t cb0 = cbOf(tb);
+                    const double2 g = __ldg(reinterpret_cast<const double2*>(a.gainTab) + (size_t) gainRow * a.nCallbacks + cb0);
+                    const int off0 = (int) (tb - cb0 * a.blockSize);
 #pragma unroll
                     for (int j = 0; j < kEqL; ++j) x[j] *= fma((double) (off0 + j), g.y, g.x);
                 }
@@ -1054,8 +1070,8 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
             {
                 double v = wtile[eq_sidx(i)];
                 const int64_t t = w0 + i;
-                const int64_t c = t >> a.blockLog2;
-                const int off = (int) t & bmask;
+                const int64_t c = cbOf(t);
+                const int off = (int) (t - c * a.blockSize);
                 const double2 g = __ldg(reinterpret_cast<const double2*>(a.gainTab) + (size_t) gainRow * a.nCallbacks + c);
                 v *= fma((double) off, g.y, g.x);
                 op[i] = finish(v);

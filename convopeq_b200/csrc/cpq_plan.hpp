@@ -60,7 +60,8 @@ struct LayerPlan
 struct ConvPlan
 {
     int numLayers = 0;
-    int blockSize = 0;
+    int blockSize = 0;   // SetImpulse's blockSize (the host's block rounded up to a power of two, LoaderThread.cpp:230)
+    int callSize = 0;    // samples per Add/Get call = the host's block (preferredCallSize, :239-245); == blockSize for power-of-two hosts
     int irLen = 0;
     int tailMode = 1;
     bool tailEnabled = true;
@@ -71,7 +72,7 @@ struct ConvPlan
 
     bool sameGeometry(const ConvPlan& o) const
     {
-        if (numLayers != o.numLayers || blockSize != o.blockSize) return false;
+        if (numLayers != o.numLayers || blockSize != o.blockSize || callSize != o.callSize) return false;
         for (int l = 0; l < numLayers; ++l)
         {
             const LayerPlan &a = layers[l], &b = o.layers[l];
@@ -106,6 +107,7 @@ inline bool makeConvPlan(int irLen, int blockSize, const cpq_filter_spec* fs, Co
     if (irLen <= 0 || blockSize <= 0) return false;
     out = ConvPlan {};
     out.blockSize = blockSize;
+    out.callSize = blockSize;
     out.irLen = irLen;
     out.hasSpec = fs != nullptr;
     if (fs) out.spec = *fs;
@@ -290,7 +292,7 @@ inline void simulateCallbacks(const ConvPlan& plan, int64_t nCallbacks, GatherPl
 {
     g = GatherPlan {};
     g.nCallbacks = nCallbacks;
-    const int B = plan.blockSize;
+    const int B = plan.callSize > 0 ? plan.callSize : plan.blockSize;
 
     // ---- L0 ring (ringWrite/ringRead; capacity never binds when Get follows every Add) ----
     {

@@ -88,7 +88,10 @@ typedef struct cpq_config
     int32_t device;        /* CUDA ordinal */
     int32_t n_streams;     /* independent streams in the batch */
     int32_t n_channels;    /* channels per stream: 1 or 2 (the reference engine is <= 2 channels) */
-    int32_t block_size;    /* host callback size the reference would run with (power of two, 64..8192) */
+    int32_t block_size;    /* host callback size the reference would run with: 64..8192, a multiple of 32.  A power of two is
+                              the regular case; otherwise (480, 960 ...) the convolver is prepared with the block rounded up
+                              to a power of two and called with this block, like the application does
+                              (ConvolverProcessor.LoaderThread.cpp:230,239-245) */
     double sample_rate;
     int64_t max_samples;   /* capacity per channel for one cpq_process call (multiple of block_size) */
     int32_t conv_boundary; /* cpq_conv_boundary */

@@ -390,7 +390,7 @@ class Ref(_Base):
 
 
 def _chain_run(self, irs, bands, x, sr, block, spec, saturation, total_gain_db, makeup, outer, do_eq, do_epilogue,
-               structure=0, agc=False):
+               structure=0, agc=False, known_block=None):
     """One stream through the per-callback ConvolverThenEQ chain (conv -> wet gain -> EQ -> makeup*headroom).
     irs: (irL, irR) or None; x: [2, T] (copied). Returns y [2, T]. Releases the GIL inside the C call."""
     L = self.lib
@@ -402,7 +402,9 @@ def _chain_run(self, irs, bands, x, sr, block, spec, saturation, total_gain_db, 
         if irs is not None:
             for c in range(2):
                 nucs[c] = self._nuc_create()
-                if not self._nuc_set_impulse(nucs[c], np.ascontiguousarray(irs[c], dtype=np.float64), block, 1.0, spec):
+                # the application prepares the convolver with the host block rounded up to a power of two (knownBlockSize) and
+                # calls it with the host block (preferredCallSize), LoaderThread.cpp:230,239-245
+                if not self._nuc_set_impulse(nucs[c], np.ascontiguousarray(irs[c], dtype=np.float64), known_block or block, 1.0, spec):
                     raise RuntimeError("SetImpulse failed")
         if do_eq:
             if pre == "cpqref_":
@@ -466,9 +468,9 @@ def _chain_free(self, handles):
 def _install_chain():
     for cls in (Oracle, Ref):
         def chain_run(self, irs, bands, x, sr, block, spec=None, saturation=0.2, total_gain_db=0.0, makeup=1.0,
-                      outer=True, do_eq=True, do_epilogue=True, structure=0, agc=False):
+                      outer=True, do_eq=True, do_epilogue=True, structure=0, agc=False, known_block=None):
             return _chain_run(self, irs, bands, x, sr, block, spec, saturation, total_gain_db, makeup, outer, do_eq, do_epilogue,
-                              structure, agc)
+                              structure, agc, known_block)
         cls.chain_run = chain_run
         cls.chain_prepare = _chain_prepare
         cls.chain_process_prepared = _chain_process_prepared

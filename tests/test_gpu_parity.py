@@ -184,6 +184,52 @@ def test_uniform_partition_extension(oracle):
         assert lo["num_layers"] == 1 and np.abs(y[ch] - want).max() <= TOL
 
 
+@pytest.mark.parametrize("block,ir_len,T,kw", [(480, 65536, 480 * 80, None), (480, 131072, 480 * 120, {}), (96, 30000, 96 * 300, None),
+                                               (960, 70000, 960 * 60, {}), (1920, 300000, 1920 * 40, None), (480, 300, 480 * 10, None)])
+def test_non_power_of_two_host_block(checker, block, ir_len, T, kw):
+    """Hosts whose block is not a power of two (480 = 10 ms at 48 kHz, ...): the application prepares the convolver with the block
+    rounded up (SetImpulse(knownBlockSize)) and calls Add/Get with the host block, so L0 goes through its output ring with
+    the reference's varying latency and the tails follow the per-call distribution schedule."""
+    ospec, cspec = _specs(kw)
+    known = 64
+    while known < block:
+        known *= 2
+    irs = [signals.synth_ir(ir_len, 60 + ch) for ch in range(2)]
+    x = np.stack([signals.noise(T, 62 + ch) for ch in range(2)])
+    eng = ConvoPeqEngine(1, 2, 48000.0, block, T)
+    for ch in range(2):
+        eng.set_impulse(0, ch, irs[ch], 1.0, cspec)
+    assert eng.latency() == known
+    y = x.copy()
+    eng.process(y, capi.STAGE_CONV)
+    eng.close()
+    for ch in range(2):
+        want, _ = checker.nuc_run(irs[ch], x[ch], known, spec=ospec, call=block)
+        assert np.abs(y[ch] - want).max() <= TOL, ch
+        assert np.abs(want).max() > 1e-3
+
+
+@pytest.mark.parametrize("agc", [False, True])
+def test_non_power_of_two_host_block_full_chain(checker, agc):
+    """480-sample host callbacks through conv -> EQ (gain ramp event / AGC per 480-sample callback) -> epilogue, three streams."""
+    sr, block, T, ir_len, n = 48000.0, 480, 480 * 100, 131072, 3
+    eng = ConvoPeqEngine(n, 2, sr, block, T, conv_boundary=capi.CONV_OUTER)
+    x = np.stack([signals.noise(T, 400 + i, 0.3) for i in range(2 * n)])
+    irs = [signals.synth_ir(ir_len, 420 + i) for i in range(2 * n)]
+    for s in range(n):
+        for ch in range(2):
+            eng.set_impulse(s, ch, irs[2 * s + ch], 1.0, capi.default_filter_spec())
+        eng.set_eq(s, signals.to_band(signals.band_params(440 + s)), agc=agc)
+    eng.set_epilogue(1.1, 0)
+    y = x.copy()
+    eng.process(y, capi.STAGE_ALL)
+    eng.close()
+    for s in range(n):
+        want = checker.chain_run((irs[2 * s], irs[2 * s + 1]), signals.to_eqband(signals.band_params(440 + s)), x[2 * s:2 * s + 2], sr, block,
+                                 OFilterSpec(), makeup=1.1, agc=agc, known_block=512)
+        assert np.abs(y[2 * s:2 * s + 2] - want).max() <= TOL, s
+
+
 def test_ir_scale(checker):
     ir = signals.synth_ir(20000, 4)
     T = 16384
@@ -484,6 +530,9 @@ def test_error_paths_fail_loudly():
     assert e.value.status == capi.ERR_NOT_READY
     with pytest.raises(capi.CpqError):
         eng.process(np.zeros((2, 1000)), capi.STAGE_EQ)   # T not a multiple of the block
+    with pytest.raises(capi.CpqError) as e:
+        ConvoPeqEngine(1, 2, 44100.0, 441, 4410)         # host blocks must be a multiple of 32
+    assert e.value.status == capi.ERR_UNSUPPORTED
     bands = signals.to_band(signals.band_params(1, modes=[3] * 20))
     mono = ConvoPeqEngine(1, 1, 48000.0, 512, 4096)
     with pytest.raises(capi.CpqError) as e:
