@@ -73,7 +73,7 @@ EXPORTS = [
     "cpq_latency", "cpq_get_timings", "cpq_get_eq_state", "cpq_cuda_stream", "cpq_kernel_launch_count",
     "cpq_plan_layout", "cpq_set_eq_mode", "cpq_band_node_active", "cpq_get_agc_state",
     "cpq_set_mix", "cpq_ir_peak_latency", "cpq_set_direct_head", "cpq_parse_eq_preset",
-    "cpq_set_convolver_bypass", "cpq_set_partial_sources", "cpq_set_stream_window", "cpq_ir_scale_factor", "cpq_ir_freq_peak_gain", "cpq_ir_min_phase",
+    "cpq_set_convolver_bypass", "cpq_set_peak_limiter", "cpq_set_partial_sources", "cpq_set_stream_window", "cpq_ir_scale_factor", "cpq_ir_freq_peak_gain", "cpq_ir_min_phase",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -121,6 +121,7 @@ def load() -> C.CDLL:
     L.cpq_set_mix.argtypes = [vp, C.c_float, C.c_int]
     L.cpq_set_direct_head.argtypes = [vp, C.c_int]
     L.cpq_set_convolver_bypass.argtypes = [vp, C.c_int]
+    L.cpq_set_peak_limiter.argtypes = [vp, C.c_double]
     L.cpq_set_partial_sources.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.cpq_set_stream_window.argtypes = [vp, C.c_int, C.c_int]
     L.cpq_ir_scale_factor.argtypes = [dp, dp, C.c_int, dp, dp, C.c_int, C.c_double, C.POINTER(IrScale)]

@@ -187,6 +187,9 @@ struct Engine
     const double* peers[CPQ_MAX_PEERS] {};
     int convBypassed = 0;               // runtimeSnapshot.bypassed: processBypassWithLatencyCompensation (Runtime.cpp:123-186)
     DevBuf<double> dryBuf;              // copy of the convolver input for the dry path (mix < 0.999) / the direct-form head
+    double limiterMs = 0.0;             // SimplePeakLimiter release (ms); 0 = stage off.  The reference engine uses 100 ms
+    DevBuf<unsigned> limFlag;           // [n_streams]
+    DevBuf<double> limEnv;              // [n_streams] envelope after the last call
     int directHead = 0;                 // enableDirectHead of SetImpulse (experimental in the reference)
     DevBuf<double> directTaps;          // [nH][32] reversed, scaled head taps
     bool postDirty = true;
@@ -1041,7 +1044,7 @@ cpq_status Engine::launchEq(EqArgs& a)
     const unsigned grid = (unsigned) a.nSeq * (unsigned) a.nRuns;
     if (a.doEq && anyPar) eq_kernel<true, true, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
     else if (a.sumsqIn || a.sumsqOut || a.nPeers > 0) eq_kernel<true, false, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
-    else if (a.postMask || a.finalClamp) eq_kernel<true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
+    else if (a.postMask || a.finalClamp || a.limFlag) eq_kernel<true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
     else eq_kernel<false><<<grid, kEqThreads, kEqSmemBytes, stream>>>(a);
     ++launches;
     CPQ_CUDA(cudaGetLastError());
@@ -1090,6 +1093,7 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
         g.doEpilogue = 0;
         g.finalClamp = 0;
         g.applyHeadroom = 0;
+        g.limFlag = nullptr;
     };
     // streams of this chunk in the Parallel structure with Mid/Side bands (Processing.cpp:790-832): every band works on the
     // band input, so Mid and Side rows are encoded once from the input, all Mid bands run on the Mid row and all Side bands
@@ -1304,6 +1308,14 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         CPQ_CUDA(postState.ensure((size_t) nSeq * kEqPostStages * 2));
     }
     const bool doDither = doEpi && ditherBits > 0;
+    const bool limiterOn = doEpi && limiterMs > 0.0;
+    if (limiterOn)
+    {
+        CPQ_CUDA(limFlag.ensure((size_t) cfg.n_streams));
+        CPQ_CUDA(limEnv.ensure((size_t) cfg.n_streams));
+        // with dither the quantised signal is what the limiter sees: no detection in the EQ launch, every stream runs it
+        CPQ_CUDA(cudaMemsetAsync(limFlag.p, doDither ? 0xff : 0, (size_t) cfg.n_streams * sizeof(unsigned), stream));
+    }
     if (doDither && uniformsPerCh != T)
     {
         setError("process: dither enabled but cpq_set_dither_uniforms does not hold exactly T samples per channel");
@@ -1362,6 +1374,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) nSeq, cfg.workspace_bytes / std::max<size_t>(perSeq, 1)));
     }
     if (hostPlanar) chunk = std::max(1, std::min(chunk, (nSeq + 31) / 32));   // short pipeline fill/drain
+    if (limiterOn) chunk = std::max(cfg.n_channels, chunk / cfg.n_channels * cfg.n_channels);   // whole streams per chunk
     if (doEq && (anyAgc || anyMs))
     {
         // AGC statistics and Mid/Side bands couple the channels of a stream: whole streams per chunk, scratch rows bounded
@@ -1444,7 +1457,10 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         a.applyHeadroom = (doEpi && ditherBits <= 0) ? 1 : 0;
         a.postc = postc.p;
         a.postMask = postMask;
-        a.finalClamp = (doEpi && outCfg.finalClamp && ditherBits <= 0) ? 1 : 0;   // with dither the dither kernel clamps
+        // scrub (bit 0) + clamp (bit 1); with dither the dither kernel does both, with the limiter the limiter kernel clamps
+        a.finalClamp = (doEpi && outCfg.finalClamp && ditherBits <= 0) ? (limiterOn ? 1 : 3) : 0;
+        a.limFlag = nullptr;
+        a.limDiv = cfg.n_channels;
         a.nPeers = 0;
         a.wetGain = equalPowerSin(cfg.conv_boundary == CPQ_CONV_OUTER ? mix : 1.0) * 1.0;   // CONVOLUTION_HEADROOM_GAIN = 1.0 (ConvolverProcessor.h:209)
     };
@@ -1654,6 +1670,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         e.setOfSeq = setOfSeq.p ? setOfSeq.p + s0 : nullptr;   // absolute set indices
         e.stateOut = stateOut.p + (size_t) s0 * CPQ_NUM_BANDS * 2;
         e.postStateOut = postMask ? postState.p + (size_t) s0 * kEqPostStages * 2 : nullptr;
+        if (limiterOn && !doDither) e.limFlag = limFlag.p + s0 / cfg.n_channels;
         if (needsDry)
         {
             // assembly + scrub + wet gain on their own, then the dry path, then the remaining stages without assembly
@@ -1700,8 +1717,24 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             d.scale = 1.0 / std::pow(2.0, ditherBits - 1);
             d.invScale = std::pow(2.0, ditherBits - 1);
             d.z = ditherZ.p + (size_t) s0 * 12;
-            d.finalClamp = outCfg.finalClamp;
+            d.finalClamp = outCfg.finalClamp ? (limiterOn ? 1 : 3) : 0;
             dither_kernel<<<(unsigned) ((ns + 31) / 32), 32, 0, stream>>>(d);
+            ++launches;
+            CPQ_CUDA(cudaGetLastError());
+        }
+        if (limiterOn)
+        {
+            LimiterArgs la {};
+            la.io = ioC;
+            la.stride = stride;
+            la.T = T;
+            la.nStreams = ns / cfg.n_channels;
+            la.nch = cfg.n_channels;
+            la.flag = limFlag.p + s0 / cfg.n_channels;
+            la.release = std::exp(-1.0 / (cfg.sample_rate * limiterMs * 0.001));   // SimplePeakLimiter::prepare
+            la.clamp = outCfg.finalClamp ? 1 : 0;
+            la.envOut = limEnv.p + s0 / cfg.n_channels;
+            limiter_kernel<<<(unsigned) ((la.nStreams + 31) / 32), 32, 0, stream>>>(la);
             ++launches;
             CPQ_CUDA(cudaGetLastError());
         }
@@ -2030,6 +2063,13 @@ cpq_status cpq_set_stream_window(cpq_handle h, int first_stream, int n_streams)
     if (n_streams > 0 && first_stream + n_streams > h->cfg.n_streams) return CPQ_ERR_INVALID;
     h->winFirst = first_stream;
     h->winCount = n_streams;
+    return CPQ_OK;
+}
+
+cpq_status cpq_set_peak_limiter(cpq_handle h, double release_ms)
+{
+    if (!h || !(release_ms >= 0.0) || !std::isfinite(release_ms)) return CPQ_ERR_INVALID;
+    h->limiterMs = release_ms;
     return CPQ_OK;
 }
 

@@ -129,7 +129,9 @@ struct EqArgs
     const double* postc;    // [kEqPostStages][kEqcStride]
     unsigned postMask;      // bit i = post stage i enabled
     double* postStateOut;   // nullable [nSeq][kEqPostStages][2] final states of the output stages
-    int finalClamp;         // scrub (non-finite or |x| >= 1e300 -> 0) + clamp to +-kOutputHeadroom after the headroom multiply
+    int finalClamp;         // after the headroom multiply: bit 0 scrub (non-finite or |x| >= 1e300 -> 0), bit 1 clamp to +-kOutputHeadroom
+    unsigned* limFlag;      // nullable [nSeq / limDiv]: set when a stored sample could engage the peak limiter (|x| > threshold - knee/2)
+    int limDiv;             // channels per stream
     const double* gainTab;  // nullable [rows][nCallbacks][2] (start, inc); row = parameter set, or stream when gainBySeq
     const double* gainConst;// [nSets] settled total gain (used when gainTab == nullptr)
     int64_t nCallbacks;
@@ -1050,18 +1052,17 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
     {
         double* op = io + w0;
         const bool mulG = a.doGain && !gainInReg, mulM = a.doEpilogue && !makeupInReg, mulH = a.doEpilogue && a.applyHeadroom;
-        const bool clampOut = POST && a.doEpilogue && a.finalClamp;
+        const bool scrubOut = POST && a.doEpilogue && (a.finalClamp & 1), clampOut = POST && a.doEpilogue && (a.finalClamp & 2);
+        bool overLim = false;   // SimplePeakLimiter is the identity while every |x| <= clipStart (its envelope stays exactly 1)
         const double gconst = (mulG && !a.gainTab) ? __ldg(a.gainConst + set) : 1.0;
         const double mk = a.makeup;
         constexpr double hr = 0.8912509381337456;
         auto finish = [&](double v) {
             if (mulM) v *= mk;
             if (mulH) v *= hr;
-            if (clampOut)
-            {
-                if (!(fabs(v) < 1.0e300)) v = 0.0;
-                v = fmin(fmax(v, -hr), hr);
-            }
+            if (scrubOut && !(fabs(v) < 1.0e300)) v = 0.0;
+            if (POST) overLim |= !(fabs(v) <= 0.8413951287507587 - 0.108748 * 0.5);
+            if (clampOut) v = fmin(fmax(v, -hr), hr);
             return v;
         };
         if (mulG && a.gainTab)
@@ -1107,6 +1108,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                 }
             }
         }
+        if (POST && a.limFlag && __any_sync(0xffffffffu, overLim) && lane == 0) atomicOr(a.limFlag + seq / a.limDiv, 1u);
     }
 }
 
@@ -1174,6 +1176,75 @@ __global__ void agc_kernel(AgcArgs a)
         a.stateOut[(size_t) st * 3 + 1] = envOut;
         a.stateOut[(size_t) st * 3 + 2] = cur;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SimplePeakLimiter (audioengine/SimplePeakLimiter.h:36-86; processOutputDouble, DSPCoreDouble.cpp:700-710) between the
+// scrub and the hard clamp: threshold kOutputHeadroom - 0.5 dB, knee 1 dB, immediate attack, exponential release, one
+// envelope per stream for both channels.  The envelope update `want < env ? want : 1 + (env - 1) r` is not a monotone map
+// of env, so it does not compose into a scan; but the stage is exactly the identity for a stream none of whose samples
+// exceeds threshold - knee/2 (the envelope never leaves 1.0), which the EQ launch's store stage detects per stream.
+// Flagged streams run the recurrence serially, one thread per stream, together with the hard clamp that follows it.
+// ---------------------------------------------------------------------------------------------
+struct LimiterArgs
+{
+    double* io;             // this chunk's [nStreams * nch][stride]
+    int64_t stride, T;
+    int nStreams, nch;
+    const unsigned* flag;   // [nStreams]
+    double release;         // exp(-1 / (sr * releaseSeconds))
+    int clamp;              // +-kOutputHeadroom after the limiter
+    double* envOut;         // nullable [nStreams]
+};
+
+__global__ void limiter_kernel(LimiterArgs a)
+{
+    const int st = blockIdx.x * blockDim.x + threadIdx.x;
+    if (st >= a.nStreams) return;
+    if (!a.flag[st])
+    {
+        if (a.envOut) a.envOut[st] = 1.0;
+        return;
+    }
+    constexpr double thr = 0.8413951287507587, knee = 0.108748, clipStart = thr - knee * 0.5, hr = 0.8912509381337456;
+    double* L = a.io + (size_t) st * a.nch * a.stride;
+    double* R = a.nch > 1 ? L + a.stride : nullptr;
+    double env = 1.0;
+    for (int64_t i = 0; i < a.T; i += 2)   // T is even (a multiple of the block)
+    {
+        double2 l = *reinterpret_cast<const double2*>(L + i);
+        double2 r = R ? *reinterpret_cast<const double2*>(R + i) : l;
+        double lv[2] = { l.x, l.y }, rv[2] = { r.x, r.y };
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+        {
+            const double al = fabs(lv[k]), ar = R ? fabs(rv[k]) : al;
+            const double peak = al < ar ? ar : al;
+            const double sp = peak < 1.0e-12 ? 1.0e-12 : peak;
+            double want = 1.0;
+            if (sp > clipStart)
+            {
+                if (sp <= thr)
+                {
+                    const double t = __ddiv_rn(sp - clipStart, knee);
+                    const double shape = __dmul_rn(__dmul_rn(t, t), __dadd_rn(3.0, -__dmul_rn(2.0, t)));
+                    want = __dadd_rn(1.0, -__dmul_rn(__dadd_rn(1.0, -__ddiv_rn(thr, sp)), shape));
+                }
+                else want = __ddiv_rn(thr, sp);
+            }
+            env = want < env ? want : __dadd_rn(1.0, __dmul_rn(env - 1.0, a.release));
+            lv[k] *= env;
+            rv[k] *= env;
+            if (a.clamp)
+            {
+                lv[k] = fmin(fmax(lv[k], -hr), hr);
+                rv[k] = fmin(fmax(rv[k], -hr), hr);
+            }
+        }
+        *reinterpret_cast<double2*>(L + i) = make_double2(lv[0], lv[1]);
+        if (R) *reinterpret_cast<double2*>(R + i) = make_double2(rv[0], rv[1]);
+    }
+    if (a.envOut) a.envOut[st] = env;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1318,7 +1389,7 @@ struct DitherArgs
     double coeff[12];
     double scale, invScale;
     double* z;                // [nSeq][12] error history (carried)
-    int finalClamp;           // scrub + clamp to +-kOutputHeadroom after the quantiser (DSPCoreDouble.cpp:665-691, 712-737)
+    int finalClamp;           // after the quantiser: bit 0 scrub, bit 1 clamp to +-kOutputHeadroom (DSPCoreDouble.cpp:665-691, 712-737)
 };
 
 __global__ void dither_kernel(DitherArgs a)
@@ -1345,11 +1416,8 @@ __global__ void dither_kernel(DitherArgs a)
         for (int t = 11; t > 0; --t) z[t] = z[t - 1];
         z[0] = err;
         double o = q;
-        if (a.finalClamp)
-        {
-            if (!(fabs(o) < 1.0e300)) o = 0.0;
-            o = fmin(fmax(o, -0.8912509381337456), 0.8912509381337456);
-        }
+        if ((a.finalClamp & 1) && !(fabs(o) < 1.0e300)) o = 0.0;
+        if (a.finalClamp & 2) o = fmin(fmax(o, -0.8912509381337456), 0.8912509381337456);
         d[i] = o;
     }
 #pragma unroll

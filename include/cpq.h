@@ -200,9 +200,14 @@ cpq_status cpq_set_output_filter(cpq_handle h, int enabled, int conv_is_last, in
 /* The rest of processOutputDouble around the headroom / dither step, inside CPQ_STAGE_EPILOGUE:
  * dc_cutoff_hz > 0: the output UltraHighRateDCBlocker pair (UltraHighRateDCBlocker.h:60-126; the engine uses 3.0 Hz,
  * AudioEngine.h:643-651) after the makeup gain; hard_clamp: the 1e300 / non-finite scrub and the
- * +-kOutputHeadroom clamp (DSPCoreDouble.cpp:665-691, 712-737).  SimplePeakLimiter (:700-710) sits between the two and is
- * the identity while |y| <= 0.7870 (threshold - knee/2); it is not part of this path. */
+ * +-kOutputHeadroom clamp (DSPCoreDouble.cpp:665-691, 712-737).  SimplePeakLimiter (:700-710) sits between the two: see
+ * cpq_set_peak_limiter. */
 cpq_status cpq_set_output_stage(cpq_handle h, double dc_cutoff_hz, int hard_clamp);
+/* SimplePeakLimiter::prepare(sr, release_ms) + processBlock with the engine's constants (audioengine/SimplePeakLimiter.h,
+ * DSPCoreDouble.cpp:700-710, threshold kOutputHeadroom - 0.5 dB, knee 1 dB; the engine prepares it with 100 ms,
+ * AudioEngine.Processing.DSPCoreLifecycle.cpp:228), between the scrub and the hard clamp inside CPQ_STAGE_EPILOGUE; one
+ * envelope per stream for both channels, reset to 1 at the start of every call.  release_ms = 0 (default) leaves the stage out. */
+cpq_status cpq_set_peak_limiter(cpq_handle h, double release_ms);
 /* state.convolverInputTrimGain: applied between the EQ and the convolver in the EQThenConvolver order when it differs from
  * 1 by more than 1e-12 (DSPCoreDouble.cpp:438-445). */
 cpq_status cpq_set_conv_input_trim(cpq_handle h, double gain);

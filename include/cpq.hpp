@@ -150,6 +150,8 @@ public:
     /// scrub + +-kOutputHeadroom hard clamp, both inside CPQ_STAGE_EPILOGUE.
     /// convolverInputTrimGain (EQThenConvolver order: pass CPQ_ORDER_EQ_THEN_CONV in `stages`).
     bool setConvolverInputTrim(double gain) { return ok(cpq_set_conv_input_trim(h_, gain)); }
+    /// SimplePeakLimiter (release 100 ms in the reference engine) between the scrub and the hard clamp; 0 = off.
+    bool setPeakLimiter(double releaseMs) { return ok(cpq_set_peak_limiter(h_, releaseMs)); }
     /// ConvolverProcessor::setBypass: the convolver stage only delays by the dry path's latency compensation.
     bool setConvolverBypass(bool bypassed) { return ok(cpq_set_convolver_bypass(h_, bypassed ? 1 : 0)); }
     /// enableDirectHead of SetImpulse / StereoConvolver::init; call before the first SetImpulse.

@@ -167,10 +167,15 @@ class _Base:
 
     def output_run(self, x: np.ndarray, sr: float, block: int, use_filter: bool = True, conv_is_last: bool = False, hc: int = 1,
                    lc: int = 0, lp: int = 1, makeup: float = 1.0, dc_cutoff: float = 3.0, headroom: bool = True,
-                   clamp: bool = True) -> np.ndarray:
+                   clamp: bool = True, limiter_ms: float = 0.0) -> np.ndarray:
         """[OutputFilter] -> makeup -> [DC blocker] -> [headroom] -> [scrub + clamp] per callback on x[channels][T]."""
         y = np.ascontiguousarray(x, dtype=np.float64).copy()
         h = self._f("out_create")(sr, dc_cutoff if dc_cutoff > 0 else 1.0)
+        if limiter_ms > 0:
+            f = self._f("out_set_limiter")
+            f.argtypes = [C.c_void_p, C.c_double]
+            f.restype = None
+            f(h, limiter_ms)
         try:
             self._f("out_process")(h, _p(y[0]), _p(y[1]) if y.shape[0] > 1 else None, y.shape[1], block, int(use_filter),
                                    int(conv_is_last), hc, lc, lp, makeup, int(dc_cutoff > 0), int(headroom), int(clamp))

@@ -1615,7 +1615,47 @@ typedef struct cpqo_out
     double w[2][3][2];   /* [ch][stage][w1,w2] */
     double dc_alpha[2];
     double dc_state[2][2];
+    double lim_release, lim_env;   /* SimplePeakLimiter: exp(-1 / (sr * release)), envelope; release 0 = limiter off */
+    int lim_on;
 } cpqo_out;
+
+/* SimplePeakLimiter::prepare / reset (audioengine/SimplePeakLimiter.h:18-30); the engine prepares it with 100 ms
+ * (AudioEngine.Processing.DSPCoreLifecycle.cpp:228).  release_ms <= 0 switches the stage off. */
+void cpqo_out_set_limiter(cpqo_out* o, double release_ms)
+{
+    o->lim_on = release_ms > 0.0;
+    const double sec = release_ms * 0.001;
+    o->lim_release = (sec > 0.0 && o->sr > 0.0) ? exp(-1.0 / (o->sr * sec)) : 0.0;
+    o->lim_env = 1.0;
+}
+
+/* SimplePeakLimiter::processBlock (:36-86) with the engine's constants (DSPCoreDouble.cpp:703-710): threshold
+ * kOutputHeadroom - 0.5 dB, knee 1 dB; attack immediate, release towards 1; one envelope for both channels. */
+static void cpqo_limiter_block(cpqo_out* o, double* L, double* R, int n)
+{
+    const double thr = 0.8413951287507587, knee = 0.108748, clip_start = thr - knee * 0.5;
+    for (int i = 0; i < n; ++i)
+    {
+        const double al = fabs(L[i]), ar = R ? fabs(R[i]) : al;
+        const double peak = al > ar ? al : ar;          /* jmax(a, b) = a < b ? b : a */
+        const double sp = peak > 1.0e-12 ? peak : 1.0e-12;
+        double want = 1.0;
+        if (sp > clip_start)
+        {
+            if (sp <= thr)
+            {
+                const double t = (sp - clip_start) / knee;
+                const double shape = t * t * (3.0 - 2.0 * t);
+                want = 1.0 - (1.0 - thr / sp) * shape;
+            }
+            else want = thr / sp;
+        }
+        if (want < o->lim_env) o->lim_env = want;
+        else o->lim_env = 1.0 + (o->lim_env - 1.0) * o->lim_release;
+        L[i] *= o->lim_env;
+        if (R) R[i] *= o->lim_env;
+    }
+}
 
 cpqo_out* cpqo_out_create(double sr, double dc_cutoff)
 {
@@ -1651,7 +1691,7 @@ static double cpqo_biquad_step(double x, const double* c, double* w)
     return y;
 }
 
-/* Per callback: [OutputFilter] -> makeup -> [DC blocker] -> [headroom] -> [scrub + clamp]. */
+/* Per callback: [OutputFilter] -> makeup -> [DC blocker] -> [headroom] -> [scrub] -> [peak limiter] -> [clamp]. */
 void cpqo_out_process(cpqo_out* o, double* L, double* R, long total, int block, int use_filter, int conv_is_last, int hc, int lc,
                       int lp, double makeup, int use_dc, int headroom, int clamp)
 {
@@ -1696,10 +1736,17 @@ void cpqo_out_process(cpqo_out* o, double* L, double* R, long total, int block, 
                 {
                     double v = d[i];
                     if (!(isfinite(v) && fabs(v) < 1.0e300)) v = 0.0;
-                    v = v < -hr ? -hr : (v > hr ? hr : v);
                     d[i] = v;
                 }
         }
+        if (o->lim_on) cpqo_limiter_block(o, ch[0], ch[1], n);
+        if (clamp)
+            for (int k = 0; k < (R ? 2 : 1); ++k)
+                for (int i = 0; i < n; ++i)
+                {
+                    const double v = ch[k][i];
+                    ch[k][i] = v < -hr ? -hr : (v > hr ? hr : v);
+                }
     }
 }
 

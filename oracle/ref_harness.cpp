@@ -40,6 +40,7 @@
 #undef protected
 #include "UltraHighRateDCBlocker.h"
 #include "IRAnalyzer.h"
+#include "SimplePeakLimiter.h"
 
 // ---- members normally provided by EQProcessor.Core.cpp -----------------------------------
 EQProcessor::EQProcessor()
@@ -332,6 +333,9 @@ struct RefOut
 {
     convo::OutputFilter filt;
     convo::UltraHighRateDCBlocker dcL, dcR;
+    SimplePeakLimiter limiter;   // audioengine/SimplePeakLimiter.h, between the scrub and the hard clamp (DSPCoreDouble.cpp:700-710)
+    bool limiterOn = false;
+    double sr = 48000.0;
 };
 void* cpqref_out_create(double sr, double dc_cutoff)
 {
@@ -339,7 +343,15 @@ void* cpqref_out_create(double sr, double dc_cutoff)
     o->filt.prepare(sr);
     o->dcL.init(sr, dc_cutoff);
     o->dcR.init(sr, dc_cutoff);
+    o->sr = sr;
     return o;
+}
+void cpqref_out_set_limiter(void* h, double release_ms)
+{
+    auto* o = static_cast<RefOut*>(h);
+    o->limiterOn = release_ms > 0.0;
+    o->limiter.prepare(o->sr, release_ms);   // the engine: 100 ms (AudioEngine.Processing.DSPCoreLifecycle.cpp:228)
+    o->limiter.reset();
 }
 void cpqref_out_destroy(void* h) { delete static_cast<RefOut*>(h); }
 void cpqref_out_design(double sr, int conv_is_last, int hc, int lc, int lp, double* out15)
@@ -383,9 +395,13 @@ void cpqref_out_process(void* h, double* L, double* R, long total, int block, in
                 {
                     double v = ch[c][i];
                     if (!(std::isfinite(v) && std::fabs(v) < 1.0e300)) v = 0.0;
-                    ch[c][i] = std::min(std::max(v, -kOutputHeadroom), kOutputHeadroom);
+                    ch[c][i] = v;
                 }
         }
+        if (o->limiterOn) o->limiter.processBlock(ch[0], ch[1], n, 0.8413951287507587, 0.108748);   // kPLThreshold, kPLKnee
+        if (clamp)
+            for (int c = 0; c < nch; ++c)
+                for (int i = 0; i < n; ++i) ch[c][i] = std::min(std::max(ch[c][i], -kOutputHeadroom), kOutputHeadroom);
     }
 }
 

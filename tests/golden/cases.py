@@ -50,6 +50,7 @@ CHAIN_CASES = {
 OUTPUT_CASES = {
     "eq_last_natural": dict(sr=48000.0, block=512, T=16384, kw=dict(conv_is_last=False, lp=1, makeup=1.2, dc_cutoff=3.0), amp=3.0, seed=21),
     "conv_last_sharp_96k": dict(sr=96000.0, block=256, T=16384, kw=dict(conv_is_last=True, hc=0, lc=1, makeup=0.8, dc_cutoff=3.0), amp=1.0, seed=22),
+    "peak_limiter": dict(sr=48000.0, block=512, T=16384, kw=dict(conv_is_last=False, lp=1, makeup=1.0, dc_cutoff=3.0, limiter_ms=100.0), amp=8.0, seed=24),
     "conv_last_soft_no_dc": dict(sr=48000.0, block=512, T=8192, kw=dict(conv_is_last=True, hc=2, lc=0, dc_cutoff=0.0, clamp=False), amp=1.0, seed=23),
 }
 FULL_CHAIN_CASES = {

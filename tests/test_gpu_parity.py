@@ -606,11 +606,12 @@ from tests.golden.cases import OUTPUT_CASES as _GOUT, FULL_CHAIN_CASES as _GFULL
 
 
 def _gpu_output(x, sr, block, stages, conv_is_last=False, hc=1, lc=0, lp=1, makeup=1.0, dc_cutoff=3.0, clamp=True, use_filter=True,
-                n_channels=2):
+                n_channels=2, limiter_ms=0.0):
     T = x.shape[1]
     eng = ConvoPeqEngine(x.shape[0] // n_channels, n_channels, sr, block, T)
     eng.set_output_filter(use_filter, conv_is_last, hc, lc, lp)
     eng.set_output_stage(dc_cutoff, clamp)
+    eng.set_peak_limiter(limiter_ms)
     eng.set_epilogue(makeup, 0)
     y = x.copy()
     eng.process(y, stages)
@@ -642,6 +643,29 @@ def test_output_stage_matches_reference_across_tiles(checker, kw, T, block, sr):
         assert np.abs(y[2 * s:2 * s + 2] - want).max() <= TOL
     ym = _gpu_output(x[:1], sr, block, capi.STAGE_OUTPUT_FILTER | capi.STAGE_EPILOGUE, n_channels=1, **kw)
     assert np.abs(ym - checker.output_run(x[:1], sr, block, **kw)).max() <= TOL
+
+
+@pytest.mark.parametrize("kw", [dict(limiter_ms=100.0), dict(limiter_ms=100.0, use_filter=False, dc_cutoff=0.0), dict(limiter_ms=30.0, clamp=False),
+                                dict(limiter_ms=100.0, makeup=0.05)])
+def test_peak_limiter_matches_reference(checker, kw):
+    """SimplePeakLimiter (audioengine/SimplePeakLimiter.h) between the scrub and the hard clamp: three stereo streams of which
+    one stays below the knee for the whole signal (the stage is then exactly the identity and its serial kernel skips the
+    stream), one is loud throughout and one has a loud burst followed by the release tail."""
+    sr, block, T = 48000.0, 512, 8192 * 4 + 512
+    x = np.stack([signals.noise(T, 800 + i) for i in range(6)])
+    x[0:2] *= 0.5                      # quiet
+    x[2:4] *= 6.0                      # loud
+    x[4:6] *= 0.5
+    x[4:6, 9000:9600] *= 14.0          # burst, then release
+    y = _gpu_output(x, sr, block, capi.STAGE_OUTPUT_FILTER | capi.STAGE_EPILOGUE, **kw)
+    for s in range(3):
+        want = checker.output_run(x[2 * s:2 * s + 2], sr, block, **kw)
+        assert np.abs(y[2 * s:2 * s + 2] - want).max() <= TOL, s
+    if kw.get("makeup", 1.0) == 1.0:
+        off = checker.output_run(x[2:4], sr, block, **{**kw, "limiter_ms": 0.0})
+        assert np.abs(y[2:4] - off).max() > 1e-2          # the limiter acted on the loud stream
+    ym = _gpu_output(x[2:3], sr, block, capi.STAGE_OUTPUT_FILTER | capi.STAGE_EPILOGUE, n_channels=1, **kw)
+    assert np.abs(ym - checker.output_run(x[2:3], sr, block, **kw)).max() <= TOL
 
 
 @pytest.mark.parametrize("name", sorted(_GFULL))

@@ -141,6 +141,16 @@ def test_output_stage_restatement_equals_reference(oracle, ref, kw, sr):
     assert np.abs(am - bm).max() <= 1e-11
 
 
+@pytest.mark.parametrize("kw", [dict(limiter_ms=100.0), dict(limiter_ms=100.0, use_filter=False, dc_cutoff=0.0), dict(limiter_ms=30.0, clamp=False)])
+def test_peak_limiter_restatement_equals_reference(oracle, ref, kw):
+    """audioengine/SimplePeakLimiter.h compiled from the reference tree, in processOutputDouble's order (scrub -> limiter -> clamp)."""
+    x = np.stack([signals.noise(24000, 31), signals.noise(24000, 32)]) * 6.0
+    x[:, 8000:12000] *= 0.05
+    a, b = oracle.output_run(x, 48000.0, 480, **kw), ref.output_run(x, 48000.0, 480, **kw)
+    assert np.abs(a - b).max() <= 1e-13
+    assert np.abs(b - ref.output_run(x, 48000.0, 480, **{**kw, "limiter_ms": 0.0})).max() > 0.1
+
+
 def test_ir_frequency_peak_gain_restatement_equals_reference(oracle, ref):
     """IRAnalyzer::estimateMaxFrequencyResponseGain (src/IRAnalyzer.cpp compiled in place) -- the FFT stage of
     IRConverter::computeScaleFactor (SURVEY 8f-2)."""
