@@ -353,7 +353,7 @@ def main():
         dfma = capi.load().cpq_probe_dfma_tflops(local, 20000)
         # FP64 instruction model per channel-sample (FMA = 2 flop): EQ 20 bands x ~14 instr, MAC 4 DFMA x (12+31)
         # taps, FFT ~ 2.5 N log2 N flop per real transform of N = 2P points -> 5 log2(2P) flop per output sample
-        flop_model = {"eq_kernel": 20 * 14.0 * 2, "mac_kernel": 8.0 * (12 + 31), "fft_fwd_kernel": 5.0 * (10 + 13), "fft_inv_kernel": 5.0 * (10 + 13)}
+        flop_model = {"eq_kernel": 20 * 14.0 * 2, "mac_kernel": 6.75 * (12 + 31), "fft_fwd_kernel": 5.0 * (10 + 13), "fft_inv_kernel": 5.0 * (10 + 13)}
         roofline = {"kernel": names[dom], "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launch_ms": dur_ms,
@@ -363,6 +363,7 @@ def main():
                                    "note": "16 B per channel-sample x channel-samples/s of the whole step on one GPU"},
                     "fp64": {"probe_dfma_tflops": dfma,
                              "achieved_tflops": flop_model[names[dom]] * cs_rank / (st[dom] * 1e-3) / 1e12,
+                             "frac": flop_model[names[dom]] * cs_rank / (st[dom] * 1e-3) / 1e12 / dfma if dfma > 0 else None,
                              "note": "FP64 instruction model of the dominant kernel vs the measured DFMA probe; this path is bound by "
                                      "the FP64 pipe and shared-memory issue, not HBM (SURVEY 8d); the HBM fraction uses the compulsory "
                                      "16 B/channel-sample"}}

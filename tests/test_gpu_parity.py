@@ -731,3 +731,52 @@ def test_eq_then_convolver_order(checker, oracle, trim):
         w.append(oracle.outer_wet(c, 1.0))
     want = checker.output_run(np.stack(w), sr, block, conv_is_last=True, makeup=1.2)
     assert np.abs(y - want).max() <= TOL
+
+
+@pytest.mark.parametrize("order", ["conv_eq", "eq_conv"])
+def test_everything_at_once(checker, oracle, order):
+    """All the optional stages of the path in one call, both processing orders, three streams with different settings:
+    Mid/Side + AGC EQ, direct-form head, dry/wet mix with latency compensation, input trim, OutputFilter, DC blocker, peak limiter,
+    clamp -- against the same chain assembled from the reference pieces."""
+    from convopeq_b200.engine import ir_peak_latency
+    sr, block, T, ir_len, n = 48000.0, 512, 8192 * 3, 50000, 3
+    mix, trim, makeup = 0.6, 0.8, 2.5
+    x = np.stack([signals.noise(T, 900 + i, 0.4) for i in range(2 * n)])
+    irs = [np.roll(signals.synth_ir(ir_len, 920 + i), 200) for i in range(2 * n)]
+    bkws = [dict(seed=940, modes=[0, 3, 4, 1, 2] * 4), dict(seed=941), dict(seed=942, modes=[4, 3] * 10)]
+    ekw = [dict(agc=True), dict(structure=1), dict()]
+    cspec, ospec = capi.default_filter_spec(), OFilterSpec()
+    eng = ConvoPeqEngine(n, 2, sr, block, T, conv_boundary=capi.CONV_OUTER, workspace_bytes=40 << 20)
+    eng.set_direct_head(True)
+    for s in range(n):
+        for ch in range(2):
+            eng.set_impulse(s, ch, irs[2 * s + ch], 0.9, cspec)
+        eng.set_eq(s, signals.to_band(signals.band_params(**bkws[s])), 0.2, 0.0, ekw[s].get("structure", 0), ekw[s].get("agc", False))
+    delay = max(ir_peak_latency(irs[2 * s], irs[2 * s + 1]) for s in range(n))     # direct head: algorithm latency 0
+    eng.set_mix(mix, delay)
+    eng.set_conv_input_trim(trim)
+    eng.set_output_filter(True, order == "eq_conv", 1, 0, 1)
+    eng.set_output_stage(3.0, True)
+    eng.set_peak_limiter(100.0)
+    eng.set_epilogue(makeup, 0)
+    y = x.copy()
+    eng.process(y, capi.STAGE_FULL | (capi.ORDER_EQ_THEN_CONV if order == "eq_conv" else 0))
+    eng.close()
+
+    def conv(v, s):
+        out = []
+        for ch in range(2):
+            wet, _ = checker.nuc_run(irs[2 * s + ch], v[ch], block, scale=0.9, spec=ospec, direct_head=True)
+            out.append(oracle.outer_mix(wet, v[ch], mix, delay))
+        return np.stack(out)
+
+    def eq(v, s):
+        l, r, _ = checker.eq_run(signals.to_eqband(signals.band_params(**bkws[s])), v[0], v[1], sr, block, **ekw[s])
+        return np.stack([l, r])
+
+    for s in range(n):
+        v = x[2 * s:2 * s + 2]
+        mid = eq(conv(v, s), s) if order == "conv_eq" else conv(eq(v, s) * trim, s)
+        want = checker.output_run(mid, sr, block, conv_is_last=(order == "eq_conv"), makeup=makeup, limiter_ms=100.0)
+        assert np.abs(y[2 * s:2 * s + 2] - want).max() <= TOL, (order, s)
+        assert np.abs(want).max() > 0.5
