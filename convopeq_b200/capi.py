@@ -71,7 +71,7 @@ EXPORTS = [
     "cpq_set_epilogue", "cpq_set_dither_uniforms", "cpq_set_output_filter", "cpq_set_output_stage", "cpq_set_conv_input_trim", "cpq_output_filter_design", "cpq_design_band", "cpq_db_to_gain", "cpq_equal_power_sin",
     "cpq_process", "cpq_process_device", "cpq_set_partition_range", "cpq_total_partitions", "cpq_get_layout",
     "cpq_latency", "cpq_get_timings", "cpq_get_eq_state", "cpq_cuda_stream", "cpq_kernel_launch_count",
-    "cpq_plan_layout", "cpq_set_eq_mode", "cpq_band_node_active", "cpq_get_agc_state",
+    "cpq_plan_layout", "cpq_plan_layout_ex", "cpq_set_eq_mode", "cpq_band_node_active", "cpq_get_agc_state",
     "cpq_set_mix", "cpq_ir_peak_latency", "cpq_set_direct_head", "cpq_parse_eq_preset",
     "cpq_set_convolver_bypass", "cpq_set_peak_limiter", "cpq_set_partial_sources", "cpq_set_stream_window", "cpq_ir_scale_factor", "cpq_ir_freq_peak_gain", "cpq_ir_min_phase",
 ]
@@ -151,6 +151,8 @@ def load() -> C.CDLL:
     L.cpq_kernel_launch_count.restype = C.c_int64
     L.cpq_plan_layout.argtypes = [C.c_int, C.c_int, C.POINTER(FilterSpec), C.c_int64, C.POINTER(Layout),
                                   C.POINTER(C.c_int64)]
+    L.cpq_plan_layout_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(FilterSpec), C.c_int64, C.POINTER(Layout),
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     L.cpq_probe_dfma_tflops.argtypes = [C.c_int, C.c_int]
     L.cpq_probe_dfma_tflops.restype = C.c_double
     L.cpq_probe_dfma_latency.argtypes = [C.c_int]

@@ -418,9 +418,9 @@ cpq_status Engine::init(const cpq_config* c)
     // Power-of-two host blocks are the reference's regular case (L0 partition == block, zero latency).  Other host blocks run
     // like the application does: SetImpulse gets the block rounded up to a power of two (knownBlockSize) while Add/Get are
     // called with the host block (preferredCallSize), LoaderThread.cpp:230,239-245 -- L0 then goes through its output ring.
-    if (cfg.block_size < 64 || cfg.block_size > 8192 || (cfg.block_size % 32) != 0)
+    if (cfg.block_size < 64 || cfg.block_size > 8192)
     {
-        setError("block_size must be in 64..8192 and a multiple of 32 (a power of two, or e.g. 480 / 960)");
+        setError("block_size must be in 64..8192");
         return CPQ_ERR_UNSUPPORTED;
     }
     if (cfg.max_samples % cfg.block_size != 0)
@@ -1258,9 +1258,9 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
 
 cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar)
 {
-    if (!dIo || T <= 0 || T > cfg.max_samples || T % cfg.block_size != 0 || stride < T || (stride & 1))
+    if (!dIo || T <= 0 || T > cfg.max_samples || T % cfg.block_size != 0 || (T & 1) || stride < T || (stride & 1))
     {
-        setError("process: T must be a positive multiple of block_size <= max_samples; stride even and >= T");
+        setError("process: T must be a positive even multiple of block_size <= max_samples; stride even and >= T");
         return CPQ_ERR_INVALID;
     }
     if ((stages & ~(CPQ_STAGE_FULL | CPQ_ORDER_EQ_THEN_CONV)) || (stages & CPQ_STAGE_FULL) == 0)
@@ -2270,6 +2270,27 @@ cpq_status cpq_plan_layout(int ir_len, int block_size, const cpq_filter_spec* sp
     if (src_offsets)
         for (int li = 1; li < plan.numLayers; ++li)
             std::memcpy(src_offsets + (size_t) (li - 1) * n_callbacks, g.tailSrc[li].data(), (size_t) n_callbacks * sizeof(int64_t));
+    return CPQ_OK;
+}
+
+cpq_status cpq_plan_layout_ex(int ir_len, int known_block_size, int call_size, const cpq_filter_spec* spec, int64_t n_callbacks,
+                              cpq_layout* out, int64_t* src_offsets, int64_t* l0_src, int32_t* l0_count)
+{
+    if (!out || n_callbacks < 0 || call_size <= 0) return CPQ_ERR_INVALID;
+    cpq::ConvPlan plan;
+    if (!cpq::makeConvPlan(ir_len, known_block_size, spec, plan)) return CPQ_ERR_INVALID;
+    plan.callSize = call_size;
+    cpq::GatherPlan g;
+    cpq::simulateCallbacks(plan, n_callbacks, g);
+    fillLayout(plan, &g, out);
+    if (src_offsets)
+        for (int li = 1; li < plan.numLayers; ++li)
+            std::memcpy(src_offsets + (size_t) (li - 1) * n_callbacks, g.tailSrc[li].data(), (size_t) n_callbacks * sizeof(int64_t));
+    for (int64_t c = 0; c < n_callbacks; ++c)
+    {
+        if (l0_src) l0_src[c] = g.l0Identity ? c * (int64_t) call_size : g.l0Src[(size_t) c];
+        if (l0_count) l0_count[c] = g.l0Identity ? call_size : g.l0Count[(size_t) c];
+    }
     return CPQ_OK;
 }
 

@@ -633,8 +633,11 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                 }
                 const int64_t c = cbOf(t);
                 const int off = (int) (t - c * a.blockSize);
-                if (a.l0) v = off < __ldg(a.l0Count + c) ? __ldg(a.l0 + (size_t) seq * a.l0Stride + __ldg(a.l0Src + c) + off) : 0.0;
-                for (int l = 0; l < a.nTail; ++l)
+                // Beyond what the L0 ring delivered the caller zero-fills the WHOLE output of the callback, tails included
+                // (StereoConvolver::process: got = Get(out, n); memset(out + got, 0, n - got), Runtime.cpp:1174-1183)
+                const bool live = !a.l0 || off < __ldg(a.l0Count + c);
+                if (a.l0) v = live ? __ldg(a.l0 + (size_t) seq * a.l0Stride + __ldg(a.l0Src + c) + off) : 0.0;
+                for (int l = 0; l < (live ? a.nTail : 0); ++l)
                 {
                     const int64_t sp = __ldg(a.tailSrc[l] + c);
                     if (sp >= 0)
@@ -683,8 +686,24 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
         const int64_t tb = w0 + (int64_t) lane * kEqL;
         if (a.blockLog2 < 0)
         {
-            // host block not a power of two (a multiple of 32): the lanes of a callback are not an aligned group
-            if (tb < a.T) atomicAdd(dst + (size_t) seq * a.nCallbacks + tb / a.blockSize, sq);
+            // host block not a power of two: the lanes of a callback are not an aligned group, and a thread's block may
+            // straddle two callbacks
+            if (tb >= a.T) return;
+            const int64_t cb0 = tb / a.blockSize;
+            const int split = (int) ((cb0 + 1) * a.blockSize - tb);
+            if (split >= kEqL) atomicAdd(dst + (size_t) seq * a.nCallbacks + cb0, sq);
+            else
+            {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < kEqL; ++j)
+                {
+                    if (j < split) s0 = fma(x[j], x[j], s0);
+                    else s1 = fma(x[j], x[j], s1);
+                }
+                atomicAdd(dst + (size_t) seq * a.nCallbacks + cb0, s0);
+                if (cb0 + 1 < a.nCallbacks) atomicAdd(dst + (size_t) seq * a.nCallbacks + cb0 + 1, s1);
+            }
             return;
         }
         const int lanesPerCb = min(32, (1 << a.blockLog2) / kEqL);
@@ -827,12 +846,18 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                 gainDone = true;
                 if (a.gainTab)
                 {
-                    const int64_t tb = w0 + (int64_t) lane * kEqL;   // a thread's block never straddles a callback (block >= 64)
+                    // a thread's block lies in one callback when the host block is a multiple of the thread block, and in at
+                    // most two otherwise (block >= 64 > kEqL)
+                    const int64_t tb = w0 + (int64_t) lane * kEqL;
                     const int64_t cb0 = cbOf(tb);
-                    const double2 g = __ldg(reinterpret_cast<const double2*>(a.gainTab) + (size_t) gainRow * a.nCallbacks + cb0);
+                    const double2* gt = reinterpret_cast<const double2*>(a.gainTab) + (size_t) gainRow * a.nCallbacks;
+                    const double2 g = __ldg(gt + cb0);
                     const int off0 = (int) (tb - cb0 * a.blockSize);
+                    const int split = a.blockSize - off0;   // samples of this block that belong to callback cb0
+                    const double2 g1 = (split < kEqL && cb0 + 1 < a.nCallbacks) ? __ldg(gt + cb0 + 1) : g;
 #pragma unroll
-                    for (int j = 0; j < kEqL; ++j) x[j] *= fma((double) (off0 + j), g.y, g.x);
+                    for (int j = 0; j < kEqL; ++j)
+                        x[j] *= j < split ? fma((double) (off0 + j), g.y, g.x) : fma((double) (j - split), g1.y, g1.x);
                 }
                 else
                 {

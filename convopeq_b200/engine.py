@@ -289,6 +289,22 @@ def ir_peak_latency(ir_l: np.ndarray, ir_r: Optional[np.ndarray] = None) -> int:
     return int(capi.load().cpq_ir_peak_latency(a.ctypes.data_as(_dp), b.ctypes.data_as(_dp) if b is not None else None, a.size))
 
 
+def plan_layout_ex(ir_len: int, known_block: int, call_size: int, spec: Optional[capi.FilterSpec], n_callbacks: int):
+    """Layer plan + gather plan for SetImpulse(known_block) with Add/Get calls of call_size samples (host-only):
+    (layout, tail sources per tail layer, L0 ring source per callback, L0 ring count per callback)."""
+    lib = capi.load()
+    out = capi.Layout()
+    src = (C.c_int64 * (2 * max(n_callbacks, 1)))()
+    l0s = (C.c_int64 * max(n_callbacks, 1))()
+    l0c = (C.c_int32 * max(n_callbacks, 1))()
+    st = lib.cpq_plan_layout_ex(ir_len, known_block, call_size, C.byref(spec) if spec is not None else None, n_callbacks,
+                                C.byref(out), src, l0s, l0c)
+    if st != capi.OK:
+        raise capi.CpqError(st, "plan_layout_ex")
+    tails = [np.array(src[i * n_callbacks:(i + 1) * n_callbacks], dtype=np.int64) for i in range(max(out.num_layers - 1, 0))]
+    return out, tails, np.array(l0s[:n_callbacks], dtype=np.int64), np.array(l0c[:n_callbacks], dtype=np.int32)
+
+
 def plan_layout(ir_len: int, block_size: int, spec: Optional[capi.FilterSpec], n_callbacks: int):
     """Host-only layer plan + gather plan (no device needed)."""
     lib = capi.load()

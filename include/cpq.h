@@ -88,8 +88,8 @@ typedef struct cpq_config
     int32_t device;        /* CUDA ordinal */
     int32_t n_streams;     /* independent streams in the batch */
     int32_t n_channels;    /* channels per stream: 1 or 2 (the reference engine is <= 2 channels) */
-    int32_t block_size;    /* host callback size the reference would run with: 64..8192, a multiple of 32.  A power of two is
-                              the regular case; otherwise (480, 960 ...) the convolver is prepared with the block rounded up
+    int32_t block_size;    /* host callback size the reference would run with: 64..8192.  A power of two is the regular
+                              case; otherwise (480, 441 ...) the convolver is prepared with the block rounded up
                               to a power of two and called with this block, like the application does
                               (ConvolverProcessor.LoaderThread.cpp:230,239-245) */
     double sample_rate;
@@ -310,6 +310,12 @@ int64_t cpq_kernel_launch_count(cpq_handle h);       /* launches since create */
  * each of n_callbacks callbacks, the delay-line stream position read (or -1 = skipped), layer-major. */
 cpq_status cpq_plan_layout(int ir_len, int block_size, const cpq_filter_spec* spec, int64_t n_callbacks,
                            cpq_layout* out, int64_t* src_offsets);
+
+/* The same for a host whose block is not a power of two: SetImpulse(known_block_size = the block rounded up to a power of
+ * two), Add/Get calls of call_size samples.  l0_src / l0_count (nullable, n_callbacks each): the position in the L0 output
+ * stream and the number of samples the reference's output ring delivers to each callback (the rest of the callback is zero). */
+cpq_status cpq_plan_layout_ex(int ir_len, int known_block_size, int call_size, const cpq_filter_spec* spec, int64_t n_callbacks,
+                              cpq_layout* out, int64_t* src_offsets, int64_t* l0_src, int32_t* l0_count);
 
 #ifdef __cplusplus
 }

@@ -23,11 +23,11 @@ def _known(block):
 @pytest.mark.parametrize("seed", range(40))
 def test_random_configuration(checker, oracle, seed):
     g = np.random.default_rng(1000 + seed)
-    block = int(g.choice([64, 96, 128, 256, 480, 512, 960, 1024]))
+    block = int(g.choice([64, 96, 100, 128, 256, 441, 480, 512, 960, 1000, 1024, 1125]))
     pow2 = (block & (block - 1)) == 0
     sr = float(g.choice([44100.0, 48000.0, 96000.0]))
     ir_len = int(g.choice([37, 3000, 20000, 70000, 140000]))
-    n_cb = int(g.integers(20, 60))
+    n_cb = int(g.integers(10, 30)) * 2          # T must be even, whatever the block
     T = block * n_cb
     n = int(g.integers(1, 4))
     use_spec = bool(g.integers(0, 2))

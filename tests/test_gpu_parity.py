@@ -185,6 +185,7 @@ def test_uniform_partition_extension(oracle):
 
 
 @pytest.mark.parametrize("block,ir_len,T,kw", [(480, 65536, 480 * 80, None), (480, 131072, 480 * 120, {}), (96, 30000, 96 * 300, None),
+                                               (441, 65536, 441 * 100, {}), (1000, 131072, 1000 * 50, None),
                                                (960, 70000, 960 * 60, {}), (1920, 300000, 1920 * 40, None), (480, 300, 480 * 10, None)])
 def test_non_power_of_two_host_block(checker, block, ir_len, T, kw):
     """Hosts whose block is not a power of two (480 = 10 ms at 48 kHz, ...): the application prepares the convolver with the block
@@ -209,10 +210,12 @@ def test_non_power_of_two_host_block(checker, block, ir_len, T, kw):
         assert np.abs(want).max() > 1e-3
 
 
+@pytest.mark.parametrize("block", [480, 441])
 @pytest.mark.parametrize("agc", [False, True])
-def test_non_power_of_two_host_block_full_chain(checker, agc):
-    """480-sample host callbacks through conv -> EQ (gain ramp event / AGC per 480-sample callback) -> epilogue, three streams."""
-    sr, block, T, ir_len, n = 48000.0, 480, 480 * 100, 131072, 3
+def test_non_power_of_two_host_block_full_chain(checker, agc, block):
+    """480- / 441-sample host callbacks through conv -> EQ (AGC per callback: a thread's 32 samples may straddle two callbacks)
+    -> epilogue, three streams."""
+    sr, T, ir_len, n = 48000.0, block * 100, 131072, 3
     eng = ConvoPeqEngine(n, 2, sr, block, T, conv_boundary=capi.CONV_OUTER)
     x = np.stack([signals.noise(T, 400 + i, 0.3) for i in range(2 * n)])
     irs = [signals.synth_ir(ir_len, 420 + i) for i in range(2 * n)]
@@ -531,8 +534,12 @@ def test_error_paths_fail_loudly():
     with pytest.raises(capi.CpqError):
         eng.process(np.zeros((2, 1000)), capi.STAGE_EQ)   # T not a multiple of the block
     with pytest.raises(capi.CpqError) as e:
-        ConvoPeqEngine(1, 2, 44100.0, 441, 4410)         # host blocks must be a multiple of 32
+        ConvoPeqEngine(1, 2, 44100.0, 32, 4096)          # host blocks below 64 (or above 8192) are outside the path
     assert e.value.status == capi.ERR_UNSUPPORTED
+    odd = ConvoPeqEngine(1, 2, 44100.0, 441, 4410)
+    with pytest.raises(capi.CpqError):
+        odd.process(np.zeros((2, 441)), capi.STAGE_EQ)   # an odd number of samples per call
+    odd.close()
     bands = signals.to_band(signals.band_params(1, modes=[3] * 20))
     mono = ConvoPeqEngine(1, 1, 48000.0, 512, 4096)
     with pytest.raises(capi.CpqError) as e:

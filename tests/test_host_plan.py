@@ -103,6 +103,36 @@ def test_offline_formulation_equals_state_machine(oracle, ir_len, block, T):
     assert np.abs(got - want).max() < 1e-12
 
 
+@pytest.mark.parametrize("known,call,ir_len,n_cb", [(128, 100, 20000, 200), (128, 96, 20000, 200), (512, 441, 140000, 44), (512, 480, 70000, 100),
+                                                    (1024, 1000, 140000, 20), (2048, 1125, 70000, 20)])
+def test_offline_formulation_for_non_power_of_two_hosts(oracle, known, call, ir_len, n_cb):
+    """SetImpulse(known block) with Add/Get calls of the host block: the L0 output ring's per-callback source / count and the tail
+    gather reproduce the Add/Get loop -- including the caller's zero-fill of everything beyond what the ring delivered
+    (StereoConvolver::process, Runtime.cpp:1174-1183), which blanks the tails too in a short callback."""
+    from scipy.signal import fftconvolve
+    from convopeq_b200.engine import plan_layout_ex
+    T = call * n_cb
+    ir, x = signals.synth_ir(ir_len, 3), signals.noise(T, 4)
+    want, _ = oracle.nuc_run(ir, x, known, call=call)
+    lay, tails, l0s, l0c = plan_layout_ex(ir_len, known, call, None, n_cb)
+    y = np.zeros(T)
+    for li in range(lay.num_layers):
+        l = lay.layers[li]
+        full = fftconvolve(x, ir[l.ir_offset:l.ir_offset + l.ir_len])
+        K = T // l.part_size
+        yl = np.zeros(T + l.part_size)
+        yl[:K * l.part_size] = full[:K * l.part_size]
+        for c in range(n_cb):
+            n = l0c[c]
+            if li == 0:
+                y[c * call:c * call + n] += yl[l0s[c]:l0s[c] + n]
+            elif tails[li - 1][c] >= 0:
+                s0 = tails[li - 1][c]
+                y[c * call:c * call + n] += l.gain * yl[s0:s0 + n]
+    assert np.abs(y - want).max() < 1e-12
+    assert (l0c < call).sum() > 1 or call in (96, 480, 1000)     # most of these hosts see recurring short callbacks
+
+
 def test_irregular_plan_reports_skips():
     lay, tails = plan_layout(65536, 1024, None, 400)
     assert lay.layers[1].skipped_callbacks > 0          # B=1024 default plan drops tail samples (SURVEY §7)
