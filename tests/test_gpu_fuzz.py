@@ -87,3 +87,55 @@ def test_random_configuration(checker, oracle, seed):
         err = np.abs(y[2 * s:2 * s + 2] - want).max()
         assert err <= TOL * max(1.0, np.abs(mid).max()), (seed, s, err, dict(block=block, sr=sr, ir_len=ir_len, spec=kw, direct=direct, eq_first=order_eq_first,
                                                                           mix=mix, eq=ekws[s], modes=bkws[s]["modes"]))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_configuration_mono_shared_and_gain_events(checker, oracle, seed):
+    """Second family: mono or stereo handles, IR / EQ shared by all streams, a total-gain change at a random callback (50 ms ramp),
+    conv -> EQ -> makeup + headroom only (no output stages), inner or outer convolver boundary."""
+    g = np.random.default_rng(3000 + seed)
+    block = int(g.choice([64, 128, 441, 480, 512, 2048]))
+    sr = float(g.choice([48000.0, 96000.0]))
+    ir_len = int(g.choice([500, 9000, 66000]))
+    T = block * int(g.integers(10, 24)) * 2
+    nch = int(g.choice([1, 2]))
+    n = int(g.integers(1, 4))
+    shared_ir, shared_eq = bool(g.integers(0, 2)), bool(g.integers(0, 2))
+    outer = bool(g.integers(0, 2))
+    gain_db = float(g.choice([0.0, -4.5]))
+    change_at = int(g.integers(1, T // block - 1))
+    change_db = float(g.choice([-9.0, 3.0]))
+    sat = float(g.choice([0.2, 0.0]))
+    makeup = float(g.choice([1.0, 0.7]))
+    eng = ConvoPeqEngine(n, nch, sr, block, T, conv_boundary=capi.CONV_OUTER if outer else capi.CONV_INNER, shared_ir=shared_ir,
+                         shared_eq=shared_eq, workspace_bytes=int(g.choice([0, 20 << 20])))
+    x = np.stack([signals.noise(T, 8000 + 10 * seed + i, 0.3) for i in range(nch * n)])
+    n_ir = nch if shared_ir else nch * n
+    irs = [signals.synth_ir(ir_len, 8500 + 10 * seed + i) for i in range(n_ir)]
+    n_eq = 1 if shared_eq else n
+    bkws = [dict(seed=9000 + 10 * seed + s, modes=[int(v) for v in g.integers(0, 3, 20)]) for s in range(n_eq)]
+    for s in range(1 if shared_ir else n):
+        for ch in range(nch):
+            eng.set_impulse(-1 if shared_ir else s, ch, irs[nch * s + ch], 1.0, None)
+    for s in range(n_eq):
+        eng.set_eq(-1 if shared_eq else s, signals.to_band(signals.band_params(**bkws[s])), sat, gain_db)
+        eng.schedule_total_gain(-1 if shared_eq else s, change_at, change_db)
+    eng.set_epilogue(makeup, 0)
+    y = x.copy()
+    eng.process(y, capi.STAGE_ALL)
+    eng.close()
+    known = _known(block)
+    for s in range(n):
+        chans = []
+        for ch in range(nch):
+            ir = irs[ch] if shared_ir else irs[nch * s + ch]
+            wet, _ = checker.nuc_run(ir, x[nch * s + ch], known, call=block)
+            chans.append(oracle.outer_wet(wet, 1.0) if outer else wet)
+        bk = bkws[0] if shared_eq else bkws[s]
+        l, r, _ = checker.eq_run(signals.to_eqband(signals.band_params(**bk)), chans[0], chans[1] if nch > 1 else None, sr, block,
+                                 saturation=sat, total_gain_db=gain_db, gain_change_db=change_db, gain_change_at=change_at * block)
+        outs = [l] if nch == 1 else [l, r]
+        for ch in range(nch):
+            want, _, _ = oracle.epilogue(outs[ch], makeup, sr, 0)
+            err = np.abs(y[nch * s + ch] - want).max()
+            assert err <= TOL, (seed, s, ch, err, dict(block=block, nch=nch, n=n, shared_ir=shared_ir, shared_eq=shared_eq, outer=outer))
