@@ -17,6 +17,7 @@ MAX_LAYERS = 3
 OK, ERR_INVALID, ERR_NOT_READY, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_GEOMETRY = range(7)
 STAGE_CONV, STAGE_EQ, STAGE_EPILOGUE, STAGE_ALL = 1, 2, 4, 7
 STAGE_OUTPUT_FILTER, STAGE_FULL = 8, 15
+STAGE_INPUT = 32
 ORDER_EQ_THEN_CONV = 16
 CONV_INNER, CONV_OUTER = 0, 1
 
@@ -73,7 +74,7 @@ EXPORTS = [
     "cpq_latency", "cpq_get_timings", "cpq_get_eq_state", "cpq_cuda_stream", "cpq_kernel_launch_count",
     "cpq_plan_layout", "cpq_plan_layout_ex", "cpq_set_eq_mode", "cpq_band_node_active", "cpq_get_agc_state",
     "cpq_set_mix", "cpq_ir_peak_latency", "cpq_set_direct_head", "cpq_parse_eq_preset",
-    "cpq_set_convolver_bypass", "cpq_set_peak_limiter", "cpq_set_partial_sources", "cpq_set_stream_window", "cpq_ir_scale_factor", "cpq_ir_freq_peak_gain", "cpq_ir_min_phase",
+    "cpq_set_convolver_bypass", "cpq_set_peak_limiter", "cpq_set_input_gain", "cpq_set_partial_sources", "cpq_set_stream_window", "cpq_ir_scale_factor", "cpq_ir_freq_peak_gain", "cpq_ir_min_phase",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -122,6 +123,7 @@ def load() -> C.CDLL:
     L.cpq_set_direct_head.argtypes = [vp, C.c_int]
     L.cpq_set_convolver_bypass.argtypes = [vp, C.c_int]
     L.cpq_set_peak_limiter.argtypes = [vp, C.c_double]
+    L.cpq_set_input_gain.argtypes = [vp, C.c_double]
     L.cpq_set_partial_sources.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.cpq_set_stream_window.argtypes = [vp, C.c_int, C.c_int]
     L.cpq_ir_scale_factor.argtypes = [dp, dp, C.c_int, dp, dp, C.c_int, C.c_double, C.POINTER(IrScale)]

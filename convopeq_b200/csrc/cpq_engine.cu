@@ -187,6 +187,7 @@ struct Engine
     const double* peers[CPQ_MAX_PEERS] {};
     int convBypassed = 0;               // runtimeSnapshot.bypassed: processBypassWithLatencyCompensation (Runtime.cpp:123-186)
     DevBuf<double> dryBuf;              // copy of the convolver input for the dry path (mix < 0.999) / the direct-form head
+    double inputGain = 1.0;             // DSPCore::processInput's headroom gain (CPQ_STAGE_INPUT)
     double limiterMs = 0.0;             // SimplePeakLimiter release (ms); 0 = stage off.  The reference engine uses 100 ms
     DevBuf<unsigned> limFlag;           // [n_streams]
     DevBuf<double> limEnv;              // [n_streams] envelope after the last call
@@ -1263,7 +1264,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         setError("process: T must be a positive even multiple of block_size <= max_samples; stride even and >= T");
         return CPQ_ERR_INVALID;
     }
-    if ((stages & ~(CPQ_STAGE_FULL | CPQ_ORDER_EQ_THEN_CONV)) || (stages & CPQ_STAGE_FULL) == 0)
+    if ((stages & ~(CPQ_STAGE_FULL | CPQ_ORDER_EQ_THEN_CONV | CPQ_STAGE_INPUT)) || (stages & (CPQ_STAGE_FULL | CPQ_STAGE_INPUT)) == 0)
     {
         setError("process: bad stage mask");
         return CPQ_ERR_INVALID;
@@ -1488,6 +1489,20 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         cudaEvent_t* ce = &evPool[c * 6];
         if (hostPlanar) cudaStreamWaitEvent(stream, evPool[c * 6 + 5], 0);
         cudaEventRecord(ce[0], stream);
+        if (stages & CPQ_STAGE_INPUT)
+        {
+            InputArgs ia {};
+            ia.io = ioC;
+            ia.stride = stride;
+            ia.T = T;
+            ia.gain = inputGain;
+            ia.applyGain = std::fabs(inputGain - 1.0) > 1e-9 ? 1 : 0;
+            ia.block = B;
+            ia.vecEnd = B / 4 * 4;
+            input_kernel<<<dim3((unsigned) std::min<int64_t>(256, (T + 255) / 256), (unsigned) ns), 256, 0, stream>>>(ia);
+            ++launches;
+            CPQ_CUDA(cudaGetLastError());
+        }
         if (eqFirst)
         {
             EqArgs p {};
@@ -1703,8 +1718,11 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             e.nTail = 0;
             e.outer = 0;
         }
-        cpq_status st = runEq(e, s0, ns);
-        if (st != CPQ_OK) return st;
+        if (doConv || doEq || doEpi || postMask || deferredOuter || e.nPeers > 0)   // an input-stage-only call has nothing left to do
+        {
+            cpq_status st = runEq(e, s0, ns);
+            if (st != CPQ_OK) return st;
+        }
         if (doDither)
         {
             DitherArgs d {};
@@ -2063,6 +2081,13 @@ cpq_status cpq_set_stream_window(cpq_handle h, int first_stream, int n_streams)
     if (n_streams > 0 && first_stream + n_streams > h->cfg.n_streams) return CPQ_ERR_INVALID;
     h->winFirst = first_stream;
     h->winCount = n_streams;
+    return CPQ_OK;
+}
+
+cpq_status cpq_set_input_gain(cpq_handle h, double gain)
+{
+    if (!h || !std::isfinite(gain)) return CPQ_ERR_INVALID;
+    h->inputGain = gain;
     return CPQ_OK;
 }
 

@@ -1273,6 +1273,33 @@ __global__ void limiter_kernel(LimiterArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// The engine's input stage (convo::input_transform::applyHighQuality64BitTransform, InputBitDepthTransform.h:86-100, from
+// DSPCore::processInput): optional gain, NaN or |v| < 1e-20 -> 0, clamp to [-1, 1] (+-Inf survives the scrub of the
+// reference's four-wide body and clamps to +-1; only its scalar remainder, n % 4 samples per callback, zeroes it).
+// ---------------------------------------------------------------------------------------------
+struct InputArgs
+{
+    double* io;
+    int64_t stride, T;
+    double gain;
+    int applyGain;
+    int block, vecEnd;   // samples per callback and block / 4 * 4: offsets >= vecEnd take the scalar remainder's rule
+};
+
+__global__ void input_kernel(InputArgs a)
+{
+    double* io = a.io + (size_t) blockIdx.y * a.stride;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < a.T; i += (int64_t) gridDim.x * blockDim.x)
+    {
+        double v = io[i];
+        if (a.applyGain) v *= a.gain;
+        const bool tailSample = (int) (i % a.block) >= a.vecEnd;
+        if (v != v || fabs(v) < 1.0e-20 || (tailSample && isinf(v))) v = 0.0;
+        io[i] = fmin(fmax(v, -1.0), 1.0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Dry path of ConvolverProcessor::process in its settled state (ConvolverProcessor.Runtime.cpp:551-568, 573-584, 675-677,
 // 748): io already holds scrub(wet) * wetGain (eq_kernel's load stage); add the input delayed by the latency-compensation
 // delay times equalPowerSin(1 - mix), or -- dry-only fast path, mix <= 0.001 -- replace io by the delayed input.

@@ -174,6 +174,10 @@ class ConvoPeqEngine:
         """ConvolverProcessor's dry/wet mix (float mixTarget) and the latency-compensation delay of its dry path."""
         self._check(self.lib.cpq_set_mix(self.h, C.c_float(mix), int(dry_delay_samples)))
 
+    def set_input_gain(self, gain: float = 1.0):
+        """Gain of the engine's input stage (STAGE_INPUT: gain, NaN / denormal scrub, clamp to [-1, 1])."""
+        self._check(self.lib.cpq_set_input_gain(self.h, gain))
+
     def set_peak_limiter(self, release_ms: float = 100.0):
         """SimplePeakLimiter between the scrub and the hard clamp (the reference engine prepares it with 100 ms); 0 = off."""
         self._check(self.lib.cpq_set_peak_limiter(self.h, release_ms))

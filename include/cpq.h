@@ -80,7 +80,11 @@ enum
     CPQ_STAGE_FULL = 15u,
     /* ProcessingOrder::EQThenConvolver (:415-451) instead of ConvolverThenEQ: EQ -> convolverInputTrimGain -> convolver
      * -> (output filter with conv_is_last) -> epilogue.  Only meaningful together with CPQ_STAGE_CONV | CPQ_STAGE_EQ. */
-    CPQ_ORDER_EQ_THEN_CONV = 16u
+    CPQ_ORDER_EQ_THEN_CONV = 16u,
+    /* DSPCore::processInput's transform of the input block before everything else (convo::input_transform::
+     * applyHighQuality64BitTransform, InputBitDepthTransform.h:86-100; AudioEngine.Processing.DSPCoreIO.cpp:203-232): input gain
+     * (cpq_set_input_gain, the reference passes 1.0), NaN and |v| < 1e-20 -> 0, clamp to [-1, 1].  Not part of CPQ_STAGE_FULL. */
+    CPQ_STAGE_INPUT = 32u
 };
 
 typedef struct cpq_config
@@ -203,6 +207,8 @@ cpq_status cpq_set_output_filter(cpq_handle h, int enabled, int conv_is_last, in
  * +-kOutputHeadroom clamp (DSPCoreDouble.cpp:665-691, 712-737).  SimplePeakLimiter (:700-710) sits between the two: see
  * cpq_set_peak_limiter. */
 cpq_status cpq_set_output_stage(cpq_handle h, double dc_cutoff_hz, int hard_clamp);
+/* Gain of the input stage (CPQ_STAGE_INPUT); applied when it differs from 1 by more than 1e-9, like the reference. */
+cpq_status cpq_set_input_gain(cpq_handle h, double gain);
 /* SimplePeakLimiter::prepare(sr, release_ms) + processBlock with the engine's constants (audioengine/SimplePeakLimiter.h,
  * DSPCoreDouble.cpp:700-710, threshold kOutputHeadroom - 0.5 dB, knee 1 dB; the engine prepares it with 100 ms,
  * AudioEngine.Processing.DSPCoreLifecycle.cpp:228), between the scrub and the hard clamp inside CPQ_STAGE_EPILOGUE; one

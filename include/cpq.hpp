@@ -150,6 +150,8 @@ public:
     /// scrub + +-kOutputHeadroom hard clamp, both inside CPQ_STAGE_EPILOGUE.
     /// convolverInputTrimGain (EQThenConvolver order: pass CPQ_ORDER_EQ_THEN_CONV in `stages`).
     bool setConvolverInputTrim(double gain) { return ok(cpq_set_conv_input_trim(h_, gain)); }
+    /// Gain of DSPCore::processInput's input transform (CPQ_STAGE_INPUT).
+    bool setInputGain(double gain) { return ok(cpq_set_input_gain(h_, gain)); }
     /// SimplePeakLimiter (release 100 ms in the reference engine) between the scrub and the hard clamp; 0 = off.
     bool setPeakLimiter(double releaseMs) { return ok(cpq_set_peak_limiter(h_, releaseMs)); }
     /// ConvolverProcessor::setBypass: the convolver stage only delays by the dry path's latency compensation.

@@ -183,6 +183,16 @@ class _Base:
             self._f("out_destroy")(h)
         return y
 
+    # ---- input stage -------------------------------------------------------------------------
+    def input_transform(self, x: np.ndarray, gain: float = 1.0) -> np.ndarray:
+        """convertDoubleToDoubleHighQuality: gain, NaN / denormal scrub, clamp to [-1, 1]."""
+        d = np.ascontiguousarray(x, dtype=np.float64).copy()
+        f = self._f("input_transform")
+        f.argtypes = [_dp, C.c_long if self.prefix == "cpqo_" else C.c_int, C.c_double]
+        f.restype = None
+        f(_p(d), d.size, gain)
+        return d
+
     # ---- IR preparation ----------------------------------------------------------------------
     def ir_freq_peak_gain(self, ir_l: np.ndarray, ir_r: Optional[np.ndarray] = None) -> float:
         """IRAnalyzer::estimateMaxFrequencyResponseGain."""

@@ -828,6 +828,27 @@ void cpqo_outer_wet(double* data, long n, double mix)
     }
 }
 
+/* The engine's input stage (convo::input_transform::applyHighQuality64BitTransform, InputBitDepthTransform.h:86-100, called
+ * from DSPCore::processInput, AudioEngine.Processing.DSPCoreIO.cpp:203-232): optional gain, then sanitizeAndLimit (:32-68):
+ * NaN or |v| < 1e-20 -> 0, clamp to [-1, 1].  The vector body (four samples at a time) keeps +-Inf and clamps it to +-1,
+ * the scalar remainder (n % 4 samples) zeroes it; both are restated. */
+void cpqo_input_transform(double* data, long n, double gain)
+{
+    const double gd = gain - 1.0;
+    if (gd > 1e-9 || gd < -1e-9)
+        for (long i = 0; i < n; ++i) data[i] *= gain;
+    const long vend = n / 4 * 4;
+    for (long i = 0; i < n; ++i)
+    {
+        double v = data[i];
+        if (i < vend) { if (v != v || fabs(v) < 1.0e-20) v = 0.0; }
+        else if (!(isfinite(v) && !(fabs(v) < 1.0e-20))) v = 0.0;
+        v = v > -1.0 ? v : -1.0;   /* _mm256_max_pd(v, vMin) then min: applied after the zeroing, so NaN never reaches it */
+        v = v < 1.0 ? v : 1.0;
+        data[i] = v;
+    }
+}
+
 /* ConvolverProcessor::process in its settled state (mix and latency smoothers at their targets, no bypass):
  * ConvolverProcessor.Runtime.cpp:367-377 (needsConvolution = mix > 0.001, needsDrySignal = mix < 0.999), :551-568 (dry =
  * input delayed by round(totalLatency) through a zero-initialised ring), :573-584 (dry-only fast path copies the dry signal,

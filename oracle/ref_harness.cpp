@@ -41,6 +41,7 @@
 #include "UltraHighRateDCBlocker.h"
 #include "IRAnalyzer.h"
 #include "SimplePeakLimiter.h"
+#include "InputBitDepthTransform.h"
 
 // ---- members normally provided by EQProcessor.Core.cpp -----------------------------------
 EQProcessor::EQProcessor()
@@ -412,6 +413,13 @@ double cpqref_ir_freq_peak_gain(const double* l, const double* r, int n)
     double* ch[2] = { const_cast<double*>(l), const_cast<double*>(r) };
     juce::AudioBuffer<double> buf(ch, r ? 2 : 1, n);
     return IRAnalyzer::estimateMaxFrequencyResponseGain(buf);
+}
+
+// convo::input_transform::convertDoubleToDoubleHighQuality (src/InputBitDepthTransform.h:123-133): the engine's input stage
+// (DSPCore::processInput, AudioEngine.Processing.DSPCoreIO.cpp:203-232) on a double buffer, in place.
+void cpqref_input_transform(double* data, int n, double gain)
+{
+    convo::input_transform::convertDoubleToDoubleHighQuality(data, data, n, gain);
 }
 
 int cpqref_abi_version(void) { return 3; }

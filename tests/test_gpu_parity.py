@@ -787,3 +787,28 @@ def test_everything_at_once(checker, oracle, order):
         want = checker.output_run(mid, sr, block, conv_is_last=(order == "eq_conv"), makeup=makeup, limiter_ms=100.0)
         assert np.abs(y[2 * s:2 * s + 2] - want).max() <= TOL, (order, s)
         assert np.abs(want).max() > 0.5
+
+
+@pytest.mark.parametrize("block,gain", [(512, 1.0), (441, 0.5), (64, 1.0 + 1e-10)])
+def test_input_stage_matches_reference(checker, block, gain):
+    """DSPCore::processInput's transform (InputBitDepthTransform.h compiled from the reference tree): gain, NaN / denormal scrub,
+    clamp to [-1, 1]; +-Inf clamps in the four-wide body and is zeroed in the scalar remainder of a callback."""
+    T = block * 20
+    x = np.stack([signals.noise(T, 70 + i, 0.6) for i in range(4)])
+    x[0, 3], x[0, 10], x[1, 11], x[2, 20], x[3, 21], x[1, 30] = np.nan, np.inf, -np.inf, 1e-25, -3e-21, 2.5
+    x[2, block - 1], x[3, 2 * block - 1] = np.inf, np.nan          # last sample of a callback: scalar remainder when block % 4 != 0
+    eng = ConvoPeqEngine(2, 2, 48000.0, block, T)
+    eng.set_input_gain(gain)
+    y = x.copy()
+    eng.process(y, capi.STAGE_INPUT)
+    # followed by the EQ in one call
+    eng.set_eq(0, signals.to_band(signals.band_params(75)))
+    eng.set_eq(1, signals.to_band(signals.band_params(76)))
+    z = x.copy()
+    eng.process(z, capi.STAGE_INPUT | capi.STAGE_EQ)
+    eng.close()
+    want = np.stack([np.concatenate([checker.input_transform(row[c * block:(c + 1) * block], gain) for c in range(20)]) for row in x])
+    assert np.array_equal(y, want)
+    for s in range(2):
+        l, r, _ = checker.eq_run(signals.to_eqband(signals.band_params(75 + s)), want[2 * s], want[2 * s + 1], 48000.0, block)
+        assert np.abs(z[2 * s] - l).max() <= TOL and np.abs(z[2 * s + 1] - r).max() <= TOL

@@ -160,3 +160,11 @@ def test_ir_frequency_peak_gain_restatement_equals_reference(oracle, ref):
                  (signals.synth_ir(100000, 4), signals.synth_ir(100000, 5)), (signals.synth_ir(3, 6), None), (ring, None)]:
         x, y = oracle.ir_freq_peak_gain(a, b), ref.ir_freq_peak_gain(a, b)
         assert abs(x - y) <= 1e-12 * y
+
+
+def test_input_transform_restatement_equals_reference(oracle, ref):
+    """convo::input_transform::convertDoubleToDoubleHighQuality (src/InputBitDepthTransform.h compiled in place)."""
+    x = np.random.default_rng(1).standard_normal(1027) * 0.8
+    x[3], x[10], x[11], x[20], x[21], x[30], x[1025], x[1026] = np.nan, np.inf, -np.inf, 1e-25, -3e-21, 2.5, np.inf, np.nan
+    for g in (1.0, 0.5, 1.0 + 1e-10, 3.0):
+        assert np.array_equal(oracle.input_transform(x, g), ref.input_transform(x, g))
