@@ -9,6 +9,10 @@
  * units compiled in place (oracle/Makefile) and tests/test_oracle_vs_ref.py checks this file against
  * it whenever it is present; tests/golden/ holds outputs of that library (generator:
  * tests/golden/make_golden.py) which tests/test_oracle_golden.py checks everywhere else.
+ * PARITY UNPINNED for three pieces whose reference files need the whole JUCE application to compile and therefore cannot be
+ * run here: cpqo_outer_mix (ConvolverProcessor::process' dry/wet mix), cpqo_ir_peak_latency / the arithmetic of
+ * cpqo_ir_scale_factor around its pinned FFT stage (LoaderThread / IRConverter), and the uniform-partition extension flag
+ * (not a reference mode at all).  Each says so at its definition; they restate the cited source lines only.
  *
  * Written from the reference's behaviour, one callback at a time, deliberately in the reference's
  * own real-time formulation (ring buffers, FDL, time-sliced tail MAC) so that it is an independent
