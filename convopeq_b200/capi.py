@@ -70,7 +70,7 @@ EXPORTS = [
     "cpq_abi_version", "cpq_status_string", "cpq_last_error", "cpq_filter_spec_default", "cpq_config_default",
     "cpq_create", "cpq_destroy", "cpq_reset", "cpq_set_impulse", "cpq_set_eq", "cpq_schedule_total_gain",
     "cpq_set_epilogue", "cpq_set_dither_uniforms", "cpq_set_output_filter", "cpq_set_output_stage", "cpq_set_conv_input_trim", "cpq_output_filter_design", "cpq_design_band", "cpq_db_to_gain", "cpq_equal_power_sin",
-    "cpq_process", "cpq_process_device", "cpq_set_partition_range", "cpq_total_partitions", "cpq_get_layout",
+    "cpq_process", "cpq_process_f32", "cpq_process_device", "cpq_set_partition_range", "cpq_total_partitions", "cpq_get_layout",
     "cpq_latency", "cpq_get_timings", "cpq_get_eq_state", "cpq_cuda_stream", "cpq_kernel_launch_count",
     "cpq_plan_layout", "cpq_plan_layout_ex", "cpq_set_eq_mode", "cpq_band_node_active", "cpq_get_agc_state",
     "cpq_set_mix", "cpq_ir_peak_latency", "cpq_set_direct_head", "cpq_parse_eq_preset",
@@ -140,6 +140,7 @@ def load() -> C.CDLL:
     L.cpq_equal_power_sin.argtypes = [C.c_double]
     L.cpq_equal_power_sin.restype = C.c_double
     L.cpq_process.argtypes = [vp, C.POINTER(dp), C.c_int64, C.c_uint]
+    L.cpq_process_f32.argtypes = [vp, C.POINTER(C.POINTER(C.c_float)), C.c_int64, C.c_uint]
     L.cpq_process_device.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_uint]
     L.cpq_set_partition_range.argtypes = [vp, C.c_int, C.c_int]
     L.cpq_total_partitions.argtypes = [vp]

@@ -197,7 +197,8 @@ struct Engine
     unsigned postIdentity = 0;          // output-filter stages whose coefficients are the identity (skipped)
     DevBuf<double> postc, postState;
     cpq_status ensureGather(int64_t nCallbacks);
-    cpq_status processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar);
+    cpq_status processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF = nullptr);
+    DevBuf<float> f32In, f32Out;        // device staging of float host buffers: 3 inbound / 2 outbound chunk slots
     cpq_status processDevice(double* dIo, int64_t stride, int64_t T, unsigned stages) { return processCore(dIo, stride, T, stages, nullptr); }
     cpq_status launchFwd(int log2P, const FwdArgs& a);
     cpq_status launchFwdLarge(int log2P, const FwdArgs& a);
@@ -1257,8 +1258,9 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
     return launchEq(f);
 }
 
-cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar)
+cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF)
 {
+    const bool hostIO = hostPlanar || hostF;
     if (!dIo || T <= 0 || T > cfg.max_samples || T % cfg.block_size != 0 || (T & 1) || stride < T || (stride & 1))
     {
         setError("process: T must be a positive even multiple of block_size <= max_samples; stride even and >= T");
@@ -1374,7 +1376,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         }
         chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) nSeq, cfg.workspace_bytes / std::max<size_t>(perSeq, 1)));
     }
-    if (hostPlanar) chunk = std::max(1, std::min(chunk, (nSeq + 31) / 32));   // short pipeline fill/drain
+    if (hostIO) chunk = std::max(1, std::min(chunk, (nSeq + 31) / 32));   // short pipeline fill/drain
     if (limiterOn) chunk = std::max(cfg.n_channels, chunk / cfg.n_channels * cfg.n_channels);   // whole streams per chunk
     if (doEq && (anyAgc || anyMs))
     {
@@ -1400,7 +1402,14 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         }
     const size_t nChunks = (size_t) ((nSeq + chunk - 1) / chunk);
     // event pool layout: [c*6 + 0..4] stage boundaries on the compute stream, [c*6 + 5] H2D done on the copy-in stream
-    for (size_t i = 0; i < nChunks * 6 + 4; ++i) poolEvent(i);
+    for (size_t i = 0; i < nChunks * 9 + 4; ++i) poolEvent(i);
+    // float host buffers: per chunk [0] inbound conversion done, [1] outbound conversion done (compute stream), [2] D2H done
+    const size_t fBase = nChunks * 6 + 4;
+    if (hostF)
+    {
+        CPQ_CUDA(f32In.ensure((size_t) 3 * chunk * T));
+        CPQ_CUDA(f32Out.ensure((size_t) 2 * chunk * T));
+    }
     cudaEvent_t evInBegin = evPool[nChunks * 6 + 0], evInEnd = evPool[nChunks * 6 + 1];
     cudaEvent_t evOutBegin = evPool[nChunks * 6 + 2], evOutEnd = evPool[nChunks * 6 + 3];
 
@@ -1409,6 +1418,14 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
     // otherwise row by row.  H2D runs at most two chunks ahead of compute so the driver's launch queue never
     // fills with copies (a full queue would stall the host before the first D2H is enqueued).
     ptrdiff_t hostPitch = 0;
+    ptrdiff_t pitchF = 0;
+    if (hostF && nSeqAll > 1)
+    {
+        pitchF = hostF[1] - hostF[0];
+        for (int s = 2; s < nSeqAll && pitchF > 0; ++s)
+            if (hostF[s] - hostF[s - 1] != pitchF) pitchF = 0;
+        if (pitchF < T) pitchF = 0;
+    }
     if (hostPlanar && nSeqAll > 1)
     {
         hostPitch = hostPlanar[1] - hostPlanar[0];
@@ -1419,7 +1436,19 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
     auto enqueueH2D = [&](size_t c) -> cudaError_t {
         const int s0 = seqLo + (int) c * chunk, ns = std::min(chunk, seqLo + nSeq - s0);
         cudaError_t e = cudaSuccess;
-        if (hostPitch == T && stride == T)   // both sides dense: one linear copy
+        if (hostF)
+        {
+            // into staging slot c % 3, free once chunk c - 3 has been converted
+            if (c >= 3) cudaStreamWaitEvent(sIn, evPool[fBase + (c - 3) * 3], 0);
+            float* slot = f32In.p + (c % 3) * (size_t) chunk * T;
+            if (pitchF > 0)
+                e = cudaMemcpy2DAsync(slot, (size_t) T * sizeof(float), hostF[s0], (size_t) pitchF * sizeof(float), (size_t) T * sizeof(float),
+                                      (size_t) ns, cudaMemcpyHostToDevice, sIn);
+            else
+                for (int s = s0; s < s0 + ns && e == cudaSuccess; ++s)
+                    e = cudaMemcpyAsync(slot + (size_t) (s - s0) * T, hostF[s], (size_t) T * sizeof(float), cudaMemcpyHostToDevice, sIn);
+        }
+        else if (hostPitch == T && stride == T)   // both sides dense: one linear copy
             e = cudaMemcpyAsync(dIo + (size_t) s0 * stride, hostPlanar[s0], (size_t) ns * T * sizeof(double), cudaMemcpyHostToDevice, sIn);
         else if (hostPitch > 0)
             e = cudaMemcpy2DAsync(dIo + (size_t) s0 * stride, (size_t) stride * sizeof(double), hostPlanar[s0], (size_t) hostPitch * sizeof(double),
@@ -1432,7 +1461,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         return e;
     };
     constexpr size_t kH2DAhead = 2;
-    if (hostPlanar)
+    if (hostIO)
     {
         cudaStreamWaitEvent(sIn, ev[0], 0);
         cudaEventRecord(evInBegin, sIn);
@@ -1487,7 +1516,14 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         const int s0 = seqLo + (int) c * chunk, ns = std::min(chunk, seqLo + nSeq - s0);
         double* ioC = dIo + (size_t) s0 * stride;
         cudaEvent_t* ce = &evPool[c * 6];
-        if (hostPlanar) cudaStreamWaitEvent(stream, evPool[c * 6 + 5], 0);
+        if (hostIO) cudaStreamWaitEvent(stream, evPool[c * 6 + 5], 0);
+        const dim3 cvGrid((unsigned) std::min<int64_t>(128, (T / 2 + 255) / 256), (unsigned) ns);
+        if (hostF)
+        {
+            convert_kernel<true><<<cvGrid, 256, 0, stream>>>(f32In.p + (c % 3) * (size_t) chunk * T, ioC, stride, T);
+            ++launches;
+            cudaEventRecord(evPool[fBase + c * 3], stream);
+        }
         cudaEventRecord(ce[0], stream);
         if (stages & CPQ_STAGE_INPUT)
         {
@@ -1757,7 +1793,27 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             CPQ_CUDA(cudaGetLastError());
         }
         cudaEventRecord(ce[4], stream);
-        if (hostPlanar)
+        if (hostF)
+        {
+            // out through staging slot c % 2, free once chunk c - 2 has left the device
+            if (c >= 2) cudaStreamWaitEvent(stream, evPool[fBase + (c - 2) * 3 + 2], 0);
+            float* slot = f32Out.p + (c % 2) * (size_t) chunk * T;
+            convert_kernel<false><<<cvGrid, 256, 0, stream>>>(slot, ioC, stride, T);
+            ++launches;
+            CPQ_CUDA(cudaGetLastError());
+            cudaEventRecord(evPool[fBase + c * 3 + 1], stream);
+            cudaStreamWaitEvent(sOut, evPool[fBase + c * 3 + 1], 0);
+            if (c == 0) cudaEventRecord(evOutBegin, sOut);
+            if (pitchF > 0)
+                CPQ_CUDA(cudaMemcpy2DAsync(hostF[s0], (size_t) pitchF * sizeof(float), slot, (size_t) T * sizeof(float), (size_t) T * sizeof(float),
+                                           (size_t) ns, cudaMemcpyDeviceToHost, sOut));
+            else
+                for (int s = s0; s < s0 + ns; ++s)
+                    CPQ_CUDA(cudaMemcpyAsync(hostF[s], slot + (size_t) (s - s0) * T, (size_t) T * sizeof(float), cudaMemcpyDeviceToHost, sOut));
+            cudaEventRecord(evPool[fBase + c * 3 + 2], sOut);
+            if (c + kH2DAhead < nChunks) CPQ_CUDA(enqueueH2D(c + kH2DAhead));
+        }
+        else if (hostPlanar)
         {
             cudaStreamWaitEvent(sOut, ce[4], 0);
             if (c == 0) cudaEventRecord(evOutBegin, sOut);
@@ -1775,7 +1831,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
     if (doConv) outerPending = (cfg.conv_boundary == CPQ_CONV_OUTER && !fullRange);
     else outerPending = false;
 
-    if (hostPlanar)
+    if (hostIO)
     {
         cudaEventRecord(evOutEnd, sOut);
         cudaStreamWaitEvent(stream, evOutEnd, 0);
@@ -1793,7 +1849,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         cudaEventElapsedTime(&ms, evPool[c * 6 + 2], evPool[c * 6 + 3]); timings.fft_inv_ms += ms;
         cudaEventElapsedTime(&ms, evPool[c * 6 + 3], evPool[c * 6 + 4]); timings.eq_ms += ms;
     }
-    if (hostPlanar)
+    if (hostIO)
     {
         cudaEventElapsedTime(&timings.h2d_ms, evInBegin, evInEnd);
         cudaEventElapsedTime(&timings.d2h_ms, evOutBegin, evOutEnd);
@@ -1806,7 +1862,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         for (size_t c = 0; c < nChunks; ++c)
         {
             float tin = 0.f, tb = 0.f, te = 0.f;
-            if (hostPlanar) cudaEventElapsedTime(&tin, ev[0], evPool[c * 6 + 5]);
+            if (hostIO) cudaEventElapsedTime(&tin, ev[0], evPool[c * 6 + 5]);
             cudaEventElapsedTime(&tb, ev[0], evPool[c * 6 + 0]);
             cudaEventElapsedTime(&te, ev[0], evPool[c * 6 + 4]);
             std::fprintf(stderr, "[cpq] chunk %zu: h2d_done %.2f compute %.2f..%.2f ms\n", c, tin, tb, te);
@@ -2209,6 +2265,28 @@ cpq_status cpq_process(cpq_handle h, double* const* planar, int64_t T, unsigned 
     CPQ_CUDA(e->io.ensure((size_t) e->nSeq * stride));
     // H2D, kernels and D2H are pipelined per sequence chunk on three streams inside processCore
     return e->processCore(e->io.p, stride, T, stages, planar);
+}
+
+cpq_status cpq_process_f32(cpq_handle h, float* const* planar, int64_t T, unsigned stages)
+{
+    if (!h || !planar) return CPQ_ERR_INVALID;
+    Engine* e = h;
+    auto setError = [&](const std::string& s) { e->setError(s); };
+    if (T <= 0 || T > e->cfg.max_samples || T % e->cfg.block_size != 0)
+    {
+        e->setError("process: T must be a positive multiple of block_size and <= max_samples");
+        return CPQ_ERR_INVALID;
+    }
+    for (int s = 0; s < e->nSeq; ++s)
+        if (!planar[s])
+        {
+            e->setError("process: null channel pointer");
+            return CPQ_ERR_INVALID;
+        }
+    CPQ_CUDA(cudaSetDevice(e->cfg.device));
+    const int64_t stride = (T + 1) & ~(int64_t) 1;
+    CPQ_CUDA(e->io.ensure((size_t) e->nSeq * stride));
+    return e->processCore(e->io.p, stride, T, stages, nullptr, planar);
 }
 
 cpq_status cpq_set_partition_range(cpq_handle h, int part_begin, int part_end)

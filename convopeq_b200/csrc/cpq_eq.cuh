@@ -1273,6 +1273,31 @@ __global__ void limiter_kernel(LimiterArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Float host buffers (the application's float path converts on entry and exit: convertFloatToDoubleHighQuality's cast,
+// InputBitDepthTransform.h:102-121, and static_cast<float> of the clamped result, AudioEngine.Processing.DSPCoreIO.cpp:524-537):
+// the wire format is FP32, the arithmetic stays FP64.
+// ---------------------------------------------------------------------------------------------
+template <bool TO_DOUBLE>
+__global__ void convert_kernel(float* __restrict__ f, double* __restrict__ d, int64_t dStride, int64_t T)
+{
+    float2* f2 = reinterpret_cast<float2*>(f + (size_t) blockIdx.y * T);
+    double2* d2 = reinterpret_cast<double2*>(d + (size_t) blockIdx.y * dStride);
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < T / 2; i += (int64_t) gridDim.x * blockDim.x)
+    {
+        if (TO_DOUBLE)
+        {
+            const float2 v = f2[i];
+            d2[i] = make_double2((double) v.x, (double) v.y);
+        }
+        else
+        {
+            const double2 v = d2[i];
+            f2[i] = make_float2(__double2float_rn(v.x), __double2float_rn(v.y));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // The engine's input stage (convo::input_transform::applyHighQuality64BitTransform, InputBitDepthTransform.h:86-100, from
 // DSPCore::processInput): optional gain, NaN or |v| < 1e-20 -> 0, clamp to [-1, 1] (+-Inf survives the scrub of the
 // reference's four-wide body and clamps to +-1; only its scalar remainder, n % 4 samples per callback, zeroes it).

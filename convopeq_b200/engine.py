@@ -201,6 +201,19 @@ class ConvoPeqEngine:
         self._check(self.lib.cpq_process(self.h, ptrs, x.shape[1], stages))
         return x
 
+    def process_f32(self, x: np.ndarray, stages: int = capi.STAGE_ALL) -> np.ndarray:
+        """In place on a float32 host array [n_seq, T]: FP32 on the wire, FP64 arithmetic."""
+        assert x.dtype == np.float32 and x.ndim == 2 and x.shape[0] == self.n_seq and x.flags["C_CONTIGUOUS"]
+        fp = C.POINTER(C.c_float)
+        ptrs = (fp * self.n_seq)(*[x[i].ctypes.data_as(fp) for i in range(self.n_seq)])
+        self._check(self.lib.cpq_process_f32(self.h, ptrs, x.shape[1], stages))
+        return x
+
+    def process_f32_host_ptrs(self, base_ptr: int, row_stride_floats: int, T: int, stages: int = capi.STAGE_ALL):
+        fp = C.POINTER(C.c_float)
+        ptrs = (fp * self.n_seq)(*[C.cast(base_ptr + 4 * i * row_stride_floats, fp) for i in range(self.n_seq)])
+        self._check(self.lib.cpq_process_f32(self.h, ptrs, T, stages))
+
     def process_host_ptrs(self, base_ptr: int, row_stride_doubles: int, T: int, stages: int = capi.STAGE_ALL):
         """Same as process() for a host buffer given by address (e.g. a pinned torch tensor)."""
         ptrs = (_dp * self.n_seq)(*[C.cast(base_ptr + 8 * i * row_stride_doubles, _dp) for i in range(self.n_seq)])

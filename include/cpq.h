@@ -281,6 +281,13 @@ double cpq_equal_power_sin(double x);       /* ConvolverProcessor.Runtime.cpp:26
  * are part of the call. */
 cpq_status cpq_process(cpq_handle h, double* const* planar, int64_t T, unsigned stages);
 
+/* Same with FP32 host buffers, in place: the wire format of hosts that hand the application float blocks (its float path casts
+ * on entry, convertFloatToDoubleHighQuality InputBitDepthTransform.h:102-121, and on exit, static_cast<float>,
+ * AudioEngine.Processing.DSPCoreIO.cpp:524-537).  Samples are promoted to FP64 on the device, every stage computes in FP64 exactly
+ * as in cpq_process, and the result is rounded to float on the way out; half the PCIe traffic.  Add CPQ_STAGE_INPUT for the
+ * input transform that follows the cast in the reference. */
+cpq_status cpq_process_f32(cpq_handle h, float* const* planar, int64_t T, unsigned stages);
+
 /* Same, data already resident: d_io is a device pointer to [n_streams*n_channels][stride] doubles. */
 cpq_status cpq_process_device(cpq_handle h, double* d_io, int64_t stride, int64_t T, unsigned stages);
 

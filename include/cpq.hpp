@@ -173,6 +173,13 @@ public:
         return ok(cpq_process(h_, planar, numSamples, stages));
     }
 
+    /// The same with float host buffers (FP32 on the wire, FP64 arithmetic).
+    bool process(float* const* planar, std::int64_t numSamples, unsigned stages = CPQ_STAGE_ALL)
+    {
+        if ((stages & CPQ_STAGE_EQ) && !pushEq()) return false;
+        return ok(cpq_process_f32(h_, planar, numSamples, stages));
+    }
+
     /// In place on device memory [numStreams * numChannels][stride].
     bool processDevice(double* deviceIO, std::int64_t stride, std::int64_t numSamples, unsigned stages = CPQ_STAGE_ALL)
     {

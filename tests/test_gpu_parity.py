@@ -812,3 +812,24 @@ def test_input_stage_matches_reference(checker, block, gain):
     for s in range(2):
         l, r, _ = checker.eq_run(signals.to_eqband(signals.band_params(75 + s)), want[2 * s], want[2 * s + 1], 48000.0, block)
         assert np.abs(z[2 * s] - l).max() <= TOL and np.abs(z[2 * s + 1] - r).max() <= TOL
+
+
+@pytest.mark.parametrize("n_streams,T", [(1, 8192), (45, 512 * 24)])
+def test_float_host_buffers(n_streams, T):
+    """cpq_process_f32: FP32 on the wire, FP64 arithmetic -- bit-identical to the double entry point fed the same (float-valued)
+    samples and rounded to float afterwards; 90 sequences move in ~30 chunks through the 3-in / 2-out staging slots."""
+    sr, block, ir_len = 48000.0, 512, 20000
+    eng = ConvoPeqEngine(n_streams, 2, sr, block, T, conv_boundary=capi.CONV_OUTER, shared_ir=True)
+    for ch in range(2):
+        eng.set_impulse(-1, ch, signals.synth_ir(ir_len, 30 + ch), 1.0, capi.default_filter_spec())
+    for s in range(n_streams):
+        eng.set_eq(s, signals.to_band(signals.band_params(100 + s % 5)))
+    eng.set_epilogue(1.0, 0)
+    xf = np.stack([signals.noise(T, 200 + i, 0.3) for i in range(2 * n_streams)]).astype(np.float32)
+    y64 = xf.astype(np.float64)
+    eng.process(y64, capi.STAGE_INPUT | capi.STAGE_ALL)
+    y32 = xf.copy()
+    eng.process_f32(y32, capi.STAGE_INPUT | capi.STAGE_ALL)
+    eng.close()
+    assert np.array_equal(y32, y64.astype(np.float32))
+    assert np.abs(y32).max() > 1e-3
