@@ -174,6 +174,7 @@ struct Engine
     int hRowOf(int stream_, int ch) const { return cfg.shared_ir ? ch : stream_ * cfg.n_channels + ch; }
 
     cpq_status init(const cpq_config* c);
+    cpq_status setKernelAttributes();
     cpq_status setImpulse(int stream_, int ch, const double* ir, int len, double scale, const cpq_filter_spec* spec);
     cpq_status ensureTwiddles(int li);
     cpq_status uploadEq(int64_t nCallbacks);
@@ -209,19 +210,12 @@ struct Engine
 };
 
 // ------------------------------------------------------------------------------------------------
-static bool g_attrDone[16][2] = {};
-
+// The >48 KB dynamic shared-memory opt-ins (cudaFuncAttributeMaxDynamicSharedMemorySize) are per device: Engine::init sets
+// all of them after cudaSetDevice, for every handle, so a process may hold handles on several GPUs (setKernelAttributes).
 template <int LOG2P>
 static cudaError_t fwdLaunch(const FwdArgs& a, cudaStream_t s)
 {
     using C = FftCfg<LOG2P>;
-    if (!g_attrDone[LOG2P][0])
-    {
-        cudaError_t e = cudaFuncSetAttribute(fft_fwd_kernel<LOG2P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fft_fwd_kernel<LOG2P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
-        if (e != cudaSuccess) return e;
-        g_attrDone[LOG2P][0] = true;
-    }
     const unsigned grid = (unsigned) ((a.totalFrames + C::FPC - 1) / C::FPC);
     const bool ir = a.halfOnly || a.applyScale || a.gain || a.tilt;   // prepare-time variant
     if (ir) fft_fwd_kernel<LOG2P, true><<<grid, C::THREADS, C::SMEM, s>>>(a);
@@ -232,12 +226,6 @@ template <int LOG2P>
 static cudaError_t invLaunch(const InvArgs& a, cudaStream_t s)
 {
     using C = FftCfg<LOG2P>;
-    if (!g_attrDone[LOG2P][1])
-    {
-        cudaError_t e = cudaFuncSetAttribute(fft_inv_kernel<LOG2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
-        if (e != cudaSuccess) return e;
-        g_attrDone[LOG2P][1] = true;
-    }
     const unsigned grid = (unsigned) ((a.totalFrames + C::FPC - 1) / C::FPC);
     fft_inv_kernel<LOG2P><<<grid, C::THREADS, C::SMEM, s>>>(a);
     return cudaGetLastError();
@@ -249,13 +237,6 @@ template <int LOG2P>
 static cudaError_t fwd16Launch(const FwdArgs& a, cudaStream_t s)
 {
     using C = Fft16Cfg<LOG2P>;
-    static bool attr = false;
-    if (!attr)
-    {
-        cudaError_t e = cudaFuncSetAttribute(fft_fwd16_kernel<LOG2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
     fft_fwd16_kernel<LOG2P><<<(unsigned) ((a.totalFrames + C::FPC - 1) / C::FPC), C::THREADS, C::SMEM, s>>>(a);
     return cudaGetLastError();
 }
@@ -263,13 +244,6 @@ template <int LOG2P>
 static cudaError_t inv16Launch(const InvArgs& a, cudaStream_t s)
 {
     using C = Fft16Cfg<LOG2P>;
-    static bool attr = false;
-    if (!attr)
-    {
-        cudaError_t e = cudaFuncSetAttribute(fft_inv16_kernel<LOG2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
     fft_inv16_kernel<LOG2P><<<(unsigned) ((a.totalFrames + C::FPC - 1) / C::FPC), C::THREADS, C::SMEM, s>>>(a);
     return cudaGetLastError();
 }
@@ -409,6 +383,39 @@ cpq_status Engine::launchInvLarge(int log2P, const InvArgs& a)
     return CPQ_OK;
 }
 
+constexpr size_t kMaxDynSmem = 227 * 1024;   // opt-in limit per CTA on sm_100
+
+template <int LOG2P>
+static cudaError_t fftAttrs()
+{
+    cudaError_t e = cudaFuncSetAttribute(fft_fwd_kernel<LOG2P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<LOG2P>::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fft_fwd_kernel<LOG2P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<LOG2P>::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fft_inv_kernel<LOG2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FftCfg<LOG2P>::SMEM);
+    return e;
+}
+template <int LOG2P>
+static cudaError_t fft16Attrs()
+{
+    cudaError_t e = cudaFuncSetAttribute(fft_fwd16_kernel<LOG2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Fft16Cfg<LOG2P>::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fft_inv16_kernel<LOG2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Fft16Cfg<LOG2P>::SMEM);
+    return e;
+}
+
+// Per device (the attribute lives in the device's context), hence per handle and unconditional.
+cpq_status Engine::setKernelAttributes()
+{
+    CPQ_CUDA(fftAttrs<6>()); CPQ_CUDA(fftAttrs<7>()); CPQ_CUDA(fftAttrs<8>()); CPQ_CUDA(fftAttrs<9>());
+    CPQ_CUDA(fftAttrs<10>()); CPQ_CUDA(fftAttrs<11>()); CPQ_CUDA(fftAttrs<12>()); CPQ_CUDA(fftAttrs<13>());
+    CPQ_CUDA(fft16Attrs<9>()); CPQ_CUDA(fft16Attrs<12>());
+    CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytes));
+    CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
+    CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
+    CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
+    CPQ_CUDA(cudaFuncSetAttribute(mac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem));
+    CPQ_CUDA(cudaFuncSetAttribute(dither_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kDitherSmemBytes));
+    return CPQ_OK;
+}
+
 cpq_status Engine::init(const cpq_config* c)
 {
     cfg = *c;
@@ -459,6 +466,10 @@ cpq_status Engine::init(const cpq_config* c)
         cfg.workspace_bytes = (size_t) 4 << 30;
         if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess)
             cfg.workspace_bytes = std::min<size_t>((size_t) 16 << 30, std::max<size_t>((size_t) 4 << 30, freeB / 4));
+    }
+    {
+        cpq_status st = setKernelAttributes();
+        if (st != CPQ_OK) return st;
     }
     CPQ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CPQ_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
@@ -1033,15 +1044,6 @@ cpq_status Engine::launchEq(EqArgs& a)
         CPQ_CUDA(cudaMemsetAsync(chainRec.p, 0xff, n * sizeof(double), stream));
     }
     a.chain.rec = reinterpret_cast<double2*>(chainRec.p);
-    static bool attrDone = false;
-    if (!attrDone)
-    {
-        CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytes));
-        CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
-        CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
-        CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
-        attrDone = true;
-    }
     CPQ_CUDA(cudaMemsetAsync(ticketFault.p, 0, sizeof(unsigned), stream));
     const unsigned grid = (unsigned) a.nSeq * (unsigned) a.nRuns;
     if (a.doEq && anyPar) eq_kernel<true, true, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
@@ -1621,11 +1623,10 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 a.framesPerCta = fpc;
                 a.ringRows = fpc <= step ? (step + (a.qEnd - a.qBegin) - 1 + kMacKT - 1) / kMacKT * kMacKT : macRingRows(a.qEnd - a.qBegin);
                 const size_t smem = macSmemBytes(a.qEnd - a.qBegin, a.ringRows);
-                static size_t macSmemSet = 0;
-                if (smem > macSmemSet)
+                if (smem > kMaxDynSmem)
                 {
-                    CPQ_CUDA(cudaFuncSetAttribute(mac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-                    macSmemSet = smem;
+                    setError("process: MAC tile exceeds the shared memory of one SM");
+                    return CPQ_ERR_UNSUPPORTED;
                 }
                 dim3 grid((unsigned) binTiles, (unsigned) ((K[li] + fpc - 1) / fpc), (unsigned) ns);
                 mac_kernel<<<grid, kMacThreads, smem, stream>>>(a);
@@ -1772,7 +1773,8 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             d.invScale = std::pow(2.0, ditherBits - 1);
             d.z = ditherZ.p + (size_t) s0 * 12;
             d.finalClamp = outCfg.finalClamp ? (limiterOn ? 1 : 3) : 0;
-            dither_kernel<<<(unsigned) ((ns + 31) / 32), 32, 0, stream>>>(d);
+            d.nch = cfg.n_channels;
+            dither_kernel<<<(unsigned) ((ns + 31) / 32), 32, kDitherSmemBytes, stream>>>(d);
             ++launches;
             CPQ_CUDA(cudaGetLastError());
         }

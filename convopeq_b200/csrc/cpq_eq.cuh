@@ -1454,7 +1454,21 @@ __global__ void ms_kernel(MsArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Dither + 12-tap error-feedback noise shaper, one thread per sequence (serial in time by nature).
+// Dither + 12-tap error-feedback noise shaper (PsychoacousticDither::processStereoBlock, PsychoacousticDither.h:293-405).
+//
+// Serial in time by nature: e[n] feeds tmp[n+1] through the quantiser, and the recurrence is chaotic (the feedback gains reach
+// 11.7, so a one-ulp difference flips the quantiser within a few hundred samples).  Parity is therefore bit-for-bit or nothing,
+// and the arithmetic below is the association of the reference as compiled by oracle/Makefile (g++ -O2 -mfma contracts
+// a*b + c): shaped = fma(c11,z11, ... fma(c2,z2, fma(c0,z0, c1*z1))); left channel of a stereo stream
+// tmp = fma(x, headroom, tpdf*scale) + shaped, right channel / mono tmp = fma(tpdf, scale, x*headroom) + shaped.
+// The dependent chain from e[n-1] to e[n] is 16 FP64 operations (11 FMA, add, mul, round, mul, sub) = about 130 cycles per
+// sample whatever the batch size -- the floor of this stage is T x 130 cycles (33 ms for 480 256 samples at 1.9 GHz), so the
+// engine runs it on a side stream where it overlaps the next chunk's transforms.
+//
+// One lane per sequence, a warp = 32 sequences.  Memory goes through shared memory in [32 sequences][32 samples] tiles so that
+// every global access is a full 256-byte row segment (the one-thread-per-sequence form touched 32 sectors per warp load):
+// cp.async brings tile k+1 (signal + 2 uniforms per sample) while tile k is computed; results are written back from shared
+// memory as 16-byte stores, half a row per lane group.
 // ---------------------------------------------------------------------------------------------
 struct DitherArgs
 {
@@ -1462,6 +1476,7 @@ struct DitherArgs
     int64_t ioStride;
     int64_t T;
     int nSeq;
+    int nch;                  // channels per stream: lane role = left channel of a stereo stream or not
     const double* uniforms;   // [nSeq][2*T]
     double coeff[12];
     double scale, invScale;
@@ -1469,36 +1484,110 @@ struct DitherArgs
     int finalClamp;           // after the quantiser: bit 0 scrub, bit 1 clamp to +-kOutputHeadroom (DSPCoreDouble.cpp:665-691, 712-737)
 };
 
-__global__ void dither_kernel(DitherArgs a)
+constexpr int kDthTile = 32;                 // samples per tile and sequence
+constexpr int kDthRow = kDthTile + 2;        // signal row pitch in doubles (16-byte aligned rows)
+constexpr int kDthURow = 2 * kDthTile + 2;   // uniform row pitch
+constexpr int kDthBufDoubles = 32 * kDthRow + 32 * kDthURow;
+constexpr size_t kDitherSmemBytes = (size_t) 2 * kDthBufDoubles * sizeof(double);
+
+__device__ __forceinline__ void dthCpAsync16(void* smem, const void* gmem)
 {
-    const int seq = blockIdx.x * blockDim.x + threadIdx.x;
-    if (seq >= a.nSeq) return;
-    double* d = a.io + (size_t) seq * a.ioStride;
-    const double* u = a.uniforms + (size_t) seq * 2 * a.T;
+    const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+
+__global__ void __launch_bounds__(32) dither_kernel(DitherArgs a)
+{
+    extern __shared__ __align__(16) double dthSmem[];
+    const int lane = threadIdx.x;
+    const int seq0 = blockIdx.x * 32;
+    const int nLocal = min(32, a.nSeq - seq0);
+    const int seq = seq0 + min(lane, nLocal - 1);          // idle lanes shadow the last sequence, they never store
+    const bool live = lane < nLocal;
+    const bool roleLeft = a.nch == 2 && (seq % 2) == 0;
+    const int64_t nTiles = (a.T + kDthTile - 1) / kDthTile;
+
+    auto issue = [&](int64_t tile, int buf) {
+        double* sig = dthSmem + (size_t) buf * kDthBufDoubles;
+        double* uni = sig + 32 * kDthRow;
+        const int64_t t0 = tile * kDthTile;
+        const int n = (int) (a.T - t0 < (int64_t) kDthTile ? a.T - t0 : (int64_t) kDthTile);      // even (T is even)
+        // signal: n/2 16-byte pieces per row; lane = piece + 16 * (row & 1)
+        for (int r = lane >> 4; r < nLocal; r += 2)
+        {
+            const int pc = lane & 15;
+            if (2 * pc < n) dthCpAsync16(sig + r * kDthRow + 2 * pc, a.io + (size_t) (seq0 + r) * a.ioStride + t0 + 2 * pc);
+        }
+        // uniforms: n 16-byte pieces per row (u1,u2 of one sample), one row per step
+        for (int r = 0; r < nLocal; ++r)
+            if (lane < n) dthCpAsync16(uni + r * kDthURow + 2 * lane, a.uniforms + ((size_t) (seq0 + r) * a.T + t0 + lane) * 2);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
     double z[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) z[i] = a.z[(size_t) seq * 12 + i];
-    for (int64_t i = 0; i < a.T; ++i)
+    double c[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) c[i] = a.coeff[i];
+    constexpr double kHeadroom = 0.8912509381337456;
+
+    issue(0, 0);
+    for (int64_t tile = 0; tile < nTiles; ++tile)
     {
-        double shaped = a.coeff[0] * z[0];
+        const int buf = (int) (tile & 1);
+        if (tile + 1 < nTiles)
+        {
+            issue(tile + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        }
+        else
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        double* sig = dthSmem + (size_t) buf * kDthBufDoubles;
+        const double* uni = sig + 32 * kDthRow;
+        const int64_t t0 = tile * kDthTile;
+        const int n = (int) (a.T - t0 < (int64_t) kDthTile ? a.T - t0 : (int64_t) kDthTile);
+        double* mine = sig + lane * kDthRow;
+        const double* myU = uni + lane * kDthURow;
+        if (live)
+            for (int i = 0; i < n; ++i)
+            {
+                const double x = mine[i];
+                const double2 uu = *reinterpret_cast<const double2*>(myU + 2 * i);
+                double shaped = __dmul_rn(c[1], z[1]);
+                shaped = __fma_rn(c[0], z[0], shaped);
 #pragma unroll
-        for (int t = 1; t < 12; ++t) shaped = __dadd_rn(shaped, __dmul_rn(a.coeff[t], z[t]));
-        const double2 uu = __ldg(reinterpret_cast<const double2*>(u) + i);
-        const double dn = __dmul_rn(__dadd_rn(uu.x - 0.5, uu.y - 0.5), a.scale);
-        const double tmp = __dadd_rn(__dadd_rn(__dmul_rn(d[i], 0.8912509381337456), dn), shaped);
-        const double q = __dmul_rn(rint(__dmul_rn(tmp, a.invScale)), a.scale);
-        double err = __dadd_rn(tmp, -q);
-        if (fabs(err) < 1.0e-20) err = 0.0;
+                for (int t = 2; t < 12; ++t) shaped = __fma_rn(c[t], z[t], shaped);
+                const double tpdf = __dadd_rn(__dadd_rn(uu.x, -0.5), __dadd_rn(uu.y, -0.5));
+                const double pre = roleLeft ? __fma_rn(x, kHeadroom, __dmul_rn(tpdf, a.scale)) : __fma_rn(tpdf, a.scale, __dmul_rn(x, kHeadroom));
+                const double tmp = __dadd_rn(pre, shaped);
+                const double q = __dmul_rn(rint(__dmul_rn(tmp, a.invScale)), a.scale);
+                double err = __dadd_rn(tmp, -q);
+                if (fabs(err) < 1.0e-20) err = 0.0;
 #pragma unroll
-        for (int t = 11; t > 0; --t) z[t] = z[t - 1];
-        z[0] = err;
-        double o = q;
-        if ((a.finalClamp & 1) && !(fabs(o) < 1.0e300)) o = 0.0;
-        if (a.finalClamp & 2) o = fmin(fmax(o, -0.8912509381337456), 0.8912509381337456);
-        d[i] = o;
+                for (int t = 11; t > 0; --t) z[t] = z[t - 1];
+                z[0] = err;
+                double o = q;
+                if ((a.finalClamp & 1) && !(fabs(o) < 1.0e300)) o = 0.0;
+                if (a.finalClamp & 2) o = fmin(fmax(o, -kHeadroom), kHeadroom);
+                mine[i] = o;
+            }
+        __syncwarp();
+        // write the tile back: 16-byte stores, lanes 0-15 one row, lanes 16-31 the next
+        for (int r = lane >> 4; r < nLocal; r += 2)
+        {
+            const int pc = lane & 15;
+            if (2 * pc < n)
+                *reinterpret_cast<double2*>(a.io + (size_t) (seq0 + r) * a.ioStride + t0 + 2 * pc) = *reinterpret_cast<const double2*>(sig + r * kDthRow + 2 * pc);
+        }
+        __syncwarp();   // the buffer is refilled by the issue() of the next iteration
     }
+    if (live)
+    {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) a.z[(size_t) seq * 12 + i] = z[i];
+        for (int i = 0; i < 12; ++i) a.z[(size_t) seq * 12 + i] = z[i];
+    }
 }
 
 // DFMA throughput probe (roofline denominator for the FP64 pipe); 8 independent chains per thread.

@@ -17,9 +17,9 @@ from . import capi
 
 _dp = C.POINTER(C.c_double)
 
-# EQProcessor::DEFAULT_FREQS (eqprocessor/EQProcessor.h:158-163)
-DEFAULT_FREQS = [25.0, 40.0, 63.0, 100.0, 160.0, 250.0, 400.0, 630.0, 1000.0, 1600.0,
-                 2500.0, 4000.0, 6300.0, 10000.0, 11000.0, 12500.0, 14000.0, 16000.0, 18000.0, 20000.0]
+# EQProcessor::DEFAULT_FREQS (eqprocessor/EQProcessor.h:158-163): the processor's own band centres
+EQPROCESSOR_DEFAULT_FREQS = (25.0, 40.0, 63.0, 100.0, 160.0, 250.0, 400.0, 630.0, 1000.0, 1600.0,
+                             2500.0, 4000.0, 6300.0, 10000.0, 11000.0, 12500.0, 14000.0, 16500.0, 18000.0, 19500.0)
 
 LOW_SHELF, PEAKING, HIGH_SHELF, LOW_PASS, HIGH_PASS = range(5)
 STEREO, LEFT, RIGHT = range(3)
@@ -249,15 +249,16 @@ class ConvoPeqEngine:
         return int(self.lib.cpq_kernel_launch_count(self.h))
 
 
-DEFAULT_FREQS = (20.0, 32.0, 50.0, 80.0, 125.0, 200.0, 315.0, 500.0, 800.0, 1250.0, 2000.0, 3150.0, 5000.0, 8000.0, 12500.0,
-                 16000.0, 19000.0, 20000.0, 22000.0, 24000.0)   # convo::EQParameters defaults (core/EQParameters.h:32-37)
+# convo::EQParameters defaults (core/EQParameters.h:32-37): the state a preset is loaded into
+EQPARAMETERS_DEFAULT_FREQS = (20.0, 32.0, 50.0, 80.0, 125.0, 200.0, 315.0, 500.0, 800.0, 1250.0, 2000.0, 3150.0, 5000.0, 8000.0, 12500.0,
+                              16000.0, 19000.0, 20000.0, 22000.0, 24000.0)
 
 
 def load_eq_preset(text: str, bands: Optional[Sequence[Band]] = None, total_gain_db: float = 0.0):
     """EQProcessor::loadFromTextFile on the contents of an EqualizerAPO / AutoEq preset; returns (bands, total_gain_db,
     ignored_filter_lines).  `bands` is the state before loading (default: convo::EQParameters{})."""
     arr = (capi.EqBandParams * capi.NUM_BANDS)()
-    start = list(bands) if bands is not None else [Band(frequency=f) for f in DEFAULT_FREQS]
+    start = list(bands) if bands is not None else [Band(frequency=f) for f in EQPARAMETERS_DEFAULT_FREQS]
     for i, b in enumerate(start):
         arr[i] = capi.EqBandParams(b.frequency, b.gain, b.q, int(b.enabled), int(b.type), int(b.channel_mode))
     g = C.c_float(total_gain_db)

@@ -265,6 +265,8 @@ class Oracle(_Base):
         L.cpqo_eq_get_state.argtypes = [C.c_void_p, _dp]
         L.cpqo_epilogue.argtypes = [_dp, C.c_long, C.c_double, C.c_double, C.c_int, _dp, _dp, _dp]
         L.cpqo_epilogue.restype = None
+        L.cpqo_epilogue_ex.argtypes = [_dp, C.c_long, C.c_double, C.c_double, C.c_int, _dp, _dp, _dp, C.c_int]
+        L.cpqo_epilogue_ex.restype = None
         L.cpqo_outer_wet.argtypes = [_dp, C.c_long, C.c_double]
         L.cpqo_outer_wet.restype = None
         L.cpqo_outer_mix.argtypes = [_dp, _dp, C.c_long, C.c_float, C.c_int]
@@ -318,12 +320,24 @@ class Oracle(_Base):
         return l, r, st
 
     def epilogue(self, x: np.ndarray, makeup_gain: float, sr: float, bit_depth: int,
-                 uniforms: Optional[np.ndarray] = None):
+                 uniforms: Optional[np.ndarray] = None, role: int = 1, z: Optional[np.ndarray] = None):
+        """One channel of makeup + headroom / dither.  role 0 = left channel of a stereo block, 1 = right channel or mono
+        (the two associations the compiled reference uses, see cpqo_epilogue_ex); z = carried error history (in/out)."""
         d = np.ascontiguousarray(x, dtype=np.float64).copy()
-        z = np.zeros(12)
+        z = np.zeros(12) if z is None else z
         tmp = np.zeros_like(d)
-        self.lib.cpqo_epilogue(_p(d), d.size, makeup_gain, sr, bit_depth, _p(uniforms), _p(z), _p(tmp))
+        self.lib.cpqo_epilogue_ex(_p(d), d.size, makeup_gain, sr, bit_depth, _p(uniforms), _p(z), _p(tmp), int(role))
         return d, tmp, z
+
+    def dither_run(self, x: np.ndarray, uniforms: np.ndarray, sr: float, bit_depth: int, block: int = 512):
+        """Same call as Ref.dither_run through the restatement: x[1 or 2][T], uniforms[channels][2T] -> (quantised, z[ch][12])."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        zs = np.zeros((x.shape[0], 12))
+        for ch in range(x.shape[0]):
+            role = 0 if (x.shape[0] == 2 and ch == 0) else 1
+            out[ch], _, zs[ch] = self.epilogue(x[ch], 1.0, sr, bit_depth, np.ascontiguousarray(uniforms[ch]), role=role)
+        return out, zs
 
     def outer_mix(self, wet: np.ndarray, dry_in: np.ndarray, mix: float, delay: int) -> np.ndarray:
         """ConvolverProcessor::process, settled: scrub(wet) * sin-gain(mix) + delayed dry * sin-gain(1 - mix) (restated, unpinned)."""
@@ -373,6 +387,21 @@ class Ref(_Base):
         L.cpqref_eq_set_total_gain.argtypes = [C.c_void_p, C.c_float]
         L.cpqref_eq_process.argtypes = [C.c_void_p, _dp, _dp, C.c_long, C.c_int]
         L.cpqref_eq_get_state.argtypes = [C.c_void_p, _dp]
+
+    def dither_run(self, x: np.ndarray, uniforms: np.ndarray, sr: float, bit_depth: int, block: int = 512,
+                   headroom: float = 0.8912509381337456):
+        """The reference's own PsychoacousticDither::processStereoBlock (PsychoacousticDither.h:293-405, compiled in place) on
+        x[1 or 2][T] with the VSL uniforms replaced by `uniforms`[channels][2T]; returns (quantised, shaper state [ch][12])."""
+        d = np.ascontiguousarray(x, dtype=np.float64).copy()
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        assert u.shape == (d.shape[0], 2 * d.shape[1])
+        z = np.zeros((2, 12))
+        f = self.lib.cpqref_dither_process
+        f.argtypes = [_dp, _dp, C.c_long, C.c_int, C.c_double, C.c_int, C.c_double, _dp, _dp, _dp]
+        f.restype = None
+        f(_p(d[0]), _p(d[1]) if d.shape[0] > 1 else None, d.shape[1], block, sr, bit_depth, headroom,
+          _p(u[0]), _p(u[1]) if d.shape[0] > 1 else None, _p(z))
+        return d, z[:d.shape[0]]
 
     def _nuc_set_impulse(self, h, ir, block, scale, spec, direct_head=False):
         return self.lib.cpqref_nuc_set_impulse(h, _p(ir), ir.size, block, scale, int(direct_head),

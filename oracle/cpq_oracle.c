@@ -1519,11 +1519,22 @@ void cpqo_dither_coeffs(double sample_rate, int bit_depth, double* out12)
 }
 
 /* One channel of the epilogue, in place.  bit_depth <= 0: y = x*makeup*0.8912509381337456.
- * Otherwise the dither/noise-shaper recurrence of processStereoBlock (:293-355) for this channel.
+ * Otherwise the dither/noise-shaper recurrence of processStereoBlock (:293-405) for this channel.
  * z[12] is the error history (carried); uniforms holds 2*n values; tmp_out (nullable) receives the
- * pre-quantiser value for 1e-10 comparisons. */
-void cpqo_epilogue(double* data, long n, double makeup_gain, double sample_rate, int bit_depth,
-                   const double* uniforms, double* z, double* tmp_out)
+ * pre-quantiser value.
+ *
+ * The recurrence is CHAOTIC: the error-feedback filter's gains (|c_k| up to 11.7) amplify a one-ulp difference in tmp
+ * until the quantiser flips, within a few hundred samples, and from there the outputs differ by whole LSBs.  Parity with
+ * the reference is therefore all or nothing, and this function reproduces the association of the reference as built by
+ * oracle/Makefile (g++ -O2 -mfma, which contracts a*b + c into fused multiply-adds; read off the disassembly of
+ * processStereoBlock in oracle/_ref):
+ *   shaped = fma(c11,z11, ... fma(c2,z2, fma(c0,z0, c1*z1)) ...)
+ *   left channel of a stereo block :  tmp = fma(x, headroom, d) + shaped,          d = ((u1-0.5)+(u2-0.5))*scale
+ *   right channel / mono block     :  tmp = fma((u1-0.5)+(u2-0.5), scale, x*headroom) + shaped
+ * `role`: 0 = left channel of a stereo block, 1 = right channel of a stereo block or the mono path.
+ * Pinned bit-for-bit against PsychoacousticDither.h compiled in place (tests/test_oracle_vs_ref.py). */
+void cpqo_epilogue_ex(double* data, long n, double makeup_gain, double sample_rate, int bit_depth,
+                      const double* uniforms, double* z, double* tmp_out, int role)
 {
     const double headroom = 0.8912509381337456;
     if (bit_depth <= 0)
@@ -1538,11 +1549,12 @@ void cpqo_epilogue(double* data, long n, double makeup_gain, double sample_rate,
     for (long i = 0; i < n; ++i)
     {
         const double x = data[i] * makeup_gain;
-        double shaped = c[0] * z[0];
-        for (int t = 1; t < 12; ++t) shaped = shaped + c[t] * z[t];
+        double shaped = c[1] * z[1];
+        shaped = fma(c[0], z[0], shaped);
+        for (int t = 2; t < 12; ++t) shaped = fma(c[t], z[t], shaped);
         const double u1 = uniforms[2 * i], u2 = uniforms[2 * i + 1];
-        const double d = ((u1 - 0.5) + (u2 - 0.5)) * scale;
-        const double tmp = (x * headroom) + d + shaped;
+        const double tpdf = (u1 - 0.5) + (u2 - 0.5);
+        const double tmp = (role == 0 ? fma(x, headroom, tpdf * scale) : fma(tpdf, scale, x * headroom)) + shaped;
         const double q = nearbyint(tmp * inv_scale) * scale; /* round-half-even, default FP env */
         double err = tmp - q;
         if (fabs(err) < 1.0e-20) err = 0.0;
@@ -1551,6 +1563,11 @@ void cpqo_epilogue(double* data, long n, double makeup_gain, double sample_rate,
         if (tmp_out) tmp_out[i] = tmp;
         data[i] = q;
     }
+}
+void cpqo_epilogue(double* data, long n, double makeup_gain, double sample_rate, int bit_depth,
+                   const double* uniforms, double* z, double* tmp_out)
+{
+    cpqo_epilogue_ex(data, n, makeup_gain, sample_rate, bit_depth, uniforms, z, tmp_out, 1);
 }
 
 /* The ConvolverThenEQ chain per callback (DSPCoreDouble.cpp:386-414,465-469,655-663), no dither. */

@@ -33,6 +33,7 @@
 
 #define private public
 #define protected public
+#include "PsychoacousticDither.h"   // with ref_shim/mkl_vsl.h standing in for oneMKL VSL (injected uniform streams)
 #include "MKLNonUniformConvolver.h"
 #include "eqprocessor/EQProcessor.h"
 #include "OutputFilter.h"
@@ -54,6 +55,32 @@ bool EQProcessor::retireBandNodeDeferred(BandNode* node) noexcept
 {
     delete node;
     return true;
+}
+
+// ---- injected-uniform VSL streams (ref_shim/mkl_vsl.h) -----------------------------------
+std::atomic<uint64_t> convo::PsychoacousticDither::instanceSeedCounterStorage_ { 0 };
+std::atomic<uint64_t>& convo::PsychoacousticDither::instanceSeedCounter() noexcept { return instanceSeedCounterStorage_; }
+namespace
+{
+struct VslInject { const double* values = nullptr; long count = 0; };
+thread_local VslInject g_vslInject[8];
+thread_local int g_vslCreated = 0;
+}
+static void cpqref_vsl_begin() { g_vslCreated = 0; for (auto& v : g_vslInject) v = VslInject {}; }
+static void cpqref_vsl_inject(int channel, const double* values, long count) { g_vslInject[channel] = VslInject { values, count }; }
+int vslNewStream(VSLStreamStatePtr* stream, int, unsigned int)
+{
+    auto* s = new cpqref_vsl_stream();
+    s->index = g_vslCreated++;
+    if (s->index < 8) { s->values = g_vslInject[s->index].values; s->count = g_vslInject[s->index].count; }
+    *stream = s;
+    return VSL_STATUS_OK;
+}
+int vslDeleteStream(VSLStreamStatePtr* stream) { delete *stream; *stream = nullptr; return VSL_STATUS_OK; }
+int vdRngUniform(int, VSLStreamStatePtr s, MKL_INT n, double* r, double, double)
+{
+    for (MKL_INT i = 0; i < n; ++i) r[i] = (s->pos < s->count) ? s->values[s->pos++] : 0.5;
+    return VSL_STATUS_OK;
 }
 
 extern "C" {
@@ -422,5 +449,33 @@ void cpqref_input_transform(double* data, int n, double gain)
     convo::input_transform::convertDoubleToDoubleHighQuality(data, data, n, gain);
 }
 
-int cpqref_abi_version(void) { return 3; }
+int cpqref_abi_version(void) { return 4; }
+
+// ------------------------------------------------------------------ dither (PsychoacousticDither.h, unmodified)
+// The header's only MKL dependency is the VSL uniform generator (:79,418-431); ref_shim/mkl_vsl.h replaces it with
+// streams that hand out injected numbers, so the noise shaper / quantiser recurrence of processStereoBlock (:293-405)
+// runs exactly as compiled from the reference.  uL / uR: 2 * total uniforms per channel (u1, u2 per sample), consumed in
+// the order the ring delivers them (prefill of 65536 at prepare(), refillRandomRingNonRt between callbacks, :440-475).
+// z_out (nullable): shaperStateBuffer of channels 0 and 1 after the run, [2][12].
+void cpqref_dither_process(double* L, double* R, long total, int block, double sr, int bits, double headroom,
+                           const double* uL, const double* uR, double* z_out)
+{
+    cpqref_vsl_begin();
+    cpqref_vsl_inject(0, uL, 2 * total);
+    if (R) cpqref_vsl_inject(1, uR, 2 * total);
+    auto* d = new convo::PsychoacousticDither(std::optional<uint64_t>(1));
+    d->prepare(sr, bits);
+    for (long pos = 0; pos < total; pos += block)
+    {
+        const int n = (int) std::min<long>(block, total - pos);
+        d->processStereoBlock(L + pos, R ? R + pos : nullptr, n, headroom);
+        // the worker thread's job (AudioEngine's refill timer): keep the ring topped up so it never runs dry
+        for (int k = 0; k < 2 * n / 2048 + 2; ++k) d->refillRandomRingNonRt();
+    }
+    if (z_out)
+        for (int c = 0; c < 2; ++c)
+            for (int t = 0; t < 12; ++t) z_out[c * 12 + t] = d->shaperStateBuffer[c * convo::PsychoacousticDither::STATE_STRIDE + t];
+    delete d;
+    cpqref_vsl_begin();
+}
 }

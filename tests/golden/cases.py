@@ -86,3 +86,17 @@ def chain_inputs(c):
     bands = signals.band_params(4000 + c["seed"])
     x = np.stack([signals.noise(c["T"], 5000 + c["seed"]), signals.noise(c["T"], 5001 + c["seed"])])
     return irs, bands, x
+
+
+# Dither (PsychoacousticDither.h compiled in place, injected uniforms); the recurrence is chaotic, vectors are bit-exact pins.
+DITHER_CASES = {
+    "stereo_48k_24bit": dict(sr=48000.0, bits=24, nch=2, block=512, T=8192, seed=1),
+    "stereo_96k_16bit_480": dict(sr=96000.0, bits=16, nch=2, block=480, T=9600, seed=2),
+    "mono_44k1_32bit": dict(sr=44100.0, bits=32, nch=1, block=64, T=4096, seed=3),
+}
+
+
+def dither_inputs(c):
+    x = np.stack([signals.noise(c["T"], 7000 + c["seed"] + i, 0.3) for i in range(c["nch"])])
+    u = np.random.default_rng(7100 + c["seed"]).random((c["nch"], 2 * c["T"]))
+    return x, u

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 from oracle.bindings import Ref, Oracle, FilterSpec  # noqa: E402
 from tests import signals  # noqa: E402
 from tests.golden.cases import (CONV_CASES, EQ_CASES, CHAIN_CASES, OUTPUT_CASES, FULL_CHAIN_CASES, conv_inputs, eq_inputs,  # noqa: E402
-                                chain_inputs, output_inputs)
+                                chain_inputs, output_inputs, DITHER_CASES, dither_inputs)
 
 
 def main():
@@ -49,6 +49,11 @@ def main():
         irs, bands, x = chain_inputs(c)
         y = ref.chain_run(irs, signals.to_eqband(bands), x, c["sr"], c["block"], FilterSpec(**c["spec"]), do_epilogue=False)
         out["full_chain/" + name] = ref.output_run(y, c["sr"], c["block"], makeup=c["makeup"], **c["out"])
+    for name, c in DITHER_CASES.items():
+        x, u = dither_inputs(c)
+        q, z = ref.dither_run(x, u, c["sr"], c["bits"], c["block"])
+        out["dither/" + name] = q
+        out["dither_z/" + name] = z
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(out), "arrays")

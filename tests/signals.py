@@ -3,8 +3,9 @@ from __future__ import annotations
 
 import numpy as np
 
+# EQProcessor::DEFAULT_FREQS (eqprocessor/EQProcessor.h:158-163)
 DEFAULT_FREQS = [25.0, 40.0, 63.0, 100.0, 160.0, 250.0, 400.0, 630.0, 1000.0, 1600.0,
-                 2500.0, 4000.0, 6300.0, 10000.0, 11000.0, 12500.0, 14000.0, 16000.0, 18000.0, 20000.0]
+                 2500.0, 4000.0, 6300.0, 10000.0, 11000.0, 12500.0, 14000.0, 16500.0, 18000.0, 19500.0]
 
 
 def noise(n: int, seed: int, amp: float = 0.1) -> np.ndarray:

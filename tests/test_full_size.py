@@ -61,11 +61,12 @@ def test_cfg1b_uniform_extension_10s_noise():
         assert np.abs(y[ch] - lin).max() <= 1e-12 * max(1.0, np.abs(lin).max()), ch
 
 
-@pytest.mark.parametrize("sat", [0.2, 0.0])
-def test_cfg2_eq_only_60s_sweep(checker, sat):
-    """configs[1]: stereo 48 kHz, 20-band peaking/shelf cascade only, 60 s log sweep."""
+@pytest.mark.parametrize("sat,stress", [(0.2, False), (0.0, False), (0.2, True), (0.0, True)])
+def test_cfg2_eq_only_60s_sweep(checker, sat, stress):
+    """configs[1]: stereo 48 kHz, 20-band peaking/shelf cascade only, 60 s log sweep; the mild set (U(-6,6) dB, Q U(0.5,4)) and
+    SURVEY 8d's stress set (Q = 20, +-24 dB alternating: pole radius 0.99998, a memory of 6e4 samples across 352 tiles)."""
     sr, T = 48000.0, _whole(2880000)
-    params = signals.band_params(seed=7)
+    params = signals.band_params(seed=7, stress=stress)
     xl, xr = signals.log_sweep(T, sr)
     eng = ConvoPeqEngine(1, 2, sr, BLOCK, T)
     eng.set_eq(0, signals.to_band(params), sat, 0.0)
@@ -132,8 +133,15 @@ def test_cfg4_batch_of_1024_stereo_streams(checker):
     x[:2 * half] = torch.randn(2 * half, T, device=dev, dtype=torch.float64, generator=g) * 0.1
     x[2 * half:] = x[:2 * half]
     x_sampled = {s: x[2 * s:2 * s + 2].cpu().numpy() for s in sampled}
+    # the same batch through the host entry point (cpq_process: chunked H2D / compute / D2H on three streams, the e2e
+    # number's path) must give the same bits as the device-resident call
+    host = torch.empty(2 * S, T, dtype=torch.float64).pin_memory()
+    host.copy_(x)
     eng.process_device(x.data_ptr(), T, T, capi.STAGE_ALL)
     torch.cuda.synchronize()
+    eng.process_host_ptrs(host.data_ptr(), T, T, capi.STAGE_ALL)
+    assert torch.equal(host, x.cpu()), "cpq_process (host buffers) differs from cpq_process_device"
+    del host
     assert torch.equal(x[:2 * half], x[2 * half:])
     assert bool(torch.isfinite(x).all())
     for s in sampled:

@@ -387,22 +387,25 @@ def test_full_chain_batch_of_streams(checker, oracle):
             assert np.abs(y[2 * s + ch] - want).max() <= TOL, (s, ch)
 
 
-def test_dither_epilogue(oracle):
-    """Injected uniforms: pre-quantiser value within 1e-10, quantised output judged in LSB flips."""
-    sr, block, T, bits = 48000.0, 512, 8192, 24
-    x = np.stack([signals.noise(T, 1, 0.3), signals.noise(T, 2, 0.3)])
-    u = np.random.default_rng(5).random((2, 2 * T))
-    eng = ConvoPeqEngine(1, 2, sr, block, T)
+@pytest.mark.parametrize("sr,bits,nch,block,T", [(48000.0, 24, 2, 512, 65536), (96000.0, 16, 2, 480, 48000), (44100.0, 32, 1, 64, 8192),
+                                                 (192000.0, 24, 2, 100, 20000)])
+def test_dither_epilogue(checker, sr, bits, nch, block, T):
+    """Injected uniforms (the VSL ring's replacement).  The shaper is chaotic, so the check is bit-for-bit: the quantised
+    output and the carried error history equal the reference's own PsychoacousticDither.h compiled in place (checker = Ref;
+    the restatement, itself pinned bit-for-bit against it, elsewhere).  70 sequences = three warps, one partly filled."""
+    n_streams = 70 // nch
+    rng = np.random.default_rng(5)
+    x = np.stack([signals.noise(T, 100 + i, 0.3) for i in range(n_streams * nch)])
+    u = rng.random((n_streams * nch, 2 * T))
+    eng = ConvoPeqEngine(n_streams, nch, sr, block, T)
     eng.set_epilogue(0.9, bits, u)
     y = x.copy()
     eng.process(y, capi.STAGE_EPILOGUE)
     eng.close()
-    lsb = 1.0 / 2 ** (bits - 1)
-    for ch in range(2):
-        want, tmp, _ = oracle.epilogue(x[ch], 0.9, sr, bits, u[ch])
-        flips = np.count_nonzero(np.abs(y[ch] - want) > 0.25 * lsb)
-        assert flips == 0, flips
-        assert np.abs(y[ch] - tmp).max() <= lsb      # quantised within one step of the pre-quantiser value
+    for s in range(0, n_streams, 7):
+        rows = slice(s * nch, (s + 1) * nch)
+        want, _ = checker.dither_run(x[rows] * 0.9, u[rows], sr, bits, block)
+        assert np.array_equal(y[rows], want), s
 
 
 def test_partition_range_partials_sum_to_full(checker):

@@ -168,7 +168,7 @@ Filter 8: ON PK Gain 2 dB Q 1
 
 def test_eq_preset_text_parser():
     """EQProcessor::loadFromTextFile (EQProcessor.Core.cpp:300-495) restated host-side (cpq_parse_eq_preset)."""
-    from convopeq_b200.engine import load_eq_preset, DEFAULT_FREQS
+    from convopeq_b200.engine import load_eq_preset, EQPARAMETERS_DEFAULT_FREQS as DEFAULT_FREQS
     bands, gain, ignored = load_eq_preset(PRESET)
     f32 = lambda v: float(np.float32(v))
     assert ignored == 0 and gain == f32(-5.25)

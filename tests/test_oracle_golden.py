@@ -8,7 +8,7 @@ import pytest
 from oracle.bindings import FilterSpec
 from tests import signals
 from tests.golden.cases import (CONV_CASES, EQ_CASES, CHAIN_CASES, OUTPUT_CASES, FULL_CHAIN_CASES, conv_inputs, eq_inputs, chain_inputs,
-                                output_inputs)
+                                output_inputs, DITHER_CASES, dither_inputs)
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden.npz"))
 TOL = 1e-12   # restatement vs reference: same algorithm, different FFT rounding (SURVEY 8c measured 5.8e-15)
@@ -83,6 +83,16 @@ def test_epilogue_headroom_and_dither_determinism(oracle):
     lsb = 1.0 / 2 ** 15
     assert np.allclose(q1 / lsb, np.round(q1 / lsb))          # quantised to the 16-bit grid
     assert np.abs(q1 - tmp).max() <= 0.5 * lsb + 1e-15         # round-to-nearest of the pre-quantiser value
+
+
+@pytest.mark.parametrize("name", sorted(DITHER_CASES))
+def test_dither_restatement_matches_golden_bit_for_bit(oracle, name):
+    """Vectors from PsychoacousticDither.h compiled in place (injected uniforms); chaotic recurrence, so exact equality."""
+    c = DITHER_CASES[name]
+    x, u = dither_inputs(c)
+    q, z = oracle.dither_run(x, u, c["sr"], c["bits"], c["block"])
+    assert np.array_equal(q, GOLD["dither/" + name])
+    assert np.array_equal(z, GOLD["dither_z/" + name])
 
 
 @pytest.mark.parametrize("name", sorted(OUTPUT_CASES))

@@ -168,3 +168,21 @@ def test_input_transform_restatement_equals_reference(oracle, ref):
     x[3], x[10], x[11], x[20], x[21], x[30], x[1025], x[1026] = np.nan, np.inf, -np.inf, 1e-25, -3e-21, 2.5, np.inf, np.nan
     for g in (1.0, 0.5, 1.0 + 1e-10, 3.0):
         assert np.array_equal(oracle.input_transform(x, g), ref.input_transform(x, g))
+
+
+@pytest.mark.parametrize("sr,bits,T,block", [(48000.0, 24, 200000, 512), (96000.0, 16, 70000, 480), (44100.0, 32, 40000, 64),
+                                             (192000.0, 20, 30000, 1000)])
+def test_dither_restatement_is_bit_identical_to_reference(oracle, ref, sr, bits, T, block):
+    """PsychoacousticDither::processStereoBlock compiled in place (mkl_vsl.h shim handing out injected uniforms) against
+    cpqo_epilogue_ex: the error-feedback recurrence is chaotic, so only bit identity is a meaningful pin.  200 000 samples
+    cross the 65 536-entry ring three times (prefill + refillRandomRingNonRt)."""
+    x = np.stack([signals.noise(T, 1, 0.3), signals.noise(T, 2, 0.3)])
+    u = np.random.default_rng(5).random((2, 2 * T))
+    q, z = ref.dither_run(x, u, sr, bits, block)
+    want, zo = oracle.dither_run(x, u, sr, bits, block)
+    assert np.array_equal(q, want) and np.array_equal(z, zo)
+    qm, zm = ref.dither_run(x[:1], u[:1], sr, bits, block)       # mono path (:362-405)
+    wm, zom = oracle.dither_run(x[:1], u[:1], sr, bits, block)
+    assert np.array_equal(qm, wm) and np.array_equal(zm, zom)
+    lsb = 1.0 / 2 ** (bits - 1)
+    assert np.allclose(q / lsb, np.round(q / lsb))
