@@ -198,6 +198,25 @@ struct Engine
     unsigned postIdentity = 0;          // output-filter stages whose coefficients are the identity (skipped)
     DevBuf<double> postc, postState;
     cpq_status ensureGather(int64_t nCallbacks);
+
+    // ---- streaming continuation (cpq_set_streaming): the state the reference keeps between callbacks, carried between calls.
+    // Per sequence: the last 2*Pmax input samples (prevInputBuf / inputAccBuf of every layer, MKLNonUniformConvolver.h:288-365),
+    // per layer the last Q-1 input spectra (the FDL) and the tail-stream samples not yet read by Get (the delay line); the EQ,
+    // output-stage, AGC, limiter and dither states live in the buffers the one-shot form already writes.
+    bool streaming = false;
+    bool contValid = false;              // false = the next call starts from Reset
+    int64_t absCallback = 0;             // callbacks processed since Reset
+    int histLen = 0;                     // input history samples per sequence
+    int fdlRows[CPQ_MAX_LAYERS] = {};    // Q - 1
+    int carryFrames[CPQ_MAX_LAYERS] = {};
+    DevBuf<double> inHist, xcat;
+    DevBuf<double2> fdl[CPQ_MAX_LAYERS];
+    DevBuf<double> tailCarry[CPQ_MAX_LAYERS];
+    cpq_status ensureStreamState();
+    cpq_status resetState();
+    size_t stateBytes() const;
+    cpq_status exportState(void* dst, size_t bytes);
+    cpq_status importState(const void* src, size_t bytes);
     cpq_status processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF = nullptr);
     DevBuf<float> f32In, f32Out;        // device staging of float host buffers: 3 inbound / 2 outbound chunk slots
     cpq_status processDevice(double* dIo, int64_t stride, int64_t T, unsigned stages) { return processCore(dIo, stride, T, stages, nullptr); }
@@ -1001,6 +1020,195 @@ cpq_status Engine::uploadEq(int64_t nCallbacks)
     return CPQ_OK;
 }
 
+// ---- streaming continuation state ---------------------------------------------------------------------------------
+// Geometry of the carried state, fixed by the layer plan:  input history 2 Pmax samples;  FDL rows Q - 1 per layer;  tail
+// window = the frames Get may still read: delayLineReadAdd starts at max(readCursor, writeCursor - outputDelaySamples)
+// (MKLNonUniformConvolver.cpp:1640-1688) and writeCursor trails the input by at most one distribution cycle.
+cpq_status Engine::ensureStreamState()
+{
+    if (!planSet)
+    {
+        // EQ / output stages only: nothing of the convolver to carry
+        histLen = 0;
+        return CPQ_OK;
+    }
+    int pmax = 0;
+    for (int li = 0; li < plan.numLayers; ++li) pmax = std::max(pmax, plan.layers[li].partSize);
+    const int wantHist = 2 * pmax;
+    const bool fresh = histLen != wantHist || !inHist.p;
+    histLen = wantHist;
+    const int B = cfg.block_size;
+    for (int li = 0; li < plan.numLayers; ++li)
+    {
+        const LayerPlan& l = plan.layers[li];
+        fdlRows[li] = l.numPartsIR - 1;
+        const int cbs = (l.numPartsIR + std::max(1, l.partsPerCallback) - 1) / std::max(1, l.partsPerCallback);
+        carryFrames[li] = li == 0 ? 0 : (l.outputDelaySamples + l.partSize - 1) / l.partSize + (int) (((int64_t) cbs * B + l.partSize - 1) / l.partSize) + 2;
+    }
+    if (!fresh) return CPQ_OK;
+    CPQ_CUDA(inHist.ensure((size_t) nSeq * histLen));
+    for (int li = 0; li < plan.numLayers; ++li)
+    {
+        const LayerPlan& l = plan.layers[li];
+        CPQ_CUDA(fdl[li].ensure((size_t) nSeq * std::max(fdlRows[li], 1) * l.partSize));
+        if (li > 0) CPQ_CUDA(tailCarry[li].ensure((size_t) nSeq * carryFrames[li] * l.partSize));
+    }
+    return resetState();
+}
+
+// MKLNonUniformConvolver::Reset (.cpp:1693) + EQProcessor state clear + PsychoacousticDither::reset for every stream
+cpq_status Engine::resetState()
+{
+    CPQ_CUDA(cudaSetDevice(cfg.device));
+    if (inHist.p) CPQ_CUDA(cudaMemsetAsync(inHist.p, 0, inHist.n * sizeof(double), stream));
+    for (int li = 0; li < CPQ_MAX_LAYERS; ++li)
+    {
+        if (fdl[li].p) CPQ_CUDA(cudaMemsetAsync(fdl[li].p, 0, fdl[li].n * sizeof(double2), stream));
+        if (tailCarry[li].p) CPQ_CUDA(cudaMemsetAsync(tailCarry[li].p, 0, tailCarry[li].n * sizeof(double), stream));
+    }
+    CPQ_CUDA(cudaMemsetAsync(ditherZ.p, 0, (size_t) nSeq * 12 * sizeof(double), stream));
+    CPQ_CUDA(cudaMemsetAsync(stateOut.p, 0, (size_t) nSeq * CPQ_NUM_BANDS * 2 * sizeof(double), stream));
+    if (postState.p) CPQ_CUDA(cudaMemsetAsync(postState.p, 0, postState.n * sizeof(double), stream));
+    CPQ_CUDA(cudaStreamSynchronize(stream));
+    absCallback = 0;
+    contValid = false;
+    outerPending = false;
+    for (auto& e : eqSets) e.events.clear();
+    gainTabCallbacks = -1;
+    return CPQ_OK;
+}
+
+// Serialised state: header, then the buffers in a fixed order.  Only meaningful for a handle with the same configuration,
+// impulses and EQ settings (the header carries the geometry to check that).
+struct StateHeader
+{
+    uint64_t magic;          // "CPQSTAT1"
+    int32_t nSeq, nStreams, histLen, numLayers;
+    int32_t fdlRows[CPQ_MAX_LAYERS], carryFrames[CPQ_MAX_LAYERS], partSize[CPQ_MAX_LAYERS];
+    int32_t contValid, hasPost, hasAgc, hasLim;
+    int64_t absCallback;
+};
+static constexpr uint64_t kStateMagic = 0x3154415453515043ull;
+
+size_t Engine::stateBytes() const
+{
+    size_t n = sizeof(StateHeader);
+    n += (size_t) nSeq * histLen * sizeof(double);
+    if (histLen > 0)
+        for (int li = 0; li < plan.numLayers; ++li)
+        {
+            n += (size_t) nSeq * fdlRows[li] * plan.layers[li].partSize * sizeof(double2);
+            n += (size_t) nSeq * carryFrames[li] * plan.layers[li].partSize * sizeof(double);
+        }
+    n += (size_t) nSeq * CPQ_NUM_BANDS * 2 * sizeof(double);     // EQ band states
+    n += (size_t) nSeq * kEqPostStages * 2 * sizeof(double);     // output-stage states
+    n += (size_t) cfg.n_streams * 3 * sizeof(double);            // AGC envelopes + gain
+    n += (size_t) cfg.n_streams * sizeof(double);                // limiter envelope
+    n += (size_t) nSeq * 12 * sizeof(double);                    // dither error history
+    return n;
+}
+
+cpq_status Engine::exportState(void* dst, size_t bytes)
+{
+    if (!streaming)
+    {
+        setError("export_state: the handle is not in streaming mode (cpq_set_streaming)");
+        return CPQ_ERR_NOT_READY;
+    }
+    cpq_status st = ensureStreamState();
+    if (st != CPQ_OK) return st;
+    if (!dst || bytes < stateBytes())
+    {
+        setError("export_state: buffer smaller than cpq_state_size()");
+        return CPQ_ERR_INVALID;
+    }
+    CPQ_CUDA(cudaSetDevice(cfg.device));
+    CPQ_CUDA(cudaStreamSynchronize(stream));
+    StateHeader h {};
+    h.magic = kStateMagic;
+    h.nSeq = nSeq; h.nStreams = cfg.n_streams; h.histLen = histLen; h.numLayers = histLen > 0 ? plan.numLayers : 0;
+    for (int li = 0; li < h.numLayers; ++li) { h.fdlRows[li] = fdlRows[li]; h.carryFrames[li] = carryFrames[li]; h.partSize[li] = plan.layers[li].partSize; }
+    h.contValid = contValid ? 1 : 0;
+    h.hasPost = postState.p ? 1 : 0; h.hasAgc = agcState.p ? 1 : 0; h.hasLim = limEnv.p ? 1 : 0;
+    h.absCallback = absCallback;
+    char* o = static_cast<char*>(dst);
+    std::memcpy(o, &h, sizeof(h));
+    o += sizeof(h);
+    auto put = [&](const void* dev, size_t n, bool present) -> cudaError_t {
+        cudaError_t e = cudaSuccess;
+        if (present && n) e = cudaMemcpy(o, dev, n, cudaMemcpyDeviceToHost);
+        else std::memset(o, 0, n);
+        o += n;
+        return e;
+    };
+    CPQ_CUDA(put(inHist.p, (size_t) nSeq * histLen * sizeof(double), histLen > 0));
+    for (int li = 0; li < h.numLayers; ++li)
+    {
+        CPQ_CUDA(put(fdl[li].p, (size_t) nSeq * fdlRows[li] * plan.layers[li].partSize * sizeof(double2), true));
+        CPQ_CUDA(put(tailCarry[li].p, (size_t) nSeq * carryFrames[li] * plan.layers[li].partSize * sizeof(double), li > 0));
+    }
+    CPQ_CUDA(put(stateOut.p, (size_t) nSeq * CPQ_NUM_BANDS * 2 * sizeof(double), true));
+    CPQ_CUDA(put(postState.p, (size_t) nSeq * kEqPostStages * 2 * sizeof(double), postState.p != nullptr));
+    CPQ_CUDA(put(agcState.p, (size_t) cfg.n_streams * 3 * sizeof(double), agcState.p != nullptr));
+    CPQ_CUDA(put(limEnv.p, (size_t) cfg.n_streams * sizeof(double), limEnv.p != nullptr));
+    CPQ_CUDA(put(ditherZ.p, (size_t) nSeq * 12 * sizeof(double), true));
+    return CPQ_OK;
+}
+
+cpq_status Engine::importState(const void* src, size_t bytes)
+{
+    if (!streaming)
+    {
+        setError("import_state: the handle is not in streaming mode (cpq_set_streaming)");
+        return CPQ_ERR_NOT_READY;
+    }
+    cpq_status st = ensureStreamState();
+    if (st != CPQ_OK) return st;
+    StateHeader h {};
+    if (!src || bytes < sizeof(h))
+    {
+        setError("import_state: short buffer");
+        return CPQ_ERR_INVALID;
+    }
+    std::memcpy(&h, src, sizeof(h));
+    bool ok = h.magic == kStateMagic && h.nSeq == nSeq && h.nStreams == cfg.n_streams && h.histLen == histLen && bytes >= stateBytes() &&
+              h.numLayers == (histLen > 0 ? plan.numLayers : 0);
+    for (int li = 0; ok && li < h.numLayers; ++li)
+        ok = h.fdlRows[li] == fdlRows[li] && h.carryFrames[li] == carryFrames[li] && h.partSize[li] == plan.layers[li].partSize;
+    if (!ok)
+    {
+        setError("import_state: the blob was exported from a handle with another configuration or layer plan");
+        return CPQ_ERR_GEOMETRY;
+    }
+    CPQ_CUDA(cudaSetDevice(cfg.device));
+    CPQ_CUDA(cudaStreamSynchronize(stream));
+    const char* o = static_cast<const char*>(src) + sizeof(h);
+    auto get = [&](void* dev, size_t n, bool present) -> cudaError_t {
+        cudaError_t e = cudaSuccess;
+        if (present && n) e = cudaMemcpy(dev, o, n, cudaMemcpyHostToDevice);
+        o += n;
+        return e;
+    };
+    CPQ_CUDA(get(inHist.p, (size_t) nSeq * histLen * sizeof(double), histLen > 0));
+    for (int li = 0; li < h.numLayers; ++li)
+    {
+        CPQ_CUDA(get(fdl[li].p, (size_t) nSeq * fdlRows[li] * plan.layers[li].partSize * sizeof(double2), true));
+        CPQ_CUDA(get(tailCarry[li].p, (size_t) nSeq * carryFrames[li] * plan.layers[li].partSize * sizeof(double), li > 0));
+    }
+    CPQ_CUDA(get(stateOut.p, (size_t) nSeq * CPQ_NUM_BANDS * 2 * sizeof(double), true));
+    if (h.hasPost) CPQ_CUDA(postState.ensure((size_t) nSeq * kEqPostStages * 2));
+    CPQ_CUDA(get(postState.p, (size_t) nSeq * kEqPostStages * 2 * sizeof(double), h.hasPost != 0));
+    if (h.hasAgc) CPQ_CUDA(agcState.ensure((size_t) cfg.n_streams * 3));
+    CPQ_CUDA(get(agcState.p, (size_t) cfg.n_streams * 3 * sizeof(double), h.hasAgc != 0));
+    if (h.hasLim) CPQ_CUDA(limEnv.ensure((size_t) cfg.n_streams));
+    CPQ_CUDA(get(limEnv.p, (size_t) cfg.n_streams * sizeof(double), h.hasLim != 0));
+    CPQ_CUDA(get(ditherZ.p, (size_t) nSeq * 12 * sizeof(double), true));
+    absCallback = h.absCallback;
+    contValid = h.contValid != 0;
+    gplanCallbacks = -1;
+    return CPQ_OK;
+}
+
 cpq_status Engine::ensureGather(int64_t nCallbacks)
 {
     if (gplanCallbacks == nCallbacks) return CPQ_OK;
@@ -1238,6 +1446,7 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
     a.gainConst = gainConst.p;
     a.setOfSeq = e.setOfSeq;
     a.stateOut = agcState.p + (size_t) st0 * 3;
+    a.stateIn = e.stateIn ? a.stateOut : nullptr;   // streaming continuation
     a.nStreams = nst;
     a.nch = nch;
     a.nCallbacks = e.nCallbacks;
@@ -1279,6 +1488,10 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
     const bool doConv = stages & CPQ_STAGE_CONV, doEq = stages & CPQ_STAGE_EQ, doEpi = stages & CPQ_STAGE_EPILOGUE;
     const int launches0 = (int) launches;
     timings = cpq_timings {};
+    // streaming continuation: this call covers callbacks [cb0, cb0 + nCallbacks) of the stream since Reset
+    const bool strm = streaming;
+    const bool cont = strm && contValid;       // carried state exists
+    const int64_t cb0 = strm ? absCallback : 0;
 
     if (doConv)
     {
@@ -1293,7 +1506,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 setError("process: cpq_set_impulse was not called for every stream-channel");
                 return CPQ_ERR_NOT_READY;
             }
-        cpq_status st = ensureGather(nCallbacks);
+        cpq_status st = ensureGather(cb0 + nCallbacks);
         if (st != CPQ_OK) return st;
     }
     if (doEq)
@@ -1321,6 +1534,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         // with dither the quantised signal is what the limiter sees: no detection in the EQ launch, every stream runs it
         CPQ_CUDA(cudaMemsetAsync(limFlag.p, doDither ? 0xff : 0, (size_t) cfg.n_streams * sizeof(unsigned), stream));
     }
+    if (doDither && !cont) CPQ_CUDA(cudaMemsetAsync(ditherZ.p, 0, (size_t) this->nSeq * 12 * sizeof(double), stream));   // PsychoacousticDither::reset
     if (doDither && uniformsPerCh != T)
     {
         setError("process: dither enabled but cpq_set_dither_uniforms does not hold exactly T samples per channel");
@@ -1365,6 +1579,27 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         return CPQ_ERR_UNSUPPORTED;
     }
     int64_t K[CPQ_MAX_LAYERS] = {};
+    int64_t kOld[CPQ_MAX_LAYERS] = {};     // streaming: frames of the layer computed by earlier calls
+    int64_t xRows[CPQ_MAX_LAYERS] = {};    // rows per sequence in the X workspace (carried FDL rows + new frames)
+    if (strm)
+    {
+        if (l0Ring || directHead || !fullRange || nPeers > 0 || (doEq && anyMs) || winFirst != 0 || winCount >= 0 ||
+            (doConv && cfg.conv_boundary == CPQ_CONV_OUTER && (convBypassed || mix < 0.999)))
+        {
+            setError("process: streaming continuation does not cover non-power-of-two host blocks, the direct-form head, "
+                     "partition-range sharding / stream windows, Mid/Side bands or a dry/wet mix below 1");
+            return CPQ_ERR_UNSUPPORTED;
+        }
+        if (doConv)
+            for (int li = 1; li < plan.numLayers; ++li)
+                if (!gplan.blockIdentity[li])
+                {
+                    setError("process: streaming continuation needs a regular layer plan (this plan drops tail blocks)");
+                    return CPQ_ERR_UNSUPPORTED;
+                }
+        cpq_status st = ensureStreamState();
+        if (st != CPQ_OK) return st;
+    }
     int chunk = nSeq;
     if (doConv)
     {
@@ -1372,10 +1607,24 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         for (int li = 0; li < plan.numLayers; ++li)
         {
             const LayerPlan& l = plan.layers[li];
-            K[li] = gplan.framesNeeded[li];
-            perSeq += (size_t) K[li] * l.partSize * sizeof(double2) * 2;
-            if (li > 0 || l0Ring) perSeq += (size_t) K[li] * l.partSize * sizeof(double);
+            if (strm)
+            {
+                // every frame whose input is complete at the end of this call, minus those earlier calls computed
+                kOld[li] = cb0 * (int64_t) B / l.partSize;
+                K[li] = (cb0 + nCallbacks) * (int64_t) B / l.partSize - kOld[li];
+                xRows[li] = fdlRows[li] + K[li];
+                perSeq += (size_t) (xRows[li] + K[li]) * l.partSize * sizeof(double2);
+                if (li > 0) perSeq += (size_t) (carryFrames[li] + K[li]) * l.partSize * sizeof(double);
+            }
+            else
+            {
+                K[li] = gplan.framesNeeded[li];
+                xRows[li] = K[li];
+                perSeq += (size_t) K[li] * l.partSize * sizeof(double2) * 2;
+                if (li > 0 || l0Ring) perSeq += (size_t) K[li] * l.partSize * sizeof(double);
+            }
         }
+        if (strm) perSeq += (size_t) (histLen + T) * sizeof(double);
         chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) nSeq, cfg.workspace_bytes / std::max<size_t>(perSeq, 1)));
     }
     if (hostIO) chunk = std::max(1, std::min(chunk, (nSeq + 31) / 32));   // short pipeline fill/drain
@@ -1398,10 +1647,37 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         for (int li = 0; li < plan.numLayers; ++li)
         {
             const LayerPlan& l = plan.layers[li];
-            CPQ_CUDA(layer[li].X.ensure((size_t) chunk * K[li] * l.partSize));
-            CPQ_CUDA(layer[li].Y.ensure((size_t) chunk * K[li] * l.partSize));
-            if (li > 0 || l0Ring) CPQ_CUDA(layer[li].tail.ensure((size_t) chunk * K[li] * l.partSize + 2));
+            CPQ_CUDA(layer[li].X.ensure((size_t) chunk * xRows[li] * l.partSize));
+            CPQ_CUDA(layer[li].Y.ensure((size_t) chunk * std::max<int64_t>(K[li], 1) * l.partSize));
+            if (li > 0 || l0Ring) CPQ_CUDA(layer[li].tail.ensure((size_t) chunk * ((strm ? carryFrames[li] : 0) + K[li]) * l.partSize + 2));
         }
+    if (strm && doConv)
+    {
+        CPQ_CUDA(xcat.ensure((size_t) chunk * (histLen + T)));
+        // this call's slice of the gather plan, relative to the start of each layer's workspace stream
+        // (= the carried samples, then the new frames): position p of the layer's output stream sits at p - base
+        std::vector<int64_t> rel((size_t) nCallbacks);
+        for (int li = 1; li < plan.numLayers; ++li)
+        {
+            const int P = plan.layers[li].partSize;
+            const int64_t base = (kOld[li] - carryFrames[li]) * (int64_t) P;
+            const int64_t have = (int64_t) (carryFrames[li] + K[li]) * P;
+            for (int64_t c = 0; c < nCallbacks; ++c)
+            {
+                const int64_t sp = gplan.tailSrc[li][(size_t) (cb0 + c)];
+                rel[(size_t) c] = sp < 0 ? -1 : sp - base;
+                if (sp >= 0 && (sp - base < 0 || sp - base + B > have))
+                {
+                    setError("process: streaming continuation: the gather plan reads outside the carried tail window");
+                    return CPQ_ERR_UNSUPPORTED;
+                }
+            }
+            CPQ_CUDA(layer[li].tailSrc.ensure((size_t) nCallbacks));
+            CPQ_CUDA(cudaMemcpyAsync(layer[li].tailSrc.p, rel.data(), (size_t) nCallbacks * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+            CPQ_CUDA(cudaStreamSynchronize(stream));   // rel is reused for the next layer
+        }
+        gplanCallbacks = -1;   // the device copies of the plan are call-relative: rebuild before any other use
+    }
     const size_t nChunks = (size_t) ((nSeq + chunk - 1) / chunk);
     // event pool layout: [c*6 + 0..4] stage boundaries on the compute stream, [c*6 + 5] H2D done on the copy-in stream
     for (size_t i = 0; i < nChunks * 9 + 4; ++i) poolEvent(i);
@@ -1550,6 +1826,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             p.bandMask = bandMask.p + s0;
             p.setOfSeq = setOfSeq.p + s0;
             p.stateOut = stateOut.p + (size_t) s0 * CPQ_NUM_BANDS * 2;
+            if (cont) p.stateIn = p.stateOut;
             p.postMask = 0;
             p.finalClamp = 0;
             p.applyHeadroom = 0;
@@ -1563,6 +1840,15 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                                        (size_t) ns, cudaMemcpyDeviceToDevice, stream));
         if (doConv && !dryOnly)
         {
+            const int64_t catLen = (int64_t) histLen + T;
+            if (strm)
+            {
+                // [carried input history | this call's input]: the frames of this call reach back up to 2 P samples
+                CPQ_CUDA(cudaMemcpy2DAsync(xcat.p, (size_t) catLen * sizeof(double), inHist.p + (size_t) s0 * histLen, (size_t) histLen * sizeof(double),
+                                           (size_t) histLen * sizeof(double), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
+                CPQ_CUDA(cudaMemcpy2DAsync(xcat.p + histLen, (size_t) catLen * sizeof(double), ioC, (size_t) stride * sizeof(double),
+                                           (size_t) T * sizeof(double), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
+            }
             // ---- forward FFTs of every layer (all read the untouched input) ----
             for (int li = 0; li < plan.numLayers; ++li)
             {
@@ -1580,6 +1866,19 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 a.out = layer[li].X.p;
                 a.outFramesPerSeq = (int) K[li];
                 a.outFrameOffset = 0;
+                if (strm)
+                {
+                    a.src = xcat.p;
+                    a.srcStride = catLen;
+                    a.frameStart0 = (int64_t) histLen + (kOld[li] - 1) * (int64_t) l.partSize - cb0 * (int64_t) B;   // >= 0: histLen = 2 Pmax
+                    a.hi = catLen;
+                    a.outFramesPerSeq = (int) xRows[li];
+                    a.outFrameOffset = fdlRows[li];
+                    if (fdlRows[li] > 0)   // the FDL: spectra of the Q - 1 frames before this call's first one
+                        CPQ_CUDA(cudaMemcpy2DAsync(layer[li].X.p, (size_t) xRows[li] * l.partSize * sizeof(double2),
+                                                   fdl[li].p + (size_t) s0 * fdlRows[li] * l.partSize, (size_t) fdlRows[li] * l.partSize * sizeof(double2),
+                                                   (size_t) fdlRows[li] * l.partSize * sizeof(double2), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
+                }
                 a.tw = layer[li].tw.p;
                 a.ptw = layer[li].ptw.p;
                 a.scratch = layer[li].Y.p;   // free until the MAC writes it
@@ -1621,6 +1920,8 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 static const int fpcEnv = [] { const char* e = getenv("CPQ_MAC_FPC"); return e ? atoi(e) : 0; }();   // tuning knob
                 if (fpcEnv > 0 && fpcEnv % step == 0 && fpcEnv < fpc && K[li] <= 2 * step) fpc = fpcEnv;   // short layers only
                 a.framesPerCta = fpc;
+                a.hist = strm ? fdlRows[li] : 0;
+                a.xRows = (int) xRows[li];
                 a.ringRows = fpc <= step ? (step + (a.qEnd - a.qBegin) - 1 + kMacKT - 1) / kMacKT * kMacKT : macRingRows(a.qEnd - a.qBegin);
                 const size_t smem = macSmemBytes(a.qEnd - a.qBegin, a.ringRows);
                 if (smem > kMaxDynSmem)
@@ -1632,12 +1933,20 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 mac_kernel<<<grid, kMacThreads, smem, stream>>>(a);
                 ++launches;
                 CPQ_CUDA(cudaGetLastError());
+                if (strm && fdlRows[li] > 0)   // the FDL the next call starts from: the last Q - 1 rows of [carried | new]
+                    CPQ_CUDA(cudaMemcpy2DAsync(fdl[li].p + (size_t) s0 * fdlRows[li] * l.partSize, (size_t) fdlRows[li] * l.partSize * sizeof(double2),
+                                               layer[li].X.p + (size_t) K[li] * l.partSize, (size_t) xRows[li] * l.partSize * sizeof(double2),
+                                               (size_t) fdlRows[li] * l.partSize * sizeof(double2), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
             }
             cudaEventRecord(ce[2], stream);
             // ---- inverse FFTs: L0 in place into io, tails into their stream buffers ----
             for (int li = 0; li < plan.numLayers; ++li)
             {
                 const LayerPlan& l = plan.layers[li];
+                if (strm && li > 0)   // the delay line: tail samples computed by earlier calls that this call's callbacks still read
+                    CPQ_CUDA(cudaMemcpy2DAsync(layer[li].tail.p, (size_t) (carryFrames[li] + K[li]) * l.partSize * sizeof(double),
+                                               tailCarry[li].p + (size_t) s0 * carryFrames[li] * l.partSize, (size_t) carryFrames[li] * l.partSize * sizeof(double),
+                                               (size_t) carryFrames[li] * l.partSize * sizeof(double), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
                 if (K[li] == 0 || qb[li] >= qe[li]) continue;
                 InvArgs a {};
                 a.in = layer[li].Y.p;
@@ -1646,12 +1955,20 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                 a.totalFrames = (int64_t) ns * K[li];
                 a.out = (li == 0 && !l0Ring) ? ioC : layer[li].tail.p;
                 a.outStride = (li == 0 && !l0Ring) ? stride : (int64_t) K[li] * l.partSize;
+                if (strm && li > 0)
+                {
+                    a.out += (size_t) carryFrames[li] * l.partSize;
+                    a.outStride = (int64_t) (carryFrames[li] + K[li]) * l.partSize;
+                }
                 a.tw = layer[li].tw.p;
                 a.ptw = layer[li].ptw.p;
                 a.scratch = layer[li].X.p;   // the MAC has consumed it
                 cpq_status st = launchInv(ilog2(l.partSize), a);
                 if (st != CPQ_OK) return st;
             }
+            if (strm)   // input history for the next call: the last histLen samples of [history | input]
+                CPQ_CUDA(cudaMemcpy2DAsync(inHist.p + (size_t) s0 * histLen, (size_t) histLen * sizeof(double), xcat.p + T, (size_t) catLen * sizeof(double),
+                                           (size_t) histLen * sizeof(double), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
         }
         else
         {
@@ -1691,7 +2008,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             for (int li = 1; li < plan.numLayers; ++li)
             {
                 e.tail[li - 1] = layer[li].tail.p;
-                e.tailStride[li - 1] = (int64_t) K[li] * plan.layers[li].partSize;
+                e.tailStride[li - 1] = (int64_t) ((strm ? carryFrames[li] : 0) + K[li]) * plan.layers[li].partSize;
                 e.tailSrc[li - 1] = layer[li].tailSrc.p;
                 e.blockMap[li - 1] = layer[li].hasBlockMap ? layer[li].blockMap.p : nullptr;
                 e.tailPartLog2[li - 1] = ilog2(plan.layers[li].partSize);
@@ -1722,6 +2039,11 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         e.setOfSeq = setOfSeq.p ? setOfSeq.p + s0 : nullptr;   // absolute set indices
         e.stateOut = stateOut.p + (size_t) s0 * CPQ_NUM_BANDS * 2;
         e.postStateOut = postMask ? postState.p + (size_t) s0 * kEqPostStages * 2 : nullptr;
+        if (cont)
+        {
+            e.stateIn = e.stateOut;
+            e.postStateIn = e.postStateOut;
+        }
         if (limiterOn && !doDither) e.limFlag = limFlag.p + s0 / cfg.n_channels;
         if (needsDry)
         {
@@ -1760,6 +2082,15 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             cpq_status st = runEq(e, s0, ns);
             if (st != CPQ_OK) return st;
         }
+        if (strm && doConv && !dryOnly)
+            for (int li = 1; li < plan.numLayers; ++li)
+            {
+                const LayerPlan& l = plan.layers[li];
+                if (K[li] == 0) continue;   // nothing new: the carried window is unchanged
+                CPQ_CUDA(cudaMemcpy2DAsync(tailCarry[li].p + (size_t) s0 * carryFrames[li] * l.partSize, (size_t) carryFrames[li] * l.partSize * sizeof(double),
+                                           layer[li].tail.p + (size_t) K[li] * l.partSize, (size_t) (carryFrames[li] + K[li]) * l.partSize * sizeof(double),
+                                           (size_t) carryFrames[li] * l.partSize * sizeof(double), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
+            }
         if (doDither)
         {
             DitherArgs d {};
@@ -1774,6 +2105,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             d.z = ditherZ.p + (size_t) s0 * 12;
             d.finalClamp = outCfg.finalClamp ? (limiterOn ? 1 : 3) : 0;
             d.nch = cfg.n_channels;
+            d.seqBase = s0;
             dither_kernel<<<(unsigned) ((ns + 31) / 32), 32, kDitherSmemBytes, stream>>>(d);
             ++launches;
             CPQ_CUDA(cudaGetLastError());
@@ -1790,6 +2122,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             la.release = std::exp(-1.0 / (cfg.sample_rate * limiterMs * 0.001));   // SimplePeakLimiter::prepare
             la.clamp = outCfg.finalClamp ? 1 : 0;
             la.envOut = limEnv.p + s0 / cfg.n_channels;
+            la.envIn = cont ? la.envOut : nullptr;
             limiter_kernel<<<(unsigned) ((la.nStreams + 31) / 32), 32, 0, stream>>>(la);
             ++launches;
             CPQ_CUDA(cudaGetLastError());
@@ -1832,6 +2165,11 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
     }
     if (doConv) outerPending = (cfg.conv_boundary == CPQ_CONV_OUTER && !fullRange);
     else outerPending = false;
+    if (strm)
+    {
+        absCallback += nCallbacks;
+        contValid = true;
+    }
 
     if (hostIO)
     {
@@ -1959,14 +2297,35 @@ void cpq_destroy(cpq_handle h)
 cpq_status cpq_reset(cpq_handle h)
 {
     if (!h) return CPQ_ERR_INVALID;
-    cudaSetDevice(h->cfg.device);
-    cudaMemsetAsync(h->ditherZ.p, 0, (size_t) h->nSeq * 12 * sizeof(double), h->stream);
-    cudaMemsetAsync(h->stateOut.p, 0, (size_t) h->nSeq * CPQ_NUM_BANDS * 2 * sizeof(double), h->stream);
-    cudaStreamSynchronize(h->stream);
-    h->outerPending = false;
-    for (auto& e : h->eqSets) e.events.clear();
-    h->gainTabCallbacks = -1;
-    return CPQ_OK;
+    return h->resetState();
+}
+
+cpq_status cpq_set_streaming(cpq_handle h, int enable)
+{
+    if (!h) return CPQ_ERR_INVALID;
+    h->streaming = enable != 0;
+    return h->resetState();
+}
+
+int64_t cpq_stream_position(cpq_handle h) { return h ? h->absCallback * (int64_t) h->cfg.block_size : -1; }
+
+size_t cpq_state_size(cpq_handle h)
+{
+    if (!h || !h->streaming) return 0;
+    if (h->ensureStreamState() != CPQ_OK) return 0;
+    return h->stateBytes();
+}
+
+cpq_status cpq_export_state(cpq_handle h, void* dst, size_t bytes)
+{
+    if (!h) return CPQ_ERR_INVALID;
+    return h->exportState(dst, bytes);
+}
+
+cpq_status cpq_import_state(cpq_handle h, const void* src, size_t bytes)
+{
+    if (!h) return CPQ_ERR_INVALID;
+    return h->importState(src, bytes);
 }
 
 cpq_status cpq_set_impulse(cpq_handle h, int stream, int channel, const double* ir, int ir_len, double scale,

@@ -125,6 +125,8 @@ struct EqArgs
     const int* setOfSeq;    // [nSeq]
     const double* sat;      // [nSets]
     double* stateOut;       // [nSeq][20][2] final states
+    const double* stateIn;  // nullable [nSeq][20][2]: states at the start of the call (streaming continuation); null = Reset
+    const double* postStateIn;   // nullable [nSeq][kEqPostStages][2]: the same for the output stages
     // linear output stages (stage index 20..23); run when postMask != 0, also without the EQ bands
     const double* postc;    // [kEqPostStages][kEqcStride]
     unsigned postMask;      // bit i = post stage i enabled
@@ -786,6 +788,13 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                 if (warp == 0)
                 {
                     double2 sv = make_double2(0.0, 0.0);   // Reset state for the first tile
+                    if (!recIn && run == 0)
+                    {
+                        // streaming continuation: the state the previous call left behind
+                        const double* si = b < CPQ_NUM_BANDS ? (a.stateIn ? a.stateIn + ((size_t) seq * CPQ_NUM_BANDS + b) * 2 : nullptr)
+                                                             : (a.postStateIn ? a.postStateIn + ((size_t) seq * kEqPostStages + (b - CPQ_NUM_BANDS)) * 2 : nullptr);
+                        if (si) sv = make_double2(ld_cg_f64(si), ld_cg_f64(si + 1));   // the same buffer receives the final state: no read-only path
+                    }
                     if (recIn)
                     {
                         sv = (preBand == b) ? pre : ld_volatile_f64x2(recIn + b);
@@ -1151,6 +1160,7 @@ struct AgcArgs
     const double* gainConst;  // [nSets]
     const int* setOfSeq;      // [nStreams * nch]
     double* stateOut;         // nullable [nStreams][3] envIn, envOut, gain after the last callback
+    const double* stateIn;    // nullable [nStreams][3]: the same at the start of the call (streaming continuation)
     int nStreams, nch;
     int64_t nCallbacks;
     double blockN;            // samples per callback
@@ -1169,6 +1179,12 @@ __global__ void agc_kernel(AgcArgs a)
         return;
     }
     double envIn = 0.0, envOut = 0.0, cur = 1.0;   // rtAgc*Shadow after the reset prepareToPlay requests
+    if (a.stateIn)
+    {
+        envIn = a.stateIn[(size_t) st * 3];
+        envOut = a.stateIn[(size_t) st * 3 + 1];
+        cur = a.stateIn[(size_t) st * 3 + 2];
+    }
     for (int64_t c = 0; c < a.nCallbacks; ++c)
     {
         double inRms = 0.0, outRms = 0.0;
@@ -1220,13 +1236,15 @@ struct LimiterArgs
     double release;         // exp(-1 / (sr * releaseSeconds))
     int clamp;              // +-kOutputHeadroom after the limiter
     double* envOut;         // nullable [nStreams]
+    const double* envIn;    // nullable [nStreams]: envelope at the start of the call (streaming continuation); null = 1.0
 };
 
 __global__ void limiter_kernel(LimiterArgs a)
 {
     const int st = blockIdx.x * blockDim.x + threadIdx.x;
     if (st >= a.nStreams) return;
-    if (!a.flag[st])
+    const double env0 = a.envIn ? a.envIn[st] : 1.0;
+    if (!a.flag[st] && env0 == 1.0)   // identity: no sample can engage the limiter and the envelope rests at 1
     {
         if (a.envOut) a.envOut[st] = 1.0;
         return;
@@ -1234,7 +1252,7 @@ __global__ void limiter_kernel(LimiterArgs a)
     constexpr double thr = 0.8413951287507587, knee = 0.108748, clipStart = thr - knee * 0.5, hr = 0.8912509381337456;
     double* L = a.io + (size_t) st * a.nch * a.stride;
     double* R = a.nch > 1 ? L + a.stride : nullptr;
-    double env = 1.0;
+    double env = env0;
     for (int64_t i = 0; i < a.T; i += 2)   // T is even (a multiple of the block)
     {
         double2 l = *reinterpret_cast<const double2*>(L + i);
@@ -1477,6 +1495,7 @@ struct DitherArgs
     int64_t T;
     int nSeq;
     int nch;                  // channels per stream: lane role = left channel of a stereo stream or not
+    int seqBase;              // absolute index of this launch's first sequence (a chunk may start on a right channel)
     const double* uniforms;   // [nSeq][2*T]
     double coeff[12];
     double scale, invScale;
@@ -1504,7 +1523,7 @@ __global__ void __launch_bounds__(32) dither_kernel(DitherArgs a)
     const int nLocal = min(32, a.nSeq - seq0);
     const int seq = seq0 + min(lane, nLocal - 1);          // idle lanes shadow the last sequence, they never store
     const bool live = lane < nLocal;
-    const bool roleLeft = a.nch == 2 && (seq % 2) == 0;
+    const bool roleLeft = a.nch == 2 && ((a.seqBase + seq) % 2) == 0;
     const int64_t nTiles = (a.T + kDthTile - 1) / kDthTile;
 
     auto issue = [&](int64_t tile, int buf) {

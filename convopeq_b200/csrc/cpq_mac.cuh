@@ -40,6 +40,9 @@ struct MacArgs
     int seqBase;         // absolute index of this launch's first sequence (sequence chunks)
     int framesPerCta;    // multiple of kMacSuper
     int ringRows;        // >= 2*kMacSuper + (qEnd - qBegin) - 1
+    int hist;            // rows of X stored before frame 0 of each sequence (streaming continuation: the carried FDL, frames
+                         // -hist..-1); frames below -hist are the zero history of a Reset engine.  0 in the one-shot form
+    int xRows;           // rows per sequence in X = hist + K
 };
 
 constexpr int kMacBins = 32;
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(kMacThreads, CPQ_MAC_MINBLOCKS) mac_kernel(Mac
     const int kc0 = blockIdx.y * a.framesPerCta;
     const int kc1 = min(a.K, kc0 + a.framesPerCta);
     const int hrow = a.hSeqMod > 0 ? ((a.seqBase + seq) % a.hSeqMod) : seq;
-    const double2* __restrict__ X = a.X + (size_t) seq * a.K * a.P + m0;
+    const double2* __restrict__ X = a.X + ((size_t) seq * a.xRows + a.hist) * a.P + m0;   // frame 0
     const double2* __restrict__ H = a.H + (size_t) hrow * a.hSeqStride + (size_t) a.qBegin * a.P + m0;
     double2* __restrict__ Y = a.Y + (size_t) seq * a.K * a.P + m0 + ml;
     const int ringBytes = R * kMacRowBytes;
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(kMacThreads, CPQ_MAC_MINBLOCKS) mac_kernel(Mac
     // Stage rows [f0, f1) of X into the ring (and, with withH, the H tile): frames before 0 are the zero history of a
     // Reset engine (plain stores by all threads), frames in [0, K) one bulk copy each, issued by warp 0.
     auto stage = [&](int f0, int f1, bool withH) {
-        const int z1 = min(f1, 0);
+        const int z1 = min(f1, -a.hist);
         if (f0 < z1)
         {
             const int n = (z1 - f0) * kMacBins;
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(kMacThreads, CPQ_MAC_MINBLOCKS) mac_kernel(Mac
         }
         // bulk copies: 8 rows per warp (lanes 0..7), H rows on lanes 8..15; the expected byte count is posted by thread 0
         // (the transaction count may run negative until then, the phase cannot complete before that arrive)
-        const int c0 = max(f0, 0), c1 = min(f1, a.K);
+        const int c0 = max(f0, -a.hist), c1 = min(f1, a.K);
         const int nRows = max(c1 - c0, 0);
         if (tid == 0) mbar_arrive_expect_tx(bar, (unsigned) (nRows + (withH ? nq : 0)) * kMacRowBytes);
 #if CPQ_MAC_STAGE1
@@ -312,7 +315,8 @@ __global__ void __launch_bounds__(kMacThreads, CPQ_MAC_MINBLOCKS) mac_kernel(Mac
             if (i0 < i1)
             {
                 int slot = (c0 + i0) % R;
-                const double2* src = X + (size_t) (c0 + i0) * a.P;
+                if (slot < 0) slot += R;
+                const double2* src = X + (int64_t) (c0 + i0) * a.P;
                 for (int i = i0; i < i1; ++i)
                 {
                     bulk_g2s(ring + slot * kMacBins, src, kMacRowBytes, bar);
@@ -333,7 +337,9 @@ __global__ void __launch_bounds__(kMacThreads, CPQ_MAC_MINBLOCKS) mac_kernel(Mac
             for (int i = g * 8 + ml; i < nRows; i += 8 * kMacGroups)
             {
                 const int f = c0 + i;
-                bulk_g2s(ring + (f % R) * kMacBins, X + (size_t) f * a.P, kMacRowBytes, bar);
+                int slot = f % R;
+                if (slot < 0) slot += R;
+                bulk_g2s(ring + slot * kMacBins, X + (int64_t) f * a.P, kMacRowBytes, bar);
             }
         }
         else if (withH && ml < 16)

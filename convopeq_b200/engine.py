@@ -237,6 +237,23 @@ class ConvoPeqEngine:
         self._check(self.lib.cpq_get_timings(self.h, C.byref(t)))
         return t
 
+    # ---- streaming continuation (cpq_set_streaming): Add/Get/EQ state carried between calls ----
+    def set_streaming(self, enable: bool = True):
+        self._check(self.lib.cpq_set_streaming(self.h, int(enable)))
+
+    def stream_position(self) -> int:
+        return int(self.lib.cpq_stream_position(self.h))
+
+    def export_state(self) -> np.ndarray:
+        n = int(self.lib.cpq_state_size(self.h))
+        blob = np.empty(n, dtype=np.uint8)
+        self._check(self.lib.cpq_export_state(self.h, blob.ctypes.data, n))
+        return blob
+
+    def import_state(self, blob: np.ndarray):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self._check(self.lib.cpq_import_state(self.h, blob.ctypes.data, blob.size))
+
     def eq_state(self, stream: int) -> np.ndarray:
         out = np.zeros((self.cfg.n_channels, capi.NUM_BANDS, 2))
         self._check(self.lib.cpq_get_eq_state(self.h, stream, out.ctypes.data_as(_dp)))

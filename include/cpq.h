@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define CPQ_ABI_VERSION 3
+#define CPQ_ABI_VERSION 4
 #define CPQ_NUM_BANDS 20        /* EQProcessor::NUM_BANDS, eqprocessor/EQProcessor.h:153 */
 #define CPQ_MAX_LAYERS 3        /* MKLNonUniformConvolver::kNumLayers, MKLNonUniformConvolver.h:391 */
 #define CPQ_NS_ORDER 12         /* PsychoacousticDither::NS_ORDER, PsychoacousticDither.h:60 */
@@ -144,8 +144,30 @@ void cpq_config_default(cpq_config* out);
 cpq_status cpq_create(const cpq_config* cfg, cpq_handle* out);
 void cpq_destroy(cpq_handle h);
 
-/* MKLNonUniformConvolver::Reset (MKLNonUniformConvolver.cpp:1693) + EQ state clear + dither state clear. */
+/* MKLNonUniformConvolver::Reset (MKLNonUniformConvolver.cpp:1693) + EQ / output-stage state clear + dither state clear.
+ * In the default one-shot mode every process call starts from this state anyway; in streaming mode (below) this is the
+ * call that starts a new stream. */
 cpq_status cpq_reset(cpq_handle h);
+
+/* Streaming continuation: the reference's path is a stream -- Add/Get keep the FDL, the partial input frame, the
+ * accumulators and the delay-line cursors of every layer between callbacks (MKLNonUniformConvolver.h:288-365, .cpp:1407-1548;
+ * cleared only by Reset, :1693), EQProcessor keeps filterState (EQProcessor.h:637) and the AGC envelopes, the limiter its
+ * envelope, the dither its error history.  With enable = 1 every cpq_process / cpq_process_f32 / cpq_process_device call
+ * continues where the previous one stopped: a signal processed in segments of any whole number of callbacks gives the
+ * convolver output of the one-shot call bit for bit, and the EQ / output-stage output to rounding (the blocked scan's tiles
+ * start at the segment boundary; identical bits when the segments are multiples of 8192 samples).  Carried per
+ * stream-channel: the last 2 Pmax input samples, Q - 1 input spectra per layer, the tail samples Get has not read yet, and
+ * the stage states.  cpq_reset returns to the Reset state; enable = 0 (default) makes every call start from Reset again.
+ * Not covered (CPQ_ERR_UNSUPPORTED from the process call): non-power-of-two host blocks, the direct-form head, partition
+ * ranges / stream windows, Mid/Side bands, a dry/wet mix below 1, plans that drop tail blocks; total-gain events scheduled
+ * with cpq_schedule_total_gain must complete their ramp inside the call they start in. */
+cpq_status cpq_set_streaming(cpq_handle h, int enable);
+int64_t cpq_stream_position(cpq_handle h);            /* samples per channel processed since Reset (streaming mode) */
+/* The carried state as one host blob (chaining segments across handles / processes / GPUs): export after any
+ * call, import into a handle with the same configuration, impulses and EQ settings (CPQ_ERR_GEOMETRY otherwise), continue. */
+size_t cpq_state_size(cpq_handle h);                  /* 0 when the handle is not in streaming mode */
+cpq_status cpq_export_state(cpq_handle h, void* dst, size_t bytes);
+cpq_status cpq_import_state(cpq_handle h, const void* src, size_t bytes);
 
 /* ---- prepare ----------------------------------------------------------------------------- */
 /* MKLNonUniformConvolver::SetImpulse(impulse, irLen, blockSize, scale, enableDirectHead=false, filterSpec)
@@ -317,6 +339,11 @@ cpq_status cpq_get_timings(cpq_handle h, cpq_timings* out);   /* CUDA-event time
 cpq_status cpq_get_eq_state(cpq_handle h, int stream, double* out /* [n_channels][20][2] ic1eq, ic2eq */);
 void* cpq_cuda_stream(cpq_handle h);                 /* cudaStream_t the kernels are launched on */
 int64_t cpq_kernel_launch_count(cpq_handle h);       /* launches since create */
+
+/* Diagnostics (bench.py's FP64 roofline denominator): measured DFMA throughput in TFLOP/s (2 flops per DFMA) of `device`
+ * over `iters` dependent-chain iterations per thread, and the dependent-issue latency of one DFMA in cycles; < 0 on error. */
+double cpq_probe_dfma_tflops(int device, int iters);
+double cpq_probe_dfma_latency(int device);
 
 /* Host-only: the layer plan + per-callback gather plan without a device (used by tests and by
  * INTEGRATION.md's binding to validate geometry). src_offsets (nullable) receives, for each layer >= 1 and
