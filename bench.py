@@ -11,6 +11,7 @@ data-path collective (weak scaling: --streams is per GPU).
   e2e        the same through the C-ABI host entry point cpq_process: pinned host buffers, H2D + D2H inside
   roofline   dominant kernel vs MEASURED_PEAKS.json HBM GB/s using the algorithmic 16 B / channel-sample
   cpu_baseline  the reference's own CPU path (oracle/_ref) on this box's host cores, bounded sample
+  other_workloads  BASELINE configs 1, 2, 3, 5 and cfg4 with 24-bit dither: device-resident and host-buffer times (rank 0)
 
 `--impl reference` times the reference CPU path alone (rank 0 only) on the same config/metric.
 """
@@ -50,6 +51,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_workloads legs (cfg1a, cfg2, cfg3, cfg5, dither)")
     return ap.parse_args()
 
 
@@ -201,6 +203,192 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# small helpers shared by the headline and the other workloads
+# ------------------------------------------------------------------------------------------------
+def _timed(stream, fn):
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    fn()
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def measure_workload(eng, x_dev, T, stages, steps=3, warm=2, host=True):
+    """Device-resident and host-buffer time of one engine on the input x_dev [n_seq, T] (restored before every step)."""
+    import torch
+    dev = x_dev.device
+    stream = torch.cuda.ExternalStream(eng.cuda_stream(), device=dev)
+    io = torch.empty_like(x_dev)
+    out = {}
+
+    def dstep():
+        io.copy_(x_dev)
+        torch.cuda.synchronize()
+        return _timed(stream, lambda: eng.process_device(io.data_ptr(), T, T, stages))
+
+    for _ in range(warm):
+        dstep()
+    ms = [dstep() for _ in range(steps)]
+    out["device_ms"] = sum(ms) / len(ms)
+    cs = float(x_dev.shape[0]) * T
+    out["channel_samples"] = cs
+    out["value"] = cs / (out["device_ms"] * 1e-3)
+    out["launches_per_step"] = int(eng.timings().kernel_launches)
+    if host:
+        h = torch.empty(x_dev.shape, dtype=torch.float64).pin_memory()
+
+        def hstep():
+            h.copy_(x_dev)
+            torch.cuda.synchronize()
+            return _timed(stream, lambda: eng.process_host_ptrs(h.data_ptr(), T, T, stages))
+
+        hstep()
+        ms = [hstep() for _ in range(steps)]
+        out["e2e_ms"] = sum(ms) / len(ms)
+        out["e2e_value"] = cs / (out["e2e_ms"] * 1e-3)
+        del h
+    del io
+    return out
+
+
+def other_workloads(local, dev, cfg4_eng, cfg4_x, T4):
+    """BASELINE configs 1, 2, 3, 5 on one GPU, plus cfg4 with the 24-bit dither branch.  Parity of each at this size is the
+    job of tests/test_full_size.py; these are the timings that go with them."""
+    import torch
+    from convopeq_b200 import capi
+    from convopeq_b200.engine import ConvoPeqEngine
+    from tests import signals
+    res = {}
+    g = torch.Generator(device=dev)
+    g.manual_seed(77)
+
+    def noise(n_seq, T):
+        return torch.randn(n_seq, T, device=dev, dtype=torch.float64, generator=g) * 0.1
+
+    def guard(name, fn):
+        try:
+            res[name] = fn()
+        except Exception as ex:   # one failing leg must not take the contract line with it
+            res[name] = {"error": f"{type(ex).__name__}: {ex}"}
+
+    def cfg1(uniform):
+        T = T_FULL
+        eng = ConvoPeqEngine(1, 2, 48000.0, 512, T, device=local, uniform_partitions=uniform)
+        for ch in range(2):
+            eng.set_impulse(0, ch, signals.synth_ir(65536, 2 + ch), 1.0, None)
+        r = measure_workload(eng, noise(2, T), T, capi.STAGE_CONV)
+        lay = eng.layout()
+        r["plan"] = " + ".join(f"{lay.layers[i].num_parts_ir}x{lay.layers[i].part_size}" for i in range(lay.num_layers))
+        r["workload"] = ("cfg1b: uniform-partition extension (not a reference mode), " if uniform else "cfg1a: the reference's own plan, ") + \
+            "stereo 48 kHz, 65,536-tap IR, block 512, 10 s noise, convolver only, filterSpec = nullptr"
+        eng.close()
+        return r
+
+    def cfg2():
+        T = 2880000 // 512 * 512
+        eng = ConvoPeqEngine(1, 2, 48000.0, 512, T, device=local)
+        eng.set_eq(0, signals.to_band(signals.band_params(seed=7)), 0.2, 0.0)
+        xl, xr = signals.log_sweep(T, 48000.0)
+        x = torch.from_numpy(np.stack([xl, xr])).to(dev)
+        r = measure_workload(eng, x, T, capi.STAGE_EQ)
+        r["workload"] = "cfg2: stereo 48 kHz, 20-band cascade only, 60 s log sweep (2 sequences: all parallelism from the tile chain)"
+        eng.close()
+        return r
+
+    def cfg3(block):
+        sr, T = 96000.0, 960000 // block * block
+        eng = ConvoPeqEngine(1, 2, sr, block, T, device=local, conv_boundary=capi.CONV_OUTER)
+        spec = capi.default_filter_spec(sample_rate=sr)
+        for ch in range(2):
+            eng.set_impulse(0, ch, signals.synth_ir(262144, 20 + ch), 1.0, spec)
+        eng.set_eq(0, signals.to_band(signals.band_params(seed=7)))
+        eng.set_epilogue(1.0, 0)
+        r = measure_workload(eng, noise(2, T), T, capi.STAGE_ALL)
+        lay = eng.layout()
+        r["plan"] = " + ".join(f"{lay.layers[i].num_parts_ir}x{lay.layers[i].part_size}" for i in range(lay.num_layers))
+        r["workload"] = f"cfg3: stereo 96 kHz, 262,144-tap IR, block {block}, conv -> EQ -> makeup+headroom, 10 s noise"
+        eng.close()
+        return r
+
+    def cfg5():
+        sr, T = 192000.0, 1920000 // 512 * 512
+        eng = ConvoPeqEngine(4, 2, sr, 512, T, device=local, conv_boundary=capi.CONV_OUTER, shared_ir=True)
+        spec = capi.default_filter_spec(sample_rate=sr)
+        for ch in range(2):
+            eng.set_impulse(-1, ch, signals.synth_ir(2097152, 40 + ch), 1.0, spec)
+        for s_ in range(4):
+            eng.set_eq(s_, signals.to_band(signals.band_params(seed=7 + s_)))
+        eng.set_epilogue(1.0, 0)
+        r = measure_workload(eng, noise(8, T), T, capi.STAGE_ALL)
+        lay = eng.layout()
+        r["plan"] = " + ".join(f"{lay.layers[i].num_parts_ir}x{lay.layers[i].part_size}" for i in range(lay.num_layers))
+        r["workload"] = "cfg5 on ONE GPU: 192 kHz, 8 channels, 2,097,152-tap IR, block 512, conv -> EQ -> makeup+headroom, 10 s noise"
+        eng.close()
+        return r
+
+    def dither():
+        n_seq = cfg4_x.shape[0]
+        u = torch.rand(n_seq, 2 * T4, device=dev, dtype=torch.float64, generator=g)
+        cfg4_eng.set_epilogue(1.0, 24)
+        cfg4_eng.set_dither_uniforms_device(u.data_ptr(), T4)
+        try:
+            r = measure_workload(cfg4_eng, cfg4_x, T4, capi.STAGE_ALL, steps=2, warm=1, host=False)
+        finally:
+            cfg4_eng.set_epilogue(1.0, 0)
+        sm_hz = 1.9e9
+        r["serial_floor_ms"] = T4 * 130.0 / sm_hz * 1e3
+        r["workload"] = ("cfg4 with the 24-bit dither branch (PsychoacousticDither, injected uniforms resident on the device): the shaper is "
+                         "one dependent chain of 16 FP64 operations per sample and sequence (about 130 cycles), so T x 130 cycles is the "
+                         "floor of that stage whatever the batch; it runs on side streams beside the next chunks' transforms")
+        del u
+        return r
+
+    guard("cfg1a", lambda: cfg1(False))
+    guard("cfg1b_uniform_extension", lambda: cfg1(True))
+    guard("cfg2", cfg2)
+    guard("cfg3_block512", lambda: cfg3(512))
+    guard("cfg3_block256", lambda: cfg3(256))
+    guard("cfg5_one_gpu", cfg5)
+    guard("cfg4_dither24", dither)
+    return res
+
+
+def pcie_duplex_ceiling(host, n_seq, T, dev, barrier, world):
+    """What this box's host <-> device path delivers with nothing else going on: the whole pinned buffer down and up at the
+    same time on two streams in 32 pieces (the copy pattern of cpq_process), every rank at once.  GB/s each way, whole job."""
+    import torch
+    import torch.distributed as dist
+    d_in = torch.empty(n_seq, T, device=dev, dtype=torch.float64)
+    d_out = torch.zeros(n_seq, T, device=dev, dtype=torch.float64)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    per = (n_seq + 31) // 32
+    best = None
+    for _ in range(3):
+        barrier()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        s1.wait_event(e0)
+        s2.wait_event(e0)
+        for r0 in range(0, n_seq, per):
+            with torch.cuda.stream(s1):
+                d_in[r0:r0 + per].copy_(host[r0:r0 + per], non_blocking=True)
+            with torch.cuda.stream(s2):
+                host[r0:r0 + per].copy_(d_out[r0:r0 + per], non_blocking=True)
+        e1.record(s1)
+        e2.record(s2)
+        torch.cuda.synchronize()
+        ms = max(e0.elapsed_time(e1), e0.elapsed_time(e2))
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best = float(t.item()) if best is None else min(best, float(t.item()))
+    del d_in, d_out
+    return n_seq * T * 8.0 * world / (best * 1e-3) / 1e9, best
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     args = parse()
     if args.impl == "reference":
@@ -220,14 +408,13 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (convopeq_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         # one process per GPU, every rank streaming over PCIe in the e2e leg: keep this rank's pinned buffers and threads on
-        # the GPU's own NUMA node
+        # the GPU's own NUMA node; when every GPU reports the same CPU list (single-node boxes) give each rank its own slice
         from convopeq_b200.dist import bind_to_gpu_numa_node
-        numa_cpus = bind_to_gpu_numa_node(local)
-    else:
-        numa_cpus = None
+        numa_cpus = bind_to_gpu_numa_node(local, local_rank=local, local_world=world)
 
     S, T = args.streams, args.samples // BLOCK * BLOCK
     n_seq = 2 * S
@@ -264,12 +451,13 @@ def main():
     def step_device():
         io_dev.copy_(x_dev)                      # restore the in-place buffer (not timed)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        eng.process_device(io_dev.data_ptr(), T, T, capi.STAGE_ALL)
-        e1.record(stream)
-        e1.synchronize()
-        return e0.elapsed_time(e1)
+        return _timed(stream, lambda: eng.process_device(io_dev.data_ptr(), T, T, capi.STAGE_ALL))
+
+    def allmax(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -291,28 +479,32 @@ def main():
     if ncu_range:
         torch.cuda.profiler.stop()
     sampler.end()
-    ms_local = sum(step_ms) / len(step_ms)
-    ms = torch.tensor([ms_local], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms.item())
+    ms_per_step = allmax(sum(step_ms) / len(step_ms))
     total_cs = float(n_seq) * T * world
     value = total_cs / (ms_per_step * 1e-3)
+
+    # ---- strong scaling of the same job (BASELINE cfg4 words it as 1,024 streams in total): each rank takes streams/world ----
+    strong = None
+    if world > 1 and S % world == 0:
+        eng.set_stream_window(0, S // world)
+        step_device()
+        barrier()
+        s_ms = [step_device() for _ in range(min(args.steps, 3))]
+        barrier()
+        eng.set_stream_window(0, -1)
+        sm = allmax(sum(s_ms) / len(s_ms))
+        strong = {"value": float(n_seq) * T / (sm * 1e-3), "unit": UNIT, "ms_per_step": sm, "streams_total": S,
+                  "streams_per_gpu": S // world, "note": "strong scaling: the 1,024-stream job divided over the ranks, device-resident"}
 
     # ---- e2e through the host entry point ----
     e2e = None
     if not args.no_e2e:
         host = torch.empty(n_seq, T, dtype=torch.float64).pin_memory()
-        host.copy_(x_dev)
-        torch.cuda.synchronize()
 
         def step_host():
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            eng.process_host_ptrs(host.data_ptr(), T, T, capi.STAGE_ALL)
-            e1.record(stream)
-            e1.synchronize()
-            return e0.elapsed_time(e1)
+            host.copy_(x_dev)                    # every step sees the same input as the device-resident steps (not timed)
+            torch.cuda.synchronize()
+            return _timed(stream, lambda: eng.process_host_ptrs(host.data_ptr(), T, T, capi.STAGE_ALL))
 
         step_host()
         barrier()
@@ -320,44 +512,68 @@ def main():
         e_ms = [step_host() for _ in range(args.steps)]
         barrier()
         sampler.end()
-        em = torch.tensor([sum(e_ms) / len(e_ms)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(em, op=dist.ReduceOp.MAX)
+        em = allmax(sum(e_ms) / len(e_ms))
         te = eng.timings()
-        e2e = {"value": total_cs / (float(em.item()) * 1e-3), "unit": UNIT,
+        e2e = {"value": total_cs / (em * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(n_seq * T * 8 * world), "d2h_bytes_per_step": int(n_seq * T * 8 * world),
-               "ms_per_step": float(em.item()), "h2d_ms": te.h2d_ms, "d2h_ms": te.d2h_ms,
-               "note": "steps run in place on the pinned host buffer (each step's output is the next step's input)"}
+               "ms_per_step": em, "h2d_ms": te.h2d_ms, "d2h_ms": te.d2h_ms,
+               "note": "cpq_process in place on a pinned host buffer that is refilled with the same input before every step"}
+        # what the box's host <-> device path can do at all, every rank at once: the e2e leg is bound by it, not by a kernel
+        try:
+            ceil_gbs, ceil_ms = pcie_duplex_ceiling(host, n_seq, T, dev, barrier, world)
+            e2e["pcie_ceiling_gbs"] = ceil_gbs
+            e2e["pcie_ceiling_ms"] = ceil_ms
+            e2e["achieved_gbs_each_way"] = n_seq * T * 8.0 * world / (em * 1e-3) / 1e9
+            e2e["frac_of_ceiling"] = e2e["achieved_gbs_each_way"] / ceil_gbs
+            e2e["pcie_note"] = ("ceiling = the same pinned buffer copied down and up simultaneously on two streams in 32 pieces by plain "
+                                "cudaMemcpyAsync, all ranks at once, best of 3, whole-job GB/s each way")
+        except Exception as ex:
+            e2e["pcie_ceiling_error"] = f"{type(ex).__name__}: {ex}"
         del host
+        # informational: a pageable host buffer (what a reference-side caller that did not pin its memory passes)
+        if world == 1:
+            try:
+                pg = np.empty((n_seq, T), dtype=np.float64)
+                pg[...] = 0.05
+                p_ms = _timed(stream, lambda: eng.process(pg, capi.STAGE_ALL))
+                e2e["pageable_host_buffers"] = {"value": total_cs / (p_ms * 1e-3), "ms_per_step": p_ms,
+                                                "note": "one cpq_process call on an unpinned numpy buffer (the driver stages pageable copies)"}
+                del pg
+            except Exception as ex:
+                e2e["pageable_host_buffers"] = {"error": f"{type(ex).__name__}: {ex}"}
         # informational: the same call with FP32 host buffers (hosts that hand the application float blocks): FP32 on the
         # wire, FP64 arithmetic.  Not the headline -- BASELINE's metric is the FP64 interface above.
         try:
             hostf = torch.empty(n_seq, T, dtype=torch.float32).pin_memory()
-            hostf.copy_(x_dev)
-            torch.cuda.synchronize()
 
             def step_host_f32():
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                eng.process_f32_host_ptrs(hostf.data_ptr(), T, T, capi.STAGE_ALL)
-                e1.record(stream)
-                e1.synchronize()
-                return e0.elapsed_time(e1)
+                hostf.copy_(x_dev)
+                torch.cuda.synchronize()
+                return _timed(stream, lambda: eng.process_f32_host_ptrs(hostf.data_ptr(), T, T, capi.STAGE_ALL))
 
             step_host_f32()
             barrier()
             f_ms = [step_host_f32() for _ in range(min(args.steps, 3))]
             barrier()
-            fm = torch.tensor([sum(f_ms) / len(f_ms)], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(fm, op=dist.ReduceOp.MAX)
-            e2e["f32_host_buffers"] = {"value": total_cs / (float(fm.item()) * 1e-3), "ms_per_step": float(fm.item()),
+            fm = allmax(sum(f_ms) / len(f_ms))
+            e2e["f32_host_buffers"] = {"value": total_cs / (fm * 1e-3), "ms_per_step": fm,
                                        "h2d_bytes_per_step": int(n_seq * T * 4 * world), "d2h_bytes_per_step": int(n_seq * T * 4 * world),
                                        "note": "cpq_process_f32: FP32 wire format, FP64 arithmetic; informational, not the headline"}
             del hostf
         except Exception as ex:   # never let the extra leg break the contract line
             e2e["f32_host_buffers"] = {"error": f"{type(ex).__name__}: {ex}"}
     clocks = sampler.stop()
+
+    others = None
+    if not args.no_others and world == 1:
+        others = other_workloads(local, dev, eng, x_dev, T)
+    cfg5_sharded = None
+    if not args.no_others and world > 1:
+        try:
+            from convopeq_b200.dist import bench_cfg5_sharded
+            cfg5_sharded = bench_cfg5_sharded(local, rank, world)
+        except Exception as ex:
+            cfg5_sharded = {"error": f"{type(ex).__name__}: {ex}"}
 
     if rank == 0:
         peaks = {}
@@ -376,11 +592,12 @@ def main():
         alg_bytes_per_launch = 16.0 * cs_rank / chunks
         dur_ms = st[dom] / chunks
         achieved = alg_bytes_per_launch / (dur_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, ncu = None, {}
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             # measured dram bytes per launch at the profiled launch size, scaled to this run's launch size
             traffic = tj[names[dom]] / tj["_channel_samples_per_launch"] * (cs_rank / chunks)
+            ncu = tj.get("_ncu", {})
         except Exception:
             pass
         dfma = capi.load().cpq_probe_dfma_tflops(local, 20000)
@@ -395,25 +612,38 @@ def main():
                     "whole_path": {"achieved": 16.0 * value / world / 1e9, "frac": 16.0 * value / world / 1e9 / hbm_peak,
                                    "note": "16 B per channel-sample x channel-samples/s of the whole step on one GPU"},
                     "fp64": {"probe_dfma_tflops": dfma,
-                             "achieved_tflops": flop_model[names[dom]] * cs_rank / (st[dom] * 1e-3) / 1e12,
-                             "frac": flop_model[names[dom]] * cs_rank / (st[dom] * 1e-3) / 1e12 / dfma if dfma > 0 else None,
-                             "note": "FP64 instruction model of the dominant kernel vs the measured DFMA probe; this path is bound by "
-                                     "the FP64 pipe and shared-memory issue, not HBM (SURVEY 8d); the HBM fraction uses the compulsory "
-                                     "16 B/channel-sample"}}
+                             "pipe_utilisation_ncu": ncu.get(names[dom], {}).get("fp64_pct"),
+                             "pipe_utilisation_source": ncu.get("_source"),
+                             "model_achieved_tflops": flop_model[names[dom]] * cs_rank / (st[dom] * 1e-3) / 1e12,
+                             "model_frac": flop_model[names[dom]] * cs_rank / (st[dom] * 1e-3) / 1e12 / dfma if dfma > 0 else None,
+                             "note": "pipe_utilisation_ncu = sm__inst_executed_pipe_fp64 (ncu --set full of this kernel, committed under "
+                                     "profiles/); model_* = FP64 instruction model of the dominant kernel vs the measured DFMA probe; this "
+                                     "path is bound by the FP64 pipe, not HBM (SURVEY 8d); the HBM fraction uses the compulsory 16 B/channel-sample"}}
         cpu = None
         if not args.no_cpu and world == 1:
             v, info = cpu_reference_run(args.cpu_seconds, min(T, 96000 // BLOCK * BLOCK))
             cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
+            try:
+                v1, info1 = cpu_reference_run(min(args.cpu_seconds, 4.0), min(T, 96000 // BLOCK * BLOCK), max_threads=1)
+                cpu["one_thread"] = {"value": v1, "cores": 1, "note": "the same chain on a single host thread (BASELINE.md section 3)"}
+            except Exception:
+                pass
+        cfg = {"workload": workload_name(S, T), "streams_per_gpu": S, "samples_per_channel": T, "ir_taps": IR_LEN,
+               "block": BLOCK, "l2_policy": "inputs (7.9 GB/GPU at 1024 streams) far exceed the 126 MB L2; no flush needed",
+               "prepare_s": t_prep, "parallelism": f"stream-sharded x{world}, no collective",
+               "numa": (f"rank 0 bound to CPUs {numa_cpus[0]}..{numa_cpus[-1]} ({len(numa_cpus)})" if numa_cpus else "not bound")}
+        if strong:
+            cfg["strong_scaling"] = strong
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": workload_name(S, T), "streams_per_gpu": S, "samples_per_channel": T, "ir_taps": IR_LEN,
-                       "block": BLOCK, "l2_policy": "inputs (7.9 GB/GPU at 1024 streams) far exceed the 126 MB L2; no flush needed",
-                       "prepare_s": t_prep, "parallelism": f"stream-sharded x{world}, no collective",
-                       "numa": (f"rank 0 bound to {len(numa_cpus)} CPUs of its GPU's NUMA node" if numa_cpus else "not bound")},
+            "data": "synthetic", "config": cfg,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        if others is not None:
+            line["other_workloads"] = others
+        if cfg5_sharded is not None:
+            line["other_workloads"] = {"cfg5_partition_range_sharded": cfg5_sharded}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -143,6 +143,9 @@ struct Engine
 
     // timing / pipelining
     cudaStream_t sIn = nullptr, sOut = nullptr;   // H2D and D2H streams of the host entry point
+    static constexpr int kDitherStreams = 32;
+    cudaStream_t sDither[kDitherStreams] {};      // the dither stage is serial in time (latency-bound): it runs beside the next chunks
+    const double* uniformsBorrowed = nullptr;     // cpq_set_dither_uniforms_device
     cudaEvent_t ev[8] {};
     std::vector<cudaEvent_t> evPool;
     cudaEvent_t poolEvent(size_t i)
@@ -166,6 +169,8 @@ struct Engine
             if (e) cudaEventDestroy(e);
         for (auto& e : evPool)
             if (e) cudaEventDestroy(e);
+        for (auto& d : sDither)
+            if (d) cudaStreamDestroy(d);
         if (sIn) cudaStreamDestroy(sIn);
         if (sOut) cudaStreamDestroy(sOut);
         if (stream) cudaStreamDestroy(stream);
@@ -218,6 +223,7 @@ struct Engine
     cpq_status exportState(void* dst, size_t bytes);
     cpq_status importState(const void* src, size_t bytes);
     cpq_status processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF = nullptr);
+    cpq_status processCoreImpl(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF);
     DevBuf<float> f32In, f32Out;        // device staging of float host buffers: 3 inbound / 2 outbound chunk slots
     cpq_status processDevice(double* dIo, int64_t stride, int64_t T, unsigned stages) { return processCore(dIo, stride, T, stages, nullptr); }
     cpq_status launchFwd(int log2P, const FwdArgs& a);
@@ -493,6 +499,7 @@ cpq_status Engine::init(const cpq_config* c)
     CPQ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CPQ_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
     CPQ_CUDA(cudaStreamCreateWithFlags(&sOut, cudaStreamNonBlocking));
+    for (auto& d : sDither) CPQ_CUDA(cudaStreamCreateWithFlags(&d, cudaStreamNonBlocking));
     for (auto& e : ev) CPQ_CUDA(cudaEventCreate(&e));
     nH = cfg.shared_ir ? cfg.n_channels : nSeq;
     haveImpulse.assign((size_t) nH, 0);
@@ -706,6 +713,8 @@ static void buildBandConstants(const cpq_svf_coeffs& c, double* out /* kEqcStrid
         out[7] = !tpt ? 0.0 : ((c.m0 == 1.0 && c.m2 == 0.0) ? 1.0 : 2.0);   // 1: Peaking pattern, out = v0 + m1 v1
         out[8] = g;
         out[9] = 2.0 * g;
+        out[10] = (double) (2.0L * ((long double) c.a1 - (long double) c.a3));   // rotated-state recurrence of the Peaking fast path
+        out[11] = (double) (2.0L * ((long double) c.a1 + (long double) c.a3));
     }
     buildScanTables(A, b, out);
 }
@@ -1469,7 +1478,29 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
     return launchEq(f);
 }
 
+// Every error exit of the pipelined implementation leaves copies in flight on the three streams (H2D still reading, D2H
+// still writing the caller's buffers): drain them before the status reaches the caller, who may free or reuse the buffers.
 cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF)
+{
+    const cpq_status st = processCoreImpl(dIo, stride, T, stages, hostPlanar, hostF);
+    if (st != CPQ_OK)
+    {
+        if (sIn) cudaStreamSynchronize(sIn);
+        if (stream) cudaStreamSynchronize(stream);
+        if (sOut) cudaStreamSynchronize(sOut);
+        cudaGetLastError();
+        if (streaming)
+        {
+            // a failed call may have advanced part of the carried state: the stream cannot be continued
+            const std::string keep = err;
+            resetState();
+            err = keep + " (streaming state was reset)";
+        }
+    }
+    return st;
+}
+
+cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF)
 {
     const bool hostIO = hostPlanar || hostF;
     if (!dIo || T <= 0 || T > cfg.max_samples || T % cfg.block_size != 0 || (T & 1) || stride < T || (stride & 1))
@@ -1535,6 +1566,8 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         CPQ_CUDA(cudaMemsetAsync(limFlag.p, doDither ? 0xff : 0, (size_t) cfg.n_streams * sizeof(unsigned), stream));
     }
     if (doDither && !cont) CPQ_CUDA(cudaMemsetAsync(ditherZ.p, 0, (size_t) this->nSeq * 12 * sizeof(double), stream));   // PsychoacousticDither::reset
+    if (doDither && cont)
+        for (auto& d : sDither) CPQ_CUDA(cudaStreamSynchronize(d));   // (paranoia: the carried history is read on the side streams)
     if (doDither && uniformsPerCh != T)
     {
         setError("process: dither enabled but cpq_set_dither_uniforms does not hold exactly T samples per channel");
@@ -1680,7 +1713,8 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
     }
     const size_t nChunks = (size_t) ((nSeq + chunk - 1) / chunk);
     // event pool layout: [c*6 + 0..4] stage boundaries on the compute stream, [c*6 + 5] H2D done on the copy-in stream
-    for (size_t i = 0; i < nChunks * 9 + 4; ++i) poolEvent(i);
+    for (size_t i = 0; i < nChunks * 11 + 4; ++i) poolEvent(i);
+    const size_t dBase = nChunks * 9 + 4;   // per chunk [0] EQ done (compute stream), [1] dither / limiter done (side stream)
     // float host buffers: per chunk [0] inbound conversion done, [1] outbound conversion done (compute stream), [2] D2H done
     const size_t fBase = nChunks * 6 + 4;
     if (hostF)
@@ -2091,6 +2125,16 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
                                            layer[li].tail.p + (size_t) K[li] * l.partSize, (size_t) (carryFrames[li] + K[li]) * l.partSize * sizeof(double),
                                            (size_t) carryFrames[li] * l.partSize * sizeof(double), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
             }
+        // The dither recurrence is one dependent chain per sequence (about 130 cycles per sample whatever the batch): on the
+        // compute stream a chunk's dither would hold up the next chunk's transforms for T x 130 cycles with a handful of warps
+        // busy, so it (and the limiter that follows it) runs on a side stream and the next chunks compute beside it.
+        cudaStream_t post = stream;
+        if (doDither)
+        {
+            cudaEventRecord(evPool[dBase + c * 2], stream);
+            post = sDither[c % kDitherStreams];
+            cudaStreamWaitEvent(post, evPool[dBase + c * 2], 0);
+        }
         if (doDither)
         {
             DitherArgs d {};
@@ -2098,7 +2142,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             d.ioStride = stride;
             d.T = T;
             d.nSeq = ns;
-            d.uniforms = uniforms.p + (size_t) s0 * 2 * T;
+            d.uniforms = (uniformsBorrowed ? uniformsBorrowed : uniforms.p) + (size_t) s0 * 2 * T;
             ditherCoeffs(cfg.sample_rate, ditherBits, d.coeff);
             d.scale = 1.0 / std::pow(2.0, ditherBits - 1);
             d.invScale = std::pow(2.0, ditherBits - 1);
@@ -2106,7 +2150,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             d.finalClamp = outCfg.finalClamp ? (limiterOn ? 1 : 3) : 0;
             d.nch = cfg.n_channels;
             d.seqBase = s0;
-            dither_kernel<<<(unsigned) ((ns + 31) / 32), 32, kDitherSmemBytes, stream>>>(d);
+            dither_kernel<<<(unsigned) ((ns + 31) / 32), 32, kDitherSmemBytes, post>>>(d);
             ++launches;
             CPQ_CUDA(cudaGetLastError());
         }
@@ -2123,11 +2167,16 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             la.clamp = outCfg.finalClamp ? 1 : 0;
             la.envOut = limEnv.p + s0 / cfg.n_channels;
             la.envIn = cont ? la.envOut : nullptr;
-            limiter_kernel<<<(unsigned) ((la.nStreams + 31) / 32), 32, 0, stream>>>(la);
+            limiter_kernel<<<(unsigned) ((la.nStreams + 31) / 32), 32, 0, post>>>(la);
             ++launches;
             CPQ_CUDA(cudaGetLastError());
         }
         cudaEventRecord(ce[4], stream);
+        if (doDither)
+        {
+            cudaEventRecord(evPool[dBase + c * 2 + 1], post);
+            if (hostF) cudaStreamWaitEvent(stream, evPool[dBase + c * 2 + 1], 0);   // the outbound conversion reads the dithered signal
+        }
         if (hostF)
         {
             // out through staging slot c % 2, free once chunk c - 2 has left the device
@@ -2150,7 +2199,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         }
         else if (hostPlanar)
         {
-            cudaStreamWaitEvent(sOut, ce[4], 0);
+            cudaStreamWaitEvent(sOut, doDither ? evPool[dBase + c * 2 + 1] : ce[4], 0);
             if (c == 0) cudaEventRecord(evOutBegin, sOut);
             if (hostPitch == T && stride == T)
                 CPQ_CUDA(cudaMemcpyAsync(hostPlanar[s0], dIo + (size_t) s0 * stride, (size_t) ns * T * sizeof(double), cudaMemcpyDeviceToHost, sOut));
@@ -2171,6 +2220,8 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         contValid = true;
     }
 
+    if (doDither)
+        for (size_t c = 0; c < nChunks; ++c) cudaStreamWaitEvent(stream, evPool[dBase + c * 2 + 1], 0);
     if (hostIO)
     {
         cudaEventRecord(evOutEnd, sOut);
@@ -2588,6 +2639,15 @@ cpq_status cpq_set_dither_uniforms(cpq_handle h, const double* uniforms, int64_t
     CPQ_CUDA(e->uniforms.ensure(n));
     CPQ_CUDA(cudaMemcpy(e->uniforms.p, uniforms, n * sizeof(double), cudaMemcpyHostToDevice));
     e->uniformsPerCh = samples_per_channel;
+    e->uniformsBorrowed = nullptr;
+    return CPQ_OK;
+}
+
+cpq_status cpq_set_dither_uniforms_device(cpq_handle h, const double* d_uniforms, int64_t samples_per_channel)
+{
+    if (!h || !d_uniforms || samples_per_channel <= 0 || (reinterpret_cast<uintptr_t>(d_uniforms) & 15)) return CPQ_ERR_INVALID;
+    h->uniformsBorrowed = d_uniforms;
+    h->uniformsPerCh = samples_per_channel;
     return CPQ_OK;
 }
 

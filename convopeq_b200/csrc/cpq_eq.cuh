@@ -53,16 +53,20 @@ namespace cpq
 #ifndef CPQ_MAX_PEERS
 #define CPQ_MAX_PEERS 8
 #endif
-constexpr int kEqThreads = 256;
-constexpr int kEqCWarps = 8;                     // every warp computes (an idle chain warp would leave one SM sub-partition half empty)
+#ifndef CPQ_EQ_WARPS
+#define CPQ_EQ_WARPS 8
+#endif
+constexpr int kEqCWarps = CPQ_EQ_WARPS;          // every warp computes (an idle chain warp would leave one SM sub-partition half empty)
 constexpr int kEqCThreads = kEqCWarps * 32;      // 256
+constexpr int kEqThreads = kEqCThreads;
+static_assert(kEqCWarps >= 6 && kEqCWarps <= 8, "mailbox rows hold 8 warps; 24 stages x 8 flags are cleared by the first 192 threads");
 constexpr int kEqL = CPQ_EQ_L;                   // samples per compute thread (16 or 32)
 constexpr int kEqTile = kEqCThreads * kEqL;      // 4096 (8192)
 constexpr int kEqPad = kEqL + 2;                 // shared-memory doubles per thread block (keeps 16-byte alignment)
 static_assert(kEqL == 16 || kEqL == 32, "samples per thread");
 
 // per (parameter set, band) constants, all double; built by buildBandConstants() in cpq_engine.cu
-constexpr int kEqcCoef = 0;                      // a1,a2,a3,m0,m1,m2, forceExact(!=0), kind (0 literal, 1 TPT peaking, 2 TPT), g, 2g
+constexpr int kEqcCoef = 0;                      // a1,a2,a3,m0,m1,m2, forceExact(!=0), kind (0 literal, 1 TPT peaking, 2 TPT), g, 2g, 2(a1-a3), 2(a1+a3)
                                                  // kind 3 (DF2T biquad): b0,b1,b2,a1,a2 in [0..4]; kind 4 (DC blocker): alpha0, alpha1 in [0..1]
 constexpr int kEqcW = 12;                        // w[L][2]    zero-state weights, c = sum_j w[j] * v0[j]
 constexpr int kEqcMs = kEqcW + 2 * kEqL;         // Ms[5][4]   A^(L*2^d), row-major 2x2
@@ -82,7 +86,7 @@ constexpr int kEqStageDc = CPQ_NUM_BANDS + 3;
 // shared memory: segment tiles | band constants | mailboxes st[20][8] (double2) | flags fl[20][8] (int) | ticket
 // shared memory: segment tiles | EQ band constants | mailboxes st[stage][8] (double2) | flags fl[stage][8] (int) | ticket |
 // output-stage constants (only allocated when such a stage runs)
-constexpr int kEqSmemDoubles = kEqCThreads * kEqPad + CPQ_NUM_BANDS * kEqcStride + kEqStages * 8 * 2 + kEqStages * 8 / 2 + 2;
+constexpr int kEqSmemDoubles = kEqCThreads * kEqPad + CPQ_NUM_BANDS * kEqcStride + kEqStages * 8 * 2 + kEqStages * 8 + 2;   // flags: 8 bytes each (mbarriers)
 constexpr size_t kEqSmemBytes = (size_t) kEqSmemDoubles * sizeof(double);
 constexpr size_t kEqSmemBytesPost = kEqSmemBytes + (size_t) kEqPostStages * kEqcStride * sizeof(double);
 
@@ -337,12 +341,57 @@ __device__ __forceinline__ void eq_pass2(double (&x)[kEqL], double& ic1, double&
 // later (A^(L/2) s + the first half's zero-state response, which pass 1 accumulates separately anyway).  One recurrence is
 // a chain of three dependent DFMAs per sample (8 cycles each); two independent chains per thread halve the time a warp
 // spends waiting on its own results (the kernel's dominant stall, profiles/r01h_stalls_eq_kernel.txt).
+#ifndef CPQ_EQ_UW
+#define CPQ_EQ_UW 1
+#endif
 template <bool SAT, int KIND>
 __device__ __forceinline__ void eq_pass2x2(double (&x)[kEqL], double sA1, double sA2, double sB1, double sB2, const double* __restrict__ bc,
                                            double alpha, double gamma, unsigned& hiMax)
 {
     const double a1 = bc[0], a2 = bc[1], a3 = bc[2], m0 = bc[3], m1 = bc[4], m2 = bc[5], g = bc[8], g2 = bc[9];
     constexpr int H = kEqL / 2;
+    auto sat = [&](double out) -> double {
+        if (SAT)
+        {
+            const double d = fma(out, out, 3.0);
+            hiMax = max(hiMax, (unsigned) __double2hiint(d));
+            double r0;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+            const double e = fma(-d, r0, 1.0);
+            const double r = fma(r0, e, r0);
+            return out * fma(gamma, r, alpha);
+        }
+        hiMax = max(hiMax, (unsigned) __double2hiint(out) & 0x7fffffffu);
+        return out;
+    };
+#if CPQ_EQ_UW
+    if (KIND == 1)
+    {
+        // Peaking band in the rotated state  u = a1 ic1 - a2 ic2,  w = a1 ic1 + a2 ic2:  v1 = u + a2 v0 and, with
+        // ic1' = 2 v1 - ic1, ic2' = ic2 + 2 g v1 (a3 = g a2):  u' = 2 (a1 - a3) v1 - w,  w' = 2 (a1 + a3) v1 - u  -- four FP64
+        // operations per sample instead of six.  u and w nearly cancel in ic2 for low bands (a2 << a1), which a long run would
+        // amplify, but a chain here is half a thread block (16 samples) from a start state the scan supplies in the (ic1, ic2)
+        // basis: measured <= 1e-13 of the long-double recurrence at |y| ~ 5 (2.7e-12 at |y| = 86, Q = 0.01, +48 dB), against
+        // 1e-14 for the (ic1, ic2) form -- a factor the 1e-10 budget absorbs (tests/test_gpu_parity.py stress cases).
+        const double cu = bc[10], cw = bc[11];
+        const double tA = a2 * sA2, tB = a2 * sB2;
+        double uA = fma(a1, sA1, -tA), wA = fma(a1, sA1, tA), uB = fma(a1, sB1, -tB), wB = fma(a1, sB1, tB);
+#pragma unroll
+        for (int j = 0; j < H; ++j)
+        {
+            const double vA = x[j], vB = x[j + H];
+            const double v1A = fma(a2, vA, uA), v1B = fma(a2, vB, uB);
+            const double nA = fma(cu, v1A, -wA), nB = fma(cu, v1B, -wB);
+            wA = fma(cw, v1A, -uA);
+            wB = fma(cw, v1B, -uB);
+            uA = nA;
+            uB = nB;
+            x[j] = sat(fma(m1, v1A, vA));
+            x[j + H] = sat(fma(m1, v1B, vB));
+        }
+        return;
+    }
+#endif
     auto step = [&](double v0, double& ic1, double& ic2) -> double {
         double out;
         if (KIND == 1)
@@ -369,18 +418,7 @@ __device__ __forceinline__ void eq_pass2x2(double (&x)[kEqL], double sA1, double
             ic2 = fma(2.0, v2, -ic2);
             out = fma(m0, v0, fma(m1, v1, m2 * v2));
         }
-        if (SAT)
-        {
-            const double d = fma(out, out, 3.0);
-            hiMax = max(hiMax, (unsigned) __double2hiint(d));
-            double r0;
-            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
-            const double e = fma(-d, r0, 1.0);
-            const double r = fma(r0, e, r0);
-            return out * fma(gamma, r, alpha);
-        }
-        hiMax = max(hiMax, (unsigned) __double2hiint(out) & 0x7fffffffu);
-        return out;
+        return sat(out);
     };
 #pragma unroll
     for (int j = 0; j < H; ++j)
@@ -393,6 +431,29 @@ __device__ __forceinline__ void eq_pass2x2(double (&x)[kEqL], double sA1, double
 #ifndef CPQ_EQ_SLEEP
 #define CPQ_EQ_SLEEP 40
 #endif
+#ifndef CPQ_EQ_MBAR
+#define CPQ_EQ_MBAR 1      // mailbox flags are mbarriers (arrive / try_wait: a waiting warp is suspended by the hardware) instead of polled words
+#endif
+__device__ __forceinline__ void eq_mbar_init(unsigned long long* bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned) __cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void eq_mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((unsigned) __cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void eq_mbar_wait(unsigned long long* bar)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "EQW_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], 0, 0x989680;\n"
+        "@p bra EQD_%=;\n"
+        "bra EQW_%=;\n"
+        "EQD_%=:\n"
+        "}\n" ::"r"((unsigned) __cvta_generic_to_shared(bar)) : "memory");
+}
 #ifndef CPQ_EQ_ILP2
 #define CPQ_EQ_ILP2 1
 #endif
@@ -410,13 +471,22 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
     double* tile = eq_smem;                                        // [7 warps][32 lanes][18]
     double* cst = tile + kEqCThreads * kEqPad;                     // this sequence's band constants
     double2* st = reinterpret_cast<double2*>(cst + CPQ_NUM_BANDS * kEqcStride);   // [stage][8] state at the start of segment w
+#if CPQ_EQ_MBAR
+    unsigned long long* fl = reinterpret_cast<unsigned long long*>(st + kEqStages * 8);   // [stage][8] mailbox mbarriers (one phase each)
+#else
     int* fl = reinterpret_cast<int*>(st + kEqStages * 8);                         // [stage][8] mailbox flags
-    unsigned* sTicket = reinterpret_cast<unsigned*>(fl + kEqStages * 8);
+#endif
+    unsigned* sTicket = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned long long*>(st + kEqStages * 8) + kEqStages * 8);
     double* cstPost = eq_smem + kEqSmemDoubles;                                   // output-stage constants (present iff postMask)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) *sTicket = atomicAdd(a.chain.ticket, 1u);
+#if CPQ_EQ_MBAR
+    if (tid < kEqStages * 8) eq_mbar_init(fl + tid);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
     if (tid < kEqStages * 8) fl[tid] = 0;
+#endif
     __syncthreads();
     const unsigned ticket = *sTicket;
     // run-major ticket order: the predecessor (same sequence, previous tile) always holds a smaller ticket
@@ -811,9 +881,13 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                 }
                 else
                 {
+#if CPQ_EQ_MBAR
+                    eq_mbar_wait(fl + b * 8 + warp);   // acquire: the poster's st[] store is visible
+#else
                     const int* f = fl + b * 8 + warp;
                     while (lds_volatile(f) == 0) { __nanosleep(CPQ_EQ_SLEEP); }   // a spinning warp would steal issue slots from the FP64 warps
                     __threadfence_block();
+#endif
                 }
             }
             double p1, p2;
@@ -829,8 +903,12 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                 if (warp + 1 < kEqCWarps)
                 {
                     st[b * 8 + warp + 1] = make_double2(o1, o2);
+#if CPQ_EQ_MBAR
+                    eq_mbar_arrive(fl + b * 8 + warp + 1);   // release
+#else
                     __threadfence_block();
                     sts_volatile(fl + b * 8 + warp + 1, 1);
+#endif
                 }
                 else if (recOut)
                     st_volatile_f64x2(recOut + b, make_double2(rec_clean(o1), rec_clean(o2)));   // state after the tile

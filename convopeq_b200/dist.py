@@ -27,11 +27,12 @@ def stream_range(n_streams: int, rank: int, world: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < extra else 0)
 
 
-def bind_to_gpu_numa_node(device_index: int):
+def bind_to_gpu_numa_node(device_index: int, local_rank: int = 0, local_world: int = 1):
     """Pin this process to the CPUs of the NUMA node the GPU hangs off, BEFORE it allocates pinned host buffers (first touch
     then places them next to the GPU's PCIe root).  With one process per GPU and host <-> device streaming on every rank,
-    buffers on the far socket halve the transfer rate.  Returns the cpu list it bound to, or None when the topology is not
-    exposed (then nothing changes)."""
+    buffers on the far socket halve the transfer rate.  When several local ranks would end up on the same CPU list (boxes
+    that expose one NUMA node for every GPU) each rank takes its own slice of it, so the ranks' copy threads do not share
+    cores.  Returns the cpu list it bound to, or None when the topology is not exposed (then nothing changes)."""
     import os
     try:
         import pynvml
@@ -54,8 +55,26 @@ def bind_to_gpu_numa_node(device_index: int):
         cpus &= os.sched_getaffinity(0)
         if not cpus:
             return None
-        os.sched_setaffinity(0, cpus)
-        return sorted(cpus)
+        cpus = sorted(cpus)
+        if local_world > 1:
+            # which local GPUs share this list?  slice it among them
+            same = []
+            for d in range(pynvml.nvmlDeviceGetCount()):
+                try:
+                    b = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(d)).busId
+                    b = (b.decode() if isinstance(b, bytes) else b).lower()
+                    if len(b.split(":")[0]) == 8:
+                        b = b[4:]
+                    with open(f"/sys/bus/pci/devices/{b}/local_cpulist") as f:
+                        if f.read().strip() == spec:
+                            same.append(d)
+                except Exception:
+                    pass
+            if device_index in same and len(same) > 1 and len(cpus) >= len(same):
+                i, n = same.index(device_index), len(same)
+                cpus = cpus[len(cpus) * i // n: len(cpus) * (i + 1) // n]
+        os.sched_setaffinity(0, set(cpus))
+        return cpus
     except Exception:
         return None
 
@@ -160,3 +179,120 @@ def process_partition_sharded(engine, io_tensor, T: int, rank: int, world: int, 
         engine.process_device(io_tensor.data_ptr(), stride, T, after)
     engine.set_partition_range(0, -1)
     return io_tensor
+
+
+def cfg5_layout(world: int):
+    """BASELINE config 5 on `world` GPUs: the 8 channels are 4 stereo pairs that share one 2,097,152-tap IR pair.  Ranks form
+    groups of two; a group owns 4 / (world / 2) pairs, and inside a group the two ranks split the flattened (layer, partition)
+    list in half -- so the forward transforms of a channel run on two GPUs instead of on all of them, the multiply-accumulate
+    is divided by the whole world, and each rank finishes (EQ, output stage) half of its group's channels after ONE pairwise
+    reduce over NVLink.  Returns (groups, ranks_per_group, pairs_per_group)."""
+    if world < 2 or world % 2 or 4 % (world // 2):
+        raise ValueError("cfg5 sharding: world must be 2, 4 or 8")
+    return world // 2, 2, 4 // (world // 2)
+
+
+def bench_cfg5_sharded(local: int, rank: int, world: int, steps: int = 3):
+    """Time cfg5 (192 kHz, 8 channels, 2M-tap IR, 10 s) partition-range sharded over `world` GPUs, with the one-GPU time of the
+    same job (rank 0 alone) beside it.  Device-resident, CUDA events on the engine stream, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from . import capi
+    from .engine import ConvoPeqEngine
+    from tests import signals
+
+    dev = torch.device("cuda", local)
+    sr, block, T, ir_len = 192000.0, 512, 1920000 // 512 * 512, 2097152
+    groups, rpg, pairs = cfg5_layout(world)
+    grp, sub = rank // rpg, rank % rpg
+    pgs = [dist.new_group(list(range(g * rpg, (g + 1) * rpg))) for g in range(groups)]
+    irs = [signals.synth_ir(ir_len, 40 + ch) for ch in range(2)]
+    spec = capi.default_filter_spec(sample_rate=sr)
+
+    def build(n_pairs, first_pair):
+        eng = ConvoPeqEngine(n_pairs, 2, sr, block, T, device=local, conv_boundary=capi.CONV_OUTER, shared_ir=True)
+        for ch in range(2):
+            eng.set_impulse(-1, ch, irs[ch], 1.0, spec)
+        for s in range(n_pairs):
+            eng.set_eq(s, signals.to_band(signals.band_params(seed=7 + first_pair + s)))
+        eng.set_epilogue(1.0, 0)
+        return eng
+
+    def allmax(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(500)
+    x_all = torch.randn(8, T, device=dev, dtype=torch.float64, generator=g) * 0.1     # the same on every rank
+    eng = build(pairs, grp * pairs)
+    x = x_all[2 * grp * pairs: 2 * (grp + 1) * pairs].contiguous()
+    io = torch.empty_like(x)
+    stream = torch.cuda.ExternalStream(eng.cuda_stream(), device=dev)
+    lay = eng.layout()
+    parts = [lay.layers[i].num_parts_ir for i in range(lay.num_layers)]
+    b, e = partition_ranges(parts, rpg)[sub]
+    # rows a rank finishes: half of the group's channels (whole streams when the group has two or more pairs)
+    n_rows = 2 * pairs
+    own_lo, own_hi = n_rows * sub // rpg, n_rows * (sub + 1) // rpg
+    whole_streams = (own_lo % 2 == 0 and own_hi % 2 == 0)
+
+    def step():
+        io.copy_(x)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        eng.set_partition_range(b, e)
+        eng.process_device(io.data_ptr(), T, T, capi.STAGE_CONV)               # returns when the partial is complete
+        dist.all_reduce(io, op=dist.ReduceOp.SUM, group=pgs[grp])             # pairwise sum over NVLink
+        torch.cuda.current_stream(dev).synchronize()
+        eng.set_partition_range(0, -1)
+        if whole_streams:
+            eng.set_stream_window(own_lo // 2, (own_hi - own_lo) // 2)
+        eng.process_device(io.data_ptr(), T, T, capi.STAGE_EQ | capi.STAGE_EPILOGUE)
+        eng.set_stream_window(0, -1)
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    step()
+    ms = [allmax(step()) for _ in range(steps)]
+    sharded_ms = sum(ms) / len(ms)
+    result_rows = io[own_lo:own_hi].clone() if whole_streams else io.clone()
+    eng.close()
+    # the same job on one GPU (rank 0; the other ranks wait)
+    one_ms, err = None, None
+    if rank == 0:
+        full = build(4, 0)
+        io1 = torch.empty_like(x_all)
+        st1 = torch.cuda.ExternalStream(full.cuda_stream(), device=dev)
+
+        def one():
+            io1.copy_(x_all)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st1)
+            full.process_device(io1.data_ptr(), T, T, capi.STAGE_ALL)
+            e1.record(st1)
+            e1.synchronize()
+            return e0.elapsed_time(e1)
+
+        one()
+        o = [one() for _ in range(steps)]
+        one_ms = sum(o) / len(o)
+        lo = 2 * grp * pairs + own_lo
+        ref = io1[lo: lo + result_rows.shape[0]] if whole_streams else io1[2 * grp * pairs: 2 * (grp + 1) * pairs]
+        err = float((ref - result_rows).abs().max().item())
+        full.close()
+    dist.barrier()
+    cs = 8.0 * T
+    return {"workload": "cfg5: 192 kHz, 8 channels (4 stereo pairs sharing one 2,097,152-tap IR pair), block 512, 10 s, conv -> EQ -> makeup+headroom",
+            "sharding": f"{groups} group(s) of {rpg} ranks; a group owns {pairs} pair(s) and splits the {sum(parts)} partitions "
+                        f"({'+'.join(map(str, parts))}) in two; one pairwise NCCL all-reduce of the partial wet signal per group",
+            "n_gpus": world, "device_ms": sharded_ms, "value": cs / (sharded_ms * 1e-3), "one_gpu_ms": one_ms,
+            "speedup_vs_one_gpu": (one_ms / sharded_ms) if one_ms else None,
+            "max_abs_diff_vs_one_gpu_rank0": err}

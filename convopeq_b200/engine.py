@@ -114,8 +114,9 @@ class ConvoPeqEngine:
             act[i] = 1 if on else 0
             mode[i] = int(b.channel_mode)
             co[i] = design_band(b, self.sample_rate) if on else capi.SvfCoeffs()
-        sat = float(np.float32(saturation))
-        gain = self.lib.cpq_db_to_gain(C.c_float(total_gain_db))
+        # EQProcessor::setNonlinearSaturation clamps to [0, 1], setTotalGain to +-48 dB (EQProcessor.Parameters.cpp:206-208, 103-106)
+        sat = float(np.float32(min(1.0, max(0.0, saturation))))
+        gain = self.lib.cpq_db_to_gain(C.c_float(min(48.0, max(-48.0, total_gain_db))))
         self._check(self.lib.cpq_set_eq(self.h, stream, co, act, mode, sat, gain))
         node = (C.c_uint8 * capi.NUM_BANDS)(*[self.lib.cpq_band_node_active(int(b.type), C.c_float(b.gain), int(bool(b.enabled)),
                                                                              self.sample_rate) for b in bands])
@@ -146,6 +147,10 @@ class ConvoPeqEngine:
             u = np.ascontiguousarray(uniforms, dtype=np.float64)
             assert u.shape[0] == self.n_seq and u.shape[1] % 2 == 0
             self._check(self.lib.cpq_set_dither_uniforms(self.h, u.ctypes.data_as(_dp), u.shape[1] // 2))
+
+    def set_dither_uniforms_device(self, data_ptr: int, samples_per_channel: int):
+        """Injected dither uniforms already on the device: [n_seq][2 * samples] doubles, borrowed."""
+        self._check(self.lib.cpq_set_dither_uniforms_device(self.h, data_ptr, samples_per_channel))
 
     def set_partition_range(self, begin: int, end: int):
         self._check(self.lib.cpq_set_partition_range(self.h, begin, end))

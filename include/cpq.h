@@ -7,8 +7,9 @@
  * This header is the drop-in boundary.  Each entry point names the reference interface it
  * replaces (paths relative to the reference's src/).  Plain C types only: no torch, no C++.
  * One handle = one CUDA device + one batch of independent stereo (or mono) streams that share a
- * sample rate, a host block size and a layer geometry.  A handle is single-threaded; different
- * handles are independent.  Errors are status codes (the reference's path is noexcept and reports
+ * sample rate, a host block size and a layer geometry.  A handle is thread-compatible, not thread-safe: one
+ * thread at a time may call into a given handle (any thread; every entry point selects the handle's device itself);
+ * different handles, on the same or on different devices, are independent and may be driven concurrently.  Errors are status codes (the reference's path is noexcept and reports
  * failure as silence + counters); cpq_last_error() gives the text.  There is no CPU fallback:
  * every compute entry point fails with CPQ_ERR_CUDA when no sm_100 device is usable.
  */
@@ -217,6 +218,9 @@ cpq_status cpq_schedule_total_gain(cpq_handle h, int stream, int64_t at_callback
  * reference's MKL VSL ring. */
 cpq_status cpq_set_epilogue(cpq_handle h, double makeup_gain, int dither_bits);
 cpq_status cpq_set_dither_uniforms(cpq_handle h, const double* uniforms, int64_t samples_per_channel);
+/* The same for uniforms that already live on the handle's device (16-byte aligned, same layout): borrowed, not copied -- the
+ * buffer must stay valid until the process calls that use it have returned. */
+cpq_status cpq_set_dither_uniforms_device(cpq_handle h, const double* d_uniforms, int64_t samples_per_channel);
 
 /* convo::OutputFilter::prepare(sr) + process(block, convIsLast, hcMode, lcMode, lpMode) (OutputFilter.h:108-131,
  * OutputFilter.cpp:72-112,139-421): three cascaded DF2T biquads between the EQ and the makeup gain
@@ -302,6 +306,10 @@ double cpq_equal_power_sin(double x);       /* ConvolverProcessor.Runtime.cpp:26
  * stream from a reset state.  T must be a multiple of block_size and <= max_samples.  H2D and D2H copies
  * are part of the call. */
 cpq_status cpq_process(cpq_handle h, double* const* planar, int64_t T, unsigned stages);
+/* Error exits: no copy is in flight when a process call returns, whatever the status.  The call works in place, so after an
+ * error the buffers hold a mixture of input and results; in particular CPQ_ERR_UNSUPPORTED for an EQ state fault (a band
+ * state reached 1e15 or went non-finite, where the reference zeroes it and carries on, EQProcessor.Processing.cpp:174-175)
+ * is detected only after the output has overwritten the input. */
 
 /* Same with FP32 host buffers, in place: the wire format of hosts that hand the application float blocks (its float path casts
  * on entry, convertFloatToDoubleHighQuality InputBitDepthTransform.h:102-121, and on exit, static_cast<float>,

@@ -17,6 +17,7 @@
 
 #include <array>
 #include <cstdint>
+#include <algorithm>
 #include <span>
 #include <string>
 #include <utility>
@@ -119,8 +120,10 @@ public:
     void setBandType(int stream, int band, int type) { if (valid(stream, band)) { p(stream).bands[(size_t) band].type = type; dirty_ = true; } }
     void setBandEnabled(int stream, int band, bool e) { if (valid(stream, band)) { p(stream).bands[(size_t) band].enabled = e; dirty_ = true; } }
     void setBandChannelMode(int stream, int band, int m) { if (valid(stream, band)) { p(stream).bands[(size_t) band].channelMode = m; dirty_ = true; } }
-    void setTotalGain(int stream, float db) { if (valid(stream, 0)) { p(stream).totalGainDb = db; dirty_ = true; } }
-    void setNonlinearSaturation(int stream, float s) { if (valid(stream, 0)) { p(stream).nonlinearSaturation = s; dirty_ = true; } }
+    /// EQProcessor::setTotalGain: jlimit(DSP_MIN_GAIN_DB, DSP_MAX_GAIN_DB) = +-48 dB (EQProcessor.Parameters.cpp:103-106)
+    void setTotalGain(int stream, float db) { if (valid(stream, 0)) { p(stream).totalGainDb = std::min(48.0f, std::max(-48.0f, db)); dirty_ = true; } }
+    /// EQProcessor::setNonlinearSaturation: jlimit(0, 1) (EQProcessor.Parameters.cpp:206-208)
+    void setNonlinearSaturation(int stream, float s) { if (valid(stream, 0)) { p(stream).nonlinearSaturation = std::min(1.0f, std::max(0.0f, s)); dirty_ = true; } }
     /// EQProcessor::loadFromTextFile on the contents of an EqualizerAPO / AutoEq preset (EQProcessor.Core.cpp:300-495).
     bool loadFromText(int stream, const std::string& text)
     {
@@ -188,6 +191,16 @@ public:
     }
 
     bool Reset() { return ok(cpq_reset(h_)); }
+    /// Streaming continuation: process() calls continue the stream (Add/Get/EQ state carried) until Reset().
+    bool setStreaming(bool enable) { return ok(cpq_set_streaming(h_, enable ? 1 : 0)); }
+    std::int64_t streamPosition() const { return cpq_stream_position(h_); }
+    std::vector<unsigned char> exportState()
+    {
+        std::vector<unsigned char> blob(cpq_state_size(h_));
+        if (blob.empty() || !ok(cpq_export_state(h_, blob.data(), blob.size()))) blob.clear();
+        return blob;
+    }
+    bool importState(const std::vector<unsigned char>& blob) { return ok(cpq_import_state(h_, blob.data(), blob.size())); }
     int getLatency() const { return cpq_latency(h_); }
     bool isReady() const { return h_ != nullptr; }
     cpq_layout getLayout() const { cpq_layout l {}; if (h_) cpq_get_layout(h_, &l); return l; }

@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: scripts/quick_bench.sh tag [extra bench args]  -> prints value / ms / stage times of a short device-only bench
 tag=$1; shift
-timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu "$@" > gpurun_out/qb_$tag.json 2>gpurun_out/qb_$tag.err
+timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --no-others "$@" > gpurun_out/qb_$tag.json 2>gpurun_out/qb_$tag.err
 python - <<P
 import json
 try:
