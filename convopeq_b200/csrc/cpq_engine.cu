@@ -436,6 +436,10 @@ cpq_status Engine::setKernelAttributes()
     CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
     CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
     CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
+    CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytes));
+    CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
+    CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
+    CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
     CPQ_CUDA(cudaFuncSetAttribute(mac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem));
     CPQ_CUDA(cudaFuncSetAttribute(dither_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kDitherSmemBytes));
     return CPQ_OK;
@@ -763,6 +767,13 @@ static void buildScanTables(const long double A[4], const long double b[2], doub
     }
     // M is now A^(32 L): one warp segment
     for (int i = 0; i < 4; ++i) out[kEqcMw + i] = (double) M[i];
+    // Pw[j] = A^(32 L j), j = 0..8: whole warp segments, for the look-back composition of the segment start states
+    long double W[4] = { 1, 0, 0, 1 };
+    for (int j = 0; j <= 8; ++j)
+    {
+        for (int i = 0; i < 4; ++i) out[kEqcPw + 4 * j + i] = (double) W[i];
+        matmul2(W, M, W);
+    }
 }
 
 // ---- linear output stages: OutputFilter (OutputFilter.cpp:28-112) and the output DC blocker (UltraHighRateDCBlocker.h:60-90) ----
@@ -1252,6 +1263,9 @@ cpq_status Engine::launchEq(EqArgs& a)
     // one CTA per (sequence, kEqTile-sample tile); tiles of a sequence are chained through (sequence, tile, band) records
     // whose payload is its own flag: all-ones = not written yet
     a.nRuns = (int) ((a.T + kEqTile - 1) / kEqTile);
+    // fewer sequences than SMs: tiles of the same sequence fill the machine and the links between them are the critical path
+    static const int lbEnv = [] { const char* e = getenv("CPQ_EQ_LOOKBACK"); return e ? atoi(e) : -1; }();   // tuning knob
+    const bool lookback = lbEnv >= 0 ? lbEnv != 0 : a.nSeq <= 32;
     a.chain.ticket = ticketFault.p;
     a.fault = ticketFault.p + 1;
     if ((a.doEq || a.postMask) && a.nRuns > 1)
@@ -1263,7 +1277,14 @@ cpq_status Engine::launchEq(EqArgs& a)
     a.chain.rec = reinterpret_cast<double2*>(chainRec.p);
     CPQ_CUDA(cudaMemsetAsync(ticketFault.p, 0, sizeof(unsigned), stream));
     const unsigned grid = (unsigned) a.nSeq * (unsigned) a.nRuns;
-    if (a.doEq && anyPar) eq_kernel<true, true, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
+    if (lookback)
+    {
+        if (a.doEq && anyPar) eq_kernel<true, true, true, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
+        else if (a.sumsqIn || a.sumsqOut || a.nPeers > 0) eq_kernel<true, false, true, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
+        else if (a.postMask || a.finalClamp || a.limFlag) eq_kernel<true, false, false, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
+        else eq_kernel<false, false, false, true><<<grid, kEqThreads, kEqSmemBytes, stream>>>(a);
+    }
+    else if (a.doEq && anyPar) eq_kernel<true, true, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
     else if (a.sumsqIn || a.sumsqOut || a.nPeers > 0) eq_kernel<true, false, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
     else if (a.postMask || a.finalClamp || a.limFlag) eq_kernel<true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
     else eq_kernel<false><<<grid, kEqThreads, kEqSmemBytes, stream>>>(a);
@@ -2498,6 +2519,16 @@ cpq_status cpq_ir_min_phase(const double* ir, int len, double* out)
 {
     if (!ir || !out || len <= 0) return CPQ_ERR_INVALID;
     return cpq::irMinimumPhase(ir, len, out) ? CPQ_OK : CPQ_ERR_UNSUPPORTED;
+}
+
+int cpq_ir_target_length(double sample_rate, double target_seconds) { return cpq::irTargetLength(sample_rate, target_seconds); }
+
+int cpq_ir_prepare(const double* ir, int len, double sample_rate, double target_seconds, double* out, int out_capacity)
+{
+    if (!ir || !out || len <= 0 || !(sample_rate > 0.0)) return -1;
+    const int target = cpq::irTargetLength(sample_rate, target_seconds);
+    if (out_capacity < target) return -1;
+    return cpq::irPrepare(ir, len, sample_rate, target_seconds, out);
 }
 
 double cpq_ir_freq_peak_gain(const double* ir_l, const double* ir_r, int len)

@@ -74,7 +74,8 @@ constexpr int kEqcPlo = kEqcMs + 20;             // Plo[8][4]  A^(L*j)
 constexpr int kEqcPhi = kEqcPlo + 32;            // Phi[4][4]  A^(8L*j)
 constexpr int kEqcMw = kEqcPhi + 16;             // A^(32L)    (one warp segment)
 constexpr int kEqcMh = kEqcMw + 4;               // A^(L/2)    (half a thread block: start state of the second pass-2 chain)
-constexpr int kEqcStride = kEqcMh + 4;           // doubles per band, staged in shared memory for all 20 bands
+constexpr int kEqcPw = kEqcMh + 4;               // Pw[9][4]   A^(32L*j), j = 0..8: whole warp segments (look-back composition)
+constexpr int kEqcStride = kEqcPw + 36;          // doubles per band, staged in shared memory for all 20 bands
 
 constexpr int kEqSeg = 32 * kEqL;                // 512 samples per warp segment
 // Stages of the scan pipeline: the 20 EQ bands, then the linear output stages of DSPCore::processDouble --
@@ -86,7 +87,9 @@ constexpr int kEqStageDc = CPQ_NUM_BANDS + 3;
 // shared memory: segment tiles | band constants | mailboxes st[20][8] (double2) | flags fl[20][8] (int) | ticket
 // shared memory: segment tiles | EQ band constants | mailboxes st[stage][8] (double2) | flags fl[stage][8] (int) | ticket |
 // output-stage constants (only allocated when such a stage runs)
-constexpr int kEqSmemDoubles = kEqCThreads * kEqPad + CPQ_NUM_BANDS * kEqcStride + kEqStages * 8 * 2 + kEqStages * 8 + 2;   // flags: 8 bytes each (mbarriers)
+// mailboxes: agg[stage][8] warp aggregates + tin[stage] tile-in states (double2 each), one mbarrier per mailbox entry
+constexpr int kEqMail = kEqStages * 9;
+constexpr int kEqSmemDoubles = kEqCThreads * kEqPad + CPQ_NUM_BANDS * kEqcStride + kEqMail * 2 + kEqMail + 2;
 constexpr size_t kEqSmemBytes = (size_t) kEqSmemDoubles * sizeof(double);
 constexpr size_t kEqSmemBytesPost = kEqSmemBytes + (size_t) kEqPostStages * kEqcStride * sizeof(double);
 
@@ -463,30 +466,26 @@ __device__ __forceinline__ void eq_mbar_wait(unsigned long long* bar)
 // POST = the launch runs output stages / the output clamp; the plain conv -> EQ -> gain launch carries none of that code.
 // PAR  = FilterStructure::Parallel: every band filters the tile *input* and the differences are summed (a second block of
 //        registers per thread, hence one CTA per SM).   STATS = the launch accumulates the AGC block statistics.
-template <bool POST, bool PAR = false, bool STATS = false>
+// LB   = look-back links instead of chained links (see bandStart): for launches with few sequences, where the links between
+//        the tiles of one sequence are the critical path.  A separate instantiation so that neither form carries the other's code.
+template <bool POST, bool PAR = false, bool STATS = false, bool LB = false>
 __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs a)
 {
     const unsigned postMask = POST ? a.postMask : 0u;
     extern __shared__ __align__(16) double eq_smem[];
     double* tile = eq_smem;                                        // [7 warps][32 lanes][18]
     double* cst = tile + kEqCThreads * kEqPad;                     // this sequence's band constants
-    double2* st = reinterpret_cast<double2*>(cst + CPQ_NUM_BANDS * kEqcStride);   // [stage][8] state at the start of segment w
-#if CPQ_EQ_MBAR
-    unsigned long long* fl = reinterpret_cast<unsigned long long*>(st + kEqStages * 8);   // [stage][8] mailbox mbarriers (one phase each)
-#else
-    int* fl = reinterpret_cast<int*>(st + kEqStages * 8);                         // [stage][8] mailbox flags
-#endif
-    unsigned* sTicket = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned long long*>(st + kEqStages * 8) + kEqStages * 8);
+    double2* agg = reinterpret_cast<double2*>(cst + CPQ_NUM_BANDS * kEqcStride);  // [stage][8] zero-state response of warp w's segment
+    double2* tin = agg + kEqStages * 8;                                           // [stage] state at the start of the tile
+    unsigned long long* mbA = reinterpret_cast<unsigned long long*>(tin + kEqStages);   // [stage][8] "aggregate posted" (one phase each)
+    unsigned long long* mbT = mbA + kEqStages * 8;                                // [stage] "tile-in state posted"
+    unsigned* sTicket = reinterpret_cast<unsigned*>(mbT + kEqStages);
     double* cstPost = eq_smem + kEqSmemDoubles;                                   // output-stage constants (present iff postMask)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) *sTicket = atomicAdd(a.chain.ticket, 1u);
-#if CPQ_EQ_MBAR
-    if (tid < kEqStages * 8) eq_mbar_init(fl + tid);
+    for (int i = tid; i < kEqMail; i += kEqThreads) eq_mbar_init(mbA + i);   // mbA and mbT are contiguous
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#else
-    if (tid < kEqStages * 8) fl[tid] = 0;
-#endif
     __syncthreads();
     const unsigned ticket = *sTicket;
     // run-major ticket order: the predecessor (same sequence, previous tile) always holds a smaller ticket
@@ -852,71 +851,119 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
             double e2 = __shfl_up_sync(0xffffffffu, c2, 1);
             if (lane == 0) { e1 = 0.0; e2 = 0.0; }
 
-            // ---- link: state at the start of this segment from the previous warp (warp 0: from the previous tile) ----
-            if (link)
-            {
-                if (warp == 0)
+            // ---- link by look-back: every warp posts the zero-state response of its segment as soon as its scan is done
+            // (it depends on nobody), warp 0 posts the state at the start of the tile (from the previous tile's record), and
+            // warp w composes  s_w = A^(1024 w) s_tile + sum_{i<w} A^(1024 (w-1-i)) agg_i  itself.  No warp waits for another
+            // warp's *state*, only for aggregates that all warps produce at about the same time, so the warps of a tile run
+            // side by side instead of one link latency behind each other, and the state that leaves the tile is ready one
+            // matrix-vector product after the state that enters it (a serial chain of eight links before). ----
+            // state at the start of the tile (warp 0 only): Reset, the carried state of a streaming call, or the previous tile's record
+            auto tileIn = [&]() -> double2 {
+                double2 sv = make_double2(0.0, 0.0);   // Reset state for the first tile
+                if (!recIn && run == 0)
                 {
-                    double2 sv = make_double2(0.0, 0.0);   // Reset state for the first tile
-                    if (!recIn && run == 0)
+                    // streaming continuation: the state the previous call left behind
+                    const double* si = b < CPQ_NUM_BANDS ? (a.stateIn ? a.stateIn + ((size_t) seq * CPQ_NUM_BANDS + b) * 2 : nullptr)
+                                                         : (a.postStateIn ? a.postStateIn + ((size_t) seq * kEqPostStages + (b - CPQ_NUM_BANDS)) * 2 : nullptr);
+                    if (si) sv = make_double2(ld_cg_f64(si), ld_cg_f64(si + 1));   // the same buffer receives the final state: no read-only path
+                }
+                if (recIn)
+                {
+                    sv = (preBand == b) ? pre : ld_volatile_f64x2(recIn + b);
+                    while (rec_pending(sv))
                     {
-                        // streaming continuation: the state the previous call left behind
-                        const double* si = b < CPQ_NUM_BANDS ? (a.stateIn ? a.stateIn + ((size_t) seq * CPQ_NUM_BANDS + b) * 2 : nullptr)
-                                                             : (a.postStateIn ? a.postStateIn + ((size_t) seq * kEqPostStages + (b - CPQ_NUM_BANDS)) * 2 : nullptr);
-                        if (si) sv = make_double2(ld_cg_f64(si), ld_cg_f64(si + 1));   // the same buffer receives the final state: no read-only path
+                        __nanosleep(100);
+                        sv = ld_volatile_f64x2(recIn + b);
                     }
-                    if (recIn)
+                    preBand = nextBand(b);
+                    if (preBand < kEqStages) pre = ld_volatile_f64x2(recIn + preBand);
+                }
+                return sv;
+            };
+            double p1 = 0.0, p2 = 0.0;
+            if (LB)
+            {
+                if (link)
+                {
+                    if (lane == 31)
                     {
-                        sv = (preBand == b) ? pre : ld_volatile_f64x2(recIn + b);
-                        while (rec_pending(sv))
+                        agg[b * 8 + warp] = make_double2(c1, c2);
+                        eq_mbar_arrive(mbA + b * 8 + warp);   // release
+                    }
+                    if (warp == 0)
+                    {
+                        const double2 sv = tileIn();
+                        if (lane == 0)
                         {
-                            __nanosleep(100);
-                            sv = ld_volatile_f64x2(recIn + b);
+                            tin[b] = sv;
+                            eq_mbar_arrive(mbT + b);
                         }
-                        preBand = nextBand(b);
-                        if (preBand < kEqStages) pre = ld_volatile_f64x2(recIn + preBand);
                     }
-                    if (lane == 0) st[b * 8] = sv;   // kept for an exact-mode replay of this band
-                    __syncwarp();
                 }
-                else
+                for (int i = 0; i < warp; ++i)
                 {
-#if CPQ_EQ_MBAR
-                    eq_mbar_wait(fl + b * 8 + warp);   // acquire: the poster's st[] store is visible
-#else
-                    const int* f = fl + b * 8 + warp;
-                    while (lds_volatile(f) == 0) { __nanosleep(CPQ_EQ_SLEEP); }   // a spinning warp would steal issue slots from the FP64 warps
-                    __threadfence_block();
-#endif
+                    if (link) eq_mbar_wait(mbA + b * 8 + i);   // acquire; a replayed band finds every mailbox already filled
+                    const double2 ai = agg[b * 8 + i];
+                    matvec2(bc + kEqcMw, p1, p2, ai.x, ai.y);  // Horner: zero-state response of segments 0..i at the start of segment i + 1
+                }
+                if (link) eq_mbar_wait(mbT + b);
+                {
+                    const double2 tv = tin[b];
+                    double q1 = tv.x, q2 = tv.y;
+                    matvec2(bc + kEqcPw + 4 * warp, q1, q2, p1, p2);   // A^(1024 w) s_tile + ...
+                    p1 = q1;
+                    p2 = q2;
+                }
+                if (link && lane == 31 && warp + 1 == kEqCWarps)
+                {
+                    double o1 = p1, o2 = p2;
+                    matvec2(bc + kEqcMw, o1, o2, c1, c2);   // state after the tile
+                    if (recOut)
+                        st_volatile_f64x2(recOut + b, make_double2(rec_clean(o1), rec_clean(o2)));
+                    else if (fullLast)
+                        storeFinal(b, o1, o2);
                 }
             }
-            double p1, p2;
+            else
             {
-                const double2 sv = st[b * 8 + warp];
-                p1 = sv.x;
-                p2 = sv.y;
-            }
-            if (link && lane == 31)
-            {
-                double o1 = p1, o2 = p2;
-                matvec2(bc + kEqcMw, o1, o2, c1, c2);   // state after this segment
-                if (warp + 1 < kEqCWarps)
+                // ---- link by chain (batches with at least one sequence per SM): warp w takes the state at the start of its
+                // segment from mailbox agg[b][w] (here: a state, not an aggregate), posted by lane 31 of warp w - 1 right after
+                // its scan.  The warps of a tile run skewed by one link latency, which also keeps them in different phases of
+                // the band loop -- measured 14 % faster than the look-back form when the machine is full of independent tiles,
+                // and twice as slow on a single stereo stream (BASELINE config 2), where the serial links are all there is. ----
+                if (link)
                 {
-                    st[b * 8 + warp + 1] = make_double2(o1, o2);
-#if CPQ_EQ_MBAR
-                    eq_mbar_arrive(fl + b * 8 + warp + 1);   // release
-#else
-                    __threadfence_block();
-                    sts_volatile(fl + b * 8 + warp + 1, 1);
-#endif
+                    if (warp == 0)
+                    {
+                        const double2 sv = tileIn();
+                        if (lane == 0) agg[b * 8] = sv;   // kept for an exact-mode replay of this band
+                        __syncwarp();
+                    }
+                    else
+                        eq_mbar_wait(mbA + b * 8 + warp);   // acquire: the poster's store is visible
                 }
-                else if (recOut)
-                    st_volatile_f64x2(recOut + b, make_double2(rec_clean(o1), rec_clean(o2)));   // state after the tile
-                else if (fullLast)
-                    storeFinal(b, o1, o2);
+                {
+                    const double2 sv = agg[b * 8 + warp];
+                    p1 = sv.x;
+                    p2 = sv.y;
+                }
+                if (link && lane == 31)
+                {
+                    double o1 = p1, o2 = p2;
+                    matvec2(bc + kEqcMw, o1, o2, c1, c2);   // state after this segment
+                    if (warp + 1 < kEqCWarps)
+                    {
+                        agg[b * 8 + warp + 1] = make_double2(o1, o2);
+                        eq_mbar_arrive(mbA + b * 8 + warp + 1);   // release
+                    }
+                    else if (recOut)
+                        st_volatile_f64x2(recOut + b, make_double2(rec_clean(o1), rec_clean(o2)));   // state after the tile
+                    else if (fullLast)
+                        storeFinal(b, o1, o2);
+                }
             }
             // ---- state at the start of this thread's block: A^(L lane) s_in + e ----
-            matvec2(bc + kEqcPlo + 4 * (lane & 7), p1, p2, 0.0, 0.0);    // A^(L (lane & 7))
+            matvec2(bc + kEqcPlo + 4 * (lane & 7), p1, p2, 0.0, 0.0);    // A^(L (lane & 7)) (state at the start of this thread's block)
             matvec2(bc + kEqcPhi + 4 * (lane >> 3), p1, p2, e1, e2);     // A^(8L (lane >> 3)) ... + e
             ic1 = p1;
             ic2 = p2;

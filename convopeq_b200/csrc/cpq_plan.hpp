@@ -434,6 +434,104 @@ inline bool designBand(int type, float freq, float gainDb, float q, double sr, c
 // IR preparation (host, one-time): IRConverter::computeScaleFactor (IRConverter.cpp:13-196) with
 // IRAnalyzer::estimateMaxFrequencyResponseGain (IRAnalyzer.cpp:63-155).
 // ------------------------------------------------------------------------------------------------
+// IR preparation between the (optional) resampler and SetImpulse (LoaderThread::doLoadStep,
+// convolver/ConvolverProcessor.LoaderThread.cpp:588-637): per channel a 1 Hz UltraHighRateDCBlocker
+// (UltraHighRateDCBlocker.h:78-188), the asymmetric Tukey window around the peak (applyAsymmetricTukey,
+// ConvolverProcessor.ResampleAndFallback.cpp:111-196), then the copy into targetLength samples
+// (computeTargetIRLength, ConvolverProcessor.StateAndUI.cpp:942-957) with a linear fade-out over the last 2 % of the copied
+// samples (256 .. 80 ms).  Resampling itself is r8brain-free-src (third party, vendored by the reference) and is not restated.
+// ------------------------------------------------------------------------------------------------
+inline void irDcBlock(double* data, int n, double sr, double cutoffHz)
+{
+    double alpha[2] = { 1.0e-6, 1.0e-6 };
+    if (std::isfinite(sr) && sr > 0.0 && std::isfinite(cutoffHz) && cutoffHz > 0.0)
+    {
+        const double ratios[2] = { 1.0 - 0.1, 1.0 + 0.1 };
+        for (int i = 0; i < 2; ++i)
+        {
+            const double omega = 2.0 * kPi * (cutoffHz * ratios[i]) / sr;
+            double a = -std::expm1(-omega);
+            if (!std::isfinite(a) || a <= 0.0 || a >= 1.0) a = 1.0e-6;
+            alpha[i] = a;
+        }
+    }
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = 0; i < n; ++i)
+    {
+        double x = data[i];
+        s0 = std::fma(alpha[0], x - s0, s0);   // the reference's build contracts state + alpha * (x - state)
+        x -= s0;
+        s1 = std::fma(alpha[1], x - s1, s1);
+        x -= s1;
+        data[i] = x;
+    }
+}
+
+inline void irAsymmetricTukey(double* data, int n)
+{
+    if (!data || n <= 0) return;
+    int peak = 0;
+    for (int i = 1; i < n; ++i)
+        if (std::fabs(data[peak]) < std::fabs(data[i])) peak = i;   // std::max_element: first of equal maxima
+    const double alphaPre = 0.05;
+    double alphaPost = 0.05 + 0.033 * (std::log2((double) n) - 10.0);
+    alphaPost = std::max(0.05, std::min(0.25, alphaPost));
+    if (peak > 0)
+    {
+        const int len = (int) std::floor(peak * alphaPre);
+        const double scale = kPi / (peak * alphaPre);
+        for (int i = 0; i < len; ++i) data[i] *= 0.5 * (1.0 + std::cos(scale * (double) i + -kPi));
+    }
+    const double dist = (double) (n - 1 - peak);
+    if (dist > 1.0e-9)
+    {
+        const int start = peak + (int) std::ceil(dist * (1.0 - alphaPost));
+        const int len = n - start;
+        if (len > 0)
+        {
+            const double scale = (kPi / alphaPost) / dist;
+            const double offset = (kPi / alphaPost) * (((double) start - (double) peak) / dist - (1.0 - alphaPost));
+            for (int i = 0; i < len; ++i) data[start + i] *= 0.5 * (1.0 + std::cos(scale * (double) i + offset));
+        }
+    }
+}
+
+inline int irTargetLength(double sr, double targetSeconds)
+{
+    int target = (int) (sr * (double) (float) targetSeconds);   // targetIRLengthSec is a float
+    target = std::min(target, 2097152);                          // MAX_IR_LATENCY, ConvolverProcessor.h:198
+    return std::max(target, 1);
+}
+
+// in[len] at the device rate -> out[targetLength] (zero padded); returns targetLength.  out must hold irTargetLength() samples.
+inline int irPrepare(const double* in, int len, double sr, double targetSeconds, double* out)
+{
+    const int target = irTargetLength(sr, targetSeconds);
+    std::vector<double> w(in, in + std::max(len, 0));
+    if (sr > 0.0 && len > 0) irDcBlock(w.data(), len, sr, 1.0);
+    if (len > 0) irAsymmetricTukey(w.data(), len);
+    std::fill(out, out + target, 0.0);
+    const int copy = std::min(target, std::max(len, 0));
+    int fade = (int) std::round((double) copy * 0.02);
+    const int maxFade = std::max(256, (int) std::round(sr * 0.080));
+    fade = std::max(256, std::min(maxFade, fade));
+    fade = std::max(0, std::min(fade, copy - 1));
+    std::copy(w.begin(), w.begin() + copy, out);
+    if (fade > 0)
+    {
+        // juce::AudioBuffer::applyGainRamp(start, n, 1, 0): gain = 1 + i * (0 - 1) / n
+        const double inc = (0.0 - 1.0) / (double) fade;
+        double g = 1.0;
+        for (int i = 0; i < fade; ++i)
+        {
+            out[copy - fade + i] *= g;
+            g += inc;
+        }
+    }
+    return target;
+}
+
+// ------------------------------------------------------------------------------------------------
 inline double irFreqPeakGain(const double* const* ch, int nch, int len)
 {
     if (len <= 0 || nch <= 0) return 1.0;

@@ -276,6 +276,18 @@ EQPARAMETERS_DEFAULT_FREQS = (20.0, 32.0, 50.0, 80.0, 125.0, 200.0, 315.0, 500.0
                               16000.0, 19000.0, 20000.0, 22000.0, 24000.0)
 
 
+def ir_prepare(ir: np.ndarray, sample_rate: float, target_seconds: float) -> np.ndarray:
+    """One channel of a loaded IR (at the device rate) through the reference's DC blocker / Tukey window / trim + fade."""
+    lib = capi.load()
+    ir = np.ascontiguousarray(ir, dtype=np.float64)
+    n = lib.cpq_ir_target_length(sample_rate, target_seconds)
+    out = np.zeros(n)
+    got = lib.cpq_ir_prepare(ir.ctypes.data_as(_dp), ir.size, sample_rate, target_seconds, out.ctypes.data_as(_dp), n)
+    if got != n:
+        raise ValueError("cpq_ir_prepare")
+    return out
+
+
 def load_eq_preset(text: str, bands: Optional[Sequence[Band]] = None, total_gain_db: float = 0.0):
     """EQProcessor::loadFromTextFile on the contents of an EqualizerAPO / AutoEq preset; returns (bands, total_gain_db,
     ignored_filter_lines).  `bands` is the state before loading (default: convo::EQParameters{})."""

@@ -274,6 +274,15 @@ cpq_status cpq_ir_scale_factor(const double* ir_l, const double* ir_r, int len, 
  * nextPow2(4 len) points, written to out[len].  CPQ_ERR_UNSUPPORTED where the reference gives up and keeps the
  * linear-phase IR (FFT above 2^23 points, non-finite spectrum). */
 cpq_status cpq_ir_min_phase(const double* ir, int len, double* out);
+/* Host-only: what LoaderThread::doLoadStep does to one channel of a loaded IR (already at the device rate) before it reaches
+ * SetImpulse (convolver/ConvolverProcessor.LoaderThread.cpp:588-637): 1 Hz UltraHighRateDCBlocker, asymmetric Tukey window
+ * around the peak (ConvolverProcessor.ResampleAndFallback.cpp:111-196), copy into targetLength = min(int(sr * target_seconds),
+ * 2^21) samples (computeTargetIRLength, ConvolverProcessor.StateAndUI.cpp:942-957; zero padded) with a linear fade-out over the
+ * last 2 % (256 samples .. 80 ms) of the copied samples.  Returns the number of samples written (= cpq_ir_target_length), or -1
+ * on a bad argument / out_capacity too small.  Sample-rate conversion is r8brain-free-src in the reference (third party) and
+ * is not part of this library: resample first. */
+int cpq_ir_target_length(double sample_rate, double target_seconds);
+int cpq_ir_prepare(const double* ir, int len, double sample_rate, double target_seconds, double* out, int out_capacity);
 /* Host-only: IRAnalyzer::estimateMaxFrequencyResponseGain on its own (linear gain; 1.0 for an empty IR). */
 double cpq_ir_freq_peak_gain(const double* ir_l, const double* ir_r, int len);
 /* Host-only: the three stages' normalised coefficients {b0,b1,b2,a1,a2} x 3 as OutputFilter::prepare computes them. */

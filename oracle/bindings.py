@@ -203,6 +203,15 @@ class _Base:
         f.restype = C.c_double
         return float(f(_p(a), _p(b), a.size))
 
+    def ir_dc_block(self, x: np.ndarray, sr: float, cutoff: float = 1.0) -> np.ndarray:
+        """UltraHighRateDCBlocker::init(sr, cutoff) + process over one buffer (IR loader stage)."""
+        d = np.ascontiguousarray(x, dtype=np.float64).copy()
+        f = self._f("ir_dc_block")
+        f.argtypes = [_dp, C.c_int, C.c_double, C.c_double]
+        f.restype = None
+        f(_p(d), d.size, sr, cutoff)
+        return d
+
     # ---- EQ ----------------------------------------------------------------------------------
     def eq_design(self, type_: int, f: float, gain_db: float, q: float, sr: float) -> np.ndarray:
         out = np.zeros(6)
@@ -360,6 +369,18 @@ class Oracle(_Base):
         out = np.zeros(3)
         self.lib.cpqo_ir_scale_factor(_p(a), _p(b), a.size, _p(c), _p(d), 0 if c is None else c.size, cur_scale, _p(out))
         return float(out[0]), bool(out[1]), float(out[2])
+
+    def ir_prepare(self, ir: np.ndarray, sr: float, target_seconds: float) -> np.ndarray:
+        """DC blocker -> asymmetric Tukey -> trim to targetLength with fade-out (restated; the DC stage is pinned)."""
+        a = np.ascontiguousarray(ir, dtype=np.float64)
+        n = min(max(int(sr * float(np.float32(target_seconds))), 1), 2097152)
+        out = np.zeros(n)
+        f = self.lib.cpqo_ir_prepare
+        f.argtypes = [_dp, C.c_int, C.c_double, C.c_double, _dp]
+        f.restype = C.c_int
+        got = f(_p(a), a.size, sr, target_seconds, _p(out))
+        assert got == n
+        return out
 
     def outer_wet(self, x: np.ndarray, mix: float = 1.0) -> np.ndarray:
         d = np.ascontiguousarray(x, dtype=np.float64).copy()

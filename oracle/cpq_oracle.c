@@ -9,10 +9,12 @@
  * units compiled in place (oracle/Makefile) and tests/test_oracle_vs_ref.py checks this file against
  * it whenever it is present; tests/golden/ holds outputs of that library (generator:
  * tests/golden/make_golden.py) which tests/test_oracle_golden.py checks everywhere else.
- * PARITY UNPINNED for three pieces whose reference files need the whole JUCE application to compile and therefore cannot be
+ * PARITY UNPINNED for the pieces whose reference files need the whole JUCE application to compile and therefore cannot be
  * run here: cpqo_outer_mix (ConvolverProcessor::process' dry/wet mix), cpqo_ir_peak_latency / the arithmetic of
- * cpqo_ir_scale_factor around its pinned FFT stage (LoaderThread / IRConverter), and the uniform-partition extension flag
- * (not a reference mode at all).  Each says so at its definition; they restate the cited source lines only.
+ * cpqo_ir_scale_factor around its pinned FFT stage (LoaderThread / IRConverter), the Tukey window and trim / fade of
+ * cpqo_ir_prepare (its DC-blocker stage is pinned), cpqo_parse-free preset parsing lives in the product and is checked on the
+ * reference's own fixture only, and the uniform-partition extension flag (not a reference mode at all).  The dither branch
+ * (cpqo_epilogue_ex) IS pinned, bit for bit, against PsychoacousticDither.h compiled in place.  Each says so at its definition; they restate the cited source lines only.
  *
  * Written from the reference's behaviour, one callback at a time, deliberately in the reference's
  * own real-time formulation (ring buffers, FDL, time-sliced tail MAC) so that it is an independent
@@ -874,6 +876,82 @@ void cpqo_outer_mix(double* wet_io, const double* dry_in, long n, float mix, int
         const double a = v * wg, b = dry * dg;
         wet_io[i] = a + b;
     }
+}
+
+/* LoaderThread::doLoadStep after the resampler (convolver/ConvolverProcessor.LoaderThread.cpp:588-637), one channel:
+ * UltraHighRateDCBlocker at 1 Hz (UltraHighRateDCBlocker.h:78-188; PINNED against the header compiled in place), the asymmetric
+ * Tukey window (ConvolverProcessor.ResampleAndFallback.cpp:111-196) and the trim to targetLength with its fade-out
+ * (LoaderThread.cpp:619-637, ConvolverProcessor.StateAndUI.cpp:942-957) -- those two UNPINNED (their files need JUCE and
+ * r8brain to compile).  Returns targetLength; out must hold that many samples. */
+void cpqo_ir_dc_block(double* d, int n, double sr, double cutoff)
+{
+    double al[2] = { 1.0e-6, 1.0e-6 };
+    if (isfinite(sr) && sr > 0.0 && isfinite(cutoff) && cutoff > 0.0)
+        for (int i = 0; i < 2; ++i)
+        {
+            const double fc = cutoff * (i == 0 ? 1.0 - 0.1 : 1.0 + 0.1);
+            double a = -expm1(-(2.0 * CPQO_PI * fc / sr));
+            if (!isfinite(a) || a <= 0.0 || a >= 1.0) a = 1.0e-6;
+            al[i] = a;
+        }
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = 0; i < n; ++i)
+    {
+        double x = d[i];
+        s0 = fma(al[0], x - s0, s0);
+        x = x - s0;
+        s1 = fma(al[1], x - s1, s1);
+        x = x - s1;
+        d[i] = x;
+    }
+}
+
+int cpqo_ir_prepare(const double* in, int len, double sr, double target_seconds, double* out)
+{
+    int target = (int) (sr * (double) (float) target_seconds);
+    if (target > 2097152) target = 2097152;
+    if (target < 1) target = 1;
+    double* w = (double*) malloc(sizeof(double) * (size_t) (len > 0 ? len : 1));
+    memcpy(w, in, sizeof(double) * (size_t) len);
+    cpqo_ir_dc_block(w, len, sr, 1.0);
+    /* asymmetric Tukey around the (first) largest |sample| */
+    int peak = 0;
+    for (int i = 1; i < len; ++i)
+        if (fabs(w[i]) > fabs(w[peak])) peak = i;
+    double a_post = 0.05 + 0.033 * (log2((double) len) - 10.0);
+    if (a_post < 0.05) a_post = 0.05;
+    if (a_post > 0.25) a_post = 0.25;
+    if (peak > 0)
+    {
+        const int n = (int) floor(peak * 0.05);
+        for (int i = 0; i < n; ++i) w[i] *= 0.5 * (1.0 + cos(CPQO_PI / (peak * 0.05) * (double) i - CPQO_PI));
+    }
+    const double dist = (double) (len - 1 - peak);
+    if (dist > 1.0e-9)
+    {
+        const int start = peak + (int) ceil(dist * (1.0 - a_post));
+        const double scale = (CPQO_PI / a_post) / dist;
+        const double offset = (CPQO_PI / a_post) * (((double) start - (double) peak) / dist - (1.0 - a_post));
+        for (int i = start; i < len; ++i) w[i] *= 0.5 * (1.0 + cos(scale * (double) (i - start) + offset));
+    }
+    memset(out, 0, sizeof(double) * (size_t) target);
+    const int copy = target < len ? target : len;
+    int fade = (int) round((double) copy * 0.02);
+    int max_fade = (int) round(sr * 0.080);
+    if (max_fade < 256) max_fade = 256;
+    if (fade < 256) fade = 256;
+    if (fade > max_fade) fade = max_fade;
+    if (fade > copy - 1) fade = copy - 1;
+    if (fade < 0) fade = 0;
+    memcpy(out, w, sizeof(double) * (size_t) copy);
+    double g = 1.0;
+    for (int i = 0; i < fade; ++i)
+    {
+        out[copy - fade + i] *= g;
+        g += (0.0 - 1.0) / (double) fade;
+    }
+    free(w);
+    return target;
 }
 
 /* estimatePeakLatencySamples, convolver/ConvolverProcessor.LoaderThread.cpp:149-207: energy centroid of the first 99.9 % of

@@ -449,7 +449,15 @@ void cpqref_input_transform(double* data, int n, double gain)
     convo::input_transform::convertDoubleToDoubleHighQuality(data, data, n, gain);
 }
 
-int cpqref_abi_version(void) { return 4; }
+// UltraHighRateDCBlocker::init + process on one buffer (the IR loader runs it at 1 Hz, LoaderThread.cpp:590-598)
+void cpqref_ir_dc_block(double* data, int n, double sr, double cutoff)
+{
+    convo::UltraHighRateDCBlocker dc;
+    dc.init(sr, cutoff);
+    dc.process(data, n);
+}
+
+int cpqref_abi_version(void) { return 5; }
 
 // ------------------------------------------------------------------ dither (PsychoacousticDither.h, unmodified)
 // The header's only MKL dependency is the VSL uniform generator (:79,418-431); ref_shim/mkl_vsl.h replaces it with

@@ -247,3 +247,23 @@ def test_ir_minimum_phase_conversion():
         e_in, e_out = np.cumsum(ir ** 2), np.cumsum(got ** 2)
         assert np.all(e_out[: n // 2] >= e_in[: n // 2] - 1e-12) and e_out[n // 8] > 0.5 * e_out[-1]
     assert ir_min_phase(np.zeros(3 * 1024 * 1024)) is None      # FFT would exceed 2^23 points: the reference skips too
+
+
+def test_ir_prepare_matches_restatement_and_has_the_loader_shape(oracle):
+    """cpq_ir_prepare (host-only) = LoaderThread::doLoadStep after the resampler: DC blocker, asymmetric Tukey, trim + fade."""
+    from convopeq_b200.engine import ir_prepare
+    from tests import signals
+    for sr, n, secs in ((48000.0, 30000, 1.0), (96000.0, 200000, 1.5), (44100.0, 5000, 0.05), (48000.0, 700, 3.0)):
+        ir = signals.synth_ir(n, 3)
+        ir[n // 50] = 1.5                      # a clear peak away from the start: both tapers are exercised
+        got = ir_prepare(ir, sr, secs)
+        want = oracle.ir_prepare(ir, sr, secs)
+        target = min(max(int(sr * float(np.float32(secs))), 1), 2097152)
+        assert got.size == target == want.size
+        assert np.abs(got - want).max() <= 1e-15
+        copy = min(target, n)
+        assert np.all(got[copy:] == 0.0)
+        if copy > 300:
+            assert abs(got[copy - 1]) <= abs(ir).max() * 2.0 / 256   # the fade-out reaches (almost) zero at the last copied sample
+        if (n // 50) * 0.05 >= 1.0:
+            assert abs(got[0]) <= 1e-15            # the pre-taper starts at zero gain

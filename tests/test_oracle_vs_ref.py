@@ -186,3 +186,17 @@ def test_dither_restatement_is_bit_identical_to_reference(oracle, ref, sr, bits,
     assert np.array_equal(qm, wm) and np.array_equal(zm, zom)
     lsb = 1.0 / 2 ** (bits - 1)
     assert np.allclose(q / lsb, np.round(q / lsb))
+
+
+def test_ir_dc_blocker_stage_is_bit_identical_to_reference(oracle, ref):
+    """UltraHighRateDCBlocker.h compiled in place at the loader's 1 Hz (LoaderThread.cpp:590-598) against the restated stage."""
+    import ctypes as C
+    for sr, n in ((48000.0, 50000), (192000.0, 20000)):
+        x = signals.synth_ir(n, 5) + 0.01
+        want = ref.ir_dc_block(x, sr, 1.0)
+        d = np.ascontiguousarray(x).copy()
+        f = oracle.lib.cpqo_ir_dc_block
+        f.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_double, C.c_double]
+        f.restype = None
+        f(d.ctypes.data_as(C.POINTER(C.c_double)), n, sr, 1.0)
+        assert np.array_equal(d, want)
