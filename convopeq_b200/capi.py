@@ -76,7 +76,7 @@ EXPORTS = [
     "cpq_set_mix", "cpq_ir_peak_latency", "cpq_set_direct_head", "cpq_parse_eq_preset",
     "cpq_set_convolver_bypass", "cpq_set_peak_limiter", "cpq_set_input_gain", "cpq_set_partial_sources", "cpq_set_stream_window", "cpq_ir_scale_factor", "cpq_ir_freq_peak_gain", "cpq_ir_min_phase",
     "cpq_ir_target_length", "cpq_ir_prepare", "cpq_set_dither_uniforms_device", "cpq_set_streaming", "cpq_stream_position", "cpq_state_size", "cpq_export_state", "cpq_import_state",
-    "cpq_probe_dfma_tflops", "cpq_probe_dfma_latency",
+    "cpq_debug_check_guards", "cpq_probe_dfma_tflops", "cpq_probe_dfma_latency",
 ]
 
 _lib: Optional[C.CDLL] = None

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/cpq.h"
@@ -36,6 +37,17 @@ namespace cpq
         }                                                                                           \
     } while (0)
 
+// Guard mode (CPQ_GUARD=1 in the environment, a debugging aid: compute-sanitizer is not available on every pool): every
+// device buffer of the engine is allocated with a 256-byte canary before and after it; cpq_debug_check_guards() reports how
+// many canaries a kernel has overwritten.  tests/test_guards.py runs every kernel family under it.
+static const bool g_guard = [] { const char* e = getenv("CPQ_GUARD"); return e && atoi(e) != 0; }();
+constexpr size_t kGuardBytes = 256;
+struct GuardRegistry
+{
+    std::vector<std::pair<unsigned char*, size_t>> live;   // raw allocation, payload bytes
+    static GuardRegistry& get() { static GuardRegistry r; return r; }
+};
+
 template <typename T>
 struct DevBuf
 {
@@ -44,7 +56,19 @@ struct DevBuf
     ~DevBuf() { release(); }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p)
+        {
+            if (g_guard)
+            {
+                unsigned char* raw = reinterpret_cast<unsigned char*>(p) - kGuardBytes;
+                auto& v = GuardRegistry::get().live;
+                for (size_t i = 0; i < v.size(); ++i)
+                    if (v[i].first == raw) { v.erase(v.begin() + (long) i); break; }
+                cudaFree(raw);
+            }
+            else
+                cudaFree(p);
+        }
         p = nullptr;
         n = 0;
     }
@@ -52,11 +76,42 @@ struct DevBuf
     {
         if (count <= n && p) return cudaSuccess;
         release();
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T));
-        if (e == cudaSuccess) n = count;
-        return e;
+        const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+        if (!g_guard)
+        {
+            cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), bytes);
+            if (e == cudaSuccess) n = count;
+            return e;
+        }
+        const size_t padded = (bytes + 15) / 16 * 16;
+        unsigned char* raw = nullptr;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&raw), padded + 2 * kGuardBytes);
+        if (e != cudaSuccess) return e;
+        cudaMemset(raw, 0xA5, kGuardBytes);
+        cudaMemset(raw + kGuardBytes + padded, 0xA5, kGuardBytes);
+        GuardRegistry::get().live.push_back({ raw, padded });
+        p = reinterpret_cast<T*>(raw + kGuardBytes);
+        n = count;
+        return cudaSuccess;
     }
 };
+
+// number of overwritten canaries among the live guarded buffers (0 = clean); -1 when guard mode is off
+static int checkGuards()
+{
+    if (!g_guard) return -1;
+    cudaDeviceSynchronize();
+    int bad = 0;
+    std::vector<unsigned char> h(kGuardBytes);
+    for (auto& g : GuardRegistry::get().live)
+        for (int side = 0; side < 2; ++side)
+        {
+            cudaMemcpy(h.data(), g.first + (side ? kGuardBytes + g.second : 0), kGuardBytes, cudaMemcpyDeviceToHost);
+            for (unsigned char c : h)
+                if (c != 0xA5) { ++bad; break; }
+        }
+    return bad;
+}
 
 struct EqSet
 {
@@ -2302,6 +2357,8 @@ struct cpq_engine : Engine {};
 extern "C" {
 
 int cpq_abi_version(void) { return CPQ_ABI_VERSION; }
+
+int cpq_debug_check_guards(void) { return cpq::checkGuards(); }
 
 const char* cpq_status_string(cpq_status s)
 {

@@ -357,6 +357,10 @@ cpq_status cpq_get_eq_state(cpq_handle h, int stream, double* out /* [n_channels
 void* cpq_cuda_stream(cpq_handle h);                 /* cudaStream_t the kernels are launched on */
 int64_t cpq_kernel_launch_count(cpq_handle h);       /* launches since create */
 
+/* Debugging aid: with CPQ_GUARD=1 in the environment every device buffer the library allocates carries a 256-byte canary on
+ * either side; returns the number of canaries that have been overwritten (0 = clean), -1 when guard mode is off. */
+int cpq_debug_check_guards(void);
+
 /* Diagnostics (bench.py's FP64 roofline denominator): measured DFMA throughput in TFLOP/s (2 flops per DFMA) of `device`
  * over `iters` dependent-chain iterations per thread, and the dependent-issue latency of one DFMA in cycles; < 0 on error. */
 double cpq_probe_dfma_tflops(int device, int iters);
