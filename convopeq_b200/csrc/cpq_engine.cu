@@ -4,6 +4,7 @@
 //   convolverRt().process -> eqRt().process(block, params, cache) -> makeup gain -> processOutputDouble
 // (AudioEngine.Processing.DSPCoreDouble.cpp:386-414,465-469,577-663) for a batch of independent streams.
 // There is no CPU path: every compute entry point needs a CUDA device.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -465,6 +466,37 @@ cpq_status Engine::launchInvLarge(int log2P, const InvArgs& a)
 
 constexpr size_t kMaxDynSmem = 227 * 1024;   // opt-in limit per CTA on sm_100
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encodeTiledFn()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// rank-3 FP64 tensor [d2][d1][d0 doubles] with a box of [1][box1][64 doubles]; out-of-bounds elements read as zero
+static bool encodeSpectraMap(MacTensorMap& out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1)
+{
+    EncodeTiledFn fn = encodeTiledFn();
+    if (!fn) return false;
+    static_assert(sizeof(CUtensorMap) == sizeof(MacTensorMap), "tensor map size");
+    CUtensorMap tm;
+    const cuuint64_t gdim[3] = { d0, d1, d2 };
+    const cuuint64_t gstride[2] = { d0 * sizeof(double), d0 * d1 * sizeof(double) };
+    const cuuint32_t box[3] = { 64, box1, 1 };
+    const cuuint32_t estride[3] = { 1, 1, 1 };
+    if (fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    std::memcpy(out.bytes, &tm, sizeof(tm));
+    return true;
+}
+
 template <int LOG2P>
 static cudaError_t fftAttrs()
 {
@@ -496,6 +528,7 @@ cpq_status Engine::setKernelAttributes()
     CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
     CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
     CPQ_CUDA(cudaFuncSetAttribute(mac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem));
+    CPQ_CUDA(cudaFuncSetAttribute(mac_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem));
     CPQ_CUDA(cudaFuncSetAttribute(dither_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kDitherSmemBytes));
     return CPQ_OK;
 }
@@ -1334,15 +1367,15 @@ cpq_status Engine::launchEq(EqArgs& a)
     const unsigned grid = (unsigned) a.nSeq * (unsigned) a.nRuns;
     if (lookback)
     {
-        if (a.doEq && anyPar) eq_kernel<true, true, true, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
-        else if (a.sumsqIn || a.sumsqOut || a.nPeers > 0) eq_kernel<true, false, true, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
-        else if (a.postMask || a.finalClamp || a.limFlag) eq_kernel<true, false, false, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
-        else eq_kernel<false, false, false, true><<<grid, kEqThreads, kEqSmemBytes, stream>>>(a);
+        if (a.doEq && anyPar) eq_kernel<true, true, true, true><<<grid, kEqThreads, eqSmemBytes(true, true), stream>>>(a);
+        else if (a.sumsqIn || a.sumsqOut || a.nPeers > 0) eq_kernel<true, false, true, true><<<grid, kEqThreads, eqSmemBytes(true, true), stream>>>(a);
+        else if (a.postMask || a.finalClamp || a.limFlag) eq_kernel<true, false, false, true><<<grid, kEqThreads, eqSmemBytes(true, true), stream>>>(a);
+        else eq_kernel<false, false, false, true><<<grid, kEqThreads, eqSmemBytes(true, false), stream>>>(a);
     }
-    else if (a.doEq && anyPar) eq_kernel<true, true, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
-    else if (a.sumsqIn || a.sumsqOut || a.nPeers > 0) eq_kernel<true, false, true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
-    else if (a.postMask || a.finalClamp || a.limFlag) eq_kernel<true><<<grid, kEqThreads, kEqSmemBytesPost, stream>>>(a);
-    else eq_kernel<false><<<grid, kEqThreads, kEqSmemBytes, stream>>>(a);
+    else if (a.doEq && anyPar) eq_kernel<true, true, true><<<grid, kEqThreads, eqSmemBytes(false, true), stream>>>(a);
+    else if (a.sumsqIn || a.sumsqOut || a.nPeers > 0) eq_kernel<true, false, true><<<grid, kEqThreads, eqSmemBytes(false, true), stream>>>(a);
+    else if (a.postMask || a.finalClamp || a.limFlag) eq_kernel<true><<<grid, kEqThreads, eqSmemBytes(false, true), stream>>>(a);
+    else eq_kernel<false><<<grid, kEqThreads, eqSmemBytes(false, false), stream>>>(a);
     ++launches;
     CPQ_CUDA(cudaGetLastError());
     return CPQ_OK;
@@ -2040,6 +2073,23 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                     return CPQ_ERR_UNSUPPORTED;
                 }
                 dim3 grid((unsigned) binTiles, (unsigned) ((K[li] + fpc - 1) / fpc), (unsigned) ns);
+                // tensor-map staging (one TMA copy per 64-frame block, no CTA barrier in the frame loop) for filters of up to
+                // 65 taps; longer ones (uniform-partition extension) keep the row-copy kernel
+                static const int tmaEnv = [] { const char* e = getenv("CPQ_MAC_TMA"); return e ? atoi(e) : 1; }();   // tuning knob
+                MacTensorMap tmX, tmH;
+                if (tmaEnv && a.qEnd - a.qBegin <= kMacTmaMaxTaps && macTmaSmemBytes(a.qEnd - a.qBegin) <= kMaxDynSmem &&
+                    encodeSpectraMap(tmX, layer[li].X.p, 2 * (uint64_t) l.partSize, (uint64_t) xRows[li], (uint64_t) ns, (uint32_t) kMacSuper) &&
+                    encodeSpectraMap(tmH, layer[li].H.p, 2 * (uint64_t) l.partSize, (uint64_t) l.numPartsIR, (uint64_t) nH, (uint32_t) (a.qEnd - a.qBegin)))
+                {
+                    mac_tma_kernel<<<grid, kMacThreads, macTmaSmemBytes(a.qEnd - a.qBegin), stream>>>(a, tmX, tmH);
+                    ++launches;
+                    CPQ_CUDA(cudaGetLastError());
+                    if (strm && fdlRows[li] > 0)
+                        CPQ_CUDA(cudaMemcpy2DAsync(fdl[li].p + (size_t) s0 * fdlRows[li] * l.partSize, (size_t) fdlRows[li] * l.partSize * sizeof(double2),
+                                                   layer[li].X.p + (size_t) K[li] * l.partSize, (size_t) xRows[li] * l.partSize * sizeof(double2),
+                                                   (size_t) fdlRows[li] * l.partSize * sizeof(double2), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
+                    continue;
+                }
                 mac_kernel<<<grid, kMacThreads, smem, stream>>>(a);
                 ++launches;
                 CPQ_CUDA(cudaGetLastError());

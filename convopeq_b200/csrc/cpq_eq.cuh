@@ -89,7 +89,12 @@ constexpr int kEqStageDc = CPQ_NUM_BANDS + 3;
 // output-stage constants (only allocated when such a stage runs)
 // mailboxes: agg[stage][8] warp aggregates + tin[stage] tile-in states (double2 each), one mbarrier per mailbox entry
 constexpr int kEqMail = kEqStages * 9;
-constexpr int kEqSmemDoubles = kEqCThreads * kEqPad + CPQ_NUM_BANDS * kEqcStride + kEqMail * 2 + kEqMail + 2;
+__host__ __device__ constexpr int eqSmemDoubles(bool lb) { return kEqCThreads * kEqPad + CPQ_NUM_BANDS * (lb ? kEqcStride : kEqcPw) + kEqMail * 2 + kEqMail + 2; }
+constexpr size_t eqSmemBytes(bool lb, bool post)
+{
+    return (size_t) (eqSmemDoubles(lb) + (post ? kEqPostStages * (lb ? kEqcStride : kEqcPw) : 0)) * sizeof(double);
+}
+constexpr int kEqSmemDoubles = eqSmemDoubles(true);
 constexpr size_t kEqSmemBytes = (size_t) kEqSmemDoubles * sizeof(double);
 constexpr size_t kEqSmemBytesPost = kEqSmemBytes + (size_t) kEqPostStages * kEqcStride * sizeof(double);
 
@@ -472,15 +477,17 @@ template <bool POST, bool PAR = false, bool STATS = false, bool LB = false>
 __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_kernel(EqArgs a)
 {
     const unsigned postMask = POST ? a.postMask : 0u;
+    // band constants in shared memory: the chained form has no use for the Pw table at the end of each band's block
+    constexpr int kStr = LB ? kEqcStride : kEqcPw;
     extern __shared__ __align__(16) double eq_smem[];
     double* tile = eq_smem;                                        // [7 warps][32 lanes][18]
     double* cst = tile + kEqCThreads * kEqPad;                     // this sequence's band constants
-    double2* agg = reinterpret_cast<double2*>(cst + CPQ_NUM_BANDS * kEqcStride);  // [stage][8] zero-state response of warp w's segment
+    double2* agg = reinterpret_cast<double2*>(cst + CPQ_NUM_BANDS * kStr);  // [stage][8] zero-state response of warp w's segment
     double2* tin = agg + kEqStages * 8;                                           // [stage] state at the start of the tile
     unsigned long long* mbA = reinterpret_cast<unsigned long long*>(tin + kEqStages);   // [stage][8] "aggregate posted" (one phase each)
     unsigned long long* mbT = mbA + kEqStages * 8;                                // [stage] "tile-in state posted"
     unsigned* sTicket = reinterpret_cast<unsigned*>(mbT + kEqStages);
-    double* cstPost = eq_smem + kEqSmemDoubles;                                   // output-stage constants (present iff postMask)
+    double* cstPost = eq_smem + eqSmemDoubles(LB);                                   // output-stage constants (present iff postMask)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) *sTicket = atomicAdd(a.chain.ticket, 1u);
@@ -503,12 +510,18 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
     if (a.doEq)
     {
         const double* __restrict__ src = a.eqc + (size_t) set * CPQ_NUM_BANDS * kEqcStride;
-        for (int i = tid; i < CPQ_NUM_BANDS * kEqcStride / 2; i += kEqThreads)
-            reinterpret_cast<double2*>(cst)[i] = __ldg(reinterpret_cast<const double2*>(src) + i);
+        for (int i = tid; i < CPQ_NUM_BANDS * kStr / 2; i += kEqThreads)
+        {
+            const int b = i / (kStr / 2), o = i - b * (kStr / 2);
+            reinterpret_cast<double2*>(cst)[i] = __ldg(reinterpret_cast<const double2*>(src + (size_t) b * kEqcStride) + o);
+        }
     }
     if (postMask)
-        for (int i = tid; i < kEqPostStages * kEqcStride / 2; i += kEqThreads)
-            reinterpret_cast<double2*>(cstPost)[i] = __ldg(reinterpret_cast<const double2*>(a.postc) + i);
+        for (int i = tid; i < kEqPostStages * kStr / 2; i += kEqThreads)
+        {
+            const int b = i / (kStr / 2), o = i - b * (kStr / 2);
+            reinterpret_cast<double2*>(cstPost)[i] = __ldg(reinterpret_cast<const double2*>(a.postc + (size_t) b * kEqcStride) + o);
+        }
     __syncthreads();   // constants + cleared flags visible; the only CTA-wide barrier besides the ticket
 
     // ---- tile-to-tile chain: records (seq, tile, band) in global memory, written by the last warp of a tile and read by
@@ -1053,7 +1066,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
             for (int b = 0; b < CPQ_NUM_BANDS; ++b)
             {
                 if (!((mask >> b) & 1u)) continue;
-                const double* __restrict__ bc = cst + b * kEqcStride;
+                const double* __restrict__ bc = cst + b * kStr;
                 unsigned dummy = 0;
                 if (!first) loadBlock(dummy);
                 first = false;
@@ -1127,7 +1140,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
             for (int b = 0; b < CPQ_NUM_BANDS; ++b)
             {
                 if (!((mask >> b) & 1u)) continue;   // uniform per CTA
-                const double* __restrict__ bc = cst + b * kEqcStride;
+                const double* __restrict__ bc = cst + b * kStr;
                 double ic1, ic2;
                 bandStart(b, bc, true, ic1, ic2);
                 linked = b;
@@ -1179,7 +1192,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
             for (int b = 0; b < CPQ_NUM_BANDS; ++b)
             {
                 if (!((mask >> b) & 1u)) continue;
-                const double* __restrict__ bc = cst + b * kEqcStride;
+                const double* __restrict__ bc = cst + b * kStr;
                 double ic1, ic2;
                 bandStart(b, bc, b > linked, ic1, ic2);
                 if (eq_pass2_exact(x, ic1, ic2, bc, sat)) atomicExch(a.fault, 1u);
@@ -1192,7 +1205,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
             for (int b = CPQ_NUM_BANDS; b < kEqStages; ++b)
             {
                 if (!((mask >> b) & 1u)) continue;
-                const double* __restrict__ bc = cstPost + (b - CPQ_NUM_BANDS) * kEqcStride;
+                const double* __restrict__ bc = cstPost + (b - CPQ_NUM_BANDS) * kStr;
                 double ic1, ic2;
                 preStage(b, gainDone, makeupDone);
                 bandStart(b, bc, true, ic1, ic2);

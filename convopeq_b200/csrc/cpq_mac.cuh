@@ -391,4 +391,129 @@ __global__ void __launch_bounds__(kMacThreads, CPQ_MAC_MINBLOCKS) mac_kernel(Mac
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The same multiply-accumulate with both operands staged by tensor-map TMA copies (cp.async.bulk.tensor, SASS UTMALDG):
+// X is a rank-3 tensor [sequence][frame][bin], a box of 64 frames x 32 bins (32 KB) is ONE copy instead of 64 row copies
+// issued through an ELECT loop, frames outside [-hist, K) -- the zero history of a Reset engine -- are the out-of-bounds fill
+// of the copy engine (no zero stores, no proxy fence), and the H tile [Q][32] is one copy as well.  The ring is NB blocks of
+// 64 rows on full / empty mbarriers: a warp waits only for the block it is about to read, the producer (thread 0) only for
+// the block it is about to overwrite -- there is no CTA barrier in the frame loop (the row-copy kernel spent 8 % of its
+// samples on that barrier and 10 % waiting for rows it had requested one super-step earlier: here the request for block s + 1
+// goes out before block s is touched and block s + 1 is not needed before super-step s + 1).  Used when the tap count is at
+// most 65 (one block of history); the row-copy kernel above keeps the uniform-partition extension's longer filters.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMacTmaNB = 3;                       // history | current | prefetch
+constexpr int kMacTmaMaxTaps = kMacSuper + 1;      // nq - 1 <= 64
+inline size_t macTmaSmemBytes(int nq) { return ((size_t) nq * kMacRowBytes + 127) / 128 * 128 + (size_t) kMacTmaNB * kMacSuper * kMacRowBytes + 128; }
+
+__device__ __forceinline__ void tma_load_3d(void* dstSmem, const void* tmap, int c0, int c1, int c2, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(dstSmem)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct alignas(64) MacTensorMap { unsigned char bytes[128]; };   // CUtensorMap (opaque here; encoded on the host)
+
+__global__ void __launch_bounds__(kMacThreads, CPQ_MAC_MINBLOCKS)
+mac_tma_kernel(MacArgs a, const __grid_constant__ MacTensorMap tmX, const __grid_constant__ MacTensorMap tmH)
+{
+    extern __shared__ __align__(128) unsigned char mac_smem[];
+    constexpr int NB = kMacTmaNB;
+    constexpr int R = NB * kMacSuper;
+    const int nq = a.qEnd - a.qBegin;
+    const size_t hBytes = ((size_t) nq * kMacRowBytes + 127) / 128 * 128;
+    double2* Hs = reinterpret_cast<double2*>(mac_smem);                      // [nq][32]
+    double2* ring = reinterpret_cast<double2*>(mac_smem + hBytes);            // [R][32]: frame f in row (f - base) mod R
+    uint64_t* full = reinterpret_cast<uint64_t*>(mac_smem + hBytes + (size_t) R * kMacRowBytes);   // [NB]
+    uint64_t* empty = full + NB;                                              // [NB]
+    uint64_t* hbar = empty + NB;
+    const int tid = threadIdx.x;
+    const int ml = tid & (kMacBins - 1);
+    const int g = tid / kMacBins;
+    const int m0 = blockIdx.x * kMacBins;
+    const int seq = blockIdx.z;
+    const int kc0 = blockIdx.y * a.framesPerCta;
+    const int kc1 = min(a.K, kc0 + a.framesPerCta);
+    const int hrow = a.hSeqMod > 0 ? ((a.seqBase + seq) % a.hSeqMod) : (a.seqBase + seq);
+    double2* __restrict__ Y = a.Y + (size_t) seq * a.K * a.P + m0 + ml;
+    constexpr int ringBytes = R * kMacRowBytes;
+    const int base = kc0 - a.qBegin;                  // frame held by ring row 0 of block 0
+    const int jmin = nq > 1 ? -1 : 0;                 // first block this CTA ever loads (one block of history)
+
+    if (tid == 0)
+    {
+        for (int i = 0; i < NB; ++i)
+        {
+            mbar_init(full + i, 1);
+            mbar_init(empty + i, kMacGroups);
+        }
+        mbar_init(hbar, 1);
+    }
+    __syncthreads();
+    // block j = frames base + 64 j .. + 63 -> ring slot j mod NB; the k-th use of a slot completes phase k of its barriers
+    auto slotOf = [&](int j) { return ((j - jmin) % NB); };
+    auto useOf = [&](int j) { return (j - jmin) / NB; };
+    auto loadBlock = [&](int j) {
+        const int sl = slotOf(j);
+        mbar_arrive_expect_tx(full + sl, (unsigned) kMacSuper * kMacRowBytes);
+        tma_load_3d(ring + (size_t) sl * kMacSuper * kMacBins, &tmX, 2 * m0, base + kMacSuper * j + a.hist, seq, full + sl);
+    };
+    if (tid == 0)
+    {
+        mbar_arrive_expect_tx(hbar, (unsigned) nq * kMacRowBytes);
+        tma_load_3d(Hs, &tmH, 2 * m0, a.qBegin, hrow, hbar);
+        for (int j = jmin; j <= 0; ++j) loadBlock(j);
+    }
+    mbar_wait(hbar, 0);
+    if (jmin < 0) mbar_wait(full + slotOf(jmin), 0);
+
+    // ring row of frame f: (f - base) mod R, with block jmin in slot 0: row = (f - base - 64 jmin) mod R
+    const int rowShift = -kMacSuper * jmin;
+    const char* ringB = reinterpret_cast<const char*>(ring) + ml * (int) sizeof(double2);
+    const char* hsB = reinterpret_cast<const char*>(Hs) + ml * (int) sizeof(double2);
+    const bool packedTile = (m0 == 0);
+    const bool slot0 = packedTile && ml == 0;
+    const int nSteps = (kc1 - kc0 + kMacSuper - 1) / kMacSuper;
+    for (int s = 0; s < nSteps; ++s)
+    {
+        if (tid == 0 && s + 1 < nSteps)
+        {
+            // block s + 1 replaces block s + 1 - NB, which every warp released at the end of super-step s - 1
+            const int j = s + 1;
+            if (j - NB >= jmin) mbar_wait(empty + slotOf(j), (unsigned) (useOf(j) - 1) & 1u);
+            loadBlock(j);
+        }
+        mbar_wait(full + slotOf(s), (unsigned) useOf(s) & 1u);
+        const int ks = kc0 + s * kMacSuper + g * kMacKT;
+        if (ks < kc1)
+        {
+            double2 acc[kMacKT];
+            int r = (ks - a.qBegin - base + rowShift) % R;     // = (ks - kc0 + rowShift) mod R, never negative
+            if (packedTile) mac_run<true>(acc, hsB, ringB, r * kMacRowBytes, ringBytes, nq, slot0);
+#if CPQ_MAC_GAUSS
+            else mac_run3<true>(acc, hsB, ringB, r * kMacRowBytes, ringBytes, nq);   // R and the run start are multiples of eight
+#else
+            else mac_run<false>(acc, hsB, ringB, r * kMacRowBytes, ringBytes, nq, slot0);
+#endif
+#pragma unroll
+            for (int i = 0; i < kMacKT; ++i)
+                if (ks + i < kc1) Y[(size_t) (ks + i) * a.P] = acc[i];
+        }
+        // this warp is done with the oldest block of the window (block s - 1; with one tap there is no history block: block s)
+        __syncwarp();
+        if (ml == 0)
+        {
+            const int jr = nq > 1 ? s - 1 : s;
+            if (jr >= jmin) mbar_arrive(empty + slotOf(jr));
+        }
+    }
+}
+
 } // namespace cpq
