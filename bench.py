@@ -337,11 +337,18 @@ def other_workloads(local, dev, cfg4_eng, cfg4_x, T4):
             r = measure_workload(cfg4_eng, cfg4_x, T4, capi.STAGE_ALL, steps=2, warm=1, host=False)
         finally:
             cfg4_eng.set_epilogue(1.0, 0)
-        sm_hz = 1.9e9
-        r["serial_floor_ms"] = T4 * 130.0 / sm_hz * 1e3
-        r["workload"] = ("cfg4 with the 24-bit dither branch (PsychoacousticDither, injected uniforms resident on the device): the shaper is "
-                         "one dependent chain of 16 FP64 operations per sample and sequence (about 130 cycles), so T x 130 cycles is the "
-                         "floor of that stage whatever the batch; it runs on side streams beside the next chunks' transforms")
+        # the stage on its own (every sequence at once, 64 warps): what the serial recurrence costs whatever runs beside it
+        try:
+            cfg4_eng.set_epilogue(1.0, 24)
+            cfg4_eng.set_dither_uniforms_device(u.data_ptr(), T4)
+            r["dither_stage_alone_ms"] = measure_workload(cfg4_eng, cfg4_x, T4, capi.STAGE_EPILOGUE, steps=2, warm=1, host=False)["device_ms"]
+        finally:
+            cfg4_eng.set_epilogue(1.0, 0)
+        r["workload"] = ("cfg4 with the 24-bit dither branch (PsychoacousticDither, injected uniforms resident on the device).  The shaper is "
+                         "one dependent chain of 18 FP64-pipe operations per sample and sequence (11 DFMA, DADD, DMUL, FRND, DMUL, DADD, DSETP, "
+                         "FSEL), serial in time by construction and chaotic, so it cannot be scanned or reassociated; dither_stage_alone_ms is "
+                         "that chain over T samples with every sequence running at once (64 warps), and the floor of the stage whatever the "
+                         "batch size.  It starts when a chunk's EQ is done; the transforms fill the register file, so it does not run beside them")
         del u
         return r
 

@@ -591,7 +591,13 @@ cpq_status Engine::init(const cpq_config* c)
     CPQ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CPQ_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
     CPQ_CUDA(cudaStreamCreateWithFlags(&sOut, cudaStreamNonBlocking));
-    for (auto& d : sDither) CPQ_CUDA(cudaStreamCreateWithFlags(&d, cudaStreamNonBlocking));
+    {
+        // highest priority: when an SM frees resources the waiting dither CTA (one warp) is placed before the next CTA of the
+        // running transform, so the serial stage starts as early as it can and runs beside the rest of the call
+        int prLow = 0, prHigh = 0;
+        CPQ_CUDA(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+        for (auto& d : sDither) CPQ_CUDA(cudaStreamCreateWithPriority(&d, cudaStreamNonBlocking, prHigh));
+    }
     for (auto& e : ev) CPQ_CUDA(cudaEventCreate(&e));
     nH = cfg.shared_ir ? cfg.n_channels : nSeq;
     haveImpulse.assign((size_t) nH, 0);

@@ -1621,10 +1621,11 @@ __global__ void ms_kernel(MsArgs a)
 // sample whatever the batch size -- the floor of this stage is T x 130 cycles (33 ms for 480 256 samples at 1.9 GHz), so the
 // engine runs it on a side stream where it overlaps the next chunk's transforms.
 //
-// One lane per sequence, a warp = 32 sequences.  Memory goes through shared memory in [32 sequences][32 samples] tiles so that
-// every global access is a full 256-byte row segment (the one-thread-per-sequence form touched 32 sectors per warp load):
-// cp.async brings tile k+1 (signal + 2 uniforms per sample) while tile k is computed; results are written back from shared
-// memory as 16-byte stores, half a row per lane group.
+// One lane per sequence, a warp = 32 sequences.  Memory goes through shared memory in [32 sequences][12 samples] tiles (the
+// one-thread-per-sequence form touched 32 sectors per warp load): cp.async brings tile k+1 (signal + 2 uniforms per sample)
+// while tile k is computed; results are written back from shared memory as 16-byte stores.  A tile is twelve samples because
+// that is the order of the shaper: the loop over a tile is fully unrolled and the error history rotates through twelve named
+// registers, one turn per tile, instead of being shifted by eleven moves per sample.
 // ---------------------------------------------------------------------------------------------
 struct DitherArgs
 {
@@ -1641,16 +1642,52 @@ struct DitherArgs
     int finalClamp;           // after the quantiser: bit 0 scrub, bit 1 clamp to +-kOutputHeadroom (DSPCoreDouble.cpp:665-691, 712-737)
 };
 
-constexpr int kDthTile = 32;                 // samples per tile and sequence
+constexpr int kDthTile = 24;                 // samples per tile and sequence: a multiple of the order of the shaper, so the 12-deep error
+                                             // history rotates through registers by name, two full turns per tile (no moves)
+constexpr int kDthStages = 3;                // tiles in flight: the copy of tile k + 2 is issued before tile k is computed
 constexpr int kDthRow = kDthTile + 2;        // signal row pitch in doubles (16-byte aligned rows)
 constexpr int kDthURow = 2 * kDthTile + 2;   // uniform row pitch
 constexpr int kDthBufDoubles = 32 * kDthRow + 32 * kDthURow;
-constexpr size_t kDitherSmemBytes = (size_t) 2 * kDthBufDoubles * sizeof(double);
+constexpr size_t kDitherSmemBytes = (size_t) kDthStages * kDthBufDoubles * sizeof(double);
 
 __device__ __forceinline__ void dthCpAsync16(void* smem, const void* gmem)
 {
     const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+
+// one sample: e[] is the error history, logical z[t] = e[(t + ROT) % 12]; the new error replaces the oldest entry
+template <int ROT>
+__device__ __forceinline__ double dither_sample(double x, double2 uu, double (&e)[12], const double (&c)[12], bool roleLeft, double scale,
+                                                double invScale, int finalClamp)
+{
+    constexpr double kHeadroom = 0.8912509381337456;
+    double shaped = __dmul_rn(c[1], e[(1 + ROT) % 12]);
+    shaped = __fma_rn(c[0], e[ROT % 12], shaped);
+#pragma unroll
+    for (int t = 2; t < 12; ++t) shaped = __fma_rn(c[t], e[(t + ROT) % 12], shaped);
+    const double tpdf = __dadd_rn(__dadd_rn(uu.x, -0.5), __dadd_rn(uu.y, -0.5));
+    const double pre = roleLeft ? __fma_rn(x, kHeadroom, __dmul_rn(tpdf, scale)) : __fma_rn(tpdf, scale, __dmul_rn(x, kHeadroom));
+    const double tmp = __dadd_rn(pre, shaped);
+    const double q = __dmul_rn(rint(__dmul_rn(tmp, invScale)), scale);
+    double err = __dadd_rn(tmp, -q);
+    if (fabs(err) < 1.0e-20) err = 0.0;
+    e[(11 + ROT) % 12] = err;   // the oldest entry (logical z[11]) becomes the newest of the next sample (ROT - 1)
+    double o = q;
+    if ((finalClamp & 1) && !(fabs(o) < 1.0e300)) o = 0.0;
+    if (finalClamp & 2) o = fmin(fmax(o, -kHeadroom), kHeadroom);
+    return o;
+}
+
+template <int J>
+__device__ __forceinline__ void dither_unrolled(double* mine, const double* myU, double (&e)[12], const double (&c)[12], bool roleLeft,
+                                                double scale, double invScale, int finalClamp)
+{
+    if constexpr (J < kDthTile)
+    {
+        mine[J] = dither_sample<(24 - J) % 12>(mine[J], *reinterpret_cast<const double2*>(myU + 2 * J), e, c, roleLeft, scale, invScale, finalClamp);
+        dither_unrolled<J + 1>(mine, myU, e, c, roleLeft, scale, invScale, finalClamp);
+    }
 }
 
 __global__ void __launch_bounds__(32) dither_kernel(DitherArgs a)
@@ -1663,43 +1700,42 @@ __global__ void __launch_bounds__(32) dither_kernel(DitherArgs a)
     const bool live = lane < nLocal;
     const bool roleLeft = a.nch == 2 && ((a.seqBase + seq) % 2) == 0;
     const int64_t nTiles = (a.T + kDthTile - 1) / kDthTile;
+    constexpr int kSigPieces = kDthTile / 2;               // 16-byte pieces per signal row
 
     auto issue = [&](int64_t tile, int buf) {
         double* sig = dthSmem + (size_t) buf * kDthBufDoubles;
         double* uni = sig + 32 * kDthRow;
         const int64_t t0 = tile * kDthTile;
         const int n = (int) (a.T - t0 < (int64_t) kDthTile ? a.T - t0 : (int64_t) kDthTile);      // even (T is even)
-        // signal: n/2 16-byte pieces per row; lane = piece + 16 * (row & 1)
-        for (int r = lane >> 4; r < nLocal; r += 2)
-        {
-            const int pc = lane & 15;
-            if (2 * pc < n) dthCpAsync16(sig + r * kDthRow + 2 * pc, a.io + (size_t) (seq0 + r) * a.ioStride + t0 + 2 * pc);
-        }
-        // uniforms: n 16-byte pieces per row (u1,u2 of one sample), one row per step
+        // signal: n/2 16-byte pieces per row, 32 / kSigPieces rows per step
+        constexpr int rowsPerStep = 32 / kSigPieces;
+        const int rr = lane / kSigPieces, pc = lane % kSigPieces;
+        if (rr < rowsPerStep)
+            for (int r = rr; r < nLocal; r += rowsPerStep)
+                if (2 * pc < n) dthCpAsync16(sig + r * kDthRow + 2 * pc, a.io + (size_t) (seq0 + r) * a.ioStride + t0 + 2 * pc);
+        // uniforms: n 16-byte pieces per row (u1, u2 of one sample): one row per step
         for (int r = 0; r < nLocal; ++r)
             if (lane < n) dthCpAsync16(uni + r * kDthURow + 2 * lane, a.uniforms + ((size_t) (seq0 + r) * a.T + t0 + lane) * 2);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    double z[12];
+    double e[12];   // e[t] = logical z[t] between tiles
 #pragma unroll
-    for (int i = 0; i < 12; ++i) z[i] = a.z[(size_t) seq * 12 + i];
+    for (int i = 0; i < 12; ++i) e[i] = a.z[(size_t) seq * 12 + i];
     double c[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) c[i] = a.coeff[i];
-    constexpr double kHeadroom = 0.8912509381337456;
 
     issue(0, 0);
+    if (nTiles > 1) issue(1, 1);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
     for (int64_t tile = 0; tile < nTiles; ++tile)
     {
-        const int buf = (int) (tile & 1);
-        if (tile + 1 < nTiles)
-        {
-            issue(tile + 1, buf ^ 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        }
-        else
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const int buf = (int) (tile % kDthStages);
+        // the buffer of tile + 2 held tile - 1, whose write-back ended with a __syncwarp
+        if (tile + 2 < nTiles) issue(tile + 2, (int) ((tile + 2) % kDthStages));
+        else asm volatile("cp.async.commit_group;" ::: "memory");   // keep one group per iteration so that wait_group 2 means "tile landed"
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
         __syncwarp();
         double* sig = dthSmem + (size_t) buf * kDthBufDoubles;
         const double* uni = sig + 32 * kDthRow;
@@ -1708,42 +1744,34 @@ __global__ void __launch_bounds__(32) dither_kernel(DitherArgs a)
         double* mine = sig + lane * kDthRow;
         const double* myU = uni + lane * kDthURow;
         if (live)
-            for (int i = 0; i < n; ++i)
-            {
-                const double x = mine[i];
-                const double2 uu = *reinterpret_cast<const double2*>(myU + 2 * i);
-                double shaped = __dmul_rn(c[1], z[1]);
-                shaped = __fma_rn(c[0], z[0], shaped);
-#pragma unroll
-                for (int t = 2; t < 12; ++t) shaped = __fma_rn(c[t], z[t], shaped);
-                const double tpdf = __dadd_rn(__dadd_rn(uu.x, -0.5), __dadd_rn(uu.y, -0.5));
-                const double pre = roleLeft ? __fma_rn(x, kHeadroom, __dmul_rn(tpdf, a.scale)) : __fma_rn(tpdf, a.scale, __dmul_rn(x, kHeadroom));
-                const double tmp = __dadd_rn(pre, shaped);
-                const double q = __dmul_rn(rint(__dmul_rn(tmp, a.invScale)), a.scale);
-                double err = __dadd_rn(tmp, -q);
-                if (fabs(err) < 1.0e-20) err = 0.0;
-#pragma unroll
-                for (int t = 11; t > 0; --t) z[t] = z[t - 1];
-                z[0] = err;
-                double o = q;
-                if ((a.finalClamp & 1) && !(fabs(o) < 1.0e300)) o = 0.0;
-                if (a.finalClamp & 2) o = fmin(fmax(o, -kHeadroom), kHeadroom);
-                mine[i] = o;
-            }
-        __syncwarp();
-        // write the tile back: 16-byte stores, lanes 0-15 one row, lanes 16-31 the next
-        for (int r = lane >> 4; r < nLocal; r += 2)
         {
-            const int pc = lane & 15;
-            if (2 * pc < n)
-                *reinterpret_cast<double2*>(a.io + (size_t) (seq0 + r) * a.ioStride + t0 + 2 * pc) = *reinterpret_cast<const double2*>(sig + r * kDthRow + 2 * pc);
+            if (n == kDthTile) dither_unrolled<0>(mine, myU, e, c, roleLeft, a.scale, a.invScale, a.finalClamp);
+            else
+                for (int i = 0; i < n; ++i)   // last, partial tile: shift the history like the reference does
+                {
+                    mine[i] = dither_sample<0>(mine[i], *reinterpret_cast<const double2*>(myU + 2 * i), e, c, roleLeft, a.scale, a.invScale, a.finalClamp);
+                    const double newest = e[11];
+#pragma unroll
+                    for (int t = 11; t > 0; --t) e[t] = e[t - 1];
+                    e[0] = newest;
+                }
+        }
+        __syncwarp();
+        // write the tile back: 16-byte stores, the same lane -> (row, piece) map as the signal loads
+        {
+            constexpr int rowsPerStep = 32 / kSigPieces;
+            const int rr = lane / kSigPieces, pc = lane % kSigPieces;
+            if (rr < rowsPerStep)
+                for (int r = rr; r < nLocal; r += rowsPerStep)
+                    if (2 * pc < n)
+                        *reinterpret_cast<double2*>(a.io + (size_t) (seq0 + r) * a.ioStride + t0 + 2 * pc) = *reinterpret_cast<const double2*>(sig + r * kDthRow + 2 * pc);
         }
         __syncwarp();   // the buffer is refilled by the issue() of the next iteration
     }
     if (live)
     {
 #pragma unroll
-        for (int i = 0; i < 12; ++i) a.z[(size_t) seq * 12 + i] = z[i];
+        for (int i = 0; i < 12; ++i) a.z[(size_t) seq * 12 + i] = e[i];
     }
 }
 

@@ -16,6 +16,9 @@
 namespace cpq
 {
 
+#ifndef CPQ_FFT16_MINB
+#define CPQ_FFT16_MINB 2
+#endif
 template <int LOG2P>
 struct Fft16Cfg
 {
@@ -49,7 +52,7 @@ __device__ __forceinline__ int fft16_bin(int t, int r)
 }
 
 template <int LOG2P>
-__global__ void __launch_bounds__(Fft16Cfg<LOG2P>::THREADS, 2) fft_fwd16_kernel(FwdArgs a)
+__global__ void __launch_bounds__(Fft16Cfg<LOG2P>::THREADS, CPQ_FFT16_MINB) fft_fwd16_kernel(FwdArgs a)
 {
     using C = Fft16Cfg<LOG2P>;
     using C8 = FftCfg<LOG2P>;
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(Fft16Cfg<LOG2P>::THREADS, 2) fft_fwd16_kernel(
 }
 
 template <int LOG2P>
-__global__ void __launch_bounds__(Fft16Cfg<LOG2P>::THREADS, 2) fft_inv16_kernel(InvArgs a)
+__global__ void __launch_bounds__(Fft16Cfg<LOG2P>::THREADS, CPQ_FFT16_MINB) fft_inv16_kernel(InvArgs a)
 {
     using C = Fft16Cfg<LOG2P>;
     using C8 = FftCfg<LOG2P>;
