@@ -36,11 +36,25 @@ out = {k: sum(v) / len(v) for k, v in traffic.items()}
 fam = collections.defaultdict(list)
 for k, v in traffic.items():
     fam[k.split("<")[0]].extend(v)
-doc = {"_source": f"{os.path.basename(rep)} ({tag}): dram__bytes_read.sum + dram__bytes_write.sum per launch, chunk of 118 sequences x 480256 samples",
+# FP64 pipe utilisation per kernel family (sm__inst_executed_pipe_fp64..pct_of_peak, as scripts/ncu_summary.py prints it): read by
+# bench.py for roofline.fp64.pipe_utilisation_ncu; time-weighted over the family's launches
+ncu = {}
+for line in summ.splitlines():
+    if not line.startswith("kernel="): continue
+    f = dict(kv.split("=", 1) for kv in line.replace("kernel=void ", "kernel=").split("  ") if "=" in kv)
+    fam_name = f["kernel"].split("<")[0].strip().replace("mac_tma_kernel", "mac_kernel").replace("fft_fwd16_kernel", "fft_fwd_kernel").replace("fft_inv16_kernel", "fft_inv_kernel")
+    ms = float(f["ms"].replace("ms", "")); pct = float(f["fp64%"])
+    a = ncu.setdefault(fam_name, [0.0, 0.0]); a[0] += ms * pct; a[1] += ms
+ncu = {k: {"fp64_pct": v[0] / v[1], "ms_in_profile": v[1]} for k, v in ncu.items() if v[1] > 0}
+ncu["_source"] = f"profiles/{tag}_ncu_kernels.txt (ncu --set full, one chunk)"
+doc = {"_ncu": ncu, "_source": f"{os.path.basename(rep)} ({tag}): dram__bytes_read.sum + dram__bytes_write.sum per launch, chunk of 118 sequences x 480256 samples",
        "_channel_samples_per_launch": 118 * 480256,
        **{k: sum(v) / len(v) for k, v in fam.items()}, "_per_kernel": out}
+for alias, real in (("mac_kernel", "mac_tma_kernel"), ("fft_fwd_kernel", "fft_fwd16_kernel"), ("fft_inv_kernel", "fft_inv16_kernel")):
+    if alias not in doc and real in doc: doc[alias] = doc[real]   # the names bench.py's stage timers use
 json.dump(doc, open(os.path.join(prof, "traffic.json"), "w"), indent=1)
-for kern, mangled in (("eq_kernel", "_ZN3cpq9eq_kernelILb0ELb0ELb0EEEvNS_6EqArgsE"), ("mac_kernel", "_ZN3cpq10mac_kernelENS_7MacArgsE")):
+for kern, mangled in (("eq_kernel", "_ZN3cpq9eq_kernelILb0ELb0ELb0ELb0EEEvNS_6EqArgsE"), ("mac_kernel", "_ZN3cpq10mac_kernelENS_7MacArgsE"),
+                      ("mac_tma_kernel", "_ZN3cpq14mac_tma_kernelENS_7MacArgsENS_12MacTensorMapES1_")):
     if kern not in fam: continue
     txt = run(py, os.path.join(root, "scripts", "ncu_stalls.py"), rep, kern, "0", "25")
     txt += "\n# per CUDA source line (needs the libcpq.so of the same build)\n" + run(py, os.path.join(root, "scripts", "ncu_lines.py"), rep, kern, mangled, "30")
