@@ -235,7 +235,9 @@ def measure_workload(eng, x_dev, T, stages, steps=3, warm=2, host=True):
     cs = float(x_dev.shape[0]) * T
     out["channel_samples"] = cs
     out["value"] = cs / (out["device_ms"] * 1e-3)
-    out["launches_per_step"] = int(eng.timings().kernel_launches)
+    tm = eng.timings()
+    out["launches_per_step"] = int(tm.kernel_launches)
+    out["stage_ms"] = {"fft_fwd": round(tm.fft_fwd_ms, 4), "mac": round(tm.mac_ms, 4), "fft_inv": round(tm.fft_inv_ms, 4), "eq": round(tm.eq_ms, 4)}
     if host:
         h = torch.empty(x_dev.shape, dtype=torch.float64).pin_memory()
 

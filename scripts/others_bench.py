@@ -9,4 +9,4 @@ class _Skip:
 res = bench.other_workloads(0, dev, _Skip(), torch.zeros(2, 2, device=dev), 2)
 for k, v in res.items():
     if "error" in v: print(k, "ERROR", v["error"][:80]); continue
-    print(f"{k:28s} device {v['device_ms']:8.3f} ms  e2e {v.get('e2e_ms', float('nan')):8.3f} ms  {v['value'] / 1e9:7.3f} G ch-samples/s  launches {v['launches_per_step']}")
+    print(f"{k:28s} device {v['device_ms']:8.3f} ms  e2e {v.get('e2e_ms', float('nan')):8.3f} ms  {v['value'] / 1e9:7.3f} G ch-samples/s  launches {v['launches_per_step']} {v.get('stage_ms')}")

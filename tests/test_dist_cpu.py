@@ -103,3 +103,76 @@ def test_two_rank_gloo_sharding():
         assert err_owner <= 1e-12, err_owner
         owned = sorted(k for d in gathered for k in d)
         assert owned == [0, 1, 2, 3, 4]          # every stream processed exactly once across ranks
+
+
+def test_cfg5_hybrid_layout_covers_pairs_and_partitions():
+    """dist.cfg5_layout: ranks in groups of two, a group owns 4 / (world / 2) stereo pairs, the two ranks of a group split
+    the partition list in half -- every (pair, partition) is computed exactly once."""
+    from convopeq_b200.dist import cfg5_layout
+    parts = [32, 64, 56]
+    for world in (2, 4, 8):
+        groups, rpg, pairs = cfg5_layout(world)
+        assert groups * rpg == world and groups * pairs == 4 and rpg == 2
+        seen = {}
+        for rank in range(world):
+            grp, sub = rank // rpg, rank % rpg
+            b, e = partition_ranges(parts, rpg)[sub]
+            for pair in range(grp * pairs, (grp + 1) * pairs):
+                for q in range(b, e):
+                    assert (pair, q) not in seen
+                    seen[(pair, q)] = rank
+        assert len(seen) == 4 * sum(parts)
+    for bad in (1, 3, 6, 16):
+        with pytest.raises(ValueError):
+            cfg5_layout(bad)
+
+
+def _group_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from convopeq_b200.dist import cfg5_layout
+        from oracle.bindings import Oracle
+        orc = Oracle()
+        groups, rpg, pairs = cfg5_layout(world)
+        grp, sub = rank // rpg, rank % rpg
+        pgs = [dist.new_group(list(range(g * rpg, (g + 1) * rpg))) for g in range(groups)]
+        ir_len, block, T = 30000, 256, 8192
+        ir = signals.synth_ir(ir_len, 31)
+        lay, _ = plan_layout(ir_len, block, None, T // block)
+        parts = [lay.layers[i].num_parts_ir for i in range(lay.num_layers)]
+        b, e = partition_ranges(parts, rpg)[sub]
+        masked = np.zeros_like(ir)
+        for li, (qb, qe) in enumerate(layer_slices(parts, b, e)):
+            L = lay.layers[li]
+            lo, hi = L.ir_offset + qb * L.part_size, min(L.ir_offset + qe * L.part_size, L.ir_offset + L.ir_len)
+            if hi > lo:
+                masked[lo:hi] = ir[lo:hi]
+        # the group's channels: pair p = channels 2p, 2p + 1 of the 8-channel stream
+        chans = range(2 * grp * pairs, 2 * (grp + 1) * pairs)
+        x = np.stack([signals.noise(T, 100 + c) for c in chans])
+        # the restatement has no partition range: a rank's partial is the full plan run on the IR with the other partitions
+        # zeroed (same layer plan, the convolver is linear in the IR)
+        part = np.stack([orc.nuc_run(masked, x[i], block)[0] for i in range(x.shape[0])])
+        t = torch.from_numpy(part)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=pgs[grp])
+        want = np.stack([orc.nuc_run(ir, x[i], block)[0] for i in range(x.shape[0])])
+        q.put((rank, float(np.abs(t.numpy() - want).max())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cfg5_hybrid_group_reduce_two_ranks_gloo():
+    """world_size 2 = one group: each rank convolves its half of the partitions, the pairwise all-reduce gives the full sum."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 200
+    procs = [ctx.Process(target=_group_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(err <= 1e-12 for _, err in res), res
