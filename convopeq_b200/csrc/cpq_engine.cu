@@ -419,6 +419,28 @@ cpq_status Engine::launchFwdLarge(int log2P, const FwdArgs& a)
     la.src = a.src; la.srcStride = a.srcStride; la.frameStart0 = a.frameStart0; la.lo = a.lo; la.hi = a.hi; la.halfOnly = a.halfOnly;
     la.rowPitchFrames = a.outFramesPerSeq; la.rowOffset = a.outFrameOffset;
     la.tw = a.tw; la.scale = a.scale; la.applyScale = a.applyScale; la.gain = a.gain; la.tilt = a.tilt;
+    static const int g2Env = [] { const char* e = getenv("CPQ_GFFT2"); return e ? atoi(e) : 1; }();   // 0: one kernel per radix pass (round 1)
+    if (g2Env && log2P >= 14)
+    {
+        // four-step transform: column pass straight from the signal into scratch, row pass into out, split in place
+        la.a = a.out;
+        const int log2N1 = log2P - 8;
+        const unsigned gc = (unsigned) (la.totalFrames * (kG2N2 / kG2Cols)), gr = (unsigned) (la.totalFrames * ((1 << log2N1) / kG2Rows));
+        const size_t sc = ((size_t) kG2Cols * ((1 << log2N1) + 1) + (1 << log2N1)) * sizeof(double2), sr = ((size_t) kG2Rows * (kG2N2 + 1) + kG2N2) * sizeof(double2);
+        switch (log2N1)
+        {
+            case 6: gfft2_cols_kernel<6, -1, true><<<gc, kG2Cols * 8, sc, stream>>>(la, nullptr, a.scratch); gfft2_rows_kernel<6, -1, false><<<gr, kG2Rows * 32, sr, stream>>>(la, a.scratch, a.out); break;
+            case 7: gfft2_cols_kernel<7, -1, true><<<gc, kG2Cols * 16, sc, stream>>>(la, nullptr, a.scratch); gfft2_rows_kernel<7, -1, false><<<gr, kG2Rows * 32, sr, stream>>>(la, a.scratch, a.out); break;
+            default: gfft2_cols_kernel<8, -1, true><<<gc, kG2Cols * 32, sc, stream>>>(la, nullptr, a.scratch); gfft2_rows_kernel<8, -1, false><<<gr, kG2Rows * 32, sr, stream>>>(la, a.scratch, a.out); break;
+        }
+        launches += 2;
+        CPQ_CUDA(cudaGetLastError());
+        const int64_t h2 = la.totalFrames * (la.P / 2 + 1);
+        gfft_split_fwd_kernel<<<(unsigned) ((h2 + 255) / 256), 256, 0, stream>>>(la, a.out);
+        ++launches;
+        CPQ_CUDA(cudaGetLastError());
+        return CPQ_OK;
+    }
     const int nPasses = (log2P % 3 ? 1 : 0) + log2P / 3;
     // start in the buffer that makes the last pass land in a.out
     double2* cur = (nPasses % 2 == 0) ? a.out : a.scratch;
@@ -456,6 +478,23 @@ cpq_status Engine::launchInvLarge(int log2P, const InvArgs& a)
     gfft_pre_inv_kernel<<<(unsigned) ((h + 255) / 256), 256, 0, stream>>>(la, cur);
     ++launches;
     CPQ_CUDA(cudaGetLastError());
+    static const int g2Env = [] { const char* e = getenv("CPQ_GFFT2"); return e ? atoi(e) : 1; }();
+    if (g2Env && log2P >= 14)
+    {
+        // four-step inverse: column pass in -> scratch, row pass scratch -> the kept half of every frame as real samples
+        const int log2N1 = log2P - 8;
+        const unsigned gc = (unsigned) (la.totalFrames * (kG2N2 / kG2Cols)), gr = (unsigned) (la.totalFrames * ((1 << log2N1) / kG2Rows));
+        const size_t sc = ((size_t) kG2Cols * ((1 << log2N1) + 1) + (1 << log2N1)) * sizeof(double2), sr = ((size_t) kG2Rows * (kG2N2 + 1) + kG2N2) * sizeof(double2);
+        switch (log2N1)
+        {
+            case 6: gfft2_cols_kernel<6, +1, false><<<gc, kG2Cols * 8, sc, stream>>>(la, cur, other); gfft2_rows_kernel<6, +1, true><<<gr, kG2Rows * 32, sr, stream>>>(la, other, nullptr); break;
+            case 7: gfft2_cols_kernel<7, +1, false><<<gc, kG2Cols * 16, sc, stream>>>(la, cur, other); gfft2_rows_kernel<7, +1, true><<<gr, kG2Rows * 32, sr, stream>>>(la, other, nullptr); break;
+            default: gfft2_cols_kernel<8, +1, false><<<gc, kG2Cols * 32, sc, stream>>>(la, cur, other); gfft2_rows_kernel<8, +1, true><<<gr, kG2Rows * 32, sr, stream>>>(la, other, nullptr); break;
+        }
+        launches += 2;
+        CPQ_CUDA(cudaGetLastError());
+        return CPQ_OK;
+    }
     CPQ_CUDA(largePasses<+1>(la, cur, other, log2P, stream, launches));
     const int64_t n = la.totalFrames * (la.P / 2);
     gfft_store_inv_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(la, cur);
@@ -530,6 +569,13 @@ cpq_status Engine::setKernelAttributes()
     CPQ_CUDA(cudaFuncSetAttribute(mac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem));
     CPQ_CUDA(cudaFuncSetAttribute(mac_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem));
     CPQ_CUDA(cudaFuncSetAttribute(dither_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kDitherSmemBytes));
+    {
+        const int g2 = (int) ((kG2Cols * 257 + 256) * sizeof(double2));   // column pass at N1 = 256; N1 = 128 needs 68 KB, N1 = 64 fits the default
+        CPQ_CUDA(cudaFuncSetAttribute(gfft2_cols_kernel<8, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2));
+        CPQ_CUDA(cudaFuncSetAttribute(gfft2_cols_kernel<8, +1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2));
+        CPQ_CUDA(cudaFuncSetAttribute(gfft2_cols_kernel<7, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2));
+        CPQ_CUDA(cudaFuncSetAttribute(gfft2_cols_kernel<7, +1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2));
+    }
     return CPQ_OK;
 }
 

@@ -186,4 +186,150 @@ __global__ void gfft_store_inv_kernel(LargeFftArgs a, const double2* __restrict_
     o[n] = z[largeRow(a, gf) + half + n];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Four-step form of the same P-point complex transform (round 2): P = N1 x 256, index n = n1 * 256 + n2 in, k = k1 + N1 * k2
+// out.  Two kernels, each moving a frame through HBM once:
+//   cols  for 16 consecutive n2 the N1-point transforms along n1 (stride 256) in shared memory, then the twiddle
+//         W_P^(k1 n2); element (k1, n2) goes back to position k1 * 256 + n2 (same places: a column block is private to its CTA)
+//   rows  for 8 consecutive k1 the 256-point transforms along n2 (contiguous rows, one warp each); element (k1, k2) goes to
+//         k1 + N1 * k2, eight consecutive k1 per 128-byte run
+// instead of one kernel per radix-8 pass (five of them at P = 32768, each reading and writing the whole frame, plus a load
+// pass): the forward transform reads the signal directly in `cols` (the complex view of the real frame is a reinterpretation),
+// the inverse writes the kept half of each frame straight to the real output in `rows`.  Twiddles of every size come from the
+// layer table (W_P^idx), so the small transforms add no tables.
+// ---------------------------------------------------------------------------------------------
+constexpr int kG2Cols = 32;       // columns per CTA in the column pass (512-byte runs per row of the frame)
+constexpr int kG2Rows = 8;        // rows per CTA in the row pass
+constexpr int kG2N2 = 256;
+
+// one Stockham pass of an N-point transform held in shared memory (stride 1), NT threads per transform, thread t.
+// All threads of the CTA call it together: `sync` separates the reads of a pass from its writes.
+// wN[m] = W_N^m (already conjugated for the inverse), a table in shared memory built once per CTA from the layer table
+template <int N, int NT, int R, int SIGN, class SyncF>
+__device__ __forceinline__ void g2_pass(double2* s, int t, int Ns, const double2* __restrict__ wN, SyncF sync)
+{
+    constexpr int per = N / R;
+    constexpr int cnt = per / NT;          // butterflies per thread
+    static_assert(per % NT == 0 && cnt >= 1, "pass geometry");
+    double2 v[cnt][R];
+#pragma unroll
+    for (int c = 0; c < cnt; ++c)
+    {
+        const int j = t + c * NT;
+        const int k = j & (Ns - 1);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+        {
+            double2 x = s[j + r * per];
+            if (r > 0 && Ns > 1) x = cmul(x, wN[k * r * (N / (Ns * R))]);   // W_{Ns R}^{k r},  k r < Ns R
+            v[c][r] = x;
+        }
+        dftR<R, SIGN>(v[c]);
+    }
+    sync();
+#pragma unroll
+    for (int c = 0; c < cnt; ++c)
+    {
+        const int j = t + c * NT;
+        const int k = j & (Ns - 1);
+        const int ob = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) s[ob + r * Ns] = v[c][r];
+    }
+    sync();
+}
+
+// N-point transform in shared memory, N in {64, 128, 256}, N / 8 threads
+template <int N, int SIGN, class SyncF>
+__device__ __forceinline__ void g2_fft(double2* s, int t, const double2* __restrict__ wN, SyncF sync)
+{
+    constexpr int NT = N / 8;
+    int Ns = 1;
+    if constexpr (N == 128) { g2_pass<N, NT, 2, SIGN>(s, t, Ns, wN, sync); Ns = 2; }
+    if constexpr (N == 256) { g2_pass<N, NT, 4, SIGN>(s, t, Ns, wN, sync); Ns = 4; }
+    g2_pass<N, NT, 8, SIGN>(s, t, Ns, wN, sync);
+    Ns *= 8;
+    g2_pass<N, NT, 8, SIGN>(s, t, Ns, wN, sync);
+}
+
+template <int LOG2N1, int SIGN, bool FROM_REAL>
+__global__ void __launch_bounds__(kG2Cols * (1 << LOG2N1) / 8) gfft2_cols_kernel(LargeFftArgs a, const double2* __restrict__ in, double2* __restrict__ out)
+{
+    constexpr int N1 = 1 << LOG2N1, C = kG2Cols, LD = N1 + 1, NT = N1 / 8, THREADS = C * NT;
+    extern __shared__ double2 g2_smem[];
+    const int tid = threadIdx.x;
+    const int64_t gf = blockIdx.x / (kG2N2 / C);
+    const int n20 = (int) (blockIdx.x % (kG2N2 / C)) * C;
+    const size_t row = largeRow(a, gf);
+    const int P = a.P;
+    const int64_t seq = gf / a.framesPerSeq, f = gf % a.framesPerSeq;
+    const double* src = FROM_REAL ? a.src + seq * a.srcStride : nullptr;
+    const int64_t g0 = FROM_REAL ? a.frameStart0 + f * (int64_t) P : 0;
+    for (int idx = tid; idx < N1 * C; idx += THREADS)
+    {
+        const int n1 = idx / C, c = idx % C;
+        const int e = n1 * kG2N2 + n20 + c;
+        double2 z;
+        if (FROM_REAL)
+        {
+            z = make_double2(0.0, 0.0);
+            if (!(a.halfOnly && 2 * e >= P))
+            {
+                const int64_t g = g0 + 2 * (int64_t) e;
+                z.x = (g >= a.lo && g < a.hi) ? __ldg(src + g) : 0.0;
+                z.y = (g + 1 >= a.lo && g + 1 < a.hi) ? __ldg(src + g + 1) : 0.0;
+            }
+        }
+        else
+            z = in[row + e];
+        g2_smem[c * LD + n1] = z;
+    }
+    double2* wN = g2_smem + C * LD;                        // W_N1^m, m < N1
+    for (int m = tid; m < N1; m += THREADS) wN[m] = twiddleFromLayerTable<SIGN>(a.tw, P, (int64_t) m * (P / N1));
+    __syncthreads();
+    g2_fft<N1, SIGN>(g2_smem + (tid / NT) * LD, tid % NT, wN, [] { __syncthreads(); });
+    for (int idx = tid; idx < N1 * C; idx += THREADS)
+    {
+        const int k1 = idx / C, c = idx % C;
+        const double2 v = cmul(g2_smem[c * LD + k1], twiddleFromLayerTable<SIGN>(a.tw, P, (int64_t) k1 * (n20 + c)));
+        out[row + (size_t) k1 * kG2N2 + n20 + c] = v;
+    }
+}
+
+template <int LOG2N1, int SIGN, bool TO_REAL>
+__global__ void __launch_bounds__(kG2Rows * 32) gfft2_rows_kernel(LargeFftArgs a, const double2* __restrict__ in, double2* __restrict__ out)
+{
+    constexpr int N1 = 1 << LOG2N1, R = kG2Rows, LD = kG2N2 + 1;
+    extern __shared__ double2 g2_smem[];
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int64_t gf = blockIdx.x / (N1 / R);
+    const int k10 = (int) (blockIdx.x % (N1 / R)) * R;
+    const size_t row = largeRow(a, gf);
+    const int P = a.P;
+    double2* mine = g2_smem + w * LD;
+    const double2* rin = in + row + (size_t) (k10 + w) * kG2N2;
+#pragma unroll
+    for (int i = 0; i < kG2N2 / 32; ++i) mine[lane + 32 * i] = rin[lane + 32 * i];
+    double2* wN = g2_smem + R * LD;                        // W_256^m
+    wN[tid] = twiddleFromLayerTable<SIGN>(a.tw, P, (int64_t) tid * (P / kG2N2));   // R * 32 = 256 threads
+    __syncthreads();
+    g2_fft<kG2N2, SIGN>(mine, lane, wN, [] { __syncwarp(); });
+    __syncthreads();
+    const int64_t seq = gf / a.framesPerSeq, f = gf % a.framesPerSeq;
+    for (int idx = tid; idx < kG2N2 * R; idx += R * 32)
+    {
+        const int k2 = idx / R, rr = idx % R;
+        const double2 v = g2_smem[rr * LD + k2];
+        const int n = (k10 + rr) + N1 * k2;
+        if (TO_REAL)
+        {
+            // z[P/2 ..) are the samples [P, 2P) of the frame: the half overlap-save keeps
+            if (n >= P / 2) reinterpret_cast<double2*>(a.dst + seq * a.dstStride + f * (int64_t) P)[n - P / 2] = v;
+        }
+        else
+            out[row + n] = v;
+    }
+}
+
 } // namespace cpq
