@@ -75,7 +75,7 @@ EXPORTS = [
     "cpq_plan_layout", "cpq_plan_layout_ex", "cpq_set_eq_mode", "cpq_band_node_active", "cpq_get_agc_state",
     "cpq_set_mix", "cpq_ir_peak_latency", "cpq_set_direct_head", "cpq_parse_eq_preset",
     "cpq_set_convolver_bypass", "cpq_set_peak_limiter", "cpq_set_input_gain", "cpq_set_partial_sources", "cpq_set_stream_window", "cpq_ir_scale_factor", "cpq_ir_freq_peak_gain", "cpq_ir_min_phase",
-    "cpq_ir_target_length", "cpq_ir_prepare", "cpq_set_dither_uniforms_device", "cpq_set_streaming", "cpq_stream_position", "cpq_state_size", "cpq_export_state", "cpq_import_state",
+    "cpq_ir_target_length", "cpq_ir_prepare", "cpq_set_dither_seed", "cpq_set_dither_uniforms_device", "cpq_set_streaming", "cpq_stream_position", "cpq_state_size", "cpq_export_state", "cpq_import_state",
     "cpq_debug_check_guards", "cpq_probe_dfma_tflops", "cpq_probe_dfma_latency",
 ]
 
@@ -160,6 +160,7 @@ def load() -> C.CDLL:
                                      C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     L.cpq_ir_target_length.argtypes = [C.c_double, C.c_double]
     L.cpq_ir_prepare.argtypes = [dp, C.c_int, C.c_double, C.c_double, dp, C.c_int]
+    L.cpq_set_dither_seed.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.cpq_set_dither_uniforms_device.argtypes = [vp, vp, C.c_int64]
     L.cpq_set_streaming.argtypes = [vp, C.c_int]
     L.cpq_stream_position.argtypes = [vp]

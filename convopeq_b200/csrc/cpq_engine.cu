@@ -202,6 +202,9 @@ struct Engine
     static constexpr int kDitherStreams = 32;
     cudaStream_t sDither[kDitherStreams] {};      // the dither stage is serial in time (latency-bound): it runs beside the next chunks
     const double* uniformsBorrowed = nullptr;     // cpq_set_dither_uniforms_device
+    bool ditherRng = false;                       // cpq_set_dither_seed: uniforms from the reference's fallback generator
+    std::vector<unsigned long long> rngSeedState; // [nSeq] fallbackState right after construction
+    DevBuf<unsigned long long> rngState;          // [nSeq] carried
     cudaEvent_t ev[8] {};
     std::vector<cudaEvent_t> evPool;
     cudaEvent_t poolEvent(size_t i)
@@ -1227,6 +1230,8 @@ cpq_status Engine::resetState()
         if (tailCarry[li].p) CPQ_CUDA(cudaMemsetAsync(tailCarry[li].p, 0, tailCarry[li].n * sizeof(double), stream));
     }
     CPQ_CUDA(cudaMemsetAsync(ditherZ.p, 0, (size_t) nSeq * 12 * sizeof(double), stream));
+    if (rngState.p && !rngSeedState.empty())
+        CPQ_CUDA(cudaMemcpyAsync(rngState.p, rngSeedState.data(), rngSeedState.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
     CPQ_CUDA(cudaMemsetAsync(stateOut.p, 0, (size_t) nSeq * CPQ_NUM_BANDS * 2 * sizeof(double), stream));
     if (postState.p) CPQ_CUDA(cudaMemsetAsync(postState.p, 0, postState.n * sizeof(double), stream));
     CPQ_CUDA(cudaStreamSynchronize(stream));
@@ -1265,6 +1270,7 @@ size_t Engine::stateBytes() const
     n += (size_t) cfg.n_streams * 3 * sizeof(double);            // AGC envelopes + gain
     n += (size_t) cfg.n_streams * sizeof(double);                // limiter envelope
     n += (size_t) nSeq * 12 * sizeof(double);                    // dither error history
+    n += (size_t) nSeq * sizeof(unsigned long long);             // dither generator state
     return n;
 }
 
@@ -1312,6 +1318,7 @@ cpq_status Engine::exportState(void* dst, size_t bytes)
     CPQ_CUDA(put(agcState.p, (size_t) cfg.n_streams * 3 * sizeof(double), agcState.p != nullptr));
     CPQ_CUDA(put(limEnv.p, (size_t) cfg.n_streams * sizeof(double), limEnv.p != nullptr));
     CPQ_CUDA(put(ditherZ.p, (size_t) nSeq * 12 * sizeof(double), true));
+    CPQ_CUDA(put(rngState.p, (size_t) nSeq * sizeof(unsigned long long), rngState.p != nullptr));
     return CPQ_OK;
 }
 
@@ -1363,6 +1370,7 @@ cpq_status Engine::importState(const void* src, size_t bytes)
     if (h.hasLim) CPQ_CUDA(limEnv.ensure((size_t) cfg.n_streams));
     CPQ_CUDA(get(limEnv.p, (size_t) cfg.n_streams * sizeof(double), h.hasLim != 0));
     CPQ_CUDA(get(ditherZ.p, (size_t) nSeq * 12 * sizeof(double), true));
+    CPQ_CUDA(get(rngState.p, (size_t) nSeq * sizeof(unsigned long long), rngState.p != nullptr));
     absCallback = h.absCallback;
     contValid = h.contValid != 0;
     gplanCallbacks = -1;
@@ -1729,7 +1737,9 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
     if (doDither && !cont) CPQ_CUDA(cudaMemsetAsync(ditherZ.p, 0, (size_t) this->nSeq * 12 * sizeof(double), stream));   // PsychoacousticDither::reset
     if (doDither && cont)
         for (auto& d : sDither) CPQ_CUDA(cudaStreamSynchronize(d));   // (paranoia: the carried history is read on the side streams)
-    if (doDither && uniformsPerCh != T)
+    if (doDither && ditherRng && !cont)   // a fresh PsychoacousticDither per stream: generator state as constructed
+        CPQ_CUDA(cudaMemcpyAsync(rngState.p, rngSeedState.data(), rngSeedState.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+    if (doDither && !ditherRng && uniformsPerCh != T)
     {
         setError("process: dither enabled but cpq_set_dither_uniforms does not hold exactly T samples per channel");
         return CPQ_ERR_NOT_READY;
@@ -2320,7 +2330,8 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             d.ioStride = stride;
             d.T = T;
             d.nSeq = ns;
-            d.uniforms = (uniformsBorrowed ? uniformsBorrowed : uniforms.p) + (size_t) s0 * 2 * T;
+            d.uniforms = ditherRng ? nullptr : (uniformsBorrowed ? uniformsBorrowed : uniforms.p) + (size_t) s0 * 2 * T;
+            d.rng = ditherRng ? rngState.p + s0 : nullptr;
             ditherCoeffs(cfg.sample_rate, ditherBits, d.coeff);
             d.scale = 1.0 / std::pow(2.0, ditherBits - 1);
             d.invScale = std::pow(2.0, ditherBits - 1);
@@ -2830,6 +2841,39 @@ cpq_status cpq_set_dither_uniforms(cpq_handle h, const double* uniforms, int64_t
     CPQ_CUDA(cudaMemcpy(e->uniforms.p, uniforms, n * sizeof(double), cudaMemcpyHostToDevice));
     e->uniformsPerCh = samples_per_channel;
     e->uniformsBorrowed = nullptr;
+    e->ditherRng = false;
+    return CPQ_OK;
+}
+
+cpq_status cpq_set_dither_seed(cpq_handle h, const uint64_t* stream_seeds)
+{
+    if (!h) return CPQ_ERR_INVALID;
+    Engine* e = h;
+    auto setError = [&](const std::string& s) { e->setError(s); };
+    if (!stream_seeds)
+    {
+        e->ditherRng = false;
+        return CPQ_OK;
+    }
+    CPQ_CUDA(cudaSetDevice(e->cfg.device));
+    // PsychoacousticDither(seed): SplitMix64(seed) hands every channel i its seedValue; fallbackState[i] = seedValue ^ 0xd1b5...
+    // (PsychoacousticDither.h:118-140); channel c of a stream is channel c of that stream's own dither object
+    e->rngSeedState.assign((size_t) e->nSeq, 0ull);
+    for (int st = 0; st < e->cfg.n_streams; ++st)
+    {
+        unsigned long long sm = stream_seeds[st];
+        for (int c = 0; c < e->cfg.n_channels; ++c)
+        {
+            unsigned long long z = (sm += 0x9e3779b97f4a7c15ull);
+            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+            z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+            z ^= z >> 31;
+            e->rngSeedState[(size_t) st * e->cfg.n_channels + c] = z ^ 0xd1b54a32d192ed03ull;
+        }
+    }
+    CPQ_CUDA(e->rngState.ensure((size_t) e->nSeq));
+    CPQ_CUDA(cudaMemcpy(e->rngState.p, e->rngSeedState.data(), (size_t) e->nSeq * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    e->ditherRng = true;
     return CPQ_OK;
 }
 
@@ -2838,6 +2882,7 @@ cpq_status cpq_set_dither_uniforms_device(cpq_handle h, const double* d_uniforms
     if (!h || !d_uniforms || samples_per_channel <= 0 || (reinterpret_cast<uintptr_t>(d_uniforms) & 15)) return CPQ_ERR_INVALID;
     h->uniformsBorrowed = d_uniforms;
     h->uniformsPerCh = samples_per_channel;
+    h->ditherRng = false;
     return CPQ_OK;
 }
 

@@ -1635,7 +1635,8 @@ struct DitherArgs
     int nSeq;
     int nch;                  // channels per stream: lane role = left channel of a stereo stream or not
     int seqBase;              // absolute index of this launch's first sequence (a chunk may start on a right channel)
-    const double* uniforms;   // [nSeq][2*T]
+    const double* uniforms;   // [nSeq][2*T]; nullptr = generate them: the reference's own fallback generator (rng below)
+    unsigned long long* rng;  // [nSeq] xorshift64* state per stream-channel (PsychoacousticDither::fallbackState, :485-497), carried
     double coeff[12];
     double scale, invScale;
     double* z;                // [nSeq][12] error history (carried)
@@ -1679,14 +1680,32 @@ __device__ __forceinline__ double dither_sample(double x, double2 uu, double (&e
     return o;
 }
 
-template <int J>
+// PsychoacousticDither::fallbackUniform (:485-497): xorshift64* step, top 53 bits -> [0, 1)
+__device__ __forceinline__ double dither_fallback_uniform(unsigned long long& x)
+{
+    x ^= x >> 12;
+    x ^= x << 25;
+    x ^= x >> 27;
+    const unsigned long long z = x * 2685821657736338717ull;
+    return (double) (z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+template <int J, bool RNG>
 __device__ __forceinline__ void dither_unrolled(double* mine, const double* myU, double (&e)[12], const double (&c)[12], bool roleLeft,
-                                                double scale, double invScale, int finalClamp)
+                                                double scale, double invScale, int finalClamp, unsigned long long& rs)
 {
     if constexpr (J < kDthTile)
     {
-        mine[J] = dither_sample<(24 - J) % 12>(mine[J], *reinterpret_cast<const double2*>(myU + 2 * J), e, c, roleLeft, scale, invScale, finalClamp);
-        dither_unrolled<J + 1>(mine, myU, e, c, roleLeft, scale, invScale, finalClamp);
+        double2 uu;
+        if (RNG)
+        {
+            uu.x = dither_fallback_uniform(rs);   // u1 then u2, as nextTPDF_MKL draws them (:560-572)
+            uu.y = dither_fallback_uniform(rs);
+        }
+        else
+            uu = *reinterpret_cast<const double2*>(myU + 2 * J);
+        mine[J] = dither_sample<(24 - J) % 12>(mine[J], uu, e, c, roleLeft, scale, invScale, finalClamp);
+        dither_unrolled<J + 1, RNG>(mine, myU, e, c, roleLeft, scale, invScale, finalClamp, rs);
     }
 }
 
@@ -1714,8 +1733,9 @@ __global__ void __launch_bounds__(32) dither_kernel(DitherArgs a)
             for (int r = rr; r < nLocal; r += rowsPerStep)
                 if (2 * pc < n) dthCpAsync16(sig + r * kDthRow + 2 * pc, a.io + (size_t) (seq0 + r) * a.ioStride + t0 + 2 * pc);
         // uniforms: n 16-byte pieces per row (u1, u2 of one sample): one row per step
-        for (int r = 0; r < nLocal; ++r)
-            if (lane < n) dthCpAsync16(uni + r * kDthURow + 2 * lane, a.uniforms + ((size_t) (seq0 + r) * a.T + t0 + lane) * 2);
+        if (a.uniforms)
+            for (int r = 0; r < nLocal; ++r)
+                if (lane < n) dthCpAsync16(uni + r * kDthURow + 2 * lane, a.uniforms + ((size_t) (seq0 + r) * a.T + t0 + lane) * 2);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
@@ -1725,6 +1745,8 @@ __global__ void __launch_bounds__(32) dither_kernel(DitherArgs a)
     double c[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) c[i] = a.coeff[i];
+    const bool useRng = a.uniforms == nullptr;
+    unsigned long long rs = useRng ? a.rng[seq] : 0ull;
 
     issue(0, 0);
     if (nTiles > 1) issue(1, 1);
@@ -1745,11 +1767,23 @@ __global__ void __launch_bounds__(32) dither_kernel(DitherArgs a)
         const double* myU = uni + lane * kDthURow;
         if (live)
         {
-            if (n == kDthTile) dither_unrolled<0>(mine, myU, e, c, roleLeft, a.scale, a.invScale, a.finalClamp);
+            if (n == kDthTile)
+            {
+                if (useRng) dither_unrolled<0, true>(mine, myU, e, c, roleLeft, a.scale, a.invScale, a.finalClamp, rs);
+                else dither_unrolled<0, false>(mine, myU, e, c, roleLeft, a.scale, a.invScale, a.finalClamp, rs);
+            }
             else
                 for (int i = 0; i < n; ++i)   // last, partial tile: shift the history like the reference does
                 {
-                    mine[i] = dither_sample<0>(mine[i], *reinterpret_cast<const double2*>(myU + 2 * i), e, c, roleLeft, a.scale, a.invScale, a.finalClamp);
+                    double2 uu;
+                    if (useRng)
+                    {
+                        uu.x = dither_fallback_uniform(rs);
+                        uu.y = dither_fallback_uniform(rs);
+                    }
+                    else
+                        uu = *reinterpret_cast<const double2*>(myU + 2 * i);
+                    mine[i] = dither_sample<0>(mine[i], uu, e, c, roleLeft, a.scale, a.invScale, a.finalClamp);
                     const double newest = e[11];
 #pragma unroll
                     for (int t = 11; t > 0; --t) e[t] = e[t - 1];
@@ -1772,6 +1806,7 @@ __global__ void __launch_bounds__(32) dither_kernel(DitherArgs a)
     {
 #pragma unroll
         for (int i = 0; i < 12; ++i) a.z[(size_t) seq * 12 + i] = e[i];
+        if (useRng) a.rng[seq] = rs;
     }
 }
 

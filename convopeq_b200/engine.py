@@ -148,6 +148,15 @@ class ConvoPeqEngine:
             assert u.shape[0] == self.n_seq and u.shape[1] % 2 == 0
             self._check(self.lib.cpq_set_dither_uniforms(self.h, u.ctypes.data_as(_dp), u.shape[1] // 2))
 
+    def set_dither_seed(self, stream_seeds: Optional[Sequence[int]]):
+        """Dither uniforms from the reference's fallback generator (PsychoacousticDither(seed) per stream); None = injected uniforms."""
+        if stream_seeds is None:
+            self._check(self.lib.cpq_set_dither_seed(self.h, None))
+            return
+        assert len(stream_seeds) == self.cfg.n_streams
+        arr = (C.c_uint64 * len(stream_seeds))(*[int(s) & 0xFFFFFFFFFFFFFFFF for s in stream_seeds])
+        self._check(self.lib.cpq_set_dither_seed(self.h, arr))
+
     def set_dither_uniforms_device(self, data_ptr: int, samples_per_channel: int):
         """Injected dither uniforms already on the device: [n_seq][2 * samples] doubles, borrowed."""
         self._check(self.lib.cpq_set_dither_uniforms_device(self.h, data_ptr, samples_per_channel))

@@ -218,6 +218,13 @@ cpq_status cpq_schedule_total_gain(cpq_handle h, int stream, int64_t at_callback
  * reference's MKL VSL ring. */
 cpq_status cpq_set_epilogue(cpq_handle h, double makeup_gain, int dither_bits);
 cpq_status cpq_set_dither_uniforms(cpq_handle h, const double* uniforms, int64_t samples_per_channel);
+/* Uniforms from the reference's own generator instead of injected ones: PsychoacousticDither falls back to a per-channel
+ * xorshift64* generator whenever its VSL stream is not valid (fallbackUniform, PsychoacousticDither.h:485-497, used by
+ * nextTPDF_MKL :560-572), seeded per channel through SplitMix64(seed) (:118-140).  stream_seeds[n_streams]: the `seed` argument
+ * of each stream's PsychoacousticDither(seed); every process call then draws two uniforms per channel-sample on the device --
+ * no 16 bytes per sample of host-supplied numbers -- and equals the reference bit for bit in that mode (pinned with a VSL
+ * shim whose vslNewStream fails).  The generator state is part of the streaming state.  NULL switches back to injected uniforms. */
+cpq_status cpq_set_dither_seed(cpq_handle h, const uint64_t* stream_seeds);
 /* The same for uniforms that already live on the handle's device (16-byte aligned, same layout): borrowed, not copied -- the
  * buffer must stay valid until the process calls that use it have returned. */
 cpq_status cpq_set_dither_uniforms_device(cpq_handle h, const double* d_uniforms, int64_t samples_per_channel);

@@ -348,6 +348,17 @@ class Oracle(_Base):
             out[ch], _, zs[ch] = self.epilogue(x[ch], 1.0, sr, bit_depth, np.ascontiguousarray(uniforms[ch]), role=role)
         return out, zs
 
+    def dither_run_seeded(self, x: np.ndarray, seed: int, sr: float, bit_depth: int, block: int = 512):
+        """PsychoacousticDither(seed) with its VSL stream unavailable (the header's own xorshift64* fallback generator)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        u = np.zeros((x.shape[0], 2 * x.shape[1]))
+        f = self.lib.cpqo_dither_fallback_uniforms
+        f.argtypes = [C.c_uint64, C.c_int, C.c_long, _dp]
+        f.restype = None
+        for ch in range(x.shape[0]):
+            f(C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), ch, 2 * x.shape[1], _p(u[ch]))
+        return self.dither_run(x, u, sr, bit_depth, block)
+
     def outer_mix(self, wet: np.ndarray, dry_in: np.ndarray, mix: float, delay: int) -> np.ndarray:
         """ConvolverProcessor::process, settled: scrub(wet) * sin-gain(mix) + delayed dry * sin-gain(1 - mix) (restated, unpinned)."""
         d = np.ascontiguousarray(wet, dtype=np.float64).copy()
@@ -422,6 +433,17 @@ class Ref(_Base):
         f.restype = None
         f(_p(d[0]), _p(d[1]) if d.shape[0] > 1 else None, d.shape[1], block, sr, bit_depth, headroom,
           _p(u[0]), _p(u[1]) if d.shape[0] > 1 else None, _p(z))
+        return d, z[:d.shape[0]]
+
+    def dither_run_seeded(self, x: np.ndarray, seed: int, sr: float, bit_depth: int, block: int = 512,
+                          headroom: float = 0.8912509381337456):
+        """The reference's PsychoacousticDither(seed) with vslNewStream failing: its own fallback generator supplies the uniforms."""
+        d = np.ascontiguousarray(x, dtype=np.float64).copy()
+        z = np.zeros((2, 12))
+        f = self.lib.cpqref_dither_process_fallback
+        f.argtypes = [_dp, _dp, C.c_long, C.c_int, C.c_double, C.c_int, C.c_double, C.c_uint64, _dp]
+        f.restype = None
+        f(_p(d[0]), _p(d[1]) if d.shape[0] > 1 else None, d.shape[1], block, sr, bit_depth, headroom, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), _p(z))
         return d, z[:d.shape[0]]
 
     def _nuc_set_impulse(self, h, ir, block, scale, spec, direct_head=False):

@@ -1642,6 +1642,28 @@ void cpqo_epilogue_ex(double* data, long n, double makeup_gain, double sample_ra
         data[i] = q;
     }
 }
+/* The uniform stream of channel `channel` of PsychoacousticDither(seed) when its VSL stream is not valid: SplitMix64(seed)
+ * hands channel i its seedValue (:118-140), fallbackState = seedValue ^ 0xd1b54a32d192ed03, then xorshift64* per draw
+ * (fallbackUniform, :485-497).  Writes n uniforms (two per sample: u1, u2). */
+void cpqo_dither_fallback_uniforms(unsigned long long seed, int channel, long n, double* out)
+{
+    unsigned long long sm = seed, x = 0;
+    for (int i = 0; i <= channel; ++i)
+    {
+        unsigned long long z = (sm += 0x9e3779b97f4a7c15ULL);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+        x = (z ^ (z >> 31)) ^ 0xd1b54a32d192ed03ULL;
+    }
+    for (long i = 0; i < n; ++i)
+    {
+        x ^= x >> 12;
+        x ^= x << 25;
+        x ^= x >> 27;
+        out[i] = (double) ((x * 2685821657736338717ULL) >> 11) * (1.0 / 9007199254740992.0);
+    }
+}
+
 void cpqo_epilogue(double* data, long n, double makeup_gain, double sample_rate, int bit_depth,
                    const double* uniforms, double* z, double* tmp_out)
 {

@@ -65,11 +65,17 @@ namespace
 struct VslInject { const double* values = nullptr; long count = 0; };
 thread_local VslInject g_vslInject[8];
 thread_local int g_vslCreated = 0;
+thread_local bool g_vslFail = false;   // vslNewStream reports failure: the reference falls back to its own xorshift64* generator
 }
 static void cpqref_vsl_begin() { g_vslCreated = 0; for (auto& v : g_vslInject) v = VslInject {}; }
 static void cpqref_vsl_inject(int channel, const double* values, long count) { g_vslInject[channel] = VslInject { values, count }; }
 int vslNewStream(VSLStreamStatePtr* stream, int, unsigned int)
 {
+    if (g_vslFail)
+    {
+        *stream = nullptr;
+        return -1;
+    }
     auto* s = new cpqref_vsl_stream();
     s->index = g_vslCreated++;
     if (s->index < 8) { s->values = g_vslInject[s->index].values; s->count = g_vslInject[s->index].count; }
@@ -447,6 +453,30 @@ double cpqref_ir_freq_peak_gain(const double* l, const double* r, int n)
 void cpqref_input_transform(double* data, int n, double gain)
 {
     convo::input_transform::convertDoubleToDoubleHighQuality(data, data, n, gain);
+}
+
+// The same with the VSL generator unavailable (vslNewStream fails): every uniform comes from the header's own
+// fallbackUniform (xorshift64*, :485-497), seeded per channel through SplitMix64(seed) (:118-140) -- a mode of the reference
+// that needs no injected numbers, so the library's cpq_set_dither_seed is pinned against it bit for bit.
+void cpqref_dither_process_fallback(double* L, double* R, long total, int block, double sr, int bits, double headroom,
+                                    unsigned long long seed, double* z_out)
+{
+    cpqref_vsl_begin();
+    g_vslFail = true;
+    auto* d = new convo::PsychoacousticDither(std::optional<uint64_t>(seed));
+    d->prepare(sr, bits);
+    for (long pos = 0; pos < total; pos += block)
+    {
+        const int n = (int) std::min<long>(block, total - pos);
+        d->processStereoBlock(L + pos, R ? R + pos : nullptr, n, headroom);
+        d->refillRandomRingNonRt();
+    }
+    if (z_out)
+        for (int c = 0; c < 2; ++c)
+            for (int t = 0; t < 12; ++t) z_out[c * 12 + t] = d->shaperStateBuffer[c * convo::PsychoacousticDither::STATE_STRIDE + t];
+    delete d;
+    g_vslFail = false;
+    cpqref_vsl_begin();
 }
 
 // UltraHighRateDCBlocker::init + process on one buffer (the IR loader runs it at 1 Hz, LoaderThread.cpp:590-598)

@@ -408,6 +408,26 @@ def test_dither_epilogue(checker, sr, bits, nch, block, T):
         assert np.array_equal(y[rows], want), s
 
 
+def test_dither_with_the_reference_fallback_generator(checker):
+    """cpq_set_dither_seed: uniforms drawn on the device by the reference's own fallback generator (one PsychoacousticDither(seed)
+    per stream); bit for bit against the reference compiled in place with its VSL stream failing."""
+    sr, bits, block, T, n_streams = 48000.0, 24, 512, 512 * 50 + 512, 37
+    x = np.stack([signals.noise(T, 300 + i, 0.3) for i in range(2 * n_streams)])
+    seeds = [(0x9E3779B97F4A7C15 * (s + 1)) & 0xFFFFFFFFFFFFFFFF for s in range(n_streams)]
+    eng = ConvoPeqEngine(n_streams, 2, sr, block, T)
+    eng.set_epilogue(0.9, bits)
+    eng.set_dither_seed(seeds)
+    y = x.copy()
+    eng.process(y, capi.STAGE_EPILOGUE)
+    y2 = x.copy()
+    eng.process(y2, capi.STAGE_EPILOGUE)        # one-shot mode: a fresh generator for every call
+    eng.close()
+    assert np.array_equal(y, y2)
+    for s in range(0, n_streams, 6):
+        want, _ = checker.dither_run_seeded(x[2 * s:2 * s + 2] * 0.9, seeds[s], sr, bits, block)
+        assert np.array_equal(y[2 * s:2 * s + 2], want), s
+
+
 def test_partition_range_partials_sum_to_full(checker):
     """cfg5 in miniature: the convolver is linear in the IR, so rank partials over partition ranges add up."""
     ir_len, block, T = 131072, 512, 32768

@@ -200,3 +200,15 @@ def test_ir_dc_blocker_stage_is_bit_identical_to_reference(oracle, ref):
         f.restype = None
         f(d.ctypes.data_as(C.POINTER(C.c_double)), n, sr, 1.0)
         assert np.array_equal(d, want)
+
+
+@pytest.mark.parametrize("seed", [1, 0xDEADBEEFCAFEF00D])
+def test_dither_fallback_generator_is_bit_identical_to_reference(oracle, ref, seed):
+    """PsychoacousticDither(seed) with vslNewStream failing: every uniform comes from the header's own xorshift64* generator
+    (fallbackUniform :485-497, seeded through SplitMix64 :118-140).  The restated generator + shaper equal it bit for bit."""
+    T = 60000
+    for nch in (2, 1):
+        x = np.stack([signals.noise(T, 1 + i, 0.3) for i in range(nch)])
+        q, z = ref.dither_run_seeded(x, seed, 48000.0, 24, 512)
+        w, zo = oracle.dither_run_seeded(x, seed, 48000.0, 24, 512)
+        assert np.array_equal(q, w) and np.array_equal(z, zo)

@@ -164,6 +164,20 @@ def test_dither_history_carries_bit_for_bit(checker):
     assert np.array_equal(y, want)
 
 
+def test_dither_generator_state_carries(checker):
+    """cpq_set_dither_seed in streaming mode: the xorshift64* state of every channel continues across calls."""
+    sr, block, T, bits = 48000.0, 512, 512 * 30, 24
+    x = np.stack([signals.noise(T, 45, 0.3), signals.noise(T, 46, 0.3)])
+    eng = ConvoPeqEngine(1, 2, sr, block, T)
+    eng.set_epilogue(1.0, bits)
+    eng.set_dither_seed([12345])
+    eng.set_streaming(True)
+    y = _segmented(eng, x, 7 * block, capi.STAGE_EPILOGUE)
+    eng.close()
+    want, _ = checker.dither_run_seeded(x, 12345, sr, bits, block)
+    assert np.array_equal(y, want)
+
+
 def test_export_import_state_moves_a_stream_to_another_handle():
     sr, block, T = 48000.0, 512, 512 * 96
     x = np.stack([signals.noise(T, 51 + i) for i in range(4)])
