@@ -2054,60 +2054,55 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 CPQ_CUDA(cudaMemcpy2DAsync(xcat.p + histLen, (size_t) catLen * sizeof(double), ioC, (size_t) stride * sizeof(double),
                                            (size_t) T * sizeof(double), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
             }
-            // ---- forward FFTs of every layer (all read the untouched input) ----
-            for (int li = 0; li < plan.numLayers; ++li)
-            {
+            // The three stages of a layer for sequences [q0, q0 + n) of this chunk.
+            auto fwdLayer = [&](int li, int q0, int n) -> cpq_status {
                 const LayerPlan& l = plan.layers[li];
-                if (K[li] == 0 || qb[li] >= qe[li]) continue;
+                if (K[li] == 0 || qb[li] >= qe[li]) return CPQ_OK;
                 FwdArgs a {};
-                a.src = ioC;
+                a.src = ioC + (size_t) q0 * stride;
                 a.srcStride = stride;
                 a.frameStart0 = -(int64_t) l.partSize;
                 a.lo = 0;
                 a.hi = T;
                 a.halfOnly = 0;
                 a.framesPerSeq = (int) K[li];
-                a.totalFrames = (int64_t) ns * K[li];
-                a.out = layer[li].X.p;
+                a.totalFrames = (int64_t) n * K[li];
+                a.out = layer[li].X.p + (size_t) q0 * xRows[li] * l.partSize;
                 a.outFramesPerSeq = (int) K[li];
                 a.outFrameOffset = 0;
                 if (strm)
                 {
-                    a.src = xcat.p;
+                    a.src = xcat.p + (size_t) q0 * catLen;
                     a.srcStride = catLen;
                     a.frameStart0 = (int64_t) histLen + (kOld[li] - 1) * (int64_t) l.partSize - cb0 * (int64_t) B;   // >= 0: histLen = 2 Pmax
                     a.hi = catLen;
                     a.outFramesPerSeq = (int) xRows[li];
                     a.outFrameOffset = fdlRows[li];
                     if (fdlRows[li] > 0)   // the FDL: spectra of the Q - 1 frames before this call's first one
-                        CPQ_CUDA(cudaMemcpy2DAsync(layer[li].X.p, (size_t) xRows[li] * l.partSize * sizeof(double2),
-                                                   fdl[li].p + (size_t) s0 * fdlRows[li] * l.partSize, (size_t) fdlRows[li] * l.partSize * sizeof(double2),
-                                                   (size_t) fdlRows[li] * l.partSize * sizeof(double2), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
+                        CPQ_CUDA(cudaMemcpy2DAsync(layer[li].X.p + (size_t) q0 * xRows[li] * l.partSize, (size_t) xRows[li] * l.partSize * sizeof(double2),
+                                                   fdl[li].p + (size_t) (s0 + q0) * fdlRows[li] * l.partSize, (size_t) fdlRows[li] * l.partSize * sizeof(double2),
+                                                   (size_t) fdlRows[li] * l.partSize * sizeof(double2), (size_t) n, cudaMemcpyDeviceToDevice, stream));
                 }
                 a.tw = layer[li].tw.p;
                 a.ptw = layer[li].ptw.p;
-                a.scratch = layer[li].Y.p;   // free until the MAC writes it
+                a.scratch = layer[li].Y.p + (size_t) q0 * K[li] * l.partSize;   // free until the MAC writes it
                 a.scale = 1.0;
-                cpq_status st = launchFwd(ilog2(l.partSize), a);
-                if (st != CPQ_OK) return st;
-            }
-            cudaEventRecord(ce[1], stream);
-            // ---- MAC ----
-            for (int li = 0; li < plan.numLayers; ++li)
-            {
+                return launchFwd(ilog2(l.partSize), a);
+            };
+            auto macLayer = [&](int li, int q0, int n) -> cpq_status {
                 const LayerPlan& l = plan.layers[li];
-                if (K[li] == 0) continue;
+                if (K[li] == 0) return CPQ_OK;
                 if (qb[li] >= qe[li])
                 {
                     // this rank holds no partition of the layer: its contribution is zero
-                    if (li == 0) CPQ_CUDA(cudaMemset2DAsync(ioC, (size_t) stride * sizeof(double), 0, (size_t) T * sizeof(double), (size_t) ns, stream));
-                    else CPQ_CUDA(cudaMemsetAsync(layer[li].tail.p, 0, (size_t) ns * K[li] * l.partSize * sizeof(double), stream));
-                    continue;
+                    if (li == 0) CPQ_CUDA(cudaMemset2DAsync(ioC + (size_t) q0 * stride, (size_t) stride * sizeof(double), 0, (size_t) T * sizeof(double), (size_t) n, stream));
+                    else CPQ_CUDA(cudaMemsetAsync(layer[li].tail.p + (size_t) q0 * K[li] * l.partSize, 0, (size_t) n * K[li] * l.partSize * sizeof(double), stream));
+                    return CPQ_OK;
                 }
                 MacArgs a {};
-                a.X = layer[li].X.p;
+                a.X = layer[li].X.p + (size_t) q0 * xRows[li] * l.partSize;
                 a.H = layer[li].H.p;
-                a.Y = layer[li].Y.p;
+                a.Y = layer[li].Y.p + (size_t) q0 * K[li] * l.partSize;
                 a.K = (int) K[li];
                 a.P = l.partSize;
                 a.Q = l.numPartsIR;
@@ -2115,13 +2110,13 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 a.qEnd = qe[li];
                 a.hSeqStride = (int64_t) l.numPartsIR * l.partSize;
                 a.hSeqMod = cfg.shared_ir ? cfg.n_channels : 0;
-                a.seqBase = s0;
-                if (!cfg.shared_ir) a.H += (size_t) s0 * a.hSeqStride;   // H rows are absolute sequence indices
+                a.seqBase = s0 + q0;
+                if (!cfg.shared_ir) a.H += (size_t) (s0 + q0) * a.hSeqStride;   // H rows are absolute sequence indices
                 // enough CTAs to fill the GPU a few times over, each amortising its H tile and ring warm-up over as many frames as possible
                 const int binTiles = l.partSize / kMacBins;
                 const int step = kMacSuper;
                 int fpc = (int) ((K[li] + step - 1) / step) * step;
-                while (fpc > 2 * step && (int64_t) binTiles * ns * ((K[li] + fpc - 1) / fpc) < 4 * 148 * 2) fpc = ((fpc / 2 + step - 1) / step) * step;
+                while (fpc > 2 * step && (int64_t) binTiles * n * ((K[li] + fpc - 1) / fpc) < 4 * 148 * 2) fpc = ((fpc / 2 + step - 1) / step) * step;
                 static const int fpcEnv = [] { const char* e = getenv("CPQ_MAC_FPC"); return e ? atoi(e) : 0; }();   // tuning knob
                 if (fpcEnv > 0 && fpcEnv % step == 0 && fpcEnv < fpc && K[li] <= 2 * step) fpc = fpcEnv;   // short layers only
                 a.framesPerCta = fpc;
@@ -2134,58 +2129,76 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                     setError("process: MAC tile exceeds the shared memory of one SM");
                     return CPQ_ERR_UNSUPPORTED;
                 }
-                dim3 grid((unsigned) binTiles, (unsigned) ((K[li] + fpc - 1) / fpc), (unsigned) ns);
+                dim3 grid((unsigned) binTiles, (unsigned) ((K[li] + fpc - 1) / fpc), (unsigned) n);
                 // tensor-map staging (one TMA copy per 64-frame block, no CTA barrier in the frame loop) for filters of up to
                 // 65 taps; longer ones (uniform-partition extension) keep the row-copy kernel
                 static const int tmaEnv = [] { const char* e = getenv("CPQ_MAC_TMA"); return e ? atoi(e) : 1; }();   // tuning knob
                 MacTensorMap tmX, tmH;
                 if (tmaEnv && a.qEnd - a.qBegin <= kMacTmaMaxTaps && macTmaSmemBytes(a.qEnd - a.qBegin) <= kMaxDynSmem &&
-                    encodeSpectraMap(tmX, layer[li].X.p, 2 * (uint64_t) l.partSize, (uint64_t) xRows[li], (uint64_t) ns, (uint32_t) kMacSuper) &&
+                    encodeSpectraMap(tmX, a.X, 2 * (uint64_t) l.partSize, (uint64_t) xRows[li], (uint64_t) n, (uint32_t) kMacSuper) &&
                     encodeSpectraMap(tmH, layer[li].H.p, 2 * (uint64_t) l.partSize, (uint64_t) l.numPartsIR, (uint64_t) nH, (uint32_t) (a.qEnd - a.qBegin)))
-                {
                     mac_tma_kernel<<<grid, kMacThreads, macTmaSmemBytes(a.qEnd - a.qBegin), stream>>>(a, tmX, tmH);
-                    ++launches;
-                    CPQ_CUDA(cudaGetLastError());
-                    if (strm && fdlRows[li] > 0)
-                        CPQ_CUDA(cudaMemcpy2DAsync(fdl[li].p + (size_t) s0 * fdlRows[li] * l.partSize, (size_t) fdlRows[li] * l.partSize * sizeof(double2),
-                                                   layer[li].X.p + (size_t) K[li] * l.partSize, (size_t) xRows[li] * l.partSize * sizeof(double2),
-                                                   (size_t) fdlRows[li] * l.partSize * sizeof(double2), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
-                    continue;
-                }
-                mac_kernel<<<grid, kMacThreads, smem, stream>>>(a);
+                else
+                    mac_kernel<<<grid, kMacThreads, smem, stream>>>(a);
                 ++launches;
                 CPQ_CUDA(cudaGetLastError());
                 if (strm && fdlRows[li] > 0)   // the FDL the next call starts from: the last Q - 1 rows of [carried | new]
-                    CPQ_CUDA(cudaMemcpy2DAsync(fdl[li].p + (size_t) s0 * fdlRows[li] * l.partSize, (size_t) fdlRows[li] * l.partSize * sizeof(double2),
-                                               layer[li].X.p + (size_t) K[li] * l.partSize, (size_t) xRows[li] * l.partSize * sizeof(double2),
-                                               (size_t) fdlRows[li] * l.partSize * sizeof(double2), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
+                    CPQ_CUDA(cudaMemcpy2DAsync(fdl[li].p + (size_t) (s0 + q0) * fdlRows[li] * l.partSize, (size_t) fdlRows[li] * l.partSize * sizeof(double2),
+                                               a.X + (size_t) K[li] * l.partSize, (size_t) xRows[li] * l.partSize * sizeof(double2),
+                                               (size_t) fdlRows[li] * l.partSize * sizeof(double2), (size_t) n, cudaMemcpyDeviceToDevice, stream));
+                return CPQ_OK;
+            };
+            auto invLayer = [&](int li, int q0, int n) -> cpq_status {
+                const LayerPlan& l = plan.layers[li];
+                const size_t tailPitch = (size_t) ((strm ? carryFrames[li] : 0) + K[li]) * l.partSize;
+                if (strm && li > 0)   // the delay line: tail samples computed by earlier calls that this call's callbacks still read
+                    CPQ_CUDA(cudaMemcpy2DAsync(layer[li].tail.p + (size_t) q0 * tailPitch, tailPitch * sizeof(double),
+                                               tailCarry[li].p + (size_t) (s0 + q0) * carryFrames[li] * l.partSize, (size_t) carryFrames[li] * l.partSize * sizeof(double),
+                                               (size_t) carryFrames[li] * l.partSize * sizeof(double), (size_t) n, cudaMemcpyDeviceToDevice, stream));
+                if (K[li] == 0 || qb[li] >= qe[li]) return CPQ_OK;
+                InvArgs a {};
+                a.in = layer[li].Y.p + (size_t) q0 * K[li] * l.partSize;
+                a.framesPerSeq = (int) K[li];
+                a.framesOut = (int) K[li];
+                a.totalFrames = (int64_t) n * K[li];
+                a.out = (li == 0 && !l0Ring) ? ioC + (size_t) q0 * stride : layer[li].tail.p + (size_t) q0 * tailPitch;
+                a.outStride = (li == 0 && !l0Ring) ? stride : (int64_t) tailPitch;
+                if (strm && li > 0) a.out += (size_t) carryFrames[li] * l.partSize;
+                a.tw = layer[li].tw.p;
+                a.ptw = layer[li].ptw.p;
+                a.scratch = layer[li].X.p + (size_t) q0 * xRows[li] * l.partSize;   // the MAC has consumed it
+                return launchInv(ilog2(l.partSize), a);
+            };
+            // L0 in slices small enough for its spectra to stay in the L2 between the three launches (tuning knob; 0 = off)
+            static const int l0Sub = [] { const char* e = getenv("CPQ_L0_SUB"); return e ? atoi(e) : 0; }();
+            const bool sliceL0 = l0Sub > 0 && !strm && !l0Ring && plan.numLayers > 1 && l0Sub < ns;
+            // ---- forward FFTs of every layer (all read the untouched input) ----
+            for (int li = sliceL0 ? 1 : 0; li < plan.numLayers; ++li)
+            {
+                cpq_status st = fwdLayer(li, 0, ns);
+                if (st != CPQ_OK) return st;
+            }
+            cudaEventRecord(ce[1], stream);
+            // ---- MAC ----
+            if (sliceL0)
+                for (int q0 = 0; q0 < ns; q0 += l0Sub)
+                {
+                    const int n = std::min(l0Sub, ns - q0);
+                    cpq_status st = fwdLayer(0, q0, n);
+                    if (st == CPQ_OK) st = macLayer(0, q0, n);
+                    if (st == CPQ_OK) st = invLayer(0, q0, n);
+                    if (st != CPQ_OK) return st;
+                }
+            for (int li = sliceL0 ? 1 : 0; li < plan.numLayers; ++li)
+            {
+                cpq_status st = macLayer(li, 0, ns);
+                if (st != CPQ_OK) return st;
             }
             cudaEventRecord(ce[2], stream);
             // ---- inverse FFTs: L0 in place into io, tails into their stream buffers ----
-            for (int li = 0; li < plan.numLayers; ++li)
+            for (int li = sliceL0 ? 1 : 0; li < plan.numLayers; ++li)
             {
-                const LayerPlan& l = plan.layers[li];
-                if (strm && li > 0)   // the delay line: tail samples computed by earlier calls that this call's callbacks still read
-                    CPQ_CUDA(cudaMemcpy2DAsync(layer[li].tail.p, (size_t) (carryFrames[li] + K[li]) * l.partSize * sizeof(double),
-                                               tailCarry[li].p + (size_t) s0 * carryFrames[li] * l.partSize, (size_t) carryFrames[li] * l.partSize * sizeof(double),
-                                               (size_t) carryFrames[li] * l.partSize * sizeof(double), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
-                if (K[li] == 0 || qb[li] >= qe[li]) continue;
-                InvArgs a {};
-                a.in = layer[li].Y.p;
-                a.framesPerSeq = (int) K[li];
-                a.framesOut = (int) K[li];
-                a.totalFrames = (int64_t) ns * K[li];
-                a.out = (li == 0 && !l0Ring) ? ioC : layer[li].tail.p;
-                a.outStride = (li == 0 && !l0Ring) ? stride : (int64_t) K[li] * l.partSize;
-                if (strm && li > 0)
-                {
-                    a.out += (size_t) carryFrames[li] * l.partSize;
-                    a.outStride = (int64_t) (carryFrames[li] + K[li]) * l.partSize;
-                }
-                a.tw = layer[li].tw.p;
-                a.ptw = layer[li].ptw.p;
-                a.scratch = layer[li].X.p;   // the MAC has consumed it
-                cpq_status st = launchInv(ilog2(l.partSize), a);
+                cpq_status st = invLayer(li, 0, ns);
                 if (st != CPQ_OK) return st;
             }
             if (strm)   // input history for the next call: the last histLen samples of [history | input]

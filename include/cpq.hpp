@@ -164,6 +164,11 @@ public:
     /// ConvolverProcessor::setMix (Runtime.cpp:816) + the dry path's latency compensation (settled state).
     bool setMix(float mix, int dryDelaySamples) { return ok(cpq_set_mix(h_, mix, dryDelaySamples)); }
     bool setOutputProtection(double dcCutoffHz, bool hardClamp) { return ok(cpq_set_output_stage(h_, dcCutoffHz, hardClamp ? 1 : 0)); }
+    /// PsychoacousticDither(seed) per stream, uniforms from the header's own fallback generator (no injected numbers needed).
+    bool setDitherSeeds(std::span<const std::uint64_t> streamSeeds)
+    {
+        return (int) streamSeeds.size() == cfg_.n_streams && ok(cpq_set_dither_seed(h_, streamSeeds.data()));
+    }
     bool setDitherUniforms(std::span<const double> uniforms, std::int64_t samplesPerChannel)
     {
         return ok(cpq_set_dither_uniforms(h_, uniforms.data(), samplesPerChannel));
