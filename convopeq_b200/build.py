@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False, out: str | None = None, de
     out_ = subprocess.run(cmd, capture_output=True, text=True)
     out = out_
     log = out.stdout + out.stderr
-    with open(os.path.join(HERE, "build.log"), "w") as f:
+    with open(os.path.join(HERE, "build.log") if target == LIB else target + ".log", "w") as f:   # build.log describes libcpq.so only
         f.write(" ".join(cmd) + "\n" + log)
     if verbose or out.returncode != 0:
         print(log[-8000:])
