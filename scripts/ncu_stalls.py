@@ -4,7 +4,9 @@ import csv, io, subprocess, sys, collections
 rep, rx = sys.argv[1], sys.argv[2]
 which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + rx], capture_output=True, text=True).stdout
+# kernel_regex "id:N" selects the N-th profiled launch (1-based) instead of a name: template instances share a base name
+sel = ["--kernel-id", ":::" + rx[3:]] if rx.startswith("id:") else ["--kernel-name", "regex:" + rx]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
 # split per kernel instance
 blocks, cur = [], []
 for line in raw.splitlines():
