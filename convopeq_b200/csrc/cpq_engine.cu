@@ -7,12 +7,16 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -96,6 +100,155 @@ struct DevBuf
         return cudaSuccess;
     }
 };
+
+// Page-locked host memory (staging slots for pageable caller buffers)
+struct PinnedBuf
+{
+    double* p = nullptr;
+    size_t n = 0;
+    ~PinnedBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(double), cudaHostAllocDefault);
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+};
+
+// Pageable caller buffers (what a host application hands over: std::vector, juce::AudioBuffer, numpy).  cudaMemcpyAsync on
+// such memory is staged by the driver through its own bounce buffer on the calling thread -- about 7 GB/s, H2D and D2H one after
+// the other.  Instead the rows of sequence chunk c are copied by a few host threads into slot c % kSlots of a pinned ring, from
+// where the chunk goes down as the pinned path's copies do; results come up into a second ring and are copied out by a second
+// set of threads.  The calling thread only enqueues; it waits for "chunk staged" before it enqueues the chunk's H2D and for
+// "slot drained" before it lets a D2H overwrite a slot.
+struct HostStager
+{
+    static constexpr int kSlots = 3;
+    struct Chunk { int s0 = 0, ns = 0; };
+    int device = 0;
+    int nThreads = 0;
+    int64_t T = 0;
+    size_t slotElems = 0;
+    double* const* rows = nullptr;        // caller rows, indexed by absolute sequence
+    double* in = nullptr;
+    double* out = nullptr;
+    std::vector<Chunk> chunks;
+    std::vector<cudaEvent_t> evH2D, evD2H;   // recorded by the calling thread when it enqueues the copies
+    std::vector<int> staged, drained;        // threads that have finished the chunk
+    size_t h2dEnqueued = 0, d2hEnqueued = 0;
+    bool abort = false;
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<std::thread> threads;
+
+    double* inSlot(size_t c) const { return in + (c % kSlots) * slotElems; }
+    double* outSlot(size_t c) const { return out + (c % kSlots) * slotElems; }
+
+    void start()
+    {
+        staged.assign(chunks.size(), 0);
+        drained.assign(chunks.size(), 0);
+        for (int j = 0; j < nThreads; ++j)
+        {
+            threads.emplace_back([this, j] { feed(j); });
+            threads.emplace_back([this, j] { drain(j); });
+        }
+    }
+    // thread j of the feeders: its share of the rows of every chunk, caller -> pinned slot
+    void feed(int j)
+    {
+        cudaSetDevice(device);
+        for (size_t c = 0; c < chunks.size(); ++c)
+        {
+            if (c >= (size_t) kSlots)
+            {
+                // the slot is free once the H2D of chunk c - kSlots has left it
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return abort || h2dEnqueued > c - kSlots; });
+                if (abort) return;
+                lk.unlock();
+                cudaEventSynchronize(evH2D[c - kSlots]);
+            }
+            const Chunk& k = chunks[c];
+            for (int r = j; r < k.ns; r += nThreads) std::memcpy(inSlot(c) + (size_t) r * T, rows[k.s0 + r], (size_t) T * sizeof(double));
+            std::lock_guard<std::mutex> lk(m);
+            if (abort) return;
+            ++staged[c];
+            cv.notify_all();
+        }
+    }
+    void drain(int j)
+    {
+        cudaSetDevice(device);
+        for (size_t c = 0; c < chunks.size(); ++c)
+        {
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return abort || d2hEnqueued > c; });
+                if (abort) return;
+            }
+            cudaEventSynchronize(evD2H[c]);
+            const Chunk& k = chunks[c];
+            for (int r = j; r < k.ns; r += nThreads) std::memcpy(rows[k.s0 + r], outSlot(c) + (size_t) r * T, (size_t) T * sizeof(double));
+            std::lock_guard<std::mutex> lk(m);
+            if (abort) return;
+            ++drained[c];
+            cv.notify_all();
+        }
+    }
+    // calling thread
+    void waitStaged(size_t c)
+    {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return staged[c] == nThreads; });
+    }
+    void waitDrained(size_t c)
+    {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return drained[c] == nThreads; });
+    }
+    void noteH2D(size_t c)
+    {
+        std::lock_guard<std::mutex> lk(m);
+        h2dEnqueued = c + 1;
+        cv.notify_all();
+    }
+    void noteD2H(size_t c)
+    {
+        std::lock_guard<std::mutex> lk(m);
+        d2hEnqueued = c + 1;
+        cv.notify_all();
+    }
+    ~HostStager()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            // a regular end has every chunk drained; anything else is an error exit: release the threads
+            if (drained.empty() || drained.back() != nThreads) abort = true;
+            cv.notify_all();
+        }
+        for (auto& t : threads) t.join();
+    }
+};
+
+static bool hostRowIsPageable(const void* p)
+{
+    cudaPointerAttributes at {};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return true;
+    }
+    return at.type == cudaMemoryTypeUnregistered;
+}
 
 // number of overwritten canaries among the live guarded buffers (0 = clean); -1 when guard mode is off
 static int checkGuards()
@@ -284,6 +437,7 @@ struct Engine
     cpq_status processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF = nullptr);
     cpq_status processCoreImpl(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF);
     DevBuf<float> f32In, f32Out;        // device staging of float host buffers: 3 inbound / 2 outbound chunk slots
+    PinnedBuf stageIn, stageOut;        // pinned staging rings for pageable FP64 host buffers (HostStager)
     cpq_status processDevice(double* dIo, int64_t stride, int64_t T, unsigned stages) { return processCore(dIo, stride, T, stages, nullptr); }
     cpq_status launchFwd(int log2P, const FwdArgs& a);
     cpq_status launchFwdLarge(int log2P, const FwdArgs& a);
@@ -1514,7 +1668,7 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
         pm.streams = parMsStreamsDev.p + p0;
         pm.streamBase = st0;
         pm.T = e.T;
-        pg = dim3((unsigned) std::min<int64_t>(64, (e.T / 2 + 255) / 256), (unsigned) parCnt);
+        pg = dim3((unsigned) std::min<int64_t>(64, ((e.T + 1) / 2 + 255) / 256), (unsigned) parCnt);
         ms_kernel<0><<<pg, 256, 0, stream>>>(pm);
         ++launches;
         EqArgs q = e;
@@ -1567,7 +1721,7 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
         m.streams = msStreamsDev[b].p + i0;
         m.streamBase = st0;
         m.T = e.T;
-        const dim3 mg((unsigned) std::min<int64_t>(64, (e.T / 2 + 255) / 256), (unsigned) cnt);
+        const dim3 mg((unsigned) std::min<int64_t>(64, ((e.T + 1) / 2 + 255) / 256), (unsigned) cnt);
         ms_kernel<0><<<mg, 256, 0, stream>>>(m);
         ++launches;
         EqArgs q = e;
@@ -1672,9 +1826,11 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
 cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF)
 {
     const bool hostIO = hostPlanar || hostF;
-    if (!dIo || T <= 0 || T > cfg.max_samples || T % cfg.block_size != 0 || (T & 1) || stride < T || (stride & 1))
+    // rows are 16-byte aligned (even stride); an odd T (odd host blocks: 441 x an odd number of callbacks) leaves one pad
+    // sample at the end of each row, which the paired accesses of the small kernels may touch
+    if (!dIo || T <= 0 || T > cfg.max_samples || T % cfg.block_size != 0 || stride < T + (T & 1) || (stride & 1))
     {
-        setError("process: T must be a positive even multiple of block_size <= max_samples; stride even and >= T");
+        setError("process: T must be a positive multiple of block_size <= max_samples; stride even and >= T");
         return CPQ_ERR_INVALID;
     }
     if ((stages & ~(CPQ_STAGE_FULL | CPQ_ORDER_EQ_THEN_CONV | CPQ_STAGE_INPUT)) || (stages & (CPQ_STAGE_FULL | CPQ_STAGE_INPUT)) == 0)
@@ -1832,6 +1988,10 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
         chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) nSeq, cfg.workspace_bytes / std::max<size_t>(perSeq, 1)));
     }
     if (hostIO) chunk = std::max(1, std::min(chunk, (nSeq + 31) / 32));   // short pipeline fill/drain
+    // pageable caller rows go through pinned staging slots (HostStager): smaller chunks bound the pinned memory (6 slots)
+    static const int stageThreadsEnv = [] { const char* e = getenv("CPQ_STAGE_THREADS"); return e ? atoi(e) : -1; }();   // 0 = let the driver stage
+    const bool pageable = hostPlanar && stageThreadsEnv != 0 && (hostRowIsPageable(hostPlanar[seqLo]) || hostRowIsPageable(hostPlanar[seqLo + nSeq - 1]));
+    if (pageable) chunk = std::max(1, std::min(chunk, (nSeq + 63) / 64));
     if (limiterOn) chunk = std::max(cfg.n_channels, chunk / cfg.n_channels * cfg.n_channels);   // whole streams per chunk
     if (doEq && (anyAgc || anyMs))
     {
@@ -1884,14 +2044,40 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
     }
     const size_t nChunks = (size_t) ((nSeq + chunk - 1) / chunk);
     // event pool layout: [c*6 + 0..4] stage boundaries on the compute stream, [c*6 + 5] H2D done on the copy-in stream
-    for (size_t i = 0; i < nChunks * 11 + 4; ++i) poolEvent(i);
+    for (size_t i = 0; i < nChunks * 12 + 4; ++i) poolEvent(i);
     const size_t dBase = nChunks * 9 + 4;   // per chunk [0] EQ done (compute stream), [1] dither / limiter done (side stream)
+    const size_t pBase = nChunks * 11 + 4;  // per chunk: D2H into the pinned staging slot done (pageable caller rows)
+    std::unique_ptr<HostStager> stager;
+    if (pageable)
+    {
+        const size_t slotElems = (size_t) chunk * T;
+        CPQ_CUDA(stageIn.ensure(HostStager::kSlots * slotElems));
+        CPQ_CUDA(stageOut.ensure(HostStager::kSlots * slotElems));
+        stager = std::make_unique<HostStager>();
+        stager->device = cfg.device;
+        const int hw = (int) std::thread::hardware_concurrency();
+        stager->nThreads = stageThreadsEnv > 0 ? stageThreadsEnv : std::max(2, std::min(16, hw / 2));   // measured on a 16-core box, cfg4: 4 threads 493 ms, 16 threads 390 ms, driver staging 1161 ms
+        stager->T = T;
+        stager->slotElems = slotElems;
+        stager->rows = hostPlanar;
+        stager->in = stageIn.p;
+        stager->out = stageOut.p;
+        for (size_t c = 0; c < nChunks; ++c)
+        {
+            const int s0 = seqLo + (int) c * chunk;
+            stager->chunks.push_back({ s0, std::min(chunk, seqLo + nSeq - s0) });
+            stager->evH2D.push_back(evPool[c * 6 + 5]);
+            stager->evD2H.push_back(evPool[pBase + c]);
+        }
+        stager->start();
+    }
     // float host buffers: per chunk [0] inbound conversion done, [1] outbound conversion done (compute stream), [2] D2H done
     const size_t fBase = nChunks * 6 + 4;
+    const int64_t Tp = (T + 1) & ~(int64_t) 1;   // row pitch of the float staging slots (8-byte aligned rows)
     if (hostF)
     {
-        CPQ_CUDA(f32In.ensure((size_t) 3 * chunk * T));
-        CPQ_CUDA(f32Out.ensure((size_t) 2 * chunk * T));
+        CPQ_CUDA(f32In.ensure((size_t) 3 * chunk * Tp));
+        CPQ_CUDA(f32Out.ensure((size_t) 2 * chunk * Tp));
     }
     cudaEvent_t evInBegin = evPool[nChunks * 6 + 0], evInEnd = evPool[nChunks * 6 + 1];
     cudaEvent_t evOutBegin = evPool[nChunks * 6 + 2], evOutEnd = evPool[nChunks * 6 + 3];
@@ -1909,7 +2095,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             if (hostF[s] - hostF[s - 1] != pitchF) pitchF = 0;
         if (pitchF < T) pitchF = 0;
     }
-    if (hostPlanar && nSeqAll > 1)
+    if (hostPlanar && nSeqAll > 1 && !pageable)
     {
         hostPitch = hostPlanar[1] - hostPlanar[0];
         for (int s = 2; s < nSeqAll && hostPitch > 0; ++s)
@@ -1923,13 +2109,19 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
         {
             // into staging slot c % 3, free once chunk c - 3 has been converted
             if (c >= 3) cudaStreamWaitEvent(sIn, evPool[fBase + (c - 3) * 3], 0);
-            float* slot = f32In.p + (c % 3) * (size_t) chunk * T;
+            float* slot = f32In.p + (c % 3) * (size_t) chunk * Tp;
             if (pitchF > 0)
-                e = cudaMemcpy2DAsync(slot, (size_t) T * sizeof(float), hostF[s0], (size_t) pitchF * sizeof(float), (size_t) T * sizeof(float),
+                e = cudaMemcpy2DAsync(slot, (size_t) Tp * sizeof(float), hostF[s0], (size_t) pitchF * sizeof(float), (size_t) T * sizeof(float),
                                       (size_t) ns, cudaMemcpyHostToDevice, sIn);
             else
                 for (int s = s0; s < s0 + ns && e == cudaSuccess; ++s)
-                    e = cudaMemcpyAsync(slot + (size_t) (s - s0) * T, hostF[s], (size_t) T * sizeof(float), cudaMemcpyHostToDevice, sIn);
+                    e = cudaMemcpyAsync(slot + (size_t) (s - s0) * Tp, hostF[s], (size_t) T * sizeof(float), cudaMemcpyHostToDevice, sIn);
+        }
+        else if (stager)
+        {
+            stager->waitStaged(c);   // the feeder threads have copied the chunk's rows into the pinned slot
+            e = cudaMemcpy2DAsync(dIo + (size_t) s0 * stride, (size_t) stride * sizeof(double), stager->inSlot(c), (size_t) T * sizeof(double),
+                                  (size_t) T * sizeof(double), (size_t) ns, cudaMemcpyHostToDevice, sIn);
         }
         else if (hostPitch == T && stride == T)   // both sides dense: one linear copy
             e = cudaMemcpyAsync(dIo + (size_t) s0 * stride, hostPlanar[s0], (size_t) ns * T * sizeof(double), cudaMemcpyHostToDevice, sIn);
@@ -1940,6 +2132,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             for (int s = s0; s < s0 + ns && e == cudaSuccess; ++s)
                 e = cudaMemcpyAsync(dIo + (size_t) s * stride, hostPlanar[s], (size_t) T * sizeof(double), cudaMemcpyHostToDevice, sIn);
         if (e == cudaSuccess) e = cudaEventRecord(evPool[c * 6 + 5], sIn);
+        if (stager && e == cudaSuccess) stager->noteH2D(c);
         if (c + 1 == nChunks && e == cudaSuccess) e = cudaEventRecord(evInEnd, sIn);
         return e;
     };
@@ -2000,10 +2193,10 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
         double* ioC = dIo + (size_t) s0 * stride;
         cudaEvent_t* ce = &evPool[c * 6];
         if (hostIO) cudaStreamWaitEvent(stream, evPool[c * 6 + 5], 0);
-        const dim3 cvGrid((unsigned) std::min<int64_t>(128, (T / 2 + 255) / 256), (unsigned) ns);
+        const dim3 cvGrid((unsigned) std::min<int64_t>(128, ((T + 1) / 2 + 255) / 256), (unsigned) ns);
         if (hostF)
         {
-            convert_kernel<true><<<cvGrid, 256, 0, stream>>>(f32In.p + (c % 3) * (size_t) chunk * T, ioC, stride, T);
+            convert_kernel<true><<<cvGrid, 256, 0, stream>>>(f32In.p + (c % 3) * (size_t) chunk * Tp, ioC, stride, T);
             ++launches;
             cudaEventRecord(evPool[fBase + c * 3], stream);
         }
@@ -2383,7 +2576,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
         {
             // out through staging slot c % 2, free once chunk c - 2 has left the device
             if (c >= 2) cudaStreamWaitEvent(stream, evPool[fBase + (c - 2) * 3 + 2], 0);
-            float* slot = f32Out.p + (c % 2) * (size_t) chunk * T;
+            float* slot = f32Out.p + (c % 2) * (size_t) chunk * Tp;
             convert_kernel<false><<<cvGrid, 256, 0, stream>>>(slot, ioC, stride, T);
             ++launches;
             CPQ_CUDA(cudaGetLastError());
@@ -2391,11 +2584,11 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             cudaStreamWaitEvent(sOut, evPool[fBase + c * 3 + 1], 0);
             if (c == 0) cudaEventRecord(evOutBegin, sOut);
             if (pitchF > 0)
-                CPQ_CUDA(cudaMemcpy2DAsync(hostF[s0], (size_t) pitchF * sizeof(float), slot, (size_t) T * sizeof(float), (size_t) T * sizeof(float),
+                CPQ_CUDA(cudaMemcpy2DAsync(hostF[s0], (size_t) pitchF * sizeof(float), slot, (size_t) Tp * sizeof(float), (size_t) T * sizeof(float),
                                            (size_t) ns, cudaMemcpyDeviceToHost, sOut));
             else
                 for (int s = s0; s < s0 + ns; ++s)
-                    CPQ_CUDA(cudaMemcpyAsync(hostF[s], slot + (size_t) (s - s0) * T, (size_t) T * sizeof(float), cudaMemcpyDeviceToHost, sOut));
+                    CPQ_CUDA(cudaMemcpyAsync(hostF[s], slot + (size_t) (s - s0) * Tp, (size_t) T * sizeof(float), cudaMemcpyDeviceToHost, sOut));
             cudaEventRecord(evPool[fBase + c * 3 + 2], sOut);
             if (c + kH2DAhead < nChunks) CPQ_CUDA(enqueueH2D(c + kH2DAhead));
         }
@@ -2403,7 +2596,15 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
         {
             cudaStreamWaitEvent(sOut, doDither ? evPool[dBase + c * 2 + 1] : ce[4], 0);
             if (c == 0) cudaEventRecord(evOutBegin, sOut);
-            if (hostPitch == T && stride == T)
+            if (stager)
+            {
+                if (c >= (size_t) HostStager::kSlots) stager->waitDrained(c - HostStager::kSlots);   // the slot's previous content has reached the caller
+                CPQ_CUDA(cudaMemcpy2DAsync(stager->outSlot(c), (size_t) T * sizeof(double), dIo + (size_t) s0 * stride, (size_t) stride * sizeof(double),
+                                           (size_t) T * sizeof(double), (size_t) ns, cudaMemcpyDeviceToHost, sOut));
+                CPQ_CUDA(cudaEventRecord(evPool[pBase + c], sOut));
+                stager->noteD2H(c);
+            }
+            else if (hostPitch == T && stride == T)
                 CPQ_CUDA(cudaMemcpyAsync(hostPlanar[s0], dIo + (size_t) s0 * stride, (size_t) ns * T * sizeof(double), cudaMemcpyDeviceToHost, sOut));
             else if (hostPitch > 0)
                 CPQ_CUDA(cudaMemcpy2DAsync(hostPlanar[s0], (size_t) hostPitch * sizeof(double), dIo + (size_t) s0 * stride, (size_t) stride * sizeof(double),
@@ -2431,6 +2632,11 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
     }
     cudaEventRecord(ev[6], stream);
     CPQ_CUDA(cudaEventSynchronize(ev[6]));
+    if (stager)
+    {
+        stager->waitDrained(nChunks - 1);   // the drain threads take the chunks in order: the last one out means all are out
+        stager.reset();
+    }
     unsigned tf[2] = {};
     CPQ_CUDA(cudaMemcpy(tf, ticketFault.p, sizeof(tf), cudaMemcpyDeviceToHost));
     cudaEventElapsedTime(&timings.total_ms, ev[0], ev[6]);

@@ -1436,9 +1436,10 @@ __global__ void limiter_kernel(LimiterArgs a)
 template <bool TO_DOUBLE>
 __global__ void convert_kernel(float* __restrict__ f, double* __restrict__ d, int64_t dStride, int64_t T)
 {
-    float2* f2 = reinterpret_cast<float2*>(f + (size_t) blockIdx.y * T);
+    // pairs: float rows have the pitch T rounded up to even, so an odd T carries one pad sample through like the double rows do
+    float2* f2 = reinterpret_cast<float2*>(f + (size_t) blockIdx.y * ((T + 1) & ~(int64_t) 1));
     double2* d2 = reinterpret_cast<double2*>(d + (size_t) blockIdx.y * dStride);
-    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < T / 2; i += (int64_t) gridDim.x * blockDim.x)
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < (T + 1) / 2; i += (int64_t) gridDim.x * blockDim.x)
     {
         if (TO_DOUBLE)
         {
@@ -1571,7 +1572,7 @@ __global__ void ms_kernel(MsArgs a)
     double2* R = reinterpret_cast<double2*>(a.io + (size_t) (2 * st + 1) * a.ioStride);
     double2* M = reinterpret_cast<double2*>(a.ms + (size_t) (2 * blockIdx.y) * a.ioStride);
     double2* S = reinterpret_cast<double2*>(a.ms + (size_t) (2 * blockIdx.y + 1) * a.ioStride);
-    const int64_t n2 = a.T / 2;
+    const int64_t n2 = (a.T + 1) / 2;   // an odd T takes the row's pad sample along
     for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t) gridDim.x * blockDim.x)
     {
         if (MODE == 0 || MODE == 2)
@@ -1725,7 +1726,7 @@ __global__ void __launch_bounds__(32) dither_kernel(DitherArgs a)
         double* sig = dthSmem + (size_t) buf * kDthBufDoubles;
         double* uni = sig + 32 * kDthRow;
         const int64_t t0 = tile * kDthTile;
-        const int n = (int) (a.T - t0 < (int64_t) kDthTile ? a.T - t0 : (int64_t) kDthTile);      // even (T is even)
+        const int n = (int) (a.T - t0 < (int64_t) kDthTile ? a.T - t0 : (int64_t) kDthTile);
         // signal: n/2 16-byte pieces per row, 32 / kSigPieces rows per step
         constexpr int rowsPerStep = 32 / kSigPieces;
         const int rr = lane / kSigPieces, pc = lane % kSigPieces;

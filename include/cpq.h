@@ -334,7 +334,8 @@ cpq_status cpq_process(cpq_handle h, double* const* planar, int64_t T, unsigned 
  * input transform that follows the cast in the reference. */
 cpq_status cpq_process_f32(cpq_handle h, float* const* planar, int64_t T, unsigned stages);
 
-/* Same, data already resident: d_io is a device pointer to [n_streams*n_channels][stride] doubles. */
+/* Same, data already resident: d_io is a device pointer to [n_streams*n_channels][stride] doubles; stride even (rows are
+ * 16-byte aligned) and >= T, i.e. >= T + 1 when T is odd (441-sample hosts): the pad sample of a row may be overwritten. */
 cpq_status cpq_process_device(cpq_handle h, double* d_io, int64_t stride, int64_t T, unsigned stages);
 
 /* Partition-range sharding for very long IRs (cfg 5): only layers/partitions in

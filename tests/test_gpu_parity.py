@@ -210,6 +210,33 @@ def test_non_power_of_two_host_block(checker, block, ir_len, T, kw):
         assert np.abs(want).max() > 1e-3
 
 
+@pytest.mark.parametrize("n_callbacks,f32", [(1, False), (101, False), (37, True)])
+def test_odd_number_of_samples_per_call(checker, n_callbacks, f32):
+    """A 441-sample host may hand over an odd number of samples (one callback, 101 callbacks): rows keep their 16-byte alignment
+    through an even pitch and the paired accesses take the pad sample along.  Conv -> EQ (AGC) -> epilogue; FP64 and FP32 host
+    buffers."""
+    block, T, sr = 441, 441 * n_callbacks, 48000.0
+    irs = [signals.synth_ir(9000, 910 + ch) for ch in range(2)]
+    x = np.stack([signals.noise(T, 912 + ch, 0.3) for ch in range(2)])
+    p = signals.band_params(913)
+    eng = ConvoPeqEngine(1, 2, sr, block, T, conv_boundary=capi.CONV_OUTER)
+    for ch in range(2):
+        eng.set_impulse(0, ch, irs[ch], 1.0, capi.default_filter_spec())
+    eng.set_eq(0, signals.to_band(p), agc=True)
+    eng.set_epilogue(1.1, 0)
+    if f32:
+        y32 = x.astype(np.float32)
+        xin = y32.astype(np.float64)
+        eng.process_f32(y32, capi.STAGE_ALL)
+        y, tol = y32.astype(np.float64), 1e-6
+    else:
+        xin, y, tol = x, x.copy(), TOL
+        eng.process(y, capi.STAGE_ALL)
+    eng.close()
+    want = checker.chain_run((irs[0], irs[1]), signals.to_eqband(p), xin, sr, block, OFilterSpec(), makeup=1.1, agc=True, known_block=512)
+    assert np.isfinite(y).all() and np.abs(y - want).max() <= tol
+
+
 @pytest.mark.parametrize("block", [480, 441])
 @pytest.mark.parametrize("agc", [False, True])
 def test_non_power_of_two_host_block_full_chain(checker, agc, block):
@@ -559,10 +586,6 @@ def test_error_paths_fail_loudly():
     with pytest.raises(capi.CpqError) as e:
         ConvoPeqEngine(1, 2, 44100.0, 32, 4096)          # host blocks below 64 (or above 8192) are outside the path
     assert e.value.status == capi.ERR_UNSUPPORTED
-    odd = ConvoPeqEngine(1, 2, 44100.0, 441, 4410)
-    with pytest.raises(capi.CpqError):
-        odd.process(np.zeros((2, 441)), capi.STAGE_EQ)   # an odd number of samples per call
-    odd.close()
     bands = signals.to_band(signals.band_params(1, modes=[3] * 20))
     mono = ConvoPeqEngine(1, 1, 48000.0, 512, 4096)
     with pytest.raises(capi.CpqError) as e:
