@@ -324,7 +324,7 @@ struct Engine
     std::vector<EqSet> eqSets;
     bool eqDirty = true;
     DevBuf<double> eqc, satDev, gainConst, gainTab, stateOut;
-    DevBuf<unsigned> bandMask;
+    DevBuf<unsigned> bandMask, scalarMask;
     DevBuf<int> setOfSeq;
     int64_t gainTabCallbacks = -1;
     bool haveGainTab = false;
@@ -1203,7 +1203,7 @@ cpq_status Engine::uploadEq(int64_t nCallbacks)
             sat[s] = eqSets[s].saturation;
             gc[s] = eqSets[s].totalGain;
         }
-        std::vector<unsigned> mask((size_t) nSeq);
+        std::vector<unsigned> mask((size_t) nSeq), scalar((size_t) nSeq);
         std::vector<int> sos((size_t) nSeq);
         anyPar = anyAgc = anyMs = false;
         msSplitMask = 0;
@@ -1226,6 +1226,8 @@ cpq_status Engine::uploadEq(int64_t nCallbacks)
                 // Processing.cpp:1239-1252: Stereo -> both; Left -> ch 0; Right -> ch 1
                 const bool on = (mode == 0) || (mode == 1 && ch == 0) || (mode == 2 && ch == 1);
                 if (on) m |= 1u << b;
+                // Stereo mode on a stereo stream is processBandStereo (SSE); everything else goes through the scalar processBand
+                if (on && (mode != 0 || cfg.n_channels < 2)) scalar[(size_t) q] |= 1u << b;
                 if (mode >= 3 && ch == 0 && e.structure != 1) msStreams[b].push_back(st);   // ascending stream order
                 if (mode >= 3 && ch == 0 && e.structure == 1 && (parMsStreams.empty() || parMsStreams.back() != st)) parMsStreams.push_back(st);
             }
@@ -1239,6 +1241,8 @@ cpq_status Engine::uploadEq(int64_t nCallbacks)
         CPQ_CUDA(satDev.ensure(nSets));
         CPQ_CUDA(gainConst.ensure(nSets));
         CPQ_CUDA(bandMask.ensure((size_t) nSeq));
+        CPQ_CUDA(scalarMask.ensure((size_t) nSeq));
+        CPQ_CUDA(cudaMemcpyAsync(scalarMask.p, scalar.data(), scalar.size() * sizeof(unsigned), cudaMemcpyHostToDevice, stream));
         CPQ_CUDA(setOfSeq.ensure((size_t) nSeq));
         CPQ_CUDA(cudaMemcpyAsync(eqc.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
         CPQ_CUDA(cudaMemcpyAsync(satDev.p, sat.data(), nSets * sizeof(double), cudaMemcpyHostToDevice, stream));
@@ -1676,6 +1680,8 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
         q.io = parMsScratch.p;
         q.nSeq = 2 * parCnt;
         q.bandMask = parMsMaskDev.p + 2 * p0;
+        q.scalarMask = nullptr;
+        q.scalarAll = (1u << CPQ_NUM_BANDS) - 1u;   // Mid / Side rows: processBand
         q.setOfSeq = parMsSetDev.p + 2 * p0;
         q.stateOut = nullptr;
         cpq_status st = launchEq(q);
@@ -1732,6 +1738,8 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
         q.io = msScratch.p;
         q.nSeq = 2 * cnt;
         q.bandMask = msMaskDev[b].p + 2 * i0;
+        q.scalarMask = nullptr;
+        q.scalarAll = (1u << CPQ_NUM_BANDS) - 1u;
         q.setOfSeq = msSetDev[b].p + 2 * i0;
         q.bandSelect = 1u << b;
         q.stateOut = nullptr;
@@ -2222,6 +2230,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             p.io = ioC;
             p.nSeq = ns;
             p.bandMask = bandMask.p + s0;
+            p.scalarMask = scalarMask.p + s0;
             p.setOfSeq = setOfSeq.p + s0;
             p.stateOut = stateOut.p + (size_t) s0 * CPQ_NUM_BANDS * 2;
             if (cont) p.stateIn = p.stateOut;
@@ -2464,6 +2473,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             e.gainTab = nullptr;
         }
         e.bandMask = bandMask.p ? bandMask.p + s0 : nullptr;
+        e.scalarMask = scalarMask.p ? scalarMask.p + s0 : nullptr;
         e.setOfSeq = setOfSeq.p ? setOfSeq.p + s0 : nullptr;   // absolute set indices
         e.stateOut = stateOut.p + (size_t) s0 * CPQ_NUM_BANDS * 2;
         e.postStateOut = postMask ? postState.p + (size_t) s0 * kEqPostStages * 2 : nullptr;
@@ -2671,8 +2681,8 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
     if (tf[1] != 0)
     {
         CPQ_CUDA(cudaMemset(ticketFault.p + 1, 0, sizeof(unsigned)));
-        setError("EQ filter state became non-finite or exceeded 1e15: the reference resets the state there "
-                 "(EQProcessor.Processing.cpp:174-175), which the blocked scan does not reproduce");
+        setError("EQ filter state became non-finite or exceeded 1e15 where the engine had not foreseen it (look-back links with a start "
+                 "state above 1e9): the reference resets the state there (EQProcessor.Processing.cpp:174-175)");
         return CPQ_ERR_UNSUPPORTED;
     }
     return CPQ_OK;

@@ -34,13 +34,17 @@
 //
 // Fast path / exact path: with |out| < 4.5 before saturation the reference's clamps and scrubs are
 // identities, so pass 2 runs without them and tracks a per-thread maximum; a flagged thread replays its block
-// from the stashed inputs with the reference's full per-sample semantics.  If a *state* leaves the
-// reference's valid range (|ic| >= 1e15 or non-finite, where the reference zeroes it, :174-175/:257-258) the
-// scan's linearity assumption is void and the kernel raises `fault`; the host reports CPQ_ERR_UNSUPPORTED.
+// from the stashed inputs with the reference's full per-sample semantics.  Where a *state* can leave the
+// reference's valid range (|ic| >= 1e15 or non-finite: the reference zeroes it and carries on, :174-175/:257-258) the
+// scan's linearity assumption is void: a warp whose segment may see such a reset for a band (non-finite or huge samples
+// in the band's input, a start state above 1e9, raw coefficient sets outside the TPT contract) runs that band over its
+// 1024 samples lane after lane with the literal recurrence, resets included, and posts the true state after the
+// segment to its successor instead of the scan's; everything downstream continues on the fast path (serialBand).
 #pragma once
 
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <type_traits>
 
 #include "../../include/cpq.h"
 
@@ -84,12 +88,18 @@ constexpr int kEqSeg = 32 * kEqL;                // 512 samples per warp segment
 constexpr int kEqPostStages = 4;                 // 0..2 OutputFilter biquads, 3 DC blocker
 constexpr int kEqStages = CPQ_NUM_BANDS + kEqPostStages;
 constexpr int kEqStageDc = CPQ_NUM_BANDS + 3;
+constexpr int kEqNoSerial = 0, kEqBailOut = 1, kEqSerial = 2;   // what a band does when a state reset is possible in its segment (bandStart)
 // shared memory: segment tiles | band constants | mailboxes st[20][8] (double2) | flags fl[20][8] (int) | ticket
 // shared memory: segment tiles | EQ band constants | mailboxes st[stage][8] (double2) | flags fl[stage][8] (int) | ticket |
 // output-stage constants (only allocated when such a stage runs)
-// mailboxes: agg[stage][8] warp aggregates + tin[stage] tile-in states (double2 each), one mbarrier per mailbox entry
+// mailboxes: agg[stage][8] warp aggregates + tin[stage] tile-in states (double2 each), one mbarrier per mailbox entry; the
+// look-back form adds endSt[stage][8], the states after segments that ran serially, with their mbarriers
 constexpr int kEqMail = kEqStages * 9;
-__host__ __device__ constexpr int eqSmemDoubles(bool lb) { return kEqCThreads * kEqPad + CPQ_NUM_BANDS * (lb ? kEqcStride : kEqcPw) + kEqMail * 2 + kEqMail + 2; }
+constexpr int kEqMailLb = kEqStages * 8;
+__host__ __device__ constexpr int eqSmemDoubles(bool lb)
+{
+    return kEqCThreads * kEqPad + CPQ_NUM_BANDS * (lb ? kEqcStride : kEqcPw) + kEqMail * 2 + kEqMail + 2 + (lb ? kEqMailLb * 3 : 0);
+}
 constexpr size_t eqSmemBytes(bool lb, bool post)
 {
     return (size_t) (eqSmemDoubles(lb) + (post ? kEqPostStages * (lb ? kEqcStride : kEqcPw) : 0)) * sizeof(double);
@@ -134,6 +144,9 @@ struct EqArgs
     int doEq;
     const double* eqc;      // [nSets][20][kEqcStride]
     const unsigned* bandMask;  // [nSeq] bit b = band b processed for this sequence
+    const unsigned* scalarMask;// nullable [nSeq] bit b = the reference runs band b of this sequence through the scalar processBand
+                               // (Left / Right / Mid / Side bands, mono streams) whose tanh returns +-1 outside +-4.5
+    unsigned scalarAll;        // the same for every sequence of the launch (Mid / Side rows)
     const int* setOfSeq;    // [nSeq]
     const double* sat;      // [nSets]
     double* stateOut;       // [nSeq][20][2] final states
@@ -226,7 +239,10 @@ __device__ __forceinline__ int eq_sidx(int t) { return t + 2 * (t / kEqL); }
 // The reference's per-sample semantics (processBandStereo, EQProcessor.Processing.cpp:191-276) over one thread's block,
 // in registers: literal recurrence, clamped tanh 27/9 with a true division, scrubs and the +-100 clamp.  Used by warps
 // in exact mode only.  Returns true if a state had to be reset (which the scan cannot represent).
-__device__ __forceinline__ bool eq_pass2_exact(double (&x)[kEqL], double& ic1, double& ic2, const double* __restrict__ bc, double sat)
+// scalarTanh: the band goes through processBand (:128-186), whose fastTanh returns +-1 outside +-4.5 (FastTanhApprox.h:101-107)
+// where the SSE form clamps its argument and evaluates (:112-119) -- the two differ by 1.6 % of `sat` beyond the threshold.
+__device__ __forceinline__ bool eq_pass2_exact(double (&x)[kEqL], double& ic1, double& ic2, const double* __restrict__ bc, double sat,
+                                               bool scalarTanh)
 {
     const double a1 = bc[0], a2 = bc[1], a3 = bc[2], m0 = bc[3], m1 = bc[4], m2 = bc[5];
     bool reset = false;
@@ -246,7 +262,13 @@ __device__ __forceinline__ bool eq_pass2_exact(double (&x)[kEqL], double& ic1, d
             double xc = (out > -4.5) ? out : -4.5;   // _mm_max_pd(x, lo): NaN -> lo
             xc = (xc < 4.5) ? xc : 4.5;
             const double x2 = xc * xc;
-            const double th = (xc * (27.0 + x2)) / fma(9.0, x2, 27.0);
+            double th = (xc * (27.0 + x2)) / fma(9.0, x2, 27.0);
+            if (scalarTanh)
+            {
+                if (out >= 4.5) th = 1.0;
+                else if (out <= -4.5) th = -1.0;
+                else if (out != out) th = out;   // neither branch taken: the polynomial of a NaN
+            }
             out = out * oneMinusSat + th * sat;
         }
         if (!eq_valid(out)) out = 0.0;
@@ -487,11 +509,15 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
     unsigned long long* mbA = reinterpret_cast<unsigned long long*>(tin + kEqStages);   // [stage][8] "aggregate posted" (one phase each)
     unsigned long long* mbT = mbA + kEqStages * 8;                                // [stage] "tile-in state posted"
     unsigned* sTicket = reinterpret_cast<unsigned*>(mbT + kEqStages);
+    double2* endSt = reinterpret_cast<double2*>(sTicket + 4);                     // look-back form: [stage][8] state after a serially run segment
+    unsigned long long* mbE = reinterpret_cast<unsigned long long*>(endSt + kEqMailLb);   // ... and "end state posted"
     double* cstPost = eq_smem + eqSmemDoubles(LB);                                   // output-stage constants (present iff postMask)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) *sTicket = atomicAdd(a.chain.ticket, 1u);
     for (int i = tid; i < kEqMail; i += kEqThreads) eq_mbar_init(mbA + i);   // mbA and mbT are contiguous
+    if (LB)
+        for (int i = tid; i < kEqMailLb; i += kEqThreads) eq_mbar_init(mbE + i);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     const unsigned ticket = *sTicket;
@@ -505,6 +531,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
     // stages this sequence runs: its active EQ bands (bits 0..19) and the enabled output stages (bits 20..23)
     const unsigned bandBits = a.doEq ? a.bandMask[seq] : 0u;   // bits 0..19 bands, bit 31 = Parallel structure
     const unsigned mask = (bandBits & ((bandBits >> 31) ? a.bandSelectPar : a.bandSelect) & ((1u << CPQ_NUM_BANDS) - 1u)) | (postMask << CPQ_NUM_BANDS);
+    const unsigned scalarBits = a.doEq ? ((a.scalarMask ? a.scalarMask[seq] : 0u) | a.scalarAll) : 0u;
     const int64_t t0 = (int64_t) run * kEqTile;
 
     if (a.doEq)
@@ -813,7 +840,32 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
         // Everything of one band up to the start state of this thread's block.  `link`: take part in the chain (wait for
         // the mailbox, post the successor's); a replayed band finds its mailbox already filled and posts nothing.
         double mid1 = 0.0, mid2 = 0.0;   // state half a block after (ic1, ic2): start of the second pass-2 chain
-        auto bandStart = [&](int b, const double* __restrict__ bc, bool link, double& ic1, double& ic2) {
+        // One band over this warp's segment the way the reference runs it, sample after sample: lane l continues from the
+        // state lane l - 1 ended with (state resets included, eq_pass2_exact).  In: (s1, s2) the state at the start of the
+        // segment; out: the state after it, (b1, b2) the state at the start of this thread's block, x the band output.
+        auto serialBand = [&](const double* __restrict__ bc, bool scalarTanh, double& s1, double& s2, double& b1, double& b2) {
+#pragma unroll 1
+            for (int l = 0; l < 32; ++l)
+            {
+                if (lane == l)
+                {
+                    b1 = s1;
+                    b2 = s2;
+                    eq_pass2_exact(x, s1, s2, bc, sat, scalarTanh);
+                }
+                s1 = __shfl_sync(0xffffffffu, s1, l);
+                s2 = __shfl_sync(0xffffffffu, s2, l);
+            }
+        };
+        // `risk`: the band's input or coefficients may drive a state out of range within this segment (warp-uniform; the same
+        // value when a band is replayed).  What happens then is the call site's `how` (a compile-time tag, so that the hot
+        // loop's instantiation carries none of the serial code): kEqNoSerial = never (output stages), kEqBailOut = return true
+        // before anything is posted (fast mode: the caller switches to exact mode and comes back), kEqSerial = run the band
+        // serially, post the true state after the segment and return true: x then already holds the band's output.
+        auto bandStart = [&](auto how, int b, const double* __restrict__ bc, bool link, double& ic1, double& ic2, bool risk) -> bool {
+            constexpr int kHow = decltype(how)::value;
+            bool serial = false;
+            if (kHow == kEqBailOut && risk) return true;
             // ---- pass 1: zero-state response of this thread's samples (four accumulation chains) ----
 #if CPQ_EQ_ILP2
             // per half block, with the same 16 weights A^(L/2-1-j) b: c = A^(L/2) lo + hi
@@ -896,11 +948,15 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
             double p1 = 0.0, p2 = 0.0;
             if (LB)
             {
+                // A segment that runs serially has no zero-state response to offer: it posts a marker, and later the state after
+                // the segment (endSt), from which its successors restart their composition.
+                serial = kHow == kEqSerial && risk;
+                const double marker = __longlong_as_double(0x7ff8c0de5e71a100ll);
                 if (link)
                 {
                     if (lane == 31)
                     {
-                        agg[b * 8 + warp] = make_double2(c1, c2);
+                        agg[b * 8 + warp] = serial ? make_double2(marker, marker) : make_double2(c1, c2);
                         eq_mbar_arrive(mbA + b * 8 + warp);   // release
                     }
                     if (warp == 0)
@@ -913,24 +969,45 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                         }
                     }
                 }
+                bool fromTile = true;
                 for (int i = 0; i < warp; ++i)
                 {
                     if (link) eq_mbar_wait(mbA + b * 8 + i);   // acquire; a replayed band finds every mailbox already filled
                     const double2 ai = agg[b * 8 + i];
-                    matvec2(bc + kEqcMw, p1, p2, ai.x, ai.y);  // Horner: zero-state response of segments 0..i at the start of segment i + 1
+                    if (__double_as_longlong(ai.x) == __double_as_longlong(marker))
+                    {
+                        if (link) eq_mbar_wait(mbE + b * 8 + i);
+                        const double2 ei = endSt[b * 8 + i];   // the state after segment i: nothing before it matters any more
+                        p1 = ei.x;
+                        p2 = ei.y;
+                        fromTile = false;
+                    }
+                    else
+                        matvec2(bc + kEqcMw, p1, p2, ai.x, ai.y);  // Horner: zero-state response of segments 0..i at the start of segment i + 1
                 }
-                if (link) eq_mbar_wait(mbT + b);
+                if (fromTile)
                 {
+                    if (link) eq_mbar_wait(mbT + b);
                     const double2 tv = tin[b];
                     double q1 = tv.x, q2 = tv.y;
                     matvec2(bc + kEqcPw + 4 * warp, q1, q2, p1, p2);   // A^(1024 w) s_tile + ...
                     p1 = q1;
                     p2 = q2;
                 }
+                double o1 = p1, o2 = p2;
+                if constexpr (kHow == kEqSerial)
+                    if (serial)
+                    {
+                        serialBand(bc, (scalarBits >> b) & 1u, o1, o2, ic1, ic2);
+                        if (link && lane == 31 && warp + 1 < kEqCWarps)
+                        {
+                            endSt[b * 8 + warp] = make_double2(o1, o2);
+                            eq_mbar_arrive(mbE + b * 8 + warp);   // release
+                        }
+                    }
                 if (link && lane == 31 && warp + 1 == kEqCWarps)
                 {
-                    double o1 = p1, o2 = p2;
-                    matvec2(bc + kEqcMw, o1, o2, c1, c2);   // state after the tile
+                    if (!serial) matvec2(bc + kEqcMw, o1, o2, c1, c2);   // state after the tile
                     if (recOut)
                         st_volatile_f64x2(recOut + b, make_double2(rec_clean(o1), rec_clean(o2)));
                     else if (fullLast)
@@ -960,10 +1037,19 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                     p1 = sv.x;
                     p2 = sv.y;
                 }
+                // the state at the start of the segment is known before anything is posted: a start state that could reach the
+                // reset threshold within the segment (transient growth of a TPT band is far below 1e6) also runs serially
+                if (kHow != kEqNoSerial)   // integer compare on the high words (1e9 = 0x41cdcd65...; NaN / Inf compare high): keeps the FP64 pipe out of the link
+                    serial = risk || max((unsigned) __double2hiint(p1) & 0x7fffffffu, (unsigned) __double2hiint(p2) & 0x7fffffffu) >= 0x41cdcd65u;
+                if (kHow == kEqBailOut && serial) return true;
+                double o1 = p1, o2 = p2;
+                if constexpr (kHow == kEqSerial)
+                {
+                    if (serial) serialBand(bc, (scalarBits >> b) & 1u, o1, o2, ic1, ic2);
+                }
+                if (!serial && lane == 31) matvec2(bc + kEqcMw, o1, o2, c1, c2);   // state after this segment
                 if (link && lane == 31)
                 {
-                    double o1 = p1, o2 = p2;
-                    matvec2(bc + kEqcMw, o1, o2, c1, c2);   // state after this segment
                     if (warp + 1 < kEqCWarps)
                     {
                         agg[b * 8 + warp + 1] = make_double2(o1, o2);
@@ -975,6 +1061,11 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                         storeFinal(b, o1, o2);
                 }
             }
+            if (kHow == kEqSerial && serial)
+            {
+                if (ownsFinal) storeFinal(b, ic1, ic2);
+                return true;
+            }
             // ---- state at the start of this thread's block: A^(L lane) s_in + e ----
             matvec2(bc + kEqcPlo + 4 * (lane & 7), p1, p2, 0.0, 0.0);    // A^(L (lane & 7)) (state at the start of this thread's block)
             matvec2(bc + kEqcPhi + 4 * (lane >> 3), p1, p2, e1, e2);     // A^(8L (lane >> 3)) ... + e
@@ -985,6 +1076,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
             mid2 = fma(mh1.x, p1, fma(mh1.y, p2, lo2));
 #endif
             if (ownsFinal) storeFinal(b, ic1, ic2);
+            return false;
         };
 
         auto preStage = [&](int b, bool& gainDone, bool& makeupDone) {
@@ -1054,6 +1146,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
 
         // ---- fast mode: bands in order until some lane leaves the regime where the reference's clamps are identities ----
         bool exactMode = a.doEq && __any_sync(0xffffffffu, hiIn >= 0x41cdcd65u);   // |x| >= 1e9 (or NaN/Inf) in the raw input
+        const bool rawBig = exactMode;   // ... which may reset the state of the band that filters it (-> serialBand)
         int linked = -1;                                                            // last band whose link this warp has served
         if (PAR && (bandBits >> 31))
         {
@@ -1071,11 +1164,12 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                 if (!first) loadBlock(dummy);
                 first = false;
                 double ic1, ic2;
-                bandStart(b, bc, true, ic1, ic2);
+                const bool ranSerial = bandStart(std::integral_constant<int, kEqSerial> {}, b, bc, true, ic1, ic2, rawBig || bc[6] != 0.0);   // every band filters the raw input
                 const double s1 = ic1, s2 = ic2;
                 unsigned hiMax = max((unsigned) __double2hiint(ic1) & 0x7fffffffu, (unsigned) __double2hiint(ic2) & 0x7fffffffu);
                 bool rare = exactMode | (hiMax >= 0x426d1a94u) | (bc[6] != 0.0);
-                if (!__any_sync(0xffffffffu, rare))
+                if (ranSerial) rare = false;
+                else if (!__any_sync(0xffffffffu, rare))
                 {
                     hiMax = 0;
                     const int kind = (int) bc[7];
@@ -1108,12 +1202,12 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
 #endif
                     rare = hiMax >= thrHi;
                 }
-                if (__any_sync(0xffffffffu, rare))
+                if (!ranSerial && __any_sync(0xffffffffu, rare))
                 {
                     loadBlock(dummy);
                     ic1 = s1;
                     ic2 = s2;
-                    if (eq_pass2_exact(x, ic1, ic2, bc, sat)) atomicExch(a.fault, 1u);
+                    if (eq_pass2_exact(x, ic1, ic2, bc, sat, (scalarBits >> b) & 1u)) atomicExch(a.fault, 1u);
                 }
 #pragma unroll
                 for (int j = 0; j < kEqL / 2; ++j)
@@ -1142,7 +1236,11 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                 if (!((mask >> b) & 1u)) continue;   // uniform per CTA
                 const double* __restrict__ bc = cst + b * kStr;
                 double ic1, ic2;
-                bandStart(b, bc, true, ic1, ic2);
+                if (bandStart(std::integral_constant<int, kEqBailOut> {}, b, bc, true, ic1, ic2, bc[6] != 0.0))
+                {
+                    exactMode = true;   // nothing of this band has been posted: exact mode replays the bands before it and runs it serially
+                    break;
+                }
                 linked = b;
                 unsigned hiMax = max((unsigned) __double2hiint(ic1) & 0x7fffffffu, (unsigned) __double2hiint(ic2) & 0x7fffffffu);
                 bool rare = (hiMax >= 0x426d1a94u) | (bc[6] != 0.0);   // |state| >= 1e12, or coefficients outside the fast path's contract
@@ -1189,13 +1287,16 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
         {
             unsigned dummy = 0;
             loadBlock(dummy);
+            bool firstBand = true;   // the band that filters the raw input
             for (int b = 0; b < CPQ_NUM_BANDS; ++b)
             {
                 if (!((mask >> b) & 1u)) continue;
                 const double* __restrict__ bc = cst + b * kStr;
                 double ic1, ic2;
-                bandStart(b, bc, b > linked, ic1, ic2);
-                if (eq_pass2_exact(x, ic1, ic2, bc, sat)) atomicExch(a.fault, 1u);
+                const bool ranSerial = bandStart(std::integral_constant<int, kEqSerial> {}, b, bc, b > linked, ic1, ic2, (rawBig && firstBand) || bc[6] != 0.0);
+                firstBand = false;
+                // a reset here was not foreseen (look-back links with a start state above 1e9): never different numbers
+                if (!ranSerial && eq_pass2_exact(x, ic1, ic2, bc, sat, (scalarBits >> b) & 1u)) atomicExch(a.fault, 1u);
             }
         }
         // ---- linear output stages (kept out of the band loop so that the hot loop's code is not disturbed) ----
@@ -1208,7 +1309,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                 const double* __restrict__ bc = cstPost + (b - CPQ_NUM_BANDS) * kStr;
                 double ic1, ic2;
                 preStage(b, gainDone, makeupDone);
-                bandStart(b, bc, true, ic1, ic2);
+                bandStart(std::integral_constant<int, kEqNoSerial> {}, b, bc, true, ic1, ic2, false);
                 postPass2(bc, ic1, ic2);
             }
         }

@@ -322,10 +322,14 @@ double cpq_equal_power_sin(double x);       /* ConvolverProcessor.Runtime.cpp:26
  * stream from a reset state.  T must be a multiple of block_size and <= max_samples.  H2D and D2H copies
  * are part of the call. */
 cpq_status cpq_process(cpq_handle h, double* const* planar, int64_t T, unsigned stages);
-/* Error exits: no copy is in flight when a process call returns, whatever the status.  The call works in place, so after an
- * error the buffers hold a mixture of input and results; in particular CPQ_ERR_UNSUPPORTED for an EQ state fault (a band
- * state reached 1e15 or went non-finite, where the reference zeroes it and carries on, EQProcessor.Processing.cpp:174-175)
- * is detected only after the output has overwritten the input. */
+/* Host buffers may be pinned (cudaHostAlloc / cudaHostRegister: the copies run at the PCIe rate) or ordinary pageable memory
+ * (rows go through pinned staging slots filled and drained by a few host threads, CPQ_STAGE_THREADS in the environment sets
+ * their number, 0 = leave it to the driver).  T may be odd (441-sample hosts).
+ * Non-finite or enormous samples: where the reference zeroes a band state that reached 1e15 or went non-finite and carries on
+ * (EQProcessor.Processing.cpp:174-175, :257-258) so does the engine -- the affected 1024-sample segment of that band runs with
+ * the literal per-sample recurrence.
+ * Error exits: no copy is in flight when a process call returns, whatever the status.  The call works in place, so after an
+ * error the buffers hold a mixture of input and results. */
 
 /* Same with FP32 host buffers, in place: the wire format of hosts that hand the application float blocks (its float path casts
  * on entry, convertFloatToDoubleHighQuality InputBitDepthTransform.h:102-121, and on exit, static_cast<float>,

@@ -604,34 +604,94 @@ def test_error_paths_fail_loudly():
     eng.close()
 
 
-def test_eq_state_overflow_is_reported():
-    """A state beyond 1e15 is zeroed by the reference (Processing.cpp:174-175); the scan cannot represent that,
-    so the engine must refuse rather than return different numbers."""
-    eng = ConvoPeqEngine(1, 2, 48000.0, 512, 4096)
-    eng.set_eq(0, signals.to_band(signals.band_params(7)))
-    x = np.zeros((2, 4096))
-    x[0, 100] = 1e200
-    with pytest.raises(capi.CpqError) as e:
-        eng.process(x, capi.STAGE_EQ)
-    assert e.value.status == capi.ERR_UNSUPPORTED
+def _poisoned(T, seed, kind):
+    """A sweep + noise with samples the reference's state guard reacts to (Processing.cpp:174-175, :257-258)."""
+    xl, xr = signals.log_sweep(T, 48000.0)
+    xl = xl + signals.noise(T, seed, 0.1)
+    xr = 0.5 * xr + signals.noise(T, seed + 1, 0.1)
+    if kind == "nan":        # non-finite samples: output 0, both states of the first band zeroed
+        xl[100], xr[5000], xl[8191], xl[8192], xr[20000] = np.nan, np.inf, -np.inf, np.nan, np.nan
+        xl[T - 3] = np.inf
+    elif kind == "huge":     # finite overflow: a state passes 1e15 and is zeroed, the other one may survive
+        xl[100], xr[777], xl[9000], xr[9001] = 1e200, -3e16, 5e15, 1e15
+        xl[T - 700] = 2e17
+    elif kind == "dense":    # one event in every 1024-sample segment of the first tiles, several in some
+        for k in range(0, min(T, 30000), 700):
+            (xl if k % 1400 == 0 else xr)[k] = np.nan if k % 2100 else 1e180
+    return xl, xr
+
+
+@pytest.mark.parametrize("kind", ["nan", "huge", "dense"])
+@pytest.mark.parametrize("structure", [0, 1])
+@pytest.mark.parametrize("n_streams", [1, 20])   # look-back links (few sequences) and chained links
+def test_eq_state_reset_matches_the_reference(checker, kind, structure, n_streams):
+    """Where the reference zeroes a runaway state and carries on, so does the engine: the affected 1024-sample segment of the
+    band runs serially with the literal recurrence and hands the true state on (serialBand); everything else stays on the
+    blocked scan.  Every stream gets its events at different positions."""
+    sr, block, T = 48000.0, 512, 8192 * 4 + 512 * 3
+    eng = ConvoPeqEngine(n_streams, 2, sr, block, T)
+    xs, ps = [], []
+    for s in range(n_streams):
+        p = signals.band_params(60 + s, stress=(s % 3 == 1), modes=[i % 3 for i in range(20)] if s % 4 == 2 else None)
+        xl, xr = _poisoned(T, 70 + 2 * s, kind)
+        xl, xr = np.roll(xl, 37 * s), np.roll(xr, 91 * s)
+        eng.set_eq(s, signals.to_band(p), 0.2, 0.0, structure, False)
+        xs += [xl, xr]
+        ps.append(p)
+    y = np.stack(xs).copy()
+    eng.process(y, capi.STAGE_EQ)
+    state = [eng.eq_state(s) for s in range(n_streams)]
     eng.close()
+    for s in range(n_streams):
+        wl, wr, wst = checker.eq_run(signals.to_eqband(ps[s]), xs[2 * s], xs[2 * s + 1], sr, block, structure=structure)
+        for got, want in ((y[2 * s], wl), (y[2 * s + 1], wr)):
+            # the Parallel structure adds the band differences to the *input*: a non-finite sample stays non-finite there
+            fin = np.isfinite(want)
+            assert (np.isfinite(got) == fin).all() and (structure == 1 or fin.all()), s
+            # after a 1e200 sample a surviving state sits just below 1e15 and takes ten thousand samples to decay: 1e-8 there
+            assert np.abs(got[fin] - want[fin]).max() <= (1e-8 if kind == "huge" else 1e-9), s
+        assert np.abs(np.asarray(state[s]).reshape(2, 20, 2) - wst).max() <= 1e-7 * max(1.0, np.abs(wst).max()), s
 
 
-def test_eq_large_signal_takes_the_exact_path(checker):
+def test_eq_state_reset_through_the_whole_chain(checker):
+    """A NaN input sample with the convolver at the inner boundary (no wet scrub): the first EQ band sees NaN for as long as a
+    partition holds the poisoned frame -- thousands of consecutive resets; chain through cpq_process with the epilogue."""
+    sr, block, T, ir_len = 48000.0, 512, 8192 * 3, 3000
+    n = 40
+    eng = ConvoPeqEngine(n, 2, sr, block, T, conv_boundary=capi.CONV_INNER)
+    x = np.stack([signals.noise(T, 800 + i, 0.3) for i in range(2 * n)])
+    irs = [signals.synth_ir(ir_len, 900 + i) for i in range(2 * n)]
+    for s in range(n):
+        x[2 * s, 1000 + 211 * s] = np.nan     # every frame it touches comes out of the convolver as NaN, in both implementations
+        for ch in range(2):
+            eng.set_impulse(s, ch, irs[2 * s + ch], 1.0, None)
+        eng.set_eq(s, signals.to_band(signals.band_params(950 + s)))
+    eng.set_epilogue(1.0, 0)
+    y = x.copy()
+    eng.process(y, capi.STAGE_ALL)
+    eng.close()
+    for s in range(0, n, 7):
+        want = checker.chain_run((irs[2 * s], irs[2 * s + 1]), signals.to_eqband(signals.band_params(950 + s)), x[2 * s:2 * s + 2], sr, block,
+                                 None, outer=False)
+        assert np.abs(y[2 * s:2 * s + 2] - want).max() <= 1e-9, s
+
+
+@pytest.mark.parametrize("modes,mono", [(None, False), ([i % 3 for i in range(20)], False), (None, True)])
+def test_eq_large_signal_takes_the_exact_path(checker, modes, mono):
     """|out| >= 4.5 before saturation: the fast pass must hand over to the exact per-sample semantics (tanh clamp,
-    +-100 clamp)."""
+    +-100 clamp).  Beyond the threshold the reference's two band functions differ: processBandStereo (Stereo bands of a stereo
+    stream) clamps the tanh argument, the scalar processBand (Left / Right bands, mono streams) returns +-1 -- both mirrored."""
     sr, block, T = 48000.0, 512, 8192
-    params = signals.band_params(7, stress=True)
+    params = signals.band_params(7, stress=True, modes=modes)
     xl, xr = signals.log_sweep(T, sr, amp=30.0)
-    eng = ConvoPeqEngine(1, 2, sr, block, T)
+    eng = ConvoPeqEngine(1, 1 if mono else 2, sr, block, T)
     eng.set_eq(0, signals.to_band(params))
-    y = np.stack([xl, xr]).copy()
+    y = (xl[None, :] if mono else np.stack([xl, xr])).copy()
     eng.process(y, capi.STAGE_EQ)
     eng.close()
-    wl, wr, _ = checker.eq_run(signals.to_eqband(params), xl, xr, sr, block)
+    wl, wr, _ = checker.eq_run(signals.to_eqband(params), xl, None if mono else xr, sr, block)
     assert np.abs(wl).max() > 4.5
-    # scalar vs SSE tanh differ for |y| >= 4.5 only in the reference's *mono* path; stereo path is what we mirror
-    assert np.abs(y[0] - wl).max() <= 1e-9 and np.abs(y[1] - wr).max() <= 1e-9
+    assert np.abs(y[0] - wl).max() <= 1e-9 and (mono or np.abs(y[1] - wr).max() <= 1e-9)
 
 
 def test_shared_ir_and_eq_across_sequence_chunks(checker):
