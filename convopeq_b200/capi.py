@@ -65,6 +65,16 @@ class Timings(C.Structure):
                 ("kernel_launches", C.c_int32), ("chunks", C.c_int32)]
 
 
+class IrFile(C.Structure):
+    _fields_ = [("channels", C.c_int32), ("bits_per_sample", C.c_int32), ("is_float", C.c_int32), ("frames", C.c_int64),
+                ("sample_rate", C.c_double)]
+
+
+class IrLoadInfo(C.Structure):
+    _fields_ = [("file_channels", C.c_int32), ("file_frames", C.c_int32), ("trimmed_frames", C.c_int32), ("target_length", C.c_int32),
+                ("peak_latency", C.c_int32), ("phase_applied", C.c_int32), ("file_sample_rate", C.c_double), ("scale_factor", C.c_double)]
+
+
 # every symbol include/cpq.h declares (tests check the library exports exactly these)
 EXPORTS = [
     "cpq_abi_version", "cpq_status_string", "cpq_last_error", "cpq_filter_spec_default", "cpq_config_default",
@@ -77,6 +87,7 @@ EXPORTS = [
     "cpq_set_convolver_bypass", "cpq_set_peak_limiter", "cpq_set_input_gain", "cpq_set_partial_sources", "cpq_set_stream_window", "cpq_ir_scale_factor", "cpq_ir_freq_peak_gain", "cpq_ir_min_phase",
     "cpq_ir_target_length", "cpq_ir_prepare", "cpq_set_dither_seed", "cpq_set_dither_uniforms_device", "cpq_set_streaming", "cpq_stream_position", "cpq_state_size", "cpq_export_state", "cpq_import_state",
     "cpq_debug_check_guards", "cpq_probe_dfma_tflops", "cpq_probe_dfma_latency",
+    "cpq_ir_decode_wav", "cpq_ir_trim_silence", "cpq_ir_mixed_phase", "cpq_load_impulse_wav",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -173,6 +184,10 @@ def load() -> C.CDLL:
     L.cpq_probe_dfma_tflops.restype = C.c_double
     L.cpq_probe_dfma_latency.argtypes = [C.c_int]
     L.cpq_probe_dfma_latency.restype = C.c_double
+    L.cpq_ir_decode_wav.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(IrFile), dp, C.c_size_t]
+    L.cpq_ir_trim_silence.argtypes = [dp, dp, C.c_int]
+    L.cpq_ir_mixed_phase.argtypes = [dp, dp, C.c_int, C.c_double, C.c_double, C.c_double, dp]
+    L.cpq_load_impulse_wav.argtypes = [vp, C.c_int, C.c_char_p, C.c_size_t, C.c_int, C.c_double, C.POINTER(FilterSpec), C.POINTER(IrLoadInfo)]
     _lib = L
     return L
 

@@ -3033,6 +3033,130 @@ int cpq_ir_peak_latency(const double* ir_l, const double* ir_r, int len)
     return std::clamp(static_cast<int>(std::floor(maxCentroid + 0.5)), 0, len - 1);
 }
 
+cpq_status cpq_ir_decode_wav(const void* bytes, size_t n, cpq_ir_file* info, double* out, size_t out_capacity)
+{
+    if (!bytes || !info) return CPQ_ERR_INVALID;
+    cpq::WavData w;
+    std::string err;
+    if (!cpq::irDecodeWav(static_cast<const uint8_t*>(bytes), n, w, err)) return CPQ_ERR_UNSUPPORTED;
+    const size_t frames = w.ch.empty() ? 0 : w.ch[0].size();
+    info->channels = w.channels;
+    info->frames = (int64_t) frames;
+    info->sample_rate = w.sampleRate;
+    info->bits_per_sample = w.bitsPerSample;
+    info->is_float = w.isFloat;
+    if (out)
+    {
+        if (out_capacity < frames * (size_t) w.channels) return CPQ_ERR_INVALID;
+        for (int c = 0; c < w.channels; ++c) std::copy(w.ch[(size_t) c].begin(), w.ch[(size_t) c].end(), out + (size_t) c * frames);
+    }
+    return CPQ_OK;
+}
+
+int cpq_ir_trim_silence(const double* ch0, const double* ch1, int n)
+{
+    return (ch0 && n > 0) ? cpq::irTrimTrailingSilence(ch0, ch1, n) : -1;
+}
+
+cpq_status cpq_ir_mixed_phase(const double* linear, const double* minimum, int len, double sample_rate, double lo_hz, double hi_hz, double* out)
+{
+    if (!linear || !minimum || !out || len <= 0) return CPQ_ERR_INVALID;
+    return cpq::irMixedPhaseFallback(linear, minimum, len, sample_rate, lo_hz, hi_hz, out) ? CPQ_OK : CPQ_ERR_UNSUPPORTED;
+}
+
+// LoaderThread::doLoadStep -> doTrimStep -> doTransformStep -> doBuildStep (convolver/ConvolverProcessor.LoaderThread.cpp:430-757)
+// for one stream, with the pieces above
+cpq_status cpq_load_impulse_wav(cpq_handle h, int stream, const void* bytes, size_t n, int phase_mode, double target_seconds,
+                                const cpq_filter_spec* spec, cpq_ir_load_info* info)
+{
+    if (!h || !bytes || phase_mode < 0 || phase_mode > 2 || !(target_seconds > 0.0)) return CPQ_ERR_INVALID;
+    Engine* e = h;
+    cpq::WavData w;
+    std::string err;
+    if (!cpq::irDecodeWav(static_cast<const uint8_t*>(bytes), n, w, err))
+    {
+        e->setError("load impulse: " + err);
+        return CPQ_ERR_UNSUPPORTED;
+    }
+    const int frames = (int) w.ch[0].size();
+    if (frames <= 0)
+    {
+        e->setError("load impulse: empty file");
+        return CPQ_ERR_INVALID;
+    }
+    const int nch = std::min(w.channels, 2);
+    const int len = cpq::irTrimTrailingSilence(w.ch[0].data(), nch > 1 ? w.ch[1].data() : nullptr, frames);
+    if (std::fabs(w.sampleRate - e->cfg.sample_rate) > 1e-6)
+    {
+        e->setError("load impulse: the file's sample rate differs from the engine's; the reference resamples with r8brain-free-src "
+                    "(third party), which this library does not contain: resample first");
+        return CPQ_ERR_UNSUPPORTED;
+    }
+    const int target = cpq::irTargetLength(w.sampleRate, target_seconds);
+    std::vector<std::vector<double>> ir((size_t) nch, std::vector<double>((size_t) target));
+    for (int c = 0; c < nch; ++c) cpq::irPrepare(w.ch[(size_t) c].data(), len, w.sampleRate, target_seconds, ir[(size_t) c].data());
+    // validateBuffer (:645-659): finite and not silent
+    auto valid = [&](const std::vector<std::vector<double>>& b) {
+        double mx = 0.0;
+        for (auto& v : b)
+            for (double x : v)
+            {
+                if (!std::isfinite(x)) return false;
+                mx = std::max(mx, std::fabs(x));
+            }
+        return mx > 1.0e-12;
+    };
+    int applied = 0;
+    if (phase_mode >= 1)
+    {
+        std::vector<std::vector<double>> mp((size_t) nch, std::vector<double>((size_t) target));
+        bool ok = true;
+        for (int c = 0; c < nch && ok; ++c) ok = cpq::irMinimumPhase(ir[(size_t) c].data(), target, mp[(size_t) c].data());
+        if (ok && valid(mp))
+        {
+            if (phase_mode == 1)
+            {
+                ir = mp;
+                applied = 1;
+            }
+            else
+            {
+                std::vector<std::vector<double>> mx((size_t) nch, std::vector<double>((size_t) target));
+                bool ok2 = true;
+                for (int c = 0; c < nch && ok2; ++c)
+                    ok2 = cpq::irMixedPhaseFallback(ir[(size_t) c].data(), mp[(size_t) c].data(), target, w.sampleRate, 200.0, 1000.0, mx[(size_t) c].data());
+                if (ok2 && valid(mx))
+                {
+                    ir = mx;
+                    applied = 2;
+                }
+            }
+        }
+    }
+    const double* chp[2] = { ir[0].data(), nch > 1 ? ir[1].data() : nullptr };
+    cpq_ir_scale sc {};
+    cpq::irScaleFactor(chp, nch, target, nullptr, 0, 0, 1.0, &sc);
+    const double scale = sc.has_scale_factor ? sc.scale_factor : 1.0;
+    const int peak = cpq_ir_peak_latency(chp[0], chp[1], target);
+    for (int c = 0; c < e->cfg.n_channels; ++c)
+    {
+        const cpq_status st = e->setImpulse(stream, c, (c == 1 && nch > 1) ? chp[1] : chp[0], target, scale, spec);
+        if (st != CPQ_OK) return st;
+    }
+    if (info)
+    {
+        info->file_channels = w.channels;
+        info->file_frames = frames;
+        info->file_sample_rate = w.sampleRate;
+        info->trimmed_frames = len;
+        info->target_length = target;
+        info->peak_latency = peak;
+        info->scale_factor = scale;
+        info->phase_applied = applied;
+    }
+    return CPQ_OK;
+}
+
 cpq_status cpq_set_conv_input_trim(cpq_handle h, double gain)
 {
     if (!h || !std::isfinite(gain)) return CPQ_ERR_INVALID;

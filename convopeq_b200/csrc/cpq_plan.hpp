@@ -20,6 +20,7 @@
 #include <cctype>
 #include <complex>
 #include <cstdlib>
+#include <cstring>
 #include <limits>
 #include <string>
 #include <vector>
@@ -657,6 +658,196 @@ inline bool irMinimumPhase(const double* ir, int len, double* out)
         out[i] = v;
     }
     return true;
+}
+
+// convertToMixedPhaseFallback ("Phase 1"), convolver/ConvolverProcessor.MixedPhase.cpp:721-865: the magnitude of the linear-phase
+// IR with a phase that follows the minimum-phase IR below loHz, a pure delay (the linear IR's peak) above hiHz and a raised-cosine
+// blend between -- one complex FFT of nextPow2(len) points per channel.  The reference's first choice, an optimised all-pass
+// cascade with a disk cache (:68-719), is a design tool and is not restated.  Returns false where the reference returns empty.
+inline bool irMixedPhaseFallback(const double* lin, const double* minp, int len, double sr, double loHz, double hiHz, double* out)
+{
+    if (!lin || !minp || !out || len <= 0 || !(sr > 0.0) || !(hiHz > loHz)) return false;
+    size_t n = 1;
+    while (n < (size_t) len) n <<= 1;
+    if (n > 8388608) return false;   // MAX_MIXED_FFT_SIZE
+    const size_t half = n / 2, nc = half + 1;
+    std::vector<std::complex<double>> tw(std::max<size_t>(n / 2, 1)), zl(n), zm(n);
+    for (size_t k = 0; k < tw.size(); ++k) tw[k] = std::polar(1.0, -2.0 * kPi * (double) k / (double) n);
+    int peakDelay = 0;
+    double maxVal = 0.0;
+    for (int i = 0; i < len; ++i)
+        if (std::fabs(lin[i]) > maxVal)
+        {
+            maxVal = std::fabs(lin[i]);
+            peakDelay = i;
+        }
+    for (size_t i = 0; i < n; ++i)
+    {
+        zl[i] = i < (size_t) len ? lin[i] : 0.0;
+        zm[i] = i < (size_t) len ? minp[i] : 0.0;
+    }
+    hostFft(zl, tw, -1);
+    hostFft(zm, tw, -1);
+    std::vector<double> dphi(nc);
+    const double invSpan = 1.0 / (hiHz - loHz);
+    for (size_t k = 0; k < nc; ++k)
+    {
+        const double freq = ((double) k * sr) / (double) n;
+        double wMin = 1.0;
+        if (freq >= hiHz) wMin = 0.0;
+        else if (freq > loHz) wMin = 0.5 * (1.0 + std::cos(kPi * ((freq - loHz) * invSpan)));
+        const double wLin = 1.0 - wMin;
+        const double phiLin = -(2.0 * kPi * (double) k / (double) n) * (double) peakDelay;
+        const double phiMin = std::atan2(zm[k].imag(), zm[k].real());
+        dphi[k] = (wLin * phiLin + wMin * phiMin) - phiLin;
+    }
+    // unwrapPhaseRadians, ConvolverProcessor.Internal.h:33-46, as written: the step is taken against the already corrected neighbour
+    double correction = 0.0;
+    for (size_t i = 1; i < nc; ++i)
+    {
+        const double delta = dphi[i] - dphi[i - 1];
+        if (delta > kPi) correction -= 2.0 * kPi;
+        else if (delta < -kPi) correction += 2.0 * kPi;
+        dphi[i] += correction;
+    }
+    for (size_t k = 0; k < n; ++k)
+    {
+        const double d = k <= half ? dphi[k] : -dphi[n - k];
+        const double re = zl[k].real(), im = zl[k].imag(), c = std::cos(d), sn = std::sin(d);
+        zl[k] = std::complex<double>(re * c - im * sn, re * sn + im * c);
+    }
+    hostFft(zl, tw, +1);
+    const double inv = 1.0 / (double) n;
+    for (int i = 0; i < len; ++i)
+    {
+        const double v = zl[(size_t) i].real() * inv;
+        out[i] = std::fabs(v) < 1.0e-18 ? 0.0 : v;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// IR file decode.  The reference reads IR files through JUCE (juce::AudioFormatManager::registerBasicFormats ->
+// WavAudioFormat, convolver/ConvolverProcessor.LoaderThread.cpp:439-486; JUCE is an external dependency that is not part of
+// the reference tree): the reader delivers 32-bit floats -- integer PCM is left-justified to 32 bits and multiplied by
+// 1.0f / 0x7fffffff (= 2^-31 in float), IEEE samples are narrowed to float -- which convertFloatToDoubleHighQuality
+// (InputBitDepthTransform.h:102-121) widens and passes through the input transform (NaN / |v| < 1e-20 -> 0, clamp to
+// [-1, 1]).  Restated for RIFF/WAVE PCM 8/16/24/32, IEEE float 32/64 and WAVE_FORMAT_EXTENSIBLE with those sub-formats.
+// ------------------------------------------------------------------------------------------------
+struct WavData
+{
+    int channels = 0;
+    double sampleRate = 0.0;
+    int bitsPerSample = 0, isFloat = 0;
+    std::vector<std::vector<double>> ch;   // [channels][frames]
+};
+
+// applyHighQuality64BitTransform with gain 1 (InputBitDepthTransform.h:86-100): the four-wide body lets +-Inf through to the clamp,
+// the scalar remainder (n % 4 samples) zeroes it -- the same rule as input_kernel
+inline void irInputTransform(double* d, int n)
+{
+    const int vecEnd = n / 4 * 4;
+    for (int i = 0; i < n; ++i)
+    {
+        double v = d[i];
+        if (v != v || std::fabs(v) < 1.0e-20 || (i >= vecEnd && std::isinf(v))) v = 0.0;
+        d[i] = std::min(std::max(v, -1.0), 1.0);
+    }
+}
+
+inline bool irDecodeWav(const uint8_t* b, size_t n, WavData& out, std::string& err)
+{
+    auto u16 = [&](size_t o) { return (uint32_t) b[o] | ((uint32_t) b[o + 1] << 8); };
+    auto u32 = [&](size_t o) { return (uint32_t) b[o] | ((uint32_t) b[o + 1] << 8) | ((uint32_t) b[o + 2] << 16) | ((uint32_t) b[o + 3] << 24); };
+    if (n < 12 || std::memcmp(b, "RIFF", 4) != 0 || std::memcmp(b + 8, "WAVE", 4) != 0)
+    {
+        err = "not a RIFF/WAVE file";
+        return false;
+    }
+    int tag = 0, channels = 0, bits = 0, align = 0;
+    double rate = 0.0;
+    size_t dataOff = 0, dataLen = 0;
+    for (size_t o = 12; o + 8 <= n;)
+    {
+        const size_t len = u32(o + 4), body = o + 8;
+        if (std::memcmp(b + o, "fmt ", 4) == 0 && len >= 16 && body + 16 <= n)
+        {
+            tag = (int) u16(body);
+            channels = (int) u16(body + 2);
+            rate = (double) u32(body + 4);
+            align = (int) u16(body + 12);
+            bits = (int) u16(body + 14);
+            if (tag == 0xFFFE && len >= 26 && body + 26 <= n) tag = (int) u16(body + 24);   // WAVE_FORMAT_EXTENSIBLE: first word of the sub-format GUID
+        }
+        else if (std::memcmp(b + o, "data", 4) == 0)
+        {
+            dataOff = body;
+            dataLen = std::min(len, n - body);
+            break;
+        }
+        o = body + len + (len & 1);
+    }
+    const bool isFloat = tag == 3;
+    if ((tag != 1 && tag != 3) || channels <= 0 || rate <= 0.0 || dataOff == 0 ||
+        !(isFloat ? (bits == 32 || bits == 64) : (bits == 8 || bits == 16 || bits == 24 || bits == 32)))
+    {
+        err = "unsupported WAVE format (PCM 8/16/24/32 and IEEE float 32/64 are read)";
+        return false;
+    }
+    const int bytes = bits / 8;
+    if (align < bytes * channels) align = bytes * channels;
+    const size_t frames = dataLen / (size_t) align;
+    out.channels = channels;
+    out.sampleRate = rate;
+    out.bitsPerSample = bits;
+    out.isFloat = isFloat ? 1 : 0;
+    out.ch.assign((size_t) channels, std::vector<double>(frames));
+    const float kFixed = 1.0f / (float) 0x7fffffff;
+    for (size_t f = 0; f < frames; ++f)
+        for (int c = 0; c < channels; ++c)
+        {
+            const uint8_t* p = b + dataOff + f * (size_t) align + (size_t) c * bytes;
+            float v;
+            if (isFloat && bits == 32)
+            {
+                uint32_t w = (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24);
+                std::memcpy(&v, &w, 4);
+            }
+            else if (isFloat)
+            {
+                uint64_t w = 0;
+                for (int i = 7; i >= 0; --i) w = (w << 8) | p[i];
+                double d;
+                std::memcpy(&d, &w, 8);
+                v = (float) d;
+            }
+            else
+            {
+                int32_t s;
+                if (bits == 8) s = (int32_t) (((uint32_t) p[0] - 128u) << 24);
+                else if (bits == 16) s = (int32_t) (((uint32_t) p[0] << 16) | ((uint32_t) p[1] << 24));
+                else if (bits == 24) s = (int32_t) (((uint32_t) p[0] << 8) | ((uint32_t) p[1] << 16) | ((uint32_t) p[2] << 24));
+                else s = (int32_t) ((uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24));
+                v = (float) s * kFixed;
+            }
+            out.ch[(size_t) c][f] = (double) v;
+        }
+    for (auto& v : out.ch) irInputTransform(v.data(), (int) v.size());
+    return true;
+}
+
+// doTrimStep's trailing-silence trim (LoaderThread.cpp:496-547): the length up to the last sample above 1e-15 in either of the
+// first two channels, at least 1
+inline int irTrimTrailingSilence(const double* ch0, const double* ch1, int n)
+{
+    int len = 0;
+    for (int j = n - 1; j >= 0; --j)
+        if (std::fabs(ch0[j]) > 1.0e-15 || (ch1 && std::fabs(ch1[j]) > 1.0e-15))
+        {
+            len = j + 1;
+            break;
+        }
+    return std::max(1, len);
 }
 
 inline void irPeakAndRms(const double* const* ch, int nch, int len, double scale, double& peak, double& rms)

@@ -208,6 +208,14 @@ class ConvoPeqEngine:
         """Output DC blocker (AudioEngine.h:643-651 uses 3 Hz) and the scrub + +-kOutputHeadroom clamp of processOutputDouble."""
         self._check(self.lib.cpq_set_output_stage(self.h, dc_cutoff_hz, int(hard_clamp)))
 
+    def load_impulse_wav(self, stream: int, data: bytes, phase_mode: int = 0, target_seconds: float = 1.0, spec=None) -> capi.IrLoadInfo:
+        """ConvolverProcessor::loadImpulseResponse for one stream from the bytes of a WAV file at the engine's rate: decode, trim,
+        DC blocker / window / target length, phase mode (0 as is, 1 minimum, 2 mixed), scale factor, peak latency, SetImpulse."""
+        info = capi.IrLoadInfo()
+        self._check(self.lib.cpq_load_impulse_wav(self.h, stream, data, len(data), phase_mode, target_seconds,
+                                                  C.byref(spec) if spec is not None else None, C.byref(info)))
+        return info
+
     def process(self, x: np.ndarray, stages: int = capi.STAGE_ALL) -> np.ndarray:
         """In place on a host array [n_seq, T] (rows = stream*n_channels + ch). H2D/D2H inside."""
         assert x.dtype == np.float64 and x.ndim == 2 and x.shape[0] == self.n_seq and x.flags["C_CONTIGUOUS"]
@@ -334,6 +342,40 @@ def ir_min_phase(ir: np.ndarray) -> Optional[np.ndarray]:
         return None
     if st != capi.OK:
         raise capi.CpqError(st, "cpq_ir_min_phase")
+    return out
+
+
+def ir_decode_wav(data: bytes):
+    """The reference's IR file decode (JUCE WavAudioFormat through float, then the input transform) -> (array [channels, frames],
+    sample_rate, bits_per_sample, is_float)."""
+    lib = capi.load()
+    info = capi.IrFile()
+    st = lib.cpq_ir_decode_wav(data, len(data), C.byref(info), None, 0)
+    if st != capi.OK:
+        raise capi.CpqError(st, "cpq_ir_decode_wav")
+    out = np.zeros((info.channels, info.frames))
+    st = lib.cpq_ir_decode_wav(data, len(data), C.byref(info), out.ctypes.data_as(_dp), out.size)
+    if st != capi.OK:
+        raise capi.CpqError(st, "cpq_ir_decode_wav")
+    return out, float(info.sample_rate), int(info.bits_per_sample), bool(info.is_float)
+
+
+def ir_trim_silence(ch0: np.ndarray, ch1: Optional[np.ndarray] = None) -> int:
+    a = np.ascontiguousarray(ch0, dtype=np.float64)
+    b = None if ch1 is None else np.ascontiguousarray(ch1, dtype=np.float64)
+    return int(capi.load().cpq_ir_trim_silence(a.ctypes.data_as(_dp), b.ctypes.data_as(_dp) if b is not None else None, a.size))
+
+
+def ir_mixed_phase(linear: np.ndarray, minimum: np.ndarray, sample_rate: float, lo_hz: float = 200.0, hi_hz: float = 1000.0):
+    """convertToMixedPhaseFallback for one channel (host-only); None where the reference returns an empty buffer."""
+    a = np.ascontiguousarray(linear, dtype=np.float64)
+    b = np.ascontiguousarray(minimum, dtype=np.float64)
+    out = np.zeros_like(a)
+    st = capi.load().cpq_ir_mixed_phase(a.ctypes.data_as(_dp), b.ctypes.data_as(_dp), a.size, sample_rate, lo_hz, hi_hz, out.ctypes.data_as(_dp))
+    if st == capi.ERR_UNSUPPORTED:
+        return None
+    if st != capi.OK:
+        raise capi.CpqError(st, "cpq_ir_mixed_phase")
     return out
 
 

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CPQ_ABI_VERSION 4
+#define CPQ_ABI_VERSION 5
 #define CPQ_NUM_BANDS 20        /* EQProcessor::NUM_BANDS, eqprocessor/EQProcessor.h:153 */
 #define CPQ_MAX_LAYERS 3        /* MKLNonUniformConvolver::kNumLayers, MKLNonUniformConvolver.h:391 */
 #define CPQ_NS_ORDER 12         /* PsychoacousticDither::NS_ORDER, PsychoacousticDither.h:60 */
@@ -290,6 +290,45 @@ cpq_status cpq_ir_min_phase(const double* ir, int len, double* out);
  * is not part of this library: resample first. */
 int cpq_ir_target_length(double sample_rate, double target_seconds);
 int cpq_ir_prepare(const double* ir, int len, double sample_rate, double target_seconds, double* out, int out_capacity);
+/* Host-only: the IR file decode of LoaderThread::doLoadStep (convolver/ConvolverProcessor.LoaderThread.cpp:439-486).  The
+ * reference reads through JUCE's WavAudioFormat (external, not in the reference tree: restated, parity unpinned): 32-bit float
+ * samples -- integer PCM left-justified to 32 bits times 1.0f / 0x7fffffff, IEEE samples narrowed to float -- widened to double
+ * and passed through the input transform (NaN / |v| < 1e-20 -> 0, clamp to [-1, 1], InputBitDepthTransform.h:86-121).  RIFF/WAVE
+ * PCM 8/16/24/32 and IEEE float 32/64 (also as WAVE_FORMAT_EXTENSIBLE); anything else is CPQ_ERR_UNSUPPORTED.  `out` (nullable)
+ * receives [channels][frames] doubles; call once with out = NULL for the sizes. */
+typedef struct cpq_ir_file
+{
+    int32_t channels;
+    int32_t bits_per_sample;
+    int32_t is_float;
+    int64_t frames;
+    double sample_rate;
+} cpq_ir_file;
+cpq_status cpq_ir_decode_wav(const void* bytes, size_t n, cpq_ir_file* info, double* out, size_t out_capacity);
+/* Host-only: doTrimStep's trailing-silence trim (:496-547): samples up to the last one above 1e-15 in either channel (ch1
+ * nullable), at least 1. */
+int cpq_ir_trim_silence(const double* ch0, const double* ch1, int n);
+/* Host-only: convertToMixedPhaseFallback (convolver/ConvolverProcessor.MixedPhase.cpp:721-865), one channel: the linear-phase
+ * IR's magnitude with the minimum-phase IR's phase below lo_hz, the delay of the linear IR's peak above hi_hz, raised-cosine blend
+ * between (reference defaults 200 / 1000 Hz).  The reference's first choice, an optimised all-pass cascade with a disk cache
+ * (:68-719), is a design tool and is not part of this library. */
+cpq_status cpq_ir_mixed_phase(const double* linear, const double* minimum, int len, double sample_rate, double lo_hz, double hi_hz, double* out);
+/* The loader pipeline for one stream (LoaderThread::doLoadStep / doTrimStep / doTransformStep / doBuildStep, :430-757): decode,
+ * trailing-silence trim, cpq_ir_prepare per channel (target_seconds: the reference's default is 1.0), phase_mode 0 as is /
+ * 1 minimum phase / 2 mixed phase (fallback form; either is skipped like in the reference when its result is not finite or
+ * silent), cpq_ir_scale_factor, cpq_ir_peak_latency, then SetImpulse for every channel of the stream (a mono file feeds both).
+ * A file at another sample rate is CPQ_ERR_UNSUPPORTED: the reference resamples with r8brain-free-src (third party). */
+typedef struct cpq_ir_load_info
+{
+    int32_t file_channels, file_frames;
+    int32_t trimmed_frames, target_length;
+    int32_t peak_latency;        /* irLatency: the dry-path delay of cpq_set_mix */
+    int32_t phase_applied;       /* 0 / 1 / 2: what the IR went through */
+    double file_sample_rate;
+    double scale_factor;
+} cpq_ir_load_info;
+cpq_status cpq_load_impulse_wav(cpq_handle h, int stream, const void* bytes, size_t n, int phase_mode, double target_seconds,
+                                const cpq_filter_spec* spec, cpq_ir_load_info* info);
 /* Host-only: IRAnalyzer::estimateMaxFrequencyResponseGain on its own (linear gain; 1.0 for an empty IR). */
 double cpq_ir_freq_peak_gain(const double* ir_l, const double* ir_r, int len);
 /* Host-only: the three stages' normalised coefficients {b0,b1,b2,a1,a2} x 3 as OutputFilter::prepare computes them. */

@@ -113,6 +113,15 @@ public:
         return SetImpulse(stream, 0, irL, scale, filterSpec) && (cfg_.n_channels < 2 || SetImpulse(stream, 1, irR, scale, filterSpec));
     }
 
+    /// ConvolverProcessor::loadImpulseResponse (src/ConvolverProcessor.h:235) for one stream, from the bytes of a WAV file at the
+    /// engine's sample rate: the loader thread's decode / trim / window / phase mode / scale factor / peak latency steps
+    /// (convolver/ConvolverProcessor.LoaderThread.cpp:430-757), then init.  phaseMode: 0 AsIs, 1 Minimum, 2 Mixed.
+    bool loadImpulseResponse(int stream, std::span<const std::uint8_t> wavFile, int phaseMode = 0, double targetIRLengthSec = 1.0,
+                             const FilterSpec* filterSpec = nullptr, cpq_ir_load_info* info = nullptr)
+    {
+        return ok(cpq_load_impulse_wav(h_, stream, wavFile.data(), wavFile.size(), phaseMode, targetIRLengthSec, filterSpec, info));
+    }
+
     // ---- EQProcessor parameter setters (values are float like the reference's UI parameters) ----
     void setBandFrequency(int stream, int band, float f) { if (valid(stream, band)) { p(stream).bands[(size_t) band].frequency = f; dirty_ = true; } }
     void setBandGain(int stream, int band, float g) { if (valid(stream, band)) { p(stream).bands[(size_t) band].gain = g; dirty_ = true; } }

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
     for name in capi.EXPORTS:
         assert hasattr(L, name), name
-    assert L.cpq_abi_version() == 4
+    assert L.cpq_abi_version() == 5
 
 
 def test_no_cpu_fallback():
