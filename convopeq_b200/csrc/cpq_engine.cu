@@ -2555,7 +2555,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             d.finalClamp = outCfg.finalClamp ? (limiterOn ? 1 : 3) : 0;
             d.nch = cfg.n_channels;
             d.seqBase = s0;
-            dither_kernel<<<(unsigned) ((ns + 31) / 32), 32, kDitherSmemBytes, post>>>(d);
+            dither_kernel<<<(unsigned) ((ns + 31) / 32), kDitherThreads, kDitherSmemBytes, post>>>(d);
             ++launches;
             CPQ_CUDA(cudaGetLastError());
         }

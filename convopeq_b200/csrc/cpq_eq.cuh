@@ -47,6 +47,7 @@
 #include <type_traits>
 
 #include "../../include/cpq.h"
+#include "cpq_mac.cuh"   // mbarrier / bulk-copy helpers
 
 namespace cpq
 {
@@ -1747,16 +1748,22 @@ struct DitherArgs
 
 constexpr int kDthTile = 24;                 // samples per tile and sequence: a multiple of the order of the shaper, so the 12-deep error
                                              // history rotates through registers by name, two full turns per tile (no moves)
-constexpr int kDthStages = 3;                // tiles in flight: the copy of tile k + 2 is issued before tile k is computed
+constexpr int kDthStages = 4;                // tile k is computed while k + 1 .. k + 3 are in flight / being written back
 constexpr int kDthRow = kDthTile + 2;        // signal row pitch in doubles (16-byte aligned rows)
 constexpr int kDthURow = 2 * kDthTile + 2;   // uniform row pitch
 constexpr int kDthBufDoubles = 32 * kDthRow + 32 * kDthURow;
-constexpr size_t kDitherSmemBytes = (size_t) kDthStages * kDthBufDoubles * sizeof(double);
+constexpr size_t kDitherSmemBytes = (size_t) kDthStages * kDthBufDoubles * sizeof(double) + 2 * kDthStages * sizeof(uint64_t);
+constexpr int kDitherThreads = 64;           // warp 0 runs the shaper, warp 1 moves the tiles
 
 __device__ __forceinline__ void dthCpAsync16(void* smem, const void* gmem)
 {
     const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all its earlier cp.async copies have landed
+__device__ __forceinline__ void dthCpAsyncArrive(uint64_t* bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // one sample: e[] is the error history, logical z[t] = e[(t + ROT) % 12]; the new error replaces the oldest entry
@@ -1792,99 +1799,127 @@ __device__ __forceinline__ double dither_fallback_uniform(unsigned long long& x)
     return (double) (z >> 11) * (1.0 / 9007199254740992.0);
 }
 
-template <int J, bool RNG>
+template <int J>
 __device__ __forceinline__ void dither_unrolled(double* mine, const double* myU, double (&e)[12], const double (&c)[12], bool roleLeft,
-                                                double scale, double invScale, int finalClamp, unsigned long long& rs)
+                                                double scale, double invScale, int finalClamp)
 {
     if constexpr (J < kDthTile)
     {
-        double2 uu;
-        if (RNG)
-        {
-            uu.x = dither_fallback_uniform(rs);   // u1 then u2, as nextTPDF_MKL draws them (:560-572)
-            uu.y = dither_fallback_uniform(rs);
-        }
-        else
-            uu = *reinterpret_cast<const double2*>(myU + 2 * J);
+        const double2 uu = *reinterpret_cast<const double2*>(myU + 2 * J);
         mine[J] = dither_sample<(24 - J) % 12>(mine[J], uu, e, c, roleLeft, scale, invScale, finalClamp);
-        dither_unrolled<J + 1, RNG>(mine, myU, e, c, roleLeft, scale, invScale, finalClamp, rs);
+        dither_unrolled<J + 1>(mine, myU, e, c, roleLeft, scale, invScale, finalClamp);
     }
 }
 
-__global__ void __launch_bounds__(32) dither_kernel(DitherArgs a)
+__global__ void __launch_bounds__(kDitherThreads) dither_kernel(DitherArgs a)
 {
     extern __shared__ __align__(16) double dthSmem[];
-    const int lane = threadIdx.x;
+    uint64_t* full = reinterpret_cast<uint64_t*>(dthSmem + (size_t) kDthStages * kDthBufDoubles);   // "tile landed" (32 copy lanes)
+    uint64_t* done = full + kDthStages;                                                               // "tile shaped" (1 arrival)
+    const int lane = threadIdx.x & 31;
+    const bool mover = threadIdx.x >= 32;
     const int seq0 = blockIdx.x * 32;
     const int nLocal = min(32, a.nSeq - seq0);
-    const int seq = seq0 + min(lane, nLocal - 1);          // idle lanes shadow the last sequence, they never store
+    const int64_t nTiles = (a.T + kDthTile - 1) / kDthTile;
+    const bool useRng = a.uniforms == nullptr;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < kDthStages; ++i)
+        {
+            mbar_init(full + i, useRng ? 64 : 32);   // the copy lanes' asynchronous arrivals (+ their own once the drawn uniforms are stored)
+            mbar_init(done + i, 1);
+        }
+    __syncthreads();
+    auto tileSamples = [&](int64_t tile) { const int64_t r = a.T - tile * kDthTile; return (int) (r < (int64_t) kDthTile ? r : (int64_t) kDthTile); };
+
+    if (mover)
+    {
+        // ---- warp 1: tiles in (cp.async, 16-byte pieces, completion counted on the stage's mbarrier) and shaped tiles out.  With one
+        // warp doing both jobs the staging loops were more instructions than the shaper and ran in series with its dependent
+        // chain (304 cycles per sample against the chain's 190, profiles/r02d_stalls_dither_kernel.txt). ----
+        constexpr int kSigPieces = kDthTile / 2;               // 16-byte pieces per signal row
+        constexpr int rowsPerStep = 32 / kSigPieces;           // signal rows covered by one warp-wide step
+        const int rr = lane / kSigPieces, pc = lane % kSigPieces;
+        const size_t sigRowStep = (size_t) rowsPerStep * a.ioStride;
+        double* const sigBase = a.io + (size_t) (seq0 + rr) * a.ioStride + 2 * pc;                 // + tile * kDthTile, + k * sigRowStep
+        const double* const uniBase = useRng ? nullptr : a.uniforms + ((size_t) seq0 * a.T + lane) * 2;   // + tile * 2 kDthTile, + r * 2 T
+        const size_t uniRowStep = (size_t) a.T * 2;
+        // cpq_set_dither_seed: the uniforms come from the reference's fallback generator, one stream per sequence -- drawn here,
+        // a tile ahead, so that the integer work stays out of the shaper's instruction stream (277 -> 207 cycles per sample)
+        unsigned long long rs = (useRng && lane < nLocal) ? a.rng[seq0 + lane] : 0ull;
+        auto issue = [&](int64_t tile) {
+            const int buf = (int) (tile % kDthStages);
+            double* sig = dthSmem + (size_t) buf * kDthBufDoubles;
+            double* uni = sig + 32 * kDthRow;
+            const int n = tileSamples(tile);
+            if (rr < rowsPerStep && 2 * pc < n)   // an odd n (odd T) takes the row's pad sample along
+            {
+                const double* g = sigBase + tile * kDthTile;
+                double* d = sig + rr * kDthRow + 2 * pc;
+                for (int r = rr; r < nLocal; r += rowsPerStep, g += sigRowStep, d += rowsPerStep * kDthRow) dthCpAsync16(d, g);
+            }
+            if (!useRng && lane < n)
+            {
+                const double* g = uniBase + tile * (2 * kDthTile);
+                double* d = uni + 2 * lane;
+                for (int r = 0; r < nLocal; ++r, g += uniRowStep, d += kDthURow) dthCpAsync16(d, g);
+            }
+            dthCpAsyncArrive(full + buf);
+            if (useRng)
+            {
+                if (lane < nLocal)
+                {
+                    double* d = uni + lane * kDthURow;
+                    for (int i = 0; i < 2 * n; ++i) d[i] = dither_fallback_uniform(rs);   // u1 then u2, as nextTPDF_MKL draws them (:560-572)
+                }
+                mbar_arrive(full + buf);   // release: the shaper's wait sees the stores
+            }
+        };
+        for (int64_t t = 0; t < kDthStages && t < nTiles; ++t) issue(t);
+        for (int64_t tile = 0; tile < nTiles; ++tile)
+        {
+            const int buf = (int) (tile % kDthStages);
+            mbar_wait(done + buf, (unsigned) ((tile / kDthStages) & 1));
+            const int n = tileSamples(tile);
+            if (rr < rowsPerStep && 2 * pc < n)
+            {
+                const double* sSrc = dthSmem + (size_t) buf * kDthBufDoubles + rr * kDthRow + 2 * pc;
+                double* g = sigBase + tile * kDthTile;
+                for (int r = rr; r < nLocal; r += rowsPerStep, g += sigRowStep, sSrc += rowsPerStep * kDthRow)
+                    *reinterpret_cast<double2*>(g) = *reinterpret_cast<const double2*>(sSrc);
+            }
+            __syncwarp();   // every lane has read its pieces before the stage is refilled
+            if (tile + kDthStages < nTiles) issue(tile + kDthStages);
+        }
+        if (useRng && lane < nLocal) a.rng[seq0 + lane] = rs;
+        return;
+    }
+
+    // ---- warp 0: the shaper, one lane per sequence ----
+    const int seq = seq0 + min(lane, nLocal - 1);          // idle lanes shadow the last sequence, they never write
     const bool live = lane < nLocal;
     const bool roleLeft = a.nch == 2 && ((a.seqBase + seq) % 2) == 0;
-    const int64_t nTiles = (a.T + kDthTile - 1) / kDthTile;
-    constexpr int kSigPieces = kDthTile / 2;               // 16-byte pieces per signal row
-
-    auto issue = [&](int64_t tile, int buf) {
-        double* sig = dthSmem + (size_t) buf * kDthBufDoubles;
-        double* uni = sig + 32 * kDthRow;
-        const int64_t t0 = tile * kDthTile;
-        const int n = (int) (a.T - t0 < (int64_t) kDthTile ? a.T - t0 : (int64_t) kDthTile);
-        // signal: n/2 16-byte pieces per row, 32 / kSigPieces rows per step
-        constexpr int rowsPerStep = 32 / kSigPieces;
-        const int rr = lane / kSigPieces, pc = lane % kSigPieces;
-        if (rr < rowsPerStep)
-            for (int r = rr; r < nLocal; r += rowsPerStep)
-                if (2 * pc < n) dthCpAsync16(sig + r * kDthRow + 2 * pc, a.io + (size_t) (seq0 + r) * a.ioStride + t0 + 2 * pc);
-        // uniforms: n 16-byte pieces per row (u1, u2 of one sample): one row per step
-        if (a.uniforms)
-            for (int r = 0; r < nLocal; ++r)
-                if (lane < n) dthCpAsync16(uni + r * kDthURow + 2 * lane, a.uniforms + ((size_t) (seq0 + r) * a.T + t0 + lane) * 2);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
     double e[12];   // e[t] = logical z[t] between tiles
 #pragma unroll
     for (int i = 0; i < 12; ++i) e[i] = a.z[(size_t) seq * 12 + i];
     double c[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) c[i] = a.coeff[i];
-    const bool useRng = a.uniforms == nullptr;
-    unsigned long long rs = useRng ? a.rng[seq] : 0ull;
-
-    issue(0, 0);
-    if (nTiles > 1) issue(1, 1);
-    else asm volatile("cp.async.commit_group;" ::: "memory");
     for (int64_t tile = 0; tile < nTiles; ++tile)
     {
         const int buf = (int) (tile % kDthStages);
-        // the buffer of tile + 2 held tile - 1, whose write-back ended with a __syncwarp
-        if (tile + 2 < nTiles) issue(tile + 2, (int) ((tile + 2) % kDthStages));
-        else asm volatile("cp.async.commit_group;" ::: "memory");   // keep one group per iteration so that wait_group 2 means "tile landed"
-        asm volatile("cp.async.wait_group 2;" ::: "memory");
-        __syncwarp();
+        mbar_wait(full + buf, (unsigned) ((tile / kDthStages) & 1));
         double* sig = dthSmem + (size_t) buf * kDthBufDoubles;
         const double* uni = sig + 32 * kDthRow;
-        const int64_t t0 = tile * kDthTile;
-        const int n = (int) (a.T - t0 < (int64_t) kDthTile ? a.T - t0 : (int64_t) kDthTile);
+        const int n = tileSamples(tile);
         double* mine = sig + lane * kDthRow;
         const double* myU = uni + lane * kDthURow;
         if (live)
         {
-            if (n == kDthTile)
-            {
-                if (useRng) dither_unrolled<0, true>(mine, myU, e, c, roleLeft, a.scale, a.invScale, a.finalClamp, rs);
-                else dither_unrolled<0, false>(mine, myU, e, c, roleLeft, a.scale, a.invScale, a.finalClamp, rs);
-            }
+            if (n == kDthTile) dither_unrolled<0>(mine, myU, e, c, roleLeft, a.scale, a.invScale, a.finalClamp);
             else
                 for (int i = 0; i < n; ++i)   // last, partial tile: shift the history like the reference does
                 {
-                    double2 uu;
-                    if (useRng)
-                    {
-                        uu.x = dither_fallback_uniform(rs);
-                        uu.y = dither_fallback_uniform(rs);
-                    }
-                    else
-                        uu = *reinterpret_cast<const double2*>(myU + 2 * i);
+                    const double2 uu = *reinterpret_cast<const double2*>(myU + 2 * i);
                     mine[i] = dither_sample<0>(mine[i], uu, e, c, roleLeft, a.scale, a.invScale, a.finalClamp);
                     const double newest = e[11];
 #pragma unroll
@@ -1893,22 +1928,12 @@ __global__ void __launch_bounds__(32) dither_kernel(DitherArgs a)
                 }
         }
         __syncwarp();
-        // write the tile back: 16-byte stores, the same lane -> (row, piece) map as the signal loads
-        {
-            constexpr int rowsPerStep = 32 / kSigPieces;
-            const int rr = lane / kSigPieces, pc = lane % kSigPieces;
-            if (rr < rowsPerStep)
-                for (int r = rr; r < nLocal; r += rowsPerStep)
-                    if (2 * pc < n)
-                        *reinterpret_cast<double2*>(a.io + (size_t) (seq0 + r) * a.ioStride + t0 + 2 * pc) = *reinterpret_cast<const double2*>(sig + r * kDthRow + 2 * pc);
-        }
-        __syncwarp();   // the buffer is refilled by the issue() of the next iteration
+        if (lane == 0) mbar_arrive(done + buf);   // release: the mover's wait sees every lane's samples
     }
     if (live)
     {
 #pragma unroll
         for (int i = 0; i < 12; ++i) a.z[(size_t) seq * 12 + i] = e[i];
-        if (useRng) a.rng[seq] = rs;
     }
 }
 
