@@ -13,7 +13,9 @@
  * run here: cpqo_outer_mix (ConvolverProcessor::process' dry/wet mix), cpqo_ir_peak_latency / the arithmetic of
  * cpqo_ir_scale_factor around its pinned FFT stage (LoaderThread / IRConverter), the Tukey window and trim / fade of
  * cpqo_ir_prepare (its DC-blocker stage is pinned), cpqo_parse-free preset parsing lives in the product and is checked on the
- * reference's own fixture only, and the uniform-partition extension flag (not a reference mode at all).  The dither branch
+ * reference's own fixture only, the product's WAV decode restates JUCE's reader (not in the reference tree; checked against an
+ * independent decoder on the reference's sample files) and its mixed-phase fallback form is checked against numpy, and the
+ * uniform-partition extension flag (not a reference mode at all).  The dither branch
  * (cpqo_epilogue_ex) IS pinned, bit for bit, against PsychoacousticDither.h compiled in place.  Each says so at its definition; they restate the cited source lines only.
  *
  * Written from the reference's behaviour, one callback at a time, deliberately in the reference's
