@@ -1364,7 +1364,10 @@ cpq_status Engine::ensureStreamState()
         const LayerPlan& l = plan.layers[li];
         fdlRows[li] = l.numPartsIR - 1;
         const int cbs = (l.numPartsIR + std::max(1, l.partsPerCallback) - 1) / std::max(1, l.partsPerCallback);
-        carryFrames[li] = li == 0 ? 0 : (l.outputDelaySamples + l.partSize - 1) / l.partSize + (int) (((int64_t) cbs * B + l.partSize - 1) / l.partSize) + 2;
+        // layer 0 carries output only when the host block differs from its partition: the reference's output ring then holds up
+        // to one partition plus one callback of samples Get has not read yet
+        carryFrames[li] = li == 0 ? (l.partSize != B ? 3 : 0)
+                                  : (l.outputDelaySamples + l.partSize - 1) / l.partSize + (int) (((int64_t) cbs * B + l.partSize - 1) / l.partSize) + 2;
     }
     if (!fresh) return CPQ_OK;
     CPQ_CUDA(inHist.ensure((size_t) nSeq * histLen));
@@ -1372,7 +1375,7 @@ cpq_status Engine::ensureStreamState()
     {
         const LayerPlan& l = plan.layers[li];
         CPQ_CUDA(fdl[li].ensure((size_t) nSeq * std::max(fdlRows[li], 1) * l.partSize));
-        if (li > 0) CPQ_CUDA(tailCarry[li].ensure((size_t) nSeq * carryFrames[li] * l.partSize));
+        if (carryFrames[li] > 0) CPQ_CUDA(tailCarry[li].ensure((size_t) nSeq * carryFrames[li] * l.partSize));
     }
     return resetState();
 }
@@ -1469,7 +1472,7 @@ cpq_status Engine::exportState(void* dst, size_t bytes)
     for (int li = 0; li < h.numLayers; ++li)
     {
         CPQ_CUDA(put(fdl[li].p, (size_t) nSeq * fdlRows[li] * plan.layers[li].partSize * sizeof(double2), true));
-        CPQ_CUDA(put(tailCarry[li].p, (size_t) nSeq * carryFrames[li] * plan.layers[li].partSize * sizeof(double), li > 0));
+        CPQ_CUDA(put(tailCarry[li].p, (size_t) nSeq * carryFrames[li] * plan.layers[li].partSize * sizeof(double), carryFrames[li] > 0));
     }
     CPQ_CUDA(put(stateOut.p, (size_t) nSeq * CPQ_NUM_BANDS * 2 * sizeof(double), true));
     CPQ_CUDA(put(postState.p, (size_t) nSeq * kEqPostStages * 2 * sizeof(double), postState.p != nullptr));
@@ -1518,7 +1521,7 @@ cpq_status Engine::importState(const void* src, size_t bytes)
     for (int li = 0; li < h.numLayers; ++li)
     {
         CPQ_CUDA(get(fdl[li].p, (size_t) nSeq * fdlRows[li] * plan.layers[li].partSize * sizeof(double2), true));
-        CPQ_CUDA(get(tailCarry[li].p, (size_t) nSeq * carryFrames[li] * plan.layers[li].partSize * sizeof(double), li > 0));
+        CPQ_CUDA(get(tailCarry[li].p, (size_t) nSeq * carryFrames[li] * plan.layers[li].partSize * sizeof(double), carryFrames[li] > 0));
     }
     CPQ_CUDA(get(stateOut.p, (size_t) nSeq * CPQ_NUM_BANDS * 2 * sizeof(double), true));
     if (h.hasPost) CPQ_CUDA(postState.ensure((size_t) nSeq * kEqPostStages * 2));
@@ -1951,11 +1954,11 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
     int64_t xRows[CPQ_MAX_LAYERS] = {};    // rows per sequence in the X workspace (carried FDL rows + new frames)
     if (strm)
     {
-        if (l0Ring || directHead || !fullRange || nPeers > 0 || (doEq && anyMs) || winFirst != 0 || winCount >= 0 ||
+        if (directHead || !fullRange || nPeers > 0 || (doEq && anyMs) || winFirst != 0 || winCount >= 0 ||
             (doConv && cfg.conv_boundary == CPQ_CONV_OUTER && (convBypassed || mix < 0.999)))
         {
-            setError("process: streaming continuation does not cover non-power-of-two host blocks, the direct-form head, "
-                     "partition-range sharding / stream windows, Mid/Side bands or a dry/wet mix below 1");
+            setError("process: streaming continuation does not cover the direct-form head, partition-range sharding / stream "
+                     "windows, Mid/Side bands or a dry/wet mix below 1");
             return CPQ_ERR_UNSUPPORTED;
         }
         if (doConv)
@@ -1982,7 +1985,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 K[li] = (cb0 + nCallbacks) * (int64_t) B / l.partSize - kOld[li];
                 xRows[li] = fdlRows[li] + K[li];
                 perSeq += (size_t) (xRows[li] + K[li]) * l.partSize * sizeof(double2);
-                if (li > 0) perSeq += (size_t) (carryFrames[li] + K[li]) * l.partSize * sizeof(double);
+                if (li > 0 || l0Ring) perSeq += (size_t) (carryFrames[li] + K[li]) * l.partSize * sizeof(double);
             }
             else
             {
@@ -2029,16 +2032,18 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
         // this call's slice of the gather plan, relative to the start of each layer's workspace stream
         // (= the carried samples, then the new frames): position p of the layer's output stream sits at p - base
         std::vector<int64_t> rel((size_t) nCallbacks);
-        for (int li = 1; li < plan.numLayers; ++li)
+        for (int li = l0Ring ? 0 : 1; li < plan.numLayers; ++li)
         {
             const int P = plan.layers[li].partSize;
             const int64_t base = (kOld[li] - carryFrames[li]) * (int64_t) P;
             const int64_t have = (int64_t) (carryFrames[li] + K[li]) * P;
             for (int64_t c = 0; c < nCallbacks; ++c)
             {
-                const int64_t sp = gplan.tailSrc[li][(size_t) (cb0 + c)];
+                // layer 0: the output ring's read position and count of the callback; tails: the delay line's read position
+                const int64_t sp = li == 0 ? gplan.l0Src[(size_t) (cb0 + c)] : gplan.tailSrc[li][(size_t) (cb0 + c)];
+                const int64_t cnt = li == 0 ? gplan.l0Count[(size_t) (cb0 + c)] : B;
                 rel[(size_t) c] = sp < 0 ? -1 : sp - base;
-                if (sp >= 0 && (sp - base < 0 || sp - base + B > have))
+                if (sp >= 0 && cnt > 0 && (sp - base < 0 || sp - base + cnt > have))
                 {
                     setError("process: streaming continuation: the gather plan reads outside the carried tail window");
                     return CPQ_ERR_UNSUPPORTED;
@@ -2046,6 +2051,8 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             }
             CPQ_CUDA(layer[li].tailSrc.ensure((size_t) nCallbacks));
             CPQ_CUDA(cudaMemcpyAsync(layer[li].tailSrc.p, rel.data(), (size_t) nCallbacks * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+            if (li == 0)
+                CPQ_CUDA(cudaMemcpyAsync(layer[0].l0Count.p, gplan.l0Count.data() + cb0, (size_t) nCallbacks * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
             CPQ_CUDA(cudaStreamSynchronize(stream));   // rel is reused for the next layer
         }
         gplanCallbacks = -1;   // the device copies of the plan are call-relative: rebuild before any other use
@@ -2353,7 +2360,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             auto invLayer = [&](int li, int q0, int n) -> cpq_status {
                 const LayerPlan& l = plan.layers[li];
                 const size_t tailPitch = (size_t) ((strm ? carryFrames[li] : 0) + K[li]) * l.partSize;
-                if (strm && li > 0)   // the delay line: tail samples computed by earlier calls that this call's callbacks still read
+                if (strm && carryFrames[li] > 0 && (li > 0 || l0Ring))   // the delay line / output ring: samples computed by earlier calls that this call's callbacks still read
                     CPQ_CUDA(cudaMemcpy2DAsync(layer[li].tail.p + (size_t) q0 * tailPitch, tailPitch * sizeof(double),
                                                tailCarry[li].p + (size_t) (s0 + q0) * carryFrames[li] * l.partSize, (size_t) carryFrames[li] * l.partSize * sizeof(double),
                                                (size_t) carryFrames[li] * l.partSize * sizeof(double), (size_t) n, cudaMemcpyDeviceToDevice, stream));
@@ -2365,7 +2372,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 a.totalFrames = (int64_t) n * K[li];
                 a.out = (li == 0 && !l0Ring) ? ioC + (size_t) q0 * stride : layer[li].tail.p + (size_t) q0 * tailPitch;
                 a.outStride = (li == 0 && !l0Ring) ? stride : (int64_t) tailPitch;
-                if (strm && li > 0) a.out += (size_t) carryFrames[li] * l.partSize;
+                if (strm && (li > 0 || l0Ring)) a.out += (size_t) carryFrames[li] * l.partSize;
                 a.tw = layer[li].tw.p;
                 a.ptw = layer[li].ptw.p;
                 a.scratch = layer[li].X.p + (size_t) q0 * xRows[li] * l.partSize;   // the MAC has consumed it
@@ -2455,7 +2462,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             if (l0Ring)
             {
                 e.l0 = layer[0].tail.p;
-                e.l0Stride = (int64_t) K[0] * plan.layers[0].partSize;
+                e.l0Stride = (int64_t) ((strm ? carryFrames[0] : 0) + K[0]) * plan.layers[0].partSize;
                 e.l0Src = layer[0].tailSrc.p;
                 e.l0Count = layer[0].l0Count.p;
             }
@@ -2521,7 +2528,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             if (st != CPQ_OK) return st;
         }
         if (strm && doConv && !dryOnly)
-            for (int li = 1; li < plan.numLayers; ++li)
+            for (int li = l0Ring ? 0 : 1; li < plan.numLayers; ++li)
             {
                 const LayerPlan& l = plan.layers[li];
                 if (K[li] == 0) continue;   // nothing new: the carried window is unchanged

@@ -242,8 +242,9 @@ __device__ __forceinline__ int eq_sidx(int t) { return t + 2 * (t / kEqL); }
 // in exact mode only.  Returns true if a state had to be reset (which the scan cannot represent).
 // scalarTanh: the band goes through processBand (:128-186), whose fastTanh returns +-1 outside +-4.5 (FastTanhApprox.h:101-107)
 // where the SSE form clamps its argument and evaluates (:112-119) -- the two differ by 1.6 % of `sat` beyond the threshold.
+// capAt > 0: (cap1, cap2) receive the state after capAt samples (the sequence's final state when it ends inside this block).
 __device__ __forceinline__ bool eq_pass2_exact(double (&x)[kEqL], double& ic1, double& ic2, const double* __restrict__ bc, double sat,
-                                               bool scalarTanh)
+                                               bool scalarTanh, int capAt = 0, double* cap1 = nullptr, double* cap2 = nullptr)
 {
     const double a1 = bc[0], a2 = bc[1], a3 = bc[2], m0 = bc[3], m1 = bc[4], m2 = bc[5];
     bool reset = false;
@@ -278,6 +279,11 @@ __device__ __forceinline__ bool eq_pass2_exact(double (&x)[kEqL], double& ic1, d
         out = (out > -100.0) ? out : -100.0;
         out = (out < 100.0) ? out : 100.0;
         x[j] = out;
+        if (j + 1 == capAt)
+        {
+            *cap1 = ic1;
+            *cap2 = ic2;
+        }
     }
     return reset;
 }
@@ -837,6 +843,42 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
         // the thread whose block starts at sample T holds the sequence's final state when the last tile is partial
         const int64_t remT = a.T - t0;
         const bool ownsFinal = remT < kEqTile && remT >= 0 && tid == (int) (remT / kEqL);
+        const int finalOff = ownsFinal ? (int) (remT % kEqL) : 0;   // T need not be a multiple of the thread block (441-sample hosts)
+        // The owner's final state: the state at the start of its block advanced over the finalOff samples the sequence still has
+        // in it (x holds the stage's *input* here; the band state does not depend on the saturated output).
+        auto storeOwned = [&](int b, const double* __restrict__ bc, double s1, double s2) {
+            if (finalOff > 0)
+            {
+                const int kind = (int) bc[7];
+#pragma unroll
+                for (int j = 0; j < kEqL - 1; ++j)
+                    if (j < finalOff)
+                    {
+                        const double v0 = x[j];
+                        if (kind == 3)        // DF2T biquad (postPass2)
+                        {
+                            const double y = fma(bc[0], v0, s1);
+                            s1 = fma(bc[1], v0, fma(-bc[3], y, s2));
+                            s2 = fma(-bc[4], y, bc[2] * v0);
+                        }
+                        else if (kind == 4)   // two one-pole sections
+                        {
+                            s1 = fma(bc[0], v0 - s1, s1);
+                            const double v = v0 - s1;
+                            s2 = fma(bc[1], v - s2, s2);
+                        }
+                        else                  // TPT SVF, literal form
+                        {
+                            const double v3 = v0 - s2;
+                            const double v1 = fma(bc[0], s1, bc[1] * v3);
+                            const double v2 = fma(bc[1], s1, fma(bc[2], v3, s2));
+                            s1 = fma(2.0, v1, -s1);
+                            s2 = fma(2.0, v2, -s2);
+                        }
+                    }
+            }
+            storeFinal(b, s1, s2);
+        };
 
         // Everything of one band up to the start state of this thread's block.  `link`: take part in the chain (wait for
         // the mailbox, post the successor's); a replayed band finds its mailbox already filled and posts nothing.
@@ -852,7 +894,8 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
                 {
                     b1 = s1;
                     b2 = s2;
-                    eq_pass2_exact(x, s1, s2, bc, sat, scalarTanh);
+                    if (ownsFinal && finalOff > 0) eq_pass2_exact(x, s1, s2, bc, sat, scalarTanh, finalOff, &b1, &b2);   // the owner keeps the state at sample T
+                    else eq_pass2_exact(x, s1, s2, bc, sat, scalarTanh);
                 }
                 s1 = __shfl_sync(0xffffffffu, s1, l);
                 s2 = __shfl_sync(0xffffffffu, s2, l);
@@ -1064,7 +1107,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
             }
             if (kHow == kEqSerial && serial)
             {
-                if (ownsFinal) storeFinal(b, ic1, ic2);
+                if (ownsFinal) storeFinal(b, ic1, ic2);   // (serialBand left the state at sample T in the owner's ic)
                 return true;
             }
             // ---- state at the start of this thread's block: A^(L lane) s_in + e ----
@@ -1076,7 +1119,7 @@ __global__ void __launch_bounds__(kEqThreads, PAR ? 1 : CPQ_EQ_MINBLOCKS) eq_ker
             mid1 = fma(mh0.x, p1, fma(mh0.y, p2, lo1));
             mid2 = fma(mh1.x, p1, fma(mh1.y, p2, lo2));
 #endif
-            if (ownsFinal) storeFinal(b, ic1, ic2);
+            if (ownsFinal) storeOwned(b, bc, ic1, ic2);
             return false;
         };
 

@@ -359,6 +359,23 @@ def test_eq_modes_batch_mixed_streams(checker):
         assert np.abs(y[2 * s:2 * s + 2] - want).max() <= TOL, s
 
 
+@pytest.mark.parametrize("block,n_cb", [(441, 3), (441, 40), (1000, 9), (100, 7)])
+def test_eq_final_state_when_the_signal_ends_inside_a_thread_block(checker, block, n_cb):
+    """The carried band state is the state after sample T - 1 also when T is not a multiple of the 32 samples a thread holds."""
+    sr, T = 44100.0, block * n_cb
+    params = signals.band_params(seed=21, types=[i % 5 for i in range(20)])
+    xl, xr = signals.log_sweep(T, sr)
+    eng = ConvoPeqEngine(1, 2, sr, block, T)
+    eng.set_eq(0, signals.to_band(params))
+    y = np.stack([xl, xr]).copy()
+    eng.process(y, capi.STAGE_EQ)
+    st = eng.eq_state(0)
+    eng.close()
+    wl, wr, wst = checker.eq_run(signals.to_eqband(params), xl, xr, sr, block)
+    assert np.abs(y[0] - wl).max() <= TOL and np.abs(y[1] - wr).max() <= TOL
+    assert np.abs(st - wst).max() <= 1e-9 * max(1.0, np.abs(wst).max())
+
+
 def test_eq_mono_stream(checker):
     sr, block, T = 48000.0, 512, 40960
     params = signals.band_params(seed=12, modes=[i % 3 for i in range(20)])

@@ -76,6 +76,47 @@ def test_segments_equal_one_shot_and_reference(checker, name, seg):
     assert np.isfinite(state2).all()
 
 
+@pytest.mark.parametrize("block,seg", [(480, 1), (480, 7), (480, 64), (441, 1), (441, 5), (1000, 3), (96, 11)])
+def test_host_blocks_that_are_not_a_power_of_two(checker, block, seg):
+    """480- / 441-sample hosts calling per callback (or a few): layer 0 then goes through the reference's output ring, whose
+    un-read samples are carried like a tail's delay line (Get's varying delivery per callback included).  441 x an odd number
+    of callbacks makes the calls odd-sized as well."""
+    sr, ir_len, n_cb = 48000.0, 65536, 130
+    T = n_cb * block
+    known = 64
+    while known < block:
+        known *= 2
+    eng, irs = _engine(sr, ir_len, T, block)
+    x = np.stack([signals.noise(T, 390 + i) for i in range(4)])
+    conv1 = x.copy()
+    eng.process(conv1, capi.STAGE_CONV)
+    full1 = x.copy()
+    eng.process(full1, capi.STAGE_ALL)
+    eng.set_streaming(True)
+    conv2 = _segmented(eng, x, seg * block, capi.STAGE_CONV)
+    assert eng.stream_position() == T
+    assert np.array_equal(conv1, conv2), np.abs(conv1 - conv2).max()
+    eng.reset()
+    full2 = _segmented(eng, x, seg * block, capi.STAGE_ALL)
+    # a third pass: half-way the stream moves to another handle
+    eng.reset()
+    half = (n_cb // 2 // seg) * seg * block      # on a segment boundary of the run above, so that the EQ's scan tiles coincide
+    a = _segmented(eng, x[:, :half], seg * block, capi.STAGE_ALL)
+    blob = eng.export_state()
+    eng.close()
+    eng2, _ = _engine(sr, ir_len, T, block)
+    eng2.set_streaming(True)
+    eng2.import_state(blob)
+    b = _segmented(eng2, x[:, half:], seg * block, capi.STAGE_ALL)
+    eng2.close()
+    assert np.abs(full1 - full2).max() <= 1e-12
+    assert np.array_equal(np.concatenate([a, b], axis=1), full2)
+    for s in range(2):
+        want = checker.chain_run((irs[2 * s], irs[2 * s + 1]), signals.to_eqband(signals.band_params(80 + s)), x[2 * s:2 * s + 2], sr, block,
+                                 OFilterSpec(sample_rate=sr), makeup=1.1, known_block=known)
+        assert np.abs(full2[2 * s:2 * s + 2] - want).max() <= TOL, s
+
+
 def test_tile_aligned_segments_are_bit_identical_for_the_whole_chain():
     """Segments of 16 callbacks = 8192 samples = one EQ scan tile: the tile grid of the segmented run coincides with the
     one-shot run's, so every stage gives the same bits."""
