@@ -337,6 +337,16 @@ struct Engine
     DevBuf<int> msStreamsDev[CPQ_NUM_BANDS], msSetDev[CPQ_NUM_BANDS];
     DevBuf<unsigned> msMaskDev[CPQ_NUM_BANDS];       // [2 * count]: bit b on the Mid row or on the Side row
     DevBuf<double> msScratch, sumsq, agcTab, agcState;
+    // streaming continuation of Mid/Side bands: EQProcessor::filterState[2] / [3] (EQProcessor.h:637) -- per band region the
+    // (Mid row, Side row) states of the streams that run the band there, in the order of msStreams[b]; region 20 = the rows of
+    // Parallel-structure streams.  Zeroed by Reset and whenever the band settings are uploaded again.
+    DevBuf<double> msState;
+    bool msImported = false;
+    // streaming continuation of the dry path (mix < 1 / bypass): the latency-compensation delay ring, ping-pong per call
+    DevBuf<double> dryHist[2];
+    int dryHistSel = 0, dryHistLen = 0;
+    double* msRegion(int b) { return msState.p + (size_t) b * 2 * cfg.n_streams * CPQ_NUM_BANDS * 2; }
+    size_t msStateCount() const { return (size_t) (CPQ_NUM_BANDS + 1) * 2 * cfg.n_streams * CPQ_NUM_BANDS * 2; }
     std::vector<int> parMsStreams;                   // sorted streams in the Parallel structure that have Mid/Side bands
     DevBuf<int> parMsStreamsDev, parMsSetDev;
     DevBuf<unsigned> parMsMaskDev;                   // [2 * count]: all Mid bands on the Mid row, all Side bands on the Side row, | 1 << 31
@@ -1308,6 +1318,9 @@ cpq_status Engine::uploadEq(int64_t nCallbacks)
             CPQ_CUDA(cudaMemcpyAsync(agcOnDev.p, on.data(), on.size(), cudaMemcpyHostToDevice, stream));
         }
         CPQ_CUDA(cudaStreamSynchronize(stream));
+        // the compact stream lists may have changed -- unless the states were just imported for exactly these settings
+        if (msState.p && !msImported) CPQ_CUDA(cudaMemsetAsync(msState.p, 0, msState.n * sizeof(double), stream));
+        msImported = false;
         eqDirty = false;
         gainTabCallbacks = -1;
     }
@@ -1395,6 +1408,9 @@ cpq_status Engine::resetState()
         CPQ_CUDA(cudaMemcpyAsync(rngState.p, rngSeedState.data(), rngSeedState.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
     CPQ_CUDA(cudaMemsetAsync(stateOut.p, 0, (size_t) nSeq * CPQ_NUM_BANDS * 2 * sizeof(double), stream));
     if (postState.p) CPQ_CUDA(cudaMemsetAsync(postState.p, 0, postState.n * sizeof(double), stream));
+    if (msState.p) CPQ_CUDA(cudaMemsetAsync(msState.p, 0, msState.n * sizeof(double), stream));
+    for (auto& d : dryHist)
+        if (d.p) CPQ_CUDA(cudaMemsetAsync(d.p, 0, d.n * sizeof(double), stream));
     CPQ_CUDA(cudaStreamSynchronize(stream));
     absCallback = 0;
     contValid = false;
@@ -1408,13 +1424,14 @@ cpq_status Engine::resetState()
 // impulses and EQ settings (the header carries the geometry to check that).
 struct StateHeader
 {
-    uint64_t magic;          // "CPQSTAT1"
+    uint64_t magic;          // "CPQSTAT2"
     int32_t nSeq, nStreams, histLen, numLayers;
     int32_t fdlRows[CPQ_MAX_LAYERS], carryFrames[CPQ_MAX_LAYERS], partSize[CPQ_MAX_LAYERS];
     int32_t contValid, hasPost, hasAgc, hasLim;
+    int32_t hasMs, dryLen;
     int64_t absCallback;
 };
-static constexpr uint64_t kStateMagic = 0x3154415453515043ull;
+static constexpr uint64_t kStateMagic = 0x3254415453515043ull;   // "CPQSTAT2"
 
 size_t Engine::stateBytes() const
 {
@@ -1432,6 +1449,8 @@ size_t Engine::stateBytes() const
     n += (size_t) cfg.n_streams * sizeof(double);                // limiter envelope
     n += (size_t) nSeq * 12 * sizeof(double);                    // dither error history
     n += (size_t) nSeq * sizeof(unsigned long long);             // dither generator state
+    n += msStateCount() * sizeof(double);                        // Mid / Side band states
+    n += (size_t) nSeq * dryHistLen * sizeof(double);            // dry path's delay ring
     return n;
 }
 
@@ -1457,6 +1476,8 @@ cpq_status Engine::exportState(void* dst, size_t bytes)
     for (int li = 0; li < h.numLayers; ++li) { h.fdlRows[li] = fdlRows[li]; h.carryFrames[li] = carryFrames[li]; h.partSize[li] = plan.layers[li].partSize; }
     h.contValid = contValid ? 1 : 0;
     h.hasPost = postState.p ? 1 : 0; h.hasAgc = agcState.p ? 1 : 0; h.hasLim = limEnv.p ? 1 : 0;
+    h.hasMs = msState.p ? 1 : 0;
+    h.dryLen = dryHistLen;
     h.absCallback = absCallback;
     char* o = static_cast<char*>(dst);
     std::memcpy(o, &h, sizeof(h));
@@ -1480,6 +1501,8 @@ cpq_status Engine::exportState(void* dst, size_t bytes)
     CPQ_CUDA(put(limEnv.p, (size_t) cfg.n_streams * sizeof(double), limEnv.p != nullptr));
     CPQ_CUDA(put(ditherZ.p, (size_t) nSeq * 12 * sizeof(double), true));
     CPQ_CUDA(put(rngState.p, (size_t) nSeq * sizeof(unsigned long long), rngState.p != nullptr));
+    CPQ_CUDA(put(msState.p, msStateCount() * sizeof(double), msState.p != nullptr));
+    CPQ_CUDA(put(dryHist[dryHistSel].p, (size_t) nSeq * dryHistLen * sizeof(double), dryHistLen > 0));
     return CPQ_OK;
 }
 
@@ -1499,7 +1522,8 @@ cpq_status Engine::importState(const void* src, size_t bytes)
         return CPQ_ERR_INVALID;
     }
     std::memcpy(&h, src, sizeof(h));
-    bool ok = h.magic == kStateMagic && h.nSeq == nSeq && h.nStreams == cfg.n_streams && h.histLen == histLen && bytes >= stateBytes() &&
+    const size_t need = stateBytes() - (size_t) nSeq * dryHistLen * sizeof(double) + (size_t) nSeq * std::max(h.dryLen, 0) * sizeof(double);
+    bool ok = h.magic == kStateMagic && h.nSeq == nSeq && h.nStreams == cfg.n_streams && h.histLen == histLen && bytes >= need &&
               h.numLayers == (histLen > 0 ? plan.numLayers : 0);
     for (int li = 0; ok && li < h.numLayers; ++li)
         ok = h.fdlRows[li] == fdlRows[li] && h.carryFrames[li] == carryFrames[li] && h.partSize[li] == plan.layers[li].partSize;
@@ -1532,6 +1556,15 @@ cpq_status Engine::importState(const void* src, size_t bytes)
     CPQ_CUDA(get(limEnv.p, (size_t) cfg.n_streams * sizeof(double), h.hasLim != 0));
     CPQ_CUDA(get(ditherZ.p, (size_t) nSeq * 12 * sizeof(double), true));
     CPQ_CUDA(get(rngState.p, (size_t) nSeq * sizeof(unsigned long long), rngState.p != nullptr));
+    if (h.hasMs) CPQ_CUDA(msState.ensure(msStateCount()));
+    CPQ_CUDA(get(msState.p, msStateCount() * sizeof(double), h.hasMs != 0));
+    if (h.dryLen > 0)
+    {
+        for (auto& d : dryHist) CPQ_CUDA(d.ensure((size_t) nSeq * h.dryLen));
+        dryHistLen = h.dryLen;
+        CPQ_CUDA(get(dryHist[dryHistSel].p, (size_t) nSeq * h.dryLen * sizeof(double), true));
+    }
+    msImported = h.hasMs != 0 && eqDirty;   // the first process call of a fresh handle uploads the band settings: keep the states
     absCallback = h.absCallback;
     contValid = h.contValid != 0;
     gplanCallbacks = -1;
@@ -1686,7 +1719,8 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
         q.scalarMask = nullptr;
         q.scalarAll = (1u << CPQ_NUM_BANDS) - 1u;   // Mid / Side rows: processBand
         q.setOfSeq = parMsSetDev.p + 2 * p0;
-        q.stateOut = nullptr;
+        q.stateOut = (streaming && msState.p) ? msRegion(CPQ_NUM_BANDS) + (size_t) 2 * p0 * CPQ_NUM_BANDS * 2 : nullptr;
+        q.stateIn = e.stateIn ? q.stateOut : nullptr;
         cpq_status st = launchEq(q);
         if (st != CPQ_OK) return st;
         ms_kernel<2><<<pg, 256, 0, stream>>>(pm);
@@ -1745,7 +1779,8 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
         q.scalarAll = (1u << CPQ_NUM_BANDS) - 1u;
         q.setOfSeq = msSetDev[b].p + 2 * i0;
         q.bandSelect = 1u << b;
-        q.stateOut = nullptr;
+        q.stateOut = (streaming && msState.p) ? msRegion(b) + (size_t) 2 * i0 * CPQ_NUM_BANDS * 2 : nullptr;
+        q.stateIn = e.stateIn ? q.stateOut : nullptr;
         st = launchEq(q);
         if (st != CPQ_OK) return st;
         ms_kernel<1><<<mg, 256, 0, stream>>>(m);
@@ -1954,11 +1989,9 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
     int64_t xRows[CPQ_MAX_LAYERS] = {};    // rows per sequence in the X workspace (carried FDL rows + new frames)
     if (strm)
     {
-        if (directHead || !fullRange || nPeers > 0 || (doEq && anyMs) || winFirst != 0 || winCount >= 0 ||
-            (doConv && cfg.conv_boundary == CPQ_CONV_OUTER && (convBypassed || mix < 0.999)))
+        if (directHead || !fullRange || nPeers > 0 || winFirst != 0 || winCount >= 0)
         {
-            setError("process: streaming continuation does not cover the direct-form head, partition-range sharding / stream "
-                     "windows, Mid/Side bands or a dry/wet mix below 1");
+            setError("process: streaming continuation does not cover the direct-form head or partition-range sharding / stream windows");
             return CPQ_ERR_UNSUPPORTED;
         }
         if (doConv)
@@ -1970,6 +2003,11 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 }
         cpq_status st = ensureStreamState();
         if (st != CPQ_OK) return st;
+        if (doEq && anyMs && !msState.p)
+        {
+            CPQ_CUDA(msState.ensure(msStateCount()));
+            CPQ_CUDA(cudaMemsetAsync(msState.p, 0, msStateCount() * sizeof(double), stream));
+        }
     }
     int chunk = nSeq;
     if (doConv)
@@ -2198,6 +2236,14 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
     // the direct-form head belongs to the rank that holds partition 0 of layer 0
     const bool direct = doConv && directHead && !dryOnly && qb[0] == 0 && qe[0] > 0;
     if (needsDry || direct) CPQ_CUDA(dryBuf.ensure((size_t) chunk * stride));
+    const bool dryCarry = strm && needsDry && dryDelay > 0;
+    if (dryCarry)
+    {
+        const bool fresh = dryHistLen != dryDelay || !dryHist[0].p;
+        for (auto& d : dryHist) CPQ_CUDA(d.ensure((size_t) this->nSeq * dryDelay));
+        dryHistLen = dryDelay;
+        if (fresh || !cont) CPQ_CUDA(cudaMemsetAsync(dryHist[dryHistSel].p, 0, (size_t) this->nSeq * dryDelay * sizeof(double), stream));
+    }
     // ProcessingOrder::EQThenConvolver (DSPCoreDouble.cpp:415-451): EQ (with its total-gain ramp) on the raw input, the
     // convolver input trim, then the convolver; the final launch then only assembles the layers and runs the output stages
     const bool eqFirst = (stages & CPQ_ORDER_EQ_THEN_CONV) && doConv && doEq;
@@ -2515,6 +2561,11 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             m.delay = dryDelay;
             m.dryGain = equalPowerSin(1.0 - mix);
             m.dryOnly = dryOnly ? 1 : 0;
+            if (dryCarry)
+            {
+                m.hist = dryHist[dryHistSel].p + (size_t) s0 * dryDelay;
+                m.histOut = dryHist[dryHistSel ^ 1].p + (size_t) s0 * dryDelay;
+            }
             mix_kernel<<<dim3((unsigned) std::min<int64_t>(256, (T + 255) / 256), (unsigned) ns), 256, 0, stream>>>(m);
             ++launches;
             CPQ_CUDA(cudaGetLastError());
@@ -2638,6 +2689,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
     {
         absCallback += nCallbacks;
         contValid = true;
+        if (dryCarry) dryHistSel ^= 1;
     }
 
     if (doDither)

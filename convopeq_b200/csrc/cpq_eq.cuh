@@ -1639,6 +1639,10 @@ struct MixArgs
     int delay;           // samples; the delay ring starts zeroed
     double dryGain;
     int dryOnly;
+    // streaming continuation: the last `delay` samples of the convolver input before this call (the delay ring's content),
+    // [nSeq][delay], and where the ring's content after this call goes (another buffer); both nullable
+    const double* hist;
+    double* histOut;
 };
 
 __global__ void mix_kernel(MixArgs a)
@@ -1647,9 +1651,15 @@ __global__ void mix_kernel(MixArgs a)
     const double* dry = a.dry + (size_t) blockIdx.y * a.stride;
     for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < a.T; i += (int64_t) gridDim.x * blockDim.x)
     {
-        const double d = i >= a.delay ? dry[i - a.delay] : 0.0;
+        const double d = i >= a.delay ? dry[i - a.delay] : (a.hist ? a.hist[(size_t) blockIdx.y * a.delay + i] : 0.0);
         io[i] = a.dryOnly ? d : __dadd_rn(io[i], __dmul_rn(d, a.dryGain));
     }
+    if (a.histOut)   // the last `delay` samples of [ring | this call's input]
+        for (int64_t j = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; j < a.delay; j += (int64_t) gridDim.x * blockDim.x)
+        {
+            const int64_t p = a.T - a.delay + j;
+            a.histOut[(size_t) blockIdx.y * a.delay + j] = p >= 0 ? dry[p] : (a.hist ? a.hist[(size_t) blockIdx.y * a.delay + a.delay + p] : 0.0);
+        }
 }
 
 // ---------------------------------------------------------------------------------------------

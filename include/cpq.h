@@ -161,7 +161,7 @@ cpq_status cpq_reset(cpq_handle h);
  * the stage states.  cpq_reset returns to the Reset state; enable = 0 (default) makes every call start from Reset again.
  * Host blocks that are not a power of two (480, 441 ...) are carried through the reference's layer-0 output ring.
  * Not covered (CPQ_ERR_UNSUPPORTED from the process call): the direct-form head, partition
- * ranges / stream windows, Mid/Side bands, a dry/wet mix below 1, plans that drop tail blocks; total-gain events scheduled
+ * ranges / stream windows, plans that drop tail blocks; total-gain events scheduled
  * with cpq_schedule_total_gain must complete their ramp inside the call they start in. */
 cpq_status cpq_set_streaming(cpq_handle h, int enable);
 int64_t cpq_stream_position(cpq_handle h);            /* samples per channel processed since Reset (streaming mode) */

@@ -117,6 +117,95 @@ def test_host_blocks_that_are_not_a_power_of_two(checker, block, seg):
         assert np.abs(full2[2 * s:2 * s + 2] - want).max() <= TOL, s
 
 
+@pytest.mark.parametrize("structure", [0, 1])
+@pytest.mark.parametrize("seg", [1, 9])
+def test_mid_side_bands_are_carried(checker, structure, seg):
+    """EQProcessor::filterState[2] / [3]: the Mid and Side rows' band states, Serial (node path) and Parallel structure, three
+    streams with different Mid/Side band sets, through conv -> EQ -> epilogue; state moved to another handle half-way."""
+    sr, block, ir_len, n_cb, n = 48000.0, 512, 20000, 60, 3
+    T = n_cb * block
+    modes = [[3, 0, 4, 1, 2] * 4, [0] * 20, [0, 4, 3, 0] * 5]
+    x = np.stack([signals.noise(T, 500 + i, 0.3) for i in range(2 * n)])
+    irs = [signals.synth_ir(ir_len, 600 + i) for i in range(2 * n)]
+
+    def make():
+        eng = ConvoPeqEngine(n, 2, sr, block, T, conv_boundary=capi.CONV_OUTER)
+        for s in range(n):
+            for ch in range(2):
+                eng.set_impulse(s, ch, irs[2 * s + ch], 1.0, None)
+            eng.set_eq(s, signals.to_band(signals.band_params(40 + s, modes=modes[s])), 0.2, 0.0, structure, s == 2)
+        eng.set_epilogue(1.1, 0)
+        return eng
+
+    eng = make()
+    one = x.copy()
+    eng.process(one, capi.STAGE_ALL)
+    eng.set_streaming(True)
+    two = _segmented(eng, x, seg * block, capi.STAGE_ALL)
+    eng.reset()
+    half = (n_cb // 2 // seg) * seg * block
+    a = _segmented(eng, x[:, :half], seg * block, capi.STAGE_ALL)
+    blob = eng.export_state()
+    eng.close()
+    eng2 = make()
+    eng2.set_streaming(True)
+    eng2.import_state(blob)
+    b = _segmented(eng2, x[:, half:], seg * block, capi.STAGE_ALL)
+    eng2.close()
+    assert np.abs(one - two).max() <= 1e-12
+    assert np.array_equal(np.concatenate([a, b], axis=1), two)
+    for s in range(n):
+        want = checker.chain_run((irs[2 * s], irs[2 * s + 1]), signals.to_eqband(signals.band_params(40 + s, modes=modes[s])),
+                                 x[2 * s:2 * s + 2], sr, block, None, makeup=1.1, structure=structure, agc=(s == 2))
+        assert np.abs(two[2 * s:2 * s + 2] - want).max() <= TOL, s
+
+
+@pytest.mark.parametrize("mix,bypass,delay", [(0.6, False, 700), (0.35, False, 5000), (1.0, True, 300), (0.0, False, 1234)])
+def test_dry_path_delay_ring_is_carried(mix, bypass, delay):
+    """ConvolverProcessor::process with mix < 1 (or bypassed): the latency-compensated dry path reads `delay` samples back, across
+    call boundaries -- calls shorter and longer than the delay; state moved to another handle half-way."""
+    sr, block, ir_len, n_cb, seg = 48000.0, 512, 20000, 48, 3
+    T = n_cb * block
+    x = np.stack([signals.noise(T, 800 + i, 0.3) for i in range(4)])
+    irs = [signals.synth_ir(ir_len, 810 + i) for i in range(4)]
+
+    def make():
+        eng = ConvoPeqEngine(2, 2, sr, block, T, conv_boundary=capi.CONV_OUTER)
+        for s in range(2):
+            for ch in range(2):
+                eng.set_impulse(s, ch, irs[2 * s + ch], 1.0, None)
+            eng.set_eq(s, signals.to_band(signals.band_params(820 + s)))
+        eng.set_epilogue(1.0, 0)
+        eng.set_mix(mix, delay)
+        eng.set_convolver_bypass(bypass)
+        return eng
+
+    eng = make()
+    conv1 = x.copy()
+    eng.process(conv1, capi.STAGE_CONV)
+    one = x.copy()
+    eng.process(one, capi.STAGE_ALL)
+    eng.set_streaming(True)
+    conv2 = _segmented(eng, x, seg * block, capi.STAGE_CONV)
+    assert np.array_equal(conv1, conv2)
+    eng.reset()
+    two = _segmented(eng, x, seg * block, capi.STAGE_ALL)
+    eng.reset()
+    half = (n_cb // 2 // seg) * seg * block
+    a = _segmented(eng, x[:, :half], seg * block, capi.STAGE_ALL)
+    blob = eng.export_state()
+    eng.close()
+    eng2 = make()
+    eng2.set_streaming(True)
+    eng2.import_state(blob)
+    b = _segmented(eng2, x[:, half:], seg * block, capi.STAGE_ALL)
+    eng2.close()
+    assert np.abs(one - two).max() <= 1e-12
+    assert np.array_equal(np.concatenate([a, b], axis=1), two)
+    if bypass or mix <= 0.001:      # the convolver stage is the delayed input alone
+        assert np.array_equal(conv1[:, delay:], x[:, :T - delay]) and not conv1[:, :delay].any()
+
+
 def test_tile_aligned_segments_are_bit_identical_for_the_whole_chain():
     """Segments of 16 callbacks = 8192 samples = one EQ scan tile: the tile grid of the segmented run coincides with the
     one-shot run's, so every stage gives the same bits."""
