@@ -1989,9 +1989,9 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
     int64_t xRows[CPQ_MAX_LAYERS] = {};    // rows per sequence in the X workspace (carried FDL rows + new frames)
     if (strm)
     {
-        if (directHead || !fullRange || nPeers > 0 || winFirst != 0 || winCount >= 0)
+        if (!fullRange || nPeers > 0 || winFirst != 0 || winCount >= 0)
         {
-            setError("process: streaming continuation does not cover the direct-form head or partition-range sharding / stream windows");
+            setError("process: streaming continuation does not cover partition-range sharding / stream windows");
             return CPQ_ERR_UNSUPPORTED;
         }
         if (doConv)
@@ -2470,6 +2470,15 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             DirectArgs d {};
             d.io = ioC;
             d.x = dryBuf.p;
+            d.xStride = stride;
+            d.lo = 0;
+            if (strm && cont && histLen >= 31)
+            {
+                // streaming continuation: the 31 samples before the call sit in front of the input in [history | input]
+                d.x = xcat.p + histLen;
+                d.xStride = (int64_t) histLen + T;
+                d.lo = -31;
+            }
             d.taps = directTaps.p;
             d.stride = stride;
             d.T = T;

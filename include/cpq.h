@@ -160,7 +160,7 @@ cpq_status cpq_reset(cpq_handle h);
  * stream-channel: the last 2 Pmax input samples, Q - 1 input spectra per layer, the tail samples Get has not read yet, and
  * the stage states.  cpq_reset returns to the Reset state; enable = 0 (default) makes every call start from Reset again.
  * Host blocks that are not a power of two (480, 441 ...) are carried through the reference's layer-0 output ring.
- * Not covered (CPQ_ERR_UNSUPPORTED from the process call): the direct-form head, partition
+ * Not covered (CPQ_ERR_UNSUPPORTED from the process call): partition
  * ranges / stream windows, plans that drop tail blocks; total-gain events scheduled
  * with cpq_schedule_total_gain must complete their ramp inside the call they start in. */
 cpq_status cpq_set_streaming(cpq_handle h, int enable);

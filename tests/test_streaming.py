@@ -206,6 +206,31 @@ def test_dry_path_delay_ring_is_carried(mix, bypass, delay):
         assert np.array_equal(conv1[:, delay:], x[:, :T - delay]) and not conv1[:, :delay].any()
 
 
+@pytest.mark.parametrize("block,seg,head", [(1024, 1, False), (2048, 3, False), (4096, 2, False), (512, 1, True), (512, 5, True)])
+def test_larger_blocks_and_the_direct_form_head(checker, block, seg, head):
+    """Blocks 1024 / 2048 / 4096 with the default FilterSpec: plans whose tail reader starves (skipped callbacks), P up to 32768
+    (the four-step transforms); and the experimental direct-form head, whose FIR reaches 31 samples back across the call boundary."""
+    sr, ir_len, n_cb = 48000.0, 131072, 72
+    T = n_cb * block
+    eng = ConvoPeqEngine(1, 2, sr, block, T)
+    if head:
+        eng.set_direct_head(True)
+    spec = capi.default_filter_spec()
+    irs = [signals.synth_ir(ir_len, 170 + ch) for ch in range(2)]
+    for ch in range(2):
+        eng.set_impulse(0, ch, irs[ch], 1.0, spec)
+    x = np.stack([signals.noise(T, 180), signals.noise(T, 181)])
+    one = x.copy()
+    eng.process(one, capi.STAGE_CONV)
+    eng.set_streaming(True)
+    two = _segmented(eng, x, seg * block, capi.STAGE_CONV)
+    eng.close()
+    assert np.array_equal(one, two), np.abs(one - two).max()
+    for ch in range(2):
+        want, _ = checker.nuc_run(irs[ch], x[ch], block, spec=OFilterSpec(), direct_head=head)
+        assert np.abs(two[ch] - want).max() <= TOL and np.abs(want).max() > 1e-3
+
+
 def test_tile_aligned_segments_are_bit_identical_for_the_whole_chain():
     """Segments of 16 callbacks = 8192 samples = one EQ scan tile: the tile grid of the segmented run coincides with the
     one-shot run's, so every stage gives the same bits."""
