@@ -436,7 +436,9 @@ struct Engine
     int histLen = 0;                     // input history samples per sequence
     int fdlRows[CPQ_MAX_LAYERS] = {};    // Q - 1
     int carryFrames[CPQ_MAX_LAYERS] = {};
-    DevBuf<double> inHist, xcat;
+    DevBuf<double> inHistBuf[2];         // input history, ping-pong per call (the forward transforms read it beside the call's input)
+    int inHistSel = 0;
+    double* inHistCur() { return inHistBuf[inHistSel].p; }
     DevBuf<double2> fdl[CPQ_MAX_LAYERS];
     DevBuf<double> tailCarry[CPQ_MAX_LAYERS];
     cpq_status ensureStreamState();
@@ -584,6 +586,7 @@ cpq_status Engine::launchFwdLarge(int log2P, const FwdArgs& a)
     la.totalFrames = a.totalFrames;
     la.framesPerSeq = a.framesPerSeq;
     la.src = a.src; la.srcStride = a.srcStride; la.frameStart0 = a.frameStart0; la.lo = a.lo; la.hi = a.hi; la.halfOnly = a.halfOnly;
+    la.histEnd = a.histEnd; la.histStride = a.histStride;
     la.rowPitchFrames = a.outFramesPerSeq; la.rowOffset = a.outFrameOffset;
     la.tw = a.tw; la.scale = a.scale; la.applyScale = a.applyScale; la.gain = a.gain; la.tilt = a.tilt;
     static const int g2Env = [] { const char* e = getenv("CPQ_GFFT2"); return e ? atoi(e) : 1; }();   // 0: one kernel per radix pass (round 1)
@@ -1369,7 +1372,7 @@ cpq_status Engine::ensureStreamState()
     int pmax = 0;
     for (int li = 0; li < plan.numLayers; ++li) pmax = std::max(pmax, plan.layers[li].partSize);
     const int wantHist = 2 * pmax;
-    const bool fresh = histLen != wantHist || !inHist.p;
+    const bool fresh = histLen != wantHist || !inHistBuf[0].p;
     histLen = wantHist;
     const int B = cfg.block_size;
     for (int li = 0; li < plan.numLayers; ++li)
@@ -1383,7 +1386,7 @@ cpq_status Engine::ensureStreamState()
                                   : (l.outputDelaySamples + l.partSize - 1) / l.partSize + (int) (((int64_t) cbs * B + l.partSize - 1) / l.partSize) + 2;
     }
     if (!fresh) return CPQ_OK;
-    CPQ_CUDA(inHist.ensure((size_t) nSeq * histLen));
+    for (auto& b : inHistBuf) CPQ_CUDA(b.ensure((size_t) nSeq * histLen));
     for (int li = 0; li < plan.numLayers; ++li)
     {
         const LayerPlan& l = plan.layers[li];
@@ -1397,7 +1400,8 @@ cpq_status Engine::ensureStreamState()
 cpq_status Engine::resetState()
 {
     CPQ_CUDA(cudaSetDevice(cfg.device));
-    if (inHist.p) CPQ_CUDA(cudaMemsetAsync(inHist.p, 0, inHist.n * sizeof(double), stream));
+    for (auto& b : inHistBuf)
+        if (b.p) CPQ_CUDA(cudaMemsetAsync(b.p, 0, b.n * sizeof(double), stream));
     for (int li = 0; li < CPQ_MAX_LAYERS; ++li)
     {
         if (fdl[li].p) CPQ_CUDA(cudaMemsetAsync(fdl[li].p, 0, fdl[li].n * sizeof(double2), stream));
@@ -1489,7 +1493,7 @@ cpq_status Engine::exportState(void* dst, size_t bytes)
         o += n;
         return e;
     };
-    CPQ_CUDA(put(inHist.p, (size_t) nSeq * histLen * sizeof(double), histLen > 0));
+    CPQ_CUDA(put(inHistCur(), (size_t) nSeq * histLen * sizeof(double), histLen > 0));
     for (int li = 0; li < h.numLayers; ++li)
     {
         CPQ_CUDA(put(fdl[li].p, (size_t) nSeq * fdlRows[li] * plan.layers[li].partSize * sizeof(double2), true));
@@ -1541,7 +1545,7 @@ cpq_status Engine::importState(const void* src, size_t bytes)
         o += n;
         return e;
     };
-    CPQ_CUDA(get(inHist.p, (size_t) nSeq * histLen * sizeof(double), histLen > 0));
+    CPQ_CUDA(get(inHistCur(), (size_t) nSeq * histLen * sizeof(double), histLen > 0));
     for (int li = 0; li < h.numLayers; ++li)
     {
         CPQ_CUDA(get(fdl[li].p, (size_t) nSeq * fdlRows[li] * plan.layers[li].partSize * sizeof(double2), true));
@@ -2033,7 +2037,6 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 if (li > 0 || l0Ring) perSeq += (size_t) K[li] * l.partSize * sizeof(double);
             }
         }
-        if (strm) perSeq += (size_t) (histLen + T) * sizeof(double);
         chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) nSeq, cfg.workspace_bytes / std::max<size_t>(perSeq, 1)));
     }
     if (hostIO) chunk = std::max(1, std::min(chunk, (nSeq + 31) / 32));   // short pipeline fill/drain
@@ -2066,7 +2069,6 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
         }
     if (strm && doConv)
     {
-        CPQ_CUDA(xcat.ensure((size_t) chunk * (histLen + T)));
         // this call's slice of the gather plan, relative to the start of each layer's workspace stream
         // (= the carried samples, then the new frames): position p of the layer's output stream sits at p - base
         std::vector<int64_t> rel((size_t) nCallbacks);
@@ -2300,15 +2302,6 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                                        (size_t) ns, cudaMemcpyDeviceToDevice, stream));
         if (doConv && !dryOnly)
         {
-            const int64_t catLen = (int64_t) histLen + T;
-            if (strm)
-            {
-                // [carried input history | this call's input]: the frames of this call reach back up to 2 P samples
-                CPQ_CUDA(cudaMemcpy2DAsync(xcat.p, (size_t) catLen * sizeof(double), inHist.p + (size_t) s0 * histLen, (size_t) histLen * sizeof(double),
-                                           (size_t) histLen * sizeof(double), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
-                CPQ_CUDA(cudaMemcpy2DAsync(xcat.p + histLen, (size_t) catLen * sizeof(double), ioC, (size_t) stride * sizeof(double),
-                                           (size_t) T * sizeof(double), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
-            }
             // The three stages of a layer for sequences [q0, q0 + n) of this chunk.
             auto fwdLayer = [&](int li, int q0, int n) -> cpq_status {
                 const LayerPlan& l = plan.layers[li];
@@ -2327,10 +2320,12 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 a.outFrameOffset = 0;
                 if (strm)
                 {
-                    a.src = xcat.p + (size_t) q0 * catLen;
-                    a.srcStride = catLen;
-                    a.frameStart0 = (int64_t) histLen + (kOld[li] - 1) * (int64_t) l.partSize - cb0 * (int64_t) B;   // >= 0: histLen = 2 Pmax
-                    a.hi = catLen;
+                    // the frames of this call reach back up to 2 P samples before it: those come from the carried input history
+                    // (histLen = 2 Pmax), read beside the call's input -- no concatenated copy
+                    a.frameStart0 = (kOld[li] - 1) * (int64_t) l.partSize - cb0 * (int64_t) B;
+                    a.lo = -(int64_t) histLen;
+                    a.histEnd = inHistCur() + (size_t) (s0 + q0) * histLen + histLen;
+                    a.histStride = histLen;
                     a.outFramesPerSeq = (int) xRows[li];
                     a.outFrameOffset = fdlRows[li];
                     if (fdlRows[li] > 0)   // the FDL: spectra of the Q - 1 frames before this call's first one
@@ -2433,6 +2428,22 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 cpq_status st = fwdLayer(li, 0, ns);
                 if (st != CPQ_OK) return st;
             }
+            if (strm && histLen > 0)
+            {
+                // input history for the next call = the last histLen samples of [history | input], into the other buffer; now,
+                // while io still holds the input (layer 0's inverse transform writes in place)
+                double* nh = inHistBuf[inHistSel ^ 1].p + (size_t) s0 * histLen;
+                const double* oh = inHistCur() + (size_t) s0 * histLen;
+                const size_t hb = (size_t) histLen * sizeof(double);
+                if (T >= histLen)
+                    CPQ_CUDA(cudaMemcpy2DAsync(nh, hb, ioC + (T - histLen), (size_t) stride * sizeof(double), hb, (size_t) ns, cudaMemcpyDeviceToDevice, stream));
+                else
+                {
+                    CPQ_CUDA(cudaMemcpy2DAsync(nh, hb, oh + T, hb, (size_t) (histLen - T) * sizeof(double), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
+                    CPQ_CUDA(cudaMemcpy2DAsync(nh + (histLen - T), hb, ioC, (size_t) stride * sizeof(double), (size_t) T * sizeof(double), (size_t) ns,
+                                               cudaMemcpyDeviceToDevice, stream));
+                }
+            }
             cudaEventRecord(ce[1], stream);
             // ---- MAC ----
             if (sliceL0)
@@ -2456,9 +2467,6 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 cpq_status st = invLayer(li, 0, ns);
                 if (st != CPQ_OK) return st;
             }
-            if (strm)   // input history for the next call: the last histLen samples of [history | input]
-                CPQ_CUDA(cudaMemcpy2DAsync(inHist.p + (size_t) s0 * histLen, (size_t) histLen * sizeof(double), xcat.p + T, (size_t) catLen * sizeof(double),
-                                           (size_t) histLen * sizeof(double), (size_t) ns, cudaMemcpyDeviceToDevice, stream));
         }
         else
         {
@@ -2470,14 +2478,11 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             DirectArgs d {};
             d.io = ioC;
             d.x = dryBuf.p;
-            d.xStride = stride;
-            d.lo = 0;
             if (strm && cont && histLen >= 31)
             {
-                // streaming continuation: the 31 samples before the call sit in front of the input in [history | input]
-                d.x = xcat.p + histLen;
-                d.xStride = (int64_t) histLen + T;
-                d.lo = -31;
+                // streaming continuation: the 31 samples before the call are the end of the input history this call started from
+                d.histEnd = inHistCur() + (size_t) s0 * histLen + histLen;
+                d.histStride = histLen;
             }
             d.taps = directTaps.p;
             d.stride = stride;
@@ -2699,6 +2704,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
         absCallback += nCallbacks;
         contValid = true;
         if (dryCarry) dryHistSel ^= 1;
+        if (doConv && !dryOnly && histLen > 0) inHistSel ^= 1;
     }
 
     if (doDither)

@@ -1672,11 +1672,11 @@ __global__ void mix_kernel(MixArgs a)
 struct DirectArgs
 {
     double* io;            // [nSeq][stride]: L0 output so far
-    const double* x;       // [nSeq][xStride]: the convolver input (copy); samples x[lo .. -1] are the input before this call
+    const double* x;       // [nSeq][stride]: the convolver input (copy)
     const double* taps;    // [nH][32]: hrev[k] = h[31 - k] * scale, zero padded at the front for shorter heads
     int64_t stride, T;
-    int64_t xStride;
-    int lo;                // 0 = Reset state before the call; -31 or less = streaming continuation (x points into [history | input])
+    const double* histEnd; // nullable (Reset state before the call): histEnd[seq * histStride + g] = input sample g < 0 (streaming continuation)
+    int64_t histStride;
     int hSeqMod, seqBase;  // row = (seqBase + seq) % hSeqMod when the IR pair is shared; 0 = seqBase + seq
 };
 
@@ -1688,7 +1688,8 @@ __global__ void direct_head_kernel(DirectArgs a)
     if (threadIdx.x < 32) h[threadIdx.x] = a.taps[(size_t) row * 32 + threadIdx.x];
     __syncthreads();
     double* io = a.io + (size_t) seq * a.stride;
-    const double* x = a.x + (size_t) seq * a.xStride;
+    const double* x = a.x + (size_t) seq * a.stride;
+    const double* hist = a.histEnd ? a.histEnd + (size_t) seq * a.histStride : nullptr;
     for (int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < a.T; t += (int64_t) gridDim.x * blockDim.x)
     {
         double s[8] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
@@ -1696,7 +1697,7 @@ __global__ void direct_head_kernel(DirectArgs a)
         for (int k = 0; k < 32; ++k)
         {
             const int64_t src = t - 31 + k;
-            const double v = src >= a.lo ? x[src] : 0.0;
+            const double v = src >= 0 ? x[src] : (hist ? hist[src] : 0.0);
             s[k & 7] = fma(h[k], v, s[k & 7]);
         }
         double y = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[4]), __dadd_rn(s[2], s[6])), __dadd_rn(__dadd_rn(s[1], s[5]), __dadd_rn(s[3], s[7])));

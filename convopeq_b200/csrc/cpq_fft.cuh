@@ -143,7 +143,19 @@ struct FwdArgs
     const double* gain;     // nullable [P+1]
     const double* tilt;     // nullable [P+1]
     double2* scratch;       // only for P > 8192 (cpq_fft_large.cuh): same geometry as out
+    // streaming continuation: samples before the call come from the carried input history instead of a concatenated copy.
+    // histEnd points one past the last history sample of sequence 0 (so histEnd[seq * histStride + g] is sample g < 0);
+    // null = no history, and then lo >= 0
+    const double* histEnd;
+    int64_t histStride;
 };
+
+// sample g of a sequence: this call's row for g >= 0, the carried history for g < 0, zero outside [lo, hi)
+__device__ __forceinline__ double fwd_sample(const double* __restrict__ src, const double* __restrict__ hist, int64_t lo, int64_t hi, int64_t g)
+{
+    if (g < lo || g >= hi) return 0.0;
+    return g >= 0 ? __ldg(src + g) : (hist ? __ldg(hist + g) : 0.0);
+}
 
 template <int LOG2P>
 struct FftCfg
@@ -194,7 +206,8 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOC
     const int64_t base = a.frameStart0 + (int64_t) f * P;
     const bool vec_ok = !IR || (a.halfOnly == 0);
     // whole frame inside the valid range and 16-byte aligned: no per-element checks (uniform per frame)
-    const bool inside = !IR && live && base >= a.lo && base + 2 * P <= a.hi && ((reinterpret_cast<uintptr_t>(src + base) & 15) == 0);
+    const double* hist = a.histEnd ? a.histEnd + seq * a.histStride : nullptr;
+    const bool inside = !IR && live && base >= 0 && base >= a.lo && base + 2 * P <= a.hi && ((reinterpret_cast<uintptr_t>(src + base) & 15) == 0);
     const double2* src2 = reinterpret_cast<const double2*>(src + base);
 
     auto gload = [&](int idx) -> double2 {
@@ -203,10 +216,10 @@ __global__ void __launch_bounds__(FftCfg<LOG2P>::THREADS, FftCfg<LOG2P>::MINBLOC
         const int64_t g = base + 2 * (int64_t) idx;
         if (!live) return make_double2(0.0, 0.0);
         if (IR && a.halfOnly && 2 * idx >= P) return make_double2(0.0, 0.0);
-        if (vec_ok && g >= a.lo && g + 1 < a.hi && ((reinterpret_cast<uintptr_t>(src + g) & 15) == 0)) return __ldg(reinterpret_cast<const double2*>(src + g));
+        if (vec_ok && g >= 0 && g >= a.lo && g + 1 < a.hi && ((reinterpret_cast<uintptr_t>(src + g) & 15) == 0)) return __ldg(reinterpret_cast<const double2*>(src + g));
         double2 z;
-        z.x = (g >= a.lo && g < a.hi) ? __ldg(src + g) : 0.0;
-        z.y = (g + 1 >= a.lo && g + 1 < a.hi) ? __ldg(src + g + 1) : 0.0;
+        z.x = fwd_sample(src, hist, a.lo, a.hi, g);
+        z.y = fwd_sample(src, hist, a.lo, a.hi, g + 1);
         return z;
     };
     auto sload = [&](int idx) -> double2 { return buf[fft_pad(idx)]; };

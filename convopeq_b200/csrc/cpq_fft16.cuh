@@ -67,14 +67,15 @@ __global__ void __launch_bounds__(Fft16Cfg<LOG2P>::THREADS, CPQ_FFT16_MINB) fft_
     const int f = (int) (gf % a.framesPerSeq);
     const double* src = a.src + seq * a.srcStride;
     const int64_t base = a.frameStart0 + (int64_t) f * P;
-    const bool inside = base >= a.lo && base + 2 * P <= a.hi && ((reinterpret_cast<uintptr_t>(src + base) & 15) == 0);
+    const double* hist = a.histEnd ? a.histEnd + seq * a.histStride : nullptr;
+    const bool inside = base >= 0 && base >= a.lo && base + 2 * P <= a.hi && ((reinterpret_cast<uintptr_t>(src + base) & 15) == 0);
     const double2* src2 = reinterpret_cast<const double2*>(src + base);
     auto gload = [&](int idx) -> double2 {
         if (inside) return __ldg(src2 + idx);
         const int64_t g = base + 2 * (int64_t) idx;
         double2 z;
-        z.x = (g >= a.lo && g < a.hi) ? __ldg(src + g) : 0.0;
-        z.y = (g + 1 >= a.lo && g + 1 < a.hi) ? __ldg(src + g + 1) : 0.0;
+        z.x = fwd_sample(src, hist, a.lo, a.hi, g);
+        z.y = fwd_sample(src, hist, a.lo, a.hi, g + 1);
         return z;
     };
     auto sload = [&](int idx) -> double2 { return buf[fft_pad(idx)]; };

@@ -37,6 +37,8 @@ struct LargeFftArgs
     // real side
     const double* src;      // forward: [nSeq][srcStride]
     int64_t srcStride, frameStart0, lo, hi;
+    const double* histEnd;  // see FwdArgs
+    int64_t histStride;
     int halfOnly;
     double* dst;            // inverse: [nSeq][dstStride], frame f -> dst[f*P .. (f+1)*P)
     int64_t dstStride;
@@ -67,12 +69,13 @@ __global__ void gfft_load_fwd_kernel(LargeFftArgs a)
     const int idx = (int) (i % a.P);
     const int64_t seq = gf / a.framesPerSeq, f = gf % a.framesPerSeq;
     const double* src = a.src + seq * a.srcStride;
+    const double* hist = a.histEnd ? a.histEnd + seq * a.histStride : nullptr;
     const int64_t g = a.frameStart0 + f * (int64_t) a.P + 2 * (int64_t) idx;
     double2 z = make_double2(0.0, 0.0);
     if (!(a.halfOnly && 2 * idx >= a.P))
     {
-        z.x = (g >= a.lo && g < a.hi) ? __ldg(src + g) : 0.0;
-        z.y = (g + 1 >= a.lo && g + 1 < a.hi) ? __ldg(src + g + 1) : 0.0;
+        z.x = fwd_sample(src, hist, a.lo, a.hi, g);
+        z.y = fwd_sample(src, hist, a.lo, a.hi, g + 1);
     }
     a.a[largeRow(a, gf) + idx] = z;
 }
@@ -265,6 +268,7 @@ __global__ void __launch_bounds__(kG2Cols * (1 << LOG2N1) / 8) gfft2_cols_kernel
     const int P = a.P;
     const int64_t seq = gf / a.framesPerSeq, f = gf % a.framesPerSeq;
     const double* src = FROM_REAL ? a.src + seq * a.srcStride : nullptr;
+    const double* hist = (FROM_REAL && a.histEnd) ? a.histEnd + seq * a.histStride : nullptr;
     const int64_t g0 = FROM_REAL ? a.frameStart0 + f * (int64_t) P : 0;
     for (int idx = tid; idx < N1 * C; idx += THREADS)
     {
@@ -277,8 +281,8 @@ __global__ void __launch_bounds__(kG2Cols * (1 << LOG2N1) / 8) gfft2_cols_kernel
             if (!(a.halfOnly && 2 * e >= P))
             {
                 const int64_t g = g0 + 2 * (int64_t) e;
-                z.x = (g >= a.lo && g < a.hi) ? __ldg(src + g) : 0.0;
-                z.y = (g + 1 >= a.lo && g + 1 < a.hi) ? __ldg(src + g + 1) : 0.0;
+                z.x = fwd_sample(src, hist, a.lo, a.hi, g);
+                z.y = fwd_sample(src, hist, a.lo, a.hi, g + 1);
             }
         }
         else
