@@ -439,7 +439,13 @@ struct Engine
     DevBuf<double> inHistBuf[2];         // input history, ping-pong per call (the forward transforms read it beside the call's input)
     int inHistSel = 0;
     double* inHistCur() { return inHistBuf[inHistSel].p; }
-    DevBuf<double2> fdl[CPQ_MAX_LAYERS];
+    // The FDL: per layer a persistent buffer of xCap rows of spectra per sequence.  Rows [xHead - fdlRows, xHead) are the spectra
+    // of the Q - 1 frames before the next call's first one; a call appends its new frames at xHead (the forward transform writes
+    // them there, the MAC reads [carried | new] in place) and xHead moves on.  When the buffer is full the carried rows are
+    // copied back to its start -- once every (xCap - 2 fdlRows) / K calls instead of a copy in and a copy out per call.
+    DevBuf<double2> xs[CPQ_MAX_LAYERS];
+    int xCap[CPQ_MAX_LAYERS] = {}, xHead[CPQ_MAX_LAYERS] = {};
+    cpq_status prepareFdl(int li, int64_t newFrames, bool cont);
     DevBuf<double> tailCarry[CPQ_MAX_LAYERS];
     cpq_status ensureStreamState();
     cpq_status resetState();
@@ -689,14 +695,16 @@ static EncodeTiledFn encodeTiledFn()
     return fn;
 }
 // rank-3 FP64 tensor [d2][d1][d0 doubles] with a box of [1][box1][64 doubles]; out-of-bounds elements read as zero
-static bool encodeSpectraMap(MacTensorMap& out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1)
+// rank-3 map [d2 sequences][d1 rows][d0 doubles]; pitchRows = rows between two sequences when that is more than the d1 rows the
+// map may touch (a window into a larger per-sequence buffer)
+static bool encodeSpectraMap(MacTensorMap& out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1, uint64_t pitchRows = 0)
 {
     EncodeTiledFn fn = encodeTiledFn();
     if (!fn) return false;
     static_assert(sizeof(CUtensorMap) == sizeof(MacTensorMap), "tensor map size");
     CUtensorMap tm;
     const cuuint64_t gdim[3] = { d0, d1, d2 };
-    const cuuint64_t gstride[2] = { d0 * sizeof(double), d0 * d1 * sizeof(double) };
+    const cuuint64_t gstride[2] = { d0 * sizeof(double), d0 * (pitchRows ? pitchRows : d1) * sizeof(double) };
     const cuuint32_t box[3] = { 64, box1, 1 };
     const cuuint32_t estride[3] = { 1, 1, 1 };
     if (fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1390,10 +1398,49 @@ cpq_status Engine::ensureStreamState()
     for (int li = 0; li < plan.numLayers; ++li)
     {
         const LayerPlan& l = plan.layers[li];
-        CPQ_CUDA(fdl[li].ensure((size_t) nSeq * std::max(fdlRows[li], 1) * l.partSize));
         if (carryFrames[li] > 0) CPQ_CUDA(tailCarry[li].ensure((size_t) nSeq * carryFrames[li] * l.partSize));
     }
     return resetState();
+}
+
+// Room for `newFrames` more spectra behind the carried ones of layer li (see Engine::xs); `cont` = the carried rows are live
+cpq_status Engine::prepareFdl(int li, int64_t newFrames, bool cont)
+{
+    const int F = fdlRows[li], P = plan.layers[li].partSize;
+    const size_t rowB = (size_t) P * sizeof(double2);
+    const int need = 2 * F + (int) newFrames;   // the copy-back of F rows to the start never overlaps its source
+    if (!xs[li].p || xCap[li] < need)
+    {
+        const int cap = need + (int) newFrames;   // a second call of this size fits before the first copy-back
+        DevBuf<double2> nb;
+        CPQ_CUDA(nb.ensure((size_t) nSeq * cap * P));
+        if (F > 0)
+        {
+            if (cont && xs[li].p)
+                CPQ_CUDA(cudaMemcpy2DAsync(nb.p, (size_t) cap * rowB, xs[li].p + (size_t) (xHead[li] - F) * P, (size_t) xCap[li] * rowB, (size_t) F * rowB,
+                                           (size_t) nSeq, cudaMemcpyDeviceToDevice, stream));
+            else
+                CPQ_CUDA(cudaMemset2DAsync(nb.p, (size_t) cap * rowB, 0, (size_t) F * rowB, (size_t) nSeq, stream));
+            CPQ_CUDA(cudaStreamSynchronize(stream));   // the old buffer is released below
+        }
+        std::swap(xs[li].p, nb.p);
+        std::swap(xs[li].n, nb.n);
+        xCap[li] = cap;
+        xHead[li] = F;
+    }
+    else if (!cont)
+    {
+        if (F > 0) CPQ_CUDA(cudaMemset2DAsync(xs[li].p, (size_t) xCap[li] * rowB, 0, (size_t) F * rowB, (size_t) nSeq, stream));
+        xHead[li] = F;
+    }
+    else if (xHead[li] + newFrames > xCap[li])
+    {
+        if (F > 0)
+            CPQ_CUDA(cudaMemcpy2DAsync(xs[li].p, (size_t) xCap[li] * rowB, xs[li].p + (size_t) (xHead[li] - F) * P, (size_t) xCap[li] * rowB, (size_t) F * rowB,
+                                       (size_t) nSeq, cudaMemcpyDeviceToDevice, stream));
+        xHead[li] = F;
+    }
+    return CPQ_OK;
 }
 
 // MKLNonUniformConvolver::Reset (.cpp:1693) + EQProcessor state clear + PsychoacousticDither::reset for every stream
@@ -1404,7 +1451,10 @@ cpq_status Engine::resetState()
         if (b.p) CPQ_CUDA(cudaMemsetAsync(b.p, 0, b.n * sizeof(double), stream));
     for (int li = 0; li < CPQ_MAX_LAYERS; ++li)
     {
-        if (fdl[li].p) CPQ_CUDA(cudaMemsetAsync(fdl[li].p, 0, fdl[li].n * sizeof(double2), stream));
+        if (xs[li].p && fdlRows[li] > 0)   // Reset: an empty FDL at the start of the buffer
+            CPQ_CUDA(cudaMemset2DAsync(xs[li].p, (size_t) xCap[li] * plan.layers[li].partSize * sizeof(double2), 0,
+                                       (size_t) fdlRows[li] * plan.layers[li].partSize * sizeof(double2), (size_t) nSeq, stream));
+        xHead[li] = fdlRows[li];
         if (tailCarry[li].p) CPQ_CUDA(cudaMemsetAsync(tailCarry[li].p, 0, tailCarry[li].n * sizeof(double), stream));
     }
     CPQ_CUDA(cudaMemsetAsync(ditherZ.p, 0, (size_t) nSeq * 12 * sizeof(double), stream));
@@ -1496,7 +1546,16 @@ cpq_status Engine::exportState(void* dst, size_t bytes)
     CPQ_CUDA(put(inHistCur(), (size_t) nSeq * histLen * sizeof(double), histLen > 0));
     for (int li = 0; li < h.numLayers; ++li)
     {
-        CPQ_CUDA(put(fdl[li].p, (size_t) nSeq * fdlRows[li] * plan.layers[li].partSize * sizeof(double2), true));
+        {
+            // the FDL rows of every sequence, gathered out of the persistent buffers
+            const size_t rowB = (size_t) plan.layers[li].partSize * sizeof(double2), n = (size_t) nSeq * fdlRows[li] * rowB;
+            if (xs[li].p && n)
+                CPQ_CUDA(cudaMemcpy2D(o, (size_t) fdlRows[li] * rowB, xs[li].p + (size_t) (xHead[li] - fdlRows[li]) * plan.layers[li].partSize,
+                                      (size_t) xCap[li] * rowB, (size_t) fdlRows[li] * rowB, (size_t) nSeq, cudaMemcpyDeviceToHost));
+            else
+                std::memset(o, 0, n);
+            o += n;
+        }
         CPQ_CUDA(put(tailCarry[li].p, (size_t) nSeq * carryFrames[li] * plan.layers[li].partSize * sizeof(double), carryFrames[li] > 0));
     }
     CPQ_CUDA(put(stateOut.p, (size_t) nSeq * CPQ_NUM_BANDS * 2 * sizeof(double), true));
@@ -1548,7 +1607,16 @@ cpq_status Engine::importState(const void* src, size_t bytes)
     CPQ_CUDA(get(inHistCur(), (size_t) nSeq * histLen * sizeof(double), histLen > 0));
     for (int li = 0; li < h.numLayers; ++li)
     {
-        CPQ_CUDA(get(fdl[li].p, (size_t) nSeq * fdlRows[li] * plan.layers[li].partSize * sizeof(double2), true));
+        {
+            const size_t rowB = (size_t) plan.layers[li].partSize * sizeof(double2), n = (size_t) nSeq * fdlRows[li] * rowB;
+            cpq_status stf = prepareFdl(li, 1, false);   // (allocates on a fresh handle; the rows land at the start of the buffer)
+            if (stf != CPQ_OK) return stf;
+            CPQ_CUDA(cudaStreamSynchronize(stream));   // its clears run on the engine stream, the copy below does not
+            if (n)
+                CPQ_CUDA(cudaMemcpy2D(xs[li].p, (size_t) xCap[li] * rowB, o, (size_t) fdlRows[li] * rowB, (size_t) fdlRows[li] * rowB, (size_t) nSeq,
+                                      cudaMemcpyHostToDevice));
+            o += n;
+        }
         CPQ_CUDA(get(tailCarry[li].p, (size_t) nSeq * carryFrames[li] * plan.layers[li].partSize * sizeof(double), carryFrames[li] > 0));
     }
     CPQ_CUDA(get(stateOut.p, (size_t) nSeq * CPQ_NUM_BANDS * 2 * sizeof(double), true));
@@ -2025,7 +2093,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 // every frame whose input is complete at the end of this call, minus those earlier calls computed
                 kOld[li] = cb0 * (int64_t) B / l.partSize;
                 K[li] = (cb0 + nCallbacks) * (int64_t) B / l.partSize - kOld[li];
-                xRows[li] = fdlRows[li] + K[li];
+                xRows[li] = K[li];   // the chunk workspace only serves as scratch in streaming mode: the spectra live in Engine::xs
                 perSeq += (size_t) (xRows[li] + K[li]) * l.partSize * sizeof(double2);
                 if (li > 0 || l0Ring) perSeq += (size_t) (carryFrames[li] + K[li]) * l.partSize * sizeof(double);
             }
@@ -2250,6 +2318,12 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
     // convolver input trim, then the convolver; the final launch then only assembles the layers and runs the output stages
     const bool eqFirst = (stages & CPQ_ORDER_EQ_THEN_CONV) && doConv && doEq;
 
+    if (strm && doConv && !dryOnly)
+        for (int li = 0; li < plan.numLayers; ++li)
+        {
+            cpq_status st = prepareFdl(li, K[li], cont);
+            if (st != CPQ_OK) return st;
+        }
     for (size_t c = 0; c < nChunks; ++c)
     {
         const int s0 = seqLo + (int) c * chunk, ns = std::min(chunk, seqLo + nSeq - s0);
@@ -2326,18 +2400,28 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                     a.lo = -(int64_t) histLen;
                     a.histEnd = inHistCur() + (size_t) (s0 + q0) * histLen + histLen;
                     a.histStride = histLen;
-                    a.outFramesPerSeq = (int) xRows[li];
-                    a.outFrameOffset = fdlRows[li];
-                    if (fdlRows[li] > 0)   // the FDL: spectra of the Q - 1 frames before this call's first one
-                        CPQ_CUDA(cudaMemcpy2DAsync(layer[li].X.p + (size_t) q0 * xRows[li] * l.partSize, (size_t) xRows[li] * l.partSize * sizeof(double2),
-                                                   fdl[li].p + (size_t) (s0 + q0) * fdlRows[li] * l.partSize, (size_t) fdlRows[li] * l.partSize * sizeof(double2),
-                                                   (size_t) fdlRows[li] * l.partSize * sizeof(double2), (size_t) n, cudaMemcpyDeviceToDevice, stream));
+                    // the new spectra go behind the carried ones in the sequence's FDL buffer -- directly, except for the four-step
+                    // transforms (P > 8192), whose scratch shares the geometry of their output: those write the chunk workspace
+                    // and the rows are copied over
+                    if (l.partSize <= 8192)
+                    {
+                        a.out = xs[li].p + (size_t) (s0 + q0) * xCap[li] * l.partSize;
+                        a.outFramesPerSeq = xCap[li];
+                        a.outFrameOffset = xHead[li];
+                    }
                 }
                 a.tw = layer[li].tw.p;
                 a.ptw = layer[li].ptw.p;
                 a.scratch = layer[li].Y.p + (size_t) q0 * K[li] * l.partSize;   // free until the MAC writes it
                 a.scale = 1.0;
-                return launchFwd(ilog2(l.partSize), a);
+                cpq_status stf = launchFwd(ilog2(l.partSize), a);
+                if (stf == CPQ_OK && strm && l.partSize > 8192)
+                {
+                    const size_t rowB = (size_t) l.partSize * sizeof(double2);
+                    CPQ_CUDA(cudaMemcpy2DAsync(xs[li].p + ((size_t) (s0 + q0) * xCap[li] + (size_t) xHead[li]) * l.partSize, (size_t) xCap[li] * rowB, a.out,
+                                               (size_t) K[li] * rowB, (size_t) K[li] * rowB, (size_t) n, cudaMemcpyDeviceToDevice, stream));
+                }
+                return stf;
             };
             auto macLayer = [&](int li, int q0, int n) -> cpq_status {
                 const LayerPlan& l = plan.layers[li];
@@ -2351,6 +2435,14 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 }
                 MacArgs a {};
                 a.X = layer[li].X.p + (size_t) q0 * xRows[li] * l.partSize;
+                int64_t xPitch = xRows[li], xExtent = xRows[li];
+                if (strm)
+                {
+                    // [carried | new] in place: a window of the sequence's FDL buffer that starts fdlRows before the new frames
+                    a.X = xs[li].p + ((size_t) (s0 + q0) * xCap[li] + (size_t) (xHead[li] - fdlRows[li])) * l.partSize;
+                    xPitch = xCap[li];
+                    xExtent = xCap[li] - (xHead[li] - fdlRows[li]);
+                }
                 a.H = layer[li].H.p;
                 a.Y = layer[li].Y.p + (size_t) q0 * K[li] * l.partSize;
                 a.K = (int) K[li];
@@ -2371,7 +2463,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 if (fpcEnv > 0 && fpcEnv % step == 0 && fpcEnv < fpc && K[li] <= 2 * step) fpc = fpcEnv;   // short layers only
                 a.framesPerCta = fpc;
                 a.hist = strm ? fdlRows[li] : 0;
-                a.xRows = (int) xRows[li];
+                a.xRows = (int) xPitch;
                 a.ringRows = fpc <= step ? (step + (a.qEnd - a.qBegin) - 1 + kMacKT - 1) / kMacKT * kMacKT : macRingRows(a.qEnd - a.qBegin);
                 const size_t smem = macSmemBytes(a.qEnd - a.qBegin, a.ringRows);
                 if (smem > kMaxDynSmem)
@@ -2385,17 +2477,13 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 static const int tmaEnv = [] { const char* e = getenv("CPQ_MAC_TMA"); return e ? atoi(e) : 1; }();   // tuning knob
                 MacTensorMap tmX, tmH;
                 if (tmaEnv && a.qEnd - a.qBegin <= kMacTmaMaxTaps && macTmaSmemBytes(a.qEnd - a.qBegin) <= kMaxDynSmem &&
-                    encodeSpectraMap(tmX, a.X, 2 * (uint64_t) l.partSize, (uint64_t) xRows[li], (uint64_t) n, (uint32_t) kMacSuper) &&
+                    encodeSpectraMap(tmX, a.X, 2 * (uint64_t) l.partSize, (uint64_t) xExtent, (uint64_t) n, (uint32_t) kMacSuper, (uint64_t) xPitch) &&
                     encodeSpectraMap(tmH, layer[li].H.p, 2 * (uint64_t) l.partSize, (uint64_t) l.numPartsIR, (uint64_t) nH, (uint32_t) (a.qEnd - a.qBegin)))
                     mac_tma_kernel<<<grid, kMacThreads, macTmaSmemBytes(a.qEnd - a.qBegin), stream>>>(a, tmX, tmH);
                 else
                     mac_kernel<<<grid, kMacThreads, smem, stream>>>(a);
                 ++launches;
                 CPQ_CUDA(cudaGetLastError());
-                if (strm && fdlRows[li] > 0)   // the FDL the next call starts from: the last Q - 1 rows of [carried | new]
-                    CPQ_CUDA(cudaMemcpy2DAsync(fdl[li].p + (size_t) (s0 + q0) * fdlRows[li] * l.partSize, (size_t) fdlRows[li] * l.partSize * sizeof(double2),
-                                               a.X + (size_t) K[li] * l.partSize, (size_t) xRows[li] * l.partSize * sizeof(double2),
-                                               (size_t) fdlRows[li] * l.partSize * sizeof(double2), (size_t) n, cudaMemcpyDeviceToDevice, stream));
                 return CPQ_OK;
             };
             auto invLayer = [&](int li, int q0, int n) -> cpq_status {
@@ -2705,6 +2793,8 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
         contValid = true;
         if (dryCarry) dryHistSel ^= 1;
         if (doConv && !dryOnly && histLen > 0) inHistSel ^= 1;
+        if (doConv && !dryOnly)
+            for (int li = 0; li < plan.numLayers; ++li) xHead[li] += (int) K[li];   // the FDL now ends with this call's last frames
     }
 
     if (doDither)
