@@ -453,7 +453,13 @@ struct Engine
     cpq_status exportState(void* dst, size_t bytes);
     cpq_status importState(const void* src, size_t bytes);
     cpq_status processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF = nullptr);
-    cpq_status processCoreImpl(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF);
+    cpq_status processCoreImpl(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF,
+                               bool deferSideStreams = false);
+    // Time segments of a device-resident call with the dither branch (processCore): the serial shaper of segment s runs on the
+    // side streams beside the transforms of segment s + 1 instead of trailing the whole call by one full-length chain.
+    bool workStarted = false;            // the chunk loop of the last processCoreImpl call has begun (buffers may be modified)
+    int forcedChunk = 0;                 // > 0: sequence chunk size of the first segment, kept for the others (chunk -> side stream map)
+    int64_t segUniTotal = 0, segUniOffset = 0;   // injected uniforms: samples per channel of the whole call, first sample of the segment
     DevBuf<float> f32In, f32Out;        // device staging of float host buffers: 3 inbound / 2 outbound chunk slots
     PinnedBuf stageIn, stageOut;        // pinned staging rings for pageable FP64 host buffers (HostStager)
     cpq_status processDevice(double* dIo, int64_t stride, int64_t T, unsigned stages) { return processCore(dIo, stride, T, stages, nullptr); }
@@ -1923,7 +1929,57 @@ cpq_status Engine::runEq(EqArgs e, int s0, int ns)
 // still writing the caller's buffers): drain them before the status reaches the caller, who may free or reuse the buffers.
 cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF)
 {
-    const cpq_status st = processCoreImpl(dIo, stride, T, stages, hostPlanar, hostF);
+    // The dither's shaper is one dependent chain per sequence (200 cycles per sample, 50 ms for 10 s of audio whatever the batch).
+    // Run after a sequence chunk's EQ it trails the call by a whole chain; run per *time segment* through the streaming
+    // continuation (segment boundaries on EQ tile boundaries, so every sample up to the quantiser is bit-identical to the one-shot
+    // call) only the last segment's chain trails.  CPQ_DITHER_SEGMENTS=1 turns it off.
+    // Measured at cfg4 (10 s, 2048 sequences): 1 / 2 / 3 / 4 segments 118 / 102 / 102 / 99 ms -- shorter segments leave the MAC's
+    // 64-frame blocks of the 4096-sample layer half empty, which eats what the shorter trailing chain returns; segments of less
+    // than 65536 samples are not worth it.
+    static const int segEnv = [] { const char* e = getenv("CPQ_DITHER_SEGMENTS"); return e ? atoi(e) : 4; }();
+    const int64_t segUnit = std::max<int64_t>(kEqTile, cfg.block_size);
+    const int64_t nSeg = std::min<int64_t>(segEnv, T / 65536);
+    const int64_t segLen = nSeg > 1 ? ((T + nSeg - 1) / nSeg + segUnit - 1) / segUnit * segUnit : T;
+    bool noEvents = !haveGainTab;
+    for (auto& e : eqSets) noEvents = noEvents && e.events.empty();
+    const bool segmented = segLen < T && !streaming && !hostPlanar && !hostF && planSet && noEvents && ditherBits > 0 &&
+                           (stages & CPQ_STAGE_CONV) && (stages & CPQ_STAGE_EPILOGUE) && T % cfg.block_size == 0;
+    cpq_status st = CPQ_OK;
+    bool done = false;
+    if (segmented)
+    {
+        streaming = true;
+        contValid = false;
+        absCallback = 0;
+        cpq_timings sum {};
+        done = true;
+        for (int64_t off = 0; off < T && st == CPQ_OK; off += segLen)
+        {
+            const int64_t len = std::min(segLen, T - off);
+            segUniTotal = T;
+            segUniOffset = off;
+            st = processCoreImpl(dIo + off, stride, len, stages, nullptr, nullptr, off + len < T);
+            if (st == CPQ_ERR_UNSUPPORTED && off == 0 && !workStarted)
+            {
+                done = false;   // outside what the continuation carries (irregular plans, stream windows ...): nothing was touched
+                st = CPQ_OK;
+                break;
+            }
+            sum.fft_fwd_ms += timings.fft_fwd_ms; sum.mac_ms += timings.mac_ms; sum.fft_inv_ms += timings.fft_inv_ms;
+            sum.eq_ms += timings.eq_ms; sum.total_ms += timings.total_ms;
+            sum.kernel_launches += timings.kernel_launches; sum.chunks += timings.chunks;
+        }
+        if (st != CPQ_OK)
+            for (auto& d : sDither) cudaStreamSynchronize(d);
+        streaming = false;
+        contValid = false;
+        absCallback = 0;
+        forcedChunk = 0;
+        segUniTotal = segUniOffset = 0;
+        gplanCallbacks = -1;
+        if (done) timings = sum;
+    }
+    if (!done) st = processCoreImpl(dIo, stride, T, stages, hostPlanar, hostF);
     if (st != CPQ_OK)
     {
         if (sIn) cudaStreamSynchronize(sIn);
@@ -1941,9 +1997,11 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
     return st;
 }
 
-cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF)
+cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsigned stages, double* const* hostPlanar, float* const* hostF,
+                                   bool deferSideStreams)
 {
     const bool hostIO = hostPlanar || hostF;
+    workStarted = false;
     // rows are 16-byte aligned (even stride); an odd T (odd host blocks: 441 x an odd number of callbacks) leaves one pad
     // sample at the end of each row, which the paired accesses of the small kernels may touch
     if (!dIo || T <= 0 || T > cfg.max_samples || T % cfg.block_size != 0 || stride < T + (T & 1) || (stride & 1))
@@ -2009,11 +2067,11 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
         CPQ_CUDA(cudaMemsetAsync(limFlag.p, doDither ? 0xff : 0, (size_t) cfg.n_streams * sizeof(unsigned), stream));
     }
     if (doDither && !cont) CPQ_CUDA(cudaMemsetAsync(ditherZ.p, 0, (size_t) this->nSeq * 12 * sizeof(double), stream));   // PsychoacousticDither::reset
-    if (doDither && cont)
+    if (doDither && cont && segUniTotal == 0)
         for (auto& d : sDither) CPQ_CUDA(cudaStreamSynchronize(d));   // (paranoia: the carried history is read on the side streams)
     if (doDither && ditherRng && !cont)   // a fresh PsychoacousticDither per stream: generator state as constructed
         CPQ_CUDA(cudaMemcpyAsync(rngState.p, rngSeedState.data(), rngSeedState.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
-    if (doDither && !ditherRng && uniformsPerCh != T)
+    if (doDither && !ditherRng && uniformsPerCh != (segUniTotal > 0 ? segUniTotal : T))
     {
         setError("process: dither enabled but cpq_set_dither_uniforms does not hold exactly T samples per channel");
         return CPQ_ERR_NOT_READY;
@@ -2108,6 +2166,12 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
         chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) nSeq, cfg.workspace_bytes / std::max<size_t>(perSeq, 1)));
     }
     if (hostIO) chunk = std::max(1, std::min(chunk, (nSeq + 31) / 32));   // short pipeline fill/drain
+    if (segUniTotal > 0)
+    {
+        // segmented call: every segment uses the first one's chunks, so that a sequence's dither stays on one side stream
+        if (forcedChunk > 0) chunk = std::min(chunk, forcedChunk);
+        else forcedChunk = chunk;
+    }
     // pageable caller rows go through pinned staging slots (HostStager): smaller chunks bound the pinned memory (6 slots)
     static const int stageThreadsEnv = [] { const char* e = getenv("CPQ_STAGE_THREADS"); return e ? atoi(e) : -1; }();   // 0 = let the driver stage
     const bool pageable = hostPlanar && stageThreadsEnv != 0 && (hostRowIsPageable(hostPlanar[seqLo]) || hostRowIsPageable(hostPlanar[seqLo + nSeq - 1]));
@@ -2318,6 +2382,14 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
     // convolver input trim, then the convolver; the final launch then only assembles the layers and runs the output stages
     const bool eqFirst = (stages & CPQ_ORDER_EQ_THEN_CONV) && doConv && doEq;
 
+    workStarted = true;
+    if (strm && doConv && !dryOnly && !cont)
+    {
+        // a stream that starts here starts from Reset, whatever an earlier stream left in the carried buffers
+        if (inHistCur()) CPQ_CUDA(cudaMemsetAsync(inHistCur(), 0, (size_t) this->nSeq * histLen * sizeof(double), stream));
+        for (int li = 0; li < plan.numLayers; ++li)
+            if (tailCarry[li].p) CPQ_CUDA(cudaMemsetAsync(tailCarry[li].p, 0, tailCarry[li].n * sizeof(double), stream));
+    }
     if (strm && doConv && !dryOnly)
         for (int li = 0; li < plan.numLayers; ++li)
         {
@@ -2706,7 +2778,8 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             d.ioStride = stride;
             d.T = T;
             d.nSeq = ns;
-            d.uniforms = ditherRng ? nullptr : (uniformsBorrowed ? uniformsBorrowed : uniforms.p) + (size_t) s0 * 2 * T;
+            d.uniRow = segUniTotal > 0 ? segUniTotal : T;
+            d.uniforms = ditherRng ? nullptr : (uniformsBorrowed ? uniformsBorrowed : uniforms.p) + ((size_t) s0 * d.uniRow + (size_t) segUniOffset) * 2;
             d.rng = ditherRng ? rngState.p + s0 : nullptr;
             ditherCoeffs(cfg.sample_rate, ditherBits, d.coeff);
             d.scale = 1.0 / std::pow(2.0, ditherBits - 1);
@@ -2797,7 +2870,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             for (int li = 0; li < plan.numLayers; ++li) xHead[li] += (int) K[li];   // the FDL now ends with this call's last frames
     }
 
-    if (doDither)
+    if (doDither && !deferSideStreams)
         for (size_t c = 0; c < nChunks; ++c) cudaStreamWaitEvent(stream, evPool[dBase + c * 2 + 1], 0);
     if (hostIO)
     {

@@ -1798,6 +1798,7 @@ struct DitherArgs
     unsigned long long* rng;  // [nSeq] xorshift64* state per stream-channel (PsychoacousticDither::fallbackState, :485-497), carried
     double coeff[12];
     double scale, invScale;
+    int64_t uniRow;           // samples per channel in a row of `uniforms` (= T unless the call is one time segment of a longer buffer)
     double* z;                // [nSeq][12] error history (carried)
     int finalClamp;           // after the quantiser: bit 0 scrub, bit 1 clamp to +-kOutputHeadroom (DSPCoreDouble.cpp:665-691, 712-737)
 };
@@ -1897,8 +1898,8 @@ __global__ void __launch_bounds__(kDitherThreads) dither_kernel(DitherArgs a)
         const int rr = lane / kSigPieces, pc = lane % kSigPieces;
         const size_t sigRowStep = (size_t) rowsPerStep * a.ioStride;
         double* const sigBase = a.io + (size_t) (seq0 + rr) * a.ioStride + 2 * pc;                 // + tile * kDthTile, + k * sigRowStep
-        const double* const uniBase = useRng ? nullptr : a.uniforms + ((size_t) seq0 * a.T + lane) * 2;   // + tile * 2 kDthTile, + r * 2 T
-        const size_t uniRowStep = (size_t) a.T * 2;
+        const double* const uniBase = useRng ? nullptr : a.uniforms + ((size_t) seq0 * a.uniRow + lane) * 2;   // + tile * 2 kDthTile, + r * 2 T
+        const size_t uniRowStep = (size_t) a.uniRow * 2;
         // cpq_set_dither_seed: the uniforms come from the reference's fallback generator, one stream per sequence -- drawn here,
         // a tile ahead, so that the integer work stays out of the shaper's instruction stream (277 -> 207 cycles per sample)
         unsigned long long rs = (useRng && lane < nLocal) ? a.rng[seq0 + lane] : 0ull;

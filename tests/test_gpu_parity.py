@@ -472,6 +472,40 @@ def test_dither_with_the_reference_fallback_generator(checker):
         assert np.array_equal(y[2 * s:2 * s + 2], want), s
 
 
+@pytest.mark.parametrize("seeded", [False, True])
+def test_dither_time_segments_equal_the_one_shot_call(seeded):
+    """A device-resident conv -> EQ -> dither call runs in time segments (the shaper of one segment beside the transforms of the
+    next, through the streaming continuation); the host-buffer call runs in one piece.  The shaper is chaotic, so equal means
+    bit for bit -- everything up to the quantiser is identical because the segments end on EQ tile boundaries.  (Both calls use
+    look-back links: at most 32 sequences per chunk.)"""
+    import torch
+    sr, block, T, n_streams = 48000.0, 512, 65536 * 3 + 512 * 3, 40
+    n_seq = 2 * n_streams
+    x = np.stack([signals.noise(T, 700 + i, 0.3) for i in range(n_seq)])
+    eng = ConvoPeqEngine(n_streams, 2, sr, block, T, conv_boundary=capi.CONV_OUTER, workspace_bytes=100 << 20)   # several small sequence chunks
+    for s in range(n_streams):
+        for ch in range(2):
+            eng.set_impulse(s, ch, signals.synth_ir(20000, 720 + (2 * s + ch) % 7), 1.0, capi.default_filter_spec())
+        eng.set_eq(s, signals.to_band(signals.band_params(740 + s % 5)))
+    if seeded:
+        eng.set_epilogue(0.9, 24)
+        eng.set_dither_seed([(0x9E3779B97F4A7C15 * (s + 1)) & 0xFFFFFFFFFFFFFFFF for s in range(n_streams)])
+    else:
+        eng.set_epilogue(0.9, 24, np.random.default_rng(6).random((n_seq, 2 * T)))
+    eng.set_peak_limiter(100.0)
+    y = x.copy()
+    eng.process(y, capi.STAGE_ALL)                       # host buffers: one piece
+    d = torch.from_numpy(x).cuda()
+    eng.process_device(d.data_ptr(), T, T, capi.STAGE_ALL)   # device-resident: time segments
+    t = eng.timings()
+    d2 = torch.from_numpy(x).cuda()
+    eng.process_device(d2.data_ptr(), T, T, capi.STAGE_ALL)  # and again: a new stream starts from Reset
+    eng.close()
+    import os
+    assert t.chunks >= 3 and (os.environ.get("CPQ_DITHER_SEGMENTS") == "1" or t.chunks % 3 == 0)   # three segments, at most 32 sequences per chunk
+    assert np.array_equal(d.cpu().numpy(), y) and np.array_equal(d2.cpu().numpy(), y)
+
+
 def test_partition_range_partials_sum_to_full(checker):
     """cfg5 in miniature: the convolver is linear in the IR, so rank partials over partition ranges add up."""
     ir_len, block, T = 131072, 512, 32768
