@@ -751,7 +751,8 @@ cpq_status Engine::setKernelAttributes()
     CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
     CPQ_CUDA(cudaFuncSetAttribute(eq_kernel<true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kEqSmemBytesPost));
     CPQ_CUDA(cudaFuncSetAttribute(mac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem));
-    CPQ_CUDA(cudaFuncSetAttribute(mac_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem));
+    CPQ_CUDA(cudaFuncSetAttribute(mac_tma_kernel<kMacGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem));
+    CPQ_CUDA(cudaFuncSetAttribute(mac_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem));
     CPQ_CUDA(cudaFuncSetAttribute(dither_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kDitherSmemBytes));
     {
         const int g2 = (int) ((kG2Cols * 257 + 256) * sizeof(double2));   // column pass at N1 = 256; N1 = 128 needs 68 KB, N1 = 64 fits the default
@@ -2528,7 +2529,14 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 if (!cfg.shared_ir) a.H += (size_t) (s0 + q0) * a.hSeqStride;   // H rows are absolute sequence indices
                 // enough CTAs to fill the GPU a few times over, each amortising its H tile and ring warm-up over as many frames as possible
                 const int binTiles = l.partSize / kMacBins;
-                const int step = kMacSuper;
+                // blocks of 32 frames (four thread groups) when that leaves less of the last block empty than blocks of 64: short
+                // calls in streaming mode, the dither's time segments
+                const int nqL = qe[li] - qb[li];
+                static const int g4Env = [] { const char* e = getenv("CPQ_MAC_G4"); return e ? atoi(e) : 1; }();   // tuning knob
+                static const int tmaEnv = [] { const char* e = getenv("CPQ_MAC_TMA"); return e ? atoi(e) : 1; }();   // tuning knob
+                const bool useTma = tmaEnv && nqL <= kMacTmaMaxTaps && macTmaSmemBytes(nqL) <= kMaxDynSmem;
+                const bool g4 = useTma && g4Env && nqL - 1 <= 32 && (K[li] + 31) / 32 * 32 < (K[li] + 63) / 64 * 64;
+                const int step = g4 ? 32 : kMacSuper;
                 int fpc = (int) ((K[li] + step - 1) / step) * step;
                 while (fpc > 2 * step && (int64_t) binTiles * n * ((K[li] + fpc - 1) / fpc) < 4 * 148 * 2) fpc = ((fpc / 2 + step - 1) / step) * step;
                 static const int fpcEnv = [] { const char* e = getenv("CPQ_MAC_FPC"); return e ? atoi(e) : 0; }();   // tuning knob
@@ -2546,12 +2554,19 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 dim3 grid((unsigned) binTiles, (unsigned) ((K[li] + fpc - 1) / fpc), (unsigned) n);
                 // tensor-map staging (one TMA copy per 64-frame block, no CTA barrier in the frame loop) for filters of up to
                 // 65 taps; longer ones (uniform-partition extension) keep the row-copy kernel
-                static const int tmaEnv = [] { const char* e = getenv("CPQ_MAC_TMA"); return e ? atoi(e) : 1; }();   // tuning knob
                 MacTensorMap tmX, tmH;
-                if (tmaEnv && a.qEnd - a.qBegin <= kMacTmaMaxTaps && macTmaSmemBytes(a.qEnd - a.qBegin) <= kMaxDynSmem &&
-                    encodeSpectraMap(tmX, a.X, 2 * (uint64_t) l.partSize, (uint64_t) xExtent, (uint64_t) n, (uint32_t) kMacSuper, (uint64_t) xPitch) &&
+                if (useTma &&
+                    encodeSpectraMap(tmX, a.X, 2 * (uint64_t) l.partSize, (uint64_t) xExtent, (uint64_t) n, (uint32_t) step, (uint64_t) xPitch) &&
                     encodeSpectraMap(tmH, layer[li].H.p, 2 * (uint64_t) l.partSize, (uint64_t) l.numPartsIR, (uint64_t) nH, (uint32_t) (a.qEnd - a.qBegin)))
-                    mac_tma_kernel<<<grid, kMacThreads, macTmaSmemBytes(a.qEnd - a.qBegin), stream>>>(a, tmX, tmH);
+                {
+                    if (g4) mac_tma_kernel<4><<<grid, kMacBins * 4, macTmaSmemBytes(a.qEnd - a.qBegin, 4), stream>>>(a, tmX, tmH);
+                    else mac_tma_kernel<kMacGroups><<<grid, kMacThreads, macTmaSmemBytes(a.qEnd - a.qBegin), stream>>>(a, tmX, tmH);
+                }
+                else if (g4)
+                {
+                    setError("process: tensor-map encoding unavailable (driver entry point cuTensorMapEncodeTiled)");
+                    return CPQ_ERR_CUDA;
+                }
                 else
                     mac_kernel<<<grid, kMacThreads, smem, stream>>>(a);
                 ++launches;

@@ -405,7 +405,10 @@ __global__ void __launch_bounds__(kMacThreads, CPQ_MAC_MINBLOCKS) mac_kernel(Mac
 // ---------------------------------------------------------------------------------------------
 constexpr int kMacTmaNB = 3;                       // history | current | prefetch
 constexpr int kMacTmaMaxTaps = kMacSuper + 1;      // nq - 1 <= 64
-inline size_t macTmaSmemBytes(int nq) { return ((size_t) nq * kMacRowBytes + 127) / 128 * 128 + (size_t) kMacTmaNB * kMacSuper * kMacRowBytes + 128; }
+inline size_t macTmaSmemBytes(int nq, int groups = kMacGroups)
+{
+    return ((size_t) nq * kMacRowBytes + 127) / 128 * 128 + (size_t) kMacTmaNB * groups * kMacKT * kMacRowBytes + 128;
+}
 
 __device__ __forceinline__ void tma_load_3d(void* dstSmem, const void* tmap, int c0, int c1, int c2, uint64_t* bar)
 {
@@ -421,12 +424,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 
 struct alignas(64) MacTensorMap { unsigned char bytes[128]; };   // CUtensorMap (opaque here; encoded on the host)
 
-__global__ void __launch_bounds__(kMacThreads, CPQ_MAC_MINBLOCKS)
+// GROUPS thread groups of 32 bins x 8 output frames: 8 (blocks of 64 frames, 256 threads) for whole signals, 4 (blocks of 32
+// frames, 128 threads) for short calls -- streaming calls of a few callbacks and the dither's time segments, where a layer has
+// fewer than 64 frames per call and the 64-frame block would leave half the CTA's warps without work.  Needs nq - 1 <= 8 GROUPS.
+template <int GROUPS>
+__global__ void __launch_bounds__(kMacBins * GROUPS, GROUPS == kMacGroups ? CPQ_MAC_MINBLOCKS : 4)
 mac_tma_kernel(MacArgs a, const __grid_constant__ MacTensorMap tmX, const __grid_constant__ MacTensorMap tmH)
 {
     extern __shared__ __align__(128) unsigned char mac_smem[];
     constexpr int NB = kMacTmaNB;
-    constexpr int R = NB * kMacSuper;
+    constexpr int kSuper = GROUPS * kMacKT;
+    constexpr int R = NB * kSuper;
     const int nq = a.qEnd - a.qBegin;
     const size_t hBytes = ((size_t) nq * kMacRowBytes + 127) / 128 * 128;
     double2* Hs = reinterpret_cast<double2*>(mac_smem);                      // [nq][32]
@@ -452,7 +460,7 @@ mac_tma_kernel(MacArgs a, const __grid_constant__ MacTensorMap tmX, const __grid
         for (int i = 0; i < NB; ++i)
         {
             mbar_init(full + i, 1);
-            mbar_init(empty + i, kMacGroups);
+            mbar_init(empty + i, GROUPS);
         }
         mbar_init(hbar, 1);
     }
@@ -462,8 +470,8 @@ mac_tma_kernel(MacArgs a, const __grid_constant__ MacTensorMap tmX, const __grid
     auto useOf = [&](int j) { return (j - jmin) / NB; };
     auto loadBlock = [&](int j) {
         const int sl = slotOf(j);
-        mbar_arrive_expect_tx(full + sl, (unsigned) kMacSuper * kMacRowBytes);
-        tma_load_3d(ring + (size_t) sl * kMacSuper * kMacBins, &tmX, 2 * m0, base + kMacSuper * j + a.hist, seq, full + sl);
+        mbar_arrive_expect_tx(full + sl, (unsigned) kSuper * kMacRowBytes);
+        tma_load_3d(ring + (size_t) sl * kSuper * kMacBins, &tmX, 2 * m0, base + kSuper * j + a.hist, seq, full + sl);
     };
     if (tid == 0)
     {
@@ -475,12 +483,12 @@ mac_tma_kernel(MacArgs a, const __grid_constant__ MacTensorMap tmX, const __grid
     if (jmin < 0) mbar_wait(full + slotOf(jmin), 0);
 
     // ring row of frame f: (f - base) mod R, with block jmin in slot 0: row = (f - base - 64 jmin) mod R
-    const int rowShift = -kMacSuper * jmin;
+    const int rowShift = -kSuper * jmin;
     const char* ringB = reinterpret_cast<const char*>(ring) + ml * (int) sizeof(double2);
     const char* hsB = reinterpret_cast<const char*>(Hs) + ml * (int) sizeof(double2);
     const bool packedTile = (m0 == 0);
     const bool slot0 = packedTile && ml == 0;
-    const int nSteps = (kc1 - kc0 + kMacSuper - 1) / kMacSuper;
+    const int nSteps = (kc1 - kc0 + kSuper - 1) / kSuper;
     for (int s = 0; s < nSteps; ++s)
     {
         if (tid == 0 && s + 1 < nSteps)
@@ -491,7 +499,7 @@ mac_tma_kernel(MacArgs a, const __grid_constant__ MacTensorMap tmX, const __grid
             loadBlock(j);
         }
         mbar_wait(full + slotOf(s), (unsigned) useOf(s) & 1u);
-        const int ks = kc0 + s * kMacSuper + g * kMacKT;
+        const int ks = kc0 + s * kSuper + g * kMacKT;
         if (ks < kc1)
         {
             double2 acc[kMacKT];

@@ -54,7 +54,7 @@ for alias, real in (("mac_kernel", "mac_tma_kernel"), ("fft_fwd_kernel", "fft_fw
     if alias not in doc and real in doc: doc[alias] = doc[real]   # the names bench.py's stage timers use
 json.dump(doc, open(os.path.join(prof, "traffic.json"), "w"), indent=1)
 for kern, mangled in (("eq_kernel", "_ZN3cpq9eq_kernelILb0ELb0ELb0ELb0EEEvNS_6EqArgsE"), ("mac_kernel", "_ZN3cpq10mac_kernelENS_7MacArgsE"),
-                      ("mac_tma_kernel", "_ZN3cpq14mac_tma_kernelENS_7MacArgsENS_12MacTensorMapES1_")):
+                      ("mac_tma_kernel", "_ZN3cpq14mac_tma_kernelILi8EEEvNS_7MacArgsENS_12MacTensorMapES2_")):
     if kern not in fam: continue
     txt = run(py, os.path.join(root, "scripts", "ncu_stalls.py"), rep, kern, "0", "25")
     txt += "\n# per CUDA source line (needs the libcpq.so of the same build)\n" + run(py, os.path.join(root, "scripts", "ncu_lines.py"), rep, kern, mangled, "30")
