@@ -349,10 +349,35 @@ def other_workloads(local, dev, cfg4_eng, cfg4_x, T4):
         r["workload"] = ("cfg4 with the 24-bit dither branch (PsychoacousticDither, injected uniforms resident on the device).  The shaper is "
                          "one dependent chain of 18 FP64-pipe operations per sample and sequence (11 DFMA, DADD, DMUL, FRND, DMUL, DADD, DSETP, "
                          "FSEL), serial in time by construction and chaotic, so it cannot be scanned or reassociated; dither_stage_alone_ms is "
-                         "that chain over T samples with every sequence running at once (64 warps), and the floor of the stage whatever the "
-                         "batch size.  It starts when a chunk's EQ is done; the transforms fill the register file, so it does not run beside them")
+                         "that chain over T samples with every sequence running at once (64 shaper warps), and the floor of the stage whatever "
+                         "the batch size.  The call runs in up to four time segments through the streaming continuation, the shaper of one "
+                         "segment beside the transforms of the next (CPQ_DITHER_SEGMENTS=1: one piece, the chain trails the call)")
         del u
         return r
+
+    def streaming():
+        """The streaming continuation (cpq_set_streaming) on the cfg4 batch: time per call for calls of 1 / 8 / 64 callbacks."""
+        out = {}
+        cfg4_eng.set_streaming(True)
+        try:
+            stream = torch.cuda.ExternalStream(cfg4_eng.cuda_stream(), device=dev)
+            for ncb in (1, 8, 64):
+                T = ncb * BLOCK
+                cfg4_eng.reset()
+                xs = cfg4_x[:, :T].contiguous()
+                ms = []
+                for _ in range(12 if ncb < 64 else 6):
+                    io = xs.clone()
+                    torch.cuda.synchronize()
+                    ms.append(_timed(stream, lambda: cfg4_eng.process_device(io.data_ptr(), T, T, capi.STAGE_ALL)))
+                med = statistics.median(ms[2:])
+                out[f"{ncb}_callbacks_per_call"] = {"ms_per_call": med, "value": cfg4_x.shape[0] * T / (med * 1e-3),
+                                                    "fraction_of_real_time": med * 1e-3 / (T / SR)}
+        finally:
+            cfg4_eng.set_streaming(False)
+        out["workload"] = ("cfg4's batch (all sequences) processed in consecutive calls of 1 / 8 / 64 host callbacks with the state carried "
+                           "between calls (FDL, input history, delay lines, EQ states), device-resident")
+        return out
 
     guard("cfg1a", lambda: cfg1(False))
     guard("cfg1b_uniform_extension", lambda: cfg1(True))
@@ -361,6 +386,7 @@ def other_workloads(local, dev, cfg4_eng, cfg4_x, T4):
     guard("cfg3_block256", lambda: cfg3(256))
     guard("cfg5_one_gpu", cfg5)
     guard("cfg4_dither24", dither)
+    guard("cfg4_streaming", streaming)
     return res
 
 
