@@ -2166,7 +2166,10 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
         }
         chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) nSeq, cfg.workspace_bytes / std::max<size_t>(perSeq, 1)));
     }
-    if (hostIO) chunk = std::max(1, std::min(chunk, (nSeq + 31) / 32));   // short pipeline fill/drain
+    // host buffers: ~32 chunks so that the copies of one chunk run beside the kernels of another (short pipeline fill / drain) --
+    // for calls large enough for that to matter; a streaming call of a few callbacks is one chunk, one copy each way
+    const size_t callBytes = (size_t) nSeq * (size_t) T * (hostF ? sizeof(float) : sizeof(double));
+    if (hostIO && callBytes >= ((size_t) 64 << 20)) chunk = std::max(1, std::min(chunk, (nSeq + 31) / 32));
     if (segUniTotal > 0)
     {
         // segmented call: every segment uses the first one's chunks, so that a sequence's dither stays on one side stream
@@ -2175,7 +2178,9 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
     }
     // pageable caller rows go through pinned staging slots (HostStager): smaller chunks bound the pinned memory (6 slots)
     static const int stageThreadsEnv = [] { const char* e = getenv("CPQ_STAGE_THREADS"); return e ? atoi(e) : -1; }();   // 0 = let the driver stage
-    const bool pageable = hostPlanar && stageThreadsEnv != 0 && (hostRowIsPageable(hostPlanar[seqLo]) || hostRowIsPageable(hostPlanar[seqLo + nSeq - 1]));
+    // (small calls are left to the driver's own staging: starting the threads would cost more than they save)
+    const bool pageable = hostPlanar && stageThreadsEnv != 0 && callBytes >= ((size_t) 32 << 20) &&
+                          (hostRowIsPageable(hostPlanar[seqLo]) || hostRowIsPageable(hostPlanar[seqLo + nSeq - 1]));
     if (pageable) chunk = std::max(1, std::min(chunk, (nSeq + 63) / 64));
     if (limiterOn) chunk = std::max(cfg.n_channels, chunk / cfg.n_channels * cfg.n_channels);   // whole streams per chunk
     if (doEq && (anyAgc || anyMs))

@@ -1,6 +1,8 @@
 """GPU parity: the CUDA path through the C ABI against the checker (the compiled reference when
 oracle/_ref exists, else the C restatement) on the same seeded inputs.  Tolerance: max abs error
 <= 1e-10 of full scale (BASELINE.json north_star); onset positions sample-exact."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -504,6 +506,36 @@ def test_dither_time_segments_equal_the_one_shot_call(seeded):
     import os
     assert t.chunks >= 3 and (os.environ.get("CPQ_DITHER_SEGMENTS") == "1" or t.chunks % 3 == 0)   # three segments, at most 32 sequences per chunk
     assert np.array_equal(d.cpu().numpy(), y) and np.array_equal(d2.cpu().numpy(), y)
+
+
+def test_pageable_host_buffers_go_through_the_staging_threads():
+    """A pageable caller buffer of more than 32 MB is staged through pinned slots by host threads (HostStager), chunk by chunk;
+    smaller ones are left to the driver.  Same samples either way: the convolver is bit-identical whatever the chunking, so the
+    staged call, the pinned call and the device-resident call must agree exactly -- rows at an irregular pitch included."""
+    import torch
+    sr, block, T, n_streams = 48000.0, 512, 512 * 200, 27      # 54 sequences x 102400 samples = 44 MB
+    n_seq = 2 * n_streams
+    eng = ConvoPeqEngine(n_streams, 2, sr, block, T)
+    for s in range(n_streams):
+        for ch in range(2):
+            eng.set_impulse(s, ch, signals.synth_ir(9000, 30 + (2 * s + ch) % 5), 1.0, None)
+    x = np.stack([signals.noise(T, 40 + i % 9, 0.3) * (1 + i) for i in range(n_seq)])
+    staged = x.copy()
+    eng.process(staged, capi.STAGE_CONV)                     # pageable, above the threshold: staging threads
+    rows = [x[i].copy() for i in range(n_seq)]                # separately allocated rows: no common pitch
+    ptrs = (C.POINTER(C.c_double) * n_seq)(*[r.ctypes.data_as(C.POINTER(C.c_double)) for r in rows])
+    assert eng.lib.cpq_process(eng.h, ptrs, T, capi.STAGE_CONV) == capi.OK
+    pinned = torch.from_numpy(x).pin_memory()
+    eng.process_host_ptrs(pinned.data_ptr(), T, T, capi.STAGE_CONV)
+    dev = torch.from_numpy(x).cuda()
+    eng.process_device(dev.data_ptr(), T, T, capi.STAGE_CONV)
+    small = x[:, :512 * 4].copy()
+    eng.process(small, capi.STAGE_CONV)                      # 1.7 MB: the driver's staging
+    eng.close()
+    want = dev.cpu().numpy()
+    assert np.abs(want).max() > 1e-3
+    assert np.array_equal(staged, want) and np.array_equal(pinned.numpy(), want) and np.array_equal(np.stack(rows), want)
+    assert np.array_equal(small, want[:, :512 * 4])
 
 
 def test_partition_range_partials_sum_to_full(checker):
