@@ -2167,9 +2167,9 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
         chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) nSeq, cfg.workspace_bytes / std::max<size_t>(perSeq, 1)));
     }
     // host buffers: ~32 chunks so that the copies of one chunk run beside the kernels of another (short pipeline fill / drain) --
-    // for calls large enough for that to matter; a streaming call of a few callbacks is one chunk, one copy each way
+    // for calls large enough for that to matter (16 MB); a streaming call of a few callbacks is one chunk, one copy each way
     const size_t callBytes = (size_t) nSeq * (size_t) T * (hostF ? sizeof(float) : sizeof(double));
-    if (hostIO && callBytes >= ((size_t) 64 << 20)) chunk = std::max(1, std::min(chunk, (nSeq + 31) / 32));
+    if (hostIO && callBytes >= ((size_t) 16 << 20)) chunk = std::max(1, std::min(chunk, (nSeq + 31) / 32));
     if (segUniTotal > 0)
     {
         // segmented call: every segment uses the first one's chunks, so that a sequence's dither stays on one side stream
