@@ -1960,9 +1960,10 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
             segUniTotal = T;
             segUniOffset = off;
             st = processCoreImpl(dIo + off, stride, len, stages, nullptr, nullptr, off + len < T);
-            if (st == CPQ_ERR_UNSUPPORTED && off == 0 && !workStarted)
+            if ((st == CPQ_ERR_UNSUPPORTED || st == CPQ_ERR_OOM) && off == 0 && !workStarted)
             {
-                done = false;   // outside what the continuation carries (irregular plans, stream windows ...): nothing was touched
+                cudaGetLastError();
+                done = false;   // outside what the continuation carries (irregular plans, stream windows ...) or no room for its buffers: nothing was touched
                 st = CPQ_OK;
                 break;
             }
@@ -2388,7 +2389,6 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
     // convolver input trim, then the convolver; the final launch then only assembles the layers and runs the output stages
     const bool eqFirst = (stages & CPQ_ORDER_EQ_THEN_CONV) && doConv && doEq;
 
-    workStarted = true;
     if (strm && doConv && !dryOnly && !cont)
     {
         // a stream that starts here starts from Reset, whatever an earlier stream left in the carried buffers
@@ -2402,6 +2402,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             cpq_status st = prepareFdl(li, K[li], cont);
             if (st != CPQ_OK) return st;
         }
+    workStarted = true;   // from here on the caller's buffers are modified
     for (size_t c = 0; c < nChunks; ++c)
     {
         const int s0 = seqLo + (int) c * chunk, ns = std::min(chunk, seqLo + nSeq - s0);

@@ -731,8 +731,9 @@ def test_eq_state_reset_matches_the_reference(checker, kind, structure, n_stream
             # the Parallel structure adds the band differences to the *input*: a non-finite sample stays non-finite there
             fin = np.isfinite(want)
             assert (np.isfinite(got) == fin).all() and (structure == 1 or fin.all()), s
-            # after a 1e200 sample a surviving state sits just below 1e15 and takes ten thousand samples to decay: 1e-8 there
-            assert np.abs(got[fin] - want[fin]).max() <= (1e-8 if kind == "huge" else 1e-9), s
+            # after a 1e200 sample a surviving state sits just below 1e15 and takes ten thousand samples to decay; below 1e9 the
+            # blocked scan takes over again, with an absolute rounding of state x 1e-16: 1e-7 there
+            assert np.abs(got[fin] - want[fin]).max() <= (1e-7 if kind == "huge" else 1e-9), s
         assert np.abs(np.asarray(state[s]).reshape(2, 20, 2) - wst).max() <= 1e-7 * max(1.0, np.abs(wst).max()), s
 
 
