@@ -34,31 +34,72 @@ def nvcc_path() -> str:
     return p
 
 
-def up_to_date() -> bool:
-    if not os.path.exists(LIB):
+def build_knobs() -> list[str]:
+    """-D flags from the environment for the kernels' compile-time tuning knobs (the macros the sources guard with #ifndef
+    CPQ_...); run-time knobs of the same prefix (read with getenv by the library) are not compile flags."""
+    import re
+    known = set()
+    for d in DEPS:
+        with open(d) as f:
+            known.update(re.findall(r"^#ifndef (CPQ_[A-Z0-9_]+)", f.read(), flags=re.M))
+    return [f"-D{k}={v}" for k, v in sorted(os.environ.items()) if k in known and v.isdigit()]
+
+
+def source_hash(extra: list[str]) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for d in sorted(os.path.abspath(x) for x in DEPS):
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS + extra).encode())
+    return h.hexdigest()
+
+
+def up_to_date(extra: list[str] | None = None) -> bool:
+    """libcpq.so exists and was built from exactly these sources and flags (a content hash beside it: file times do not survive
+    every way a tree gets copied, and a stale-looking library must not send eight ranks into nvcc at once)."""
+    if not os.path.exists(LIB) or not os.path.exists(LIB + ".hash"):
         return False
-    t = os.path.getmtime(LIB)
-    return all(os.path.getmtime(d) <= t for d in DEPS)
+    with open(LIB + ".hash") as f:
+        return f.read().strip() == source_hash(build_knobs() if extra is None else extra)
 
 
 def build(force: bool = False, verbose: bool = False, out: str | None = None, defines: dict | None = None) -> str:
-    """Build libcpq.so.  `out` + `defines` build a tuning variant elsewhere (selected at run time with CPQ_LIB)."""
-    if out is None and not force and up_to_date():
+    """Build libcpq.so.  `out` + `defines` build a tuning variant elsewhere (selected at run time with CPQ_LIB).
+    Safe under concurrent callers (one process per GPU importing the package at once): an exclusive lock around the check and
+    the compile, and the library appears under its name only when it is complete."""
+    import fcntl
+    extra = build_knobs()
+    if out is None and not force and up_to_date(extra):
         return LIB
-    extra = [f"-D{k}={v}" for k, v in os.environ.items() if k.startswith("CPQ_") and k.isupper() and v.isdigit()]   # tuning knobs
-    extra += [f"-D{k}={v}" for k, v in (defines or {}).items()]
+    extra_all = extra + [f"-D{k}={v}" for k, v in (defines or {}).items()]
     target = out or LIB
     os.makedirs(os.path.dirname(target), exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", target] + SOURCES
-    out_ = subprocess.run(cmd, capture_output=True, text=True)
-    out = out_
-    log = out.stdout + out.stderr
-    with open(os.path.join(HERE, "build.log") if target == LIB else target + ".log", "w") as f:   # build.log describes libcpq.so only
-        f.write(" ".join(cmd) + "\n" + log)
-    if verbose or out.returncode != 0:
-        print(log[-8000:])
-    if out.returncode != 0:
-        raise RuntimeError("nvcc failed building libcpq.so")
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if out is None and not force and up_to_date(extra):   # another process built it while this one waited
+                return LIB
+            tmp = f"{target}.tmp.{os.getpid()}"
+            cmd = [nvcc_path()] + NVCC_FLAGS + extra_all + ["-o", tmp] + SOURCES
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            log = res.stdout + res.stderr
+            with open(os.path.join(HERE, "build.log") if target == LIB else target + ".log", "w") as f:   # build.log describes libcpq.so only
+                f.write(" ".join(cmd).replace(tmp, target) + "\n" + log)
+            if verbose or res.returncode != 0:
+                print(log[-8000:])
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building libcpq.so")
+            os.replace(tmp, target)
+            if target == LIB:
+                with open(LIB + ".hash.tmp", "w") as f:
+                    f.write(source_hash(extra) + "\n")
+                os.replace(LIB + ".hash.tmp", LIB + ".hash")
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return target
 
 
