@@ -1943,7 +1943,8 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
     const int64_t segLen = nSeg > 1 ? ((T + nSeg - 1) / nSeg + segUnit - 1) / segUnit * segUnit : T;
     bool noEvents = !haveGainTab;
     for (auto& e : eqSets) noEvents = noEvents && e.events.empty();
-    const bool segmented = segLen < T && !streaming && !hostPlanar && !hostF && planSet && noEvents && ditherBits > 0 &&
+    // (segments are whole callbacks and whole EQ tiles: host blocks that do not divide 8192 samples stay in one piece)
+    const bool segmented = segLen < T && segUnit % cfg.block_size == 0 && !streaming && !hostPlanar && !hostF && planSet && noEvents && ditherBits > 0 &&
                            (stages & CPQ_STAGE_CONV) && (stages & CPQ_STAGE_EPILOGUE) && T % cfg.block_size == 0;
     cpq_status st = CPQ_OK;
     bool done = false;

@@ -508,6 +508,28 @@ def test_dither_time_segments_equal_the_one_shot_call(seeded):
     assert np.array_equal(d.cpu().numpy(), y) and np.array_equal(d2.cpu().numpy(), y)
 
 
+def test_dither_with_a_block_that_does_not_divide_the_eq_tile_stays_in_one_piece():
+    """480-sample callbacks: time segments would not be whole callbacks and whole EQ tiles at once, so the device-resident call
+    runs in one piece like the host call -- same bits."""
+    import torch
+    sr, block, T, n_streams = 48000.0, 480, 480 * 300, 3
+    x = np.stack([signals.noise(T, 760 + i, 0.3) for i in range(2 * n_streams)])
+    eng = ConvoPeqEngine(n_streams, 2, sr, block, T)
+    for s in range(n_streams):
+        for ch in range(2):
+            eng.set_impulse(s, ch, signals.synth_ir(20000, 770 + 2 * s + ch), 1.0, capi.default_filter_spec())
+        eng.set_eq(s, signals.to_band(signals.band_params(780 + s)))
+    eng.set_epilogue(0.9, 24)
+    eng.set_dither_seed([11, 12, 13])
+    y = x.copy()
+    eng.process(y, capi.STAGE_ALL)
+    d = torch.from_numpy(x).cuda()
+    eng.process_device(d.data_ptr(), T, T, capi.STAGE_ALL)
+    chunks = eng.timings().chunks
+    eng.close()
+    assert chunks == 1 and np.array_equal(d.cpu().numpy(), y)
+
+
 def test_pageable_host_buffers_go_through_the_staging_threads():
     """A pageable caller buffer of more than 32 MB is staged through pinned slots by host threads (HostStager), chunk by chunk;
     smaller ones are left to the driver.  Same samples either way: the convolver is bit-identical whatever the chunking, so the
