@@ -276,6 +276,7 @@ struct EqSet
     double totalGain = 1.0;
     bool set = false;
     std::vector<GainEvent> events;
+    GainRampState ramp;                      // streaming continuation: the total-gain ramp between calls
     int structure = 0;                       // EQParameters::filterStructure: 0 Serial, 1 Parallel
     int agc = 0;                             // EQParameters::agcEnabled
     uint8_t nodeActive[CPQ_NUM_BANDS];       // BandNode::active, used instead of `active` when the node path runs (Mid/Side)
@@ -1347,8 +1348,10 @@ cpq_status Engine::uploadEq(int64_t nCallbacks)
         setError("Mid/Side bands need a stereo handle (n_channels = 2)");
         return CPQ_ERR_UNSUPPORTED;
     }
+    // streaming continuation: a ramp that a previous call started goes on in this one (and a set whose ramp has settled at a
+    // new gain keeps it: the table then holds that gain for every callback)
     bool anyEvents = false;
-    for (auto& e : eqSets) anyEvents |= !e.events.empty();
+    for (auto& e : eqSets) anyEvents |= !e.events.empty() || (streaming && e.ramp.live);
     if (anyEvents && anyAgc)
     {
         setError("total-gain events and AGC in one handle: with AGC the reference never applies the total-gain ramp (Processing.cpp:1255-1274)");
@@ -1361,13 +1364,14 @@ cpq_status Engine::uploadEq(int64_t nCallbacks)
         const int steps = std::max(1, (int) (cfg.sample_rate * 0.05 + 0.5));   // SMOOTHING_TIME_SEC, computeTotalSteps
         for (size_t s = 0; s < nSets; ++s)
         {
-            gainRampTable(eqSets[s].totalGain, steps, cfg.block_size, nCallbacks, eqSets[s].events, one);
+            gainRampTable(eqSets[s].totalGain, steps, cfg.block_size, nCallbacks, eqSets[s].events, one, streaming ? &eqSets[s].ramp : nullptr);
             std::memcpy(tab.data() + s * (size_t) nCallbacks * 2, one.data(), one.size() * sizeof(double));
+            if (streaming) eqSets[s].events.clear();   // consumed: at_callback counts from the call that follows the scheduling
         }
         CPQ_CUDA(gainTab.ensure(tab.size()));
         CPQ_CUDA(cudaMemcpyAsync(gainTab.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
         CPQ_CUDA(cudaStreamSynchronize(stream));
-        gainTabCallbacks = nCallbacks;
+        gainTabCallbacks = streaming ? -1 : nCallbacks;   // a stream's table is this call's only
     }
     return CPQ_OK;
 }
@@ -1476,7 +1480,11 @@ cpq_status Engine::resetState()
     absCallback = 0;
     contValid = false;
     outerPending = false;
-    for (auto& e : eqSets) e.events.clear();
+    for (auto& e : eqSets)
+    {
+        e.events.clear();
+        e.ramp = GainRampState {};
+    }
     gainTabCallbacks = -1;
     return CPQ_OK;
 }
@@ -1953,6 +1961,7 @@ cpq_status Engine::processCore(double* dIo, int64_t stride, int64_t T, unsigned 
         streaming = true;
         contValid = false;
         absCallback = 0;
+        for (auto& e : eqSets) e.ramp = GainRampState {};
         cpq_timings sum {};
         done = true;
         for (int64_t off = 0; off < T && st == CPQ_OK; off += segLen)
@@ -3093,6 +3102,7 @@ cpq_status cpq_set_eq(cpq_handle h, int stream, const cpq_svf_coeffs coeffs[CPQ_
     e.totalGain = total_gain_lin;
     e.set = true;
     e.events.clear();
+    e.ramp = cpq::GainRampState {};   // the total gain is set, not ramped to
     h->eqDirty = true;
     return CPQ_OK;
 }

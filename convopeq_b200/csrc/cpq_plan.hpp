@@ -1059,12 +1059,27 @@ inline double equalPowerSin(double x)
 // Total-gain LinearRamp evaluated per callback: (start, increment) pairs.
 struct GainEvent { int64_t atCallback; double target; };
 
+// The LinearRamp's state between callbacks (DspNumericPolicy.h:319-421): what a stream carries from one call to the next
+struct GainRampState
+{
+    double current = 1.0, target = 1.0, step = 0.0;
+    int remaining = 0;      // samples the ramp still has to go; 0 = settled at `target`
+    bool live = false;      // false: settled at the parameter set's total gain (no ramp has been started since Reset)
+};
+
 inline void gainRampTable(double initial, int totalSteps, int blockSize, int64_t nCallbacks,
-                          std::vector<GainEvent> events, std::vector<double>& startInc /* [nCallbacks][2] */)
+                          std::vector<GainEvent> events, std::vector<double>& startInc /* [nCallbacks][2] */, GainRampState* carry = nullptr)
 {
     std::stable_sort(events.begin(), events.end(), [](const GainEvent& a, const GainEvent& b) { return a.atCallback < b.atCallback; });
     double current = initial, target = initial, step = 0.0, wanted = initial;
     int remaining = 0;
+    if (carry && carry->live)   // a stream continues: the ramp goes on from where the previous call left it
+    {
+        current = carry->current;
+        target = wanted = carry->target;
+        step = carry->step;
+        remaining = carry->remaining;
+    }
     size_t ev = 0;
     startInc.resize((size_t) nCallbacks * 2);
     for (int64_t c = 0; c < nCallbacks; ++c)
@@ -1085,6 +1100,15 @@ inline void gainRampTable(double initial, int totalSteps, int blockSize, int64_t
         }
         startInc[(size_t) c * 2] = start;
         startInc[(size_t) c * 2 + 1] = (current - start) / (double) blockSize;
+    }
+    if (carry)
+    {
+        // events beyond this call would be lost: the caller schedules relative to the call that follows
+        carry->current = current;
+        carry->target = target;
+        carry->step = step;
+        carry->remaining = remaining;
+        carry->live = true;
     }
 }
 

@@ -161,8 +161,9 @@ cpq_status cpq_reset(cpq_handle h);
  * the stage states.  cpq_reset returns to the Reset state; enable = 0 (default) makes every call start from Reset again.
  * Host blocks that are not a power of two (480, 441 ...) are carried through the reference's layer-0 output ring.
  * Not covered (CPQ_ERR_UNSUPPORTED from the process call): partition
- * ranges / stream windows, plans that drop tail blocks; total-gain events scheduled
- * with cpq_schedule_total_gain must complete their ramp inside the call they start in. */
+ * ranges / stream windows, plans that drop tail blocks.  cpq_schedule_total_gain counts at_callback from the start of the call
+ * that follows it; a ramp still in progress at the end of a call goes on in the next one (it is not part of the exported state:
+ * export once it has settled). */
 cpq_status cpq_set_streaming(cpq_handle h, int enable);
 int64_t cpq_stream_position(cpq_handle h);            /* samples per channel processed since Reset (streaming mode) */
 /* The carried state as one host blob (chaining segments across handles / processes / GPUs): export after any

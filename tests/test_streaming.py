@@ -231,6 +231,37 @@ def test_larger_blocks_and_the_direct_form_head(checker, block, seg, head):
         assert np.abs(two[ch] - want).max() <= TOL and np.abs(want).max() > 1e-3
 
 
+@pytest.mark.parametrize("seg", [1, 3, 16])
+def test_total_gain_ramp_across_calls(checker, seg):
+    """EQProcessor::setTotalGain mid-stream: the 50 ms LinearRamp (4.7 callbacks) starts in one call and goes on in the next ones;
+    at_callback counts from the call that follows the scheduling."""
+    sr, block, n_cb, at = 48000.0, 512, 48, 20
+    T = n_cb * block
+    params = signals.band_params(seed=7)
+    xl, xr = signals.log_sweep(T, sr)
+    x = np.stack([xl, xr])
+    eng = ConvoPeqEngine(1, 2, sr, block, T)
+    eng.set_eq(0, signals.to_band(params), 0.2, 0.0)
+    eng.schedule_total_gain(0, at, -6.0)
+    one = x.copy()
+    eng.process(one, capi.STAGE_EQ)
+    eng.set_eq(0, signals.to_band(params), 0.2, 0.0)       # clears the schedule
+    eng.set_streaming(True)
+    two = np.empty_like(x)
+    for c0 in range(0, n_cb, seg):
+        c1 = min(n_cb, c0 + seg)
+        if c0 <= at < c1:
+            eng.schedule_total_gain(0, at - c0, -6.0)
+        part = np.ascontiguousarray(x[:, c0 * block:c1 * block])
+        eng.process(part, capi.STAGE_EQ)
+        two[:, c0 * block:c1 * block] = part
+    eng.close()
+    wl, wr, _ = checker.eq_run(signals.to_eqband(params), xl, xr, sr, block, gain_change_db=-6.0, gain_change_at=at * block)
+    assert np.abs(one - two).max() <= 1e-12
+    assert np.abs(two[0] - wl).max() <= TOL and np.abs(two[1] - wr).max() <= TOL
+    assert abs(two[0, -1] / one[0, -1] - 1.0) < 1e-9 and np.abs(two[:, (at + 6) * block:]).max() < 0.9 * np.abs(x).max() * 2
+
+
 def test_tile_aligned_segments_are_bit_identical_for_the_whole_chain():
     """Segments of 16 callbacks = 8192 samples = one EQ scan tile: the tile grid of the segmented run coincides with the
     one-shot run's, so every stage gives the same bits."""
