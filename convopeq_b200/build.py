@@ -59,8 +59,11 @@ def source_hash(extra: list[str]) -> str:
 def up_to_date(extra: list[str] | None = None) -> bool:
     """libcpq.so exists and was built from exactly these sources and flags (a content hash beside it: file times do not survive
     every way a tree gets copied, and a stale-looking library must not send eight ranks into nvcc at once)."""
-    if not os.path.exists(LIB) or not os.path.exists(LIB + ".hash"):
+    if not os.path.exists(LIB):
         return False
+    if not os.path.exists(LIB + ".hash"):   # a library without its hash file (copied on its own): fall back on the file times
+        t = os.path.getmtime(LIB)
+        return all(os.path.getmtime(d) <= t for d in DEPS)
     with open(LIB + ".hash") as f:
         return f.read().strip() == source_hash(build_knobs() if extra is None else extra)
 
