@@ -313,7 +313,8 @@ struct Engine
     int nH = 0;
     LayerDev layer[CPQ_MAX_LAYERS];
     GatherPlan gplan;
-    int64_t gplanCallbacks = -1;
+    int64_t gplanCallbacks = -1;        // callbacks the device copies of the gather plan hold (one-shot calls)
+    int64_t gplanHostCallbacks = -1;    // callbacks the host copy covers (streaming calls read their slice from it)
     int partBegin = 0, partEnd = -1;    // partition-range sharding
     bool outerPending = false;
 
@@ -426,6 +427,7 @@ struct Engine
     unsigned postIdentity = 0;          // output-filter stages whose coefficients are the identity (skipped)
     DevBuf<double> postc, postState;
     cpq_status ensureGather(int64_t nCallbacks);
+    cpq_status ensureGatherHost(int64_t nCallbacks);
 
     // ---- streaming continuation (cpq_set_streaming): the state the reference keeps between callbacks, carried between calls.
     // Per sequence: the last 2*Pmax input samples (prevInputBuf / inputAccBuf of every layer, MKLNonUniformConvolver.h:288-365),
@@ -936,6 +938,7 @@ cpq_status Engine::setImpulse(int stream_, int ch, const double* ir, int len, do
         plan = p;
         planSet = true;
         gplanCallbacks = -1;
+        gplanHostCallbacks = -1;
         for (int li = 0; li < plan.numLayers; ++li)
         {
             const LayerPlan& l = plan.layers[li];
@@ -1658,10 +1661,25 @@ cpq_status Engine::importState(const void* src, size_t bytes)
     return CPQ_OK;
 }
 
+// Streaming calls need the plan of callbacks [cb0, cb0 + n) of a stream that may have been running for hours: the integer
+// state machine is run ahead to a horizon and only again when the stream passes it (one pass per 65 536 callbacks, ~12 minutes of
+// audio at block 512), not from callback 0 in every call.
+cpq_status Engine::ensureGatherHost(int64_t nCallbacks)
+{
+    if (gplanHostCallbacks >= nCallbacks) return CPQ_OK;
+    const int64_t horizon = (nCallbacks + 65536 + 65535) / 65536 * 65536;
+    simulateCallbacks(plan, horizon, gplan);
+    gplanHostCallbacks = horizon;
+    gplanCallbacks = -1;   // the device copies (one-shot form) no longer match
+    for (int li = 1; li < plan.numLayers; ++li) layer[li].hasBlockMap = !gplan.blockIdentity[li];
+    return CPQ_OK;
+}
+
 cpq_status Engine::ensureGather(int64_t nCallbacks)
 {
     if (gplanCallbacks == nCallbacks) return CPQ_OK;
     simulateCallbacks(plan, nCallbacks, gplan);
+    gplanHostCallbacks = nCallbacks;
     if (!gplan.l0Identity)
     {
         CPQ_CUDA(layer[0].tailSrc.ensure((size_t) nCallbacks));
@@ -2050,7 +2068,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
                 setError("process: cpq_set_impulse was not called for every stream-channel");
                 return CPQ_ERR_NOT_READY;
             }
-        cpq_status st = ensureGather(cb0 + nCallbacks);
+        cpq_status st = strm ? ensureGatherHost(cb0 + nCallbacks) : ensureGather(nCallbacks);
         if (st != CPQ_OK) return st;
     }
     if (doEq)
@@ -2240,6 +2258,7 @@ cpq_status Engine::processCoreImpl(double* dIo, int64_t stride, int64_t T, unsig
             }
             CPQ_CUDA(layer[li].tailSrc.ensure((size_t) nCallbacks));
             CPQ_CUDA(cudaMemcpyAsync(layer[li].tailSrc.p, rel.data(), (size_t) nCallbacks * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+            if (li == 0) CPQ_CUDA(layer[0].l0Count.ensure((size_t) nCallbacks));
             if (li == 0)
                 CPQ_CUDA(cudaMemcpyAsync(layer[0].l0Count.p, gplan.l0Count.data() + cb0, (size_t) nCallbacks * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
             CPQ_CUDA(cudaStreamSynchronize(stream));   // rel is reused for the next layer
